@@ -1,0 +1,589 @@
+/*
+ * rf_oracle.c — scalar CPU restatement of the RayforceDB columnar hot path.  TEST INFRASTRUCTURE ONLY
+ * (see rf_oracle.h).  Compile: gcc -shared -fPIC -O2 -fsigned-char -fno-fast-math rf_oracle.c -lm
+ *
+ * Parity status: PINNED — checked against golden vectors transcribed from the reference's tests
+ * (tests/golden/reference_kat.json) and differentially against the reference compiled from source
+ * (oracle/_ref/librayforce_ref.so) by tests/test_oracle_pinning.py.
+ *
+ * All citations are paths inside the reference tree (commit 2151d51d).
+ */
+#include "rf_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef int16_t i16;
+typedef int32_t i32;
+typedef int64_t i64;
+typedef uint64_t u64;
+typedef uint8_t u8;
+typedef double f64;
+
+/* ------------------------------------------------------------------ scalar semantics (core/ops.h:63-197) */
+
+/* core/ops.h:63-70: NaN by bit pattern, not by x != x (the reference builds with -funsafe-math-optimizations) */
+static inline int isnan64(f64 x) {
+    u64 u;
+    memcpy(&u, &x, 8);
+    return (u & 0x7FF0000000000000ULL) == 0x7FF0000000000000ULL && (u & 0x000FFFFFFFFFFFFFULL) != 0;
+}
+static inline f64 null_f64(void) {
+    const u64 u = 0x7FF8000000000000ULL; /* a quiet NaN; tests compare NaNs as a class */
+    f64 d;
+    memcpy(&d, &u, 8);
+    return d;
+}
+
+/* wrap-around integer arithmetic: the reference relies on plain C signed ops compiled -O3 */
+static inline i64 wadd64(i64 a, i64 b) { return (i64)((u64)a + (u64)b); }
+static inline i64 wsub64(i64 a, i64 b) { return (i64)((u64)a - (u64)b); }
+static inline i64 wmul64(i64 a, i64 b) { return (i64)((u64)a * (u64)b); }
+static inline i32 wadd32(i32 a, i32 b) { return (i32)((uint32_t)a + (uint32_t)b); }
+static inline i32 wsub32(i32 a, i32 b) { return (i32)((uint32_t)a - (uint32_t)b); }
+static inline i32 wmul32(i32 a, i32 b) { return (i32)((uint32_t)a * (uint32_t)b); }
+
+/* core/ops.h:218-277 widening/narrowing keeps nullness */
+static inline i64 i32_to_i64(i32 x) { return x == RFO_NULL_I32 ? RFO_NULL_I64 : (i64)x; }
+static inline f64 i32_to_f64(i32 x) { return x == RFO_NULL_I32 ? null_f64() : (f64)x; }
+static inline f64 i64_to_f64(i64 x) { return x == RFO_NULL_I64 ? null_f64() : (f64)x; }
+static inline i32 i64_to_i32(i64 x) { return x == RFO_NULL_I64 ? RFO_NULL_I32 : (i32)x; }
+static inline i64 i16_to_i64(i16 x) { return x == RFO_NULL_I16 ? RFO_NULL_I64 : (i64)x; }
+/* f64 -> int: NaN -> null, otherwise C truncation.  Out-of-range casts are UB in C; the x86 cvttsd2si the
+ * reference compiles to yields INT_MIN ("integer indefinite") which is also the null sentinel. */
+static inline i64 f64_to_i64(f64 x) {
+    if (isnan64(x)) return RFO_NULL_I64;
+    if (!(x > -9223372036854775808.0 && x < 9223372036854775808.0)) return RFO_NULL_I64;
+    return (i64)x;
+}
+static inline i32 f64_to_i32(f64 x) {
+    if (isnan64(x)) return RFO_NULL_I32;
+    if (!(x > -2147483649.0 && x < 2147483648.0)) return RFO_NULL_I32;
+    return (i32)x;
+}
+
+/* core/ops.h:165-168: floor division / modulo built on C truncating ops */
+static inline i64 eucl_div64(i64 x, i64 y) {
+    if (y == -1) return (i64)(0 - (u64)x); /* avoids the INT_MIN / -1 trap; same value mod 2^64 */
+    return (x / y) - ((((x < 0) != (y < 0)) && (x % y != 0)) ? 1 : 0);
+}
+static inline i64 eucl_mod64(i64 x, i64 y) { return wsub64(x, wmul64(eucl_div64(x, y), y)); }
+static inline i32 eucl_div32(i32 x, i32 y) {
+    if (y == -1) return (i32)(0 - (uint32_t)x);
+    return (x / y) - ((((x < 0) != (y < 0)) && (x % y != 0)) ? 1 : 0);
+}
+static inline i32 eucl_mod32(i32 x, i32 y) { return wsub32(x, wmul32(eucl_div32(x, y), y)); }
+
+int rfo_type_size(int type) {
+    switch (type) {
+        case RFO_B8: case RFO_U8: return 1;
+        case RFO_I16: return 2;
+        case RFO_I32: case RFO_DATE: case RFO_TIME: return 4;
+        case RFO_I64: case RFO_SYMBOL: case RFO_TIMESTAMP: case RFO_F64: return 8;
+        default: return 0;
+    }
+}
+
+/* storage class of a type code */
+enum { K_NONE = 0, K_U8, K_I16, K_I32, K_I64, K_F64 };
+static int kind_of(int type) {
+    switch (type) {
+        case RFO_B8: case RFO_U8: return K_U8;
+        case RFO_I16: return K_I16;
+        case RFO_I32: case RFO_DATE: case RFO_TIME: return K_I32;
+        case RFO_I64: case RFO_SYMBOL: case RFO_TIMESTAMP: return K_I64;
+        case RFO_F64: return K_F64;
+        default: return K_NONE;
+    }
+}
+
+/* ------------------------------------------------------------------ predicate scan (core/cmp.c) */
+
+/* core/ops.h:74-127.  Integers compare as plain values (a null is just the smallest value, Q4);
+ * doubles order NaN below everything and NaN == NaN. */
+static inline int cmp_i64(int op, i64 a, i64 b) {
+    switch (op) {
+        case RFO_EQ: return a == b; case RFO_NE: return a != b; case RFO_LT: return a < b;
+        case RFO_GT: return a > b;  case RFO_LE: return a <= b; default: return a >= b;
+    }
+}
+static inline int eq_f64(f64 a, f64 b) { return isnan64(a) ? isnan64(b) : isnan64(b) ? 0 : a == b; }
+static inline int lt_f64(f64 a, f64 b) { return isnan64(a) ? !isnan64(b) : isnan64(b) ? 0 : a < b; }
+static inline int gt_f64(f64 a, f64 b) { return isnan64(b) ? !isnan64(a) : isnan64(a) ? 0 : a > b; }
+static inline int cmp_f64(int op, f64 a, f64 b) {
+    switch (op) {
+        case RFO_EQ: return eq_f64(a, b); case RFO_NE: return !eq_f64(a, b); case RFO_LT: return lt_f64(a, b);
+        case RFO_GT: return gt_f64(a, b); case RFO_LE: return !gt_f64(a, b); default: return !lt_f64(a, b);
+    }
+}
+
+/* load element i of a (vector or atom) operand, widened to i64 / f64 with null mapping */
+static inline i64 ld_as_i64(int kind, const void *p, i64 i) {
+    switch (kind) {
+        case K_U8: return (i64)((const u8 *)p)[i];
+        case K_I16: return i16_to_i64(((const i16 *)p)[i]);
+        case K_I32: return i32_to_i64(((const i32 *)p)[i]);
+        default: return ((const i64 *)p)[i];
+    }
+}
+static inline f64 ld_as_f64(int kind, const void *p, i64 i) {
+    switch (kind) {
+        case K_U8: return (f64)((const u8 *)p)[i];
+        case K_I16: { i16 v = ((const i16 *)p)[i]; return v == RFO_NULL_I16 ? null_f64() : (f64)v; }
+        case K_I32: return i32_to_f64(((const i32 *)p)[i]);
+        case K_I64: return i64_to_f64(((const i64 *)p)[i]);
+        default: return ((const f64 *)p)[i];
+    }
+}
+
+/* core/cmp.c:77-332: mixed-width integer operands are promoted (null-preserving) to the wider type, any F64 side
+ * promotes both to F64.  Comparing same-width integers needs no conversion, and widening is monotone with the null
+ * sentinel mapping to the wider null sentinel (still the minimum), so promoting everything to i64 is equivalent. */
+int64_t rfo_cmp(int op, int xt, const void *x, int64_t xn, int yt, const void *y, int64_t yn, uint8_t *out) {
+    int kx = kind_of(xt), ky = kind_of(yt);
+    if (!kx || !ky || op < RFO_EQ || op > RFO_GE) return RFO_ERR_TYPE;
+    if (xn >= 0 && yn >= 0 && xn != yn) return RFO_ERR_LENGTH; /* core/cmp.c:625-627 */
+    i64 n = xn >= 0 ? xn : (yn >= 0 ? yn : 1);
+    int use_f = (kx == K_F64 || ky == K_F64);
+    for (i64 i = 0; i < n; i++) {
+        i64 ix = xn >= 0 ? i : 0, iy = yn >= 0 ? i : 0;
+        out[i] = use_f ? (u8)cmp_f64(op, ld_as_f64(kx, x, ix), ld_as_f64(ky, y, iy))
+                       : (u8)cmp_i64(op, ld_as_i64(kx, x, ix), ld_as_i64(ky, y, iy));
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------ selection vector (core/ops.c:255-273) */
+int64_t rfo_where(const uint8_t *mask, int64_t n, int64_t *ids) {
+    i64 j = 0;
+    for (i64 i = 0; i < n; i++)
+        if (mask[i]) ids[j++] = i;
+    return j;
+}
+
+/* ------------------------------------------------------------------ gather (core/rayforce.c:1036-1098) */
+int rfo_at_ids(int type, const void *col, const int64_t *ids, int64_t m, void *out) {
+    switch (kind_of(type)) {
+        case K_U8: for (i64 i = 0; i < m; i++) ((u8 *)out)[i] = ((const u8 *)col)[ids[i]]; return RFO_OK;
+        case K_I16: for (i64 i = 0; i < m; i++) ((i16 *)out)[i] = ((const i16 *)col)[ids[i]]; return RFO_OK;
+        case K_I32: for (i64 i = 0; i < m; i++) ((i32 *)out)[i] = ((const i32 *)col)[ids[i]]; return RFO_OK;
+        case K_I64: for (i64 i = 0; i < m; i++) ((i64 *)out)[i] = ((const i64 *)col)[ids[i]]; return RFO_OK;
+        case K_F64: for (i64 i = 0; i < m; i++) ((f64 *)out)[i] = ((const f64 *)col)[ids[i]]; return RFO_OK;
+        default: return RFO_ERR_TYPE;
+    }
+}
+
+/* ------------------------------------------------------------------ ungrouped folds (core/math.c:1785-2045) */
+
+/* core/ops.h:183-188: null-skipping min / max */
+static inline i64 min_i64(i64 a, i64 b) { return a == RFO_NULL_I64 ? b : b == RFO_NULL_I64 ? a : (a < b ? a : b); }
+static inline i64 max_i64(i64 a, i64 b) { return a == RFO_NULL_I64 ? b : b == RFO_NULL_I64 ? a : (a > b ? a : b); }
+static inline i32 min_i32(i32 a, i32 b) { return a == RFO_NULL_I32 ? b : b == RFO_NULL_I32 ? a : (a < b ? a : b); }
+static inline i32 max_i32(i32 a, i32 b) { return a == RFO_NULL_I32 ? b : b == RFO_NULL_I32 ? a : (a > b ? a : b); }
+static inline i16 min_i16(i16 a, i16 b) { return a == RFO_NULL_I16 ? b : b == RFO_NULL_I16 ? a : (a < b ? a : b); }
+static inline i16 max_i16(i16 a, i16 b) { return a == RFO_NULL_I16 ? b : b == RFO_NULL_I16 ? a : (a > b ? a : b); }
+static inline f64 min_f64(f64 a, f64 b) { return isnan64(a) ? b : isnan64(b) ? a : (a < b ? a : b); }
+static inline f64 max_f64(f64 a, f64 b) { return isnan64(a) ? b : isnan64(b) ? a : (a > b ? a : b); }
+
+static i64 count_nonnull(int type, const void *x, i64 n) { /* core/math.c:1785-1835, CNT* core/ops.h:148-152 */
+    i64 c = 0;
+    switch (kind_of(type)) {
+        case K_U8: return n;
+        case K_I16: for (i64 i = 0; i < n; i++) c += ((const i16 *)x)[i] != RFO_NULL_I16; return c;
+        case K_I32: for (i64 i = 0; i < n; i++) c += ((const i32 *)x)[i] != RFO_NULL_I32; return c;
+        case K_I64: for (i64 i = 0; i < n; i++) c += ((const i64 *)x)[i] != RFO_NULL_I64; return c;
+        case K_F64: for (i64 i = 0; i < n; i++) c += !isnan64(((const f64 *)x)[i]); return c;
+        default: return -1;
+    }
+}
+
+int rfo_fold(int op, int type, const void *x, int64_t n, void *out, int *out_type) {
+    int k = kind_of(type);
+    memset(out, 0, 8);
+    if (!k) return RFO_ERR_TYPE;
+    switch (op) {
+        case RFO_COUNT: /* (count x) = length, nulls included: core/misc.c:43-85 -> ops_count core/ops.c:169 */
+            *(i64 *)out = n; *out_type = RFO_I64; return RFO_OK;
+        case RFO_CNT: /* non-null count, B8 unsupported: core/math.c:1785-1835 */
+            if (type == RFO_B8 || type == RFO_SYMBOL) return RFO_ERR_TYPE;
+            *(i64 *)out = count_nonnull(type, x, n); *out_type = RFO_I64; return RFO_OK;
+        case RFO_SUM: /* core/math.c:1837-1871: U8,I16 -> i64; I32/TIME stay 32-bit; DATE/TIMESTAMP/B8 -> type error */
+            switch (type) {
+                case RFO_U8: { i64 s = 0; for (i64 i = 0; i < n; i++) s += ((const u8 *)x)[i];
+                               *(i64 *)out = s; *out_type = RFO_I64; return RFO_OK; }
+                case RFO_I16: { i64 s = 0;
+                               for (i64 i = 0; i < n; i++) { i64 v = i16_to_i64(((const i16 *)x)[i]);
+                                                             if (v != RFO_NULL_I64) s = wadd64(s, v); }
+                               *(i64 *)out = s; *out_type = RFO_I64; return RFO_OK; }
+                case RFO_I32: case RFO_TIME: { i32 s = 0;
+                               for (i64 i = 0; i < n; i++) { i32 v = ((const i32 *)x)[i];
+                                                             if (v != RFO_NULL_I32) s = wadd32(s, v); }
+                               *(i32 *)out = s; *out_type = type; return RFO_OK; }
+                case RFO_I64: { i64 s = 0;
+                               for (i64 i = 0; i < n; i++) { i64 v = ((const i64 *)x)[i];
+                                                             if (v != RFO_NULL_I64) s = wadd64(s, v); }
+                               *(i64 *)out = s; *out_type = RFO_I64; return RFO_OK; }
+                case RFO_F64: { f64 s = 0.0;
+                               for (i64 i = 0; i < n; i++) { f64 v = ((const f64 *)x)[i];
+                                                             if (!isnan64(v)) s = s + v; }
+                               *(f64 *)out = s; *out_type = RFO_F64; return RFO_OK; }
+                default: return RFO_ERR_TYPE;
+            }
+        case RFO_MIN: case RFO_MAX: { /* core/math.c:1909-2045: accumulator starts as the typed null */
+            int mn = (op == RFO_MIN);
+            *out_type = type;
+            if (type == RFO_B8 || type == RFO_SYMBOL) return RFO_ERR_TYPE;
+            switch (k) {
+                case K_U8: { const u8 *p = x; u8 a = n > 0 ? p[0] : 0;
+                             for (i64 i = 1; i < n; i++) a = mn ? (a < p[i] ? a : p[i]) : (a > p[i] ? a : p[i]);
+                             *(u8 *)out = a; return RFO_OK; }
+                case K_I16: { const i16 *p = x; i16 a = RFO_NULL_I16;
+                             for (i64 i = 0; i < n; i++) a = mn ? min_i16(a, p[i]) : max_i16(a, p[i]);
+                             *(i16 *)out = a; return RFO_OK; }
+                case K_I32: { const i32 *p = x; i32 a = RFO_NULL_I32;
+                             for (i64 i = 0; i < n; i++) a = mn ? min_i32(a, p[i]) : max_i32(a, p[i]);
+                             *(i32 *)out = a; return RFO_OK; }
+                case K_I64: { const i64 *p = x; i64 a = RFO_NULL_I64;
+                             for (i64 i = 0; i < n; i++) a = mn ? min_i64(a, p[i]) : max_i64(a, p[i]);
+                             *(i64 *)out = a; return RFO_OK; }
+                default: { const f64 *p = x; f64 a = null_f64();
+                             for (i64 i = 0; i < n; i++) a = mn ? min_f64(a, p[i]) : max_f64(a, p[i]);
+                             *(f64 *)out = a; return RFO_OK; }
+            }
+        }
+        case RFO_AVG: { /* core/math.c:2445-2490: sum / non-null count through FDIVI64 / FDIVF64 */
+            u8 tmp[8]; int tt; f64 r;
+            *out_type = RFO_F64;
+            if (!(type == RFO_U8 || type == RFO_I16 || type == RFO_I32 || type == RFO_I64 || type == RFO_F64))
+                return RFO_ERR_TYPE;
+            rfo_fold(RFO_SUM, type, x, n, tmp, &tt);
+            i64 c = (type == RFO_U8) ? n : count_nonnull(type, x, n);
+            if (type == RFO_F64) {
+                f64 s; memcpy(&s, tmp, 8);
+                f64 cf = i64_to_f64(c);
+                r = (cf == 0.0 || isnan64(s) || isnan64(cf)) ? null_f64() : s / cf;
+            } else {
+                i64 s;
+                if (type == RFO_I32) { i32 s32; memcpy(&s32, tmp, 4); s = i32_to_i64(s32); }
+                else memcpy(&s, tmp, 8);
+                r = (c == 0 || s == RFO_NULL_I64 || c == RFO_NULL_I64) ? null_f64() : (f64)s / (f64)c;
+            }
+            *(f64 *)out = r; return RFO_OK;
+        }
+        default: return RFO_ERR_TYPE;
+    }
+}
+
+double rfo_sum_f64_exact(const double *x, int64_t n) {
+    __float128 s = 0;
+    for (i64 i = 0; i < n; i++)
+        if (!isnan64(x[i])) s += (__float128)x[i];
+    return (double)s;
+}
+
+/* ------------------------------------------------------------------ element-wise arithmetic (core/math.c) */
+
+/* For op and operand types (I32/I64/F64) return the computation type `mt` and the result type `ot`, following the
+ * per-case macro arguments in core/math.c:251-1782 and infer_*_type core/math.c:92-223.  0 = unsupported. */
+static int binop_types(int op, int xt, int yt, int *mt, int *ot) {
+    int okx = (xt == RFO_I32 || xt == RFO_I64 || xt == RFO_F64), oky = (yt == RFO_I32 || yt == RFO_I64 || yt == RFO_F64);
+    if (!okx || !oky) return 0;
+    int anyf = (xt == RFO_F64 || yt == RFO_F64), any64 = (xt == RFO_I64 || yt == RFO_I64);
+    int wide = anyf ? RFO_F64 : any64 ? RFO_I64 : RFO_I32; /* usual promotion */
+    switch (op) {
+        case RFO_ADD: case RFO_SUB: case RFO_MUL: *mt = wide; *ot = wide; return 1;
+        case RFO_DIV: /* result keeps the LEFT operand's type (infer_div_type), computed in the promoted type */
+            *mt = wide; *ot = xt; return 1;
+        case RFO_FDIV: *mt = RFO_F64; *ot = RFO_F64; return 1;
+        case RFO_MOD: /* integer % integer takes the RIGHT operand's type; anything with F64 is F64 */
+            *mt = wide; *ot = anyf ? RFO_F64 : yt; return 1;
+        default: return 0;
+    }
+}
+int rfo_binop_type(int op, int xt, int yt) {
+    int mt, ot;
+    return binop_types(op, xt, yt, &mt, &ot) ? ot : RFO_ERR_TYPE;
+}
+
+/* core/ops.h:153-177 — null-propagating scalar ops in each computation type */
+static inline i32 op_i32(int op, i32 x, i32 y) {
+    if (x == RFO_NULL_I32 || y == RFO_NULL_I32) return RFO_NULL_I32;
+    switch (op) {
+        case RFO_ADD: return wadd32(x, y); case RFO_SUB: return wsub32(x, y); case RFO_MUL: return wmul32(x, y);
+        case RFO_DIV: return y == 0 ? RFO_NULL_I32 : eucl_div32(x, y);
+        default: return y == 0 ? RFO_NULL_I32 : eucl_mod32(x, y);
+    }
+}
+static inline i64 op_i64(int op, i64 x, i64 y) {
+    if (x == RFO_NULL_I64 || y == RFO_NULL_I64) return RFO_NULL_I64;
+    switch (op) {
+        case RFO_ADD: return wadd64(x, y); case RFO_SUB: return wsub64(x, y); case RFO_MUL: return wmul64(x, y);
+        case RFO_DIV: return y == 0 ? RFO_NULL_I64 : eucl_div64(x, y);
+        default: return y == 0 ? RFO_NULL_I64 : eucl_mod64(x, y);
+    }
+}
+static inline f64 op_f64(int op, f64 x, f64 y) {
+    if (isnan64(x) || isnan64(y)) return null_f64();
+    switch (op) {
+        case RFO_ADD: return x + y; case RFO_SUB: return x - y; case RFO_MUL: return x * y;
+        case RFO_DIV: return y == 0.0 ? null_f64() : floor(x / y);                  /* DIVF64 / FEUCL_DIV */
+        default: return y == 0.0 ? null_f64() : x - floor(x / y) * y;               /* MODF64 / FEUCL_MOD */
+    }
+}
+/* fdiv: core/math.c:1365-1447.  Left operand I32/I64 uses FDIVI64 *applied to already-converted doubles*
+ * (core/ops.h:173): its null test compares against (double)INT64_MIN; left F64 uses FDIVF64 (core/ops.h:174). */
+static inline f64 op_fdiv(int left_is_int, f64 x, f64 y) {
+    if (left_is_int) {
+        const f64 nul = -9223372036854775808.0;
+        if (y == 0 || x == nul || y == nul) return null_f64();
+        return x / y;
+    }
+    if (y == 0.0 || isnan64(x) || isnan64(y)) return null_f64();
+    return x / y;
+}
+
+int64_t rfo_binop(int op, int xt, const void *x, int64_t xn, int yt, const void *y, int64_t yn, void *out,
+                  int *out_type) {
+    int mt, ot;
+    if (!binop_types(op, xt, yt, &mt, &ot)) return RFO_ERR_TYPE;
+    if (xn >= 0 && yn >= 0 && xn != yn) return RFO_ERR_LENGTH; /* core/math.c:2287-2289 */
+    i64 n = xn >= 0 ? xn : (yn >= 0 ? yn : 1);
+    int kx = kind_of(xt), ky = kind_of(yt);
+    *out_type = ot;
+    for (i64 i = 0; i < n; i++) {
+        i64 ix = xn >= 0 ? i : 0, iy = yn >= 0 ? i : 0;
+        if (op == RFO_FDIV) {
+            ((f64 *)out)[i] = op_fdiv(xt != RFO_F64, ld_as_f64(kx, x, ix), ld_as_f64(ky, y, iy));
+        } else if (mt == RFO_F64) {
+            f64 r = op_f64(op, ld_as_f64(kx, x, ix), ld_as_f64(ky, y, iy));
+            if (ot == RFO_F64) ((f64 *)out)[i] = r;
+            else if (ot == RFO_I64) ((i64 *)out)[i] = f64_to_i64(r);
+            else ((i32 *)out)[i] = f64_to_i32(r);
+        } else if (mt == RFO_I64) {
+            i64 r = op_i64(op, ld_as_i64(kx, x, ix), ld_as_i64(ky, y, iy));
+            if (ot == RFO_I64) ((i64 *)out)[i] = r;
+            else ((i32 *)out)[i] = i64_to_i32(r);
+        } else {
+            ((i32 *)out)[i] = op_i32(op, ((const i32 *)x)[ix], ((const i32 *)y)[iy]);
+        }
+    }
+    return n;
+}
+
+/* core/ops.h:190-192.  The reference computes (i64_t) casts inside doubles; results are doubles. */
+int rfo_unop_f64(int op, const double *x, int64_t n, double *out) {
+    for (i64 i = 0; i < n; i++) {
+        f64 v = x[i], r;
+        if (isnan64(v)) { out[i] = null_f64(); continue; }
+        switch (op) {
+            case RFO_ROUND: r = (f64)(v >= 0.0 ? (i64)(v + 0.5) : (i64)(v - 0.5)); break;
+            case RFO_FLOOR: r = (v < 0.0 && (f64)(i64)v != v) ? (f64)(i64)v - 1.0 : (f64)(i64)v; break;
+            case RFO_CEIL: { f64 w = -v; f64 fl = (w < 0.0 && (f64)(i64)w != w) ? (f64)(i64)w - 1.0 : (f64)(i64)w;
+                             r = -fl; break; }
+            default: return RFO_ERR_TYPE;
+        }
+        out[i] = r;
+    }
+    return RFO_OK;
+}
+
+/* ------------------------------------------------------------------ group index (core/index.c, core/hash.c) */
+
+static u64 fnv1a64(i64 key) { /* core/hash.c:530-542 */
+    u64 h = 14695981039346656037ull;
+    for (int i = 0; i < 8; i++) { h ^= (u8)((u64)key >> (i * 8)); h *= 1099511628211ull; }
+    return h;
+}
+static int is_prime(i64 v) {
+    if (v < 2) return 0;
+    if (v % 2 == 0) return v == 2;
+    for (i64 d = 3; d * d <= v; d += 2) if (v % d == 0) return 0;
+    return 1;
+}
+
+int rfo_group_i64(const int64_t *keys, const int64_t *filter, int64_t len, int64_t *group_ids, int64_t *first_ids,
+                  int64_t *hk, rfo_group_info_t *info) {
+    memset(info, 0, sizeof(*info));
+    if (len == 0) { /* core/index.c:408-409: empty scope, range 0 <= len 0 -> dense path with zero groups */
+        info->min = info->max = RFO_NULL_I64; info->range = 0; info->dense = 1; info->index_type = RFO_INDEX_SHIFT;
+        return RFO_OK;
+    }
+    /* scope: core/index.c:376-435 */
+    i64 mn, mx;
+    mn = mx = filter ? keys[filter[0]] : keys[0];
+    for (i64 i = 0; i < len; i++) { i64 v = filter ? keys[filter[i]] : keys[i]; if (v < mn) mn = v; if (v > mx) mx = v; }
+    info->min = mn; info->max = mx;
+    info->range = (i64)((u64)mx - (u64)mn + 1); /* wraps like the reference's i64 arithmetic (core/index.c:434) */
+    i64 groups = 0;
+    if (info->range <= len && info->range > 0) {
+        /* perfect hash: core/index.c:2013-2055.  (A wrapped negative range is <= len in the reference and would index
+         * out of bounds there; we treat it as sparse — unreachable for the test inputs.) */
+        i64 range = info->range;
+        i64 *slot = hk ? hk : (i64 *)malloc((size_t)range * 8);
+        for (i64 i = 0; i < range; i++) slot[i] = RFO_NULL_I64;
+        for (i64 i = 0; i < len; i++) {
+            i64 s = (filter ? keys[filter[i]] : keys[i]) - mn;
+            if (slot[s] == RFO_NULL_I64) { slot[s] = groups; first_ids[groups] = i; groups++; }
+            group_ids[i] = slot[s];
+        }
+        if (!hk) free(slot);
+        info->dense = 1;
+        info->index_type = range <= RFO_INDEX_SCOPE_LIMIT ? RFO_INDEX_SHIFT : RFO_INDEX_IDS; /* core/index.c:2063 */
+    } else {
+        /* open addressing, linear probing, FNV-1a, prime capacity >= len/0.75, empty marker NULL_I64:
+         * core/hash.c:35-56,129-148; single-chunk path of core/index.c:1800-1835 (first-occurrence numbering).
+         * The reference keeps no first_ids on this path (meta = NULL_OBJ, core/index.c:1975); we record them anyway. */
+        i64 cap = (i64)ceil((f64)len / 0.75);
+        while (!is_prime(cap)) cap++;
+        i64 *tk = (i64 *)malloc((size_t)cap * 8), *tv = (i64 *)malloc((size_t)cap * 8);
+        for (i64 i = 0; i < cap; i++) tk[i] = RFO_NULL_I64;
+        for (i64 i = 0; i < len; i++) {
+            i64 k = filter ? keys[filter[i]] : keys[i];
+            i64 s = (i64)(fnv1a64(k) % (u64)cap);
+            while (tk[s] != RFO_NULL_I64 && tk[s] != k) s = (s + 1) % cap;
+            if (tk[s] == RFO_NULL_I64) { tk[s] = k; tv[s] = groups; first_ids[groups] = i; groups++; }
+            group_ids[i] = tv[s];
+        }
+        free(tk); free(tv);
+        info->dense = 0;
+        info->index_type = RFO_INDEX_IDS;
+    }
+    info->groups = groups;
+    return RFO_OK;
+}
+
+/* ------------------------------------------------------------------ grouped aggregates (core/aggr.c) */
+
+int rfo_aggr(int op, int val_type, const void *val, const int64_t *filter, const int64_t *gid, int64_t len,
+             int64_t groups, void *out, int *out_type) {
+    int k = kind_of(val_type);
+    if (!k) return RFO_ERR_TYPE;
+#define ROW(i) (filter ? filter[i] : (i))
+    switch (op) {
+        case RFO_COUNT: { /* core/aggr.c:1317-1378: rows per group, nulls included */
+            i64 *o = out; *out_type = RFO_I64;
+            if (k == K_U8 || k == K_I16) return RFO_ERR_TYPE;
+            for (i64 g = 0; g < groups; g++) o[g] = 0;
+            for (i64 i = 0; i < len; i++) o[gid[i]]++;
+            return RFO_OK;
+        }
+        case RFO_SUM: /* core/aggr.c:1078-1105: STICKY null (ADD*, not FOLD_ADD*), accumulator in the value type */
+            *out_type = val_type;
+            if (k == K_I64 && val_type == RFO_I64) {
+                i64 *o = out; const i64 *v = val;
+                for (i64 g = 0; g < groups; g++) o[g] = 0;
+                for (i64 i = 0; i < len; i++) { i64 a = o[gid[i]], b = v[ROW(i)];
+                    o[gid[i]] = (a == RFO_NULL_I64 || b == RFO_NULL_I64) ? RFO_NULL_I64 : wadd64(a, b); }
+                return RFO_OK;
+            }
+            if (k == K_I32) {
+                i32 *o = out; const i32 *v = val;
+                for (i64 g = 0; g < groups; g++) o[g] = 0;
+                for (i64 i = 0; i < len; i++) { i32 a = o[gid[i]], b = v[ROW(i)];
+                    o[gid[i]] = (a == RFO_NULL_I32 || b == RFO_NULL_I32) ? RFO_NULL_I32 : wadd32(a, b); }
+                return RFO_OK;
+            }
+            if (k == K_F64) {
+                f64 *o = out; const f64 *v = val;
+                for (i64 g = 0; g < groups; g++) o[g] = 0.0;
+                for (i64 i = 0; i < len; i++) { f64 a = o[gid[i]], b = v[ROW(i)];
+                    o[gid[i]] = (isnan64(a) || isnan64(b)) ? null_f64() : a + b; }
+                return RFO_OK;
+            }
+            return RFO_ERR_TYPE;
+        case RFO_MIN: case RFO_MAX: { /* core/aggr.c:1152-1315: min starts at +INF, max at NULL; I32 unsupported */
+            int mn = (op == RFO_MIN);
+            *out_type = val_type;
+            if (val_type == RFO_I64 || val_type == RFO_TIMESTAMP) {
+                i64 *o = out; const i64 *v = val;
+                for (i64 g = 0; g < groups; g++) o[g] = mn ? RFO_INF_I64 : RFO_NULL_I64;
+                for (i64 i = 0; i < len; i++) { i64 *a = &o[gid[i]]; *a = mn ? min_i64(*a, v[ROW(i)]) : max_i64(*a, v[ROW(i)]); }
+                return RFO_OK;
+            }
+            if (val_type == RFO_DATE || val_type == RFO_TIME) {
+                i32 *o = out; const i32 *v = val;
+                for (i64 g = 0; g < groups; g++) o[g] = mn ? RFO_INF_I32 : RFO_NULL_I32;
+                for (i64 i = 0; i < len; i++) { i32 *a = &o[gid[i]]; *a = mn ? min_i32(*a, v[ROW(i)]) : max_i32(*a, v[ROW(i)]); }
+                return RFO_OK;
+            }
+            if (val_type == RFO_F64) {
+                f64 *o = out; const f64 *v = val;
+                for (i64 g = 0; g < groups; g++) o[g] = mn ? (f64)INFINITY : null_f64();
+                for (i64 i = 0; i < len; i++) { f64 *a = &o[gid[i]]; *a = mn ? min_f64(*a, v[ROW(i)]) : max_f64(*a, v[ROW(i)]); }
+                return RFO_OK;
+            }
+            return RFO_ERR_TYPE;
+        }
+        case RFO_AVG: { /* core/aggr.c:1455-1875, 2013-2060: f64 sum of non-null values / non-null count */
+            f64 *o = out; *out_type = RFO_F64;
+            if (!(val_type == RFO_I32 || val_type == RFO_DATE || val_type == RFO_TIME || val_type == RFO_I64 ||
+                  val_type == RFO_F64)) return RFO_ERR_TYPE;
+            i64 *c = (i64 *)calloc((size_t)(groups > 0 ? groups : 1), 8);
+            for (i64 g = 0; g < groups; g++) o[g] = 0.0;
+            for (i64 i = 0; i < len; i++) {
+                i64 r = ROW(i), g = gid[i];
+                if (k == K_I64) { i64 v = ((const i64 *)val)[r]; if (v != RFO_NULL_I64) { o[g] += (f64)v; c[g]++; } }
+                else if (k == K_I32) { i32 v = ((const i32 *)val)[r]; if (v != RFO_NULL_I32) { o[g] += (f64)v; c[g]++; } }
+                else { f64 v = ((const f64 *)val)[r]; if (!isnan64(v)) { o[g] += v; c[g]++; } }
+            }
+            for (i64 g = 0; g < groups; g++) o[g] = c[g] == 0 ? null_f64() : o[g] / (f64)c[g];
+            free(c);
+            return RFO_OK;
+        }
+        default: return RFO_ERR_TYPE;
+    }
+#undef ROW
+}
+
+/* ------------------------------------------------------------------ key sort (core/sort.c) */
+
+/* order-preserving map to u64: integers flip the sign bit (core/sort.c:313), doubles core/sort.c:266-285 */
+static inline u64 sortable(int kind, const void *x, i64 i) {
+    switch (kind) {
+        case K_U8: return ((const u8 *)x)[i];
+        case K_I16: return (u64)(uint16_t)(((const i16 *)x)[i] ^ (i16)0x8000);
+        case K_I32: return (u64)((uint32_t)((const i32 *)x)[i] ^ 0x80000000u);
+        case K_I64: return (u64)((const i64 *)x)[i] ^ 0x8000000000000000ULL;
+        default: {
+            f64 v = ((const f64 *)x)[i];
+            u64 u;
+            if (isnan64(v)) return 0;
+            memcpy(&u, &v, 8);
+            return (u & 0x8000000000000000ULL) ? ~u : (u | 0x8000000000000000ULL);
+        }
+    }
+}
+
+/* The reference runs 16-bit-digit LSD counting passes; any stable sort by the same key yields the identical
+ * permutation, so the restatement uses a stable bottom-up merge sort on (key, original index). */
+int rfo_sort(int type, const void *x, int64_t n, int descending, int64_t *perm) {
+    int k = kind_of(type);
+    if (!k || type == RFO_SYMBOL) return RFO_ERR_TYPE;
+    if (n == 0) return RFO_OK;
+    u64 *key = (u64 *)malloc((size_t)n * 8);
+    i64 *tmp = (i64 *)malloc((size_t)n * 8);
+    for (i64 i = 0; i < n; i++) { key[i] = sortable(k, x, i); if (descending) key[i] = ~key[i]; perm[i] = i; }
+    i64 *src = perm, *dst = tmp;
+    for (i64 w = 1; w < n; w *= 2) {
+        for (i64 lo = 0; lo < n; lo += 2 * w) {
+            i64 mid = lo + w < n ? lo + w : n, hi = lo + 2 * w < n ? lo + 2 * w : n;
+            i64 a = lo, b = mid, o = lo;
+            while (a < mid && b < hi) dst[o++] = (key[src[b]] < key[src[a]]) ? src[b++] : src[a++];
+            while (a < mid) dst[o++] = src[a++];
+            while (b < hi) dst[o++] = src[b++];
+        }
+        i64 *t = src; src = dst; dst = t;
+    }
+    if (src != perm) memcpy(perm, src, (size_t)n * 8);
+    free(key); free(tmp);
+    return RFO_OK;
+}
+
+/* ------------------------------------------------------------------ synthetic data */
+uint64_t rfo_splitmix64(uint64_t seed, uint64_t i) {
+    u64 z = seed + (i + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
