@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: 1e9-row int64 filter (x < k) + sum per B200 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--rows R] [--impl ours|reference]
+
+A "step" is one pass of the hot path over the GPU's row-range shard of the column:
+    select {s: (sum x) from: t where: (< x k)}        (reference: core/cmp.c -> core/ops.c ops_where ->
+                                                        core/rayforce.c at_ids -> core/math.c ray_sum)
+executed as ONE fused sm_100a kernel (rfb_filter_fold_dev), its 3-number result read back to the host, and for N > 1
+one NCCL all-reduce of the per-GPU (rows, sum) partials.  Prints ONE JSON line (rank 0):
+
+  value      billion rows/s over all GPUs, column resident in HBM when the timed region starts (CUDA events, max over ranks)
+  roofline   the fused kernel alone: algorithmic bytes (8 B/row) / mean CUDA-event duration of the launches inside the
+             timed region, against MEASURED_PEAKS.json hbm_gbs
+  e2e        same metric through the host-pointer C-ABI call (rfb_filter_fold_host): pinned HOST column in, chunked
+             cudaMemcpyAsync + kernels inside the timed region, host result out
+  cpu_baseline  the reference's own CPU implementation (oracle/_ref, compiled from the reference sources) running the same
+             Rayfall select on a bounded sample, all host cores, on rank 0 at N = 1
+
+`--impl reference` times only that CPU arm (rank 0) and prints the same line shape with "impl": "reference".
+Nothing here reads /root/reference at run time.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 42
+MODULUS = 1 << 40          # x[i] = splitmix64(SEED, global_row) mod 2^40
+K_CONST = 1 << 39          # predicate x < 2^39 -> 50 % selectivity
+GOLDEN = 0x9E3779B97F4A7C15
+METRIC = "billion rows/sec on 1e9-row int64 filter+sum"
+UNIT = "Grows/s"
+CPU_SAMPLE_ROWS = 100_000_000
+
+
+def shifted_seed(seed: int, first_row: int) -> int:
+    """splitmix64(seed', i) == splitmix64(seed, first_row + i)"""
+    return (seed + first_row * GOLDEN) & 0xFFFFFFFFFFFFFFFF
+
+
+def splitmix_column(seed: int, first_row: int, n: int, modulus: int) -> np.ndarray:
+    """numpy restatement of the synthetic column (same generator as rfb_fill_splitmix_dev / rfo_splitmix64)"""
+    out = np.empty(n, np.int64)
+    step = 1 << 24
+    with np.errstate(over="ignore"):
+        for lo in range(0, n, step):
+            hi = min(n, lo + step)
+            i = np.arange(first_row + lo + 1, first_row + hi + 1, dtype=np.uint64)
+            z = np.uint64(seed) + i * np.uint64(GOLDEN)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+            out[lo:hi] = (z % np.uint64(modulus)).astype(np.int64)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """samples SM clock + throttle reasons of one GPU while the timed regions run (NVML, ~2 ms period)"""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU reference arm
+
+def cpu_reference_run(steps: int, warmup: int, sample_rows: int = CPU_SAMPLE_ROWS):
+    """Times the reference's own CPU path on a bounded sample: the Rayfall query
+    (select {s: (sum x) from: t where: (< x k)}) through the reference evaluator compiled from its sources
+    (oracle/_ref/librayforce_ref.so, all host cores).  Falls back to the single-threaded C port (oracle/) when the
+    compiled reference is not present.  -> dict(value, seconds_per_step, kind, cores, sample, check)"""
+    from oracle import bindings as ob
+    col = splitmix_column(SEED, 0, sample_rows, MODULUS)
+    expect_sum = int(col[col < K_CONST].sum(dtype=np.int64))
+    times = []
+    if ob.Reference.available():
+        R = ob.Reference.get()
+        o = R.eval("(set x (til %d))" % sample_rows)
+        dst = np.frombuffer((C.c_char * (sample_rows * 8)).from_address(o + 16), dtype=np.int64)
+        dst[:] = col
+        R.eval("(set t (table [x] (list x)))")
+        q = "(select {s: (sum x) from: t where: (< x %d)})" % K_CONST
+        got = None
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            r = R.eval(q)
+            dt = time.perf_counter() - t0
+            cols = R.list_items(R.list_items(r)[1])
+            got = int(R.to_numpy(cols[0], drop=False)[0][0])
+            R.drop(r)
+            if i >= warmup:
+                times.append(dt)
+        kind, cores = "reference", R.cores
+        R.eval("(set t 0)")
+        R.eval("(set x 0)")
+    else:
+        O = ob.Oracle()
+        got = None
+        for i in range(max(1, warmup // 3) + max(1, steps // 3)):
+            t0 = time.perf_counter()
+            m = O.cmp(ob.LT, ob.I64, col, ob.I64, K_CONST)
+            ids = O.where(m)
+            g = O.at_ids(ob.I64, col, ids)
+            got = int(O.fold(ob.SUM, ob.I64, g)[0])
+            dt = time.perf_counter() - t0
+            if i >= max(1, warmup // 3):
+                times.append(dt)
+        kind, cores = "port", 1
+    if got != expect_sum:
+        raise SystemExit("CPU reference arm produced %d, expected %d" % (got, expect_sum))
+    sec = statistics.mean(times)
+    return {"value": sample_rows / sec / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d-row prefix of the same splitmix64 column, Rayfall select through the reference evaluator, "
+                      "mean of %d runs (best %.1f ms)" % (sample_rows, len(times), min(times) * 1e3),
+            "seconds_per_step": sec}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "select {s: (sum x) from: t where: (< x k)}: int64 column, x = splitmix64(42, row) mod 2^40, "
+                        "k = 2^39 (50%% selectivity), %d rows per GPU sharded by row range" % args.rows,
+            "rows_per_gpu": args.rows, "global_rows": args.rows * world, "selectivity": 0.5,
+            "l2_policy": "inputs (8 GB per GPU) far exceed the 126 MB L2; no flush needed",
+            "merge": "none (1 GPU)" if world == 1 else "one NCCL all-reduce of (rows, nonnull, sum) per step"}
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from rayforce_b200 import Context, capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    ctx = Context(local, stream=stream.cuda_stream)
+    n = args.rows
+    K, W = args.steps, args.warmup
+
+    # --- the shard: rows [rank*n, (rank+1)*n) of the global column, generated straight into HBM
+    with torch.cuda.stream(stream):
+        x = torch.empty(n, dtype=torch.int64, device=dev)
+        res = torch.zeros(8, dtype=torch.int64, device=dev)      # rfb_fold_t image for the device-side merge
+    ctx.fill_splitmix(capi.I64, x, n, shifted_seed(SEED, rank * n), MODULUS)
+    ctx.sync()
+
+    def step_resident(ev_s=None, ev_e=None):
+        """one pass, column resident in HBM -> (rows, sum) on the host"""
+        if world == 1:
+            if ev_s is not None:
+                ev_s.record(stream)
+            ctx.filter_fold_async(capi.LT, capi.I64, x, K_CONST, capi.F_SUM | capi.F_CNT, capi.I64, x, n)
+            if ev_e is not None:
+                ev_e.record(stream)
+            r = ctx.fold_result(capi.I64)
+            return r.rows, r.sum
+        ctx.set_result_ptr(res)
+        if ev_s is not None:
+            ev_s.record(stream)
+        ctx.filter_fold_async(capi.LT, capi.I64, x, K_CONST, capi.F_SUM | capi.F_CNT, capi.I64, x, n)
+        if ev_e is not None:
+            ev_e.record(stream)
+        with torch.cuda.stream(stream):
+            dist.all_reduce(res[:3])                              # rows, nonnull, sum_i64 (wraps mod 2^64)
+            h = res[:3].cpu()
+        ctx.set_result_ptr(None)
+        return int(h[0]), int(h[2])
+
+    sampler = ClockSampler(local)
+
+    # --- device-resident timing
+    for _ in range(max(W, 3)):
+        first = step_resident()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctx.launches
+    if rank == 0:
+        sampler.start()
+    t_start.record(stream)
+    for i in range(K):
+        got = step_resident(*evs[i])
+    t_end.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = ctx.launches - launches0
+    total_ms = t_start.elapsed_time(t_end)
+    kernel_ms = statistics.mean(s.elapsed_time(e) for s, e in evs)
+    assert got == first, "non-deterministic result %r vs %r" % (got, first)
+
+    # --- end to end: pinned HOST column in, host result out, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hx_t = torch.empty(n, dtype=torch.int64, pin_memory=True)
+        with torch.cuda.stream(stream):
+            hx_t.copy_(x, non_blocking=True)
+        stream.synchronize()
+        hx = hx_t.numpy()
+        Ke = max(1, min(K, args.e2e_steps))
+
+        def step_e2e():
+            r, nbytes = ctx.filter_fold_host(capi.LT, capi.I64, hx, K_CONST, capi.F_SUM | capi.F_CNT, capi.I64, hx)
+            rows, s = r.rows, r.sum
+            if world > 1:
+                t = torch.tensor([rows, s], dtype=torch.int64).to(dev)
+                dist.all_reduce(t)
+                rows, s = (int(v) for v in t.cpu())
+            return (rows, s), nbytes
+
+        for _ in range(2):
+            ge, nbytes = step_e2e()
+        assert ge == first, "host-layer result %r differs from device-layer result %r" % (ge, first)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        le0 = ctx.launches
+        e0.record(stream)
+        w0 = time.perf_counter()
+        for _ in range(Ke):
+            step_e2e()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
+        e2e_ms = max(e0.elapsed_time(e1), (w1 - w0) * 1e3)       # the copies run on a second stream: take the larger
+        if world > 1:
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        e2e = {"value": n * world * Ke / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
+               "d2h_bytes_per_step": 64 * ((n * 8 + (64 << 20) - 1) // (64 << 20)), "steps": Ke,
+               "ms_per_step": e2e_ms / Ke, "launches_per_step": (ctx.launches - le0) // Ke,
+               "api": "rfb_filter_fold_host (pinned host column -> chunked cudaMemcpyAsync + fused kernel -> host result)"}
+        del hx, hx_t
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, kernel_ms = (float(v) for v in t.cpu())
+
+    if rank == 0:
+        peaks, peak_src = None, "fallback"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+            peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            peak = 6650.0
+        achieved = 8.0 * n / (kernel_ms * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": n * world * K / (total_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
+                "steps": K, "warmup": max(W, 3), "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": workload_config(args, world),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": args.ncu_traffic, "kernel": "k_scan_fold<i64,i64,SUM|CNT,pred,same-column>",
+                             "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": 8 * n, "peak_source": peak_src},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "result": {"rows_selected": int(first[0]), "sum": int(first[1])}}
+        if world == 1 and not args.no_cpu:
+            try:
+                r = cpu_reference_run(steps=3, warmup=1)
+                line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:  # the checker is optional at bench time; say so rather than hide it
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ncu-traffic", type=float, default=None,
+                    help="dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,236 @@
+/*
+ * rfb200.h — C ABI of librfb200.so: the B200 (sm_100a) implementation of RayforceDB's vectorised columnar
+ * execution hot path.  Plain pointers and sizes only; no C++/torch types.  Host side stays pure C.
+ *
+ * Two layers live in this header:
+ *   1. device layer  (rfb_*_dev)  — operands are DEVICE pointers; kernels are enqueued on the context's stream.
+ *                                   This is what a host that keeps columns resident in HBM calls, and what
+ *                                   bench.py times as `value`.
+ *   2. host layer    (rfb_*_host) — operands are HOST pointers (column payloads, i.e. (char*)obj + 16 of a
+ *                                   reference obj_t); the call pins, ships the column to HBM with cudaMemcpyAsync
+ *                                   in a chunked pipeline overlapped with the kernels, and returns host results.
+ *                                   bench.py times this as `e2e`.
+ * The obj_t-level operator surface (ray_lt, ray_where, ray_sum, index_group, aggr_sum, ray_sort_asc, ...) that the
+ * reference's evaluator binds is in rfb200_ops.h and is implemented in pure C on top of this header.
+ *
+ * Element type codes are the reference's (core/rayforce.h:50-62); nulls are its in-band sentinels
+ * (core/rayforce.h:97-100).  Each entry point cites the reference function whose loop it replaces
+ * (paths inside the reference tree, commit 2151d51d).
+ *
+ * Error convention: every function returns RFB_OK (0) or a negative rfb_status; rfb_last_error() gives the text.
+ * RFB_ERR_TYPE / RFB_ERR_LENGTH correspond to the reference's err_type / err_length (core/error.h:86-97) so the
+ * operator layer can raise the same Rayfall errors.  There is NO CPU fallback: without a CUDA device every compute
+ * entry point fails with RFB_ERR_CUDA.
+ */
+#ifndef RFB200_H
+#define RFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFB_ABI_VERSION 1
+
+typedef enum {
+    RFB_OK = 0,
+    RFB_ERR_TYPE = -1,   /* unsupported element type combination (reference: err_type) */
+    RFB_ERR_LENGTH = -2, /* vector lengths differ (reference: err_length) */
+    RFB_ERR_CUDA = -3,   /* CUDA runtime failure, or no device */
+    RFB_ERR_ARG = -4,    /* bad argument (NULL pointer, negative size, unknown op) */
+    RFB_ERR_NOMEM = -5   /* device or pinned allocation failed (reference: err_limit) */
+} rfb_status;
+
+/* element types == reference TYPE_* */
+enum { RFB_B8 = 1, RFB_U8 = 2, RFB_I16 = 3, RFB_I32 = 4, RFB_I64 = 5, RFB_SYMBOL = 6, RFB_DATE = 7, RFB_TIME = 8,
+       RFB_TIMESTAMP = 9, RFB_F64 = 10 };
+
+/* comparison operators: ray_eq/ne/lt/gt/le/ge (core/cmp.c:692-697) */
+enum { RFB_EQ = 0, RFB_NE = 1, RFB_LT = 2, RFB_GT = 3, RFB_LE = 4, RFB_GE = 5 };
+
+/* which folds a reduction kernel computes (bit set).  ray_sum/min/max/cnt (core/math.c:1785-2045) */
+enum { RFB_F_SUM = 1, RFB_F_CNT = 2, RFB_F_MIN = 4, RFB_F_MAX = 8, RFB_F_ALL = 15 };
+
+/* element-wise arithmetic: ray_add/sub/mul/div/fdiv/mod (core/math.c:2436-2441) */
+enum { RFB_ADD = 0, RFB_SUB = 1, RFB_MUL = 2, RFB_DIV = 3, RFB_FDIV = 4, RFB_MOD = 5 };
+enum { RFB_ROUND = 0, RFB_FLOOR = 1, RFB_CEIL = 2 };
+
+/* grouped aggregates: aggr_sum/min/max/count/avg (core/aggr.c:1078-1453, 2013-2133) */
+enum { RFB_A_SUM = 0, RFB_A_MIN = 1, RFB_A_MAX = 2, RFB_A_COUNT = 3, RFB_A_AVG = 4 };
+
+/* group index kinds (core/index.h:31-36) */
+enum { RFB_INDEX_IDS = 0, RFB_INDEX_SHIFT = 1 };
+
+#define RFB_NULL_I16 ((int16_t)0x8000)
+#define RFB_NULL_I32 ((int32_t)0x80000000)
+#define RFB_NULL_I64 ((int64_t)0x8000000000000000LL)
+#define RFB_INF_I64 ((int64_t)0x7FFFFFFFFFFFFFFFLL)
+#define RFB_INDEX_SCOPE_LIMIT (4096 * 128) /* core/index.h:29 */
+
+/* A scalar operand ("atom").  `type` is an element type code; the value sits in the matching member. */
+typedef struct {
+    int32_t type;
+    int32_t _pad;
+    union {
+        int64_t i64;
+        double f64;
+        int32_t i32;
+        int16_t i16;
+        uint8_t u8;
+    } v;
+} rfb_scalar_t;
+
+/* Result of a fold over one column (all requested folds at once).
+ * sum: the null-skipping sum in the reference's accumulator type for the column (core/math.c:1850-1871):
+ *      U8/I16/I64 -> sum_i64 (wraps mod 2^64); I32/TIME -> sum_i64 holds the value wrapped to 32 bits, sign-extended;
+ *      F64 -> sum_f64 (NaN skipped).  rows = elements folded (after the filter); nonnull = non-null among them.
+ * min/max: null-skipping; typed null when nothing was folded (MINI64(NULL,y)=y, core/ops.h:185).
+ *      integers in min_i64/max_i64 (sign-extended), F64 in min_f64/max_f64. */
+typedef struct {
+    int64_t rows;
+    int64_t nonnull;
+    int64_t sum_i64;
+    double sum_f64;
+    int64_t min_i64, max_i64;
+    double min_f64, max_f64;
+} rfb_fold_t;
+
+typedef struct rfb_ctx rfb_ctx_t; /* opaque: device, stream, scratch, pinned staging */
+
+/* ------------------------------------------------------------------ context / memory / transfers */
+int rfb_abi_version(void);
+const char *rfb_last_error(void);               /* thread-local, never NULL */
+int rfb_device_count(void);                     /* 0 without a usable CUDA device; never fails */
+int rfb_ctx_create(int device, rfb_ctx_t **out);
+void rfb_ctx_destroy(rfb_ctx_t *ctx);
+int rfb_ctx_set_stream(rfb_ctx_t *ctx, void *cuda_stream); /* adopt a caller-owned cudaStream_t (NULL = own) */
+void *rfb_ctx_stream(rfb_ctx_t *ctx);
+/* Redirect the rfb_fold_t written by the *_fold_dev kernels to caller-provided device-visible memory (NULL = back to
+ * the context's own mapped pinned slot).  Used when the next consumer is on the device (e.g. an NCCL all-reduce of
+ * per-GPU partial aggregates); calls must then pass out == NULL. */
+int rfb_ctx_set_result_ptr(rfb_ctx_t *ctx, void *device_visible);
+int rfb_ctx_sm_count(rfb_ctx_t *ctx);
+int rfb_sync(rfb_ctx_t *ctx);
+int64_t rfb_launch_count(rfb_ctx_t *ctx);       /* kernels launched through this context so far */
+
+int rfb_dev_alloc(rfb_ctx_t *ctx, size_t bytes, void **dptr);
+int rfb_dev_free(rfb_ctx_t *ctx, void *dptr);
+int rfb_dev_memset(rfb_ctx_t *ctx, void *dptr, int byte, size_t bytes);
+int rfb_host_pin(void *p, size_t bytes);        /* cudaHostRegister: column payload stays where the host put it */
+int rfb_host_unpin(void *p);
+int rfb_host_alloc_pinned(size_t bytes, void **p);
+int rfb_host_free_pinned(void *p);
+/* column shipping: async on the context stream; `pinned` tells whether src/dst is page-locked */
+int rfb_h2d(rfb_ctx_t *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int rfb_d2h(rfb_ctx_t *ctx, void *dst_host, const void *src_dev, size_t bytes);
+
+/* deterministic synthetic columns generated in HBM (bench / tests): x[i] = splitmix64(seed, i) % modulus (+ offset),
+ * every `null_every`-th element (if > 0) replaced by the type's null.  type: I32, I64 or F64 (F64: value / scale). */
+int rfb_fill_splitmix_dev(rfb_ctx_t *ctx, int type, void *x, int64_t n, uint64_t seed, uint64_t modulus,
+                          int64_t offset, int64_t null_every, double f64_scale);
+
+/* ------------------------------------------------------------------ device layer: scan / fold */
+
+/* ray_sum / ray_min / ray_max / ray_cnt over one column (core/math.c:1785-2045; driver unop_fold :2176-2231).
+ * folds: bit set of RFB_F_*.  Result is written to *out (host memory) after the stream is synchronised.
+ * Every *_fold_dev call accepts out == NULL: the kernel is only enqueued and the result is collected later with
+ * rfb_fold_result() (one outstanding fold per context). */
+int rfb_fold_dev(rfb_ctx_t *ctx, int folds, int type, const void *x, int64_t n, rfb_fold_t *out);
+int rfb_fold_result(rfb_ctx_t *ctx, rfb_fold_t *out);
+
+/* Fused `select {(fold v) from t where (cmp p k)}`: predicate scan + selection + gather + fold in ONE pass
+ * (replaces ray_lt -> ray_where -> filter_collect -> ray_sum: core/cmp.c:335, core/ops.c:255,
+ * core/rayforce.c:1100, core/math.c:1874-1890).  pred/val may be the same column (8 B/row) or differ.
+ * The mask, the id vector and the gathered column are never materialised. */
+int rfb_filter_fold_dev(rfb_ctx_t *ctx, int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k, int folds,
+                        int val_type, const void *val, int64_t n, rfb_fold_t *out);
+
+/* Fused `(fold (+ (* a b) c))` over three F64 columns with the reference's NaN propagation (MULF64/ADDF64,
+ * core/ops.h:155,164) and NaN-skipping fold: replaces ray_mul -> ray_add -> ray_sum/ray_cnt. */
+int rfb_fma_fold_dev(rfb_ctx_t *ctx, int folds, const double *a, const double *b, const double *c, int64_t n,
+                     rfb_fold_t *out);
+
+/* ------------------------------------------------------------------ device layer: operator-exact building blocks */
+
+/* ray_eq..ray_ge -> cmp_map (core/cmp.c:335-683): mask[i] = OP(x[i], y[i]) as 0/1 bytes.
+ * xn / yn: element count, or -1 when that side is the atom *xs / *ys.  Returns RFB_ERR_LENGTH if both are vectors
+ * of different length. */
+int rfb_cmp_dev(rfb_ctx_t *ctx, int op, int xt, const void *x, int64_t xn, const rfb_scalar_t *xs, int yt,
+                const void *y, int64_t yn, const rfb_scalar_t *ys, uint8_t *mask);
+
+/* ray_where -> ops_where (core/ops.c:255-273): ascending row ids of the set bytes.  ids must have room for n.
+ * *count (host) receives the number written. */
+int rfb_where_dev(rfb_ctx_t *ctx, const uint8_t *mask, int64_t n, int64_t *ids, int64_t *count);
+
+/* ray_where(ray_<cmp>(x, k)) without the mask: ids of rows where OP(x[i], k) */
+int rfb_cmp_where_dev(rfb_ctx_t *ctx, int op, int type, const void *x, int64_t n, const rfb_scalar_t *k, int64_t *ids,
+                      int64_t *count);
+
+/* filter_collect -> at_ids (core/rayforce.c:1036-1159): out[i] = col[ids[i]] */
+int rfb_gather_dev(rfb_ctx_t *ctx, int type, const void *col, const int64_t *ids, int64_t m, void *out);
+
+/* ray_sum(MAPFILTER[col, ids]) without materialising the gathered column (core/math.c:1874-1890) */
+int rfb_gather_fold_dev(rfb_ctx_t *ctx, int folds, int type, const void *col, const int64_t *ids, int64_t m,
+                        rfb_fold_t *out);
+
+/* ray_add..ray_mod -> binop_map (core/math.c:2280-2345) for I32/I64/F64 operands (vector or atom).
+ * rfb_binop_type answers the result element type (infer_math_type & co, core/math.c:92-223) or RFB_ERR_TYPE. */
+int rfb_binop_type(int op, int xt, int yt);
+int rfb_binop_dev(rfb_ctx_t *ctx, int op, int xt, const void *x, int64_t xn, const rfb_scalar_t *xs, int yt,
+                  const void *y, int64_t yn, const rfb_scalar_t *ys, void *out);
+/* ray_round / ray_floor / ray_ceil -> unop_map (core/math.c:2047-2117, 2233-2278) */
+int rfb_unop_f64_dev(rfb_ctx_t *ctx, int op, const double *x, int64_t n, double *out);
+
+/* ------------------------------------------------------------------ device layer: group-by */
+
+/* index_group -> index_group_i64 (core/index.c:2094-2106): scope (min/max) + first-occurrence group numbering.
+ * keys: I64 column; filter: row ids or NULL; len: number of (filtered) rows.
+ * Outputs (device): group_ids[len] row-position -> gid; first_ids[len] (first `groups` valid) position of each
+ * group's first row.  Dense path when range <= len (perfect hash, core/index.c:2013-2055), else open-addressing
+ * hash (core/index.c:1777-1911).  Both number groups by first occurrence (reference order at -c 1 / dense). */
+typedef struct {
+    int32_t index_type; /* RFB_INDEX_SHIFT if dense and range <= RFB_INDEX_SCOPE_LIMIT else RFB_INDEX_IDS */
+    int32_t dense;
+    int64_t groups;
+    int64_t min, max, range;
+} rfb_group_info_t;
+int rfb_group_i64_dev(rfb_ctx_t *ctx, const int64_t *keys, const int64_t *filter, int64_t len, int64_t *group_ids,
+                      int64_t *first_ids, rfb_group_info_t *info);
+
+/* aggr_sum/min/max/count/avg (core/aggr.c AGGR_ITER :73-161): out[gid] (+)= val[row]; sticky-null sum, +INF-init
+ * min, NULL-init max, row count, f64 avg.  out: `groups` elements of rfb_aggr_type(op, val_type). */
+int rfb_aggr_type(int op, int val_type);
+int rfb_aggr_dev(rfb_ctx_t *ctx, int op, int val_type, const void *val, const int64_t *filter,
+                 const int64_t *group_ids, int64_t len, int64_t groups, void *out);
+
+/* Fused `select {s: (sum v) c: (count v) from t by k [where (cmp p kk)]}` on a dense key domain: one scope pass +
+ * one accumulate pass; never materialises group_ids.  keys: I64 or I32 (I32 is a superset of the reference, Q1).
+ * Outputs (device arrays sized `max_groups`): group keys in first-occurrence order, sums (I64, sticky null), counts.
+ * *groups (host) = number of groups.  pred may be NULL (no filter). */
+int rfb_group_sum_count_dev(rfb_ctx_t *ctx, int key_type, const void *keys, const int64_t *val, int64_t n,
+                            int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k, int64_t max_groups,
+                            int64_t *out_keys, int64_t *out_sums, int64_t *out_counts, int64_t *groups);
+
+/* ------------------------------------------------------------------ device layer: sort */
+
+/* ray_sort_asc / ray_sort_desc (core/sort.c:430-479, 691-740): stable permutation (I64 row ids).
+ * Types: U8/B8, I16, I32/DATE/TIME, I64/TIMESTAMP, F64 (NaN first ascending, -0.0 < +0.0). */
+int rfb_sort_dev(rfb_ctx_t *ctx, int type, const void *x, int64_t n, int descending, int64_t *perm);
+
+/* ------------------------------------------------------------------ host layer (e2e): HOST pointers in, host results out */
+
+/* Same contract as rfb_filter_fold_dev but pred/val are HOST column payloads.  The column is shipped in chunks of
+ * `chunk_rows` (0 = default) through pinned staging (or directly if the caller pinned it with rfb_host_pin), each
+ * chunk's kernel overlapping the next chunk's copy.  h2d_bytes (optional) receives the bytes copied. */
+int rfb_filter_fold_host(rfb_ctx_t *ctx, int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k, int folds,
+                         int val_type, const void *val, int64_t n, int64_t chunk_rows, rfb_fold_t *out,
+                         int64_t *h2d_bytes);
+int rfb_fold_host(rfb_ctx_t *ctx, int folds, int type, const void *x, int64_t n, int64_t chunk_rows, rfb_fold_t *out,
+                  int64_t *h2d_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFB200_H */

@@ -1,0 +1,496 @@
+// k_fold.cu — streaming scan + fold kernels (sm_100a).
+//
+//   rfb_fold_dev          ray_sum / ray_min / ray_max / ray_cnt        (reference core/math.c:1785-2045)
+//   rfb_filter_fold_dev   select {(fold v) from t where (cmp p k)} fused into one pass: replaces
+//                         ray_lt -> ray_where -> filter_collect -> ray_sum (core/cmp.c:335, core/ops.c:255,
+//                         core/rayforce.c:1100, core/math.c:1874-1890)
+//   rfb_fma_fold_dev      (fold (+ (* a b) c)) over three F64 columns
+//   rfb_gather_fold_dev   ray_sum(MAPFILTER[col, ids]) without materialising the gather
+//
+// Shape of every kernel: persistent grid (SM count x resident CTAs), each CTA walks interleaved tiles; every thread
+// issues all of its 128-bit L1-bypassing loads for a tile before consuming them (>= 128 B in flight per thread,
+// ~128 KB per SM) so HBM latency is covered by memory-level parallelism; per-thread accumulators -> warp shuffle
+// tree -> shared-memory tree -> one partial per CTA; the last CTA to finish (atomic ticket) folds the partials in
+// index order and writes the result straight into mapped pinned host memory.  All trees are fixed, so fp64 results
+// are run-to-run deterministic.  HBM roofline: algorithmic bytes = sizeof(elem) per row per distinct column.
+#include "rfb_common.cuh"
+
+namespace {
+
+constexpr int THREADS = 256;
+constexpr int BLOCKS_PER_SM = 4;
+
+enum { FS_SUMCNT = RFB_F_SUM | RFB_F_CNT, FS_MINMAX = RFB_F_MIN | RFB_F_MAX, FS_ALL = RFB_F_ALL };
+
+// predicate = unsigned range test on an order-preserving 64-bit key, optionally negated.
+// All six comparison operators against a constant reduce to it (see make_pred_range).
+struct PredRange {
+    u64 lo, span;
+    u32 negate;
+};
+
+__host__ __device__ __forceinline__ u64 key_of_i64(i64 x) { return (u64)x ^ 0x8000000000000000ULL; }
+// doubles: -0.0 == +0.0 must hold for comparisons (unlike the sort key), NaN is below everything and equals NaN
+__host__ __device__ __forceinline__ u64 key_of_f64(f64 x) { return f64_sort_key(x == 0.0 ? 0.0 : x); }
+
+template <typename P> __device__ __forceinline__ u64 pred_key(P x) {
+    if constexpr (Elem<P>::kind == K_F64) return key_of_f64(x);
+    else return key_of_i64(widen_i64(x));
+}
+
+__device__ __forceinline__ bool pred_test(u64 key, const PredRange &pr) { return ((key - pr.lo) <= pr.span) != (bool)pr.negate; }
+
+struct Partial {
+    i64 rows, nonnull;
+    u64 sum, mn, mx;  // bit patterns of i64 or f64 depending on the value kind
+};
+
+template <typename V, int FOLDS> struct Acc {
+    typedef typename Elem<V>::acc_t A;
+    static constexpr bool FLT = (Elem<V>::kind == K_F64);
+    i64 rows, nonnull;
+    A sum, mn, mx;
+    __device__ __forceinline__ static A min_identity() { if constexpr (FLT) return (A)bits_f64(0x7FF0000000000000ULL); else return (A)RFB_INF_I64; }
+    __device__ __forceinline__ static A max_identity() { if constexpr (FLT) return (A)bits_f64(0xFFF0000000000000ULL); else return (A)NULL_I64; }
+    __device__ __forceinline__ void init() { rows = 0; nonnull = 0; sum = (A)0; mn = min_identity(); mx = max_identity(); }
+    __device__ __forceinline__ static A widen(V v) { if constexpr (FLT) return (A)widen_f64(v); else return (A)widen_i64(v); }
+    // fold one element; `sel` = row passed the predicate.  Nulls are skipped (FOLD_ADD*, MIN*, MAX*, CNT*: core/ops.h)
+    __device__ __forceinline__ void take(V v, bool sel) {
+        const bool ok = sel && !Elem<V>::is_null(v);
+        rows += sel;
+        nonnull += ok;
+        const A w = widen(v);
+        if (FOLDS & RFB_F_SUM) {
+            if (FLT) sum = sum + (ok ? w : (A)0);              // x + 0.0 == x for every non-NaN x that can occur here
+            else sum = (A)((u64)sum + (ok ? (u64)w : 0ULL));   // wraps mod 2^64 like the reference's plain C add
+        }
+        if (FOLDS & RFB_F_MIN) { const A c = ok ? w : min_identity(); mn = c < mn ? c : mn; }
+        if (FOLDS & RFB_F_MAX) { const A c = ok ? w : max_identity(); mx = c > mx ? c : mx; }
+    }
+};
+
+__device__ __forceinline__ u64 to_bits(i64 v) { return (u64)v; }
+__device__ __forceinline__ u64 to_bits(f64 v) { return f64_bits(v); }
+template <typename A> __device__ __forceinline__ A from_bits(u64 b);
+template <> __device__ __forceinline__ i64 from_bits<i64>(u64 b) { return (i64)b; }
+template <> __device__ __forceinline__ f64 from_bits<f64>(u64 b) { return bits_f64(b); }
+
+struct MinPlain { template <typename T> __device__ __forceinline__ T operator()(T a, T b) const { return b < a ? b : a; } };
+struct MaxPlain { template <typename T> __device__ __forceinline__ T operator()(T a, T b) const { return b > a ? b : a; } };
+
+// CTA-level finish shared by all fold kernels: block tree -> partial -> last CTA folds partials -> host result.
+// vkind: element kind of the value column (decides how sum/min/max are reported, rfb200.h rfb_fold_t).
+template <typename A, int FOLDS>
+__device__ __forceinline__ void finish_fold(i64 rows, i64 nonnull, A sum, A mn, A mx, A min_id, A max_id, int vkind,
+                                            Partial *partials, u32 *ticket, rfb_fold_t *out) {
+    constexpr bool FLT = (sizeof(A) == 8) && (A(0.5) != A(0));  // true for f64, false for i64
+    __shared__ u64 red_smem[32];
+    __shared__ bool is_last;
+    rows = block_reduce<i64>(rows, OpAddWrap(), 0, (i64 *)red_smem);
+    nonnull = block_reduce<i64>(nonnull, OpAddWrap(), 0, (i64 *)red_smem);
+    if (FOLDS & RFB_F_SUM) {
+        if (FLT) sum = block_reduce<A>(sum, OpAdd(), (A)0, (A *)red_smem);
+        else sum = (A)block_reduce<i64>((i64)sum, OpAddWrap(), 0, (i64 *)red_smem);
+    }
+    if (FOLDS & RFB_F_MIN) mn = block_reduce<A>(mn, MinPlain(), min_id, (A *)red_smem);
+    if (FOLDS & RFB_F_MAX) mx = block_reduce<A>(mx, MaxPlain(), max_id, (A *)red_smem);
+    if (threadIdx.x == 0) {
+        Partial p;
+        p.rows = rows; p.nonnull = nonnull; p.sum = to_bits(sum); p.mn = to_bits(mn); p.mx = to_bits(mx);
+        partials[blockIdx.x] = p;
+        __threadfence();
+        const u32 t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // last CTA: fixed-order fold of the per-CTA partials
+    i64 r = 0, nn = 0; A s = (A)0, lo = min_id, hi = max_id;
+    for (u32 b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        const Partial p = partials[b];
+        r += p.rows; nn += p.nonnull;
+        if (FOLDS & RFB_F_SUM) { if (FLT) s = s + from_bits<A>(p.sum); else s = (A)((u64)s + p.sum); }
+        if (FOLDS & RFB_F_MIN) { A c = from_bits<A>(p.mn); lo = c < lo ? c : lo; }
+        if (FOLDS & RFB_F_MAX) { A c = from_bits<A>(p.mx); hi = c > hi ? c : hi; }
+    }
+    r = block_reduce<i64>(r, OpAddWrap(), 0, (i64 *)red_smem);
+    nn = block_reduce<i64>(nn, OpAddWrap(), 0, (i64 *)red_smem);
+    if (FOLDS & RFB_F_SUM) {
+        if (FLT) s = block_reduce<A>(s, OpAdd(), (A)0, (A *)red_smem);
+        else s = (A)block_reduce<i64>((i64)s, OpAddWrap(), 0, (i64 *)red_smem);
+    }
+    if (FOLDS & RFB_F_MIN) lo = block_reduce<A>(lo, MinPlain(), min_id, (A *)red_smem);
+    if (FOLDS & RFB_F_MAX) hi = block_reduce<A>(hi, MaxPlain(), max_id, (A *)red_smem);
+    if (threadIdx.x == 0) {
+        rfb_fold_t res;
+        res.rows = r; res.nonnull = nn;
+        res.sum_i64 = 0; res.sum_f64 = 0.0; res.min_i64 = res.max_i64 = 0; res.min_f64 = res.max_f64 = 0.0;
+        if (FLT) {
+            res.sum_f64 = (f64)s;
+            res.min_f64 = nn ? (f64)lo : null_f64();
+            res.max_f64 = nn ? (f64)hi : null_f64();
+        } else {
+            i64 si = (i64)s, nul = NULL_I64;
+            if (vkind == K_I32) { si = (i64)(i32)(u32)(u64)si; nul = (i64)NULL_I32; }  // I32/TIME sums wrap in 32 bits
+            if (vkind == K_I16) nul = (i64)NULL_I16;
+            if (vkind == K_U8) nul = 0;
+            res.sum_i64 = si;
+            res.min_i64 = nn ? (i64)lo : nul;
+            res.max_i64 = nn ? (i64)hi : nul;
+        }
+        *out = res;
+        *ticket = 0;  // re-arm for the next launch on this stream
+        __threadfence_system();
+    }
+}
+
+// ------------------------------------------------------------------ scan + fold over one or two columns
+
+template <typename P, typename V, int FOLDS, bool HAS_PRED, bool SAME>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_scan_fold(const P *__restrict__ pred, PredRange pr, const V *__restrict__ val, i64 n, i64 chunks, int vkind,
+            Partial *partials, u32 *ticket, rfb_fold_t *out) {
+    constexpr bool TWO = HAS_PRED && !SAME;
+    constexpr int SZ_MIN = TWO ? (sizeof(P) < sizeof(V) ? sizeof(P) : sizeof(V)) : sizeof(V);
+    constexpr int RPT = 16 / SZ_MIN;                       // rows per thread-chunk
+    constexpr int NV_V = RPT * (int)sizeof(V) / 16;         // 16-byte loads per chunk, value column
+    constexpr int NV_P = TWO ? RPT * (int)sizeof(P) / 16 : 0;
+    constexpr int UNROLL = (8 / (NV_V + NV_P)) > 0 ? 8 / (NV_V + NV_P) : 1;
+    constexpr int TILE = THREADS * UNROLL;                  // chunks per tile
+
+    Acc<V, FOLDS> acc;
+    acc.init();
+
+    const i64 tiles = (chunks + TILE - 1) / TILE;
+    for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const i64 c0 = tile * TILE + threadIdx.x;
+        Vec16<V> vv[UNROLL][NV_V];
+        Vec16<P> pv[UNROLL][TWO ? NV_P : 1];
+        const bool full = (tile + 1) * (i64)TILE <= chunks;
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) {
+            const i64 c = c0 + (i64)j * THREADS;
+            if (full || c < chunks) {
+                const char *vb = (const char *)val + c * (RPT * sizeof(V));
+#pragma unroll
+                for (int q = 0; q < NV_V; q++) vv[j][q].raw = ld_stream16(vb + 16 * q);
+                if (TWO) {
+                    const char *pb = (const char *)pred + c * (RPT * sizeof(P));
+#pragma unroll
+                    for (int q = 0; q < NV_P; q++) pv[j][q].raw = ld_stream16(pb + 16 * q);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) {
+            const i64 c = c0 + (i64)j * THREADS;
+            if (full || c < chunks) {
+#pragma unroll
+                for (int r = 0; r < RPT; r++) {
+                    const V v = vv[j][r / Vec16<V>::N].e[r % Vec16<V>::N];
+                    bool sel = true;
+                    if (HAS_PRED) {
+                        if (SAME) sel = pred_test(pred_key<P>(*reinterpret_cast<const P *>(&v)), pr);
+                        else sel = pred_test(pred_key<P>(pv[j][r / Vec16<P>::N].e[r % Vec16<P>::N]), pr);
+                    }
+                    acc.take(v, sel);
+                }
+            }
+        }
+    }
+    // rows not covered by whole chunks (and everything, when a pointer is not 16-byte aligned: chunks == 0)
+    for (i64 r = chunks * RPT + (i64)blockIdx.x * THREADS + threadIdx.x; r < n; r += (i64)gridDim.x * THREADS) {
+        const V v = ld_stream(val + r);
+        bool sel = true;
+        if (HAS_PRED) sel = pred_test(pred_key<P>(SAME ? *reinterpret_cast<const P *>(&v) : ld_stream(pred + r)), pr);
+        acc.take(v, sel);
+    }
+    typedef typename Acc<V, FOLDS>::A A;
+    finish_fold<A, FOLDS>(acc.rows, acc.nonnull, acc.sum, acc.mn, acc.mx, Acc<V, FOLDS>::min_identity(),
+                          Acc<V, FOLDS>::max_identity(), vkind, partials, ticket, out);
+}
+
+// ------------------------------------------------------------------ (fold (+ (* a b) c)) over three F64 columns
+
+template <int FOLDS>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_fma_fold(const f64 *__restrict__ a, const f64 *__restrict__ b, const f64 *__restrict__ c, i64 n, i64 chunks,
+           Partial *partials, u32 *ticket, rfb_fold_t *out) {
+    constexpr int UNROLL = 2;  // 3 columns x 2 loads = 6 x 16 B in flight per thread
+    constexpr int TILE = THREADS * UNROLL;
+    Acc<f64, FOLDS> acc;
+    acc.init();
+    // MULF64 then ADDF64 (core/ops.h:155,164): NaN in -> NaN out; the products/sums of non-NaN values are plain IEEE
+    // ops (no fused multiply-add: the reference materialises a*b, rounding it, before adding c).
+    auto eval = [](f64 x, f64 y, f64 z) -> f64 {
+        const f64 m = (isnan64(x) || isnan64(y)) ? null_f64() : __dmul_rn(x, y);
+        return (isnan64(m) || isnan64(z)) ? null_f64() : __dadd_rn(m, z);
+    };
+    const i64 tiles = (chunks + TILE - 1) / TILE;
+    for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        Vec16<f64> va[UNROLL], vb[UNROLL], vc[UNROLL];
+        const i64 c0 = tile * TILE + threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) {
+            const i64 ch = c0 + (i64)j * THREADS;
+            if (ch < chunks) {
+                va[j].raw = ld_stream16(a + 2 * ch);
+                vb[j].raw = ld_stream16(b + 2 * ch);
+                vc[j].raw = ld_stream16(c + 2 * ch);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) {
+            const i64 ch = c0 + (i64)j * THREADS;
+            if (ch < chunks) {
+                acc.take(eval(va[j].e[0], vb[j].e[0], vc[j].e[0]), true);
+                acc.take(eval(va[j].e[1], vb[j].e[1], vc[j].e[1]), true);
+            }
+        }
+    }
+    for (i64 r = chunks * 2 + (i64)blockIdx.x * THREADS + threadIdx.x; r < n; r += (i64)gridDim.x * THREADS)
+        acc.take(eval(ld_stream(a + r), ld_stream(b + r), ld_stream(c + r)), true);
+    finish_fold<f64, FOLDS>(acc.rows, acc.nonnull, acc.sum, acc.mn, acc.mx, Acc<f64, FOLDS>::min_identity(),
+                            Acc<f64, FOLDS>::max_identity(), K_F64, partials, ticket, out);
+}
+
+// ------------------------------------------------------------------ fold through a selection vector (MAPFILTER)
+
+template <typename V, int FOLDS>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_gather_fold(const V *__restrict__ col, const i64 *__restrict__ ids, i64 m, int vkind, Partial *partials, u32 *ticket,
+              rfb_fold_t *out) {
+    Acc<V, FOLDS> acc;
+    acc.init();
+    constexpr int UNROLL = 4;
+    const i64 stride = (i64)gridDim.x * THREADS;
+    i64 i = (i64)blockIdx.x * THREADS + threadIdx.x;
+    for (; i + (UNROLL - 1) * stride < m; i += UNROLL * stride) {
+        i64 id[UNROLL];
+        V v[UNROLL];
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) id[j] = ld_stream(ids + i + j * stride);
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) v[j] = __ldg(col + id[j]);
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) acc.take(v[j], true);
+    }
+    for (; i < m; i += stride) acc.take(__ldg(col + ld_stream(ids + i)), true);
+    typedef typename Acc<V, FOLDS>::A A;
+    finish_fold<A, FOLDS>(acc.rows, acc.nonnull, acc.sum, acc.mn, acc.mx, Acc<V, FOLDS>::min_identity(),
+                          Acc<V, FOLDS>::max_identity(), vkind, partials, ticket, out);
+}
+
+// ------------------------------------------------------------------ host-side dispatch
+
+inline int foldset_of(int folds) {
+    if (!(folds & ~FS_SUMCNT)) return FS_SUMCNT;
+    if (!(folds & ~FS_MINMAX)) return FS_MINMAX;
+    return FS_ALL;
+}
+
+struct Scratch {
+    Partial *partials;
+    u32 *ticket;
+    rfb_fold_t *result;  // mapped pinned host memory
+};
+inline Scratch scratch_of(rfb_ctx_t *ctx) {
+    Scratch s;
+    s.ticket = (u32 *)ctx->d_scratch;
+    s.partials = (Partial *)((char *)ctx->d_scratch + 256);
+    s.result = ctx->result_override ? (rfb_fold_t *)ctx->result_override : (rfb_fold_t *)ctx->h_result + ctx->result_slot;
+    return s;
+}
+
+// scalar -> i64 (null-preserving) or f64
+bool scalar_as_i64(const rfb_scalar_t *k, i64 *out) {
+    switch (rfb_kind_of(k->type)) {
+        case K_U8: *out = k->v.u8; return true;
+        case K_I16: *out = k->v.i16 == NULL_I16 ? NULL_I64 : (i64)k->v.i16; return true;
+        case K_I32: *out = k->v.i32 == NULL_I32 ? NULL_I64 : (i64)k->v.i32; return true;
+        case K_I64: *out = k->v.i64; return true;
+        default: return false;
+    }
+}
+bool scalar_as_f64(const rfb_scalar_t *k, f64 *out) {
+    i64 t;
+    if (rfb_kind_of(k->type) == K_F64) { *out = k->v.f64; return true; }
+    if (!scalar_as_i64(k, &t)) return false;
+    *out = (rfb_kind_of(k->type) != K_U8 && t == NULL_I64) ? null_f64() : (f64)t;
+    return true;
+}
+
+// OP(x, k)  <=>  key(x) in [lo, lo+span] (xor negate)
+PredRange make_pred_range(int op, u64 kk) {
+    PredRange pr;
+    const u64 MAXK = ~0ULL;
+    pr.negate = 0;
+    switch (op) {
+        case RFB_EQ: pr.lo = kk; pr.span = 0; break;
+        case RFB_NE: pr.lo = kk; pr.span = 0; pr.negate = 1; break;
+        case RFB_LE: pr.lo = 0; pr.span = kk; break;
+        case RFB_GE: pr.lo = kk; pr.span = MAXK - kk; break;
+        case RFB_LT: if (kk == 0) { pr.lo = 0; pr.span = MAXK; pr.negate = 1; } else { pr.lo = 0; pr.span = kk - 1; } break;
+        default /*GT*/: if (kk == MAXK) { pr.lo = 0; pr.span = MAXK; pr.negate = 1; } else { pr.lo = kk + 1; pr.span = MAXK - kk - 1; } break;
+    }
+    return pr;
+}
+
+inline bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
+
+template <typename P, typename V, int FOLDS, bool HAS_PRED, bool SAME>
+int launch_scan_fold(rfb_ctx_t *ctx, const void *pred, PredRange pr, const void *val, i64 n, int vkind) {
+    constexpr bool TWO = HAS_PRED && !SAME;
+    constexpr int SZ_MIN = TWO ? (sizeof(P) < sizeof(V) ? sizeof(P) : sizeof(V)) : sizeof(V);
+    constexpr int RPT = 16 / SZ_MIN;
+    const bool vec_ok = aligned16(val) && (!TWO || aligned16(pred));
+    const i64 chunks = vec_ok ? n / RPT : 0;
+    const i64 work = vec_ok ? (chunks + 7) / 8 + 1 : n;  // rough thread-work estimate for sizing small grids
+    const int grid = rfb_grid_for(ctx, work, THREADS, BLOCKS_PER_SM);
+    Scratch s = scratch_of(ctx);
+    k_scan_fold<P, V, FOLDS, HAS_PRED, SAME><<<grid, THREADS, 0, ctx->stream>>>(
+        (const P *)pred, pr, (const V *)val, n, chunks, vkind, s.partials, s.ticket, s.result);
+    RFB_CHECK_LAUNCH(ctx);
+    return RFB_OK;
+}
+
+template <typename P, typename V, bool HAS_PRED, bool SAME>
+int dispatch_foldset(rfb_ctx_t *ctx, int fs, const void *pred, PredRange pr, const void *val, i64 n, int vkind) {
+    switch (fs) {
+        case FS_SUMCNT: return launch_scan_fold<P, V, FS_SUMCNT, HAS_PRED, SAME>(ctx, pred, pr, val, n, vkind);
+        case FS_MINMAX: return launch_scan_fold<P, V, FS_MINMAX, HAS_PRED, SAME>(ctx, pred, pr, val, n, vkind);
+        default: return launch_scan_fold<P, V, FS_ALL, HAS_PRED, SAME>(ctx, pred, pr, val, n, vkind);
+    }
+}
+
+template <typename P>
+int dispatch_val(rfb_ctx_t *ctx, int fs, const void *pred, PredRange pr, int vkind, const void *val, i64 n, bool same) {
+    switch (vkind) {
+        case K_I32:
+            if (same && Elem<P>::kind == K_I32) return dispatch_foldset<i32, i32, true, true>(ctx, fs, pred, pr, val, n, vkind);
+            return dispatch_foldset<P, i32, true, false>(ctx, fs, pred, pr, val, n, vkind);
+        case K_I64:
+            if (same && Elem<P>::kind == K_I64) return dispatch_foldset<i64, i64, true, true>(ctx, fs, pred, pr, val, n, vkind);
+            return dispatch_foldset<P, i64, true, false>(ctx, fs, pred, pr, val, n, vkind);
+        case K_F64:
+            if (same && Elem<P>::kind == K_F64) return dispatch_foldset<f64, f64, true, true>(ctx, fs, pred, pr, val, n, vkind);
+            return dispatch_foldset<P, f64, true, false>(ctx, fs, pred, pr, val, n, vkind);
+        default:
+            rfb_set_error("filter+fold: unsupported value type");
+            return RFB_ERR_TYPE;
+    }
+}
+
+int wait_result(rfb_ctx_t *ctx, rfb_fold_t *out) {
+    if (!out) return RFB_OK;  // asynchronous form: the caller collects with rfb_fold_result()
+    if (ctx->result_override) { rfb_set_error("fold results are redirected (rfb_ctx_set_result_ptr): pass out == NULL"); return RFB_ERR_ARG; }
+    RFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, (rfb_fold_t *)ctx->h_result + ctx->result_slot, sizeof(rfb_fold_t));
+    return RFB_OK;
+}
+
+}  // namespace
+
+// launch only (result lands in ctx->h_result after the stream drains); used by the host-layer pipeline too
+int rfb_fold_launch(rfb_ctx_t *ctx, int folds, int type, const void *x, i64 n) {
+    const int fs = foldset_of(folds), vk = rfb_kind_of(type);
+    PredRange pr = {0, 0, 0};
+    if (type == RFB_B8 || type == RFB_SYMBOL) { rfb_set_error("fold: unsupported type %d", type); return RFB_ERR_TYPE; }
+    switch (vk) {
+        case K_U8: return dispatch_foldset<u8, u8, false, false>(ctx, fs, nullptr, pr, x, n, vk);
+        case K_I16: return dispatch_foldset<i16, i16, false, false>(ctx, fs, nullptr, pr, x, n, vk);
+        case K_I32: return dispatch_foldset<i32, i32, false, false>(ctx, fs, nullptr, pr, x, n, vk);
+        case K_I64: return dispatch_foldset<i64, i64, false, false>(ctx, fs, nullptr, pr, x, n, vk);
+        case K_F64: return dispatch_foldset<f64, f64, false, false>(ctx, fs, nullptr, pr, x, n, vk);
+        default: rfb_set_error("fold: unsupported type %d", type); return RFB_ERR_TYPE;
+    }
+}
+
+int rfb_filter_fold_launch(rfb_ctx_t *ctx, int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k, int folds,
+                           int val_type, const void *val, i64 n) {
+    const int fs = foldset_of(folds), pk = rfb_kind_of(pred_type), vk = rfb_kind_of(val_type);
+    if (cmp_op < RFB_EQ || cmp_op > RFB_GE) { rfb_set_error("bad comparison op %d", cmp_op); return RFB_ERR_ARG; }
+    const bool same = (pred == val) && (pk == vk);
+    if (pk == K_I32 || pk == K_I64) {
+        i64 kv;
+        if (!scalar_as_i64(k, &kv)) { rfb_set_error("filter+fold: integer column vs non-integer constant"); return RFB_ERR_TYPE; }
+        PredRange pr = make_pred_range(cmp_op, key_of_i64(kv));
+        return pk == K_I32 ? dispatch_val<i32>(ctx, fs, pred, pr, vk, val, n, same)
+                           : dispatch_val<i64>(ctx, fs, pred, pr, vk, val, n, same);
+    }
+    if (pk == K_F64) {
+        f64 kv;
+        if (!scalar_as_f64(k, &kv)) { rfb_set_error("filter+fold: bad constant type"); return RFB_ERR_TYPE; }
+        PredRange pr = make_pred_range(cmp_op, key_of_f64(kv));
+        return dispatch_val<f64>(ctx, fs, pred, pr, vk, val, n, same);
+    }
+    rfb_set_error("filter+fold: unsupported predicate column type %d", pred_type);
+    return RFB_ERR_TYPE;
+}
+
+extern "C" int rfb_fold_dev(rfb_ctx_t *ctx, int folds, int type, const void *x, int64_t n, rfb_fold_t *out) {
+    RFB_ARG(ctx && n >= 0 && (x || n == 0), "rfb_fold_dev");
+    int rc = rfb_fold_launch(ctx, folds, type, x, n);
+    if (rc) return rc;
+    return wait_result(ctx, out);
+}
+
+extern "C" int rfb_filter_fold_dev(rfb_ctx_t *ctx, int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k,
+                                   int folds, int val_type, const void *val, int64_t n, rfb_fold_t *out) {
+    RFB_ARG(ctx && k && n >= 0 && ((pred && val) || n == 0), "rfb_filter_fold_dev");
+    int rc = rfb_filter_fold_launch(ctx, cmp_op, pred_type, pred, k, folds, val_type, val, n);
+    if (rc) return rc;
+    return wait_result(ctx, out);
+}
+
+extern "C" int rfb_fma_fold_dev(rfb_ctx_t *ctx, int folds, const double *a, const double *b, const double *c, int64_t n,
+                                rfb_fold_t *out) {
+    RFB_ARG(ctx && n >= 0 && ((a && b && c) || n == 0), "rfb_fma_fold_dev");
+    const bool vec_ok = aligned16(a) && aligned16(b) && aligned16(c);
+    const i64 chunks = vec_ok ? n / 2 : 0;
+    const int grid = rfb_grid_for(ctx, vec_ok ? chunks / 2 + 1 : n, THREADS, BLOCKS_PER_SM);
+    Scratch s = scratch_of(ctx);
+    switch (foldset_of(folds)) {
+        case FS_SUMCNT: k_fma_fold<FS_SUMCNT><<<grid, THREADS, 0, ctx->stream>>>(a, b, c, n, chunks, s.partials, s.ticket, s.result); break;
+        case FS_MINMAX: k_fma_fold<FS_MINMAX><<<grid, THREADS, 0, ctx->stream>>>(a, b, c, n, chunks, s.partials, s.ticket, s.result); break;
+        default: k_fma_fold<FS_ALL><<<grid, THREADS, 0, ctx->stream>>>(a, b, c, n, chunks, s.partials, s.ticket, s.result); break;
+    }
+    RFB_CHECK_LAUNCH(ctx);
+    return wait_result(ctx, out);
+}
+
+template <typename V> static int gather_fold_t(rfb_ctx_t *ctx, int fs, const void *col, const i64 *ids, i64 m, int vk) {
+    const int grid = rfb_grid_for(ctx, m / 4 + 1, THREADS, BLOCKS_PER_SM);
+    Scratch s = scratch_of(ctx);
+    switch (fs) {
+        case FS_SUMCNT: k_gather_fold<V, FS_SUMCNT><<<grid, THREADS, 0, ctx->stream>>>((const V *)col, ids, m, vk, s.partials, s.ticket, s.result); break;
+        case FS_MINMAX: k_gather_fold<V, FS_MINMAX><<<grid, THREADS, 0, ctx->stream>>>((const V *)col, ids, m, vk, s.partials, s.ticket, s.result); break;
+        default: k_gather_fold<V, FS_ALL><<<grid, THREADS, 0, ctx->stream>>>((const V *)col, ids, m, vk, s.partials, s.ticket, s.result); break;
+    }
+    RFB_CHECK_LAUNCH(ctx);
+    return RFB_OK;
+}
+
+extern "C" int rfb_gather_fold_dev(rfb_ctx_t *ctx, int folds, int type, const void *col, const int64_t *ids, int64_t m,
+                                   rfb_fold_t *out) {
+    RFB_ARG(ctx && m >= 0 && ((col && ids) || m == 0), "rfb_gather_fold_dev");
+    const int fs = foldset_of(folds), vk = rfb_kind_of(type);
+    int rc;
+    if (type == RFB_B8 || type == RFB_SYMBOL) { rfb_set_error("fold: unsupported type %d", type); return RFB_ERR_TYPE; }
+    switch (vk) {
+        case K_U8: rc = gather_fold_t<u8>(ctx, fs, col, ids, m, vk); break;
+        case K_I16: rc = gather_fold_t<i16>(ctx, fs, col, ids, m, vk); break;
+        case K_I32: rc = gather_fold_t<i32>(ctx, fs, col, ids, m, vk); break;
+        case K_I64: rc = gather_fold_t<i64>(ctx, fs, col, ids, m, vk); break;
+        case K_F64: rc = gather_fold_t<f64>(ctx, fs, col, ids, m, vk); break;
+        default: rfb_set_error("fold: unsupported type %d", type); return RFB_ERR_TYPE;
+    }
+    if (rc) return rc;
+    return wait_result(ctx, out);
+}
+
+extern "C" int rfb_fold_result(rfb_ctx_t *ctx, rfb_fold_t *out) {
+    RFB_ARG(ctx && out, "rfb_fold_result");
+    return wait_result(ctx, out);
+}
