@@ -48,10 +48,24 @@ def f64_sum_ok(got: float, cpu: float, exact: float) -> bool:
     return abs(got - exact) <= max(ulp(exact), abs(cpu - exact))
 
 
-def same_f64(a, b) -> bool:
-    """bit-equality with all NaNs identified (the reference treats any NaN as the null)"""
+def same_f64(a, b, zero_sign=True, max_ulp=0) -> bool:
+    """bit-equality with all NaNs identified (the reference treats any NaN as the null).
+    zero_sign=False identifies -0.0 with +0.0: the reference is built with -funsafe-math-optimizations (which implies
+    -fno-signed-zeros) and its own goldens print both as "0.0" (tests/lang.c:2551,2565 of the reference).
+    max_ulp=1 is used for float division only: -freciprocal-math lets the reference's compiler turn x / atom into
+    x * (1 / atom), so its quotients are only defined to 1 ULP (golden tests/lang.c:2395: (div [-3.0] -5.0))."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     if a.shape != b.shape:
         return False
     na, nb = np.isnan(a), np.isnan(b)
-    return bool(np.array_equal(na, nb) and np.array_equal(a[~na].view(np.int64), b[~nb].view(np.int64)))
+    if not np.array_equal(na, nb):
+        return False
+    a, b = a[~na], b[~nb]
+    if not zero_sign:
+        a, b = a + 0.0, b + 0.0          # -0.0 + 0.0 == +0.0
+    if max_ulp == 0:
+        return bool(np.array_equal(a.view(np.int64), b.view(np.int64)))
+    fin = np.isfinite(a) & np.isfinite(b)
+    if not np.array_equal(a[~fin], b[~fin]):
+        return False
+    return bool(np.all(np.abs(a[fin] - b[fin]) <= max_ulp * np.spacing(np.abs(b[fin]))))
