@@ -1,0 +1,484 @@
+// k_map.cu — element-wise column kernels (sm_100a): one output element per row, no cross-row dependence.
+//
+//   rfb_cmp_dev       ray_eq/ne/lt/gt/le/ge -> cmp_map                 (reference core/cmp.c:35-68 loops, :335-683 driver)
+//   rfb_binop_dev     ray_add/sub/mul/div/fdiv/mod -> binop_map        (core/math.c:55-90 loops, :251-1782 matrix, :2280-2345)
+//   rfb_unop_f64_dev  ray_round/floor/ceil -> unop_map                 (core/math.c:2047-2117, core/ops.h:190-192)
+//
+// All three are pure HBM streams (cmp: 8+8 B in, 1 B out per row; binop: 8+8 in, 8 out).  Shape: each thread owns
+// "lanes" of R = 16 / sizeof(widest operand) consecutive rows; lane j of thread t in a tile covers rows
+// (tile*TILE + j*THREADS + t)*R .. +R, so every load instruction of a warp touches one contiguous 512-byte span (and the
+// narrower operand a contiguous 512/k span).  All loads of a tile are issued before the first use (UNROLL vectors in
+// flight per operand per thread) and bypass L1 allocation.  Grid = SM count x resident CTAs, grid-stride over tiles.
+#include "rfb_common.cuh"
+
+namespace {
+
+constexpr int THREADS = 256;
+constexpr int BLOCKS_PER_SM = 4;
+
+template <int BYTES> struct RawVec;
+template <> struct RawVec<16> { typedef vec16 type; };
+template <> struct RawVec<8> { typedef u64 type; };
+template <> struct RawVec<4> { typedef u32 type; };
+template <> struct RawVec<2> { typedef unsigned short type; };
+template <> struct RawVec<1> { typedef u8 type; };
+
+// R consecutive elements of T moved with one load/store of R*sizeof(T) bytes
+template <typename T, int R> union Pack {
+    typename RawVec<R * (int)sizeof(T)>::type raw;
+    T e[R];
+    __device__ __forceinline__ Pack() {}
+};
+template <typename T, int R> __device__ __forceinline__ void ld_pack(Pack<T, R> &p, const T *src) {
+    if constexpr (R * sizeof(T) == 16) p.raw = ld_stream16(src);
+    else p.raw = __ldcs(reinterpret_cast<const typename RawVec<R * (int)sizeof(T)>::type *>(src));
+}
+template <typename T, int R> __device__ __forceinline__ void st_pack(T *dst, const Pack<T, R> &p) {
+    if constexpr (R * sizeof(T) == 16) st_stream16(dst, p.raw);
+    else __stcs(reinterpret_cast<typename RawVec<R * (int)sizeof(T)>::type *>(dst), p.raw);
+}
+
+template <int A, int B> struct MaxI { static constexpr int v = A > B ? A : B; };
+template <bool C, typename A, typename B> struct Sel { typedef A type; };
+template <typename A, typename B> struct Sel<false, A, B> { typedef B type; };
+
+// Generic two-input map.  F: out = f(x, y).  XA / YA: that side is an atom (broadcast), passed by value.
+template <typename X, typename Y, typename O, bool XA, bool YA, typename F>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_map2(const X *__restrict__ x, X xa, const Y *__restrict__ y, Y ya, O *__restrict__ out, i64 n, bool vec_ok, F f) {
+    constexpr int WX = XA ? 1 : (int)sizeof(X), WY = YA ? 1 : (int)sizeof(Y);
+    constexpr int R = 16 / MaxI<MaxI<WX, WY>::v, (int)sizeof(O)>::v;   // rows per lane
+    constexpr int UNROLL = 4;
+    constexpr i64 TILE = (i64)THREADS * UNROLL * R;                     // rows per tile
+    const i64 nvec = vec_ok ? (n / TILE) * TILE : 0;
+    for (i64 base = (i64)blockIdx.x * TILE; base < nvec; base += (i64)gridDim.x * TILE) {
+        typedef typename Sel<XA, u8, X>::type XV;  // an atom side needs no registers: its pack degenerates to bytes
+        typedef typename Sel<YA, u8, Y>::type YV;
+        Pack<XV, R> px[UNROLL];
+        Pack<YV, R> py[UNROLL];
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) {
+            const i64 r = base + ((i64)j * THREADS + threadIdx.x) * R;
+            if constexpr (!XA) ld_pack<X, R>(px[j], x + r);
+            if constexpr (!YA) ld_pack<Y, R>(py[j], y + r);
+        }
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) {
+            const i64 r = base + ((i64)j * THREADS + threadIdx.x) * R;
+            Pack<O, R> po;
+#pragma unroll
+            for (int e = 0; e < R; e++) {
+                X a; Y b;
+                if constexpr (XA) a = xa; else a = px[j].e[e];
+                if constexpr (YA) b = ya; else b = py[j].e[e];
+                po.e[e] = f(a, b);
+            }
+            st_pack<O, R>(out + r, po);
+        }
+    }
+    // tail (and everything when a pointer is not 16-byte aligned)
+    for (i64 r = nvec + (i64)blockIdx.x * THREADS + threadIdx.x; r < n; r += (i64)gridDim.x * THREADS)
+        out[r] = f(XA ? xa : ld_stream(x + r), YA ? ya : ld_stream(y + r));
+}
+
+template <typename X, typename O, typename F>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_map1(const X *__restrict__ x, O *__restrict__ out, i64 n, bool vec_ok, F f) {
+    constexpr int R = 16 / MaxI<(int)sizeof(X), (int)sizeof(O)>::v;
+    constexpr int UNROLL = 8;
+    constexpr i64 TILE = (i64)THREADS * UNROLL * R;
+    const i64 nvec = vec_ok ? (n / TILE) * TILE : 0;
+    for (i64 base = (i64)blockIdx.x * TILE; base < nvec; base += (i64)gridDim.x * TILE) {
+        Pack<X, R> px[UNROLL];
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) ld_pack<X, R>(px[j], x + base + ((i64)j * THREADS + threadIdx.x) * R);
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) {
+            Pack<O, R> po;
+#pragma unroll
+            for (int e = 0; e < R; e++) po.e[e] = f(px[j].e[e]);
+            st_pack<O, R>(out + base + ((i64)j * THREADS + threadIdx.x) * R, po);
+        }
+    }
+    for (i64 r = nvec + (i64)blockIdx.x * THREADS + threadIdx.x; r < n; r += (i64)gridDim.x * THREADS) out[r] = f(ld_stream(x + r));
+}
+
+inline bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
+
+template <typename X, typename Y, typename O, bool XA, bool YA, typename F>
+int launch_map2(rfb_ctx_t *ctx, const void *x, X xa, const void *y, Y ya, void *out, i64 n, F f) {
+    if (n == 0) return RFB_OK;
+    const bool vec_ok = (XA || aligned16(x)) && (YA || aligned16(y)) && aligned16(out);
+    const int grid = rfb_grid_for(ctx, n, THREADS * 8, BLOCKS_PER_SM);
+    k_map2<X, Y, O, XA, YA, F><<<grid, THREADS, 0, ctx->stream>>>((const X *)x, xa, (const Y *)y, ya, (O *)out, n, vec_ok, f);
+    RFB_CHECK_LAUNCH(ctx);
+    return RFB_OK;
+}
+
+// ------------------------------------------------------------------ comparisons
+
+// order-preserving u64 keys: integers compare as plain values (null = smallest); doubles put NaN below
+// everything, NaN == NaN and -0.0 == +0.0 (core/ops.h:74-127)
+__host__ __device__ __forceinline__ u64 ckey_i64(i64 v) { return (u64)v ^ 0x8000000000000000ULL; }
+__host__ __device__ __forceinline__ u64 ckey_f64(f64 v) { return f64_sort_key(v == 0.0 ? 0.0 : v); }
+
+template <bool FLT, typename T> __device__ __forceinline__ u64 ckey(T v) {
+    if constexpr (FLT || Elem<T>::kind == K_F64) return ckey_f64(widen_f64(v));
+    else return ckey_i64(widen_i64(v));
+}
+
+// 3-bit truth table indexed by sign(a - b) + 1: bit0 a<b, bit1 a==b, bit2 a>b
+inline u32 cmp_lut(int op) {
+    switch (op) {
+        case RFB_EQ: return 0b010; case RFB_NE: return 0b101; case RFB_LT: return 0b001;
+        case RFB_GT: return 0b100; case RFB_LE: return 0b011; default: return 0b110;
+    }
+}
+inline int mirror_op(int op) {  // x OP y  <=>  y OP' x
+    switch (op) { case RFB_LT: return RFB_GT; case RFB_GT: return RFB_LT; case RFB_LE: return RFB_GE; case RFB_GE: return RFB_LE; default: return op; }
+}
+
+template <bool FLT, typename X, typename Y> struct CmpVV {
+    u32 lut;
+    __device__ __forceinline__ u8 operator()(X a, Y b) const {
+        const u64 ka = ckey<FLT>(a), kb = ckey<FLT>(b);
+        const int idx = (ka > kb) - (ka < kb) + 1;
+        return (u8)((lut >> idx) & 1u);
+    }
+};
+// vector vs atom: the atom is already a key
+template <bool FLT, typename X> struct CmpVA {
+    u32 lut;
+    u64 kb;
+    __device__ __forceinline__ u8 operator()(X a, u8) const {
+        const u64 ka = ckey<FLT>(a);
+        const int idx = (ka > kb) - (ka < kb) + 1;
+        return (u8)((lut >> idx) & 1u);
+    }
+};
+
+template <bool FLT, typename X>
+int cmp_va(rfb_ctx_t *ctx, int op, const void *x, i64 n, u64 kb, u8 *mask) {
+    CmpVA<FLT, X> f{cmp_lut(op), kb};
+    return launch_map2<X, u8, u8, false, true>(ctx, x, X(), nullptr, (u8)0, mask, n, f);
+}
+template <typename X>
+int cmp_va_x(rfb_ctx_t *ctx, int op, bool flt, const void *x, i64 n, u64 kb, u8 *mask) {
+    return flt ? cmp_va<true, X>(ctx, op, x, n, kb, mask) : cmp_va<false, X>(ctx, op, x, n, kb, mask);
+}
+
+template <typename X, typename Y>
+int cmp_vv(rfb_ctx_t *ctx, int op, const void *x, const void *y, i64 n, u8 *mask) {
+    constexpr bool FLT = Elem<X>::kind == K_F64 || Elem<Y>::kind == K_F64;
+    CmpVV<FLT, X, Y> f{cmp_lut(op)};
+    return launch_map2<X, Y, u8, false, false>(ctx, x, X(), y, Y(), mask, n, f);
+}
+template <typename X>
+int cmp_vv_y(rfb_ctx_t *ctx, int op, const void *x, int ky, const void *y, i64 n, u8 *mask) {
+    switch (ky) {
+        case K_U8: return cmp_vv<X, u8>(ctx, op, x, y, n, mask);
+        case K_I16: return cmp_vv<X, i16>(ctx, op, x, y, n, mask);
+        case K_I32: return cmp_vv<X, i32>(ctx, op, x, y, n, mask);
+        case K_I64: return cmp_vv<X, i64>(ctx, op, x, y, n, mask);
+        default: return cmp_vv<X, f64>(ctx, op, x, y, n, mask);
+    }
+}
+
+// scalar -> widened value (host)
+bool scalar_i64(const rfb_scalar_t *s, i64 *out) {
+    switch (rfb_kind_of(s->type)) {
+        case K_U8: *out = s->v.u8; return true;
+        case K_I16: *out = s->v.i16 == NULL_I16 ? NULL_I64 : (i64)s->v.i16; return true;
+        case K_I32: *out = s->v.i32 == NULL_I32 ? NULL_I64 : (i64)s->v.i32; return true;
+        case K_I64: *out = s->v.i64; return true;
+        default: return false;
+    }
+}
+bool scalar_f64(const rfb_scalar_t *s, f64 *out) {
+    if (rfb_kind_of(s->type) == K_F64) { *out = s->v.f64; return true; }
+    i64 t;
+    if (!scalar_i64(s, &t)) return false;
+    *out = (rfb_kind_of(s->type) != K_U8 && t == NULL_I64) ? null_f64() : (f64)t;
+    return true;
+}
+
+// temporal types only compare with themselves (the reference converts DATE<->TIMESTAMP units, which this layer does
+// not model); plain numeric kinds mix freely
+bool cmp_types_ok(int xt, int yt) {
+    auto plain = [](int t) { return t == RFB_B8 || t == RFB_U8 || t == RFB_I16 || t == RFB_I32 || t == RFB_I64 || t == RFB_F64; };
+    if (!rfb_kind_of(xt) || !rfb_kind_of(yt)) return false;
+    return (plain(xt) && plain(yt)) || xt == yt;
+}
+
+}  // namespace
+
+extern "C" int rfb_cmp_dev(rfb_ctx_t *ctx, int op, int xt, const void *x, int64_t xn, const rfb_scalar_t *xs, int yt,
+                           const void *y, int64_t yn, const rfb_scalar_t *ys, uint8_t *mask) {
+    RFB_ARG(ctx && op >= RFB_EQ && op <= RFB_GE, "rfb_cmp_dev: op");
+    RFB_ARG((xn >= 0 ? (x || xn == 0) : xs != nullptr) && (yn >= 0 ? (y || yn == 0) : ys != nullptr), "rfb_cmp_dev: operands");
+    if (!cmp_types_ok(xt, yt)) { rfb_set_error("cmp: unsupported operand types %d, %d", xt, yt); return RFB_ERR_TYPE; }
+    if (xn >= 0 && yn >= 0 && xn != yn) { rfb_set_error("cmp: vector lengths differ (%lld vs %lld)", (long long)xn, (long long)yn); return RFB_ERR_LENGTH; }
+    const int kx = rfb_kind_of(xt), ky = rfb_kind_of(yt);
+    const bool flt = (kx == K_F64 || ky == K_F64);
+    if (xn < 0 && yn < 0) {  // atom vs atom: one byte, computed by the same kernel on a 1-element broadcast
+        RFB_ARG(mask, "rfb_cmp_dev: mask");
+        rfb_set_error("cmp: both operands are atoms; the operator layer folds constants on the host");
+        return RFB_ERR_ARG;
+    }
+    if (xn >= 0 && yn >= 0) {
+        RFB_ARG(mask || xn == 0, "rfb_cmp_dev: mask");
+        switch (kx) {
+            case K_U8: return cmp_vv_y<u8>(ctx, op, x, ky, y, xn, mask);
+            case K_I16: return cmp_vv_y<i16>(ctx, op, x, ky, y, xn, mask);
+            case K_I32: return cmp_vv_y<i32>(ctx, op, x, ky, y, xn, mask);
+            case K_I64: return cmp_vv_y<i64>(ctx, op, x, ky, y, xn, mask);
+            default: return cmp_vv_y<f64>(ctx, op, x, ky, y, xn, mask);
+        }
+    }
+    // vector vs atom (atom on the left: mirror the operator)
+    const bool atom_left = xn < 0;
+    const void *v = atom_left ? y : x;
+    const i64 n = atom_left ? yn : xn;
+    const int kv = atom_left ? ky : kx;
+    const rfb_scalar_t *s = atom_left ? xs : ys;
+    const int vop = atom_left ? mirror_op(op) : op;
+    RFB_ARG(mask || n == 0, "rfb_cmp_dev: mask");
+    u64 kb;
+    if (flt) { f64 d; if (!scalar_f64(s, &d)) return RFB_ERR_TYPE; kb = ckey_f64(d); }
+    else { i64 d; if (!scalar_i64(s, &d)) return RFB_ERR_TYPE; kb = ckey_i64(d); }
+    switch (kv) {
+        case K_U8: return cmp_va_x<u8>(ctx, vop, flt, v, n, kb, mask);
+        case K_I16: return cmp_va_x<i16>(ctx, vop, flt, v, n, kb, mask);
+        case K_I32: return cmp_va_x<i32>(ctx, vop, flt, v, n, kb, mask);
+        case K_I64: return cmp_va_x<i64>(ctx, vop, flt, v, n, kb, mask);
+        default: return cmp_va_x<f64>(ctx, vop, flt, v, n, kb, mask);
+    }
+}
+
+// ------------------------------------------------------------------ arithmetic
+
+namespace {
+
+// null-propagating scalar ops in each computation type (core/ops.h:153-177)
+__device__ __forceinline__ i64 eucl_div64(i64 x, i64 y) {
+    if (y == -1) return (i64)(0 - (u64)x);
+    const i64 q = x / y, r = x - q * y;
+    return q - ((((x < 0) != (y < 0)) && r != 0) ? 1 : 0);
+}
+__device__ __forceinline__ i32 eucl_div32(i32 x, i32 y) {
+    if (y == -1) return (i32)(0 - (u32)x);
+    const i32 q = x / y, r = x - q * y;
+    return q - ((((x < 0) != (y < 0)) && r != 0) ? 1 : 0);
+}
+__device__ __forceinline__ i32 op_i32(int op, i32 x, i32 y) {
+    if (x == NULL_I32 || y == NULL_I32) return NULL_I32;
+    switch (op) {
+        case RFB_ADD: return (i32)((u32)x + (u32)y);
+        case RFB_SUB: return (i32)((u32)x - (u32)y);
+        case RFB_MUL: return (i32)((u32)x * (u32)y);
+        case RFB_DIV: return y == 0 ? NULL_I32 : eucl_div32(x, y);
+        default: return y == 0 ? NULL_I32 : (i32)((u32)x - (u32)eucl_div32(x, y) * (u32)y);
+    }
+}
+__device__ __forceinline__ i64 op_i64(int op, i64 x, i64 y) {
+    if (x == NULL_I64 || y == NULL_I64) return NULL_I64;
+    switch (op) {
+        case RFB_ADD: return (i64)((u64)x + (u64)y);
+        case RFB_SUB: return (i64)((u64)x - (u64)y);
+        case RFB_MUL: return (i64)((u64)x * (u64)y);
+        case RFB_DIV: return y == 0 ? NULL_I64 : eucl_div64(x, y);
+        default: return y == 0 ? NULL_I64 : (i64)((u64)x - (u64)eucl_div64(x, y) * (u64)y);
+    }
+}
+// plain IEEE ops, never contracted into FMAs: the reference materialises every intermediate
+__device__ __forceinline__ f64 op_f64(int op, f64 x, f64 y) {
+    if (isnan64(x) || isnan64(y)) return null_f64();
+    switch (op) {
+        case RFB_ADD: return __dadd_rn(x, y);
+        case RFB_SUB: return __dsub_rn(x, y);
+        case RFB_MUL: return __dmul_rn(x, y);
+        case RFB_DIV: return y == 0.0 ? null_f64() : floor(__ddiv_rn(x, y));
+        default: return y == 0.0 ? null_f64() : __dsub_rn(x, __dmul_rn(floor(__ddiv_rn(x, y)), y));
+    }
+}
+__device__ __forceinline__ f64 op_fdiv(bool left_is_int, f64 x, f64 y) {
+    if (left_is_int) {  // FDIVI64 applied to converted doubles (core/ops.h:173): null test against (double)INT64_MIN
+        const f64 nul = -9223372036854775808.0;
+        if (y == 0.0 || x == nul || y == nul || isnan64(y)) return null_f64();
+        return __ddiv_rn(x, y);
+    }
+    if (y == 0.0 || isnan64(x) || isnan64(y)) return null_f64();
+    return __ddiv_rn(x, y);
+}
+// f64 -> integer with the x86 cvttsd2si behaviour the reference compiles to: NaN / out of range -> INT_MIN (= null)
+__device__ __forceinline__ i64 f64_to_i64(f64 x) {
+    if (isnan64(x) || !(x > -9223372036854775808.0 && x < 9223372036854775808.0)) return NULL_I64;
+    return (i64)x;
+}
+__device__ __forceinline__ i32 f64_to_i32(f64 x) {
+    if (isnan64(x) || !(x > -2147483649.0 && x < 2147483648.0)) return NULL_I32;
+    return (i32)x;
+}
+__device__ __forceinline__ i32 i64_to_i32(i64 x) { return x == NULL_I64 ? NULL_I32 : (i32)x; }
+
+template <typename M> struct Conv;  // widen an operand into computation type M
+template <> struct Conv<i32> { template <typename T> __device__ __forceinline__ static i32 of(T v) { return (i32)v; } };
+template <> struct Conv<i64> { template <typename T> __device__ __forceinline__ static i64 of(T v) { return widen_i64(v); } };
+template <> struct Conv<f64> { template <typename T> __device__ __forceinline__ static f64 of(T v) { return widen_f64(v); } };
+
+// X, Y operand element types; M computation type; O output type
+template <typename X, typename Y, typename M, typename O> struct BinOp {
+    int op;
+    bool left_is_int;
+    __device__ __forceinline__ O operator()(X a, Y b) const {
+        if constexpr (Elem<M>::kind == K_F64) {
+            const f64 x = Conv<f64>::of(a), y = Conv<f64>::of(b);
+            if (op == RFB_FDIV) return (O)op_fdiv(left_is_int, x, y);
+            const f64 r = op_f64(op, x, y);
+            if constexpr (Elem<O>::kind == K_F64) return r;
+            else if constexpr (Elem<O>::kind == K_I64) return f64_to_i64(r);
+            else return f64_to_i32(r);
+        } else if constexpr (Elem<M>::kind == K_I64) {
+            const i64 r = op_i64(op, Conv<i64>::of(a), Conv<i64>::of(b));
+            if constexpr (Elem<O>::kind == K_I64) return r;
+            else if constexpr (Elem<O>::kind == K_I32) return i64_to_i32(r);
+            else return (O)r;
+        } else {
+            return (O)op_i32(op, (i32)a, (i32)b);
+        }
+    }
+};
+
+// result typing: the per-case macro arguments of core/math.c:251-1782 / infer_*_type core/math.c:92-223
+bool binop_types(int op, int xt, int yt, int *mt, int *ot) {
+    const bool okx = (xt == RFB_I32 || xt == RFB_I64 || xt == RFB_F64), oky = (yt == RFB_I32 || yt == RFB_I64 || yt == RFB_F64);
+    if (!okx || !oky) return false;
+    const bool anyf = (xt == RFB_F64 || yt == RFB_F64), any64 = (xt == RFB_I64 || yt == RFB_I64);
+    const int wide = anyf ? RFB_F64 : any64 ? RFB_I64 : RFB_I32;
+    switch (op) {
+        case RFB_ADD: case RFB_SUB: case RFB_MUL: *mt = wide; *ot = wide; return true;
+        case RFB_DIV: *mt = wide; *ot = xt; return true;                    // keeps the LEFT operand's type
+        case RFB_FDIV: *mt = RFB_F64; *ot = RFB_F64; return true;
+        case RFB_MOD: *mt = wide; *ot = anyf ? RFB_F64 : yt; return true;   // integer % integer: RIGHT operand's type
+        default: return false;
+    }
+}
+
+template <typename T> T scalar_as(const rfb_scalar_t *s) {
+    if (!s) return T();
+    switch (rfb_kind_of(s->type)) {
+        case K_I32: return (T)s->v.i32;
+        case K_I64: return (T)s->v.i64;
+        case K_F64: return (T)s->v.f64;
+        default: return T();
+    }
+}
+
+template <typename X, typename Y, typename M, typename O>
+int binop_form(rfb_ctx_t *ctx, int op, bool left_is_int, const void *x, i64 xn, const rfb_scalar_t *xs, const void *y,
+               i64 yn, const rfb_scalar_t *ys, void *out) {
+    BinOp<X, Y, M, O> f{op, left_is_int};
+    const i64 n = xn >= 0 ? xn : yn;
+    if (xn >= 0 && yn >= 0) return launch_map2<X, Y, O, false, false>(ctx, x, X(), y, Y(), out, n, f);
+    if (xn >= 0) return launch_map2<X, Y, O, false, true>(ctx, x, X(), nullptr, scalar_as<Y>(ys), out, n, f);
+    return launch_map2<X, Y, O, true, false>(ctx, nullptr, scalar_as<X>(xs), y, Y(), out, n, f);
+}
+
+template <typename X, typename Y, typename M>
+int binop_out(rfb_ctx_t *ctx, int op, int ot, bool lii, const void *x, i64 xn, const rfb_scalar_t *xs, const void *y, i64 yn,
+              const rfb_scalar_t *ys, void *out) {
+    switch (ot) {
+        case RFB_I32: return binop_form<X, Y, M, i32>(ctx, op, lii, x, xn, xs, y, yn, ys, out);
+        case RFB_I64: return binop_form<X, Y, M, i64>(ctx, op, lii, x, xn, xs, y, yn, ys, out);
+        default: return binop_form<X, Y, M, f64>(ctx, op, lii, x, xn, xs, y, yn, ys, out);
+    }
+}
+
+template <typename X, typename Y>
+int binop_xy(rfb_ctx_t *ctx, int op, int mt, int ot, bool lii, const void *x, i64 xn, const rfb_scalar_t *xs, const void *y,
+             i64 yn, const rfb_scalar_t *ys, void *out) {
+    constexpr int kx = Elem<X>::kind, ky = Elem<Y>::kind;
+    // only the (M, O) pairs binop_types can produce for this (X, Y) are instantiated
+    if (mt == RFB_F64) {
+        if constexpr (kx == K_F64 || ky == K_F64) return binop_out<X, Y, f64>(ctx, op, ot, lii, x, xn, xs, y, yn, ys, out);
+        else return binop_form<X, Y, f64, f64>(ctx, op, lii, x, xn, xs, y, yn, ys, out);  // fdiv of two integer columns
+    }
+    if (mt == RFB_I64) {
+        if constexpr (kx != K_F64 && ky != K_F64 && (kx == K_I64 || ky == K_I64)) {
+            if (ot == RFB_I32) return binop_form<X, Y, i64, i32>(ctx, op, lii, x, xn, xs, y, yn, ys, out);
+            return binop_form<X, Y, i64, i64>(ctx, op, lii, x, xn, xs, y, yn, ys, out);
+        }
+    }
+    if constexpr (kx == K_I32 && ky == K_I32) return binop_form<i32, i32, i32, i32>(ctx, op, lii, x, xn, xs, y, yn, ys, out);
+    rfb_set_error("binop: internal type dispatch");
+    return RFB_ERR_TYPE;
+}
+
+template <typename X>
+int binop_x(rfb_ctx_t *ctx, int op, int mt, int ot, int yt, bool lii, const void *x, i64 xn, const rfb_scalar_t *xs,
+            const void *y, i64 yn, const rfb_scalar_t *ys, void *out) {
+    switch (yt) {
+        case RFB_I32: return binop_xy<X, i32>(ctx, op, mt, ot, lii, x, xn, xs, y, yn, ys, out);
+        case RFB_I64: return binop_xy<X, i64>(ctx, op, mt, ot, lii, x, xn, xs, y, yn, ys, out);
+        default: return binop_xy<X, f64>(ctx, op, mt, ot, lii, x, xn, xs, y, yn, ys, out);
+    }
+}
+
+}  // namespace
+
+extern "C" int rfb_binop_type(int op, int xt, int yt) {
+    int mt, ot;
+    return binop_types(op, xt, yt, &mt, &ot) ? ot : RFB_ERR_TYPE;
+}
+
+extern "C" int rfb_binop_dev(rfb_ctx_t *ctx, int op, int xt, const void *x, int64_t xn, const rfb_scalar_t *xs, int yt,
+                             const void *y, int64_t yn, const rfb_scalar_t *ys, void *out) {
+    RFB_ARG(ctx, "rfb_binop_dev: ctx");
+    int mt, ot;
+    if (!binop_types(op, xt, yt, &mt, &ot)) { rfb_set_error("binop %d: unsupported operand types %d, %d", op, xt, yt); return RFB_ERR_TYPE; }
+    if (xn >= 0 && yn >= 0 && xn != yn) { rfb_set_error("binop: vector lengths differ (%lld vs %lld)", (long long)xn, (long long)yn); return RFB_ERR_LENGTH; }
+    if (xn < 0 && yn < 0) { rfb_set_error("binop: both operands are atoms; the operator layer folds constants on the host"); return RFB_ERR_ARG; }
+    RFB_ARG((xn >= 0 ? (x || xn == 0) : xs != nullptr) && (yn >= 0 ? (y || yn == 0) : ys != nullptr), "rfb_binop_dev: operands");
+    RFB_ARG(out || (xn >= 0 ? xn : yn) == 0, "rfb_binop_dev: out");
+    if ((xn < 0 && xs->type != xt) || (yn < 0 && ys->type != yt)) { rfb_set_error("binop: scalar type tag does not match operand type"); return RFB_ERR_ARG; }
+    const bool lii = xt != RFB_F64;
+    switch (xt) {
+        case RFB_I32: return binop_x<i32>(ctx, op, mt, ot, yt, lii, x, xn, xs, y, yn, ys, out);
+        case RFB_I64: return binop_x<i64>(ctx, op, mt, ot, yt, lii, x, xn, xs, y, yn, ys, out);
+        default: return binop_x<f64>(ctx, op, mt, ot, yt, lii, x, xn, xs, y, yn, ys, out);
+    }
+}
+
+// ------------------------------------------------------------------ round / floor / ceil
+
+namespace {
+// core/ops.h:190-192: the reference rounds through an (i64) cast
+__device__ __forceinline__ f64 trunc_via_i64(f64 v) { return (f64)f64_to_i64(v); }
+__device__ __forceinline__ f64 floor_ref(f64 v) {
+    const f64 t = trunc_via_i64(v);
+    return (v < 0.0 && t != v) ? __dsub_rn(t, 1.0) : t;
+}
+struct UnopF64 {
+    int op;
+    __device__ __forceinline__ f64 operator()(f64 v) const {
+        if (isnan64(v)) return null_f64();
+        switch (op) {
+            case RFB_ROUND: return v >= 0.0 ? trunc_via_i64(__dadd_rn(v, 0.5)) : trunc_via_i64(__dsub_rn(v, 0.5));
+            case RFB_FLOOR: return floor_ref(v);
+            default: return -floor_ref(-v);
+        }
+    }
+};
+}  // namespace
+
+extern "C" int rfb_unop_f64_dev(rfb_ctx_t *ctx, int op, const double *x, int64_t n, double *out) {
+    RFB_ARG(ctx && n >= 0 && ((x && out) || n == 0), "rfb_unop_f64_dev");
+    if (op < RFB_ROUND || op > RFB_CEIL) { rfb_set_error("unop: unknown op %d", op); return RFB_ERR_ARG; }
+    if (n == 0) return RFB_OK;
+    const bool vec_ok = aligned16(x) && aligned16(out);
+    const int grid = rfb_grid_for(ctx, n, THREADS * 16, BLOCKS_PER_SM);
+    UnopF64 f{op};
+    k_map1<f64, f64, UnopF64><<<grid, THREADS, 0, ctx->stream>>>(x, out, n, vec_ok, f);
+    RFB_CHECK_LAUNCH(ctx);
+    return RFB_OK;
+}
