@@ -22,24 +22,6 @@ constexpr int BLOCKS_PER_SM = 4;
 
 enum { FS_SUMCNT = RFB_F_SUM | RFB_F_CNT, FS_MINMAX = RFB_F_MIN | RFB_F_MAX, FS_ALL = RFB_F_ALL };
 
-// predicate = unsigned range test on an order-preserving 64-bit key, optionally negated.
-// All six comparison operators against a constant reduce to it (see make_pred_range).
-struct PredRange {
-    u64 lo, span;
-    u32 negate;
-};
-
-__host__ __device__ __forceinline__ u64 key_of_i64(i64 x) { return (u64)x ^ 0x8000000000000000ULL; }
-// doubles: -0.0 == +0.0 must hold for comparisons (unlike the sort key), NaN is below everything and equals NaN
-__host__ __device__ __forceinline__ u64 key_of_f64(f64 x) { return f64_sort_key(x == 0.0 ? 0.0 : x); }
-
-template <typename P> __device__ __forceinline__ u64 pred_key(P x) {
-    if constexpr (Elem<P>::kind == K_F64) return key_of_f64(x);
-    else return key_of_i64(widen_i64(x));
-}
-
-__device__ __forceinline__ bool pred_test(u64 key, const PredRange &pr) { return ((key - pr.lo) <= pr.span) != (bool)pr.negate; }
-
 struct Partial {
     i64 rows, nonnull;
     u64 sum, mn, mx;  // bit patterns of i64 or f64 depending on the value kind
@@ -303,41 +285,6 @@ inline Scratch scratch_of(rfb_ctx_t *ctx) {
     return s;
 }
 
-// scalar -> i64 (null-preserving) or f64
-bool scalar_as_i64(const rfb_scalar_t *k, i64 *out) {
-    switch (rfb_kind_of(k->type)) {
-        case K_U8: *out = k->v.u8; return true;
-        case K_I16: *out = k->v.i16 == NULL_I16 ? NULL_I64 : (i64)k->v.i16; return true;
-        case K_I32: *out = k->v.i32 == NULL_I32 ? NULL_I64 : (i64)k->v.i32; return true;
-        case K_I64: *out = k->v.i64; return true;
-        default: return false;
-    }
-}
-bool scalar_as_f64(const rfb_scalar_t *k, f64 *out) {
-    i64 t;
-    if (rfb_kind_of(k->type) == K_F64) { *out = k->v.f64; return true; }
-    if (!scalar_as_i64(k, &t)) return false;
-    *out = (rfb_kind_of(k->type) != K_U8 && t == NULL_I64) ? null_f64() : (f64)t;
-    return true;
-}
-
-// OP(x, k)  <=>  key(x) in [lo, lo+span] (xor negate)
-PredRange make_pred_range(int op, u64 kk) {
-    PredRange pr;
-    const u64 MAXK = ~0ULL;
-    pr.negate = 0;
-    switch (op) {
-        case RFB_EQ: pr.lo = kk; pr.span = 0; break;
-        case RFB_NE: pr.lo = kk; pr.span = 0; pr.negate = 1; break;
-        case RFB_LE: pr.lo = 0; pr.span = kk; break;
-        case RFB_GE: pr.lo = kk; pr.span = MAXK - kk; break;
-        case RFB_LT: if (kk == 0) { pr.lo = 0; pr.span = MAXK; pr.negate = 1; } else { pr.lo = 0; pr.span = kk - 1; } break;
-        default /*GT*/: if (kk == MAXK) { pr.lo = 0; pr.span = MAXK; pr.negate = 1; } else { pr.lo = kk + 1; pr.span = MAXK - kk - 1; } break;
-    }
-    return pr;
-}
-
-inline bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
 
 template <typename P, typename V, int FOLDS, bool HAS_PRED, bool SAME>
 int launch_scan_fold(rfb_ctx_t *ctx, const void *pred, PredRange pr, const void *val, i64 n, int vkind) {

@@ -1,0 +1,618 @@
+// k_group.cu — hash / perfect-hash group-by and grouped aggregates (sm_100a).
+//
+//   rfb_group_i64_dev         index_group -> index_group_i64: scope + group numbering (reference core/index.c:402-435,
+//                             2002-2092 perfect hash, 1777-1911 + core/hash.c open addressing)
+//   rfb_aggr_dev              aggr_sum/min/max/count/avg (core/aggr.c AGGR_ITER :73-161, :1078-1453, :1455-2133)
+//   rfb_group_sum_count_dev   select {s: (sum v) c: (count v) from t by k [where ...]} fused: never materialises group ids
+//
+// Group numbering must be the reference's: groups are numbered in order of first occurrence in (filtered) row order
+// (core/index.c:2037-2055, sequential there).  The device does it without a sequential scan:
+//   1. scope     min/max of the keys (one streaming reduction)                                   -> dense or sparse?
+//   2. claim     every row does first_row[slot(key)] = min(first_row[slot], row): a plain load filters out almost every
+//                atomic once a slot has been claimed by an earlier row (values only decrease, so a stale read is safe)
+//                dense  : slot = key - min (direct addressing, "perfect hash")
+//                sparse : slot = open-addressing table in HBM/L2, 64-bit CAS insert, linear probing, load factor <= 0.5
+//   3. number    rows [0, max(first_row)] are compacted in row order by the predicate first_row[slot(key_row)] == row
+//                (the chained-scan compaction of rfb_scan.cuh): the g-th such row IS the first row of group g
+//                -> first_ids[g] = row, gid_of_slot[slot] = g
+//   4. assign    group_ids[row] = gid_of_slot[slot(key_row)]
+// Aggregates are per-group accumulators updated with L2 atomics (red.global), finalised by a small per-group kernel
+// (sticky-null sums, +INF/NULL-initialised min/max, f64 averages).
+#include "rfb_scan.cuh"
+
+namespace {
+
+constexpr int THREADS = 256;
+constexpr int BLOCKS_PER_SM = 4;
+constexpr u64 NO_ROW = ~0ULL;
+constexpr int NUM_J = 8;  // rows per lane in the numbering pass
+
+template <typename T> __global__ void k_fill(T *p, i64 n, T v) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) p[i] = v;
+}
+template <typename T> int fill(rfb_ctx_t *ctx, T *p, i64 n, T v) {
+    if (n <= 0) return RFB_OK;
+    k_fill<T><<<rfb_grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(p, n, v);
+    RFB_CHECK_LAUNCH(ctx);
+    return RFB_OK;
+}
+
+// ------------------------------------------------------------------ row sources and slot functions
+
+// position i of the (filtered) row sequence -> key
+struct KeySrc {
+    const i64 *keys;
+    const i64 *filter;  // or nullptr
+    __device__ __forceinline__ i64 operator()(i64 i) const { return filter ? __ldg(keys + ld_stream(filter + i)) : ld_stream(keys + i); }
+};
+
+struct DenseSlot {
+    i64 min;
+    __device__ __forceinline__ i64 operator()(i64 key) const { return (i64)((u64)key - (u64)min); }
+};
+
+__host__ __device__ __forceinline__ u64 mix64(u64 z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+// open-addressing table: tk[cap] keys (EMPTY = NULL_I64, like the reference's ht_oa tables, core/hash.c:35-56) plus one
+// dedicated slot `cap` for the NULL_I64 key itself (which the reference's table cannot represent).
+struct HashSlot {
+    i64 *tk;
+    u64 mask;
+    i64 cap;
+    __device__ __forceinline__ i64 insert(i64 key) const {
+        if (key == NULL_I64) return cap;
+        u64 s = mix64((u64)key) & mask;
+        while (true) {
+            i64 cur = (i64)scan::ld_relaxed((const u64 *)&tk[s]);
+            if (cur == key) return (i64)s;
+            if (cur == NULL_I64) {
+                const i64 old = (i64)atomicCAS((unsigned long long *)&tk[s], (unsigned long long)NULL_I64, (unsigned long long)key);
+                if (old == NULL_I64 || old == key) return (i64)s;
+            }
+            s = (s + 1) & mask;
+        }
+    }
+    __device__ __forceinline__ i64 operator()(i64 key) const {  // lookup of a key known to be present
+        if (key == NULL_I64) return cap;
+        u64 s = mix64((u64)key) & mask;
+        while (__ldg(&tk[s]) != key) s = (s + 1) & mask;
+        return (i64)s;
+    }
+};
+
+__device__ __forceinline__ void claim_first(u64 *first_row, i64 slot, i64 row) {
+    if (__ldcg(&first_row[slot]) > (u64)row) atomicMin((unsigned long long *)&first_row[slot], (unsigned long long)row);
+}
+
+// ------------------------------------------------------------------ 1. scope
+
+__global__ void k_scope_init(i64 *mm) { mm[0] = RFB_INF_I64; mm[1] = NULL_I64; mm[2] = 0; }
+
+template <typename Src>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_scope(Src src, i64 n, i64 *mm) {
+    __shared__ i64 red[32];
+    i64 lo = RFB_INF_I64, hi = NULL_I64;
+    constexpr int U = 4;
+    const i64 stride = (i64)gridDim.x * THREADS;
+    i64 i = (i64)blockIdx.x * THREADS + threadIdx.x;
+    for (; i + (U - 1) * stride < n; i += U * stride) {
+        i64 k[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) k[j] = src(i + j * stride);
+#pragma unroll
+        for (int j = 0; j < U; j++) { lo = k[j] < lo ? k[j] : lo; hi = k[j] > hi ? k[j] : hi; }
+    }
+    for (; i < n; i += stride) { const i64 k = src(i); lo = k < lo ? k : lo; hi = k > hi ? k : hi; }
+    struct Mn { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b < a ? b : a; } };
+    struct Mx { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b > a ? b : a; } };
+    lo = block_reduce<i64>(lo, Mn(), RFB_INF_I64, red);
+    hi = block_reduce<i64>(hi, Mx(), NULL_I64, red);
+    if (threadIdx.x == 0) {
+        atomicMin((long long *)&mm[0], (long long)lo);
+        atomicMax((long long *)&mm[1], (long long)hi);
+    }
+}
+
+// ------------------------------------------------------------------ 2. claim
+
+template <typename Src, typename Slot, bool INSERT>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_claim(Src src, Slot slot, i64 n, u64 *first_row) {
+    constexpr int U = 4;
+    const i64 stride = (i64)gridDim.x * THREADS;
+    i64 i = (i64)blockIdx.x * THREADS + threadIdx.x;
+    for (; i + (U - 1) * stride < n; i += U * stride) {
+        i64 k[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) k[j] = src(i + j * stride);
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            i64 s;
+            if constexpr (INSERT) s = slot.insert(k[j]); else s = slot(k[j]);
+            claim_first(first_row, s, i + j * stride);
+        }
+    }
+    for (; i < n; i += stride) {
+        const i64 k = src(i);
+        i64 s;
+        if constexpr (INSERT) s = slot.insert(k); else s = slot(k);
+        claim_first(first_row, s, i);
+    }
+}
+
+// max over the claimed first rows (bounds the numbering pass)
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_max_first(const u64 *first_row, i64 slots, i64 *mm) {
+    __shared__ i64 red[32];
+    i64 hi = -1;
+    for (i64 i = (i64)blockIdx.x * THREADS + threadIdx.x; i < slots; i += (i64)gridDim.x * THREADS) {
+        const u64 f = first_row[i];
+        if (f != NO_ROW && (i64)f > hi) hi = (i64)f;
+    }
+    struct Mx { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b > a ? b : a; } };
+    hi = block_reduce<i64>(hi, Mx(), (i64)-1, red);
+    if (threadIdx.x == 0) atomicMax((long long *)&mm[2], (long long)(hi + 1));
+}
+
+// ------------------------------------------------------------------ 3. number
+
+template <typename Src, typename Slot>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_number(Src src, Slot slot, i64 limit, const u64 *first_row, i64 *gid_of_slot, i64 *first_ids, scan::TileCtl ctl) {
+    __shared__ scan::TileSmem sm;
+    scan::compact_rows<NUM_J>(
+        limit, ctl, sm, [&](i64 r) { return __ldcg(&first_row[slot(src(r))]) == (u64)r; },
+        [&](i64 r, i64 g) {
+            first_ids[g] = r;
+            gid_of_slot[slot(src(r))] = g;
+        });
+}
+
+// ------------------------------------------------------------------ 4. assign
+
+template <typename Src, typename Slot>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_assign(Src src, Slot slot, i64 n, const i64 *__restrict__ gid_of_slot, i64 *__restrict__ group_ids) {
+    constexpr int U = 4;
+    const i64 stride = (i64)gridDim.x * THREADS;
+    i64 i = (i64)blockIdx.x * THREADS + threadIdx.x;
+    for (; i + (U - 1) * stride < n; i += U * stride) {
+        i64 k[U], g[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) k[j] = src(i + j * stride);
+#pragma unroll
+        for (int j = 0; j < U; j++) g[j] = __ldg(&gid_of_slot[slot(k[j])]);
+#pragma unroll
+        for (int j = 0; j < U; j++) __stcs(group_ids + i + j * stride, g[j]);
+    }
+    for (; i < n; i += stride) group_ids[i] = __ldg(&gid_of_slot[slot(src(i))]);
+}
+
+int d2h_sync(rfb_ctx_t *ctx, void *dst, const void *src, size_t bytes) {
+    RFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    RFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RFB_OK;
+}
+
+inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+template <typename Slot, bool INSERT>
+int number_groups(rfb_ctx_t *ctx, KeySrc src, Slot slot, i64 len, i64 slots, u64 *first_row, i64 *gid_of_slot, void *tile_work,
+                  i64 *mm, i64 *group_ids, i64 *first_ids, i64 *groups) {
+    const int grid = rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM);
+    k_claim<KeySrc, Slot, INSERT><<<grid, THREADS, 0, ctx->stream>>>(src, slot, len, first_row);
+    RFB_CHECK_LAUNCH(ctx);
+    k_max_first<<<rfb_grid_for(ctx, slots, THREADS, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(first_row, slots, mm);
+    RFB_CHECK_LAUNCH(ctx);
+    i64 limit = 0;
+    int rc = d2h_sync(ctx, &limit, mm + 2, 8);
+    if (rc) return rc;
+    const i64 tiles = (limit + scan::RowTile<NUM_J>::TILE - 1) / scan::RowTile<NUM_J>::TILE;
+    scan::TileCtl ctl;
+    rc = scan::prepare_tiles(ctx, tile_work, tiles, ctx->h_count, &ctl);
+    if (rc) return rc;
+    k_number<KeySrc, Slot><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(src, slot, limit, first_row, gid_of_slot, first_ids, ctl);
+    RFB_CHECK_LAUNCH(ctx);
+    if (group_ids) {
+        k_assign<KeySrc, Slot><<<grid, THREADS, 0, ctx->stream>>>(src, slot, len, gid_of_slot, group_ids);
+        RFB_CHECK_LAUNCH(ctx);
+    }
+    RFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *groups = *(volatile i64 *)ctx->h_count;
+    return RFB_OK;
+}
+
+}  // namespace
+
+extern "C" int rfb_group_i64_dev(rfb_ctx_t *ctx, const int64_t *keys, const int64_t *filter, int64_t len,
+                                 int64_t *group_ids, int64_t *first_ids, rfb_group_info_t *info) {
+    RFB_ARG(ctx && info && len >= 0 && ((keys && first_ids) || len == 0), "rfb_group_i64_dev");
+    memset(info, 0, sizeof(*info));
+    if (len == 0) {  // core/index.c:408-409: empty scope -> dense path with zero groups
+        info->min = info->max = NULL_I64;
+        info->dense = 1;
+        info->index_type = RFB_INDEX_SHIFT;
+        return RFB_OK;
+    }
+    KeySrc src{keys, filter};
+    i64 *mm = (i64 *)((char *)ctx->d_scratch + 32768);  // {min, max, limit}
+    k_scope_init<<<1, 1, 0, ctx->stream>>>(mm);
+    RFB_CHECK_LAUNCH(ctx);
+    k_scope<KeySrc><<<rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(src, len, mm);
+    RFB_CHECK_LAUNCH(ctx);
+    i64 h[2];
+    int rc = d2h_sync(ctx, h, mm, 16);
+    if (rc) return rc;
+    info->min = h[0];
+    info->max = h[1];
+    info->range = (i64)((u64)h[1] - (u64)h[0] + 1);
+    const i64 tiles_max = (len + scan::RowTile<NUM_J>::TILE - 1) / scan::RowTile<NUM_J>::TILE;
+    i64 groups = 0;
+    if (info->range > 0 && info->range <= len) {
+        // dense: first_row[range] | gid_of_slot[range] | tile states
+        const i64 range = info->range;
+        const size_t b1 = align256((size_t)range * 8);
+        void *w;
+        rc = rfb_ensure_work(ctx, 2 * b1 + scan::tiles_bytes(tiles_max), &w);
+        if (rc) return rc;
+        u64 *first_row = (u64 *)w;
+        i64 *gid_of_slot = (i64 *)((char *)w + b1);
+        RFB_CUDA(cudaMemsetAsync(first_row, 0xFF, (size_t)range * 8, ctx->stream));
+        rc = number_groups<DenseSlot, false>(ctx, src, DenseSlot{info->min}, len, range, first_row, gid_of_slot, (char *)w + 2 * b1,
+                                             mm, group_ids, first_ids, &groups);
+        if (rc) return rc;
+        info->dense = 1;
+        info->index_type = range <= RFB_INDEX_SCOPE_LIMIT ? RFB_INDEX_SHIFT : RFB_INDEX_IDS;  // core/index.c:2063
+    } else {
+        // sparse: tk[cap+1] | first_row[cap+1] | gid_of_slot[cap+1] | tile states.  cap = power of two >= 2*len
+        i64 cap = 1024;
+        while (cap < 2 * len) cap <<= 1;
+        const size_t b1 = align256((size_t)(cap + 1) * 8);
+        void *w;
+        rc = rfb_ensure_work(ctx, 3 * b1 + scan::tiles_bytes(tiles_max), &w);
+        if (rc) return rc;
+        i64 *tk = (i64 *)w;
+        u64 *first_row = (u64 *)((char *)w + b1);
+        i64 *gid_of_slot = (i64 *)((char *)w + 2 * b1);
+        rc = fill<i64>(ctx, tk, cap + 1, NULL_I64);   // EMPTY marker
+        if (rc) return rc;
+        RFB_CUDA(cudaMemsetAsync(first_row, 0xFF, (size_t)(cap + 1) * 8, ctx->stream));
+        HashSlot hs{tk, (u64)(cap - 1), cap};
+        rc = number_groups<HashSlot, true>(ctx, src, hs, len, cap + 1, first_row, gid_of_slot, (char *)w + 3 * b1, mm, group_ids,
+                                           first_ids, &groups);
+        if (rc) return rc;
+        info->dense = 0;
+        info->index_type = RFB_INDEX_IDS;
+    }
+    info->groups = groups;
+    return RFB_OK;
+}
+
+// ------------------------------------------------------------------ grouped aggregates
+
+namespace {
+
+struct ValRow {
+    const i64 *filter;
+    __device__ __forceinline__ i64 operator()(i64 i) const { return filter ? ld_stream(filter + i) : i; }
+};
+
+
+__device__ __forceinline__ f64 key_to_f64(u64 k) {  // inverse of f64_sort_key; key 0 = null
+    if (k == 0) return null_f64();
+    return bits_f64((k & 0x8000000000000000ULL) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k);
+}
+
+enum { AK_SUM_I64, AK_SUM_I32, AK_SUM_F64, AK_MIN_I64, AK_MAX_I64, AK_MIN_I32, AK_MAX_I32, AK_MIN_F64, AK_MAX_F64, AK_COUNT,
+       AK_AVG_I64, AK_AVG_I32, AK_AVG_F64 };
+
+// acc: main accumulator array (typed per kind), aux: null flags (sum) or non-null counts (avg)
+template <int KIND, typename V>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_aggr(const V *__restrict__ val, ValRow row, const i64 *__restrict__ gid, i64 n, void *acc, void *aux) {
+    constexpr int U = 4;
+    const i64 stride = (i64)gridDim.x * THREADS;
+    auto one = [&](i64 g, V v) {
+        if constexpr (KIND == AK_SUM_I64) {
+            if (v == NULL_I64) ((u32 *)aux)[g] = 1u; else atomicAdd((unsigned long long *)acc + g, (unsigned long long)v);
+        } else if constexpr (KIND == AK_SUM_I32) {
+            if (v == NULL_I32) ((u32 *)aux)[g] = 1u; else atomicAdd((u32 *)acc + g, (u32)v);
+        } else if constexpr (KIND == AK_SUM_F64) {
+            if (isnan64(v)) ((u32 *)aux)[g] = 1u; else atomicAdd((f64 *)acc + g, v);
+        } else if constexpr (KIND == AK_MIN_I64) {
+            if (v != NULL_I64) atomicMin((long long *)acc + g, (long long)v);
+        } else if constexpr (KIND == AK_MAX_I64) {
+            atomicMax((long long *)acc + g, (long long)v);    // NULL is the minimum: never wins
+        } else if constexpr (KIND == AK_MIN_I32) {
+            if (v != NULL_I32) atomicMin((int *)acc + g, (int)v);
+        } else if constexpr (KIND == AK_MAX_I32) {
+            atomicMax((int *)acc + g, (int)v);
+        } else if constexpr (KIND == AK_MIN_F64) {
+            if (!isnan64(v)) atomicMin((unsigned long long *)acc + g, (unsigned long long)f64_sort_key(v));
+        } else if constexpr (KIND == AK_MAX_F64) {
+            atomicMax((unsigned long long *)acc + g, (unsigned long long)f64_sort_key(v));   // NaN -> key 0: never wins
+        } else if constexpr (KIND == AK_AVG_I64) {
+            if (v != NULL_I64) { atomicAdd((unsigned long long *)acc + g, (unsigned long long)v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
+        } else if constexpr (KIND == AK_AVG_I32) {
+            if (v != NULL_I32) { atomicAdd((unsigned long long *)acc + g, (unsigned long long)(i64)v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
+        } else if constexpr (KIND == AK_AVG_F64) {
+            if (!isnan64(v)) { atomicAdd((f64 *)acc + g, v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
+        }
+    };
+    i64 i = (i64)blockIdx.x * THREADS + threadIdx.x;
+    for (; i + (U - 1) * stride < n; i += U * stride) {
+        i64 g[U];
+        V v[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) { g[j] = ld_stream(gid + i + j * stride); v[j] = row.filter ? __ldg(val + row(i + j * stride)) : ld_stream(val + i + j * stride); }
+#pragma unroll
+        for (int j = 0; j < U; j++) one(g[j], v[j]);
+    }
+    for (; i < n; i += stride) one(ld_stream(gid + i), row.filter ? __ldg(val + row(i)) : ld_stream(val + i));
+}
+
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_count(const i64 *__restrict__ gid, i64 n, unsigned long long *acc) {
+    for (i64 i = (i64)blockIdx.x * THREADS + threadIdx.x; i < n; i += (i64)gridDim.x * THREADS) atomicAdd(acc + ld_stream(gid + i), 1ULL);
+}
+
+template <int KIND> __global__ void k_aggr_final(void *out, const void *acc, const void *aux, i64 groups) {
+    for (i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (i64)gridDim.x * blockDim.x) {
+        if constexpr (KIND == AK_SUM_I64) { if (((const u32 *)aux)[g]) ((i64 *)out)[g] = NULL_I64; }
+        else if constexpr (KIND == AK_SUM_I32) { if (((const u32 *)aux)[g]) ((i32 *)out)[g] = NULL_I32; }
+        else if constexpr (KIND == AK_SUM_F64) { if (((const u32 *)aux)[g]) ((f64 *)out)[g] = null_f64(); }
+        else if constexpr (KIND == AK_MIN_F64 || KIND == AK_MAX_F64) ((f64 *)out)[g] = key_to_f64(((const u64 *)acc)[g]);
+        else if constexpr (KIND == AK_AVG_I64 || KIND == AK_AVG_I32) {
+            const i64 c = ((const i64 *)aux)[g];
+            ((f64 *)out)[g] = c == 0 ? null_f64() : __ddiv_rn((f64)((const i64 *)acc)[g], (f64)c);
+        } else if constexpr (KIND == AK_AVG_F64) {
+            const i64 c = ((const i64 *)aux)[g];
+            ((f64 *)out)[g] = c == 0 ? null_f64() : __ddiv_rn(((const f64 *)acc)[g], (f64)c);
+        }
+    }
+}
+
+template <int KIND, typename V>
+int run_aggr(rfb_ctx_t *ctx, const void *val, const i64 *filter, const i64 *gid, i64 len, i64 groups, void *acc, void *aux, void *out) {
+    if (len > 0) {
+        k_aggr<KIND, V><<<rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>((const V *)val, ValRow{filter}, gid, len, acc, aux);
+        RFB_CHECK_LAUNCH(ctx);
+    }
+    k_aggr_final<KIND><<<rfb_grid_for(ctx, groups, 256, 8), 256, 0, ctx->stream>>>(out, acc, aux, groups);
+    RFB_CHECK_LAUNCH(ctx);
+    return RFB_OK;
+}
+
+}  // namespace
+
+extern "C" int rfb_aggr_type(int op, int val_type) {
+    const int k = rfb_kind_of(val_type);
+    if (!k) return RFB_ERR_TYPE;
+    switch (op) {
+        case RFB_A_COUNT: return (k == K_U8 || k == K_I16) ? RFB_ERR_TYPE : RFB_I64;
+        case RFB_A_SUM: return (val_type == RFB_I64 || k == K_I32 || k == K_F64) ? val_type : RFB_ERR_TYPE;
+        case RFB_A_MIN: case RFB_A_MAX:
+            return (val_type == RFB_I64 || val_type == RFB_TIMESTAMP || val_type == RFB_DATE || val_type == RFB_TIME || val_type == RFB_F64) ? val_type : RFB_ERR_TYPE;
+        case RFB_A_AVG: return (k == K_I32 || val_type == RFB_I64 || k == K_F64) ? RFB_F64 : RFB_ERR_TYPE;
+        default: return RFB_ERR_TYPE;
+    }
+}
+
+extern "C" int rfb_aggr_dev(rfb_ctx_t *ctx, int op, int val_type, const void *val, const int64_t *filter,
+                            const int64_t *group_ids, int64_t len, int64_t groups, void *out) {
+    RFB_ARG(ctx && len >= 0 && groups >= 0 && ((val && group_ids) || len == 0) && (out || groups == 0), "rfb_aggr_dev");
+    const int ot = rfb_aggr_type(op, val_type);
+    if (ot < 0) { rfb_set_error("aggr %d: unsupported value type %d", op, val_type); return RFB_ERR_TYPE; }
+    if (groups == 0) return RFB_OK;
+    const int k = rfb_kind_of(val_type);
+    void *w;
+    int rc = rfb_ensure_work(ctx, 2 * align256((size_t)groups * 8), &w);
+    if (rc) return rc;
+    void *acc = w, *aux = (char *)w + align256((size_t)groups * 8);
+    switch (op) {
+        case RFB_A_COUNT:
+            RFB_CUDA(cudaMemsetAsync(out, 0, (size_t)groups * 8, ctx->stream));
+            if (len > 0) {
+                k_count<<<rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(group_ids, len, (unsigned long long *)out);
+                RFB_CHECK_LAUNCH(ctx);
+            }
+            return RFB_OK;
+        case RFB_A_SUM:
+            RFB_CUDA(cudaMemsetAsync(out, 0, (size_t)groups * rfb_type_size(val_type), ctx->stream));
+            RFB_CUDA(cudaMemsetAsync(aux, 0, (size_t)groups * 4, ctx->stream));
+            if (k == K_I64) return run_aggr<AK_SUM_I64, i64>(ctx, val, filter, group_ids, len, groups, out, aux, out);
+            if (k == K_I32) return run_aggr<AK_SUM_I32, i32>(ctx, val, filter, group_ids, len, groups, out, aux, out);
+            return run_aggr<AK_SUM_F64, f64>(ctx, val, filter, group_ids, len, groups, out, aux, out);
+        case RFB_A_MIN:
+            if (k == K_I64) { rc = fill<i64>(ctx, (i64 *)out, groups, RFB_INF_I64); if (rc) return rc; return run_aggr<AK_MIN_I64, i64>(ctx, val, filter, group_ids, len, groups, out, aux, out); }
+            if (k == K_I32) { rc = fill<i32>(ctx, (i32 *)out, groups, (i32)0x7FFFFFFF); if (rc) return rc; return run_aggr<AK_MIN_I32, i32>(ctx, val, filter, group_ids, len, groups, out, aux, out); }
+            rc = fill<u64>(ctx, (u64 *)acc, groups, f64_sort_key(bits_f64(0x7FF0000000000000ULL)));
+            if (rc) return rc;
+            return run_aggr<AK_MIN_F64, f64>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
+        case RFB_A_MAX:
+            if (k == K_I64) { rc = fill<i64>(ctx, (i64 *)out, groups, NULL_I64); if (rc) return rc; return run_aggr<AK_MAX_I64, i64>(ctx, val, filter, group_ids, len, groups, out, aux, out); }
+            if (k == K_I32) { rc = fill<i32>(ctx, (i32 *)out, groups, NULL_I32); if (rc) return rc; return run_aggr<AK_MAX_I32, i32>(ctx, val, filter, group_ids, len, groups, out, aux, out); }
+            RFB_CUDA(cudaMemsetAsync(acc, 0, (size_t)groups * 8, ctx->stream));
+            return run_aggr<AK_MAX_F64, f64>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
+        default:  // AVG
+            RFB_CUDA(cudaMemsetAsync(acc, 0, (size_t)groups * 8, ctx->stream));
+            RFB_CUDA(cudaMemsetAsync(aux, 0, (size_t)groups * 8, ctx->stream));
+            if (k == K_I64) return run_aggr<AK_AVG_I64, i64>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
+            if (k == K_I32) return run_aggr<AK_AVG_I32, i32>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
+            return run_aggr<AK_AVG_F64, f64>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
+    }
+}
+
+// ------------------------------------------------------------------ fused dense group-by: sum + count [+ where]
+
+namespace {
+
+struct Accums {
+    u64 *first_row;   // [range]
+    u64 *sum;         // [range] wrapping i64 sums of the non-null values
+    u64 *cnt;         // [range] rows (nulls included: aggr_count counts rows, core/aggr.c:1336-1342)
+    u32 *has_null;    // [range] sticky-null marker for the sum (core/aggr.c:1088)
+};
+
+template <typename K, typename P, bool HAS_PRED>
+struct FusedSrc {
+    const K *keys;
+    const P *pred;
+    PredRange pr;
+    __device__ __forceinline__ bool selected(i64 i) const {
+        if constexpr (HAS_PRED) return pred_test(pred_key<P>(ld_stream(pred + i)), pr);
+        else return true;
+    }
+    __device__ __forceinline__ i64 key(i64 i) const { return (i64)ld_stream(keys + i); }
+};
+
+template <typename FS>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_fused_scope(FS fs, i64 n, i64 *mm) {
+    __shared__ i64 red[32];
+    i64 lo = RFB_INF_I64, hi = NULL_I64;
+    for (i64 i = (i64)blockIdx.x * THREADS + threadIdx.x; i < n; i += (i64)gridDim.x * THREADS) {
+        const i64 k = fs.key(i);
+        if (fs.selected(i)) { lo = k < lo ? k : lo; hi = k > hi ? k : hi; }
+    }
+    struct Mn { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b < a ? b : a; } };
+    struct Mx { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b > a ? b : a; } };
+    lo = block_reduce<i64>(lo, Mn(), RFB_INF_I64, red);
+    hi = block_reduce<i64>(hi, Mx(), NULL_I64, red);
+    if (threadIdx.x == 0) {
+        atomicMin((long long *)&mm[0], (long long)lo);
+        atomicMax((long long *)&mm[1], (long long)hi);
+    }
+}
+
+template <typename FS>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_fused_accum(FS fs, const i64 *__restrict__ val, i64 n, i64 kmin, Accums a) {
+    constexpr int U = 4;
+    const i64 stride = (i64)gridDim.x * THREADS;
+    auto one = [&](i64 i, i64 k, i64 v, bool sel) {
+        if (!sel) return;
+        const i64 s = (i64)((u64)k - (u64)kmin);
+        claim_first(a.first_row, s, i);
+        if (v == NULL_I64) a.has_null[s] = 1u; else atomicAdd((unsigned long long *)a.sum + s, (unsigned long long)v);
+        atomicAdd((unsigned long long *)a.cnt + s, 1ULL);
+    };
+    i64 i = (i64)blockIdx.x * THREADS + threadIdx.x;
+    for (; i + (U - 1) * stride < n; i += U * stride) {
+        i64 k[U], v[U];
+        bool sel[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) { k[j] = fs.key(i + j * stride); v[j] = ld_stream(val + i + j * stride); sel[j] = fs.selected(i + j * stride); }
+#pragma unroll
+        for (int j = 0; j < U; j++) one(i + j * stride, k[j], v[j], sel[j]);
+    }
+    for (; i < n; i += stride) one(i, fs.key(i), ld_stream(val + i), fs.selected(i));
+}
+
+template <typename FS>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_fused_emit(FS fs, i64 limit, i64 kmin, Accums a, i64 max_groups, i64 *out_keys, i64 *out_sums, i64 *out_counts, scan::TileCtl ctl) {
+    __shared__ scan::TileSmem sm;
+    scan::compact_rows<NUM_J>(
+        limit, ctl, sm,
+        [&](i64 r) { return fs.selected(r) && __ldcg(&a.first_row[(i64)((u64)fs.key(r) - (u64)kmin)]) == (u64)r; },
+        [&](i64 r, i64 g) {
+            if (g >= max_groups) return;
+            const i64 k = fs.key(r), s = (i64)((u64)k - (u64)kmin);
+            out_keys[g] = k;
+            out_sums[g] = a.has_null[s] ? NULL_I64 : (i64)a.sum[s];
+            out_counts[g] = (i64)a.cnt[s];
+        });
+}
+
+template <typename FS>
+int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 *out_keys, i64 *out_sums, i64 *out_counts, i64 *groups) {
+    i64 *mm = (i64 *)((char *)ctx->d_scratch + 32768);
+    k_scope_init<<<1, 1, 0, ctx->stream>>>(mm);
+    RFB_CHECK_LAUNCH(ctx);
+    const int grid = rfb_grid_for(ctx, n, THREADS * 4, BLOCKS_PER_SM);
+    k_fused_scope<FS><<<grid, THREADS, 0, ctx->stream>>>(fs, n, mm);
+    RFB_CHECK_LAUNCH(ctx);
+    i64 h[2];
+    int rc = d2h_sync(ctx, h, mm, 16);
+    if (rc) return rc;
+    if (h[0] > h[1]) { *groups = 0; return RFB_OK; }   // nothing selected
+    const i64 range = (i64)((u64)h[1] - (u64)h[0] + 1);
+    if (range <= 0 || range > (1ll << 28)) {
+        rfb_set_error("fused group-by: key range %lld is not a dense domain (use rfb_group_i64_dev + rfb_aggr_dev)", (long long)range);
+        return RFB_ERR_ARG;
+    }
+    const i64 tiles_max = (n + scan::RowTile<NUM_J>::TILE - 1) / scan::RowTile<NUM_J>::TILE;
+    const size_t b8 = align256((size_t)range * 8), b4 = align256((size_t)range * 4);
+    void *w;
+    rc = rfb_ensure_work(ctx, 3 * b8 + b4 + scan::tiles_bytes(tiles_max), &w);
+    if (rc) return rc;
+    Accums a;
+    a.first_row = (u64 *)w;
+    a.sum = (u64 *)((char *)w + b8);
+    a.cnt = (u64 *)((char *)w + 2 * b8);
+    a.has_null = (u32 *)((char *)w + 3 * b8);
+    RFB_CUDA(cudaMemsetAsync(a.first_row, 0xFF, (size_t)range * 8, ctx->stream));
+    RFB_CUDA(cudaMemsetAsync(a.sum, 0, 2 * b8 + b4, ctx->stream));
+    k_fused_accum<FS><<<grid, THREADS, 0, ctx->stream>>>(fs, val, n, h[0], a);
+    RFB_CHECK_LAUNCH(ctx);
+    k_max_first<<<rfb_grid_for(ctx, range, THREADS, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(a.first_row, range, mm);
+    RFB_CHECK_LAUNCH(ctx);
+    i64 limit = 0;
+    rc = d2h_sync(ctx, &limit, mm + 2, 8);
+    if (rc) return rc;
+    const i64 tiles = (limit + scan::RowTile<NUM_J>::TILE - 1) / scan::RowTile<NUM_J>::TILE;
+    scan::TileCtl ctl;
+    rc = scan::prepare_tiles(ctx, (char *)w + 3 * b8 + b4, tiles, ctx->h_count, &ctl);
+    if (rc) return rc;
+    k_fused_emit<FS><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(fs, limit, h[0], a, max_groups, out_keys, out_sums, out_counts, ctl);
+    RFB_CHECK_LAUNCH(ctx);
+    RFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *groups = *(volatile i64 *)ctx->h_count;
+    if (*groups > max_groups) {
+        rfb_set_error("fused group-by: %lld groups exceed the output capacity %lld", (long long)*groups, (long long)max_groups);
+        return RFB_ERR_ARG;
+    }
+    return RFB_OK;
+}
+
+template <typename K, typename P>
+int fused_pred(rfb_ctx_t *ctx, const void *keys, const void *pred, PredRange pr, const i64 *val, i64 n, i64 max_groups, i64 *ok,
+               i64 *os, i64 *oc, i64 *groups) {
+    FusedSrc<K, P, true> fs{(const K *)keys, (const P *)pred, pr};
+    return fused_run(ctx, fs, val, n, max_groups, ok, os, oc, groups);
+}
+
+template <typename K>
+int fused_key(rfb_ctx_t *ctx, const void *keys, int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k, const i64 *val,
+              i64 n, i64 max_groups, i64 *ok, i64 *os, i64 *oc, i64 *groups) {
+    if (!pred) {
+        FusedSrc<K, i64, false> fs{(const K *)keys, nullptr, PredRange{0, 0, 0}};
+        return fused_run(ctx, fs, val, n, max_groups, ok, os, oc, groups);
+    }
+    PredRange pr;
+    if (!rfb_make_pred(cmp_op, pred_type, k, &pr)) { rfb_set_error("fused group-by: unsupported predicate types"); return RFB_ERR_TYPE; }
+    switch (rfb_kind_of(pred_type)) {
+        case K_I32: return fused_pred<K, i32>(ctx, keys, pred, pr, val, n, max_groups, ok, os, oc, groups);
+        case K_I64: return fused_pred<K, i64>(ctx, keys, pred, pr, val, n, max_groups, ok, os, oc, groups);
+        case K_F64: return fused_pred<K, f64>(ctx, keys, pred, pr, val, n, max_groups, ok, os, oc, groups);
+        default: rfb_set_error("fused group-by: unsupported predicate column type %d", pred_type); return RFB_ERR_TYPE;
+    }
+}
+
+}  // namespace
+
+extern "C" int rfb_group_sum_count_dev(rfb_ctx_t *ctx, int key_type, const void *keys, const int64_t *val, int64_t n,
+                                       int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k,
+                                       int64_t max_groups, int64_t *out_keys, int64_t *out_sums, int64_t *out_counts,
+                                       int64_t *groups) {
+    RFB_ARG(ctx && groups && n >= 0 && max_groups >= 0 && ((keys && val) || n == 0) && (!pred || k), "rfb_group_sum_count_dev");
+    RFB_ARG((out_keys && out_sums && out_counts) || max_groups == 0, "rfb_group_sum_count_dev: outputs");
+    *groups = 0;
+    if (n == 0) return RFB_OK;
+    switch (rfb_kind_of(key_type)) {
+        case K_I32: return fused_key<i32>(ctx, keys, cmp_op, pred_type, pred, k, val, n, max_groups, out_keys, out_sums, out_counts, groups);
+        case K_I64: return fused_key<i64>(ctx, keys, cmp_op, pred_type, pred, k, val, n, max_groups, out_keys, out_sums, out_counts, groups);
+        default: rfb_set_error("fused group-by: key type %d (I32 or I64 keys)", key_type); return RFB_ERR_TYPE;
+    }
+}

@@ -103,7 +103,6 @@ k_map1(const X *__restrict__ x, O *__restrict__ out, i64 n, bool vec_ok, F f) {
     for (i64 r = nvec + (i64)blockIdx.x * THREADS + threadIdx.x; r < n; r += (i64)gridDim.x * THREADS) out[r] = f(ld_stream(x + r));
 }
 
-inline bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
 
 template <typename X, typename Y, typename O, bool XA, bool YA, typename F>
 int launch_map2(rfb_ctx_t *ctx, const void *x, X xa, const void *y, Y ya, void *out, i64 n, F f) {

@@ -1,0 +1,242 @@
+// k_select.cu — selection vectors and gathers (sm_100a).
+//
+//   rfb_where_dev       ray_where -> ops_where: byte mask -> ascending i64 row ids   (reference core/ops.c:255-273,
+//                       two sequential passes on one thread there)
+//   rfb_cmp_where_dev   ray_where(ray_<cmp>(x, k)) without ever writing the mask
+//   rfb_gather_dev      filter_collect -> at_ids: out[i] = col[ids[i]]              (core/rayforce.c:1036-1159)
+//
+// Compaction is ONE pass: a chained scan with decoupled look-back.  Tiles take their index from an atomic ticket (so a
+// tile only ever waits on tiles that already started), each CTA counts its selected rows with warp ballots, publishes
+// (AGGREGATE | count) in a 64-bit status word, walks back over its predecessors' words 32 at a time until it meets an
+// INCLUSIVE one, publishes its own inclusive prefix and then writes its row ids at that offset.  Order is preserved:
+// within a warp the rank of a row is a popcount over the ballot masks of lower rows.  Traffic: mask bytes (or the 8-byte
+// predicate column) read once + 8 bytes written per selected row.
+#include "rfb_scan.cuh"
+
+namespace {
+
+using scan::THREADS;
+using scan::WARPS;
+using scan::TileCtl;
+using scan::TileSmem;
+constexpr int BLOCKS_PER_SM = 4;
+
+// ---- byte mask -> ids.  Lane owns 16 consecutive mask bytes per step (one 128-bit load), J steps per tile.
+constexpr int MASK_J = 4;
+constexpr int MASK_TILE = THREADS * 16 * MASK_J;  // 16384 rows per tile
+
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_where_mask(const u8 *__restrict__ mask, i64 n, i64 *__restrict__ ids, TileCtl ctl) {
+    __shared__ TileSmem sm;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 tile = scan::take_tile(ctl, sm);
+    const i64 wbase = (i64)tile * MASK_TILE + (i64)warp * (32 * 16 * MASK_J);
+    u32 bits[MASK_J];    // this lane's 16 flags per step
+    u32 excl[MASK_J];    // selected rows of this warp before this lane's first row in step j
+    u32 warp_total = 0;
+#pragma unroll
+    for (int j = 0; j < MASK_J; j++) {
+        const i64 r0 = wbase + ((i64)j * 32 + lane) * 16;
+        u32 b = 0;
+        if (r0 + 16 <= n) {
+            Vec16<u8> v;
+            v.raw = ld_stream16(mask + r0);
+#pragma unroll
+            for (int e = 0; e < 16; e++) b |= (v.e[e] != 0 ? 1u : 0u) << e;
+        } else {
+            for (int e = 0; e < 16; e++)
+                if (r0 + e < n && mask[r0 + e] != 0) b |= 1u << e;
+        }
+        bits[j] = b;
+        u32 c = __popc(b), incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        excl[j] = warp_total + incl - c;
+        warp_total += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    const u64 obase = scan::tile_offsets(ctl, tile, warp_total, sm);
+#pragma unroll
+    for (int j = 0; j < MASK_J; j++) {
+        const i64 r0 = wbase + ((i64)j * 32 + lane) * 16;
+        i64 *o = ids + obase + excl[j];
+        u32 b = bits[j];
+        while (b) {
+            const int e = __ffs(b) - 1;
+            b &= b - 1;
+            *o++ = r0 + e;
+        }
+    }
+}
+
+// ---- predicate on a typed column -> ids.  Lane owns R = 16/sizeof(P) consecutive rows per step.
+template <typename P> struct CmpTile {
+    static constexpr int R = 16 / (int)sizeof(P);
+    static constexpr int J = 8;
+    static constexpr int WROWS = 32 * R * J;
+    static constexpr int TILE = WARPS * WROWS;
+};
+
+template <typename P>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_where_cmp(const P *__restrict__ x, PredRange pr, i64 n, bool vec_ok, i64 *__restrict__ ids, TileCtl ctl) {
+    constexpr int R = CmpTile<P>::R, J = CmpTile<P>::J;
+    __shared__ TileSmem sm;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 tile = scan::take_tile(ctl, sm);
+    const i64 wbase = (i64)tile * CmpTile<P>::TILE + (i64)warp * CmpTile<P>::WROWS;
+    Vec16<P> v[J];
+    const bool full = vec_ok && wbase + CmpTile<P>::WROWS <= n;
+    if (full) {
+#pragma unroll
+        for (int j = 0; j < J; j++) v[j].raw = ld_stream16(x + wbase + ((i64)j * 32 + lane) * R);
+    } else {
+#pragma unroll
+        for (int j = 0; j < J; j++)
+#pragma unroll
+            for (int e = 0; e < R; e++) {
+                const i64 r = wbase + ((i64)j * 32 + lane) * R + e;
+                v[j].e[e] = r < n ? x[r] : P();
+            }
+    }
+    u32 bits[J], excl[J], warp_total = 0;
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+        u32 b = 0;
+#pragma unroll
+        for (int e = 0; e < R; e++) {
+            const i64 r = wbase + ((i64)j * 32 + lane) * R + e;
+            const bool sel = (full || r < n) && pred_test(pred_key<P>(v[j].e[e]), pr);
+            b |= (sel ? 1u : 0u) << e;
+        }
+        bits[j] = b;
+        // rank of this lane's first row: selected rows in lower lanes (any element), via one ballot per element
+        u32 before = 0, tot = 0;
+#pragma unroll
+        for (int e = 0; e < R; e++) {
+            const u32 m = __ballot_sync(0xffffffffu, (b >> e) & 1u);
+            before += __popc(m & ((1u << lane) - 1u));
+            tot += __popc(m);
+        }
+        excl[j] = warp_total + before;
+        warp_total += tot;
+    }
+    const u64 obase = scan::tile_offsets(ctl, tile, warp_total, sm);
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+        const i64 r0 = wbase + ((i64)j * 32 + lane) * R;
+        i64 *o = ids + obase + excl[j];
+#pragma unroll
+        for (int e = 0; e < R; e++)
+            if ((bits[j] >> e) & 1u) *o++ = r0 + e;
+    }
+}
+
+int prepare_tiles(rfb_ctx_t *ctx, i64 tiles, TileCtl *ctl) {
+    void *w;
+    int rc = rfb_ensure_work(ctx, scan::tiles_bytes(tiles), &w);
+    if (rc) return rc;
+    return scan::prepare_tiles(ctx, w, tiles, ctx->h_count, ctl);
+}
+
+int finish_count(rfb_ctx_t *ctx, i64 *count) {
+    RFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *count = *(volatile i64 *)ctx->h_count;
+    return RFB_OK;
+}
+
+template <typename P>
+int where_cmp_t(rfb_ctx_t *ctx, const void *x, PredRange pr, i64 n, i64 *ids) {
+    const i64 tiles = (n + CmpTile<P>::TILE - 1) / CmpTile<P>::TILE;
+    TileCtl ctl;
+    int rc = prepare_tiles(ctx, tiles, &ctl);
+    if (rc) return rc;
+    k_where_cmp<P><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>((const P *)x, pr, n, aligned16(x), ids, ctl);
+    RFB_CHECK_LAUNCH(ctx);
+    return RFB_OK;
+}
+
+// ---- gather
+template <typename T>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_gather(const T *__restrict__ col, const i64 *__restrict__ ids, i64 m, T *__restrict__ out) {
+    constexpr int UNROLL = 8;
+    const i64 stride = (i64)gridDim.x * THREADS;
+    i64 i = (i64)blockIdx.x * THREADS + threadIdx.x;
+    for (; i + (UNROLL - 1) * stride < m; i += UNROLL * stride) {
+        i64 id[UNROLL];
+        T v[UNROLL];
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) id[j] = ld_stream(ids + i + j * stride);
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) v[j] = __ldg(col + id[j]);
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) __stcs(out + i + j * stride, v[j]);
+    }
+    for (; i < m; i += stride) out[i] = __ldg(col + ld_stream(ids + i));
+}
+
+template <typename T> int gather_t(rfb_ctx_t *ctx, const void *col, const i64 *ids, i64 m, void *out) {
+    const int grid = rfb_grid_for(ctx, m, THREADS * 8, BLOCKS_PER_SM * 2);
+    k_gather<T><<<grid, THREADS, 0, ctx->stream>>>((const T *)col, ids, m, (T *)out);
+    RFB_CHECK_LAUNCH(ctx);
+    return RFB_OK;
+}
+
+}  // namespace
+
+extern "C" int rfb_where_dev(rfb_ctx_t *ctx, const uint8_t *mask, int64_t n, int64_t *ids, int64_t *count) {
+    RFB_ARG(ctx && count && n >= 0 && ((mask && ids) || n == 0), "rfb_where_dev");
+    *count = 0;
+    if (n == 0) return RFB_OK;
+    TileCtl ctl;
+    if (aligned16(mask)) {
+        const i64 tiles = (n + MASK_TILE - 1) / MASK_TILE;
+        int rc = prepare_tiles(ctx, tiles, &ctl);
+        if (rc) return rc;
+        k_where_mask<<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(mask, n, ids, ctl);
+        RFB_CHECK_LAUNCH(ctx);
+    } else {
+        // unaligned payload: treat the bytes as a U8 column and select != 0 with the typed kernel's scalar path
+        PredRange pr = make_pred_range(RFB_NE, key_of_i64(0));
+        const i64 tiles = (n + CmpTile<u8>::TILE - 1) / CmpTile<u8>::TILE;
+        int rc = prepare_tiles(ctx, tiles, &ctl);
+        if (rc) return rc;
+        k_where_cmp<u8><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(mask, pr, n, false, ids, ctl);
+        RFB_CHECK_LAUNCH(ctx);
+    }
+    return finish_count(ctx, count);
+}
+
+extern "C" int rfb_cmp_where_dev(rfb_ctx_t *ctx, int op, int type, const void *x, int64_t n, const rfb_scalar_t *k,
+                                 int64_t *ids, int64_t *count) {
+    RFB_ARG(ctx && count && k && n >= 0 && ((x && ids) || n == 0), "rfb_cmp_where_dev");
+    *count = 0;
+    PredRange pr;
+    if (!rfb_make_pred(op, type, k, &pr)) { rfb_set_error("cmp+where: unsupported column/constant types %d, %d", type, k->type); return RFB_ERR_TYPE; }
+    if (n == 0) return RFB_OK;
+    int rc;
+    switch (rfb_kind_of(type)) {
+        case K_U8: rc = where_cmp_t<u8>(ctx, x, pr, n, ids); break;
+        case K_I16: rc = where_cmp_t<i16>(ctx, x, pr, n, ids); break;
+        case K_I32: rc = where_cmp_t<i32>(ctx, x, pr, n, ids); break;
+        case K_I64: rc = where_cmp_t<i64>(ctx, x, pr, n, ids); break;
+        default: rc = where_cmp_t<f64>(ctx, x, pr, n, ids); break;
+    }
+    if (rc) return rc;
+    return finish_count(ctx, count);
+}
+
+extern "C" int rfb_gather_dev(rfb_ctx_t *ctx, int type, const void *col, const int64_t *ids, int64_t m, void *out) {
+    RFB_ARG(ctx && m >= 0 && ((col && ids && out) || m == 0), "rfb_gather_dev");
+    if (m == 0) return RFB_OK;
+    switch (rfb_type_size(type)) {
+        case 1: return gather_t<u8>(ctx, col, ids, m, out);
+        case 2: return gather_t<i16>(ctx, col, ids, m, out);
+        case 4: return gather_t<i32>(ctx, col, ids, m, out);
+        case 8: return gather_t<i64>(ctx, col, ids, m, out);
+        default: rfb_set_error("gather: unsupported type %d", type); return RFB_ERR_TYPE;
+    }
+}

@@ -1,0 +1,274 @@
+// k_sort.cu — key sort (sm_100a): stable LSD radix sort returning the i64 permutation.
+//
+//   rfb_sort_dev   ray_sort_asc / ray_sort_desc (reference core/sort.c:183-428 ascending, :481-689 descending; single
+//                  threaded there: counting sort for 8/16-bit keys, 16-bit-digit LSD radix for 32/64-bit keys)
+//
+// Any stable sort on the reference's key order yields the same permutation, so the device is free to pick its own digit
+// width: 8-bit digits, least significant first.  Keys are mapped to unsigned integers exactly like the reference
+// (core/sort.c:266-285,313): integers flip the sign bit (nulls first), doubles flip sign / all bits with every NaN -> 0
+// (NaN first, -0.0 before +0.0); descending sorts the complemented key, which keeps equal keys in original order.
+//
+// Per pass:  HIST    G persistent CTAs, CTA b owns the contiguous chunk b of the current sequence: 256-bin counts
+//            SCAN    exclusive scan of the digit-major (256 x G) count matrix  -> first output slot of (digit, chunk)
+//            SCATTER CTA b walks its chunk tile by tile (2048 rows): warp-level multisplit (match.any) ranks rows of equal
+//                    digit in (warp, step, lane) order, warp counts are scanned across the CTA, and a running per-digit
+//                    base carried in shared memory keeps tiles of one chunk in order => stable.
+// One census kernel up front takes the bitwise OR and AND of all keys; a pass whose digit is constant over the column is skipped
+// (e.g. the upper bytes of small integers).  The first executed pass reads the typed column and synthesises the row ids;
+// the last one writes only the permutation.  HBM traffic per executed pass: 8N (hist) + 16N read + 16N written.
+#include "rfb_common.cuh"
+
+namespace {
+
+constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+constexpr int ITEMS = 8;
+constexpr int TILE = THREADS * ITEMS;  // 2048
+constexpr int RADIX = 256;
+
+template <typename T> __device__ __forceinline__ u64 sortable(T v);
+template <> __device__ __forceinline__ u64 sortable<u8>(u8 v) { return v; }
+template <> __device__ __forceinline__ u64 sortable<i16>(i16 v) { return (u64)(unsigned short)((unsigned short)v ^ 0x8000u); }
+template <> __device__ __forceinline__ u64 sortable<i32>(i32 v) { return (u64)((u32)v ^ 0x80000000u); }
+template <> __device__ __forceinline__ u64 sortable<i64>(i64 v) { return (u64)v ^ 0x8000000000000000ULL; }
+template <> __device__ __forceinline__ u64 sortable<f64>(f64 v) { return f64_sort_key(v); }
+
+// where a pass reads its (key, row id) pairs from
+template <typename T> struct ColumnSrc {      // first pass: the typed column itself
+    const T *col;
+    u64 flip;  // 0 ascending, all-ones (within the key width) descending
+    __device__ __forceinline__ u64 key(i64 i) const { return sortable<T>(ld_stream(col + i)) ^ flip; }
+    __device__ __forceinline__ i64 val(i64 i) const { return i; }
+};
+struct PairSrc {                              // later passes: the previous pass's output
+    const u64 *keys;
+    const i64 *vals;
+    __device__ __forceinline__ u64 key(i64 i) const { return ld_stream(keys + i); }
+    __device__ __forceinline__ i64 val(i64 i) const { return ld_stream(vals + i); }
+};
+
+// ---- census: bitwise OR and AND of all keys.  A pass whose digit is the same in every key (OR byte == AND byte) leaves
+// the sequence unchanged and is skipped.
+template <typename T>
+__global__ void __launch_bounds__(THREADS) k_census(ColumnSrc<T> src, i64 n, unsigned long long *or_and) {
+    u64 o = 0, a = ~0ULL;
+    constexpr int U = 4;
+    const i64 stride = (i64)gridDim.x * THREADS;
+    i64 i = (i64)blockIdx.x * THREADS + threadIdx.x;
+    for (; i + (U - 1) * stride < n; i += U * stride) {
+        u64 k[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) k[j] = src.key(i + j * stride);
+#pragma unroll
+        for (int j = 0; j < U; j++) { o |= k[j]; a &= k[j]; }
+    }
+    for (; i < n; i += stride) { const u64 k = src.key(i); o |= k; a &= k; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        o |= __shfl_xor_sync(0xffffffffu, o, d);
+        a &= __shfl_xor_sync(0xffffffffu, a, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicOr(&or_and[0], (unsigned long long)o);
+        atomicAnd(&or_and[1], (unsigned long long)a);
+    }
+}
+
+// ---- per-chunk digit histogram
+template <typename Src>
+__global__ void __launch_bounds__(THREADS) k_hist(Src src, i64 n, i64 chunk, int shift, u32 *bh /* [256][G] */) {
+    __shared__ u32 h[RADIX];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const i64 lo = (i64)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    for (i64 i = lo + threadIdx.x; i < hi; i += THREADS) atomicAdd(&h[(src.key(i) >> shift) & 255], 1u);
+    __syncthreads();
+    bh[(i64)threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
+}
+
+// ---- exclusive scan of the (256 x G) matrix in row-major (digit-major) order; one CTA
+__global__ void __launch_bounds__(1024) k_scan_counts(const u32 *bh, i64 *offs, int total) {
+    __shared__ i64 wsum[32];
+    __shared__ i64 carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < total; base += 1024) {
+        const int i = base + threadIdx.x;
+        const i64 v = i < total ? (i64)bh[i] : 0;
+        i64 incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const i64 o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            i64 w = wsum[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const i64 o = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            wsum[lane] = wi - w;
+        }
+        __syncthreads();
+        const i64 c = carry;
+        if (i < total) offs[i] = c + wsum[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + wsum[31] + incl;
+        __syncthreads();
+    }
+}
+
+// ---- stable scatter of one chunk
+template <typename Src, bool WRITE_KEYS>
+__global__ void __launch_bounds__(THREADS)
+k_scatter(Src src, i64 n, i64 chunk, int shift, const i64 *__restrict__ offs /* [256][G] */, u64 *__restrict__ keys_out,
+          i64 *__restrict__ vals_out) {
+    __shared__ u32 whist[WARPS][RADIX];
+    __shared__ i64 base[RADIX];    // next free output slot of each digit for this chunk
+    __shared__ i64 tbase[RADIX];   // ... at the start of the current tile
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lt = (1u << lane) - 1u;
+    base[threadIdx.x] = offs[(i64)threadIdx.x * gridDim.x + blockIdx.x];
+    const i64 lo = (i64)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    for (i64 t0 = lo; t0 < hi; t0 += TILE) {
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) whist[w][threadIdx.x] = 0;
+        __syncthreads();
+        u64 key[ITEMS];
+        i64 val[ITEMS];
+        u32 rank[ITEMS];
+        const i64 wb = t0 + (i64)warp * (32 * ITEMS);
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            const i64 i = wb + j * 32 + lane;
+            const bool ok = i < hi;
+            key[j] = ok ? src.key(i) : ~0ULL;
+            val[j] = ok ? src.val(i) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            const i64 i = wb + j * 32 + lane;
+            const bool ok = i < hi;
+            const u32 d = (u32)(key[j] >> shift) & 255u;
+            const u32 vmask = __ballot_sync(0xffffffffu, ok);
+            const u32 peers = __match_any_sync(0xffffffffu, ok ? d : 256u + (u32)lane) & vmask;
+            const u32 prior = whist[warp][d];
+            __syncwarp();
+            if (ok && (peers & lt) == 0) whist[warp][d] = prior + __popc(peers);   // lowest peer lane publishes
+            __syncwarp();
+            rank[j] = prior + __popc(peers & lt);
+        }
+        __syncthreads();
+        {   // thread d: scan digit d's counts over the warps, advance the running base
+            const int d = threadIdx.x;
+            u32 s = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) { const u32 c = whist[w][d]; whist[w][d] = s; s += c; }
+            const i64 b = base[d];
+            tbase[d] = b;
+            base[d] = b + s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            const i64 i = wb + j * 32 + lane;
+            if (i < hi) {
+                const u32 d = (u32)(key[j] >> shift) & 255u;
+                const i64 pos = tbase[d] + whist[warp][d] + rank[j];
+                if (WRITE_KEYS) keys_out[pos] = key[j];
+                vals_out[pos] = val[j];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_iota(i64 *p, i64 n) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) p[i] = i;
+}
+
+inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+template <typename Src>
+int run_pass(rfb_ctx_t *ctx, Src src, i64 n, int G, i64 chunk, int shift, u32 *bh, i64 *offs, u64 *keys_out, i64 *vals_out, bool last) {
+    k_hist<Src><<<G, THREADS, 0, ctx->stream>>>(src, n, chunk, shift, bh);
+    RFB_CHECK_LAUNCH(ctx);
+    k_scan_counts<<<1, 1024, 0, ctx->stream>>>(bh, offs, RADIX * G);
+    RFB_CHECK_LAUNCH(ctx);
+    if (last) k_scatter<Src, false><<<G, THREADS, 0, ctx->stream>>>(src, n, chunk, shift, offs, keys_out, vals_out);
+    else k_scatter<Src, true><<<G, THREADS, 0, ctx->stream>>>(src, n, chunk, shift, offs, keys_out, vals_out);
+    RFB_CHECK_LAUNCH(ctx);
+    return RFB_OK;
+}
+
+template <typename T>
+int sort_t(rfb_ctx_t *ctx, const void *x, i64 n, int descending, i64 *perm) {
+    constexpr int NPASS = (int)sizeof(T);
+    const u64 width_mask = NPASS == 8 ? ~0ULL : ((1ULL << (8 * NPASS)) - 1);
+    ColumnSrc<T> col{(const T *)x, descending ? width_mask : 0ULL};
+    // persistent chunks: G CTAs, chunk a multiple of the tile
+    int G = ctx->sm_count * 8;
+    i64 chunk = ((n + G - 1) / G + TILE - 1) / TILE * TILE;
+    G = (int)((n + chunk - 1) / chunk);
+    // workspace: census {or, and} | bh[256*G] u32 | offs[256*G] i64 | keysA[n] | keysB[n] | valsA[n]
+    const size_t b_census = 256, b_bh = align256((size_t)RADIX * G * 4), b_offs = align256((size_t)RADIX * G * 8),
+                 b_n = align256((size_t)n * 8);
+    void *w;
+    int rc = rfb_ensure_work(ctx, b_census + b_bh + b_offs + 3 * b_n, &w);
+    if (rc) return rc;
+    unsigned long long *census = (unsigned long long *)w;
+    u32 *bh = (u32 *)((char *)w + b_census);
+    i64 *offs = (i64 *)((char *)w + b_census + b_bh);
+    u64 *keysA = (u64 *)((char *)w + b_census + b_bh + b_offs), *keysB = (u64 *)((char *)keysA + b_n);
+    i64 *valsA = (i64 *)((char *)keysB + b_n);
+    RFB_CUDA(cudaMemsetAsync(census, 0, 8, ctx->stream));
+    RFB_CUDA(cudaMemsetAsync(census + 1, 0xFF, 8, ctx->stream));
+    k_census<T><<<rfb_grid_for(ctx, n, THREADS * 4, 4), THREADS, 0, ctx->stream>>>(col, n, census);
+    RFB_CHECK_LAUNCH(ctx);
+    unsigned long long hc[2];
+    RFB_CUDA(cudaMemcpyAsync(hc, census, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    RFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    int passes[8], np = 0;
+    for (int p = 0; p < NPASS; p++)
+        if ((((hc[0] ^ hc[1]) >> (8 * p)) & 255ULL) != 0) passes[np++] = p;
+    if (np == 0) {  // all keys equal: the identity permutation (stable)
+        k_iota<<<rfb_grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(perm, n);
+        RFB_CHECK_LAUNCH(ctx);
+        return RFB_OK;
+    }
+    // ping-pong so that the LAST pass lands in `perm`: vals alternate between perm and valsA
+    u64 *kin = nullptr, *kout = keysA;
+    i64 *vin = nullptr;
+    i64 *vout = (np % 2 == 1) ? perm : valsA;
+    for (int q = 0; q < np; q++) {
+        const bool last = (q == np - 1);
+        const int shift = 8 * passes[q];
+        if (q == 0) rc = run_pass(ctx, col, n, G, chunk, shift, bh, offs, kout, vout, last);
+        else rc = run_pass(ctx, PairSrc{kin, vin}, n, G, chunk, shift, bh, offs, kout, vout, last);
+        if (rc) return rc;
+        kin = kout;
+        kout = (kout == keysA) ? keysB : keysA;
+        vin = vout;
+        vout = (vout == perm) ? valsA : perm;
+    }
+    return RFB_OK;
+}
+
+}  // namespace
+
+extern "C" int rfb_sort_dev(rfb_ctx_t *ctx, int type, const void *x, int64_t n, int descending, int64_t *perm) {
+    RFB_ARG(ctx && n >= 0 && ((x && perm) || n == 0), "rfb_sort_dev");
+    if (type == RFB_SYMBOL || !rfb_kind_of(type)) { rfb_set_error("sort: unsupported type %d", type); return RFB_ERR_TYPE; }
+    if (n == 0) return RFB_OK;
+    switch (rfb_kind_of(type)) {
+        case K_U8: return sort_t<u8>(ctx, x, n, descending, perm);
+        case K_I16: return sort_t<i16>(ctx, x, n, descending, perm);
+        case K_I32: return sort_t<i32>(ctx, x, n, descending, perm);
+        case K_I64: return sort_t<i64>(ctx, x, n, descending, perm);
+        default: return sort_t<f64>(ctx, x, n, descending, perm);
+    }
+}

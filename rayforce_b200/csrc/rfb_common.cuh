@@ -34,6 +34,7 @@ struct rfb_ctx {
     void *d_scratch;
     size_t scratch_bytes;
     void *h_result;            // mapped pinned host memory, RFB_RESULT_SLOTS rfb_fold_t slots: kernels write results here
+    i64 *h_count;              // mapped pinned: small integer results (selection counts, group counts)
     int result_slot;           // slot the next fold launch reports into (host layer: one per chunk)
     void *result_override;     // when set (rfb_ctx_set_result_ptr) fold kernels report there instead (device-visible memory)
     // growable device workspace (sort / group temporaries)
@@ -230,6 +231,78 @@ template <typename T, typename Op> __device__ __forceinline__ T block_reduce(T v
     }
     return v;
 }
+
+// ------------------------------------------------------------------ predicates against a constant
+
+// predicate = unsigned range test on an order-preserving 64-bit key, optionally negated.
+// All six comparison operators against a constant reduce to it (see make_pred_range).
+struct PredRange {
+    u64 lo, span;
+    u32 negate;
+};
+
+__host__ __device__ __forceinline__ u64 key_of_i64(i64 x) { return (u64)x ^ 0x8000000000000000ULL; }
+// doubles: -0.0 == +0.0 must hold for comparisons (unlike the sort key), NaN is below everything and equals NaN
+__host__ __device__ __forceinline__ u64 key_of_f64(f64 x) { return f64_sort_key(x == 0.0 ? 0.0 : x); }
+
+template <typename P> __device__ __forceinline__ u64 pred_key(P x) {
+    if constexpr (Elem<P>::kind == K_F64) return key_of_f64(x);
+    else return key_of_i64(widen_i64(x));
+}
+
+__device__ __forceinline__ bool pred_test(u64 key, const PredRange &pr) { return ((key - pr.lo) <= pr.span) != (bool)pr.negate; }
+
+// scalar -> i64 (null-preserving) or f64
+static inline bool scalar_as_i64(const rfb_scalar_t *k, i64 *out) {
+    switch (rfb_kind_of(k->type)) {
+        case K_U8: *out = k->v.u8; return true;
+        case K_I16: *out = k->v.i16 == NULL_I16 ? NULL_I64 : (i64)k->v.i16; return true;
+        case K_I32: *out = k->v.i32 == NULL_I32 ? NULL_I64 : (i64)k->v.i32; return true;
+        case K_I64: *out = k->v.i64; return true;
+        default: return false;
+    }
+}
+static inline bool scalar_as_f64(const rfb_scalar_t *k, f64 *out) {
+    i64 t;
+    if (rfb_kind_of(k->type) == K_F64) { *out = k->v.f64; return true; }
+    if (!scalar_as_i64(k, &t)) return false;
+    *out = (rfb_kind_of(k->type) != K_U8 && t == NULL_I64) ? null_f64() : (f64)t;
+    return true;
+}
+
+// OP(x, k)  <=>  key(x) in [lo, lo+span] (xor negate)
+static inline PredRange make_pred_range(int op, u64 kk) {
+    PredRange pr;
+    const u64 MAXK = ~0ULL;
+    pr.negate = 0;
+    switch (op) {
+        case RFB_EQ: pr.lo = kk; pr.span = 0; break;
+        case RFB_NE: pr.lo = kk; pr.span = 0; pr.negate = 1; break;
+        case RFB_LE: pr.lo = 0; pr.span = kk; break;
+        case RFB_GE: pr.lo = kk; pr.span = MAXK - kk; break;
+        case RFB_LT: if (kk == 0) { pr.lo = 0; pr.span = MAXK; pr.negate = 1; } else { pr.lo = 0; pr.span = kk - 1; } break;
+        default /*GT*/: if (kk == MAXK) { pr.lo = 0; pr.span = MAXK; pr.negate = 1; } else { pr.lo = kk + 1; pr.span = MAXK - kk - 1; } break;
+    }
+    return pr;
+}
+
+// Build the range test for `OP(column, k)`; the constant is widened into the column's comparison domain (integers compare
+// as i64 with null = minimum, anything against F64 compares as f64).  Returns false for unsupported type mixes.
+static inline bool rfb_make_pred(int op, int col_type, const rfb_scalar_t *k, PredRange *pr) {
+    const int ck = rfb_kind_of(col_type);
+    if (op < RFB_EQ || op > RFB_GE || !ck || !k) return false;
+    if (ck == K_F64) {
+        f64 kv;
+        if (!scalar_as_f64(k, &kv)) return false;
+        *pr = make_pred_range(op, key_of_f64(kv));
+        return true;
+    }
+    i64 kv;
+    if (!scalar_as_i64(k, &kv)) return false;   // integer column vs F64 constant: handled by the mask path (rfb_cmp_dev)
+    *pr = make_pred_range(op, key_of_i64(kv));
+    return true;
+}
+static inline bool aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
 
 // splitmix64: the synthetic-column generator shared with the oracle (oracle/rf_oracle.c rfo_splitmix64)
 __host__ __device__ __forceinline__ u64 splitmix64(u64 seed, u64 i) {

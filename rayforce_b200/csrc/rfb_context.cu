@@ -74,8 +74,9 @@ int rfb_ctx_create(int device, rfb_ctx_t **out) {
     ctx->scratch_bytes = 1 << 16;
     RFB_CUDA(cudaMalloc(&ctx->d_scratch, ctx->scratch_bytes));
     RFB_CUDA(cudaMemset(ctx->d_scratch, 0, ctx->scratch_bytes));
-    RFB_CUDA(cudaHostAlloc(&ctx->h_result, RFB_RESULT_SLOTS * sizeof(rfb_fold_t), cudaHostAllocMapped | cudaHostAllocPortable));
-    memset(ctx->h_result, 0, RFB_RESULT_SLOTS * sizeof(rfb_fold_t));
+    RFB_CUDA(cudaHostAlloc(&ctx->h_result, RFB_RESULT_SLOTS * sizeof(rfb_fold_t) + 4096, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(ctx->h_result, 0, RFB_RESULT_SLOTS * sizeof(rfb_fold_t) + 4096);
+    ctx->h_count = (i64 *)((char *)ctx->h_result + RFB_RESULT_SLOTS * sizeof(rfb_fold_t));
     for (int i = 0; i < RFB_STAGE_BUFS; i++) {
         RFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
         RFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_kernel[i], cudaEventDisableTiming));

@@ -151,3 +151,128 @@ class Context:
         nb = C.c_int64(0)
         check(self.lib.rfb_fold_host(self.h, folds, type_, _hptr(x), x.shape[0], chunk_rows, C.byref(f), C.byref(nb)))
         return FoldResult(f, type_), nb.value
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Operator-exact device-layer building blocks.  Operands are torch CUDA tensors (vectors) or Python scalars (atoms).
+
+def _operand(x, t):
+    """-> (device pointer, length or -1, Scalar or None)"""
+    import torch
+    if isinstance(x, torch.Tensor):
+        return _dptr(x), x.shape[0], None
+    return 0, -1, Scalar.of(t, x)
+
+
+def _torch_dtype(t):
+    import torch
+    return {capi.B8: torch.uint8, capi.U8: torch.uint8, capi.I16: torch.int16, capi.I32: torch.int32, capi.DATE: torch.int32,
+            capi.TIME: torch.int32, capi.I64: torch.int64, capi.SYMBOL: torch.int64, capi.TIMESTAMP: torch.int64,
+            capi.F64: torch.float64}[t]
+
+
+def _sref(s):
+    return C.byref(s) if s is not None else None
+
+
+class _Ops:
+    """mixin for Context: ray_eq.., ray_where, filter_collect, ray_add.., index_group, aggr_*, ray_sort_* on device columns"""
+
+    def _empty(self, n, t):
+        import torch
+        with torch.cuda.device(self.device):
+            return torch.empty(max(n, 0), dtype=_torch_dtype(t), device="cuda:%d" % self.device)
+
+    def cmp(self, op, xt, x, yt, y):
+        """ray_eq/ne/lt/gt/le/ge: -> B8 mask (uint8 tensor)"""
+        xp, xn, xs = _operand(x, xt)
+        yp, yn, ys = _operand(y, yt)
+        n = xn if xn >= 0 else yn
+        mask = self._empty(n, capi.B8)
+        check(self.lib.rfb_cmp_dev(self.h, op, xt, xp, xn, _sref(xs), yt, yp, yn, _sref(ys), _dptr(mask)))
+        return mask
+
+    def where(self, mask):
+        """ray_where: B8 mask -> ascending i64 row ids"""
+        n = mask.shape[0]
+        ids = self._empty(n, capi.I64)
+        cnt = C.c_int64(0)
+        check(self.lib.rfb_where_dev(self.h, _dptr(mask), n, _dptr(ids), C.byref(cnt)))
+        return ids[:cnt.value]
+
+    def cmp_where(self, op, t, x, k):
+        n = x.shape[0]
+        ids = self._empty(n, capi.I64)
+        cnt = C.c_int64(0)
+        s = Scalar.of(t, k)
+        check(self.lib.rfb_cmp_where_dev(self.h, op, t, _dptr(x), n, C.byref(s), _dptr(ids), C.byref(cnt)))
+        return ids[:cnt.value]
+
+    def gather(self, t, col, ids):
+        """filter_collect / at_ids"""
+        out = self._empty(ids.shape[0], t)
+        check(self.lib.rfb_gather_dev(self.h, t, _dptr(col), _dptr(ids), ids.shape[0], _dptr(out)))
+        return out
+
+    def binop_type(self, op, xt, yt):
+        r = self.lib.rfb_binop_type(op, xt, yt)
+        if r < 0:
+            raise RfbError(r, "binop %d: unsupported operand types %d, %d" % (op, xt, yt))
+        return r
+
+    def binop(self, op, xt, x, yt, y):
+        """ray_add/sub/mul/div/fdiv/mod -> (tensor, result type)"""
+        ot = self.binop_type(op, xt, yt)
+        xp, xn, xs = _operand(x, xt)
+        yp, yn, ys = _operand(y, yt)
+        if xn >= 0 and yn >= 0 and xn != yn:
+            check(self.lib.rfb_binop_dev(self.h, op, xt, xp, xn, _sref(xs), yt, yp, yn, _sref(ys), None))
+        out = self._empty(xn if xn >= 0 else yn, ot)
+        check(self.lib.rfb_binop_dev(self.h, op, xt, xp, xn, _sref(xs), yt, yp, yn, _sref(ys), _dptr(out)))
+        return out, ot
+
+    def unop_f64(self, op, x):
+        out = self._empty(x.shape[0], capi.F64)
+        check(self.lib.rfb_unop_f64_dev(self.h, op, _dptr(x), x.shape[0], _dptr(out)))
+        return out
+
+    def group_i64(self, keys, filt=None):
+        """index_group on an I64 key column -> (group_ids, first_ids, GroupInfo)"""
+        n = keys.shape[0] if filt is None else filt.shape[0]
+        gids = self._empty(n, capi.I64)
+        firsts = self._empty(n, capi.I64)
+        info = capi.GroupInfo()
+        check(self.lib.rfb_group_i64_dev(self.h, _dptr(keys), _dptr(filt), n, _dptr(gids), _dptr(firsts), C.byref(info)))
+        return gids, firsts[:info.groups], info
+
+    def aggr(self, op, vt, val, gids, groups, filt=None):
+        """aggr_sum/min/max/count/avg -> (tensor[groups], result type)"""
+        ot = self.lib.rfb_aggr_type(op, vt)
+        if ot < 0:
+            raise RfbError(ot, "aggr %d: unsupported value type %d" % (op, vt))
+        out = self._empty(groups, ot)
+        check(self.lib.rfb_aggr_dev(self.h, op, vt, _dptr(val), _dptr(filt), _dptr(gids), gids.shape[0], groups, _dptr(out)))
+        self.sync()
+        return out, ot
+
+    def group_sum_count(self, key_type, keys, val, max_groups, cmp_op=None, pred_type=None, pred=None, k=None):
+        """fused select {s: (sum v) c: (count v) from t by k [where (cmp p k)]} -> (keys, sums, counts) tensors"""
+        n = keys.shape[0]
+        ok, osum, oc = (self._empty(max_groups, capi.I64) for _ in range(3))
+        g = C.c_int64(0)
+        s = Scalar.of(pred_type, k) if pred is not None else None
+        check(self.lib.rfb_group_sum_count_dev(self.h, key_type, _dptr(keys), _dptr(val), n, cmp_op or 0, pred_type or 0,
+                                               _dptr(pred), _sref(s), max_groups, _dptr(ok), _dptr(osum), _dptr(oc), C.byref(g)))
+        return ok[:g.value], osum[:g.value], oc[:g.value]
+
+    def sort(self, t, x, descending=False):
+        """ray_sort_asc / ray_sort_desc -> i64 permutation"""
+        perm = self._empty(x.shape[0], capi.I64)
+        check(self.lib.rfb_sort_dev(self.h, t, _dptr(x), x.shape[0], int(descending), _dptr(perm)))
+        self.sync()
+        return perm
+
+
+for _name, _fn in list(vars(_Ops).items()):
+    if not _name.startswith("__"):
+        setattr(Context, _name, _fn)

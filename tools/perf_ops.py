@@ -1,0 +1,117 @@
+#!/usr/bin/env python
+"""Per-operator device timings (CUDA events, column resident in HBM) for DESIGN.md's kernel table.
+    python tools/perf_ops.py [--rows 1000000000] [--reps 5]
+Prints one JSON object per operator: ms, algorithmic bytes, achieved GB/s and fraction of the measured HBM peak."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from rayforce_b200 import Context, capi  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=1_000_000_000)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    n = args.rows
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        peak = 6650.0
+    torch.cuda.set_device(0)
+    st = torch.cuda.Stream()
+    ctx = Context(0, stream=st.cuda_stream)
+    dev = "cuda:0"
+
+    def col(t, seed, modulus, offset=0, scale=1.0, null_every=0):
+        x = torch.empty(n, dtype={capi.I64: torch.int64, capi.I32: torch.int32, capi.F64: torch.float64}[t], device=dev)
+        ctx.fill_splitmix(t, x, n, seed, modulus, offset, null_every, scale)
+        return x
+
+    def timed(name, fn, alg_bytes, note=""):
+        if args.only and args.only not in name:
+            return
+        for _ in range(2):
+            fn()
+        ctx.sync()
+        ms = []
+        for _ in range(args.reps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(st)
+            fn()
+            e.record(st)
+            ctx.sync()
+            torch.cuda.synchronize()
+            ms.append(s.elapsed_time(e))
+        best = min(ms)
+        gbs = alg_bytes / (best * 1e-3) / 1e9
+        print(json.dumps({"op": name, "rows": n, "ms_best": round(best, 3), "ms_median": round(sorted(ms)[len(ms) // 2], 3),
+                          "grows_per_s": round(n / best / 1e6, 2), "alg_bytes": alg_bytes, "GBps": round(gbs, 1),
+                          "frac_of_measured_hbm": round(gbs / peak, 3), "note": note}), flush=True)
+
+    with torch.cuda.stream(st):
+        x = col(capi.I64, 42, 1 << 40)
+        K = 1 << 39
+        timed("sum_i64", lambda: ctx.fold(capi.F_SUM | capi.F_CNT, capi.I64, x, n), 8 * n)
+        timed("minmax_i64", lambda: ctx.fold(capi.F_MIN | capi.F_MAX, capi.I64, x, n), 8 * n)
+        timed("filter_sum_i64_same_col", lambda: ctx.filter_fold(capi.LT, capi.I64, x, K, capi.F_SUM | capi.F_CNT, capi.I64, x, n), 8 * n)
+        y = col(capi.I64, 43, 1 << 20)
+        timed("filter_sum_i64_two_cols", lambda: ctx.filter_fold(capi.LT, capi.I64, x, K, capi.F_SUM | capi.F_CNT, capi.I64, y, n), 16 * n)
+        timed("cmp_lt_mask", lambda: ctx.cmp(capi.LT, capi.I64, x, capi.I64, K), 9 * n, "8 B in + 1 B mask out")
+        mask = ctx.cmp(capi.LT, capi.I64, x, capi.I64, K)
+        sel = int(ctx.where(mask).shape[0])
+        timed("where_mask", lambda: ctx.where(mask), n + 8 * sel, "1 B in + 8 B per selected row out")
+        timed("cmp_where_fused", lambda: ctx.cmp_where(capi.LT, capi.I64, x, K), 8 * n + 8 * sel)
+        ids = ctx.where(mask)
+        del mask
+        timed("gather_i64", lambda: ctx.gather(capi.I64, x, ids), 24 * sel, "ids 8 + col 8 + out 8 per selected row")
+        timed("gather_fold_i64", lambda: ctx.gather_fold(capi.F_SUM | capi.F_CNT, capi.I64, x, ids, sel), 16 * sel)
+        del ids
+        timed("add_i64_vv", lambda: ctx.binop(capi.ADD, capi.I64, x, capi.I64, y), 24 * n)
+        timed("mul_i64_va", lambda: ctx.binop(capi.MUL, capi.I64, x, capi.I64, 3), 16 * n)
+        timed("div_i64_va", lambda: ctx.binop(capi.DIV, capi.I64, x, capi.I64, 7), 16 * n)
+        del x
+        # config 3: fp64 a*b+c -> avg
+        a, b, c = col(capi.F64, 1, 1 << 20, 0, float(1 << 20)), col(capi.F64, 2, 1 << 20, 0, float(1 << 20)), col(capi.F64, 3, 1 << 20, 0, float(1 << 20))
+        timed("fma_avg_f64_fused", lambda: ctx.fma_fold(capi.F_SUM | capi.F_CNT, a, b, c, n), 24 * n, "config 3 fused")
+
+        def unfused():
+            t1, _ = ctx.binop(capi.MUL, capi.F64, a, capi.F64, b)
+            t2, _ = ctx.binop(capi.ADD, capi.F64, t1, capi.F64, c)
+            return ctx.fold(capi.F_SUM | capi.F_CNT, capi.F64, t2, n)
+        timed("fma_avg_f64_operator_at_a_time", unfused, 24 * n, "same work as three operators (64 B/row of traffic)")
+        timed("floor_f64", lambda: ctx.unop_f64(capi.FLOOR, a), 16 * n)
+        del a, b, c
+        # config 4: group-by 1e5 keys sum + count
+        k32 = col(capi.I32, 7, 100_000)
+        timed("group_sum_count_i32keys_1e5", lambda: ctx.group_sum_count(capi.I32, k32, y, 100_000), 12 * n, "config 4 fused (2 passes over keys)")
+        timed("group_sum_count_i32keys_1e5_where", lambda: ctx.group_sum_count(capi.I32, k32, y, 100_000, capi.LT, capi.I64, y, 1 << 19), 12 * n)
+        del k32
+        k64 = col(capi.I64, 7, 100_000)
+        timed("group_sum_count_i64keys_1e5", lambda: ctx.group_sum_count(capi.I64, k64, y, 100_000), 16 * n)
+        timed("index_group_i64_dense_1e5", lambda: ctx.group_i64(k64), 16 * n, "scope + claim + number + assign (group_ids written)")
+        gids, firsts, info = ctx.group_i64(k64)
+        timed("aggr_sum_i64_1e5", lambda: ctx.aggr(capi.A_SUM, capi.I64, y, gids, info.groups), 16 * n)
+        timed("aggr_avg_i64_1e5", lambda: ctx.aggr(capi.A_AVG, capi.I64, y, gids, info.groups), 16 * n)
+        del gids, firsts, k64
+        k100 = col(capi.I64, 9, 100)
+        timed("group_sum_count_i64keys_100", lambda: ctx.group_sum_count(capi.I64, k100, y, 100), 16 * n, "low cardinality (H2O id1-like)")
+        del k100
+    if n <= 250_000_000 or args.only == "sort":
+        with torch.cuda.stream(st):
+            ks = col(capi.I64, 11, 0)
+            timed("sort_i64_full_width", lambda: ctx.sort(capi.I64, ks), 8 * n, "8 radix passes")
+            k40 = col(capi.I64, 11, 1 << 32)
+            timed("sort_i64_32bit_range", lambda: ctx.sort(capi.I64, k40), 8 * n, "4 passes (constant digits skipped)")
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
