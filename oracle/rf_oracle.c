@@ -143,13 +143,30 @@ static inline f64 ld_as_f64(int kind, const void *p, i64 i) {
 int64_t rfo_cmp(int op, int xt, const void *x, int64_t xn, int yt, const void *y, int64_t yn, uint8_t *out) {
     int kx = kind_of(xt), ky = kind_of(yt);
     if (!kx || !ky || op < RFO_EQ || op > RFO_GE) return RFO_ERR_TYPE;
+    /* the type matrix core/cmp.c:77-258: plain numerics I16/I32/I64/F64 mix freely; DATE/TIME/TIMESTAMP/SYMBOL only with
+     * themselves; B8/U8 are atom-only (:78-85), so any vector form is a type error.  DATE<->TIMESTAMP (:243-257, unit
+     * conversion) is not modelled. */
+    {
+        int px = (xt == RFO_I16 || xt == RFO_I32 || xt == RFO_I64 || xt == RFO_F64);
+        int py = (yt == RFO_I16 || yt == RFO_I32 || yt == RFO_I64 || yt == RFO_F64);
+        int same_special = (xt == yt) && (xt == RFO_DATE || xt == RFO_TIME || xt == RFO_TIMESTAMP || xt == RFO_SYMBOL);
+        int atoms_u8 = (xn < 0 && yn < 0) && (kx == K_U8 && ky == K_U8);
+        int date_ts = (xt == RFO_DATE && yt == RFO_TIMESTAMP) || (xt == RFO_TIMESTAMP && yt == RFO_DATE);
+        if (!((px && py) || same_special || atoms_u8 || date_ts)) return RFO_ERR_TYPE;
+    }
+    /* DATE vs TIMESTAMP: the date side goes through date_to_timestamp (core/ops.h:264, core/cmp.c:243-257) */
+    const i64 NANOS_FROM_DAY = 86400000000000LL;
+    i64 sx = (xt == RFO_DATE && yt == RFO_TIMESTAMP) ? NANOS_FROM_DAY : 1, sy = (yt == RFO_DATE && xt == RFO_TIMESTAMP) ? NANOS_FROM_DAY : 1;
     if (xn >= 0 && yn >= 0 && xn != yn) return RFO_ERR_LENGTH; /* core/cmp.c:625-627 */
     i64 n = xn >= 0 ? xn : (yn >= 0 ? yn : 1);
     int use_f = (kx == K_F64 || ky == K_F64);
     for (i64 i = 0; i < n; i++) {
         i64 ix = xn >= 0 ? i : 0, iy = yn >= 0 ? i : 0;
-        out[i] = use_f ? (u8)cmp_f64(op, ld_as_f64(kx, x, ix), ld_as_f64(ky, y, iy))
-                       : (u8)cmp_i64(op, ld_as_i64(kx, x, ix), ld_as_i64(ky, y, iy));
+        if (use_f) { out[i] = (u8)cmp_f64(op, ld_as_f64(kx, x, ix), ld_as_f64(ky, y, iy)); continue; }
+        i64 a = ld_as_i64(kx, x, ix), b = ld_as_i64(ky, y, iy);
+        if (a != RFO_NULL_I64) a = wmul64(a, sx);
+        if (b != RFO_NULL_I64) b = wmul64(b, sy);
+        out[i] = (u8)cmp_i64(op, a, b);
     }
     return n;
 }
@@ -468,20 +485,21 @@ int rfo_aggr(int op, int val_type, const void *val, const int64_t *filter, const
             for (i64 i = 0; i < len; i++) o[gid[i]]++;
             return RFO_OK;
         }
-        case RFO_SUM: /* core/aggr.c:1078-1105: STICKY null (ADD*, not FOLD_ADD*), accumulator in the value type */
+        case RFO_SUM: /* core/aggr.c:1078-1150: STICKY null (ADD*, not FOLD_ADD*), accumulator in the value type.
+                       * The driver aggr_sum (:1107-1150) accepts I16, I64 and F64 only (I32/DATE/TIME exist only as parted). */
             *out_type = val_type;
-            if (k == K_I64 && val_type == RFO_I64) {
+            if (val_type == RFO_I64) {
                 i64 *o = out; const i64 *v = val;
                 for (i64 g = 0; g < groups; g++) o[g] = 0;
                 for (i64 i = 0; i < len; i++) { i64 a = o[gid[i]], b = v[ROW(i)];
                     o[gid[i]] = (a == RFO_NULL_I64 || b == RFO_NULL_I64) ? RFO_NULL_I64 : wadd64(a, b); }
                 return RFO_OK;
             }
-            if (k == K_I32) {
-                i32 *o = out; const i32 *v = val;
+            if (val_type == RFO_I16) {
+                i16 *o = out; const i16 *v = val;
                 for (i64 g = 0; g < groups; g++) o[g] = 0;
-                for (i64 i = 0; i < len; i++) { i32 a = o[gid[i]], b = v[ROW(i)];
-                    o[gid[i]] = (a == RFO_NULL_I32 || b == RFO_NULL_I32) ? RFO_NULL_I32 : wadd32(a, b); }
+                for (i64 i = 0; i < len; i++) { i16 a = o[gid[i]], b = v[ROW(i)];
+                    o[gid[i]] = (a == RFO_NULL_I16 || b == RFO_NULL_I16) ? RFO_NULL_I16 : (i16)((uint16_t)a + (uint16_t)b); }
                 return RFO_OK;
             }
             if (k == K_F64) {
@@ -501,6 +519,12 @@ int rfo_aggr(int op, int val_type, const void *val, const int64_t *filter, const
                 for (i64 i = 0; i < len; i++) { i64 *a = &o[gid[i]]; *a = mn ? min_i64(*a, v[ROW(i)]) : max_i64(*a, v[ROW(i)]); }
                 return RFO_OK;
             }
+            if (val_type == RFO_I16) {
+                i16 *o = out; const i16 *v = val;
+                for (i64 g = 0; g < groups; g++) o[g] = mn ? (i16)0x7FFF : RFO_NULL_I16;
+                for (i64 i = 0; i < len; i++) { i16 *a = &o[gid[i]]; *a = mn ? min_i16(*a, v[ROW(i)]) : max_i16(*a, v[ROW(i)]); }
+                return RFO_OK;
+            }
             if (val_type == RFO_DATE || val_type == RFO_TIME) {
                 i32 *o = out; const i32 *v = val;
                 for (i64 g = 0; g < groups; g++) o[g] = mn ? RFO_INF_I32 : RFO_NULL_I32;
@@ -517,14 +541,15 @@ int rfo_aggr(int op, int val_type, const void *val, const int64_t *filter, const
         }
         case RFO_AVG: { /* core/aggr.c:1455-1875, 2013-2060: f64 sum of non-null values / non-null count */
             f64 *o = out; *out_type = RFO_F64;
-            if (!(val_type == RFO_I32 || val_type == RFO_DATE || val_type == RFO_TIME || val_type == RFO_I64 ||
-                  val_type == RFO_F64)) return RFO_ERR_TYPE;
+            if (!(val_type == RFO_I16 || val_type == RFO_I32 || val_type == RFO_DATE || val_type == RFO_TIME ||
+                  val_type == RFO_I64 || val_type == RFO_F64)) return RFO_ERR_TYPE;
             i64 *c = (i64 *)calloc((size_t)(groups > 0 ? groups : 1), 8);
             for (i64 g = 0; g < groups; g++) o[g] = 0.0;
             for (i64 i = 0; i < len; i++) {
                 i64 r = ROW(i), g = gid[i];
                 if (k == K_I64) { i64 v = ((const i64 *)val)[r]; if (v != RFO_NULL_I64) { o[g] += (f64)v; c[g]++; } }
                 else if (k == K_I32) { i32 v = ((const i32 *)val)[r]; if (v != RFO_NULL_I32) { o[g] += (f64)v; c[g]++; } }
+                else if (k == K_I16) { i16 v = ((const i16 *)val)[r]; if (v != RFO_NULL_I16) { o[g] += (f64)v; c[g]++; } }
                 else { f64 v = ((const f64 *)val)[r]; if (!isnan64(v)) { o[g] += v; c[g]++; } }
             }
             for (i64 g = 0; g < groups; g++) o[g] = c[g] == 0 ? null_f64() : o[g] / (f64)c[g];

@@ -359,6 +359,7 @@ int rfb_filter_fold_launch(rfb_ctx_t *ctx, int cmp_op, int pred_type, const void
     const int fs = foldset_of(folds), pk = rfb_kind_of(pred_type), vk = rfb_kind_of(val_type);
     if (cmp_op < RFB_EQ || cmp_op > RFB_GE) { rfb_set_error("bad comparison op %d", cmp_op); return RFB_ERR_ARG; }
     const bool same = (pred == val) && (pk == vk);
+    if (!rfb_cmp_types_ok(pred_type, k->type)) { rfb_set_error("filter+fold: unsupported comparison types %d, %d", pred_type, k->type); return RFB_ERR_TYPE; }
     if (pk == K_I32 || pk == K_I64) {
         i64 kv;
         if (!scalar_as_i64(k, &kv)) { rfb_set_error("filter+fold: integer column vs non-integer constant"); return RFB_ERR_TYPE; }

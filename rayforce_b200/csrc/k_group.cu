@@ -305,8 +305,10 @@ __device__ __forceinline__ f64 key_to_f64(u64 k) {  // inverse of f64_sort_key; 
     return bits_f64((k & 0x8000000000000000ULL) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k);
 }
 
-enum { AK_SUM_I64, AK_SUM_I32, AK_SUM_F64, AK_MIN_I64, AK_MAX_I64, AK_MIN_I32, AK_MAX_I32, AK_MIN_F64, AK_MAX_F64, AK_COUNT,
-       AK_AVG_I64, AK_AVG_I32, AK_AVG_F64 };
+enum { AK_SUM_I64, AK_SUM_I16, AK_SUM_F64, AK_MIN_I64, AK_MAX_I64, AK_MIN_I32, AK_MAX_I32, AK_MIN_I16, AK_MAX_I16, AK_MIN_F64,
+       AK_MAX_F64, AK_COUNT, AK_AVG_I64, AK_AVG_I32, AK_AVG_I16, AK_AVG_F64 };
+// 16-bit values have no native atomics: I16 sums accumulate mod 2^32 and min/max in 32-bit slots of the workspace, and the
+// finalise kernel narrows them (a sum mod 2^32 truncated to 16 bits is the reference's 16-bit wrapping sum)
 
 // acc: main accumulator array (typed per kind), aux: null flags (sum) or non-null counts (avg)
 template <int KIND, typename V>
@@ -317,8 +319,8 @@ k_aggr(const V *__restrict__ val, ValRow row, const i64 *__restrict__ gid, i64 n
     auto one = [&](i64 g, V v) {
         if constexpr (KIND == AK_SUM_I64) {
             if (v == NULL_I64) ((u32 *)aux)[g] = 1u; else atomicAdd((unsigned long long *)acc + g, (unsigned long long)v);
-        } else if constexpr (KIND == AK_SUM_I32) {
-            if (v == NULL_I32) ((u32 *)aux)[g] = 1u; else atomicAdd((u32 *)acc + g, (u32)v);
+        } else if constexpr (KIND == AK_SUM_I16) {
+            if (v == NULL_I16) ((u32 *)aux)[g] = 1u; else atomicAdd((u32 *)acc + g, (u32)(i32)v);
         } else if constexpr (KIND == AK_SUM_F64) {
             if (isnan64(v)) ((u32 *)aux)[g] = 1u; else atomicAdd((f64 *)acc + g, v);
         } else if constexpr (KIND == AK_MIN_I64) {
@@ -329,6 +331,10 @@ k_aggr(const V *__restrict__ val, ValRow row, const i64 *__restrict__ gid, i64 n
             if (v != NULL_I32) atomicMin((int *)acc + g, (int)v);
         } else if constexpr (KIND == AK_MAX_I32) {
             atomicMax((int *)acc + g, (int)v);
+        } else if constexpr (KIND == AK_MIN_I16) {
+            if (v != NULL_I16) atomicMin((int *)acc + g, (int)v);
+        } else if constexpr (KIND == AK_MAX_I16) {
+            atomicMax((int *)acc + g, (int)v);
         } else if constexpr (KIND == AK_MIN_F64) {
             if (!isnan64(v)) atomicMin((unsigned long long *)acc + g, (unsigned long long)f64_sort_key(v));
         } else if constexpr (KIND == AK_MAX_F64) {
@@ -337,6 +343,8 @@ k_aggr(const V *__restrict__ val, ValRow row, const i64 *__restrict__ gid, i64 n
             if (v != NULL_I64) { atomicAdd((unsigned long long *)acc + g, (unsigned long long)v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
         } else if constexpr (KIND == AK_AVG_I32) {
             if (v != NULL_I32) { atomicAdd((unsigned long long *)acc + g, (unsigned long long)(i64)v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
+        } else if constexpr (KIND == AK_AVG_I16) {
+            if (v != NULL_I16) { atomicAdd((unsigned long long *)acc + g, (unsigned long long)(i64)v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
         } else if constexpr (KIND == AK_AVG_F64) {
             if (!isnan64(v)) { atomicAdd((f64 *)acc + g, v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
         }
@@ -360,10 +368,11 @@ __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_count(const i64 *__r
 template <int KIND> __global__ void k_aggr_final(void *out, const void *acc, const void *aux, i64 groups) {
     for (i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (i64)gridDim.x * blockDim.x) {
         if constexpr (KIND == AK_SUM_I64) { if (((const u32 *)aux)[g]) ((i64 *)out)[g] = NULL_I64; }
-        else if constexpr (KIND == AK_SUM_I32) { if (((const u32 *)aux)[g]) ((i32 *)out)[g] = NULL_I32; }
+        else if constexpr (KIND == AK_SUM_I16) ((i16 *)out)[g] = ((const u32 *)aux)[g] ? NULL_I16 : (i16)(unsigned short)((const u32 *)acc)[g];
+        else if constexpr (KIND == AK_MIN_I16 || KIND == AK_MAX_I16) ((i16 *)out)[g] = (i16)((const i32 *)acc)[g];
         else if constexpr (KIND == AK_SUM_F64) { if (((const u32 *)aux)[g]) ((f64 *)out)[g] = null_f64(); }
         else if constexpr (KIND == AK_MIN_F64 || KIND == AK_MAX_F64) ((f64 *)out)[g] = key_to_f64(((const u64 *)acc)[g]);
-        else if constexpr (KIND == AK_AVG_I64 || KIND == AK_AVG_I32) {
+        else if constexpr (KIND == AK_AVG_I64 || KIND == AK_AVG_I32 || KIND == AK_AVG_I16) {
             const i64 c = ((const i64 *)aux)[g];
             ((f64 *)out)[g] = c == 0 ? null_f64() : __ddiv_rn((f64)((const i64 *)acc)[g], (f64)c);
         } else if constexpr (KIND == AK_AVG_F64) {
@@ -391,10 +400,11 @@ extern "C" int rfb_aggr_type(int op, int val_type) {
     if (!k) return RFB_ERR_TYPE;
     switch (op) {
         case RFB_A_COUNT: return (k == K_U8 || k == K_I16) ? RFB_ERR_TYPE : RFB_I64;
-        case RFB_A_SUM: return (val_type == RFB_I64 || k == K_I32 || k == K_F64) ? val_type : RFB_ERR_TYPE;
+        // the non-parted drivers' switch tables: aggr_sum core/aggr.c:1107-1150, aggr_max/min :1152-1315, aggr_avg :2013-2133
+        case RFB_A_SUM: return (val_type == RFB_I16 || val_type == RFB_I64 || k == K_F64) ? val_type : RFB_ERR_TYPE;
         case RFB_A_MIN: case RFB_A_MAX:
-            return (val_type == RFB_I64 || val_type == RFB_TIMESTAMP || val_type == RFB_DATE || val_type == RFB_TIME || val_type == RFB_F64) ? val_type : RFB_ERR_TYPE;
-        case RFB_A_AVG: return (k == K_I32 || val_type == RFB_I64 || k == K_F64) ? RFB_F64 : RFB_ERR_TYPE;
+            return (val_type == RFB_I16 || val_type == RFB_I64 || val_type == RFB_TIMESTAMP || val_type == RFB_DATE || val_type == RFB_TIME || val_type == RFB_F64) ? val_type : RFB_ERR_TYPE;
+        case RFB_A_AVG: return (val_type == RFB_I16 || k == K_I32 || val_type == RFB_I64 || k == K_F64) ? RFB_F64 : RFB_ERR_TYPE;
         default: return RFB_ERR_TYPE;
     }
 }
@@ -422,17 +432,22 @@ extern "C" int rfb_aggr_dev(rfb_ctx_t *ctx, int op, int val_type, const void *va
             RFB_CUDA(cudaMemsetAsync(out, 0, (size_t)groups * rfb_type_size(val_type), ctx->stream));
             RFB_CUDA(cudaMemsetAsync(aux, 0, (size_t)groups * 4, ctx->stream));
             if (k == K_I64) return run_aggr<AK_SUM_I64, i64>(ctx, val, filter, group_ids, len, groups, out, aux, out);
-            if (k == K_I32) return run_aggr<AK_SUM_I32, i32>(ctx, val, filter, group_ids, len, groups, out, aux, out);
+            if (k == K_I16) {
+                RFB_CUDA(cudaMemsetAsync(acc, 0, (size_t)groups * 4, ctx->stream));
+                return run_aggr<AK_SUM_I16, i16>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
+            }
             return run_aggr<AK_SUM_F64, f64>(ctx, val, filter, group_ids, len, groups, out, aux, out);
         case RFB_A_MIN:
             if (k == K_I64) { rc = fill<i64>(ctx, (i64 *)out, groups, RFB_INF_I64); if (rc) return rc; return run_aggr<AK_MIN_I64, i64>(ctx, val, filter, group_ids, len, groups, out, aux, out); }
             if (k == K_I32) { rc = fill<i32>(ctx, (i32 *)out, groups, (i32)0x7FFFFFFF); if (rc) return rc; return run_aggr<AK_MIN_I32, i32>(ctx, val, filter, group_ids, len, groups, out, aux, out); }
+            if (k == K_I16) { rc = fill<i32>(ctx, (i32 *)acc, groups, (i32)0x7FFF); if (rc) return rc; return run_aggr<AK_MIN_I16, i16>(ctx, val, filter, group_ids, len, groups, acc, aux, out); }
             rc = fill<u64>(ctx, (u64 *)acc, groups, f64_sort_key(bits_f64(0x7FF0000000000000ULL)));
             if (rc) return rc;
             return run_aggr<AK_MIN_F64, f64>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
         case RFB_A_MAX:
             if (k == K_I64) { rc = fill<i64>(ctx, (i64 *)out, groups, NULL_I64); if (rc) return rc; return run_aggr<AK_MAX_I64, i64>(ctx, val, filter, group_ids, len, groups, out, aux, out); }
             if (k == K_I32) { rc = fill<i32>(ctx, (i32 *)out, groups, NULL_I32); if (rc) return rc; return run_aggr<AK_MAX_I32, i32>(ctx, val, filter, group_ids, len, groups, out, aux, out); }
+            if (k == K_I16) { rc = fill<i32>(ctx, (i32 *)acc, groups, (i32)NULL_I16); if (rc) return rc; return run_aggr<AK_MAX_I16, i16>(ctx, val, filter, group_ids, len, groups, acc, aux, out); }
             RFB_CUDA(cudaMemsetAsync(acc, 0, (size_t)groups * 8, ctx->stream));
             return run_aggr<AK_MAX_F64, f64>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
         default:  // AVG
@@ -440,6 +455,7 @@ extern "C" int rfb_aggr_dev(rfb_ctx_t *ctx, int op, int val_type, const void *va
             RFB_CUDA(cudaMemsetAsync(aux, 0, (size_t)groups * 8, ctx->stream));
             if (k == K_I64) return run_aggr<AK_AVG_I64, i64>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
             if (k == K_I32) return run_aggr<AK_AVG_I32, i32>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
+            if (k == K_I16) return run_aggr<AK_AVG_I16, i16>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
             return run_aggr<AK_AVG_F64, f64>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
     }
 }

@@ -121,9 +121,13 @@ int launch_map2(rfb_ctx_t *ctx, const void *x, X xa, const void *y, Y ya, void *
 __host__ __device__ __forceinline__ u64 ckey_i64(i64 v) { return (u64)v ^ 0x8000000000000000ULL; }
 __host__ __device__ __forceinline__ u64 ckey_f64(f64 v) { return f64_sort_key(v == 0.0 ? 0.0 : v); }
 
-template <bool FLT, typename T> __device__ __forceinline__ u64 ckey(T v) {
+// `scale` converts units (DATE days -> TIMESTAMP nanoseconds), null-preserving like date_to_timestamp (core/ops.h:264)
+template <bool FLT, typename T> __device__ __forceinline__ u64 ckey(T v, i64 scale) {
     if constexpr (FLT || Elem<T>::kind == K_F64) return ckey_f64(widen_f64(v));
-    else return ckey_i64(widen_i64(v));
+    else {
+        const i64 w = widen_i64(v);
+        return ckey_i64(w == NULL_I64 ? w : w * scale);
+    }
 }
 
 // 3-bit truth table indexed by sign(a - b) + 1: bit0 a<b, bit1 a==b, bit2 a>b
@@ -139,8 +143,9 @@ inline int mirror_op(int op) {  // x OP y  <=>  y OP' x
 
 template <bool FLT, typename X, typename Y> struct CmpVV {
     u32 lut;
+    i64 sx, sy;
     __device__ __forceinline__ u8 operator()(X a, Y b) const {
-        const u64 ka = ckey<FLT>(a), kb = ckey<FLT>(b);
+        const u64 ka = ckey<FLT>(a, sx), kb = ckey<FLT>(b, sy);
         const int idx = (ka > kb) - (ka < kb) + 1;
         return (u8)((lut >> idx) & 1u);
     }
@@ -149,37 +154,37 @@ template <bool FLT, typename X, typename Y> struct CmpVV {
 template <bool FLT, typename X> struct CmpVA {
     u32 lut;
     u64 kb;
+    i64 sx;
     __device__ __forceinline__ u8 operator()(X a, u8) const {
-        const u64 ka = ckey<FLT>(a);
+        const u64 ka = ckey<FLT>(a, sx);
         const int idx = (ka > kb) - (ka < kb) + 1;
         return (u8)((lut >> idx) & 1u);
     }
 };
 
 template <bool FLT, typename X>
-int cmp_va(rfb_ctx_t *ctx, int op, const void *x, i64 n, u64 kb, u8 *mask) {
-    CmpVA<FLT, X> f{cmp_lut(op), kb};
+int cmp_va(rfb_ctx_t *ctx, int op, const void *x, i64 n, u64 kb, i64 sx, u8 *mask) {
+    CmpVA<FLT, X> f{cmp_lut(op), kb, sx};
     return launch_map2<X, u8, u8, false, true>(ctx, x, X(), nullptr, (u8)0, mask, n, f);
 }
 template <typename X>
-int cmp_va_x(rfb_ctx_t *ctx, int op, bool flt, const void *x, i64 n, u64 kb, u8 *mask) {
-    return flt ? cmp_va<true, X>(ctx, op, x, n, kb, mask) : cmp_va<false, X>(ctx, op, x, n, kb, mask);
+int cmp_va_x(rfb_ctx_t *ctx, int op, bool flt, const void *x, i64 n, u64 kb, i64 sx, u8 *mask) {
+    return flt ? cmp_va<true, X>(ctx, op, x, n, kb, sx, mask) : cmp_va<false, X>(ctx, op, x, n, kb, sx, mask);
 }
 
 template <typename X, typename Y>
-int cmp_vv(rfb_ctx_t *ctx, int op, const void *x, const void *y, i64 n, u8 *mask) {
+int cmp_vv(rfb_ctx_t *ctx, int op, const void *x, const void *y, i64 n, i64 sx, i64 sy, u8 *mask) {
     constexpr bool FLT = Elem<X>::kind == K_F64 || Elem<Y>::kind == K_F64;
-    CmpVV<FLT, X, Y> f{cmp_lut(op)};
+    CmpVV<FLT, X, Y> f{cmp_lut(op), sx, sy};
     return launch_map2<X, Y, u8, false, false>(ctx, x, X(), y, Y(), mask, n, f);
 }
 template <typename X>
-int cmp_vv_y(rfb_ctx_t *ctx, int op, const void *x, int ky, const void *y, i64 n, u8 *mask) {
+int cmp_vv_y(rfb_ctx_t *ctx, int op, const void *x, int ky, const void *y, i64 n, i64 sx, i64 sy, u8 *mask) {
     switch (ky) {
-        case K_U8: return cmp_vv<X, u8>(ctx, op, x, y, n, mask);
-        case K_I16: return cmp_vv<X, i16>(ctx, op, x, y, n, mask);
-        case K_I32: return cmp_vv<X, i32>(ctx, op, x, y, n, mask);
-        case K_I64: return cmp_vv<X, i64>(ctx, op, x, y, n, mask);
-        default: return cmp_vv<X, f64>(ctx, op, x, y, n, mask);
+        case K_I16: return cmp_vv<X, i16>(ctx, op, x, y, n, sx, sy, mask);
+        case K_I32: return cmp_vv<X, i32>(ctx, op, x, y, n, sx, sy, mask);
+        case K_I64: return cmp_vv<X, i64>(ctx, op, x, y, n, sx, sy, mask);
+        default: return cmp_vv<X, f64>(ctx, op, x, y, n, sx, sy, mask);
     }
 }
 
@@ -201,24 +206,17 @@ bool scalar_f64(const rfb_scalar_t *s, f64 *out) {
     return true;
 }
 
-// temporal types only compare with themselves (the reference converts DATE<->TIMESTAMP units, which this layer does
-// not model); plain numeric kinds mix freely
-bool cmp_types_ok(int xt, int yt) {
-    auto plain = [](int t) { return t == RFB_B8 || t == RFB_U8 || t == RFB_I16 || t == RFB_I32 || t == RFB_I64 || t == RFB_F64; };
-    if (!rfb_kind_of(xt) || !rfb_kind_of(yt)) return false;
-    return (plain(xt) && plain(yt)) || xt == yt;
-}
-
 }  // namespace
 
 extern "C" int rfb_cmp_dev(rfb_ctx_t *ctx, int op, int xt, const void *x, int64_t xn, const rfb_scalar_t *xs, int yt,
                            const void *y, int64_t yn, const rfb_scalar_t *ys, uint8_t *mask) {
     RFB_ARG(ctx && op >= RFB_EQ && op <= RFB_GE, "rfb_cmp_dev: op");
     RFB_ARG((xn >= 0 ? (x || xn == 0) : xs != nullptr) && (yn >= 0 ? (y || yn == 0) : ys != nullptr), "rfb_cmp_dev: operands");
-    if (!cmp_types_ok(xt, yt)) { rfb_set_error("cmp: unsupported operand types %d, %d", xt, yt); return RFB_ERR_TYPE; }
+    if (!rfb_cmp_types_ok(xt, yt)) { rfb_set_error("cmp: unsupported operand types %d, %d", xt, yt); return RFB_ERR_TYPE; }
     if (xn >= 0 && yn >= 0 && xn != yn) { rfb_set_error("cmp: vector lengths differ (%lld vs %lld)", (long long)xn, (long long)yn); return RFB_ERR_LENGTH; }
     const int kx = rfb_kind_of(xt), ky = rfb_kind_of(yt);
     const bool flt = (kx == K_F64 || ky == K_F64);
+    const i64 sx = rfb_cmp_scale(xt, yt), sy = rfb_cmp_scale(yt, xt);
     if (xn < 0 && yn < 0) {  // atom vs atom: one byte, computed by the same kernel on a 1-element broadcast
         RFB_ARG(mask, "rfb_cmp_dev: mask");
         rfb_set_error("cmp: both operands are atoms; the operator layer folds constants on the host");
@@ -227,11 +225,10 @@ extern "C" int rfb_cmp_dev(rfb_ctx_t *ctx, int op, int xt, const void *x, int64_
     if (xn >= 0 && yn >= 0) {
         RFB_ARG(mask || xn == 0, "rfb_cmp_dev: mask");
         switch (kx) {
-            case K_U8: return cmp_vv_y<u8>(ctx, op, x, ky, y, xn, mask);
-            case K_I16: return cmp_vv_y<i16>(ctx, op, x, ky, y, xn, mask);
-            case K_I32: return cmp_vv_y<i32>(ctx, op, x, ky, y, xn, mask);
-            case K_I64: return cmp_vv_y<i64>(ctx, op, x, ky, y, xn, mask);
-            default: return cmp_vv_y<f64>(ctx, op, x, ky, y, xn, mask);
+            case K_I16: return cmp_vv_y<i16>(ctx, op, x, ky, y, xn, sx, sy, mask);
+            case K_I32: return cmp_vv_y<i32>(ctx, op, x, ky, y, xn, sx, sy, mask);
+            case K_I64: return cmp_vv_y<i64>(ctx, op, x, ky, y, xn, sx, sy, mask);
+            default: return cmp_vv_y<f64>(ctx, op, x, ky, y, xn, sx, sy, mask);
         }
     }
     // vector vs atom (atom on the left: mirror the operator)
@@ -244,13 +241,18 @@ extern "C" int rfb_cmp_dev(rfb_ctx_t *ctx, int op, int xt, const void *x, int64_
     RFB_ARG(mask || n == 0, "rfb_cmp_dev: mask");
     u64 kb;
     if (flt) { f64 d; if (!scalar_f64(s, &d)) return RFB_ERR_TYPE; kb = ckey_f64(d); }
-    else { i64 d; if (!scalar_i64(s, &d)) return RFB_ERR_TYPE; kb = ckey_i64(d); }
+    else {
+        i64 d;
+        if (!scalar_i64(s, &d)) return RFB_ERR_TYPE;
+        const i64 sa = atom_left ? sx : sy;
+        kb = ckey_i64(d == NULL_I64 ? d : d * sa);
+    }
+    const i64 sv = atom_left ? sy : sx;
     switch (kv) {
-        case K_U8: return cmp_va_x<u8>(ctx, vop, flt, v, n, kb, mask);
-        case K_I16: return cmp_va_x<i16>(ctx, vop, flt, v, n, kb, mask);
-        case K_I32: return cmp_va_x<i32>(ctx, vop, flt, v, n, kb, mask);
-        case K_I64: return cmp_va_x<i64>(ctx, vop, flt, v, n, kb, mask);
-        default: return cmp_va_x<f64>(ctx, vop, flt, v, n, kb, mask);
+        case K_I16: return cmp_va_x<i16>(ctx, vop, flt, v, n, kb, sv, mask);
+        case K_I32: return cmp_va_x<i32>(ctx, vop, flt, v, n, kb, sv, mask);
+        case K_I64: return cmp_va_x<i64>(ctx, vop, flt, v, n, kb, sv, mask);
+        default: return cmp_va_x<f64>(ctx, vop, flt, v, n, kb, sv, mask);
     }
 }
 

@@ -234,6 +234,19 @@ template <typename T, typename Op> __device__ __forceinline__ T block_reduce(T v
 
 // ------------------------------------------------------------------ predicates against a constant
 
+// Operand types the reference's comparison matrix accepts for vector operands (core/cmp.c:77-258): any mix of the plain
+// numeric types I16/I32/I64/F64, a temporal/symbol type with itself, or DATE against TIMESTAMP (the date is converted to
+// nanoseconds, core/cmp.c:243-257, core/ops.h:264).  B8/U8 compare as atoms only there: a type error at this layer.
+#define RFB_NANOS_FROM_DAY 86400000000000LL
+static inline bool rfb_cmp_types_ok(int xt, int yt) {
+    auto plain = [](int t) { return t == RFB_I16 || t == RFB_I32 || t == RFB_I64 || t == RFB_F64; };
+    if (plain(xt) && plain(yt)) return true;
+    if ((xt == RFB_DATE && yt == RFB_TIMESTAMP) || (xt == RFB_TIMESTAMP && yt == RFB_DATE)) return true;
+    return xt == yt && (xt == RFB_DATE || xt == RFB_TIME || xt == RFB_TIMESTAMP || xt == RFB_SYMBOL);
+}
+// multiplier that brings an operand of type t into the comparison unit of the pair (1 except DATE vs TIMESTAMP)
+static inline i64 rfb_cmp_scale(int t, int other) { return (t == RFB_DATE && other == RFB_TIMESTAMP) ? RFB_NANOS_FROM_DAY : 1; }
+
 // predicate = unsigned range test on an order-preserving 64-bit key, optionally negated.
 // All six comparison operators against a constant reduce to it (see make_pred_range).
 struct PredRange {
@@ -291,6 +304,7 @@ static inline PredRange make_pred_range(int op, u64 kk) {
 static inline bool rfb_make_pred(int op, int col_type, const rfb_scalar_t *k, PredRange *pr) {
     const int ck = rfb_kind_of(col_type);
     if (op < RFB_EQ || op > RFB_GE || !ck || !k) return false;
+    if (!rfb_cmp_types_ok(col_type, k->type) || rfb_cmp_scale(col_type, k->type) != 1 || rfb_cmp_scale(k->type, col_type) != 1) return false;  // unit-converting pairs go through rfb_cmp_dev
     if (ck == K_F64) {
         f64 kv;
         if (!scalar_as_f64(k, &kv)) return false;

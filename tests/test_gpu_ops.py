@@ -16,12 +16,13 @@ SIZES = [1, 2, 31, 1023, 16385, 200_003]
 CMPS = [ob.EQ, ob.NE, ob.LT, ob.GT, ob.LE, ob.GE]
 ARITH = [ob.ADD, ob.SUB, ob.MUL, ob.DIV, ob.FDIV, ob.MOD]
 ALL_T = [ob.U8, ob.I16, ob.I32, ob.I64, ob.F64]
+CMP_T = [ob.I16, ob.I32, ob.I64, ob.F64]      # the reference's vector comparison matrix (core/cmp.c:77-258)
 
 
 # ---------------------------------------------------------------- comparisons -> mask
 
 @pytest.mark.parametrize("op", CMPS)
-@pytest.mark.parametrize("xt,yt", [(a, b) for a in ALL_T for b in ALL_T])
+@pytest.mark.parametrize("xt,yt", [(a, b) for a in CMP_T for b in CMP_T] + [(ob.DATE, ob.DATE), (ob.TIMESTAMP, ob.TIMESTAMP)])
 def test_cmp_vector_vector(ctx, oracle, op, xt, yt):
     n = 40_007
     x = rng_col(xt, n, seed=xt * 7 + 1, null_frac=0.05, lo=-20 if xt != ob.U8 else 0, hi=20)
@@ -37,7 +38,7 @@ def test_cmp_vector_vector(ctx, oracle, op, xt, yt):
 @pytest.mark.parametrize("op", CMPS)
 @pytest.mark.parametrize("t,kt,k", [(ob.I64, ob.I64, 3), (ob.I64, ob.I64, ob.NULL_I64), (ob.I32, ob.I64, -2), (ob.I64, ob.I32, 0),
                                     (ob.I64, ob.F64, 2.5), (ob.F64, ob.I64, 1), (ob.F64, ob.F64, float("nan")),
-                                    (ob.F64, ob.F64, -0.0), (ob.I16, ob.I16, ob.NULL_I16), (ob.U8, ob.U8, 7)])
+                                    (ob.F64, ob.F64, -0.0), (ob.I16, ob.I16, ob.NULL_I16), (ob.TIME, ob.TIME, 7)])
 @pytest.mark.parametrize("n", [1, 17, 70_001])
 def test_cmp_vector_atom_both_sides(ctx, oracle, op, t, kt, k, n):
     x = rng_col(t, n, seed=n + t, null_frac=0.05, lo=-9 if t != ob.U8 else 0, hi=9)
@@ -47,6 +48,19 @@ def test_cmp_vector_atom_both_sides(ctx, oracle, op, t, kt, k, n):
     d = dev(x)
     assert np.array_equal(host(ctx.cmp(op, t, d, kt, k)), oracle.cmp(op, t, x, kt, k))
     assert np.array_equal(host(ctx.cmp(op, kt, k, t, d)), oracle.cmp(op, kt, k, t, x))
+
+
+@pytest.mark.parametrize("xt,yt", [(ob.U8, ob.U8), (ob.B8, ob.B8), (ob.U8, ob.I64), (ob.DATE, ob.I32), (ob.DATE, ob.TIMESTAMP), (ob.I64, ob.TIMESTAMP)])
+def test_cmp_type_errors_match_the_reference_matrix(ctx, oracle, xt, yt):
+    x, y = rng_col(xt, 100, 1, lo=0, hi=9), rng_col(yt, 100, 2, lo=0, hi=9)
+    with pytest.raises(ob.OracleError):
+        oracle.cmp(ob.LT, xt, x, yt, y)
+    with pytest.raises(capi.RfbError) as e:
+        ctx.cmp(ob.LT, xt, dev(x), yt, dev(y))
+    assert e.value.kind == "type"
+    with pytest.raises(capi.RfbError) as e:
+        ctx.cmp_where(ob.LT, xt, dev(x), 3) if xt in (ob.U8, ob.B8) else ctx.cmp(ob.LT, xt, dev(x), yt, 3)
+    assert e.value.kind == "type"
 
 
 def test_cmp_length_mismatch_and_unaligned(ctx, oracle):
@@ -76,7 +90,7 @@ def test_where_unaligned_mask(ctx, oracle):
     assert np.array_equal(host(ctx.where(dev(mask)[5:])), oracle.where(mask[5:]))
 
 
-@pytest.mark.parametrize("t", ALL_T)
+@pytest.mark.parametrize("t", CMP_T + [ob.TIMESTAMP])
 @pytest.mark.parametrize("op", [ob.LT, ob.EQ, ob.GE])
 @pytest.mark.parametrize("n", [1, 4097, 300_001])
 def test_cmp_where_equals_where_of_cmp(ctx, oracle, t, op, n):
@@ -207,7 +221,7 @@ def test_group_dense_matches_oracle_numbering(ctx, oracle, n, card, filtered):
     assert np.array_equal(host(gf), wf) and np.array_equal(host(gg), wg)
 
 
-@pytest.mark.parametrize("n", [2, 1000, 200_003])
+@pytest.mark.parametrize("n", [4, 1000, 200_003])
 @pytest.mark.parametrize("filtered", [False, True])
 def test_group_sparse_matches_oracle_numbering(ctx, oracle, n, filtered):
     r = np.random.default_rng(n)
@@ -226,9 +240,9 @@ def test_group_empty(ctx):
     assert gi.groups == 0 and gi.dense == 1
 
 
-AGGR_CASES = [(ob.SUM, ob.I64), (ob.SUM, ob.I32), (ob.SUM, ob.F64), (ob.SUM, ob.TIME), (ob.MIN, ob.I64), (ob.MAX, ob.I64),
+AGGR_CASES = [(ob.SUM, ob.I64), (ob.SUM, ob.I16), (ob.SUM, ob.F64), (ob.MIN, ob.I64), (ob.MAX, ob.I64), (ob.MIN, ob.I16), (ob.MAX, ob.I16),
               (ob.MIN, ob.F64), (ob.MAX, ob.F64), (ob.MIN, ob.DATE), (ob.MAX, ob.TIME), (ob.MIN, ob.TIMESTAMP), (ob.COUNT, ob.I64),
-              (ob.COUNT, ob.F64), (ob.AVG, ob.I64), (ob.AVG, ob.I32), (ob.AVG, ob.F64)]
+              (ob.COUNT, ob.F64), (ob.COUNT, ob.I32), (ob.AVG, ob.I64), (ob.AVG, ob.I32), (ob.AVG, ob.I16), (ob.AVG, ob.F64), (ob.AVG, ob.TIME)]
 A_OF = {ob.SUM: capi.A_SUM, ob.MIN: capi.A_MIN, ob.MAX: capi.A_MAX, ob.COUNT: capi.A_COUNT, ob.AVG: capi.A_AVG}
 
 
@@ -262,10 +276,16 @@ def test_aggr_sticky_null_and_all_null_group(ctx, oracle):
     assert host(s).tolist() == [ob.NULL_I64, 7, ob.NULL_I64]
 
 
-def test_aggr_type_errors(ctx):
-    gid, v32 = dev(np.zeros(4, np.int64)), dev(np.zeros(4, np.int32))
+@pytest.mark.parametrize("op,vt", [(ob.SUM, ob.I32), (ob.SUM, ob.TIME), (ob.SUM, ob.TIMESTAMP), (ob.MIN, ob.I32), (ob.MAX, ob.I32),
+                                   (ob.AVG, ob.TIMESTAMP), (ob.COUNT, ob.I16), (ob.COUNT, ob.U8)])
+def test_aggr_type_errors_match_the_reference_drivers(ctx, oracle, op, vt):
+    # the reference's non-parted aggr_* switch tables (core/aggr.c:1107-1150, 1152-1315, 2013-2133); pinned against the
+    # compiled reference in tests/test_oracle_vs_reference.py::test_grouped_aggregate_type_errors
+    gid, val = np.zeros(4, np.int64), rng_col(vt, 4, 1, lo=0, hi=9)
+    with pytest.raises(ob.OracleError):
+        oracle.aggr(op, vt, val, gid, 1)
     with pytest.raises(capi.RfbError) as e:
-        ctx.aggr(capi.A_MIN, ob.I32, v32, gid, 1)       # the reference has no grouped min/max for I32
+        ctx.aggr(A_OF[op], vt, dev(val), dev(gid), 1)
     assert e.value.kind == "type"
 
 
