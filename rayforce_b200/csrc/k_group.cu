@@ -311,58 +311,121 @@ enum { AK_SUM_I64, AK_SUM_I16, AK_SUM_F64, AK_MIN_I64, AK_MAX_I64, AK_MIN_I32, A
 // finalise kernel narrows them (a sum mod 2^32 truncated to 16 bits is the reference's 16-bit wrapping sum)
 
 // acc: main accumulator array (typed per kind), aux: null flags (sum) or non-null counts (avg)
-template <int KIND, typename V>
+template <int KIND, typename V> __device__ __forceinline__ void aggr_one(void *acc, void *aux, i64 g, V v) {
+    if constexpr (KIND == AK_SUM_I64) {
+        if (v == NULL_I64) ((u32 *)aux)[g] = 1u; else atomicAdd((unsigned long long *)acc + g, (unsigned long long)v);
+    } else if constexpr (KIND == AK_SUM_I16) {
+        if (v == NULL_I16) ((u32 *)aux)[g] = 1u; else atomicAdd((u32 *)acc + g, (u32)(i32)v);
+    } else if constexpr (KIND == AK_SUM_F64) {
+        if (isnan64(v)) ((u32 *)aux)[g] = 1u; else atomicAdd((f64 *)acc + g, v);
+    } else if constexpr (KIND == AK_MIN_I64) {
+        if (v != NULL_I64) atomicMin((long long *)acc + g, (long long)v);
+    } else if constexpr (KIND == AK_MAX_I64) {
+        atomicMax((long long *)acc + g, (long long)v);    // NULL is the minimum: never wins
+    } else if constexpr (KIND == AK_MIN_I32) {
+        if (v != NULL_I32) atomicMin((int *)acc + g, (int)v);
+    } else if constexpr (KIND == AK_MAX_I32) {
+        atomicMax((int *)acc + g, (int)v);
+    } else if constexpr (KIND == AK_MIN_I16) {
+        if (v != NULL_I16) atomicMin((int *)acc + g, (int)v);
+    } else if constexpr (KIND == AK_MAX_I16) {
+        atomicMax((int *)acc + g, (int)v);
+    } else if constexpr (KIND == AK_MIN_F64) {
+        if (!isnan64(v)) atomicMin((unsigned long long *)acc + g, (unsigned long long)f64_sort_key(v));
+    } else if constexpr (KIND == AK_MAX_F64) {
+        atomicMax((unsigned long long *)acc + g, (unsigned long long)f64_sort_key(v));   // NaN -> key 0: never wins
+    } else if constexpr (KIND == AK_COUNT) {
+        atomicAdd((unsigned long long *)acc + g, 1ULL);
+    } else if constexpr (KIND == AK_AVG_I64) {
+        if (v != NULL_I64) { atomicAdd((unsigned long long *)acc + g, (unsigned long long)v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
+    } else if constexpr (KIND == AK_AVG_I32) {
+        if (v != NULL_I32) { atomicAdd((unsigned long long *)acc + g, (unsigned long long)(i64)v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
+    } else if constexpr (KIND == AK_AVG_I16) {
+        if (v != NULL_I16) { atomicAdd((unsigned long long *)acc + g, (unsigned long long)(i64)v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
+    } else if constexpr (KIND == AK_AVG_F64) {
+        if (!isnan64(v)) { atomicAdd((f64 *)acc + g, v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
+    }
+}
+
+// fold one CTA-private slot (shared memory) into the device-wide accumulators
+template <int KIND> __device__ __forceinline__ void aggr_merge(void *acc, void *aux, const void *sacc, const void *saux, i64 g) {
+    if constexpr (KIND == AK_SUM_I64 || KIND == AK_COUNT) {
+        const u64 v = ((const u64 *)sacc)[g];
+        if (v) atomicAdd((unsigned long long *)acc + g, (unsigned long long)v);
+        if (KIND == AK_SUM_I64 && ((const u32 *)saux)[g]) ((u32 *)aux)[g] = 1u;
+    } else if constexpr (KIND == AK_SUM_I16) {
+        const u32 v = ((const u32 *)sacc)[g];
+        if (v) atomicAdd((u32 *)acc + g, v);
+        if (((const u32 *)saux)[g]) ((u32 *)aux)[g] = 1u;
+    } else if constexpr (KIND == AK_MIN_I64) atomicMin((long long *)acc + g, ((const long long *)sacc)[g]);
+    else if constexpr (KIND == AK_MAX_I64) atomicMax((long long *)acc + g, ((const long long *)sacc)[g]);
+    else if constexpr (KIND == AK_MIN_I32 || KIND == AK_MIN_I16) atomicMin((int *)acc + g, ((const int *)sacc)[g]);
+    else if constexpr (KIND == AK_MAX_I32 || KIND == AK_MAX_I16) atomicMax((int *)acc + g, ((const int *)sacc)[g]);
+    else if constexpr (KIND == AK_MIN_F64) atomicMin((unsigned long long *)acc + g, ((const unsigned long long *)sacc)[g]);
+    else if constexpr (KIND == AK_MAX_F64) atomicMax((unsigned long long *)acc + g, ((const unsigned long long *)sacc)[g]);
+    else if constexpr (KIND == AK_AVG_I64 || KIND == AK_AVG_I32 || KIND == AK_AVG_I16) {
+        const u64 c = ((const u64 *)saux)[g];
+        if (c) { atomicAdd((unsigned long long *)acc + g, (unsigned long long)((const u64 *)sacc)[g]); atomicAdd((unsigned long long *)aux + g, (unsigned long long)c); }
+    } else if constexpr (KIND == AK_AVG_F64) {
+        const u64 c = ((const u64 *)saux)[g];
+        if (c) { atomicAdd((f64 *)acc + g, ((const f64 *)sacc)[g]); atomicAdd((unsigned long long *)aux + g, (unsigned long long)c); }
+    }
+}
+
+constexpr int PRIV_GROUPS = 3072;   // CTA-private accumulators in shared memory: 2 x 8 B x 3072 = 48 KB
+
+// PRIV: groups <= PRIV_GROUPS.  Every CTA folds its rows into shared-memory accumulators (initialised from the device-wide
+// ones' initial values, which are each operator's identity) and merges them once at the end: the hot atomics never leave
+// the SM, which is what low-cardinality keys (H2O id1-like, 100 groups) need — device-wide atomics serialise per address.
+template <int KIND, typename V, bool PRIV>
 __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
-k_aggr(const V *__restrict__ val, ValRow row, const i64 *__restrict__ gid, i64 n, void *acc, void *aux) {
+k_aggr(const V *__restrict__ val, ValRow row, const i64 *__restrict__ gid, i64 n, i64 groups, void *acc, void *aux) {
     constexpr int U = 4;
-    const i64 stride = (i64)gridDim.x * THREADS;
-    auto one = [&](i64 g, V v) {
-        if constexpr (KIND == AK_SUM_I64) {
-            if (v == NULL_I64) ((u32 *)aux)[g] = 1u; else atomicAdd((unsigned long long *)acc + g, (unsigned long long)v);
-        } else if constexpr (KIND == AK_SUM_I16) {
-            if (v == NULL_I16) ((u32 *)aux)[g] = 1u; else atomicAdd((u32 *)acc + g, (u32)(i32)v);
-        } else if constexpr (KIND == AK_SUM_F64) {
-            if (isnan64(v)) ((u32 *)aux)[g] = 1u; else atomicAdd((f64 *)acc + g, v);
-        } else if constexpr (KIND == AK_MIN_I64) {
-            if (v != NULL_I64) atomicMin((long long *)acc + g, (long long)v);
-        } else if constexpr (KIND == AK_MAX_I64) {
-            atomicMax((long long *)acc + g, (long long)v);    // NULL is the minimum: never wins
-        } else if constexpr (KIND == AK_MIN_I32) {
-            if (v != NULL_I32) atomicMin((int *)acc + g, (int)v);
-        } else if constexpr (KIND == AK_MAX_I32) {
-            atomicMax((int *)acc + g, (int)v);
-        } else if constexpr (KIND == AK_MIN_I16) {
-            if (v != NULL_I16) atomicMin((int *)acc + g, (int)v);
-        } else if constexpr (KIND == AK_MAX_I16) {
-            atomicMax((int *)acc + g, (int)v);
-        } else if constexpr (KIND == AK_MIN_F64) {
-            if (!isnan64(v)) atomicMin((unsigned long long *)acc + g, (unsigned long long)f64_sort_key(v));
-        } else if constexpr (KIND == AK_MAX_F64) {
-            atomicMax((unsigned long long *)acc + g, (unsigned long long)f64_sort_key(v));   // NaN -> key 0: never wins
-        } else if constexpr (KIND == AK_AVG_I64) {
-            if (v != NULL_I64) { atomicAdd((unsigned long long *)acc + g, (unsigned long long)v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
-        } else if constexpr (KIND == AK_AVG_I32) {
-            if (v != NULL_I32) { atomicAdd((unsigned long long *)acc + g, (unsigned long long)(i64)v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
-        } else if constexpr (KIND == AK_AVG_I16) {
-            if (v != NULL_I16) { atomicAdd((unsigned long long *)acc + g, (unsigned long long)(i64)v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
-        } else if constexpr (KIND == AK_AVG_F64) {
-            if (!isnan64(v)) { atomicAdd((f64 *)acc + g, v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
+    extern __shared__ u64 s_priv[];
+    void *a = acc, *x = aux;
+    if constexpr (PRIV) {
+        // private slots start at the operator's identity (NOT a copy of the device-wide slots: an early CTA may already
+        // have merged into those)
+        u64 *sa = s_priv, *sx = s_priv + groups;
+        for (i64 g = threadIdx.x; g < groups; g += THREADS) {
+            if constexpr (KIND == AK_MIN_I64) ((i64 *)sa)[g] = RFB_INF_I64;
+            else if constexpr (KIND == AK_MAX_I64) ((i64 *)sa)[g] = NULL_I64;
+            else if constexpr (KIND == AK_MIN_I32) ((i32 *)sa)[g] = (i32)0x7FFFFFFF;
+            else if constexpr (KIND == AK_MAX_I32) ((i32 *)sa)[g] = NULL_I32;
+            else if constexpr (KIND == AK_MIN_I16) ((i32 *)sa)[g] = (i32)0x7FFF;
+            else if constexpr (KIND == AK_MAX_I16) ((i32 *)sa)[g] = (i32)NULL_I16;
+            else if constexpr (KIND == AK_MIN_F64) sa[g] = f64_sort_key(bits_f64(0x7FF0000000000000ULL));
+            else sa[g] = 0;   // sums, counts, averages, MAX_F64 (key 0 = null)
+            sx[g] = 0;
         }
-    };
+        __syncthreads();
+        a = sa;
+        x = sx;
+    }
+    const i64 stride = (i64)gridDim.x * THREADS;
     i64 i = (i64)blockIdx.x * THREADS + threadIdx.x;
     for (; i + (U - 1) * stride < n; i += U * stride) {
         i64 g[U];
         V v[U];
 #pragma unroll
-        for (int j = 0; j < U; j++) { g[j] = ld_stream(gid + i + j * stride); v[j] = row.filter ? __ldg(val + row(i + j * stride)) : ld_stream(val + i + j * stride); }
+        for (int j = 0; j < U; j++) {
+            g[j] = ld_stream(gid + i + j * stride);
+            if constexpr (KIND == AK_COUNT) v[j] = V();
+            else v[j] = row.filter ? __ldg(val + row(i + j * stride)) : ld_stream(val + i + j * stride);
+        }
 #pragma unroll
-        for (int j = 0; j < U; j++) one(g[j], v[j]);
+        for (int j = 0; j < U; j++) aggr_one<KIND, V>(a, x, g[j], v[j]);
     }
-    for (; i < n; i += stride) one(ld_stream(gid + i), row.filter ? __ldg(val + row(i)) : ld_stream(val + i));
-}
-
-__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_count(const i64 *__restrict__ gid, i64 n, unsigned long long *acc) {
-    for (i64 i = (i64)blockIdx.x * THREADS + threadIdx.x; i < n; i += (i64)gridDim.x * THREADS) atomicAdd(acc + ld_stream(gid + i), 1ULL);
+    for (; i < n; i += stride) {
+        V v;
+        if constexpr (KIND == AK_COUNT) v = V();
+        else v = row.filter ? __ldg(val + row(i)) : ld_stream(val + i);
+        aggr_one<KIND, V>(a, x, ld_stream(gid + i), v);
+    }
+    if constexpr (PRIV) {
+        __syncthreads();
+        for (i64 g = threadIdx.x; g < groups; g += THREADS) aggr_merge<KIND>(acc, aux, a, x, g);
+    }
 }
 
 template <int KIND> __global__ void k_aggr_final(void *out, const void *acc, const void *aux, i64 groups) {
@@ -385,9 +448,19 @@ template <int KIND> __global__ void k_aggr_final(void *out, const void *acc, con
 template <int KIND, typename V>
 int run_aggr(rfb_ctx_t *ctx, const void *val, const i64 *filter, const i64 *gid, i64 len, i64 groups, void *acc, void *aux, void *out) {
     if (len > 0) {
-        k_aggr<KIND, V><<<rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>((const V *)val, ValRow{filter}, gid, len, acc, aux);
+        const int grid = rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM);
+        // F64 sums stay on the device-wide path (one accumulator per group, like the reference's single running sum)
+        if constexpr (KIND != AK_SUM_F64) {
+            if (groups <= PRIV_GROUPS && len >= 65536) {
+                k_aggr<KIND, V, true><<<grid, THREADS, (size_t)groups * 16, ctx->stream>>>((const V *)val, ValRow{filter}, gid, len, groups, acc, aux);
+                RFB_CHECK_LAUNCH(ctx);
+                goto finalise;
+            }
+        }
+        k_aggr<KIND, V, false><<<grid, THREADS, 0, ctx->stream>>>((const V *)val, ValRow{filter}, gid, len, groups, acc, aux);
         RFB_CHECK_LAUNCH(ctx);
     }
+finalise:
     k_aggr_final<KIND><<<rfb_grid_for(ctx, groups, 256, 8), 256, 0, ctx->stream>>>(out, acc, aux, groups);
     RFB_CHECK_LAUNCH(ctx);
     return RFB_OK;
@@ -423,11 +496,7 @@ extern "C" int rfb_aggr_dev(rfb_ctx_t *ctx, int op, int val_type, const void *va
     switch (op) {
         case RFB_A_COUNT:
             RFB_CUDA(cudaMemsetAsync(out, 0, (size_t)groups * 8, ctx->stream));
-            if (len > 0) {
-                k_count<<<rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(group_ids, len, (unsigned long long *)out);
-                RFB_CHECK_LAUNCH(ctx);
-            }
-            return RFB_OK;
+            return run_aggr<AK_COUNT, i64>(ctx, nullptr, nullptr, group_ids, len, groups, out, aux, out);
         case RFB_A_SUM:
             RFB_CUDA(cudaMemsetAsync(out, 0, (size_t)groups * rfb_type_size(val_type), ctx->stream));
             RFB_CUDA(cudaMemsetAsync(aux, 0, (size_t)groups * 4, ctx->stream));
@@ -501,15 +570,30 @@ __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_fused_scope(FS fs, i
     }
 }
 
-template <typename FS>
+constexpr int FUSED_PRIV = 1536;   // 28 B x 1536 = 42 KB of CTA-private accumulators (fits the default 48 KB window)
+
+// PRIV (range <= FUSED_PRIV): first-row / sum / count / null-flag slots live in shared memory per CTA and are merged into
+// the device-wide arrays once per CTA; otherwise every row updates the device-wide (L2-resident) arrays directly.
+template <typename FS, bool PRIV>
 __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
-k_fused_accum(FS fs, const i64 *__restrict__ val, i64 n, i64 kmin, Accums a) {
+k_fused_accum(FS fs, const i64 *__restrict__ val, i64 n, i64 kmin, i64 range, Accums ga) {
     constexpr int U = 4;
+    extern __shared__ u64 s_fused[];
+    Accums a = ga;
+    if constexpr (PRIV) {
+        a.first_row = s_fused;
+        a.sum = s_fused + range;
+        a.cnt = s_fused + 2 * range;
+        a.has_null = (u32 *)(s_fused + 3 * range);
+        for (i64 s = threadIdx.x; s < range; s += THREADS) { a.first_row[s] = NO_ROW; a.sum[s] = 0; a.cnt[s] = 0; a.has_null[s] = 0; }
+        __syncthreads();
+    }
     const i64 stride = (i64)gridDim.x * THREADS;
     auto one = [&](i64 i, i64 k, i64 v, bool sel) {
         if (!sel) return;
         const i64 s = (i64)((u64)k - (u64)kmin);
-        claim_first(a.first_row, s, i);
+        if constexpr (PRIV) { if (a.first_row[s] > (u64)i) atomicMin((unsigned long long *)&a.first_row[s], (unsigned long long)i); }
+        else claim_first(a.first_row, s, i);
         if (v == NULL_I64) a.has_null[s] = 1u; else atomicAdd((unsigned long long *)a.sum + s, (unsigned long long)v);
         atomicAdd((unsigned long long *)a.cnt + s, 1ULL);
     };
@@ -523,6 +607,17 @@ k_fused_accum(FS fs, const i64 *__restrict__ val, i64 n, i64 kmin, Accums a) {
         for (int j = 0; j < U; j++) one(i + j * stride, k[j], v[j], sel[j]);
     }
     for (; i < n; i += stride) one(i, fs.key(i), ld_stream(val + i), fs.selected(i));
+    if constexpr (PRIV) {
+        __syncthreads();
+        for (i64 s = threadIdx.x; s < range; s += THREADS) {
+            const u64 c = a.cnt[s];
+            if (!c) continue;
+            atomicMin((unsigned long long *)&ga.first_row[s], (unsigned long long)a.first_row[s]);
+            atomicAdd((unsigned long long *)ga.sum + s, (unsigned long long)a.sum[s]);
+            atomicAdd((unsigned long long *)ga.cnt + s, (unsigned long long)c);
+            if (a.has_null[s]) ga.has_null[s] = 1u;
+        }
+    }
 }
 
 template <typename FS>
@@ -570,7 +665,8 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
     a.has_null = (u32 *)((char *)w + 3 * b8);
     RFB_CUDA(cudaMemsetAsync(a.first_row, 0xFF, (size_t)range * 8, ctx->stream));
     RFB_CUDA(cudaMemsetAsync(a.sum, 0, 2 * b8 + b4, ctx->stream));
-    k_fused_accum<FS><<<grid, THREADS, 0, ctx->stream>>>(fs, val, n, h[0], a);
+    if (range <= FUSED_PRIV && n >= 65536) k_fused_accum<FS, true><<<grid, THREADS, (size_t)range * 28, ctx->stream>>>(fs, val, n, h[0], range, a);
+    else k_fused_accum<FS, false><<<grid, THREADS, 0, ctx->stream>>>(fs, val, n, h[0], range, a);
     RFB_CHECK_LAUNCH(ctx);
     k_max_first<<<rfb_grid_for(ctx, range, THREADS, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(a.first_row, range, mm);
     RFB_CHECK_LAUNCH(ctx);

@@ -248,8 +248,9 @@ A_OF = {ob.SUM: capi.A_SUM, ob.MIN: capi.A_MIN, ob.MAX: capi.A_MAX, ob.COUNT: ca
 
 @pytest.mark.parametrize("op,vt", AGGR_CASES)
 @pytest.mark.parametrize("filtered", [False, True])
-def test_aggr(ctx, oracle, op, vt, filtered):
-    n, card = 200_003, 777
+@pytest.mark.parametrize("card", [777, 5000])      # CTA-private shared-memory accumulators / device-wide atomics
+def test_aggr(ctx, oracle, op, vt, filtered, card):
+    n = 200_003
     r = np.random.default_rng(op * 31 + vt)
     keys = r.integers(0, card, n).astype(np.int64)
     val = rng_col(vt, n, seed=vt + op, null_frac=0.0005, lo=-1000, hi=1000)
