@@ -1,0 +1,607 @@
+/*
+ * rfb_ops.c — reference-facing operator layer (pure C) on top of the C ABI of include/rfb200.h.
+ * See include/rfb200_ops.h for the contract.  No arithmetic on column data happens in this file: it classifies the
+ * operands exactly like the reference's dispatchers do, ships column payloads to HBM (once per query scope), calls the
+ * device-layer entry points and wraps the results into host-allocated objects.
+ */
+#define _GNU_SOURCE
+#include "rfb200_ops.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "rfb200.h"
+
+typedef rfb_obj_p obj_p;
+
+/* ------------------------------------------------------------------ state */
+
+#define MAX_COLS 64
+typedef struct {
+    const void *host; /* payload pointer identity */
+    int64_t len;
+    int type;
+    void *dev;
+    size_t bytes;
+    uint64_t print; /* fingerprint of sampled payload words: guards against a freed-and-reused host block */
+} col_entry_t;
+
+typedef struct {
+    void *dev;
+    size_t bytes;
+} pool_entry_t;
+
+static struct {
+    int ready;
+    const rfb_host_api_t *host;
+    rfb_ctx_t *ctx;
+    int64_t min_rows;
+    int scope_depth;
+    col_entry_t cols[MAX_COLS];
+    int ncols;
+    pool_entry_t pool[MAX_COLS]; /* free device buffers kept for reuse */
+    int npool;
+    char err[256];
+} G;
+
+static void set_err(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(G.err, sizeof(G.err), fmt, ap);
+    va_end(ap);
+}
+const char *rfb_ops_last_error(void) { return G.err; }
+
+/* ------------------------------------------------------------------ builtin malloc host (standalone / tests) */
+
+static int type_size(int t) {
+    switch (t) {
+        case RFB_T_B8: case RFB_T_U8: return 1;
+        case RFB_T_I16: return 2;
+        case RFB_T_I32: case RFB_T_DATE: case RFB_T_TIME: return 4;
+        case RFB_T_I64: case RFB_T_SYMBOL: case RFB_T_TIMESTAMP: case RFB_T_F64: return 8;
+        default: return 0;
+    }
+}
+static int is_listlike(int t) { return t == RFB_T_LIST || t == RFB_T_MAPFILTER || t == RFB_T_MAPGROUP; }
+
+static rfb_obj_t bh_null = {0, 0, RFB_T_NULL, 0, 1, {0}};
+static rfb_obj_t bh_err = {0, 0, RFB_T_ERR, 0, 1, {0}};
+static __thread const char *bh_last_err = "";
+
+static obj_p bh_vector(int8_t type, int64_t len) {
+    const int t = type < 0 ? -type : type;
+    const int64_t w = (t == RFB_T_LIST) ? 8 : type_size(t);
+    obj_p o = (obj_p)calloc(1, 16 + (size_t)(len > 0 ? len : 0) * (size_t)(w ? w : 8) + 16);
+    if (!o) return NULL;
+    o->type = (int8_t)t;
+    o->rc = 1;
+    o->len = len;
+    return o;
+}
+static obj_p bh_atom(int8_t type) {
+    obj_p o = (obj_p)calloc(1, 16);
+    if (!o) return NULL;
+    o->type = (int8_t)-type;
+    o->rc = 1;
+    return o;
+}
+static obj_p bh_clone(obj_p o) {
+    if (o && o != &bh_null && o != &bh_err) __atomic_add_fetch(&o->rc, 1, __ATOMIC_RELAXED);
+    return o;
+}
+static void bh_drop(obj_p o) {
+    if (!o || o == &bh_null || o == &bh_err) return;
+    if (__atomic_sub_fetch(&o->rc, 1, __ATOMIC_ACQ_REL) != 0) return;
+    if (is_listlike(o->type))
+        for (int64_t i = 0; i < o->len; i++) bh_drop(RFB_OBJ_LIST(o)[i]);
+    free(o);
+}
+static obj_p bh_err_type(void) { bh_last_err = "type"; return &bh_err; }
+static obj_p bh_err_length(void) { bh_last_err = "length"; return &bh_err; }
+static obj_p bh_err_limit(void) { bh_last_err = "limit"; return &bh_err; }
+const char *rfb_ops_builtin_last_error(void) { return bh_last_err; }
+
+static const rfb_host_api_t builtin_host = {bh_vector, bh_atom, bh_clone, bh_drop, bh_err_type, bh_err_length, bh_err_limit, &bh_null};
+const rfb_host_api_t *rfb_ops_builtin_host(void) { return &builtin_host; }
+
+/* ------------------------------------------------------------------ init / scope / device columns */
+
+int rfb_ops_init(const rfb_host_api_t *host, int device) {
+    if (G.ready) return 0;
+    if (!host) { set_err("rfb_ops_init: host api is NULL"); return RFB_ERR_ARG; }
+    int rc = rfb_ctx_create(device, &G.ctx);
+    if (rc) { set_err("%s", rfb_last_error()); return rc; }
+    G.host = host;
+    const char *e = getenv("RFB200_MIN_ROWS");
+    G.min_rows = e ? atoll(e) : 0;
+    G.ready = 1;
+    return 0;
+}
+
+static void release_columns(void) {
+    for (int i = 0; i < G.ncols; i++) {
+        if (G.npool < MAX_COLS) { G.pool[G.npool].dev = G.cols[i].dev; G.pool[G.npool].bytes = G.cols[i].bytes; G.npool++; }
+        else rfb_dev_free(G.ctx, G.cols[i].dev);
+    }
+    G.ncols = 0;
+}
+
+void rfb_ops_shutdown(void) {
+    if (!G.ready) return;
+    release_columns();
+    for (int i = 0; i < G.npool; i++) rfb_dev_free(G.ctx, G.pool[i].dev);
+    G.npool = 0;
+    rfb_ctx_destroy(G.ctx);
+    memset(&G, 0, sizeof(G));
+}
+
+void rfb_ops_set_min_rows(int64_t n) { G.min_rows = n; }
+int64_t rfb_ops_launches(void) { return G.ready ? rfb_launch_count(G.ctx) : 0; }
+void rfb_ops_scope_begin(void) { G.scope_depth++; }
+void rfb_ops_scope_end(void) {
+    if (G.scope_depth > 0 && --G.scope_depth == 0 && G.ready) { rfb_sync(G.ctx); release_columns(); }
+}
+
+/* 64 strided 8-byte samples + the tail, mixed.  The host may free a vector and get the same block back for a different
+ * vector of the same shape inside one scope; a stale HBM image must not be served for it. */
+static uint64_t fingerprint(const void *payload, size_t bytes) {
+    uint64_t h = 0x9E3779B97F4A7C15ULL ^ bytes, w;
+    if (bytes < 8) { w = 0; memcpy(&w, payload, bytes); return h ^ w; }
+    const size_t step = (bytes / 64) & ~(size_t)7;
+    for (int i = 0; i < 64; i++) {
+        memcpy(&w, (const char *)payload + (step ? step * i : 0), 8);
+        h = (h ^ w) * 0xBF58476D1CE4E5B9ULL;
+        h ^= h >> 29;
+        if (!step) break;
+    }
+    memcpy(&w, (const char *)payload + bytes - 8, 8);
+    return (h ^ w) * 0x94D049BB133111EBULL;
+}
+
+/* a device buffer of at least `bytes` (from the reuse pool when one fits within 2x) */
+static void *dev_buffer(size_t bytes, size_t *got) {
+    if (bytes == 0) bytes = 16;
+    int best = -1;
+    for (int i = 0; i < G.npool; i++)
+        if (G.pool[i].bytes >= bytes && G.pool[i].bytes <= 2 * bytes + 4096 && (best < 0 || G.pool[i].bytes < G.pool[best].bytes)) best = i;
+    if (best >= 0) {
+        void *d = G.pool[best].dev;
+        *got = G.pool[best].bytes;
+        G.pool[best] = G.pool[--G.npool];
+        return d;
+    }
+    void *d = NULL;
+    if (rfb_dev_alloc(G.ctx, bytes, &d) != RFB_OK) {
+        /* out of device memory: drop the pool and retry once */
+        for (int i = 0; i < G.npool; i++) rfb_dev_free(G.ctx, G.pool[i].dev);
+        G.npool = 0;
+        if (rfb_dev_alloc(G.ctx, bytes, &d) != RFB_OK) { set_err("%s", rfb_last_error()); return NULL; }
+    }
+    *got = bytes;
+    return d;
+}
+
+/* Track a device buffer for the rest of the scope (or this call).  host != NULL registers it as the HBM image of that
+ * host payload so later operators find it. */
+static int track(void *dev, size_t bytes, const void *host, int64_t len, int type) {
+    if (G.ncols == MAX_COLS) { /* table full: recycle the oldest entry */
+        rfb_sync(G.ctx);
+        if (G.npool < MAX_COLS) { G.pool[G.npool].dev = G.cols[0].dev; G.pool[G.npool].bytes = G.cols[0].bytes; G.npool++; }
+        else rfb_dev_free(G.ctx, G.cols[0].dev);
+        memmove(&G.cols[0], &G.cols[1], sizeof(col_entry_t) * (MAX_COLS - 1));
+        G.ncols--;
+    }
+    col_entry_t *e = &G.cols[G.ncols++];
+    e->host = host; e->len = len; e->type = type; e->dev = dev; e->bytes = bytes;
+    e->print = host ? fingerprint(host, (size_t)len * type_size(type)) : 0;
+    return 0;
+}
+
+/* device image of a host vector's payload: cache hit inside a scope, else one cudaMemcpyAsync */
+static void *dev_column(obj_p v) {
+    const int w = type_size(v->type);
+    const void *payload = RFB_OBJ_PAYLOAD(v);
+    for (int i = 0; i < G.ncols; i++)
+        if (G.cols[i].host == payload && G.cols[i].len == v->len && G.cols[i].type == v->type) {
+            if (G.cols[i].print == fingerprint(payload, (size_t)v->len * w)) return G.cols[i].dev;
+            G.cols[i].host = NULL; /* the block was reused for other data: forget the image (buffer freed at scope end) */
+        }
+    size_t got = 0;
+    void *d = dev_buffer((size_t)v->len * w, &got);
+    if (!d) return NULL;
+    if (v->len > 0 && rfb_h2d(G.ctx, d, payload, (size_t)v->len * w) != RFB_OK) { set_err("%s", rfb_last_error()); rfb_dev_free(G.ctx, d); return NULL; }
+    track(d, got, payload, v->len, v->type);
+    return d;
+}
+
+/* scratch / result buffer on the device, alive until the end of the scope (or call) */
+static void *dev_temp(size_t bytes) {
+    size_t got = 0;
+    void *d = dev_buffer(bytes, &got);
+    if (d) track(d, got, NULL, 0, 0);
+    return d;
+}
+
+/* host vector of `type` filled from device memory; the device copy is registered as its HBM image */
+static obj_p to_host_vector(int type, int64_t len, void *dev) {
+    obj_p r = G.host->vector((int8_t)type, len);
+    if (!r || r->type == RFB_T_ERR) return r ? r : G.host->err_limit();
+    if (len > 0) {
+        if (rfb_d2h(G.ctx, RFB_OBJ_PAYLOAD(r), dev, (size_t)len * type_size(type)) != RFB_OK || rfb_sync(G.ctx) != RFB_OK) {
+            set_err("%s", rfb_last_error());
+            G.host->drop_obj(r);
+            return G.host->err_limit();
+        }
+    }
+    for (int i = 0; i < G.ncols; i++)
+        if (G.cols[i].dev == dev) {
+            G.cols[i].host = RFB_OBJ_PAYLOAD(r); G.cols[i].len = len; G.cols[i].type = type;
+            G.cols[i].print = fingerprint(RFB_OBJ_PAYLOAD(r), (size_t)len * type_size(type));
+        }
+    return r;
+}
+
+typedef struct { int entered; } call_scope_t;
+static call_scope_t enter(void) { call_scope_t c = {1}; G.scope_depth++; return c; }
+static void leave(call_scope_t c) { if (c.entered) rfb_ops_scope_end(); }
+
+static obj_p status_to_obj(int rc) {
+    set_err("%s", rfb_last_error());
+    switch (rc) {
+        case RFB_ERR_TYPE: return G.host->err_type();
+        case RFB_ERR_LENGTH: return G.host->err_length();
+        default: return G.host->err_limit();
+    }
+}
+
+/* ------------------------------------------------------------------ operand classification */
+
+static int is_num_type(int t) { return type_size(t) != 0; }
+static int is_vec(obj_p o) { return o && o->type > 0 && is_num_type(o->type); }
+static int is_atom(obj_p o) { return o && o->type < 0 && is_num_type(-o->type); }
+static int too_small(int64_t n) { return n < G.min_rows; }
+
+static rfb_scalar_t scalar_of(obj_p a) {
+    rfb_scalar_t s;
+    memset(&s, 0, sizeof(s));
+    s.type = -a->type;
+    switch (type_size(s.type)) {
+        case 1: s.v.u8 = a->u8; break;
+        case 2: s.v.i16 = a->i16; break;
+        case 4: s.v.i32 = a->i32; break;
+        default: s.v.i64 = a->i64; break;
+    }
+    return s;
+}
+
+static obj_p make_atom(int type, const void *bits) {
+    obj_p a = G.host->atom((int8_t)type);
+    if (!a) return G.host->err_limit();
+    a->i64 = 0;
+    memcpy(&a->i64, bits, (size_t)type_size(type));
+    return a;
+}
+
+/* ------------------------------------------------------------------ comparisons */
+
+static obj_p cmp_op(int op, obj_p x, obj_p y) {
+    if (!G.ready) return NULL;
+    const int xv = is_vec(x), yv = is_vec(y);
+    if (!(xv || yv) || !((xv || is_atom(x)) && (yv || is_atom(y)))) return NULL; /* atoms only, lists, tables, enums... */
+    const int64_t n = xv ? x->len : y->len;
+    if (xv && yv && x->len != y->len) return G.host->err_length();
+    if (too_small(n)) return NULL;
+    call_scope_t sc = enter();
+    obj_p res = NULL;
+    const int xt = xv ? x->type : -x->type, yt = yv ? y->type : -y->type;
+    rfb_scalar_t xs, ys;
+    void *dx = NULL, *dy = NULL;
+    if (xv) { dx = dev_column(x); if (!dx) { res = G.host->err_limit(); goto out; } } else xs = scalar_of(x);
+    if (yv) { dy = dev_column(y); if (!dy) { res = G.host->err_limit(); goto out; } } else ys = scalar_of(y);
+    void *dm = dev_temp((size_t)n);
+    if (!dm) { res = G.host->err_limit(); goto out; }
+    int rc = rfb_cmp_dev(G.ctx, op, xt, dx, xv ? n : -1, xv ? NULL : &xs, yt, dy, yv ? n : -1, yv ? NULL : &ys, (uint8_t *)dm);
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = to_host_vector(RFB_T_B8, n, dm);
+out:
+    leave(sc);
+    return res;
+}
+obj_p rfb_ray_eq(obj_p x, obj_p y) { return cmp_op(RFB_EQ, x, y); }
+obj_p rfb_ray_ne(obj_p x, obj_p y) { return cmp_op(RFB_NE, x, y); }
+obj_p rfb_ray_lt(obj_p x, obj_p y) { return cmp_op(RFB_LT, x, y); }
+obj_p rfb_ray_gt(obj_p x, obj_p y) { return cmp_op(RFB_GT, x, y); }
+obj_p rfb_ray_le(obj_p x, obj_p y) { return cmp_op(RFB_LE, x, y); }
+obj_p rfb_ray_ge(obj_p x, obj_p y) { return cmp_op(RFB_GE, x, y); }
+
+/* ------------------------------------------------------------------ where / filter */
+
+obj_p rfb_ray_where(obj_p mask) {
+    if (!G.ready || !mask) return NULL;
+    if (mask->type != RFB_T_B8) return (mask->type > 0 && is_num_type(mask->type)) ? G.host->err_type() : NULL;
+    if (too_small(mask->len)) return NULL;
+    call_scope_t sc = enter();
+    obj_p res;
+    const int64_t n = mask->len;
+    void *dm = dev_column(mask), *di = dev_temp((size_t)(n > 0 ? n : 1) * 8);
+    int64_t cnt = 0;
+    if (!dm || !di) { res = G.host->err_limit(); goto out; }
+    int rc = rfb_where_dev(G.ctx, (const uint8_t *)dm, n, (int64_t *)di, &cnt);
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = to_host_vector(RFB_T_I64, cnt, di);
+out:
+    leave(sc);
+    return res;
+}
+
+static obj_p pair_of(obj_p a, obj_p b, int type) {
+    obj_p r = G.host->vector(RFB_T_LIST, 2);
+    if (!r || r->type == RFB_T_ERR) return r ? r : G.host->err_limit();
+    RFB_OBJ_LIST(r)[0] = G.host->clone_obj(a);
+    RFB_OBJ_LIST(r)[1] = G.host->clone_obj(b);
+    r->type = (int8_t)type;
+    return r;
+}
+obj_p rfb_filter_map(obj_p val, obj_p index) { return (G.ready && is_vec(val) && index) ? pair_of(val, index, RFB_T_MAPFILTER) : NULL; }
+obj_p rfb_group_map(obj_p val, obj_p index) { return (G.ready && is_vec(val) && index) ? pair_of(val, index, RFB_T_MAPGROUP) : NULL; }
+
+obj_p rfb_filter_collect(obj_p val, obj_p index) {
+    if (!G.ready || !is_vec(val) || !index || index->type != RFB_T_I64) return NULL;
+    if (too_small(index->len)) return NULL;
+    call_scope_t sc = enter();
+    obj_p res;
+    const int64_t m = index->len;
+    void *dc = dev_column(val), *di = dev_column(index), *dout = dev_temp((size_t)(m > 0 ? m : 1) * type_size(val->type));
+    if (!dc || !di || !dout) { res = G.host->err_limit(); goto out; }
+    int rc = rfb_gather_dev(G.ctx, val->type, dc, (const int64_t *)di, m, dout);
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = to_host_vector(val->type, m, dout);
+out:
+    leave(sc);
+    return res;
+}
+
+/* ------------------------------------------------------------------ ungrouped folds */
+
+enum { F_SUM, F_MIN, F_MAX, F_AVG, F_CNT };
+
+/* result atom typing: ray_sum_partial core/math.c:1850-1871, ray_min/max :1922-2045, ray_avg :2445-2526 */
+static obj_p fold_result(int what, int type, const rfb_fold_t *f) {
+    const int flt = (type == RFB_T_F64);
+    switch (what) {
+        case F_CNT: return make_atom(RFB_T_I64, &f->nonnull);
+        case F_SUM:
+            if (flt) return make_atom(RFB_T_F64, &f->sum_f64);
+            if (type == RFB_T_I32 || type == RFB_T_TIME) { int32_t s = (int32_t)f->sum_i64; return make_atom(type, &s); }
+            return make_atom(RFB_T_I64, &f->sum_i64);
+        case F_MIN: case F_MAX: {
+            if (flt) return make_atom(RFB_T_F64, what == F_MIN ? &f->min_f64 : &f->max_f64);
+            int64_t v = what == F_MIN ? f->min_i64 : f->max_i64;
+            return make_atom(type, &v); /* little endian: the low bytes are the narrow value */
+        }
+        default: { /* avg = sum / non-null count, 0Nf when nothing was counted (FDIVI64 / FDIVF64 core/ops.h:173-174) */
+            double r;
+            if (f->nonnull == 0) r = NAN;
+            else if (flt) r = f->sum_f64 / (double)f->nonnull;
+            else r = (double)f->sum_i64 / (double)f->nonnull;
+            return make_atom(RFB_T_F64, &r);
+        }
+    }
+}
+
+static int fold_type_ok(int what, int type) {
+    switch (what) {
+        case F_SUM: return type == RFB_T_U8 || type == RFB_T_I16 || type == RFB_T_I32 || type == RFB_T_I64 || type == RFB_T_F64 || type == RFB_T_TIME;
+        case F_AVG: return type == RFB_T_U8 || type == RFB_T_I16 || type == RFB_T_I32 || type == RFB_T_I64 || type == RFB_T_F64;
+        case F_CNT: return type != RFB_T_B8 && type != RFB_T_SYMBOL;
+        default: return type != RFB_T_B8 && type != RFB_T_SYMBOL;
+    }
+}
+
+static obj_p aggr_op(int op, obj_p val, obj_p index);
+
+static obj_p fold_op(int what, obj_p x) {
+    if (!G.ready || !x) return NULL;
+    if (x->type == RFB_T_MAPGROUP && x->len == 2) {
+        static const int A[] = {RFB_A_SUM, RFB_A_MIN, RFB_A_MAX, RFB_A_AVG, -1};
+        return A[what] < 0 ? NULL : aggr_op(A[what], RFB_OBJ_LIST(x)[0], RFB_OBJ_LIST(x)[1]);
+    }
+    obj_p col = x, ids = NULL;
+    if (x->type == RFB_T_MAPFILTER && x->len == 2) { col = RFB_OBJ_LIST(x)[0]; ids = RFB_OBJ_LIST(x)[1]; if (!ids || ids->type != RFB_T_I64) return NULL; }
+    if (!is_vec(col)) return NULL;
+    if (!fold_type_ok(what, col->type)) return G.host->err_type();
+    const int64_t n = ids ? ids->len : col->len;
+    if (too_small(n)) return NULL;
+    call_scope_t sc = enter();
+    obj_p res;
+    rfb_fold_t f;
+    const int folds = (what == F_MIN || what == F_MAX) ? (RFB_F_MIN | RFB_F_MAX) : (RFB_F_SUM | RFB_F_CNT);
+    void *dc = dev_column(col), *di = ids ? dev_column(ids) : NULL;
+    if (!dc || (ids && !di)) { res = G.host->err_limit(); goto out; }
+    int rc = ids ? rfb_gather_fold_dev(G.ctx, folds, col->type, dc, (const int64_t *)di, n, &f)
+                 : rfb_fold_dev(G.ctx, folds, col->type, dc, n, &f);
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = fold_result(what, col->type, &f);
+out:
+    leave(sc);
+    return res;
+}
+obj_p rfb_ray_sum(obj_p x) { return fold_op(F_SUM, x); }
+obj_p rfb_ray_min(obj_p x) { return fold_op(F_MIN, x); }
+obj_p rfb_ray_max(obj_p x) { return fold_op(F_MAX, x); }
+obj_p rfb_ray_avg(obj_p x) { return fold_op(F_AVG, x); }
+obj_p rfb_ray_cnt(obj_p x) { return fold_op(F_CNT, x); }
+
+/* ------------------------------------------------------------------ element-wise */
+
+static obj_p bin_op(int op, obj_p x, obj_p y) {
+    if (!G.ready) return NULL;
+    const int xv = is_vec(x), yv = is_vec(y);
+    if (!(xv || yv) || !((xv || is_atom(x)) && (yv || is_atom(y)))) return NULL;
+    const int xt = xv ? x->type : -x->type, yt = yv ? y->type : -y->type;
+    const int ot = rfb_binop_type(op, xt, yt);
+    if (ot < 0) return NULL; /* the reference's matrix is wider (dates, times, u8...): leave those to the CPU body */
+    if (xv && yv && x->len != y->len) return G.host->err_length();
+    const int64_t n = xv ? x->len : y->len;
+    if (too_small(n)) return NULL;
+    call_scope_t sc = enter();
+    obj_p res;
+    rfb_scalar_t xs, ys;
+    void *dx = NULL, *dy = NULL;
+    if (xv) { dx = dev_column(x); if (!dx) { res = G.host->err_limit(); goto out; } } else xs = scalar_of(x);
+    if (yv) { dy = dev_column(y); if (!dy) { res = G.host->err_limit(); goto out; } } else ys = scalar_of(y);
+    void *dout = dev_temp((size_t)(n > 0 ? n : 1) * type_size(ot));
+    if (!dout) { res = G.host->err_limit(); goto out; }
+    int rc = rfb_binop_dev(G.ctx, op, xt, dx, xv ? n : -1, xv ? NULL : &xs, yt, dy, yv ? n : -1, yv ? NULL : &ys, dout);
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = to_host_vector(ot, n, dout);
+out:
+    leave(sc);
+    return res;
+}
+obj_p rfb_ray_add(obj_p x, obj_p y) { return bin_op(RFB_ADD, x, y); }
+obj_p rfb_ray_sub(obj_p x, obj_p y) { return bin_op(RFB_SUB, x, y); }
+obj_p rfb_ray_mul(obj_p x, obj_p y) { return bin_op(RFB_MUL, x, y); }
+obj_p rfb_ray_div(obj_p x, obj_p y) { return bin_op(RFB_DIV, x, y); }
+obj_p rfb_ray_fdiv(obj_p x, obj_p y) { return bin_op(RFB_FDIV, x, y); }
+obj_p rfb_ray_mod(obj_p x, obj_p y) { return bin_op(RFB_MOD, x, y); }
+
+static obj_p un_op(int op, obj_p x) {
+    if (!G.ready || !x || x->type != RFB_T_F64) return NULL; /* integer / temporal inputs are returned as-is by the CPU body */
+    if (too_small(x->len)) return NULL;
+    call_scope_t sc = enter();
+    obj_p res;
+    void *dx = dev_column(x), *dout = dev_temp((size_t)(x->len > 0 ? x->len : 1) * 8);
+    if (!dx || !dout) { res = G.host->err_limit(); goto out; }
+    int rc = rfb_unop_f64_dev(G.ctx, op, (const double *)dx, x->len, (double *)dout);
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = to_host_vector(RFB_T_F64, x->len, dout);
+out:
+    leave(sc);
+    return res;
+}
+obj_p rfb_ray_round(obj_p x) { return un_op(RFB_ROUND, x); }
+obj_p rfb_ray_floor(obj_p x) { return un_op(RFB_FLOOR, x); }
+obj_p rfb_ray_ceil(obj_p x) { return un_op(RFB_CEIL, x); }
+
+/* ------------------------------------------------------------------ group-by */
+
+static int is_null_obj(obj_p o) { return !o || o == G.host->null_obj || o->type == RFB_T_NULL; }
+
+static obj_p i64_atom(int64_t v) { return make_atom(RFB_T_I64, &v); }
+
+obj_p rfb_index_group(obj_p keys, obj_p filter) {
+    if (!G.ready || !keys) return NULL;
+    /* index_group has no I32/DATE/TIME case (core/index.c:2177-2224): single-key grouping exists for I64-kind keys */
+    if (!(keys->type == RFB_T_I64 || keys->type == RFB_T_SYMBOL || keys->type == RFB_T_TIMESTAMP)) return NULL;
+    const int filtered = !is_null_obj(filter);
+    if (filtered && filter->type != RFB_T_I64) return NULL; /* parted filters */
+    const int64_t len = filtered ? filter->len : keys->len;
+    if (too_small(len)) return NULL;
+    call_scope_t sc = enter();
+    obj_p res = NULL, gids = NULL, firsts = NULL;
+    rfb_group_info_t info;
+    void *dk = dev_column(keys), *df = filtered ? dev_column(filter) : NULL;
+    void *dg = dev_temp((size_t)(len > 0 ? len : 1) * 8), *dfi = dev_temp((size_t)(len > 0 ? len : 1) * 8);
+    if (!dk || (filtered && !df) || !dg || !dfi) { res = G.host->err_limit(); goto out; }
+    int rc = rfb_group_i64_dev(G.ctx, (const int64_t *)dk, (const int64_t *)df, len, (int64_t *)dg, (int64_t *)dfi, &info);
+    if (rc) { res = status_to_obj(rc); goto out; }
+    gids = to_host_vector(RFB_T_I64, len, dg);
+    firsts = to_host_vector(RFB_T_I64, info.groups, dfi);
+    res = G.host->vector(RFB_T_LIST, 7);
+    if (!res || res->type == RFB_T_ERR || gids->type == RFB_T_ERR || firsts->type == RFB_T_ERR) { res = G.host->err_limit(); goto out; }
+    RFB_OBJ_LIST(res)[0] = i64_atom(RFB_INDEX_IDS);
+    RFB_OBJ_LIST(res)[1] = i64_atom(info.groups);
+    RFB_OBJ_LIST(res)[2] = gids;
+    RFB_OBJ_LIST(res)[3] = i64_atom(RFB_NULL_I64);
+    RFB_OBJ_LIST(res)[4] = G.host->null_obj;
+    RFB_OBJ_LIST(res)[5] = filtered ? G.host->clone_obj(filter) : G.host->null_obj;
+    RFB_OBJ_LIST(res)[6] = firsts;
+out:
+    leave(sc);
+    return res;
+}
+
+static obj_p aggr_op(int op, obj_p val, obj_p index) {
+    if (!G.ready || !is_vec(val) || !index || index->type != RFB_T_LIST || index->len != 7) return NULL;
+    obj_p *ix = RFB_OBJ_LIST(index);
+    if (!ix[0] || ix[0]->type != -RFB_T_I64 || ix[0]->i64 != RFB_INDEX_IDS) return NULL; /* SHIFT / parted / window indices: CPU body */
+    obj_p gids = ix[2], filter = ix[5];
+    if (!gids || gids->type != RFB_T_I64) return NULL;
+    const int filtered = !is_null_obj(filter);
+    if (filtered && filter->type != RFB_T_I64) return NULL;
+    const int64_t groups = ix[1]->i64, len = gids->len;
+    const int ot = rfb_aggr_type(op, val->type);
+    if (ot < 0) return G.host->err_type();
+    if (too_small(len)) return NULL;
+    call_scope_t sc = enter();
+    obj_p res;
+    void *dv = dev_column(val), *dg = dev_column(gids), *df = filtered ? dev_column(filter) : NULL;
+    void *dout = dev_temp((size_t)(groups > 0 ? groups : 1) * 8);
+    if (!dv || !dg || (filtered && !df) || !dout) { res = G.host->err_limit(); goto out; }
+    int rc = rfb_aggr_dev(G.ctx, op, val->type, dv, (const int64_t *)df, (const int64_t *)dg, len, groups, dout);
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = to_host_vector(ot, groups, dout);
+out:
+    leave(sc);
+    return res;
+}
+obj_p rfb_aggr_sum(obj_p v, obj_p i) { return aggr_op(RFB_A_SUM, v, i); }
+obj_p rfb_aggr_min(obj_p v, obj_p i) { return aggr_op(RFB_A_MIN, v, i); }
+obj_p rfb_aggr_max(obj_p v, obj_p i) { return aggr_op(RFB_A_MAX, v, i); }
+obj_p rfb_aggr_count(obj_p v, obj_p i) { return aggr_op(RFB_A_COUNT, v, i); }
+obj_p rfb_aggr_avg(obj_p v, obj_p i) { return aggr_op(RFB_A_AVG, v, i); }
+
+/* ------------------------------------------------------------------ sort */
+
+static obj_p sort_op(obj_p x, int desc) {
+    if (!G.ready || !is_vec(x) || x->type == RFB_T_SYMBOL) return NULL; /* symbols sort by string: CPU body */
+    if (x->attrs != 0) return NULL;                                     /* ATTR_ASC/DESC shortcut (core/sort.c:437-451) */
+    if (too_small(x->len)) return NULL;
+    call_scope_t sc = enter();
+    obj_p res;
+    void *dx = dev_column(x), *dp = dev_temp((size_t)(x->len > 0 ? x->len : 1) * 8);
+    if (!dx || !dp) { res = G.host->err_limit(); goto out; }
+    int rc = rfb_sort_dev(G.ctx, x->type, dx, x->len, desc, (int64_t *)dp);
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = to_host_vector(RFB_T_I64, x->len, dp);
+out:
+    leave(sc);
+    return res;
+}
+obj_p rfb_ray_sort_asc(obj_p x) { return sort_op(x, 0); }
+obj_p rfb_ray_sort_desc(obj_p x) { return sort_op(x, 1); }
+
+/* ------------------------------------------------------------------ fused query entry points */
+
+static obj_p where_fold(int op, int what, obj_p pred, obj_p k, obj_p val) {
+    if (!G.ready || !is_vec(pred) || !is_vec(val) || !is_atom(k)) return G.ready ? G.host->err_type() : NULL;
+    if (pred->len != val->len) return G.host->err_length();
+    if (op < RFB_EQ || op > RFB_GE || what < F_SUM || what > F_AVG || !fold_type_ok(what, val->type)) return G.host->err_type();
+    rfb_fold_t f;
+    rfb_scalar_t ks = scalar_of(k);
+    const int folds = (what == F_MIN || what == F_MAX) ? (RFB_F_MIN | RFB_F_MAX) : (RFB_F_SUM | RFB_F_CNT);
+    int rc;
+    if (G.scope_depth == 0) {
+        /* one-shot: stream the host column(s) through the chunked copy/compute pipeline (no device residency needed) */
+        rc = rfb_filter_fold_host(G.ctx, op, pred->type, RFB_OBJ_PAYLOAD(pred), &ks, folds, val->type, RFB_OBJ_PAYLOAD(val), pred->len, 0, &f, NULL);
+    } else {
+        void *dp = dev_column(pred), *dv = (val == pred) ? dp : dev_column(val);
+        if (!dp || !dv) return G.host->err_limit();
+        rc = rfb_filter_fold_dev(G.ctx, op, pred->type, dp, &ks, folds, val->type, dv, pred->len, &f);
+    }
+    if (rc) return status_to_obj(rc);
+    return fold_result(what, val->type, &f);
+}
+
+obj_p rfb_where_lt_sum(obj_p col, obj_p k) { return where_fold(RFB_LT, F_SUM, col, k, col); }
+
+obj_p rfb_where_fold(obj_p *args, int64_t n) {
+    if (!G.ready) return NULL;
+    if (n != 5 || !args[0] || !args[1] || args[0]->type != -RFB_T_I64 || args[1]->type != -RFB_T_I64) return G.host->err_type();
+    return where_fold((int)args[0]->i64, (int)args[1]->i64, args[2], args[3], args[4]);
+}

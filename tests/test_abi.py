@@ -11,8 +11,8 @@ from rayforce_b200 import capi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_functions():
-    src = open(os.path.join(ROOT, "include", "rfb200.h")).read()
+def declared_functions(header="rfb200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = re.findall(r"\b(rfb_[a-z0-9_]+)\s*\(", src)
     return sorted(set(n for n in names if not n.endswith("_t")))
@@ -56,3 +56,28 @@ def test_no_cpu_fallback_without_a_device():
     from rayforce_b200 import Context, RfbError
     with pytest.raises(RfbError):
         Context(0)
+
+
+def test_operator_layer_exports_every_declared_symbol():
+    """include/rfb200_ops.h: the reference-facing operator layer (pure C) — same check, no compute"""
+    from rayforce_b200 import ops
+    assert os.path.exists(ops.OPS_PATH), "run __graft_entry__.build() first"
+    capi.load()
+    lib = C.CDLL(ops.OPS_PATH)
+    names = [n for n in declared_functions("rfb200_ops.h") if n.startswith("rfb_")]
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    # every operator the Python harness binds is declared in the header
+    for n in ops.UNARY + ops.BINARY:
+        assert "rfb_" + n in names, n
+    # the builtin host hands out objects with the reference's 16-byte header layout (core/rayforce.h:112-133)
+    lib.rfb_ops_builtin_host.restype = C.POINTER(ops.HostApi)
+    host = lib.rfb_ops_builtin_host().contents
+    v = host.vector(capi.I64, 3)
+    assert C.c_int8.from_address(v + 2).value == capi.I64 and C.c_uint32.from_address(v + 4).value == 1
+    assert C.c_int64.from_address(v + 8).value == 3
+    host.drop_obj(v)
+    a = host.atom(capi.F64)
+    assert C.c_int8.from_address(a + 2).value == -capi.F64
+    host.drop_obj(a)

@@ -1,0 +1,199 @@
+"""GPU parity of the reference-facing operator layer (include/rfb200_ops.h): reference obj_t objects in, objects out.
+The first block replays known answers of the reference's OWN tests (tests/golden/, extracted from tests/lang.c and
+tests/sort.c of the reference) through the operators `ray_sum`, `ray_lt`, `ray_add`, ... exactly as its evaluator
+would call them; the second block walks the operator sequences of SURVEY §3.1-3.4 (select where / by, avg of an
+expression, iasc) and compares every intermediate object with the oracle."""
+import collections
+
+import numpy as np
+import pytest
+
+from oracle import bindings as ob
+from rayforce_b200 import capi
+from rayforce_b200.ops import Ops, OpsError, Declined, MAPFILTER, MAPGROUP
+from tests import golden_io
+from tests.util import rng_col, same_f64, f64_sum_ok
+
+pytestmark = pytest.mark.gpu
+
+NAME = {"sum": "ray_sum", "avg": "ray_avg", "min": "ray_min", "max": "ray_max", "where": "ray_where", "round": "ray_round",
+        "floor": "ray_floor", "ceil": "ray_ceil", "iasc": "ray_sort_asc", "idesc": "ray_sort_desc",
+        "eq": "ray_eq", "ne": "ray_ne", "lt": "ray_lt", "gt": "ray_gt", "le": "ray_le", "ge": "ray_ge", "add": "ray_add",
+        "sub": "ray_sub", "mul": "ray_mul", "div": "ray_div", "fdiv": "ray_fdiv", "mod": "ray_mod"}
+UNOPS = ("round", "floor", "ceil")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    return Ops.get(0)
+
+
+def test_reference_goldens_through_the_operator_layer(ops):
+    """every golden whose operands the GPU layer accepts must reproduce the reference's answer; the rest must be DECLINED
+    (never silently different).  Atom-only forms are the CPU body's job by contract."""
+    ran, declined, bad = collections.Counter(), collections.Counter(), []
+    for c in golden_io.load_cases():
+        if c["op"] not in NAME:
+            continue
+        args = []
+        for a in c["args"]:
+            t, atom, arr = golden_io.decode(a)
+            args.append(ops.atom(t, arr[0]) if atom else ops.vec(t, arr))
+        r = ops.call(NAME[c["op"]], *args)
+        try:
+            got, gt = ops.value(r)
+        except Declined:
+            declined[c["op"]] += 1
+            ops.drop(*args)
+            continue
+        except OpsError as e:
+            if c.get("error") != e.kind:
+                bad.append((c["src"], c["expr"], "raised %s" % e.kind))
+            ran[c["op"]] += 1
+            ops.drop(*args)
+            continue
+        ops.drop(*args)
+        if "error" in c:
+            bad.append((c["src"], c["expr"], "returned a value, reference raises " + c["error"]))
+            continue
+        et, eatom, earr = golden_io.decode(c["expect"])
+        garr = np.atleast_1d(got)
+        if et == ob.F64:
+            ok = gt == et and same_f64(garr, earr, zero_sign=c["op"] not in UNOPS, max_ulp=1 if c["op"] == "fdiv" else 0)
+        else:
+            ok = gt == et and garr.shape == earr.shape and np.array_equal(garr.astype(np.int64), earr.astype(np.int64))
+        if not ok:
+            bad.append((c["src"], c["expr"], "got %d %r want %d %r" % (gt, garr[:6], et, earr[:6])))
+        ran[c["op"]] += 1
+    assert not bad, "%d mismatches: %r" % (len(bad), bad[:8])
+    for op, least in (("sum", 8), ("min", 8), ("max", 8), ("avg", 5), ("lt", 3), ("add", 15), ("sub", 15), ("mul", 10), ("div", 50),
+                      ("fdiv", 50), ("mod", 50), ("iasc", 8), ("idesc", 8), ("where", 2), ("floor", 1)):
+        assert ran[op] >= least, (op, ran[op], declined[op])
+    assert ops.launches > 500
+
+
+def test_select_where_sum_operator_sequence(ops, oracle):
+    """ray_lt -> ray_where -> filter_map -> ray_sum(MAPFILTER) and filter_collect, inside one query scope"""
+    n = 300_007
+    col = rng_col(ob.I64, n, 5, null_frac=0.01, lo=-1000, hi=1000)
+    x, k = ops.vec(ob.I64, col), ops.atom(ob.I64, 37)
+    with ops.scope():
+        mask = ops.call("ray_lt", x, k)
+        m, mt = ops.value(mask, drop=False)
+        assert mt == ob.B8 and np.array_equal(m, oracle.cmp(ob.LT, ob.I64, col, ob.I64, 37))
+        ids = ops.call("ray_where", mask)
+        i, it = ops.value(ids, drop=False)
+        assert it == ob.I64 and np.array_equal(i, oracle.where(m))
+        lazy = ops.call("filter_map", x, ids)
+        assert ops.type_of(lazy) == MAPFILTER
+        sel = oracle.at_ids(ob.I64, col, i)
+        for name, op in (("ray_sum", ob.SUM), ("ray_min", ob.MIN), ("ray_max", ob.MAX), ("ray_avg", ob.AVG)):
+            got, gt = ops.value(ops.call(name, lazy))
+            want, wt = oracle.fold(op, ob.I64, sel)
+            assert gt == wt and (same_f64([got], [want]) if wt == ob.F64 else int(got) == int(want)), name
+        g, gt = ops.value(ops.call("filter_collect", x, ids))
+        assert gt == ob.I64 and np.array_equal(g, sel)
+        ops.drop(lazy, ids, mask)
+    # the fused entry point gives the same answer in one pass (outside a scope: streamed from the host column)
+    got, gt = ops.value(ops.call("where_lt_sum", x, k))
+    assert gt == ob.I64 and int(got) == int(oracle.fold(ob.SUM, ob.I64, sel)[0])
+    got, gt = ops.value(ops.where_fold(capi.LT, 3, x, k, x))
+    assert gt == ob.F64 and same_f64([got], [oracle.fold(ob.AVG, ob.I64, sel)[0]])
+    ops.drop(x, k)
+
+
+@pytest.mark.parametrize("filtered", [False, True])
+def test_select_by_operator_sequence(ops, oracle, filtered):
+    """index_group -> group_map -> ray_sum(MAPGROUP) / aggr_*; index object layout of core/index.c:1696-1699"""
+    n = 200_003
+    r = np.random.default_rng(1)
+    keys = (r.integers(0, 1000, n) - 17).astype(np.int64)
+    val = rng_col(ob.I64, n, 2, null_frac=0.001, lo=-1000, hi=1000)
+    filt = np.sort(r.choice(n, n // 3, replace=False)).astype(np.int64) if filtered else None
+    wg, wf, wi = oracle.group_i64(keys, filt)
+    ko, vo = ops.vec(ob.I64, keys), ops.vec(ob.I64, val)
+    fo = ops.vec(ob.I64, filt) if filtered else ops.NULL
+    with ops.scope():
+        idx = ops.call("index_group", ko, fo)
+        it = ops.items(idx)
+        assert ops.len_of(idx) == 7 and ops.value(it[0], drop=False)[0] == capi.INDEX_IDS
+        assert int(ops.value(it[1], drop=False)[0]) == wi.groups
+        assert np.array_equal(ops.value(it[2], drop=False)[0], wg)
+        assert np.array_equal(ops.value(it[6], drop=False)[0], wf)
+        lazy = ops.call("group_map", vo, idx)
+        assert ops.type_of(lazy) == MAPGROUP
+        for name, op in (("aggr_sum", ob.SUM), ("aggr_min", ob.MIN), ("aggr_max", ob.MAX), ("aggr_count", ob.COUNT), ("aggr_avg", ob.AVG)):
+            got, gt = ops.value(ops.call(name, vo, idx))
+            want, wt = oracle.aggr(op, ob.I64, val, wg, wi.groups, filt)
+            assert gt == wt and (same_f64(got, want) if wt == ob.F64 else np.array_equal(got, want)), name
+        got, gt = ops.value(ops.call("ray_sum", lazy))           # FN_AGGR functions receive the lazy pair (eval.c:737)
+        assert np.array_equal(got, oracle.aggr(ob.SUM, ob.I64, val, wg, wi.groups, filt)[0])
+        ops.drop(lazy, idx)
+    ops.drop(ko, vo)
+    if filtered:
+        ops.drop(fo)
+
+
+def test_avg_of_expression_operator_sequence(ops, oracle):
+    """(avg (+ (* a b) c)) as ray_mul -> ray_add -> ray_avg"""
+    n = 250_001
+    a, b, c = (rng_col(ob.F64, n, s, null_frac=0.01, lo=0, hi=1) for s in (1, 2, 3))
+    ao, bo, co = (ops.vec(ob.F64, v) for v in (a, b, c))
+    with ops.scope():
+        t1 = ops.call("ray_mul", ao, bo)
+        t2 = ops.call("ray_add", t1, co)
+        want = oracle.binop(ob.ADD, ob.F64, oracle.binop(ob.MUL, ob.F64, a, ob.F64, b)[0], ob.F64, c)[0]
+        assert same_f64(ops.value(t2, drop=False)[0], want)
+        got, gt = ops.value(ops.call("ray_avg", t2))
+        cnt = np.count_nonzero(~np.isnan(want))
+        assert gt == ob.F64 and f64_sum_ok(float(got) * cnt, float(oracle.fold(ob.SUM, ob.F64, want)[0]), oracle.sum_f64_exact(want)) or \
+            abs(float(got) - float(oracle.fold(ob.AVG, ob.F64, want)[0])) <= 4 * np.spacing(abs(float(got)))
+        ops.drop(t1, t2)
+    ops.drop(ao, bo, co)
+
+
+def test_errors_and_declines_follow_the_reference(ops):
+    a, b = ops.vec(ob.I64, np.arange(10)), ops.vec(ob.I64, np.arange(11))
+    for name in ("ray_lt", "ray_add"):
+        with pytest.raises(OpsError) as e:                        # vec (op) vec of different length -> "length"
+            ops.value(ops.call(name, a, b))
+        assert e.value.kind == "length"
+    d = ops.vec(ob.DATE, np.arange(10))
+    with pytest.raises(OpsError) as e:                            # (sum [2020.02.03 ...]) -> "type" (tests/lang.c:2463)
+        ops.value(ops.call("ray_sum", d))
+    assert e.value.kind == "type"
+    u = ops.vec(ob.U8, np.arange(10))
+    with pytest.raises(OpsError) as e:                            # U8 vectors do not compare (core/cmp.c:78-85)
+        ops.value(ops.call("ray_eq", u, u))
+    assert e.value.kind == "type"
+    x, y = ops.atom(ob.I64, 1), ops.atom(ob.I64, 2)
+    with pytest.raises(Declined):                                 # atom (op) atom: the CPU body's job
+        ops.value(ops.call("ray_add", x, y))
+    k32 = ops.vec(ob.I32, np.arange(10))
+    with pytest.raises(Declined):                                 # no single-key grouping on I32 in the reference
+        ops.value(ops.call("index_group", k32, ops.NULL))
+    ops.drop(a, b, d, u, x, y, k32)
+
+
+def test_min_rows_threshold_declines_small_inputs(ops):
+    a = ops.vec(ob.I64, np.arange(100))
+    ops.L.rfb_ops_set_min_rows(1000)
+    try:
+        with pytest.raises(Declined):
+            ops.value(ops.call("ray_sum", a))
+    finally:
+        ops.L.rfb_ops_set_min_rows(0)
+    assert int(ops.value(ops.call("ray_sum", a))[0]) == 4950
+    ops.drop(a)
+
+
+def test_scope_does_not_serve_a_stale_image_when_the_host_reuses_a_block(ops):
+    with ops.scope():
+        a = ops.vec(ob.I64, np.arange(1000))
+        assert int(ops.value(ops.call("ray_sum", a))[0]) == 499500
+        # same block, same shape, different content (what a freed-and-reallocated temporary looks like)
+        import ctypes as C
+        new = np.arange(1000, dtype=np.int64) * 3
+        C.memmove(a + 16, new.ctypes.data, new.nbytes)
+        assert int(ops.value(ops.call("ray_sum", a))[0]) == 499500 * 3
+        ops.drop(a)

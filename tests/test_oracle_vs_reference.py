@@ -34,6 +34,18 @@ def test_cmp(oracle, reference, op, xt, yt):
         assert np.array_equal(oracle.cmp(op, xt, k, yt, y), reference.cmp(op, xt, k, yt, y))
 
 
+@pytest.mark.parametrize("op", CMPS)
+def test_cmp_date_vs_timestamp(oracle, reference, op):
+    n = 20_011
+    r = np.random.default_rng(op)
+    d = r.integers(8000, 8010, n).astype(np.int32)
+    d[::19] = ob.NULL_I32
+    ts = (r.integers(8000, 8010, n) * 86400_000_000_000 + r.integers(-1, 2, n) * 3600_000_000_000).astype(np.int64)
+    ts[::23] = ob.NULL_I64
+    assert np.array_equal(oracle.cmp(op, ob.DATE, d, ob.TIMESTAMP, ts), reference.cmp(op, ob.DATE, d, ob.TIMESTAMP, ts))
+    assert np.array_equal(oracle.cmp(op, ob.TIMESTAMP, ts, ob.DATE, d), reference.cmp(op, ob.TIMESTAMP, ts, ob.DATE, d))
+
+
 @pytest.mark.parametrize("xt,yt", [(ob.U8, ob.U8), (ob.B8, ob.B8), (ob.U8, ob.I64), (ob.DATE, ob.I32), (ob.I64, ob.TIMESTAMP)])
 def test_cmp_type_errors(oracle, reference, xt, yt):
     x, y = rng_col(xt, 50, 1, lo=0, hi=9), rng_col(yt, 50, 2, lo=0, hi=9)
