@@ -1,0 +1,120 @@
+/*
+ * rayforce_shim.c — the reference-side binding of rayforce-b200.
+ *
+ * This file is what a RayforceDB maintainer adds to the reference build.  It is compiled against the reference's own
+ * headers and linked with the reference's UNMODIFIED objects using GNU ld's `--wrap`: every reference to one of the
+ * hot-path operators (from the builtin table in core/env.c:119-271, from core/query.c, core/eval.c, ...) is redirected
+ * to `__wrap_<name>` below, which offers the call to the GPU operator layer (include/rfb200_ops.h) and otherwise
+ * continues with `__real_<name>`, the reference's CPU body.
+ *
+ *   gcc -include $REF/core/def.h -I$REF -Iinclude -c integration/rayforce_shim.c
+ *   gcc -o rayforce_dropin $REF_OBJECTS rayforce_shim.o -Lrayforce_b200 -lrfb200_ops -lrfb200 \
+ *       -Wl,--wrap=ray_lt,--wrap=ray_sum,... (the list is WRAPPED_SYMBOLS in oracle/Makefile)
+ *
+ * The GPU layer DECLINES (returns NULL) whatever is outside its path — atoms, lists, tables, parted/MAPCOMMON columns,
+ * symbols/GUIDs, vectors shorter than RFB200_MIN_ROWS — so the reference's behaviour for those is untouched.
+ * Environment: RFB200_DISABLE=1 keeps every call on the CPU bodies; RFB200_MIN_ROWS=n sets the size gate;
+ * RFB200_SHIM_STATS=1 prints per-operator GPU/CPU call counts and the kernel-launch count at exit.
+ */
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "core/rayforce.h"
+#include "core/error.h"
+#include "core/ops.h"
+
+#include "rfb200_ops.h"
+
+/* ---- the host API vtable: the reference's own allocator and error constructors */
+static rfb_obj_p h_vector(int8_t t, int64_t n) { return (rfb_obj_p)vector(t, n); }
+static rfb_obj_p h_atom(int8_t t) { return (rfb_obj_p)atom(t); }
+static rfb_obj_p h_clone(rfb_obj_p o) { return (rfb_obj_p)clone_obj((obj_p)o); }
+static void h_drop(rfb_obj_p o) { drop_obj((obj_p)o); }
+static rfb_obj_p h_err_type(void) { return (rfb_obj_p)err_type(0, 0, 0, 0); }
+static rfb_obj_p h_err_length(void) { return (rfb_obj_p)err_length(0, 0, 0, 0, 0, 0); }
+static rfb_obj_p h_err_limit(void) { return (rfb_obj_p)err_limit(0); }
+static rfb_host_api_t host_api;
+
+static int state = 0; /* 0 = not tried, 1 = GPU layer bound, -1 = unavailable (CPU bodies only) */
+static pthread_t owner;
+static int want_stats = 0;
+
+enum { S_EQ, S_NE, S_LT, S_GT, S_LE, S_GE, S_WHERE, S_COLLECT, S_SUM, S_MIN, S_MAX, S_AVG, S_ADD, S_SUB, S_MUL, S_DIV, S_FDIV,
+       S_MOD, S_ROUND, S_FLOOR, S_CEIL, S_INDEX_GROUP, S_AGGR_SUM, S_AGGR_MIN, S_AGGR_MAX, S_AGGR_COUNT, S_AGGR_AVG, S_SORT_ASC,
+       S_SORT_DESC, S_SELECT, S_N };
+static const char *S_NAME[S_N] = {"ray_eq", "ray_ne", "ray_lt", "ray_gt", "ray_le", "ray_ge", "ray_where", "filter_collect", "ray_sum",
+                                  "ray_min", "ray_max", "ray_avg", "ray_add", "ray_sub", "ray_mul", "ray_div", "ray_fdiv", "ray_mod",
+                                  "ray_round", "ray_floor", "ray_ceil", "index_group", "aggr_sum", "aggr_min", "aggr_max", "aggr_count",
+                                  "aggr_avg", "ray_sort_asc", "ray_sort_desc", "ray_select"};
+static long n_gpu[S_N], n_cpu[S_N];
+
+static void print_stats(void) {
+    long g = 0, c = 0;
+    for (int i = 0; i < S_N; i++) { g += n_gpu[i]; c += n_cpu[i]; }
+    fprintf(stderr, "[rfb200 shim] operator calls handled on the GPU: %ld, on the reference CPU bodies: %ld, kernels launched: %lld\n", g, c,
+            (long long)rfb_ops_launches());
+    for (int i = 0; i < S_N; i++)
+        if (n_gpu[i] || n_cpu[i]) fprintf(stderr, "[rfb200 shim]   %-16s gpu %8ld   cpu %8ld\n", S_NAME[i], n_gpu[i], n_cpu[i]);
+}
+
+static int gpu_ok(void) {
+    if (state == 0) {
+        const char *d = getenv("RFB200_DISABLE");
+        want_stats = getenv("RFB200_SHIM_STATS") != NULL;
+        host_api.vector = h_vector; host_api.atom = h_atom; host_api.clone_obj = h_clone; host_api.drop_obj = h_drop;
+        host_api.err_type = h_err_type; host_api.err_length = h_err_length; host_api.err_limit = h_err_limit;
+        host_api.null_obj = (rfb_obj_p)NULL_OBJ;
+        if (d && d[0] == '1') state = -1;
+        else if (rfb_ops_init(&host_api, 0) == 0) { state = 1; owner = pthread_self(); }
+        else {
+            state = -1;
+            fprintf(stderr, "[rfb200 shim] GPU layer unavailable (%s): using the reference CPU bodies\n", rfb_ops_last_error());
+        }
+        if (want_stats) atexit(print_stats);
+    }
+    /* objects must be allocated on the calling thread's heap and the layer keeps per-query state: one owner thread */
+    return state == 1 && pthread_equal(owner, pthread_self());
+}
+
+#define WRAP1(sym, slot)                                                   \
+    obj_p __real_##sym(obj_p x);                                           \
+    obj_p __wrap_##sym(obj_p x) {                                          \
+        if (gpu_ok()) {                                                    \
+            obj_p r = (obj_p)rfb_##sym((rfb_obj_p)x);                      \
+            if (r) { n_gpu[slot]++; return r; }                            \
+        }                                                                  \
+        n_cpu[slot]++;                                                     \
+        return __real_##sym(x);                                            \
+    }
+#define WRAP2(sym, slot)                                                   \
+    obj_p __real_##sym(obj_p x, obj_p y);                                  \
+    obj_p __wrap_##sym(obj_p x, obj_p y) {                                 \
+        if (gpu_ok()) {                                                    \
+            obj_p r = (obj_p)rfb_##sym((rfb_obj_p)x, (rfb_obj_p)y);        \
+            if (r) { n_gpu[slot]++; return r; }                            \
+        }                                                                  \
+        n_cpu[slot]++;                                                     \
+        return __real_##sym(x, y);                                         \
+    }
+
+WRAP2(ray_eq, S_EQ) WRAP2(ray_ne, S_NE) WRAP2(ray_lt, S_LT) WRAP2(ray_gt, S_GT) WRAP2(ray_le, S_LE) WRAP2(ray_ge, S_GE)
+WRAP1(ray_where, S_WHERE) WRAP2(filter_collect, S_COLLECT)
+WRAP1(ray_sum, S_SUM) WRAP1(ray_min, S_MIN) WRAP1(ray_max, S_MAX) WRAP1(ray_avg, S_AVG)
+WRAP2(ray_add, S_ADD) WRAP2(ray_sub, S_SUB) WRAP2(ray_mul, S_MUL) WRAP2(ray_div, S_DIV) WRAP2(ray_fdiv, S_FDIV) WRAP2(ray_mod, S_MOD)
+WRAP1(ray_round, S_ROUND) WRAP1(ray_floor, S_FLOOR) WRAP1(ray_ceil, S_CEIL)
+WRAP2(index_group, S_INDEX_GROUP)
+WRAP2(aggr_sum, S_AGGR_SUM) WRAP2(aggr_min, S_AGGR_MIN) WRAP2(aggr_max, S_AGGR_MAX) WRAP2(aggr_count, S_AGGR_COUNT) WRAP2(aggr_avg, S_AGGR_AVG)
+WRAP1(ray_sort_asc, S_SORT_ASC) WRAP1(ray_sort_desc, S_SORT_DESC)
+
+/* a query is the residency scope: columns are shipped to HBM once per select (core/query.c:607) */
+obj_p __real_ray_select(obj_p obj);
+obj_p __wrap_ray_select(obj_p obj) {
+    const int on = gpu_ok();
+    if (on) rfb_ops_scope_begin();
+    n_cpu[S_SELECT]++;
+    obj_p r = __real_ray_select(obj);
+    if (on) rfb_ops_scope_end();
+    return r;
+}

@@ -244,9 +244,9 @@ def test_group_sparse_matches_oracle_numbering(ctx, oracle, n, filtered):
     keys = pool[r.integers(0, pool.shape[0], n)]
     filt = np.sort(r.choice(n, max(1, n // 2), replace=False)).astype(np.int64) if filtered else None
     wg, wf, wi = oracle.group_i64(keys, filt)
-    assert wi.dense == 0
     gg, gf, gi = ctx.group_i64(dev(keys), dev(filt) if filtered else None)
-    assert (gi.groups, gi.dense, gi.index_type) == (wi.groups, 0, capi.INDEX_IDS)
+    assert n < 100 or wi.dense == 0           # (a 2-row filter of 4 wide keys can still be "dense": range <= len)
+    assert (gi.groups, gi.dense, gi.index_type) == (wi.groups, wi.dense, wi.index_type)
     assert np.array_equal(host(gf), wf) and np.array_equal(host(gg), wg)
 
 
