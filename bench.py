@@ -185,7 +185,7 @@ def workload_config(args, world):
                         "k = 2^39 (50%% selectivity), %d rows per GPU sharded by row range" % args.rows,
             "rows_per_gpu": args.rows, "global_rows": args.rows * world, "selectivity": 0.5,
             "l2_policy": "inputs (8 GB per GPU) far exceed the 126 MB L2; no flush needed",
-            "merge": "none (1 GPU)" if world == 1 else "one NCCL all-reduce of (rows, nonnull, sum) per step"}
+            "merge": "none (1 GPU)" if world == 1 else "one NCCL all-reduce of (nonnull, sum) per step"}
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -226,7 +226,7 @@ def run_gpu_arm(args):
             if ev_e is not None:
                 ev_e.record(stream)
             r = ctx.fold_result(capi.I64)
-            return r.rows, r.sum
+            return r.nonnull, r.sum
         ctx.set_result_ptr(res)
         if ev_s is not None:
             ev_s.record(stream)
@@ -234,10 +234,10 @@ def run_gpu_arm(args):
         if ev_e is not None:
             ev_e.record(stream)
         with torch.cuda.stream(stream):
-            dist.all_reduce(res[:3])                              # rows, nonnull, sum_i64 (wraps mod 2^64)
-            h = res[:3].cpu()
+            dist.all_reduce(res[1:3])                             # nonnull, sum_i64 (wraps mod 2^64)
+            h = res[1:3].cpu()
         ctx.set_result_ptr(None)
-        return int(h[0]), int(h[2])
+        return int(h[0]), int(h[1])
 
     sampler = ClockSampler(local)
 
@@ -276,7 +276,7 @@ def run_gpu_arm(args):
 
         def step_e2e():
             r, nbytes = ctx.filter_fold_host(capi.LT, capi.I64, hx, K_CONST, capi.F_SUM | capi.F_CNT, capi.I64, hx)
-            rows, s = r.rows, r.sum
+            rows, s = r.nonnull, r.sum
             if world > 1:
                 t = torch.tensor([rows, s], dtype=torch.int64).to(dev)
                 dist.all_reduce(t)
@@ -328,10 +328,10 @@ def run_gpu_arm(args):
                 "steps": K, "warmup": max(W, 3), "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": workload_config(args, world),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": args.ncu_traffic, "kernel": "k_scan_fold<i64,i64,SUM|CNT,pred,same-column>",
+                             "traffic": args.ncu_traffic, "kernel": "k_scan_fold<i64,i64,SUM|CNT,pred,same-column,null-free predicate>",
                              "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": 8 * n, "peak_source": peak_src},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "result": {"rows_selected": int(first[0]), "sum": int(first[1])}}
+                "result": {"rows_selected_nonnull": int(first[0]), "sum": int(first[1])}}
         if world == 1 and not args.no_cpu:
             try:
                 r = cpu_reference_run(steps=3, warmup=1)

@@ -51,7 +51,7 @@ enum { RFB_B8 = 1, RFB_U8 = 2, RFB_I16 = 3, RFB_I32 = 4, RFB_I64 = 5, RFB_SYMBOL
 enum { RFB_EQ = 0, RFB_NE = 1, RFB_LT = 2, RFB_GT = 3, RFB_LE = 4, RFB_GE = 5 };
 
 /* which folds a reduction kernel computes (bit set).  ray_sum/min/max/cnt (core/math.c:1785-2045) */
-enum { RFB_F_SUM = 1, RFB_F_CNT = 2, RFB_F_MIN = 4, RFB_F_MAX = 8, RFB_F_ALL = 15 };
+enum { RFB_F_SUM = 1, RFB_F_CNT = 2, RFB_F_MIN = 4, RFB_F_MAX = 8, RFB_F_ROWS = 16, RFB_F_ALL = 31 };
 
 /* element-wise arithmetic: ray_add/sub/mul/div/fdiv/mod (core/math.c:2436-2441) */
 enum { RFB_ADD = 0, RFB_SUB = 1, RFB_MUL = 2, RFB_DIV = 3, RFB_FDIV = 4, RFB_MOD = 5 };
@@ -85,7 +85,9 @@ typedef struct {
 /* Result of a fold over one column (all requested folds at once).
  * sum: the null-skipping sum in the reference's accumulator type for the column (core/math.c:1850-1871):
  *      U8/I16/I64 -> sum_i64 (wraps mod 2^64); I32/TIME -> sum_i64 holds the value wrapped to 32 bits, sign-extended;
- *      F64 -> sum_f64 (NaN skipped).  rows = elements folded (after the filter); nonnull = non-null among them.
+ *      F64 -> sum_f64 (NaN skipped).  nonnull = non-null elements folded (after the filter) — what ray_cnt / ray_avg use.
+ *      rows = elements selected by the filter, nulls included; exact whenever RFB_F_ROWS is requested (and always
+ *      without a filter); -1 when it was not requested and the kernel took the path that never looks at nulls.
  * min/max: null-skipping; typed null when nothing was folded (MINI64(NULL,y)=y, core/ops.h:185).
  *      integers in min_i64/max_i64 (sign-extended), F64 in min_f64/max_f64. */
 typedef struct {

@@ -17,20 +17,25 @@
 
 namespace {
 
-constexpr int THREADS = 256;
+constexpr int THREADS = 256;       // gather / fma kernels
 constexpr int BLOCKS_PER_SM = 4;
 
-enum { FS_SUMCNT = RFB_F_SUM | RFB_F_CNT, FS_MINMAX = RFB_F_MIN | RFB_F_MAX, FS_ALL = RFB_F_ALL };
+enum { FS_SUMCNT = RFB_F_SUM | RFB_F_CNT, FS_MINMAX = RFB_F_MIN | RFB_F_MAX, FS_ALL = RFB_F_SUM | RFB_F_CNT | RFB_F_MIN | RFB_F_MAX };
 
 struct Partial {
     i64 rows, nonnull;
     u64 sum, mn, mx;  // bit patterns of i64 or f64 depending on the value kind
 };
 
-template <typename V, int FOLDS> struct Acc {
+// Per-thread accumulators.  Row counters are 32-bit (a thread sees far fewer than 2^31 rows; the launcher checks) because
+// the scan kernels are bound by the INT32 pipe, not by HBM, as soon as the per-row instruction count reaches ~12
+// (profiles/r01_bw_probe.txt): every 64-bit add saved is bandwidth gained.
+//   LEAN: the predicate has been adjusted on the host so that it never selects a null of the (same) column, so no null test
+//         is needed and nonnull == selected rows.
+template <typename V, int FOLDS, bool COUNT_ROWS, bool LEAN> struct Acc {
     typedef typename Elem<V>::acc_t A;
     static constexpr bool FLT = (Elem<V>::kind == K_F64);
-    i64 rows, nonnull;
+    u32 rows, nonnull;
     A sum, mn, mx;
     __device__ __forceinline__ static A min_identity() { if constexpr (FLT) return (A)bits_f64(0x7FF0000000000000ULL); else return (A)RFB_INF_I64; }
     __device__ __forceinline__ static A max_identity() { if constexpr (FLT) return (A)bits_f64(0xFFF0000000000000ULL); else return (A)NULL_I64; }
@@ -38,8 +43,8 @@ template <typename V, int FOLDS> struct Acc {
     __device__ __forceinline__ static A widen(V v) { if constexpr (FLT) return (A)widen_f64(v); else return (A)widen_i64(v); }
     // fold one element; `sel` = row passed the predicate.  Nulls are skipped (FOLD_ADD*, MIN*, MAX*, CNT*: core/ops.h)
     __device__ __forceinline__ void take(V v, bool sel) {
-        const bool ok = sel && !Elem<V>::is_null(v);
-        rows += sel;
+        const bool ok = LEAN ? sel : (sel && !Elem<V>::is_null(v));
+        if (COUNT_ROWS) rows += sel;
         nonnull += ok;
         const A w = widen(v);
         if (FOLDS & RFB_F_SUM) {
@@ -62,8 +67,10 @@ struct MaxPlain { template <typename T> __device__ __forceinline__ T operator()(
 
 // CTA-level finish shared by all fold kernels: block tree -> partial -> last CTA folds partials -> host result.
 // vkind: element kind of the value column (decides how sum/min/max are reported, rfb200.h rfb_fold_t).
+// rows_override >= 0: the selected-row count is known to the host (no predicate) ; -1: report the counted rows;
+// -2: rows were not counted (null-excluding fast path) -> reported as -1.
 template <typename A, int FOLDS>
-__device__ __forceinline__ void finish_fold(i64 rows, i64 nonnull, A sum, A mn, A mx, A min_id, A max_id, int vkind,
+__device__ __forceinline__ void finish_fold(i64 rows, i64 nonnull, A sum, A mn, A mx, A min_id, A max_id, int vkind, i64 rows_override,
                                             Partial *partials, u32 *ticket, rfb_fold_t *out) {
     constexpr bool FLT = (sizeof(A) == 8) && (A(0.5) != A(0));  // true for f64, false for i64
     __shared__ u64 red_smem[32];
@@ -106,7 +113,8 @@ __device__ __forceinline__ void finish_fold(i64 rows, i64 nonnull, A sum, A mn, 
     if (FOLDS & RFB_F_MAX) hi = block_reduce<A>(hi, MaxPlain(), max_id, (A *)red_smem);
     if (threadIdx.x == 0) {
         rfb_fold_t res;
-        res.rows = r; res.nonnull = nn;
+        res.rows = rows_override >= 0 ? rows_override : (rows_override == -2 ? -1 : r);
+        res.nonnull = nn;
         res.sum_i64 = 0; res.sum_f64 = 0.0; res.min_i64 = res.max_i64 = 0; res.min_f64 = res.max_f64 = 0.0;
         if (FLT) {
             res.sum_f64 = (f64)s;
@@ -129,68 +137,85 @@ __device__ __forceinline__ void finish_fold(i64 rows, i64 nonnull, A sum, A mn, 
 
 // ------------------------------------------------------------------ scan + fold over one or two columns
 
-template <typename P, typename V, int FOLDS, bool HAS_PRED, bool SAME>
-__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+// Launch shape per fold set.  sum/count kernels are the bandwidth-critical ones: 512 threads x 4 CTAs = all 2048 thread
+// slots of the SM (<= 32 registers), 4 x 16 B in flight per thread (128 KB per SM); the min/max and all-folds kernels
+// carry more live state and keep 256 threads x 4 CTAs x 8 loads.
+#ifndef SC_THREADS   // overridable for tuning sweeps (tools/sweep_scan_cfg.sh)
+#define SC_THREADS 512
+#define SC_BPS 4
+#define SC_LOADS 4
+#endif
+template <int FOLDS> struct ScanCfg {
+    static constexpr int THREADS = (FOLDS == FS_SUMCNT) ? SC_THREADS : 256;
+    static constexpr int BPS = (FOLDS == FS_SUMCNT) ? SC_BPS : 4;
+    static constexpr int LOADS = (FOLDS == FS_SUMCNT) ? SC_LOADS : 8;   // 16-byte loads in flight per thread
+};
+
+// integer predicate test with the bias folded into the constant: (x ^ S) - lo == x - (lo ^ S)  (mod 2^64)
+template <typename P> __device__ __forceinline__ bool pred_sel(P x, const PredRange &pr) {
+    if constexpr (Elem<P>::kind == K_F64) return pred_test(key_of_f64(x), pr);
+    else return (((u64)widen_i64(x) - pr.lo_int) <= pr.span) != (bool)pr.negate;
+}
+
+template <typename P, typename V, int FOLDS, bool HAS_PRED, bool SAME, bool LEAN>
+__global__ void __launch_bounds__(ScanCfg<FOLDS>::THREADS, ScanCfg<FOLDS>::BPS)
 k_scan_fold(const P *__restrict__ pred, PredRange pr, const V *__restrict__ val, i64 n, i64 chunks, int vkind,
             Partial *partials, u32 *ticket, rfb_fold_t *out) {
+    constexpr int THREADS_ = ScanCfg<FOLDS>::THREADS;
     constexpr bool TWO = HAS_PRED && !SAME;
     constexpr int SZ_MIN = TWO ? (sizeof(P) < sizeof(V) ? sizeof(P) : sizeof(V)) : sizeof(V);
     constexpr int RPT = 16 / SZ_MIN;                       // rows per thread-chunk
     constexpr int NV_V = RPT * (int)sizeof(V) / 16;         // 16-byte loads per chunk, value column
     constexpr int NV_P = TWO ? RPT * (int)sizeof(P) / 16 : 0;
-    constexpr int UNROLL = (8 / (NV_V + NV_P)) > 0 ? 8 / (NV_V + NV_P) : 1;
-    constexpr int TILE = THREADS * UNROLL;                  // chunks per tile
+    constexpr int UNROLL = (ScanCfg<FOLDS>::LOADS / (NV_V + NV_P)) > 0 ? ScanCfg<FOLDS>::LOADS / (NV_V + NV_P) : 1;
+    constexpr int TILE = THREADS_ * UNROLL;                 // chunks per tile
+    constexpr bool COUNT_ROWS = HAS_PRED && !LEAN;
 
-    Acc<V, FOLDS> acc;
+    Acc<V, FOLDS, COUNT_ROWS, LEAN> acc;
     acc.init();
 
-    const i64 tiles = (chunks + TILE - 1) / TILE;
+    // full tiles only: no bounds checks, no predicated loads in the hot loop
+    const i64 tiles = chunks / TILE;
     for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const i64 c0 = tile * TILE + threadIdx.x;
         Vec16<V> vv[UNROLL][NV_V];
         Vec16<P> pv[UNROLL][TWO ? NV_P : 1];
-        const bool full = (tile + 1) * (i64)TILE <= chunks;
 #pragma unroll
         for (int j = 0; j < UNROLL; j++) {
-            const i64 c = c0 + (i64)j * THREADS;
-            if (full || c < chunks) {
-                const char *vb = (const char *)val + c * (RPT * sizeof(V));
+            const i64 c = c0 + (i64)j * THREADS_;
+            const char *vb = (const char *)val + c * (RPT * sizeof(V));
 #pragma unroll
-                for (int q = 0; q < NV_V; q++) vv[j][q].raw = ld_stream16(vb + 16 * q);
-                if (TWO) {
-                    const char *pb = (const char *)pred + c * (RPT * sizeof(P));
+            for (int q = 0; q < NV_V; q++) vv[j][q].raw = ld_stream16(vb + 16 * q);
+            if (TWO) {
+                const char *pb = (const char *)pred + c * (RPT * sizeof(P));
 #pragma unroll
-                    for (int q = 0; q < NV_P; q++) pv[j][q].raw = ld_stream16(pb + 16 * q);
-                }
+                for (int q = 0; q < NV_P; q++) pv[j][q].raw = ld_stream16(pb + 16 * q);
             }
         }
 #pragma unroll
         for (int j = 0; j < UNROLL; j++) {
-            const i64 c = c0 + (i64)j * THREADS;
-            if (full || c < chunks) {
 #pragma unroll
-                for (int r = 0; r < RPT; r++) {
-                    const V v = vv[j][r / Vec16<V>::N].e[r % Vec16<V>::N];
-                    bool sel = true;
-                    if (HAS_PRED) {
-                        if (SAME) sel = pred_test(pred_key<P>(*reinterpret_cast<const P *>(&v)), pr);
-                        else sel = pred_test(pred_key<P>(pv[j][r / Vec16<P>::N].e[r % Vec16<P>::N]), pr);
-                    }
-                    acc.take(v, sel);
+            for (int r = 0; r < RPT; r++) {
+                const V v = vv[j][r / Vec16<V>::N].e[r % Vec16<V>::N];
+                bool sel = true;
+                if (HAS_PRED) {
+                    if (SAME) sel = pred_sel<P>(*reinterpret_cast<const P *>(&v), pr);
+                    else sel = pred_sel<P>(pv[j][r / Vec16<P>::N].e[r % Vec16<P>::N], pr);
                 }
+                acc.take(v, sel);
             }
         }
     }
-    // rows not covered by whole chunks (and everything, when a pointer is not 16-byte aligned: chunks == 0)
-    for (i64 r = chunks * RPT + (i64)blockIdx.x * THREADS + threadIdx.x; r < n; r += (i64)gridDim.x * THREADS) {
+    // the remaining rows: less than one tile (and everything, when a pointer is not 16-byte aligned: chunks == 0)
+    for (i64 r = tiles * TILE * RPT + (i64)blockIdx.x * THREADS_ + threadIdx.x; r < n; r += (i64)gridDim.x * THREADS_) {
         const V v = ld_stream(val + r);
         bool sel = true;
-        if (HAS_PRED) sel = pred_test(pred_key<P>(SAME ? *reinterpret_cast<const P *>(&v) : ld_stream(pred + r)), pr);
+        if (HAS_PRED) sel = pred_sel<P>(SAME ? *reinterpret_cast<const P *>(&v) : ld_stream(pred + r), pr);
         acc.take(v, sel);
     }
-    typedef typename Acc<V, FOLDS>::A A;
-    finish_fold<A, FOLDS>(acc.rows, acc.nonnull, acc.sum, acc.mn, acc.mx, Acc<V, FOLDS>::min_identity(),
-                          Acc<V, FOLDS>::max_identity(), vkind, partials, ticket, out);
+    typedef typename Acc<V, FOLDS, COUNT_ROWS, LEAN>::A A;
+    finish_fold<A, FOLDS>((i64)acc.rows, (i64)acc.nonnull, acc.sum, acc.mn, acc.mx, Acc<V, FOLDS, COUNT_ROWS, LEAN>::min_identity(),
+                          Acc<V, FOLDS, COUNT_ROWS, LEAN>::max_identity(), vkind, HAS_PRED ? (LEAN ? -2 : -1) : n, partials, ticket, out);
 }
 
 // ------------------------------------------------------------------ (fold (+ (* a b) c)) over three F64 columns
@@ -201,7 +226,7 @@ k_fma_fold(const f64 *__restrict__ a, const f64 *__restrict__ b, const f64 *__re
            Partial *partials, u32 *ticket, rfb_fold_t *out) {
     constexpr int UNROLL = 2;  // 3 columns x 2 loads = 6 x 16 B in flight per thread
     constexpr int TILE = THREADS * UNROLL;
-    Acc<f64, FOLDS> acc;
+    Acc<f64, FOLDS, false, false> acc;
     acc.init();
     // MULF64 then ADDF64 (core/ops.h:155,164): NaN in -> NaN out; the products/sums of non-NaN values are plain IEEE
     // ops (no fused multiply-add: the reference materialises a*b, rounding it, before adding c).
@@ -233,8 +258,8 @@ k_fma_fold(const f64 *__restrict__ a, const f64 *__restrict__ b, const f64 *__re
     }
     for (i64 r = chunks * 2 + (i64)blockIdx.x * THREADS + threadIdx.x; r < n; r += (i64)gridDim.x * THREADS)
         acc.take(eval(ld_stream(a + r), ld_stream(b + r), ld_stream(c + r)), true);
-    finish_fold<f64, FOLDS>(acc.rows, acc.nonnull, acc.sum, acc.mn, acc.mx, Acc<f64, FOLDS>::min_identity(),
-                            Acc<f64, FOLDS>::max_identity(), K_F64, partials, ticket, out);
+    finish_fold<f64, FOLDS>(0, (i64)acc.nonnull, acc.sum, acc.mn, acc.mx, Acc<f64, FOLDS, false, false>::min_identity(),
+                            Acc<f64, FOLDS, false, false>::max_identity(), K_F64, n, partials, ticket, out);
 }
 
 // ------------------------------------------------------------------ fold through a selection vector (MAPFILTER)
@@ -243,7 +268,7 @@ template <typename V, int FOLDS>
 __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
 k_gather_fold(const V *__restrict__ col, const i64 *__restrict__ ids, i64 m, int vkind, Partial *partials, u32 *ticket,
               rfb_fold_t *out) {
-    Acc<V, FOLDS> acc;
+    Acc<V, FOLDS, false, false> acc;
     acc.init();
     constexpr int UNROLL = 4;
     const i64 stride = (i64)gridDim.x * THREADS;
@@ -259,14 +284,15 @@ k_gather_fold(const V *__restrict__ col, const i64 *__restrict__ ids, i64 m, int
         for (int j = 0; j < UNROLL; j++) acc.take(v[j], true);
     }
     for (; i < m; i += stride) acc.take(__ldg(col + ld_stream(ids + i)), true);
-    typedef typename Acc<V, FOLDS>::A A;
-    finish_fold<A, FOLDS>(acc.rows, acc.nonnull, acc.sum, acc.mn, acc.mx, Acc<V, FOLDS>::min_identity(),
-                          Acc<V, FOLDS>::max_identity(), vkind, partials, ticket, out);
+    typedef typename Acc<V, FOLDS, false, false>::A A;
+    finish_fold<A, FOLDS>(0, (i64)acc.nonnull, acc.sum, acc.mn, acc.mx, Acc<V, FOLDS, false, false>::min_identity(),
+                          Acc<V, FOLDS, false, false>::max_identity(), vkind, m, partials, ticket, out);
 }
 
 // ------------------------------------------------------------------ host-side dispatch
 
 inline int foldset_of(int folds) {
+    folds &= ~RFB_F_ROWS;
     if (!(folds & ~FS_SUMCNT)) return FS_SUMCNT;
     if (!(folds & ~FS_MINMAX)) return FS_MINMAX;
     return FS_ALL;
@@ -286,47 +312,72 @@ inline Scratch scratch_of(rfb_ctx_t *ctx) {
 }
 
 
-template <typename P, typename V, int FOLDS, bool HAS_PRED, bool SAME>
+template <typename P, typename V, int FOLDS, bool HAS_PRED, bool SAME, bool LEAN>
 int launch_scan_fold(rfb_ctx_t *ctx, const void *pred, PredRange pr, const void *val, i64 n, int vkind) {
     constexpr bool TWO = HAS_PRED && !SAME;
     constexpr int SZ_MIN = TWO ? (sizeof(P) < sizeof(V) ? sizeof(P) : sizeof(V)) : sizeof(V);
     constexpr int RPT = 16 / SZ_MIN;
+    constexpr int THREADS_ = ScanCfg<FOLDS>::THREADS;
     const bool vec_ok = aligned16(val) && (!TWO || aligned16(pred));
     const i64 chunks = vec_ok ? n / RPT : 0;
-    const i64 work = vec_ok ? (chunks + 7) / 8 + 1 : n;  // rough thread-work estimate for sizing small grids
-    const int grid = rfb_grid_for(ctx, work, THREADS, BLOCKS_PER_SM);
+    const i64 work = vec_ok ? (chunks + ScanCfg<FOLDS>::LOADS - 1) / ScanCfg<FOLDS>::LOADS + 1 : n;  // thread-work estimate for small grids
+    const int grid = rfb_grid_for(ctx, work, THREADS_, ScanCfg<FOLDS>::BPS);
+    if (n / ((i64)grid * THREADS_) >= (1ll << 30)) {   // per-thread row counters are 32-bit
+        rfb_set_error("fold: column of %lld rows is beyond the per-launch limit", (long long)n);
+        return RFB_ERR_ARG;
+    }
     Scratch s = scratch_of(ctx);
-    k_scan_fold<P, V, FOLDS, HAS_PRED, SAME><<<grid, THREADS, 0, ctx->stream>>>(
+    k_scan_fold<P, V, FOLDS, HAS_PRED, SAME, LEAN><<<grid, THREADS_, 0, ctx->stream>>>(
         (const P *)pred, pr, (const V *)val, n, chunks, vkind, s.partials, s.ticket, s.result);
     RFB_CHECK_LAUNCH(ctx);
     return RFB_OK;
 }
 
 template <typename P, typename V, bool HAS_PRED, bool SAME>
-int dispatch_foldset(rfb_ctx_t *ctx, int fs, const void *pred, PredRange pr, const void *val, i64 n, int vkind) {
+int dispatch_foldset(rfb_ctx_t *ctx, int fs, bool lean, const void *pred, PredRange pr, const void *val, i64 n, int vkind) {
     switch (fs) {
-        case FS_SUMCNT: return launch_scan_fold<P, V, FS_SUMCNT, HAS_PRED, SAME>(ctx, pred, pr, val, n, vkind);
-        case FS_MINMAX: return launch_scan_fold<P, V, FS_MINMAX, HAS_PRED, SAME>(ctx, pred, pr, val, n, vkind);
-        default: return launch_scan_fold<P, V, FS_ALL, HAS_PRED, SAME>(ctx, pred, pr, val, n, vkind);
+        case FS_SUMCNT:
+            if constexpr (HAS_PRED && SAME && Elem<V>::kind != K_F64) {
+                if (lean) return launch_scan_fold<P, V, FS_SUMCNT, HAS_PRED, SAME, true>(ctx, pred, pr, val, n, vkind);
+            }
+            return launch_scan_fold<P, V, FS_SUMCNT, HAS_PRED, SAME, false>(ctx, pred, pr, val, n, vkind);
+        case FS_MINMAX: return launch_scan_fold<P, V, FS_MINMAX, HAS_PRED, SAME, false>(ctx, pred, pr, val, n, vkind);
+        default: return launch_scan_fold<P, V, FS_ALL, HAS_PRED, SAME, false>(ctx, pred, pr, val, n, vkind);
     }
 }
 
 template <typename P>
-int dispatch_val(rfb_ctx_t *ctx, int fs, const void *pred, PredRange pr, int vkind, const void *val, i64 n, bool same) {
+int dispatch_val(rfb_ctx_t *ctx, int fs, bool lean, const void *pred, PredRange pr, int vkind, const void *val, i64 n, bool same) {
     switch (vkind) {
         case K_I32:
-            if (same && Elem<P>::kind == K_I32) return dispatch_foldset<i32, i32, true, true>(ctx, fs, pred, pr, val, n, vkind);
-            return dispatch_foldset<P, i32, true, false>(ctx, fs, pred, pr, val, n, vkind);
+            if (same && Elem<P>::kind == K_I32) return dispatch_foldset<i32, i32, true, true>(ctx, fs, lean, pred, pr, val, n, vkind);
+            return dispatch_foldset<P, i32, true, false>(ctx, fs, false, pred, pr, val, n, vkind);
         case K_I64:
-            if (same && Elem<P>::kind == K_I64) return dispatch_foldset<i64, i64, true, true>(ctx, fs, pred, pr, val, n, vkind);
-            return dispatch_foldset<P, i64, true, false>(ctx, fs, pred, pr, val, n, vkind);
+            if (same && Elem<P>::kind == K_I64) return dispatch_foldset<i64, i64, true, true>(ctx, fs, lean, pred, pr, val, n, vkind);
+            return dispatch_foldset<P, i64, true, false>(ctx, fs, false, pred, pr, val, n, vkind);
         case K_F64:
-            if (same && Elem<P>::kind == K_F64) return dispatch_foldset<f64, f64, true, true>(ctx, fs, pred, pr, val, n, vkind);
-            return dispatch_foldset<P, f64, true, false>(ctx, fs, pred, pr, val, n, vkind);
+            if (same && Elem<P>::kind == K_F64) return dispatch_foldset<f64, f64, true, true>(ctx, fs, false, pred, pr, val, n, vkind);
+            return dispatch_foldset<P, f64, true, false>(ctx, fs, false, pred, pr, val, n, vkind);
         default:
             rfb_set_error("filter+fold: unsupported value type");
             return RFB_ERR_TYPE;
     }
+}
+
+// Make the predicate reject the column's own null (biased key 0) so the kernel can drop the per-row null test:
+// sum/nonnull are unchanged, only the count of selected NULL rows is lost (hence not done when RFB_F_ROWS is requested).
+bool exclude_null_key(PredRange *pr) {
+    if (!pr->negate) {
+        if (pr->lo != 0) return true;               // the null key is outside the selected range already
+        if (pr->span == 0) return false;            // selects exactly the nulls
+        pr->lo = 1; pr->span -= 1;
+    } else {
+        if (pr->lo == 0) return true;               // the null key is inside the rejected range already
+        if (pr->lo != 1) return false;
+        pr->lo = 0; pr->span += 1;                  // grow the rejected range over key 0
+    }
+    pr->lo_int = pr->lo ^ 0x8000000000000000ULL;
+    return true;
 }
 
 int wait_result(rfb_ctx_t *ctx, rfb_fold_t *out) {
@@ -342,14 +393,14 @@ int wait_result(rfb_ctx_t *ctx, rfb_fold_t *out) {
 // launch only (result lands in ctx->h_result after the stream drains); used by the host-layer pipeline too
 int rfb_fold_launch(rfb_ctx_t *ctx, int folds, int type, const void *x, i64 n) {
     const int fs = foldset_of(folds), vk = rfb_kind_of(type);
-    PredRange pr = {0, 0, 0};
+    PredRange pr = {0, 0, 0, 0};
     if (type == RFB_B8 || type == RFB_SYMBOL) { rfb_set_error("fold: unsupported type %d", type); return RFB_ERR_TYPE; }
     switch (vk) {
-        case K_U8: return dispatch_foldset<u8, u8, false, false>(ctx, fs, nullptr, pr, x, n, vk);
-        case K_I16: return dispatch_foldset<i16, i16, false, false>(ctx, fs, nullptr, pr, x, n, vk);
-        case K_I32: return dispatch_foldset<i32, i32, false, false>(ctx, fs, nullptr, pr, x, n, vk);
-        case K_I64: return dispatch_foldset<i64, i64, false, false>(ctx, fs, nullptr, pr, x, n, vk);
-        case K_F64: return dispatch_foldset<f64, f64, false, false>(ctx, fs, nullptr, pr, x, n, vk);
+        case K_U8: return dispatch_foldset<u8, u8, false, false>(ctx, fs, false, nullptr, pr, x, n, vk);
+        case K_I16: return dispatch_foldset<i16, i16, false, false>(ctx, fs, false, nullptr, pr, x, n, vk);
+        case K_I32: return dispatch_foldset<i32, i32, false, false>(ctx, fs, false, nullptr, pr, x, n, vk);
+        case K_I64: return dispatch_foldset<i64, i64, false, false>(ctx, fs, false, nullptr, pr, x, n, vk);
+        case K_F64: return dispatch_foldset<f64, f64, false, false>(ctx, fs, false, nullptr, pr, x, n, vk);
         default: rfb_set_error("fold: unsupported type %d", type); return RFB_ERR_TYPE;
     }
 }
@@ -364,14 +415,15 @@ int rfb_filter_fold_launch(rfb_ctx_t *ctx, int cmp_op, int pred_type, const void
         i64 kv;
         if (!scalar_as_i64(k, &kv)) { rfb_set_error("filter+fold: integer column vs non-integer constant"); return RFB_ERR_TYPE; }
         PredRange pr = make_pred_range(cmp_op, key_of_i64(kv));
-        return pk == K_I32 ? dispatch_val<i32>(ctx, fs, pred, pr, vk, val, n, same)
-                           : dispatch_val<i64>(ctx, fs, pred, pr, vk, val, n, same);
+        const bool lean = same && fs == FS_SUMCNT && !(folds & RFB_F_ROWS) && exclude_null_key(&pr);
+        return pk == K_I32 ? dispatch_val<i32>(ctx, fs, lean, pred, pr, vk, val, n, same)
+                           : dispatch_val<i64>(ctx, fs, lean, pred, pr, vk, val, n, same);
     }
     if (pk == K_F64) {
         f64 kv;
         if (!scalar_as_f64(k, &kv)) { rfb_set_error("filter+fold: bad constant type"); return RFB_ERR_TYPE; }
         PredRange pr = make_pred_range(cmp_op, key_of_f64(kv));
-        return dispatch_val<f64>(ctx, fs, pred, pr, vk, val, n, same);
+        return dispatch_val<f64>(ctx, fs, false, pred, pr, vk, val, n, same);
     }
     rfb_set_error("filter+fold: unsupported predicate column type %d", pred_type);
     return RFB_ERR_TYPE;

@@ -252,6 +252,7 @@ static inline i64 rfb_cmp_scale(int t, int other) { return (t == RFB_DATE && oth
 struct PredRange {
     u64 lo, span;
     u32 negate;
+    u64 lo_int;  // lo ^ 2^63: integer columns test (x - lo_int) <= span directly, (x ^ S) - lo == x - (lo ^ S) mod 2^64
 };
 
 __host__ __device__ __forceinline__ u64 key_of_i64(i64 x) { return (u64)x ^ 0x8000000000000000ULL; }
@@ -296,6 +297,7 @@ static inline PredRange make_pred_range(int op, u64 kk) {
         case RFB_LT: if (kk == 0) { pr.lo = 0; pr.span = MAXK; pr.negate = 1; } else { pr.lo = 0; pr.span = kk - 1; } break;
         default /*GT*/: if (kk == MAXK) { pr.lo = 0; pr.span = MAXK; pr.negate = 1; } else { pr.lo = kk + 1; pr.span = MAXK - kk - 1; } break;
     }
+    pr.lo_int = pr.lo ^ 0x8000000000000000ULL;
     return pr;
 }
 

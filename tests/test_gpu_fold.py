@@ -133,6 +133,28 @@ def test_filter_fold_extreme_constants(ctx, oracle, op, k):
     check_fold(got, oracle_folds(oracle, ob.I64, sel), ob.I64, ids.shape[0])
 
 
+@pytest.mark.parametrize("t", [ob.I64, ob.I32])
+@pytest.mark.parametrize("k", ["null", "null+1", -3, 0, 7, "max"])
+@pytest.mark.parametrize("op", CMPS)
+def test_filter_fold_sum_count_fast_path_never_sees_nulls(ctx, oracle, op, k, t):
+    """sum/count on the predicate's own column takes the kernel whose predicate was adjusted on the host to reject the
+    column's null sentinel (no per-row null test): sum and non-null count must still be the reference's, for every
+    operator and for constants at the edges of the domain; `rows` is exact again as soon as RFB_F_ROWS is asked for"""
+    info = np.iinfo(ob.NP_OF[t])
+    kk = {"null": info.min, "null+1": info.min + 1, "max": info.max}.get(k, k)
+    n = 150_001
+    col = rng_col(t, n, seed=17, null_frac=0.05, lo=-10, hi=10)
+    col[::97] = info.min + 1
+    col[1::97] = info.max
+    ids, sel = unfused(oracle, op, t, col, kk, t, col)
+    d = dev(col)
+    got = ctx.filter_fold(op, t, d, kk, capi.F_SUM | capi.F_CNT, t, d, n)
+    assert got.sum == int(oracle.fold(ob.SUM, t, sel)[0]) and got.nonnull == int(oracle.fold(ob.CNT, t, sel)[0])
+    assert got.rows in (-1, ids.shape[0])
+    got = ctx.filter_fold(op, t, d, kk, capi.F_SUM | capi.F_CNT | capi.F_ROWS, t, d, n)
+    assert (got.rows, got.sum, got.nonnull) == (ids.shape[0], int(oracle.fold(ob.SUM, t, sel)[0]), int(oracle.fold(ob.CNT, t, sel)[0]))
+
+
 @pytest.mark.parametrize("pt,vt", [(ob.I64, ob.I64), (ob.I32, ob.I64), (ob.I64, ob.I32), (ob.I32, ob.I32),
                                    (ob.F64, ob.I64), (ob.I64, ob.F64), (ob.F64, ob.F64), (ob.I32, ob.F64)])
 @pytest.mark.parametrize("op", [ob.LT, ob.GE, ob.EQ])
@@ -171,7 +193,9 @@ def test_filter_fold_reference_golden_25001_rows(ctx):
     col = np.arange(n, dtype=np.int64)
     d = dev(col)
     got = ctx.filter_fold(ob.LT, ob.I64, d, 500, capi.F_SUM | capi.F_CNT, ob.I64, d, n)
-    assert (got.rows, got.sum) == (500, 124750)
+    assert (got.nonnull, got.sum) == (500, 124750)
+    got = ctx.filter_fold(ob.LT, ob.I64, d, 500, capi.F_SUM | capi.F_CNT | capi.F_ROWS, ob.I64, d, n)
+    assert (got.rows, got.nonnull, got.sum) == (500, 500, 124750)
 
 
 # ---------------------------------------------------------------- fused (fold (+ (* a b) c))
