@@ -180,6 +180,23 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic_bytes(rows):
+    """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/*scan_fold*_full.txt, taken at 1e9 rows); None when no capture matches this row count"""
+    import glob
+    import re
+    if rows != 1_000_000_000:
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*scan_fold*_full.txt")), reverse=True):
+        txt = open(path).read()
+        rd = re.search(r"dram__bytes_read\.sum\s+([0-9.]+)\s+(\w+)", txt)
+        wr = re.search(r"dram__bytes_write\.sum\s+([0-9.]+)\s+(\w+)", txt)
+        if rd and wr:
+            return float(rd.group(1)) * unit[rd.group(2)] + float(wr.group(1)) * unit[wr.group(2)], os.path.relpath(path, ROOT)
+    return None, None
+
+
 def workload_config(args, world):
     return {"workload": "select {s: (sum x) from: t where: (< x k)}: int64 column, x = splitmix64(42, row) mod 2^40, "
                         "k = 2^39 (50%% selectivity), %d rows per GPU sharded by row range" % args.rows,
@@ -324,11 +341,12 @@ def run_gpu_arm(args):
         except Exception:
             peak = 6650.0
         achieved = 8.0 * n / (kernel_ms * 1e-3) / 1e9
+        traffic, traffic_src = (args.ncu_traffic, "--ncu-traffic") if args.ncu_traffic else ncu_traffic_bytes(n)
         line = {"metric": METRIC, "value": n * world * K / (total_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
                 "steps": K, "warmup": max(W, 3), "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": workload_config(args, world),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": args.ncu_traffic, "kernel": "k_scan_fold<i64,i64,SUM|CNT,pred,same-column,null-free predicate>",
+                             "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_scan_fold<i64,i64,SUM|CNT,pred,same-column,null-free predicate>",
                              "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": 8 * n, "peak_source": peak_src},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "result": {"rows_selected_nonnull": int(first[0]), "sum": int(first[1])}}
