@@ -141,8 +141,8 @@ __device__ __forceinline__ void finish_fold(i64 rows, i64 nonnull, A sum, A mn, 
 // slots of the SM (<= 32 registers), 4 x 16 B in flight per thread (128 KB per SM); the min/max and all-folds kernels
 // carry more live state and keep 256 threads x 4 CTAs x 8 loads.
 #ifndef SC_THREADS   // overridable for tuning sweeps (tools/sweep_scan_cfg.sh)
-#define SC_THREADS 512
-#define SC_BPS 4
+#define SC_THREADS 1024
+#define SC_BPS 2
 #define SC_LOADS 4
 #endif
 template <int FOLDS> struct ScanCfg {

@@ -699,7 +699,7 @@ template <typename K>
 int fused_key(rfb_ctx_t *ctx, const void *keys, int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k, const i64 *val,
               i64 n, i64 max_groups, i64 *ok, i64 *os, i64 *oc, i64 *groups) {
     if (!pred) {
-        FusedSrc<K, i64, false> fs{(const K *)keys, nullptr, PredRange{0, 0, 0}};
+        FusedSrc<K, i64, false> fs{(const K *)keys, nullptr, PredRange{0, 0, 0, 0}};
         return fused_run(ctx, fs, val, n, max_groups, ok, os, oc, groups);
     }
     PredRange pr;

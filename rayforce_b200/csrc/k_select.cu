@@ -22,27 +22,36 @@ using scan::TileSmem;
 constexpr int BLOCKS_PER_SM = 4;
 
 // ---- byte mask -> ids.  Lane owns 16 consecutive mask bytes per step (one 128-bit load), J steps per tile.
+// The ids of one warp-step (<= 512) are staged in shared memory in output order and written out by the whole warp as
+// contiguous 256-byte stores: writing them straight from the lanes touches 32 different sectors per instruction (each lane
+// owns a ~64-byte run), which quadrupled the L2 write transactions.
 constexpr int MASK_J = 4;
 constexpr int MASK_TILE = THREADS * 16 * MASK_J;  // 16384 rows per tile
 
 __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
 k_where_mask(const u8 *__restrict__ mask, i64 n, i64 *__restrict__ ids, TileCtl ctl) {
     __shared__ TileSmem sm;
+    __shared__ i64 stage[WARPS][512];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u32 tile = scan::take_tile(ctl, sm);
+    const u32 tile = blockIdx.x;
     const i64 wbase = (i64)tile * MASK_TILE + (i64)warp * (32 * 16 * MASK_J);
     u32 bits[MASK_J];    // this lane's 16 flags per step
-    u32 excl[MASK_J];    // selected rows of this warp before this lane's first row in step j
+    u32 excl[MASK_J];    // selected rows of this warp-step before this lane's first row
+    u32 tot[MASK_J];     // selected rows of this warp-step
     u32 warp_total = 0;
+    Vec16<u8> v[MASK_J];
+    const bool full = wbase + 32 * 16 * MASK_J <= n;
+    if (full) {
+#pragma unroll
+        for (int j = 0; j < MASK_J; j++) v[j].raw = ld_stream16(mask + wbase + ((i64)j * 32 + lane) * 16);
+    }
 #pragma unroll
     for (int j = 0; j < MASK_J; j++) {
         const i64 r0 = wbase + ((i64)j * 32 + lane) * 16;
         u32 b = 0;
-        if (r0 + 16 <= n) {
-            Vec16<u8> v;
-            v.raw = ld_stream16(mask + r0);
+        if (full) {
 #pragma unroll
-            for (int e = 0; e < 16; e++) b |= (v.e[e] != 0 ? 1u : 0u) << e;
+            for (int e = 0; e < 16; e++) b |= (v[j].e[e] != 0 ? 1u : 0u) << e;
         } else {
             for (int e = 0; e < 16; e++)
                 if (r0 + e < n && mask[r0 + e] != 0) b |= 1u << e;
@@ -54,38 +63,45 @@ k_where_mask(const u8 *__restrict__ mask, i64 n, i64 *__restrict__ ids, TileCtl 
             const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += o;
         }
-        excl[j] = warp_total + incl - c;
-        warp_total += __shfl_sync(0xffffffffu, incl, 31);
+        excl[j] = incl - c;
+        tot[j] = __shfl_sync(0xffffffffu, incl, 31);
+        warp_total += tot[j];
     }
-    const u64 obase = scan::tile_offsets(ctl, tile, warp_total, sm);
+    u64 obase = scan::tile_offsets<WARPS>(ctl, tile, warp_total, sm);
 #pragma unroll
     for (int j = 0; j < MASK_J; j++) {
         const i64 r0 = wbase + ((i64)j * 32 + lane) * 16;
-        i64 *o = ids + obase + excl[j];
+        i64 *st = &stage[warp][excl[j]];
         u32 b = bits[j];
         while (b) {
             const int e = __ffs(b) - 1;
             b &= b - 1;
-            *o++ = r0 + e;
+            *st++ = r0 + e;
         }
+        __syncwarp();
+        for (u32 q = lane; q < tot[j]; q += 32) ids[obase + q] = stage[warp][q];
+        __syncwarp();
+        obase += tot[j];
     }
 }
 
 // ---- predicate on a typed column -> ids.  Lane owns R = 16/sizeof(P) consecutive rows per step.
+constexpr int CMP_THREADS = 512;
+constexpr int CMP_WARPS = CMP_THREADS / 32;
 template <typename P> struct CmpTile {
     static constexpr int R = 16 / (int)sizeof(P);
     static constexpr int J = 8;
     static constexpr int WROWS = 32 * R * J;
-    static constexpr int TILE = WARPS * WROWS;
+    static constexpr int TILE = CMP_WARPS * WROWS;
 };
 
 template <typename P>
-__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+__global__ void __launch_bounds__(CMP_THREADS, 2)
 k_where_cmp(const P *__restrict__ x, PredRange pr, i64 n, bool vec_ok, i64 *__restrict__ ids, TileCtl ctl) {
     constexpr int R = CmpTile<P>::R, J = CmpTile<P>::J;
-    __shared__ TileSmem sm;
+    __shared__ scan::TileSmemT<CMP_WARPS> sm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u32 tile = scan::take_tile(ctl, sm);
+    const u32 tile = blockIdx.x;
     const i64 wbase = (i64)tile * CmpTile<P>::TILE + (i64)warp * CmpTile<P>::WROWS;
     Vec16<P> v[J];
     const bool full = vec_ok && wbase + CmpTile<P>::WROWS <= n;
@@ -123,7 +139,7 @@ k_where_cmp(const P *__restrict__ x, PredRange pr, i64 n, bool vec_ok, i64 *__re
         excl[j] = warp_total + before;
         warp_total += tot;
     }
-    const u64 obase = scan::tile_offsets(ctl, tile, warp_total, sm);
+    const u64 obase = scan::tile_offsets<CMP_WARPS>(ctl, tile, warp_total, sm);
 #pragma unroll
     for (int j = 0; j < J; j++) {
         const i64 r0 = wbase + ((i64)j * 32 + lane) * R;
@@ -153,7 +169,7 @@ int where_cmp_t(rfb_ctx_t *ctx, const void *x, PredRange pr, i64 n, i64 *ids) {
     TileCtl ctl;
     int rc = prepare_tiles(ctx, tiles, &ctl);
     if (rc) return rc;
-    k_where_cmp<P><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>((const P *)x, pr, n, aligned16(x), ids, ctl);
+    k_where_cmp<P><<<(unsigned)tiles, CMP_THREADS, 0, ctx->stream>>>((const P *)x, pr, n, aligned16(x), ids, ctl);
     RFB_CHECK_LAUNCH(ctx);
     return RFB_OK;
 }
@@ -204,7 +220,7 @@ extern "C" int rfb_where_dev(rfb_ctx_t *ctx, const uint8_t *mask, int64_t n, int
         const i64 tiles = (n + CmpTile<u8>::TILE - 1) / CmpTile<u8>::TILE;
         int rc = prepare_tiles(ctx, tiles, &ctl);
         if (rc) return rc;
-        k_where_cmp<u8><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(mask, pr, n, false, ids, ctl);
+        k_where_cmp<u8><<<(unsigned)tiles, CMP_THREADS, 0, ctx->stream>>>(mask, pr, n, false, ids, ctl);
         RFB_CHECK_LAUNCH(ctx);
     }
     return finish_count(ctx, count);

@@ -1,10 +1,12 @@
 // rfb_scan.cuh — single-pass order-preserving compaction (chained scan with decoupled look-back), shared by the
 // selection-vector kernels (k_select.cu) and the group-numbering kernels (k_group.cu).
 //
-// Tiles take their index from an atomic ticket (so a tile only ever waits on tiles that already started), each CTA
-// counts its selected rows with warp ballots, publishes (AGGREGATE | count) in a 64-bit status word, walks back over its
-// predecessors' words 32 at a time until it meets an INCLUSIVE one, publishes its own inclusive prefix and then writes
-// its outputs at that offset.
+// Tile index = blockIdx.x.  A tile only waits on lower-numbered tiles, and the hardware work distributor hands out the
+// CTAs of a 1-D grid in increasing index order, so every predecessor has started by the time a tile spins on its status
+// word (the same assumption CUB's DeviceScan makes; an atomic ticket per tile cost ~25 % of the kernel on B200: one
+// global round trip plus a CTA barrier before the first load could be issued).  Each CTA counts its selected rows with
+// warp ballots, publishes (AGGREGATE | count) in a 64-bit status word, walks back over its predecessors' words 32 at a
+// time until it meets an INCLUSIVE one, publishes its own inclusive prefix and then writes its outputs at that offset.
 #pragma once
 #include "rfb_common.cuh"
 
@@ -53,37 +55,31 @@ __device__ __forceinline__ u64 lookback(u64 *state, u32 tile, u64 block_total) {
 
 struct TileCtl {
     u64 *state;     // one status word per tile (zeroed before the launch)
-    u32 *ticket;    // dynamic tile index
     i64 *total;     // device-visible: receives the number of outputs (written by the last tile)
     u32 tiles;
 };
 
-struct TileSmem {
-    u64 warp[WARPS];
+template <int NWARPS> struct TileSmemT {
+    u64 warp[NWARPS];
     u64 prefix;
-    u32 tile;
 };
-
-__device__ __forceinline__ u32 take_tile(const TileCtl &ctl, TileSmem &sm) {
-    if (threadIdx.x == 0) sm.tile = atomicAdd(ctl.ticket, 1u);
-    __syncthreads();
-    return sm.tile;
-}
+typedef TileSmemT<WARPS> TileSmem;
 
 // warp totals -> CTA offsets + global prefix.  Returns the global output offset of this warp's first selected row.
-__device__ __forceinline__ u64 tile_offsets(const TileCtl &ctl, u32 tile, u32 warp_total, TileSmem &sm) {
+template <int NWARPS>
+__device__ __forceinline__ u64 tile_offsets(const TileCtl &ctl, u32 tile, u32 warp_total, TileSmemT<NWARPS> &sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) sm.warp[warp] = warp_total;
     __syncthreads();
     if (warp == 0) {
-        u64 t = lane < WARPS ? sm.warp[lane] : 0, incl = t;
+        u64 t = lane < NWARPS ? sm.warp[lane] : 0, incl = t;
 #pragma unroll
-        for (int d = 1; d < WARPS; d <<= 1) {
+        for (int d = 1; d < NWARPS; d <<= 1) {
             const u64 o = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += o;
         }
-        const u64 block_total = __shfl_sync(0xffffffffu, incl, WARPS - 1);
-        if (lane < WARPS) sm.warp[lane] = incl - t;   // exclusive offset of each warp inside the tile
+        const u64 block_total = __shfl_sync(0xffffffffu, incl, NWARPS - 1);
+        if (lane < NWARPS) sm.warp[lane] = incl - t;   // exclusive offset of each warp inside the tile
         const u64 excl = lookback(ctl.state, tile, block_total);
         if (lane == 0) {
             sm.prefix = excl;
@@ -101,7 +97,7 @@ template <int J> struct RowTile { static constexpr int WROWS = 32 * J, TILE = WA
 template <int J, typename FlagFn, typename EmitFn>
 __device__ __forceinline__ void compact_rows(i64 n, const TileCtl &ctl, TileSmem &sm, FlagFn flag, EmitFn emit) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u32 tile = take_tile(ctl, sm);
+    const u32 tile = blockIdx.x;
     const i64 wbase = (i64)tile * RowTile<J>::TILE + (i64)warp * RowTile<J>::WROWS;
     bool f[J];
 #pragma unroll
@@ -126,7 +122,6 @@ __device__ __forceinline__ void compact_rows(i64 n, const TileCtl &ctl, TileSmem
 static inline int prepare_tiles(rfb_ctx_t *ctx, void *work, i64 tiles, i64 *total, TileCtl *ctl) {
     const size_t bytes = (size_t)tiles * 8 + 64;
     RFB_CUDA(cudaMemsetAsync(work, 0, bytes, ctx->stream));
-    ctl->ticket = (u32 *)work;
     ctl->state = (u64 *)((char *)work + 64);
     ctl->total = total;
     ctl->tiles = (u32)tiles;
