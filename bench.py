@@ -230,7 +230,7 @@ def run_gpu_arm(args):
     # --- the shard: rows [rank*n, (rank+1)*n) of the global column, generated straight into HBM
     with torch.cuda.stream(stream):
         x = torch.empty(n, dtype=torch.int64, device=dev)
-        res = torch.zeros(8, dtype=torch.int64, device=dev)      # rfb_fold_t image for the device-side merge
+        res = torch.zeros(16, dtype=torch.int64, device=dev)     # rfb_fold_t image (72 bytes) for the device-side merge
     ctx.fill_splitmix(capi.I64, x, n, shifted_seed(SEED, rank * n), MODULUS)
     ctx.sync()
 
@@ -321,7 +321,7 @@ def run_gpu_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t.item())
         e2e = {"value": n * world * Ke / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
-               "d2h_bytes_per_step": 64 * ((n * 8 + (64 << 20) - 1) // (64 << 20)), "steps": Ke,
+               "d2h_bytes_per_step": 72 * ((n * 8 + (64 << 20) - 1) // (64 << 20)), "steps": Ke,
                "ms_per_step": e2e_ms / Ke, "launches_per_step": (ctx.launches - le0) // Ke,
                "api": "rfb_filter_fold_host (pinned host column -> chunked cudaMemcpyAsync + fused kernel -> host result)"}
         del hx, hx_t

@@ -97,6 +97,8 @@ typedef struct {
     double sum_f64;
     int64_t min_i64, max_i64;
     double min_f64, max_f64;
+    double sum_f64_err; /* F64 sums are accumulated error-free (TwoSum) as hi + lo; sum_f64 is hi + lo rounded once and this
+                           is the residual it dropped, so partial results can be merged without losing the 1-ULP property */
 } rfb_fold_t;
 
 typedef struct rfb_ctx rfb_ctx_t; /* opaque: device, stream, scratch, pinned staging */

@@ -58,7 +58,8 @@ class Scalar(C.Structure):
 class Fold(C.Structure):
     """rfb_fold_t"""
     _fields_ = [("rows", C.c_int64), ("nonnull", C.c_int64), ("sum_i64", C.c_int64), ("sum_f64", C.c_double),
-                ("min_i64", C.c_int64), ("max_i64", C.c_int64), ("min_f64", C.c_double), ("max_f64", C.c_double)]
+                ("min_i64", C.c_int64), ("max_i64", C.c_int64), ("min_f64", C.c_double), ("max_f64", C.c_double),
+                ("sum_f64_err", C.c_double)]
 
 
 class GroupInfo(C.Structure):

@@ -25,7 +25,51 @@ enum { FS_SUMCNT = RFB_F_SUM | RFB_F_CNT, FS_MINMAX = RFB_F_MIN | RFB_F_MAX, FS_
 struct Partial {
     i64 rows, nonnull;
     u64 sum, mn, mx;  // bit patterns of i64 or f64 depending on the value kind
+    u64 comp;         // f64 sums: bits of the compensation (low-order) term
 };
+
+// fp64 sums are carried as an unevaluated pair (hi, lo) and every addition is an error-free TwoSum (Knuth): the final
+// hi + lo is the exact sum of the inputs rounded ONCE (barring catastrophic cancellation), i.e. within 1 ULP of the true
+// sum no matter how the rows are split over threads, CTAs, chunks or GPUs — which is what makes the north_star's
+// "within 1 ULP" meaningful against a CPU path whose own summation order is unspecified.  ~7 flops per row: free next
+// to 8 bytes of HBM traffic.
+struct dd { f64 hi, lo; };
+__device__ __forceinline__ void two_sum_acc(f64 &hi, f64 &lo, f64 x) {
+    const f64 t = __dadd_rn(hi, x);
+    const f64 bp = __dsub_rn(t, hi);
+    lo = __dadd_rn(lo, __dadd_rn(__dsub_rn(hi, __dsub_rn(t, bp)), __dsub_rn(x, bp)));
+    hi = t;
+}
+__device__ __forceinline__ dd dd_add(dd a, dd b) {
+    two_sum_acc(a.hi, a.lo, b.hi);
+    a.lo = __dadd_rn(a.lo, b.lo);
+    return a;
+}
+__device__ __forceinline__ dd dd_block_reduce(dd v, f64 *smem /* 64 doubles */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        dd o;
+        o.hi = __shfl_down_sync(0xffffffffu, v.hi, d);
+        o.lo = __shfl_down_sync(0xffffffffu, v.lo, d);
+        v = dd_add(v, o);
+    }
+    __syncthreads();
+    if (lane == 0) { smem[2 * warp] = v.hi; smem[2 * warp + 1] = v.lo; }
+    __syncthreads();
+    if (warp == 0) {
+        v.hi = lane < nwarps ? smem[2 * lane] : 0.0;
+        v.lo = lane < nwarps ? smem[2 * lane + 1] : 0.0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            dd o;
+            o.hi = __shfl_down_sync(0xffffffffu, v.hi, d);
+            o.lo = __shfl_down_sync(0xffffffffu, v.lo, d);
+            v = dd_add(v, o);
+        }
+    }
+    return v;  // valid in thread 0
+}
 
 // Per-thread accumulators.  Row counters are 32-bit (a thread sees far fewer than 2^31 rows; the launcher checks) because
 // the scan kernels are bound by the INT32 pipe, not by HBM, as soon as the per-row instruction count reaches ~12
@@ -37,9 +81,10 @@ template <typename V, int FOLDS, bool COUNT_ROWS, bool LEAN> struct Acc {
     static constexpr bool FLT = (Elem<V>::kind == K_F64);
     u32 rows, nonnull;
     A sum, mn, mx;
+    A comp;  // f64 sums only: running compensation term
     __device__ __forceinline__ static A min_identity() { if constexpr (FLT) return (A)bits_f64(0x7FF0000000000000ULL); else return (A)RFB_INF_I64; }
     __device__ __forceinline__ static A max_identity() { if constexpr (FLT) return (A)bits_f64(0xFFF0000000000000ULL); else return (A)NULL_I64; }
-    __device__ __forceinline__ void init() { rows = 0; nonnull = 0; sum = (A)0; mn = min_identity(); mx = max_identity(); }
+    __device__ __forceinline__ void init() { rows = 0; nonnull = 0; sum = (A)0; comp = (A)0; mn = min_identity(); mx = max_identity(); }
     __device__ __forceinline__ static A widen(V v) { if constexpr (FLT) return (A)widen_f64(v); else return (A)widen_i64(v); }
     // fold one element; `sel` = row passed the predicate.  Nulls are skipped (FOLD_ADD*, MIN*, MAX*, CNT*: core/ops.h)
     __device__ __forceinline__ void take(V v, bool sel) {
@@ -48,8 +93,8 @@ template <typename V, int FOLDS, bool COUNT_ROWS, bool LEAN> struct Acc {
         nonnull += ok;
         const A w = widen(v);
         if (FOLDS & RFB_F_SUM) {
-            if (FLT) sum = sum + (ok ? w : (A)0);              // x + 0.0 == x for every non-NaN x that can occur here
-            else sum = (A)((u64)sum + (ok ? (u64)w : 0ULL));   // wraps mod 2^64 like the reference's plain C add
+            if constexpr (FLT) two_sum_acc(sum, comp, ok ? w : (A)0);   // adding 0.0 is exact: skipped rows leave (sum, comp) alone
+            else sum = (A)((u64)sum + (ok ? (u64)w : 0ULL));            // wraps mod 2^64 like the reference's plain C add
         }
         if (FOLDS & RFB_F_MIN) { const A c = ok ? w : min_identity(); mn = c < mn ? c : mn; }
         if (FOLDS & RFB_F_MAX) { const A c = ok ? w : max_identity(); mx = c > mx ? c : mx; }
@@ -70,22 +115,22 @@ struct MaxPlain { template <typename T> __device__ __forceinline__ T operator()(
 // rows_override >= 0: the selected-row count is known to the host (no predicate) ; -1: report the counted rows;
 // -2: rows were not counted (null-excluding fast path) -> reported as -1.
 template <typename A, int FOLDS>
-__device__ __forceinline__ void finish_fold(i64 rows, i64 nonnull, A sum, A mn, A mx, A min_id, A max_id, int vkind, i64 rows_override,
+__device__ __forceinline__ void finish_fold(i64 rows, i64 nonnull, A sum, A comp, A mn, A mx, A min_id, A max_id, int vkind, i64 rows_override,
                                             Partial *partials, u32 *ticket, rfb_fold_t *out) {
     constexpr bool FLT = (sizeof(A) == 8) && (A(0.5) != A(0));  // true for f64, false for i64
-    __shared__ u64 red_smem[32];
+    __shared__ u64 red_smem[64];
     __shared__ bool is_last;
     rows = block_reduce<i64>(rows, OpAddWrap(), 0, (i64 *)red_smem);
     nonnull = block_reduce<i64>(nonnull, OpAddWrap(), 0, (i64 *)red_smem);
     if (FOLDS & RFB_F_SUM) {
-        if (FLT) sum = block_reduce<A>(sum, OpAdd(), (A)0, (A *)red_smem);
+        if constexpr (FLT) { dd r = dd_block_reduce(dd{(f64)sum, (f64)comp}, (f64 *)red_smem); sum = (A)r.hi; comp = (A)r.lo; }
         else sum = (A)block_reduce<i64>((i64)sum, OpAddWrap(), 0, (i64 *)red_smem);
     }
     if (FOLDS & RFB_F_MIN) mn = block_reduce<A>(mn, MinPlain(), min_id, (A *)red_smem);
     if (FOLDS & RFB_F_MAX) mx = block_reduce<A>(mx, MaxPlain(), max_id, (A *)red_smem);
     if (threadIdx.x == 0) {
         Partial p;
-        p.rows = rows; p.nonnull = nonnull; p.sum = to_bits(sum); p.mn = to_bits(mn); p.mx = to_bits(mx);
+        p.rows = rows; p.nonnull = nonnull; p.sum = to_bits(sum); p.mn = to_bits(mn); p.mx = to_bits(mx); p.comp = to_bits(comp);
         partials[blockIdx.x] = p;
         __threadfence();
         const u32 t = atomicAdd(ticket, 1u);
@@ -95,18 +140,21 @@ __device__ __forceinline__ void finish_fold(i64 rows, i64 nonnull, A sum, A mn, 
     if (!is_last) return;
     __threadfence();
     // last CTA: fixed-order fold of the per-CTA partials
-    i64 r = 0, nn = 0; A s = (A)0, lo = min_id, hi = max_id;
+    i64 r = 0, nn = 0; A s = (A)0, sc = (A)0, lo = min_id, hi = max_id;
     for (u32 b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
         const Partial p = partials[b];
         r += p.rows; nn += p.nonnull;
-        if (FOLDS & RFB_F_SUM) { if (FLT) s = s + from_bits<A>(p.sum); else s = (A)((u64)s + p.sum); }
+        if (FOLDS & RFB_F_SUM) {
+            if constexpr (FLT) { dd t = dd_add(dd{(f64)s, (f64)sc}, dd{bits_f64(p.sum), bits_f64(p.comp)}); s = (A)t.hi; sc = (A)t.lo; }
+            else s = (A)((u64)s + p.sum);
+        }
         if (FOLDS & RFB_F_MIN) { A c = from_bits<A>(p.mn); lo = c < lo ? c : lo; }
         if (FOLDS & RFB_F_MAX) { A c = from_bits<A>(p.mx); hi = c > hi ? c : hi; }
     }
     r = block_reduce<i64>(r, OpAddWrap(), 0, (i64 *)red_smem);
     nn = block_reduce<i64>(nn, OpAddWrap(), 0, (i64 *)red_smem);
     if (FOLDS & RFB_F_SUM) {
-        if (FLT) s = block_reduce<A>(s, OpAdd(), (A)0, (A *)red_smem);
+        if constexpr (FLT) { dd t = dd_block_reduce(dd{(f64)s, (f64)sc}, (f64 *)red_smem); s = (A)t.hi; sc = (A)t.lo; }
         else s = (A)block_reduce<i64>((i64)s, OpAddWrap(), 0, (i64 *)red_smem);
     }
     if (FOLDS & RFB_F_MIN) lo = block_reduce<A>(lo, MinPlain(), min_id, (A *)red_smem);
@@ -115,9 +163,10 @@ __device__ __forceinline__ void finish_fold(i64 rows, i64 nonnull, A sum, A mn, 
         rfb_fold_t res;
         res.rows = rows_override >= 0 ? rows_override : (rows_override == -2 ? -1 : r);
         res.nonnull = nn;
-        res.sum_i64 = 0; res.sum_f64 = 0.0; res.min_i64 = res.max_i64 = 0; res.min_f64 = res.max_f64 = 0.0;
-        if (FLT) {
-            res.sum_f64 = (f64)s;
+        res.sum_i64 = 0; res.sum_f64 = 0.0; res.min_i64 = res.max_i64 = 0; res.min_f64 = res.max_f64 = 0.0; res.sum_f64_err = 0.0;
+        if constexpr (FLT) {
+            res.sum_f64 = __dadd_rn((f64)s, (f64)sc);                                        // the one rounding
+            res.sum_f64_err = __dadd_rn(__dsub_rn((f64)s, res.sum_f64), (f64)sc);            // what it dropped (for further merging)
             res.min_f64 = nn ? (f64)lo : null_f64();
             res.max_f64 = nn ? (f64)hi : null_f64();
         } else {
@@ -214,7 +263,7 @@ k_scan_fold(const P *__restrict__ pred, PredRange pr, const V *__restrict__ val,
         acc.take(v, sel);
     }
     typedef typename Acc<V, FOLDS, COUNT_ROWS, LEAN>::A A;
-    finish_fold<A, FOLDS>((i64)acc.rows, (i64)acc.nonnull, acc.sum, acc.mn, acc.mx, Acc<V, FOLDS, COUNT_ROWS, LEAN>::min_identity(),
+    finish_fold<A, FOLDS>((i64)acc.rows, (i64)acc.nonnull, acc.sum, acc.comp, acc.mn, acc.mx, Acc<V, FOLDS, COUNT_ROWS, LEAN>::min_identity(),
                           Acc<V, FOLDS, COUNT_ROWS, LEAN>::max_identity(), vkind, HAS_PRED ? (LEAN ? -2 : -1) : n, partials, ticket, out);
 }
 
@@ -258,7 +307,7 @@ k_fma_fold(const f64 *__restrict__ a, const f64 *__restrict__ b, const f64 *__re
     }
     for (i64 r = chunks * 2 + (i64)blockIdx.x * THREADS + threadIdx.x; r < n; r += (i64)gridDim.x * THREADS)
         acc.take(eval(ld_stream(a + r), ld_stream(b + r), ld_stream(c + r)), true);
-    finish_fold<f64, FOLDS>(0, (i64)acc.nonnull, acc.sum, acc.mn, acc.mx, Acc<f64, FOLDS, false, false>::min_identity(),
+    finish_fold<f64, FOLDS>(0, (i64)acc.nonnull, acc.sum, acc.comp, acc.mn, acc.mx, Acc<f64, FOLDS, false, false>::min_identity(),
                             Acc<f64, FOLDS, false, false>::max_identity(), K_F64, n, partials, ticket, out);
 }
 
@@ -285,7 +334,7 @@ k_gather_fold(const V *__restrict__ col, const i64 *__restrict__ ids, i64 m, int
     }
     for (; i < m; i += stride) acc.take(__ldg(col + ld_stream(ids + i)), true);
     typedef typename Acc<V, FOLDS, false, false>::A A;
-    finish_fold<A, FOLDS>(0, (i64)acc.nonnull, acc.sum, acc.mn, acc.mx, Acc<V, FOLDS, false, false>::min_identity(),
+    finish_fold<A, FOLDS>(0, (i64)acc.nonnull, acc.sum, acc.comp, acc.mn, acc.mx, Acc<V, FOLDS, false, false>::min_identity(),
                           Acc<V, FOLDS, false, false>::max_identity(), vkind, m, partials, ticket, out);
 }
 

@@ -37,7 +37,10 @@ void combine(rfb_fold_t *acc, const rfb_fold_t *part, int vkind, bool first) {
     acc->rows += part->rows;
     acc->nonnull += part->nonnull;
     if (vkind == K_F64) {
-        acc->sum_f64 = acc->sum_f64 + part->sum_f64;
+        // error-free merge of the chunk sums: (hi, lo) pairs added with TwoSum, rounded once at the end (finalise_f64)
+        const double a = acc->sum_f64, b = part->sum_f64, t = a + b, bp = t - a;
+        acc->sum_f64_err = acc->sum_f64_err + part->sum_f64_err + ((a - (t - bp)) + (b - bp));
+        acc->sum_f64 = t;
         if (!part_empty) {
             acc->min_f64 = acc_empty ? part->min_f64 : (part->min_f64 < acc->min_f64 ? part->min_f64 : acc->min_f64);
             acc->max_f64 = acc_empty ? part->max_f64 : (part->max_f64 > acc->max_f64 ? part->max_f64 : acc->max_f64);
@@ -100,6 +103,11 @@ int pipeline(rfb_ctx_t *ctx, bool has_pred, int cmp_op, int pred_type, const voi
     const rfb_fold_t *slots = (const rfb_fold_t *)ctx->h_result;
     const int vk = rfb_kind_of(val_type);
     for (i64 c = 0; c < nchunks; c++) combine(out, &slots[c], vk, c == 0);
+    if (vk == K_F64) {  // round the merged pair once
+        const double hi = out->sum_f64, lo = out->sum_f64_err, s = hi + lo;
+        out->sum_f64_err = (hi - s) + lo;
+        out->sum_f64 = s;
+    }
     if (h2d_bytes) *h2d_bytes = copied;
     return RFB_OK;
 }

@@ -43,9 +43,11 @@ def ulp(x: float) -> float:
 
 
 def f64_sum_ok(got: float, cpu: float, exact: float) -> bool:
-    """north_star tolerance for fp64 reductions: within 1 ULP of the exactly-rounded sum, or no worse than the
-    reference CPU path's own error (whose order is unspecified under -fassociative-math)."""
-    return abs(got - exact) <= max(ulp(exact), abs(cpu - exact))
+    """north_star tolerance for fp64 reductions: within 1 ULP.  The reference CPU path's own summation order is unspecified
+    (thread count x -fassociative-math), so "of the reference" is not well defined; the GPU kernels accumulate error-free
+    (TwoSum) and round once, and are held to 1 ULP of the EXACT sum (a __float128 sum rounded to double) — which also
+    puts them within the reference's own error of the reference.  `cpu` is kept for reporting only."""
+    return abs(got - exact) <= ulp(exact)
 
 
 def same_f64(a, b, zero_sign=True, max_ulp=0) -> bool:
