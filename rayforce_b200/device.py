@@ -190,6 +190,7 @@ class _Ops:
         n = xn if xn >= 0 else yn
         mask = self._empty(n, capi.B8)
         check(self.lib.rfb_cmp_dev(self.h, op, xt, xp, xn, _sref(xs), yt, yp, yn, _sref(ys), _dptr(mask)))
+        self.sync()   # the context's stream is non-blocking: make the result visible to torch's streams
         return mask
 
     def where(self, mask):
@@ -212,6 +213,7 @@ class _Ops:
         """filter_collect / at_ids"""
         out = self._empty(ids.shape[0], t)
         check(self.lib.rfb_gather_dev(self.h, t, _dptr(col), _dptr(ids), ids.shape[0], _dptr(out)))
+        self.sync()
         return out
 
     def binop_type(self, op, xt, yt):
@@ -229,11 +231,13 @@ class _Ops:
             check(self.lib.rfb_binop_dev(self.h, op, xt, xp, xn, _sref(xs), yt, yp, yn, _sref(ys), None))
         out = self._empty(xn if xn >= 0 else yn, ot)
         check(self.lib.rfb_binop_dev(self.h, op, xt, xp, xn, _sref(xs), yt, yp, yn, _sref(ys), _dptr(out)))
+        self.sync()
         return out, ot
 
     def unop_f64(self, op, x):
         out = self._empty(x.shape[0], capi.F64)
         check(self.lib.rfb_unop_f64_dev(self.h, op, _dptr(x), x.shape[0], _dptr(out)))
+        self.sync()
         return out
 
     def group_i64(self, keys, filt=None):
