@@ -231,6 +231,7 @@ def run_gpu_arm(args):
     with torch.cuda.stream(stream):
         x = torch.empty(n, dtype=torch.int64, device=dev)
         res = torch.zeros(16, dtype=torch.int64, device=dev)     # rfb_fold_t image (72 bytes) for the device-side merge
+    res_host = torch.zeros(2, dtype=torch.int64).pin_memory()    # merged (nonnull, sum) lands here
     ctx.fill_splitmix(capi.I64, x, n, shifted_seed(SEED, rank * n), MODULUS)
     ctx.sync()
 
@@ -252,9 +253,10 @@ def run_gpu_arm(args):
             ev_e.record(stream)
         with torch.cuda.stream(stream):
             dist.all_reduce(res[1:3])                             # nonnull, sum_i64 (wraps mod 2^64)
-            h = res[1:3].cpu()
+            res_host.copy_(res[1:3], non_blocking=True)
+        stream.synchronize()
         ctx.set_result_ptr(None)
-        return int(h[0]), int(h[1])
+        return int(res_host[0]), int(res_host[1])
 
     sampler = ClockSampler(local)
 

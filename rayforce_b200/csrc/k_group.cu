@@ -574,6 +574,28 @@ constexpr int FUSED_PRIV = 1536;   // 28 B x 1536 = 42 KB of CTA-private accumul
 
 // PRIV (range <= FUSED_PRIV): first-row / sum / count / null-flag slots live in shared memory per CTA and are merged into
 // the device-wide arrays once per CTA; otherwise every row updates the device-wide (L2-resident) arrays directly.
+// first-row claims over a row prefix [r0, r1) only (device-wide path): in the accumulate pass a claim costs one L2 read per
+// row although it can only change anything while a key has not been seen yet; the host extends the prefix until every
+// non-empty slot has been claimed (one short pass for any column whose keys all occur early, e.g. uniform keys).
+template <typename FS>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_fused_claim(FS fs, i64 r0, i64 r1, i64 kmin, u64 *first_row) {
+    for (i64 i = r0 + (i64)blockIdx.x * THREADS + threadIdx.x; i < r1; i += (i64)gridDim.x * THREADS)
+        if (fs.selected(i)) claim_first(first_row, (i64)((u64)fs.key(i) - (u64)kmin), i);
+}
+
+// mm[3] = slots with rows, mm[4] = slots whose first row is known
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_slot_census(const u64 *first_row, const u64 *cnt, i64 range, i64 *mm) {
+    __shared__ i64 red[32];
+    i64 nonempty = 0, claimed = 0;
+    for (i64 s = (i64)blockIdx.x * THREADS + threadIdx.x; s < range; s += (i64)gridDim.x * THREADS) {
+        nonempty += cnt[s] != 0;
+        claimed += first_row[s] != NO_ROW;
+    }
+    nonempty = block_reduce<i64>(nonempty, OpAddWrap(), 0, red);
+    claimed = block_reduce<i64>(claimed, OpAddWrap(), 0, red);
+    if (threadIdx.x == 0) { atomicAdd((unsigned long long *)&mm[3], (unsigned long long)nonempty); atomicAdd((unsigned long long *)&mm[4], (unsigned long long)claimed); }
+}
+
 template <typename FS, bool PRIV>
 __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
 k_fused_accum(FS fs, const i64 *__restrict__ val, i64 n, i64 kmin, i64 range, Accums ga) {
@@ -593,7 +615,7 @@ k_fused_accum(FS fs, const i64 *__restrict__ val, i64 n, i64 kmin, i64 range, Ac
         if (!sel) return;
         const i64 s = (i64)((u64)k - (u64)kmin);
         if constexpr (PRIV) { if (a.first_row[s] > (u64)i) atomicMin((unsigned long long *)&a.first_row[s], (unsigned long long)i); }
-        else claim_first(a.first_row, s, i);
+        // (device-wide path: first rows are claimed afterwards on a row prefix, k_fused_claim)
         if (v == NULL_I64) a.has_null[s] = 1u; else atomicAdd((unsigned long long *)a.sum + s, (unsigned long long)v);
         atomicAdd((unsigned long long *)a.cnt + s, 1ULL);
     };
@@ -665,9 +687,29 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
     a.has_null = (u32 *)((char *)w + 3 * b8);
     RFB_CUDA(cudaMemsetAsync(a.first_row, 0xFF, (size_t)range * 8, ctx->stream));
     RFB_CUDA(cudaMemsetAsync(a.sum, 0, 2 * b8 + b4, ctx->stream));
-    if (range <= FUSED_PRIV && n >= 65536) k_fused_accum<FS, true><<<grid, THREADS, (size_t)range * 28, ctx->stream>>>(fs, val, n, h[0], range, a);
-    else k_fused_accum<FS, false><<<grid, THREADS, 0, ctx->stream>>>(fs, val, n, h[0], range, a);
-    RFB_CHECK_LAUNCH(ctx);
+    if (range <= FUSED_PRIV && n >= 65536) {
+        k_fused_accum<FS, true><<<grid, THREADS, (size_t)range * 28, ctx->stream>>>(fs, val, n, h[0], range, a);
+        RFB_CHECK_LAUNCH(ctx);
+    } else {
+        k_fused_accum<FS, false><<<grid, THREADS, 0, ctx->stream>>>(fs, val, n, h[0], range, a);
+        RFB_CHECK_LAUNCH(ctx);
+        i64 r0 = 0, r1 = 32 * range > 65536 ? 32 * range : 65536;
+        while (true) {
+            if (r1 > n) r1 = n;
+            k_fused_claim<FS><<<rfb_grid_for(ctx, r1 - r0, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(fs, r0, r1, h[0], a.first_row);
+            RFB_CHECK_LAUNCH(ctx);
+            if (r1 == n) break;
+            RFB_CUDA(cudaMemsetAsync(mm + 3, 0, 16, ctx->stream));
+            k_slot_census<<<rfb_grid_for(ctx, range, THREADS, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(a.first_row, a.cnt, range, mm);
+            RFB_CHECK_LAUNCH(ctx);
+            i64 census[2];
+            rc = d2h_sync(ctx, census, mm + 3, 16);
+            if (rc) return rc;
+            if (census[0] == census[1]) break;   // every key that occurs has its first row
+            r0 = r1;
+            r1 = r1 * 4;
+        }
+    }
     k_max_first<<<rfb_grid_for(ctx, range, THREADS, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(a.first_row, range, mm);
     RFB_CHECK_LAUNCH(ctx);
     i64 limit = 0;

@@ -332,6 +332,23 @@ def test_fused_group_sum_count(ctx, oracle, key_type, with_pred, n, card):
     assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val, wg, wi.groups, filt)[0])
 
 
+def test_fused_group_late_first_occurrence(ctx, oracle):
+    """device-wide path: first rows are claimed on a growing row prefix; a key that only shows up in the last rows must
+    still get its (late) first row and its place in the first-occurrence order"""
+    n, card = 1_000_003, 2000
+    r = np.random.default_rng(5)
+    keys = r.integers(0, card - 3, n).astype(np.int64)
+    keys[n - 1] = card - 1
+    keys[n // 2] = card - 2
+    keys[70_000] = card - 3
+    val = r.integers(0, 1000, n).astype(np.int64)
+    gk, gs, gc = ctx.group_sum_count(ob.I64, dev(keys), dev(val), card)
+    wg, wf, wi = oracle.group_i64(keys)
+    assert np.array_equal(host(gk), keys[wf]) and host(gk)[-1] == card - 1
+    assert np.array_equal(host(gs), oracle.aggr(ob.SUM, ob.I64, val, wg, wi.groups)[0])
+    assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val, wg, wi.groups)[0])
+
+
 def test_fused_group_nothing_selected(ctx):
     keys, val = dev(np.arange(100, dtype=np.int64)), dev(np.arange(100, dtype=np.int64))
     gk, gs, gc = ctx.group_sum_count(ob.I64, keys, val, 10, cmp_op=capi.LT, pred_type=ob.I64, pred=val, k=-5)
