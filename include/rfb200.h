@@ -203,6 +203,14 @@ typedef struct {
 int rfb_group_i64_dev(rfb_ctx_t *ctx, const int64_t *keys, const int64_t *filter, int64_t len, int64_t *group_ids,
                       int64_t *first_ids, rfb_group_info_t *info);
 
+/* index_group_list, perfect-hash key-fusion path (core/index.c:2308-2424): groups rows by the TUPLE of `ncols` (<= 8) I64-kind
+ * key columns, numbered by first occurrence like the single-key index.  Every column's scope is taken, the tuple is fused
+ * into one key sum_c (col_c - min_c) * stride_c and grouped by rfb_group_i64_dev.  RFB_ERR_ARG when the product of the key
+ * ranges does not fit 62 bits (the reference then hashes rows and radix-partitions, core/index.c:2556-2729: not built).
+ * Outputs as rfb_group_i64_dev (info->min/max/range describe the fused key). */
+int rfb_group_keys_i64_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const *cols, const int64_t *filter, int64_t len,
+                           int64_t *group_ids, int64_t *first_ids, rfb_group_info_t *info);
+
 /* aggr_sum/min/max/count/avg (core/aggr.c AGGR_ITER :73-161): out[gid] (+)= val[row]; sticky-null sum, +INF-init
  * min, NULL-init max, row count, f64 avg.  out: `groups` elements of rfb_aggr_type(op, val_type). */
 int rfb_aggr_type(int op, int val_type);

@@ -173,6 +173,21 @@ class Oracle:
             raise OracleError(r)
         return gids, firsts[:info.groups].copy(), info
 
+    def group_multi(self, cols, filt=None):
+        cols = [np.ascontiguousarray(c, np.int64) for c in cols]
+        if filt is not None:
+            filt = np.ascontiguousarray(filt, np.int64)
+        n = cols[0].shape[0] if filt is None else filt.shape[0]
+        gids, firsts = np.empty(n, np.int64), np.empty(n, np.int64)
+        arr = (C.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+        g = C.c_int64(0)
+        self.L.rfo_group_multi.restype = C.c_int
+        self.L.rfo_group_multi.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+        r = self.L.rfo_group_multi(len(cols), arr, _ptr(filt), n, _ptr(gids), _ptr(firsts), C.byref(g))
+        if r < 0:
+            raise OracleError(r)
+        return gids, firsts[:g.value].copy(), g.value
+
     def aggr(self, op, vt, val, gids, groups, filt=None):
         val = np.ascontiguousarray(val, NP_OF[vt])
         gids = np.ascontiguousarray(gids, np.int64)

@@ -470,6 +470,38 @@ int rfo_group_i64(const int64_t *keys, const int64_t *filter, int64_t len, int64
     return RFO_OK;
 }
 
+/* multi-key grouping: core/index.c:2731-2793 index_group_list (perfect-hash key fusion :2308-2424, or row hashes + radix
+ * partitions :2556-2729).  Whatever the internal path, groups are numbered by first occurrence of the key TUPLE in
+ * (filtered) row order (pinned against the reference's `select ... by: {a: a b: b}` in tests/test_oracle_vs_reference.py).
+ * Restated with one open-addressing table over tuple hashes. */
+int rfo_group_multi(int ncols, const int64_t *const *cols, const int64_t *filter, int64_t len, int64_t *group_ids,
+                    int64_t *first_ids, int64_t *groups_out) {
+    if (ncols < 1) return RFO_ERR_TYPE;
+    i64 cap = 16;
+    while (cap < 2 * len + 1) cap <<= 1;
+    i64 *slot = (i64 *)malloc((size_t)cap * 8);   /* group id or -1 */
+    for (i64 i = 0; i < cap; i++) slot[i] = -1;
+    i64 groups = 0;
+    for (i64 i = 0; i < len; i++) {
+        const i64 row = filter ? filter[i] : i;
+        u64 h = 0x9E3779B97F4A7C15ULL;
+        for (int c = 0; c < ncols; c++) h = (h ^ fnv1a64(cols[c][row])) * 0xBF58476D1CE4E5B9ULL;
+        i64 s = (i64)(h & (u64)(cap - 1));
+        for (;;) {
+            const i64 g = slot[s];
+            if (g < 0) { slot[s] = groups; first_ids[groups] = i; group_ids[i] = groups; groups++; break; }
+            const i64 frow = filter ? filter[first_ids[g]] : first_ids[g];
+            int same = 1;
+            for (int c = 0; c < ncols && same; c++) same = cols[c][frow] == cols[c][row];
+            if (same) { group_ids[i] = g; break; }
+            s = (s + 1) & (cap - 1);
+        }
+    }
+    free(slot);
+    *groups_out = groups;
+    return RFO_OK;
+}
+
 /* ------------------------------------------------------------------ grouped aggregates (core/aggr.c) */
 
 int rfo_aggr(int op, int val_type, const void *val, const int64_t *filter, const int64_t *gid, int64_t len,

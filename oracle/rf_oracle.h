@@ -85,6 +85,10 @@ typedef struct {
 int rfo_group_i64(const int64_t *keys, const int64_t *filter, int64_t len, int64_t *group_ids, int64_t *first_ids,
                   int64_t *hk, rfo_group_info_t *info);
 
+/* multi-key grouping (core/index.c:2731-2793): first-occurrence numbering of key tuples */
+int rfo_group_multi(int ncols, const int64_t *const *cols, const int64_t *filter, int64_t len, int64_t *group_ids,
+                    int64_t *first_ids, int64_t *groups_out);
+
 /* ---- grouped aggregates: core/aggr.c:73-161 (AGGR_ITER), :1078-1453, :1455-2133 ----
  * val: column of val_type indexed by row; filter: row ids or NULL; group_ids[i] for i in [0,len).
  * out: `groups` entries of *out_type (sum/min/max: val type; count: I64; avg: F64). */

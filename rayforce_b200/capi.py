@@ -115,6 +115,7 @@ SIGNATURES = {
     "rfb_binop_dev": (_ci, [_vp, _ci, _ci, _vp, _i64, _P(Scalar), _ci, _vp, _i64, _P(Scalar), _vp]),
     "rfb_unop_f64_dev": (_ci, [_vp, _ci, _vp, _i64, _vp]),
     "rfb_group_i64_dev": (_ci, [_vp, _vp, _vp, _i64, _vp, _vp, _P(GroupInfo)]),
+    "rfb_group_keys_i64_dev": (_ci, [_vp, _ci, _P(_vp), _vp, _i64, _vp, _vp, _P(GroupInfo)]),
     "rfb_aggr_type": (_ci, [_ci, _ci]),
     "rfb_aggr_dev": (_ci, [_vp, _ci, _ci, _vp, _vp, _vp, _i64, _i64, _vp]),
     "rfb_group_sum_count_dev": (_ci, [_vp, _ci, _vp, _vp, _i64, _ci, _ci, _vp, _P(Scalar), _i64, _vp, _vp, _vp, _P(_i64)]),

@@ -290,6 +290,71 @@ extern "C" int rfb_group_i64_dev(rfb_ctx_t *ctx, const int64_t *keys, const int6
     return RFB_OK;
 }
 
+// ------------------------------------------------------------------ multi-key grouping: perfect-hash key fusion
+
+namespace {
+constexpr int MAX_KEY_COLS = 8;
+struct FuseSpec {
+    const i64 *col[MAX_KEY_COLS];
+    i64 min[MAX_KEY_COLS];
+    i64 stride[MAX_KEY_COLS];
+    int ncols;
+};
+// fused[i] = sum_c (col_c[row_i] - min_c) * stride_c : a bijection from key tuples to [0, prod ranges)
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_fuse_keys(FuseSpec f, const i64 *__restrict__ filter, i64 n, i64 *__restrict__ fused) {
+    for (i64 i = (i64)blockIdx.x * THREADS + threadIdx.x; i < n; i += (i64)gridDim.x * THREADS) {
+        const i64 row = filter ? ld_stream(filter + i) : i;
+        u64 k = 0;
+        for (int c = 0; c < f.ncols; c++) {
+            const i64 v = filter ? __ldg(f.col[c] + row) : ld_stream(f.col[c] + row);
+            k += ((u64)v - (u64)f.min[c]) * (u64)f.stride[c];
+        }
+        fused[i] = (i64)k;
+    }
+}
+}  // namespace
+
+extern "C" int rfb_group_keys_i64_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const *cols, const int64_t *filter, int64_t len,
+                                      int64_t *group_ids, int64_t *first_ids, rfb_group_info_t *info) {
+    RFB_ARG(ctx && info && cols && ncols >= 1 && ncols <= MAX_KEY_COLS && len >= 0 && (first_ids || len == 0), "rfb_group_keys_i64_dev");
+    for (int c = 0; c < ncols; c++) RFB_ARG(cols[c] || len == 0, "rfb_group_keys_i64_dev: key column");
+    if (ncols == 1 || len == 0) return rfb_group_i64_dev(ctx, len ? cols[0] : nullptr, filter, len, group_ids, first_ids, info);
+    FuseSpec f;
+    f.ncols = ncols;
+    i64 *mm = (i64 *)((char *)ctx->d_scratch + 32768);
+    unsigned __int128 space = 1;
+    i64 range[MAX_KEY_COLS];
+    for (int c = 0; c < ncols; c++) {   // per-column scope (core/index.c:2308-2340 does the same before fusing)
+        KeySrc src{cols[c], filter};
+        k_scope_init<<<1, 1, 0, ctx->stream>>>(mm);
+        RFB_CHECK_LAUNCH(ctx);
+        k_scope<KeySrc><<<rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(src, len, mm);
+        RFB_CHECK_LAUNCH(ctx);
+        i64 h[2];
+        int rc = d2h_sync(ctx, h, mm, 16);
+        if (rc) return rc;
+        f.col[c] = cols[c];
+        f.min[c] = h[0];
+        const unsigned __int128 r = (unsigned __int128)((u64)h[1] - (u64)h[0]) + 1;
+        space *= r;
+        if (space > ((unsigned __int128)1 << 62)) {
+            rfb_set_error("multi-key group-by: the product of the key ranges does not fit 62 bits (row-hash grouping is not built)");
+            return RFB_ERR_ARG;
+        }
+        range[c] = (i64)r;
+    }
+    i64 stride = 1;
+    for (int c = ncols - 1; c >= 0; c--) { f.stride[c] = stride; stride *= range[c]; }
+    i64 *fused = nullptr;
+    RFB_CUDA(cudaMalloc(&fused, (size_t)len * 8));
+    k_fuse_keys<<<rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(f, filter, len, fused);
+    ctx->launches++;
+    int rc = cudaGetLastError() == cudaSuccess ? rfb_group_i64_dev(ctx, fused, nullptr, len, group_ids, first_ids, info) : RFB_ERR_CUDA;
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(fused);
+    return rc;
+}
+
 // ------------------------------------------------------------------ grouped aggregates
 
 namespace {

@@ -249,6 +249,16 @@ class _Ops:
         check(self.lib.rfb_group_i64_dev(self.h, _dptr(keys), _dptr(filt), n, _dptr(gids), _dptr(firsts), C.byref(info)))
         return gids, firsts[:info.groups], info
 
+    def group_keys(self, cols, filt=None):
+        """index_group_list (perfect-hash fusion): group by the tuple of I64-kind key columns"""
+        n = cols[0].shape[0] if filt is None else filt.shape[0]
+        gids = self._empty(n, capi.I64)
+        firsts = self._empty(n, capi.I64)
+        info = capi.GroupInfo()
+        arr = (C.c_void_p * len(cols))(*[_dptr(c) for c in cols])
+        check(self.lib.rfb_group_keys_i64_dev(self.h, len(cols), arr, _dptr(filt), n, _dptr(gids), _dptr(firsts), C.byref(info)))
+        return gids, firsts[:info.groups], info
+
     def aggr(self, op, vt, val, gids, groups, filt=None):
         """aggr_sum/min/max/count/avg -> (tensor[groups], result type)"""
         ot = self.lib.rfb_aggr_type(op, vt)

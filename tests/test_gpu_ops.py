@@ -250,6 +250,27 @@ def test_group_sparse_matches_oracle_numbering(ctx, oracle, n, filtered):
     assert np.array_equal(host(gf), wf) and np.array_equal(host(gg), wg)
 
 
+@pytest.mark.parametrize("ncols", [2, 3, 6])
+@pytest.mark.parametrize("filtered", [False, True])
+@pytest.mark.parametrize("n", [5, 70_001, 500_003])
+def test_group_multi_key_matches_oracle_numbering(ctx, oracle, ncols, filtered, n):
+    """index_group_list (perfect-hash key fusion, reference core/index.c:2308-2424): first-occurrence numbering of key tuples"""
+    r = np.random.default_rng(n + ncols)
+    cols = [(r.integers(0, 3 + c, n) * (c + 1) - 7 * c).astype(np.int64) for c in range(ncols)]
+    filt = np.sort(r.choice(n, max(1, n // 3), replace=False)).astype(np.int64) if filtered else None
+    wg, wf, groups = oracle.group_multi(cols, filt)
+    gg, gf, gi = ctx.group_keys([dev(c) for c in cols], dev(filt) if filtered else None)
+    assert gi.groups == groups
+    assert np.array_equal(host(gf), wf) and np.array_equal(host(gg), wg)
+
+
+def test_group_multi_key_space_too_large(ctx):
+    a = dev(np.array([0, 1 << 40, 5], np.int64))
+    with pytest.raises(capi.RfbError) as e:
+        ctx.group_keys([a, a, a])
+    assert e.value.kind == "arg"
+
+
 def test_group_empty(ctx):
     gg, gf, gi = ctx.group_i64(dev(np.empty(0, np.int64)), None)
     assert gi.groups == 0 and gi.dense == 1 and gf.shape[0] == 0

@@ -202,6 +202,35 @@ def test_grouped_aggregate_type_errors(oracle, reference, op, vt):
         reference.group_aggr(keys, vt, val, [op])
 
 
+@pytest.mark.parametrize("n", [1000, 60_000])
+def test_multi_key_group_by_through_rayfall_select(oracle, reference, n):
+    """(select {s: (sum v) c: (count v) from: t by: {a: a b: b c: c}}) through the reference's evaluator: its key-tuple order
+    is first occurrence, and sums/counts per tuple match the oracle's multi-key index + grouped aggregates"""
+    import ctypes as C
+    if not reference_scope_is_safe(n, reference.cores):
+        pytest.skip("reference index_scope_i64 reads out of bounds at this length / thread count (Q12)")
+    r = np.random.default_rng(n)
+    a, b, c = r.integers(0, 7, n), r.integers(-3, 4, n) * 1000, r.integers(100, 104, n)
+    v = r.integers(-50, 50, n)
+    for name, arr in (("mk_a", a), ("mk_b", b), ("mk_c", c), ("mk_v", v)):
+        o = reference.eval("(set %s (til %d))" % (name, n))
+        np.frombuffer((C.c_char * (n * 8)).from_address(o + 16), dtype=np.int64)[:] = arr
+    reference.eval("(set mk_t (table [a b c v] (list mk_a mk_b mk_c mk_v)))")
+    res = reference.eval("(select {s: (sum v) n: (count v) from: mk_t by: {a: a b: b c: c}})")
+    cols = [reference.to_numpy(x, drop=False)[0] for x in reference.list_items(reference.list_items(res)[1])]
+    gids, firsts, groups = oracle.group_multi([a, b, c])
+    assert groups == cols[0].shape[0]
+    want = np.stack([a[firsts], b[firsts], c[firsts], oracle.aggr(ob.SUM, ob.I64, v, gids, groups)[0],
+                     oracle.aggr(ob.COUNT, ob.I64, v, gids, groups)[0]])
+    got = np.stack(cols)
+    if n >= 16384:
+        # above its parallel threshold the reference's group ORDER depends on its thread count (the same Q9 as the
+        # single-key hash path): compare per key tuple
+        want = want[:, np.lexsort(want[:3][::-1])]
+        got = got[:, np.lexsort(got[:3][::-1])]
+    assert np.array_equal(got, want)
+
+
 def test_group_sparse_as_key_sorted_sets(oracle, reference):
     """hash path (range > len): the reference's group order depends on its thread count, so compare per key"""
     n = 100_003
