@@ -22,6 +22,8 @@ typedef double f64;
 
 #define RFB_RESULT_SLOTS 1024
 #define RFB_STAGE_BUFS 3
+#define RFB_HOST_RING 4
+#define RFB_HOST_RING_BYTES (16u << 20)
 
 struct rfb_ctx {
     int device;
@@ -43,12 +45,22 @@ struct rfb_ctx {
     // host layer staging
     void *d_stage[2][RFB_STAGE_BUFS];  // [column][ring slot] device staging for chunked column shipping
     size_t stage_bytes;
+    // pageable host memory: copier threads fill a ring of pinned buffers that the DMA engine drains (rfb_host.cu)
+    void *h_ring[RFB_HOST_RING];
+    cudaEvent_t ev_ring[RFB_HOST_RING];
+    int ring_next;
+    void *copy_pool;
     cudaEvent_t ev_copy[RFB_STAGE_BUFS], ev_kernel[RFB_STAGE_BUFS];
 };
 
 void rfb_set_error(const char *fmt, ...);
 int rfb_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 int rfb_ensure_work(rfb_ctx_t *ctx, size_t bytes, void **out);
+// host<->device copies that pick the fast route for the memory they are given (rfb_host.cu): pinned -> one async DMA;
+// pageable -> copier threads through the pinned ring.  `stream`: where the DMA is enqueued.
+int rfb_copy_h2d(rfb_ctx_t *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t stream);
+int rfb_copy_d2h(rfb_ctx_t *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t stream);
+void rfb_copy_shutdown(rfb_ctx_t *ctx);
 // launch-only entry points of k_fold.cu: the result lands in h_result[result_slot] once the stream drains
 int rfb_fold_launch(rfb_ctx_t *ctx, int folds, int type, const void *x, i64 n);
 int rfb_filter_fold_launch(rfb_ctx_t *ctx, int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k, int folds,

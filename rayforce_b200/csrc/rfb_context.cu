@@ -97,6 +97,7 @@ void rfb_ctx_destroy(rfb_ctx_t *ctx) {
         cudaEventDestroy(ctx->ev_copy[i]);
         cudaEventDestroy(ctx->ev_kernel[i]);
     }
+    rfb_copy_shutdown(ctx);
     if (ctx->d_work) cudaFree(ctx->d_work);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -176,12 +177,12 @@ int rfb_host_free_pinned(void *p) {
 }
 int rfb_h2d(rfb_ctx_t *ctx, void *dst_dev, const void *src_host, size_t bytes) {
     RFB_ARG(ctx && (bytes == 0 || (dst_dev && src_host)), "rfb_h2d");
-    if (bytes) RFB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bytes) return rfb_copy_h2d(ctx, dst_dev, src_host, bytes, ctx->stream);
     return RFB_OK;
 }
 int rfb_d2h(rfb_ctx_t *ctx, void *dst_host, const void *src_dev, size_t bytes) {
     RFB_ARG(ctx && (bytes == 0 || (dst_host && src_dev)), "rfb_d2h");
-    if (bytes) RFB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bytes) return rfb_copy_d2h(ctx, dst_host, src_dev, bytes, ctx->stream);
     return RFB_OK;
 }
 

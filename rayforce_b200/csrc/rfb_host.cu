@@ -8,7 +8,181 @@
 //
 // Pinned (cudaHostAlloc / rfb_host_pin) payloads are DMA'd directly; pageable payloads still work (the driver stages
 // them) but at a fraction of the PCIe rate — INTEGRATION.md tells the reference side to pin its column blocks.
+#include <pthread.h>
+#include <stdlib.h>
+#include <unistd.h>
+
 #include "rfb_common.cuh"
+
+// ------------------------------------------------------------------ copies that suit the memory they are given
+//
+// Measured on the B200 host (profiles/r01_h2d_probe.txt): DMA from pinned memory 55.6 GB/s; cudaMemcpy from pageable
+// memory 11 GB/s; cudaHostRegister itself only 12 GB/s (so registering per query buys nothing); 8 copier threads filling
+// a ring of pinned 16 MiB buffers that the DMA engine drains: 31 GB/s.  The reference's columns live in pageable heap
+// blocks, so that last route is what its integration gets unless it pins its blocks once at allocation.
+
+namespace {
+
+struct CopyPool {
+    int nthreads;
+    pthread_t th[16];
+    pthread_mutex_t mu;
+    pthread_cond_t cv_work, cv_done;
+    const char *src;
+    char *dst;
+    size_t bytes;
+    unsigned long gen;
+    int pending;
+    bool stop;
+};
+
+struct WorkerArg { CopyPool *p; int id; };
+
+void *copy_worker(void *a) {
+    WorkerArg *wa = (WorkerArg *)a;
+    CopyPool *p = wa->p;
+    const int id = wa->id;
+    free(wa);
+    unsigned long seen = 0;
+    for (;;) {
+        pthread_mutex_lock(&p->mu);
+        while (p->gen == seen && !p->stop) pthread_cond_wait(&p->cv_work, &p->mu);
+        if (p->stop) { pthread_mutex_unlock(&p->mu); return nullptr; }
+        seen = p->gen;
+        const char *src = p->src; char *dst = p->dst; const size_t bytes = p->bytes;
+        pthread_mutex_unlock(&p->mu);
+        const size_t per = (bytes / (size_t)(p->nthreads + 1) + 63) & ~(size_t)63, lo = per * (size_t)(id + 1);
+        if (lo < bytes) memcpy(dst + lo, src + lo, (lo + per < bytes) ? per : bytes - lo);
+        pthread_mutex_lock(&p->mu);
+        if (--p->pending == 0) pthread_cond_signal(&p->cv_done);
+        pthread_mutex_unlock(&p->mu);
+    }
+}
+
+CopyPool *pool_of(rfb_ctx_t *ctx) {
+    if (ctx->copy_pool) return (CopyPool *)ctx->copy_pool;
+    CopyPool *p = (CopyPool *)calloc(1, sizeof(CopyPool));
+    if (!p) return nullptr;
+    long cores = sysconf(_SC_NPROCESSORS_ONLN);
+    const char *e = getenv("RFB200_COPY_THREADS");
+    int want = e ? atoi(e) : 8;
+    if (want > cores - 1) want = (int)cores - 1;
+    if (want > 16) want = 16;
+    if (want < 0) want = 0;
+    pthread_mutex_init(&p->mu, nullptr);
+    pthread_cond_init(&p->cv_work, nullptr);
+    pthread_cond_init(&p->cv_done, nullptr);
+    for (int i = 0; i < want; i++) {   // the calling thread copies the first slice itself
+        WorkerArg *wa = (WorkerArg *)malloc(sizeof(WorkerArg));
+        wa->p = p; wa->id = p->nthreads;
+        if (pthread_create(&p->th[p->nthreads], nullptr, copy_worker, wa) == 0) p->nthreads++; else free(wa);
+    }
+    ctx->copy_pool = p;
+    return p;
+}
+
+// memcpy split over the pool (the caller takes slice 0)
+void parallel_memcpy(CopyPool *p, void *dst, const void *src, size_t bytes) {
+    if (!p || p->nthreads == 0 || bytes < (1u << 20)) { memcpy(dst, src, bytes); return; }
+    pthread_mutex_lock(&p->mu);
+    p->src = (const char *)src; p->dst = (char *)dst; p->bytes = bytes;
+    p->pending = p->nthreads;
+    p->gen++;
+    pthread_cond_broadcast(&p->cv_work);
+    pthread_mutex_unlock(&p->mu);
+    const size_t per = (bytes / (size_t)(p->nthreads + 1) + 63) & ~(size_t)63;
+    memcpy(dst, src, per < bytes ? per : bytes);
+    pthread_mutex_lock(&p->mu);
+    while (p->pending) pthread_cond_wait(&p->cv_done, &p->mu);
+    pthread_mutex_unlock(&p->mu);
+}
+
+bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+int ensure_ring(rfb_ctx_t *ctx) {
+    for (int i = 0; i < RFB_HOST_RING; i++)
+        if (!ctx->h_ring[i]) {
+            RFB_CUDA(cudaHostAlloc(&ctx->h_ring[i], RFB_HOST_RING_BYTES, cudaHostAllocDefault));
+            RFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_ring[i], cudaEventDisableTiming));
+        }
+    return RFB_OK;
+}
+
+constexpr size_t STAGED_MIN = 4u << 20;   // below this the plain call is as good
+
+}  // namespace
+
+int rfb_copy_h2d(rfb_ctx_t *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t stream) {
+    if (bytes < STAGED_MIN || is_pinned(src_host)) {
+        RFB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, stream));
+        return RFB_OK;
+    }
+    int rc = ensure_ring(ctx);
+    if (rc) return rc;
+    CopyPool *pool = pool_of(ctx);
+    for (size_t off = 0; off < bytes; off += RFB_HOST_RING_BYTES) {
+        const size_t len = bytes - off < RFB_HOST_RING_BYTES ? bytes - off : RFB_HOST_RING_BYTES;
+        const int b = ctx->ring_next;
+        ctx->ring_next = (b + 1) % RFB_HOST_RING;
+        RFB_CUDA(cudaEventSynchronize(ctx->ev_ring[b]));   // the DMA that last used this pinned buffer is done
+        parallel_memcpy(pool, ctx->h_ring[b], (const char *)src_host + off, len);
+        RFB_CUDA(cudaMemcpyAsync((char *)dst_dev + off, ctx->h_ring[b], len, cudaMemcpyHostToDevice, stream));
+        RFB_CUDA(cudaEventRecord(ctx->ev_ring[b], stream));
+    }
+    return RFB_OK;
+}
+
+// device -> pageable host: DMA into the pinned ring, copier threads move it out.  Returns with the data in place.
+int rfb_copy_d2h(rfb_ctx_t *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t stream) {
+    if (bytes < STAGED_MIN || is_pinned(dst_host)) {
+        RFB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, stream));
+        return RFB_OK;
+    }
+    int rc = ensure_ring(ctx);
+    if (rc) return rc;
+    CopyPool *pool = pool_of(ctx);
+    const size_t nchunks = (bytes + RFB_HOST_RING_BYTES - 1) / RFB_HOST_RING_BYTES;
+    // software pipeline: chunk c's DMA is in flight while chunk c-1 is copied out of its pinned buffer
+    for (size_t c = 0; c <= nchunks; c++) {
+        if (c < nchunks) {
+            const size_t off = c * RFB_HOST_RING_BYTES, len = bytes - off < RFB_HOST_RING_BYTES ? bytes - off : RFB_HOST_RING_BYTES;
+            const int b = (int)(c % RFB_HOST_RING);
+            if (c >= RFB_HOST_RING - 1) { /* buffer b was drained by the host at step c - RING + 1 <= c - 1: free */ }
+            RFB_CUDA(cudaMemcpyAsync(ctx->h_ring[b], (const char *)src_dev + off, len, cudaMemcpyDeviceToHost, stream));
+            RFB_CUDA(cudaEventRecord(ctx->ev_ring[b], stream));
+        }
+        if (c >= 1) {
+            const size_t pc = c - 1, off = pc * RFB_HOST_RING_BYTES, len = bytes - off < RFB_HOST_RING_BYTES ? bytes - off : RFB_HOST_RING_BYTES;
+            const int b = (int)(pc % RFB_HOST_RING);
+            RFB_CUDA(cudaEventSynchronize(ctx->ev_ring[b]));
+            parallel_memcpy(pool, (char *)dst_host + off, ctx->h_ring[b], len);
+        }
+    }
+    ctx->ring_next = 0;
+    return RFB_OK;
+}
+
+void rfb_copy_shutdown(rfb_ctx_t *ctx) {
+    CopyPool *p = (CopyPool *)ctx->copy_pool;
+    if (p) {
+        pthread_mutex_lock(&p->mu);
+        p->stop = true;
+        pthread_cond_broadcast(&p->cv_work);
+        pthread_mutex_unlock(&p->mu);
+        for (int i = 0; i < p->nthreads; i++) pthread_join(p->th[i], nullptr);
+        pthread_mutex_destroy(&p->mu);
+        pthread_cond_destroy(&p->cv_work);
+        pthread_cond_destroy(&p->cv_done);
+        free(p);
+        ctx->copy_pool = nullptr;
+    }
+    for (int i = 0; i < RFB_HOST_RING; i++)
+        if (ctx->h_ring[i]) { cudaFreeHost(ctx->h_ring[i]); cudaEventDestroy(ctx->ev_ring[i]); ctx->h_ring[i] = nullptr; }
+}
 
 namespace {
 
@@ -78,12 +252,12 @@ int pipeline(rfb_ctx_t *ctx, bool has_pred, int cmp_op, int pred_type, const voi
         // the staging slot is free once the kernel that last read it has finished
         if (c >= RFB_STAGE_BUFS) RFB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_kernel[b], 0));
         if (rows > 0) {
-            RFB_CUDA(cudaMemcpyAsync(ctx->d_stage[0][b], (const char *)val + r0 * vsz, (size_t)rows * vsz,
-                                     cudaMemcpyHostToDevice, ctx->copy_stream));
+            rc = rfb_copy_h2d(ctx, ctx->d_stage[0][b], (const char *)val + r0 * vsz, (size_t)rows * vsz, ctx->copy_stream);
+            if (rc) { ctx->result_slot = saved_slot; return rc; }
             copied += rows * vsz;
             if (ncols == 2) {
-                RFB_CUDA(cudaMemcpyAsync(ctx->d_stage[1][b], (const char *)pred + r0 * psz, (size_t)rows * psz,
-                                         cudaMemcpyHostToDevice, ctx->copy_stream));
+                rc = rfb_copy_h2d(ctx, ctx->d_stage[1][b], (const char *)pred + r0 * psz, (size_t)rows * psz, ctx->copy_stream);
+                if (rc) { ctx->result_slot = saved_slot; return rc; }
                 copied += rows * psz;
             }
         }

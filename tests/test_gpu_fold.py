@@ -255,6 +255,21 @@ def test_filter_fold_host_matches_device_layer(ctx, oracle, chunk):
     assert got.min == float(oracle.fold(ob.MIN, ob.F64, sel)[0]) and got.max == float(oracle.fold(ob.MAX, ob.F64, sel)[0])
 
 
+def test_host_layer_pageable_column_goes_through_the_pinned_ring(ctx, oracle):
+    """pageable host columns >= 4 MiB are moved by copier threads through a ring of pinned 16 MiB buffers
+    (rfb_copy_h2d); 10M rows = 80 MB = five ring buffers, reused once"""
+    n = 10_000_019
+    col = rng_col(ob.I64, n, seed=77, null_frac=0.01, lo=-(1 << 30), hi=1 << 30)
+    got, nbytes = ctx.filter_fold_host(ob.GE, ob.I64, col, -5, capi.F_ALL, ob.I64, col)
+    sel = col[(col >= -5)]
+    nn = sel[sel != ob.NULL_I64]
+    assert nbytes == 8 * n and got.rows == sel.shape[0] and got.nonnull == nn.shape[0]
+    assert got.sum == int(nn.sum(dtype=np.int64)) and got.min == int(nn.min()) and got.max == int(nn.max())
+    got2, _ = ctx.fold_host(capi.F_SUM | capi.F_CNT, ob.I64, col, chunk_rows=3_000_000)
+    allnn = col[col != ob.NULL_I64]
+    assert got2.sum == int(allnn.sum(dtype=np.int64)) and got2.nonnull == allnn.shape[0]
+
+
 def test_fold_host_empty_and_small(ctx, oracle):
     got, nbytes = ctx.fold_host(capi.F_ALL, ob.I64, np.empty(0, np.int64))
     assert (got.rows, got.sum, got.min, nbytes) == (0, 0, ob.NULL_I64, 0)

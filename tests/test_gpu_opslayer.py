@@ -152,6 +152,18 @@ def test_avg_of_expression_operator_sequence(ops, oracle):
     ops.drop(ao, bo, co)
 
 
+def test_large_operands_and_results_use_the_staged_copies(ops, oracle):
+    """16 MB operands / results: host objects are pageable, so both directions go through the copier-thread ring"""
+    n = 2_000_003
+    x = rng_col(ob.I64, n, 9, null_frac=0.01, lo=-1000, hi=1000)
+    xo, k = ops.vec(ob.I64, x), ops.atom(ob.I64, 10)
+    got, gt = ops.value(ops.call("ray_add", xo, k))
+    assert gt == ob.I64 and np.array_equal(got, oracle.binop(ob.ADD, ob.I64, x, ob.I64, 10)[0])
+    perm, pt = ops.value(ops.call("ray_sort_asc", xo))
+    assert np.array_equal(perm, oracle.sort(ob.I64, x))
+    ops.drop(xo, k)
+
+
 def test_errors_and_declines_follow_the_reference(ops):
     a, b = ops.vec(ob.I64, np.arange(10)), ops.vec(ob.I64, np.arange(11))
     for name in ("ray_lt", "ray_add"):
