@@ -114,10 +114,16 @@ int ensure_ring(rfb_ctx_t *ctx) {
 
 constexpr size_t STAGED_MIN = 4u << 20;   // below this the plain call is as good
 
+bool staged_enabled() {   // RFB200_STAGED_COPY=0 falls back to plain cudaMemcpyAsync from/to pageable memory
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("RFB200_STAGED_COPY"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+
 }  // namespace
 
 int rfb_copy_h2d(rfb_ctx_t *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t stream) {
-    if (bytes < STAGED_MIN || is_pinned(src_host)) {
+    if (bytes < STAGED_MIN || !staged_enabled() || is_pinned(src_host)) {
         RFB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, stream));
         return RFB_OK;
     }
@@ -138,7 +144,7 @@ int rfb_copy_h2d(rfb_ctx_t *ctx, void *dst_dev, const void *src_host, size_t byt
 
 // device -> pageable host: DMA into the pinned ring, copier threads move it out.  Returns with the data in place.
 int rfb_copy_d2h(rfb_ctx_t *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t stream) {
-    if (bytes < STAGED_MIN || is_pinned(dst_host)) {
+    if (bytes < STAGED_MIN || !staged_enabled() || is_pinned(dst_host)) {
         RFB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, stream));
         return RFB_OK;
     }

@@ -85,6 +85,7 @@ def test_fma_avg_1e9_closed_form(ctx):
     i = torch.arange(n, dtype=torch.int64, device="cuda")
     a, b, c = (i % 1024).double(), (i % 7).double(), (i % 13).double()
     del i
+    torch.cuda.synchronize()      # the inputs were produced on torch's stream; the context launches on its own
     got = ctx.fma_fold(capi.F_SUM | capi.F_CNT, a, b, c, n)
     period = 93184
     j = np.arange(period, dtype=np.int64)
