@@ -164,6 +164,12 @@ int rfb_fma_fold_dev(rfb_ctx_t *ctx, int folds, const double *a, const double *b
 int rfb_cmp_dev(rfb_ctx_t *ctx, int op, int xt, const void *x, int64_t xn, const rfb_scalar_t *xs, int yt,
                 const void *y, int64_t yn, const rfb_scalar_t *ys, uint8_t *mask);
 
+/* and / or / not on B8 masks: and_op_partial / or_op_partial (core/logic.c:34-86; the right side may be one broadcast byte:
+ * bn == -1, value bs) and ray_not (core/order.c:422-443; b ignored).  out may alias a (the reference updates in place). */
+enum { RFB_M_AND = 0, RFB_M_OR = 1, RFB_M_NOT = 2 };
+int rfb_mask_logic_dev(rfb_ctx_t *ctx, int op, const uint8_t *a, int64_t n, const uint8_t *b, int64_t bn, uint8_t bs,
+                       uint8_t *out);
+
 /* ray_where -> ops_where (core/ops.c:255-273): ascending row ids of the set bytes.  ids must have room for n.
  * *count (host) receives the number written. */
 int rfb_where_dev(rfb_ctx_t *ctx, const uint8_t *mask, int64_t n, int64_t *ids, int64_t *count);

@@ -19,6 +19,7 @@ ADD, SUB, MUL, DIV, FDIV, MOD = range(6)
 ROUND, FLOOR, CEIL = range(3)
 A_SUM, A_MIN, A_MAX, A_COUNT, A_AVG = range(5)
 INDEX_IDS, INDEX_SHIFT = 0, 1
+M_AND, M_OR, M_NOT = 0, 1, 2
 OK, ERR_TYPE, ERR_LENGTH, ERR_CUDA, ERR_ARG, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 
 NULL_I16 = -(2 ** 15)
@@ -107,6 +108,7 @@ SIGNATURES = {
     "rfb_filter_fold_dev": (_ci, [_vp, _ci, _ci, _vp, _P(Scalar), _ci, _ci, _vp, _i64, _P(Fold)]),
     "rfb_fma_fold_dev": (_ci, [_vp, _ci, _vp, _vp, _vp, _i64, _P(Fold)]),
     "rfb_cmp_dev": (_ci, [_vp, _ci, _ci, _vp, _i64, _P(Scalar), _ci, _vp, _i64, _P(Scalar), _vp]),
+    "rfb_mask_logic_dev": (_ci, [_vp, _ci, _vp, _i64, _vp, _i64, C.c_uint8, _vp]),
     "rfb_where_dev": (_ci, [_vp, _vp, _i64, _vp, _P(_i64)]),
     "rfb_cmp_where_dev": (_ci, [_vp, _ci, _ci, _vp, _i64, _P(Scalar), _vp, _P(_i64)]),
     "rfb_gather_dev": (_ci, [_vp, _ci, _vp, _vp, _i64, _vp]),

@@ -483,3 +483,34 @@ extern "C" int rfb_unop_f64_dev(rfb_ctx_t *ctx, int op, const double *x, int64_t
     RFB_CHECK_LAUNCH(ctx);
     return RFB_OK;
 }
+
+// ------------------------------------------------------------------ mask logic: and / or / not  
+
+namespace {
+struct MaskAnd { __device__ __forceinline__ u8 operator()(u8 a, u8 b) const { return (u8)((a != 0) & (b != 0)); } };
+struct MaskOr { __device__ __forceinline__ u8 operator()(u8 a, u8 b) const { return (u8)((a != 0) | (b != 0)); } };
+struct MaskNot { __device__ __forceinline__ u8 operator()(u8 a) const { return (u8)(a == 0); } };
+}  // namespace
+
+// and_op_partial / or_op_partial (reference core/logic.c:34-86): mask[i] = mask[i] && next[i]; the right side may be one
+// broadcast byte (bn == -1).  ray_not (core/order.c:422-443): out[i] = !x[i].
+extern "C" int rfb_mask_logic_dev(rfb_ctx_t *ctx, int op, const uint8_t *a, int64_t n, const uint8_t *b, int64_t bn, uint8_t bs,
+                                  uint8_t *out) {
+    RFB_ARG(ctx && n >= 0 && ((a && out) || n == 0), "rfb_mask_logic_dev");
+    if (n == 0) return RFB_OK;
+    if (op == RFB_M_NOT) {
+        const bool vec_ok = aligned16(a) && aligned16(out);
+        k_map1<u8, u8, MaskNot><<<rfb_grid_for(ctx, n, THREADS * 128, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(a, out, n, vec_ok, MaskNot());
+        RFB_CHECK_LAUNCH(ctx);
+        return RFB_OK;
+    }
+    if (op != RFB_M_AND && op != RFB_M_OR) { rfb_set_error("mask logic: unknown op %d", op); return RFB_ERR_ARG; }
+    if (bn >= 0 && bn != n) { rfb_set_error("mask logic: vector lengths differ"); return RFB_ERR_LENGTH; }
+    RFB_ARG(bn < 0 || b, "rfb_mask_logic_dev: right operand");
+    if (bn >= 0) {
+        if (op == RFB_M_AND) return launch_map2<u8, u8, u8, false, false>(ctx, a, (u8)0, b, (u8)0, out, n, MaskAnd());
+        return launch_map2<u8, u8, u8, false, false>(ctx, a, (u8)0, b, (u8)0, out, n, MaskOr());
+    }
+    if (op == RFB_M_AND) return launch_map2<u8, u8, u8, false, true>(ctx, a, (u8)0, nullptr, bs, out, n, MaskAnd());
+    return launch_map2<u8, u8, u8, false, true>(ctx, a, (u8)0, nullptr, bs, out, n, MaskOr());
+}

@@ -193,6 +193,17 @@ class _Ops:
         self.sync()   # the context's stream is non-blocking: make the result visible to torch's streams
         return mask
 
+    def mask_logic(self, op, a, b=None):
+        """and / or (b: mask tensor or a Python bool broadcast) / not on B8 masks"""
+        import torch
+        out = self._empty(a.shape[0], capi.B8)
+        if isinstance(b, torch.Tensor):
+            check(self.lib.rfb_mask_logic_dev(self.h, op, _dptr(a), a.shape[0], _dptr(b), b.shape[0], 0, _dptr(out)))
+        else:
+            check(self.lib.rfb_mask_logic_dev(self.h, op, _dptr(a), a.shape[0], None, -1, int(bool(b)), _dptr(out)))
+        self.sync()
+        return out
+
     def where(self, mask):
         """ray_where: B8 mask -> ascending i64 row ids"""
         n = mask.shape[0]

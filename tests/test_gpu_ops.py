@@ -88,6 +88,26 @@ def test_cmp_length_mismatch_and_unaligned(ctx, oracle):
     assert np.array_equal(host(ctx.cmp(ob.GE, ob.I64, d[1:], ob.I64, 0)), oracle.cmp(ob.GE, ob.I64, x[1:], ob.I64, 0))
 
 
+@pytest.mark.parametrize("n", [1, 17, 25001, 1_000_003])
+def test_mask_logic_and_or_not(ctx, n):
+    """and / or / not on masks (reference core/logic.c:34-86, core/order.c:422-443; golden shape tests/lang.c:2893-2897:
+    a 25001-row `and` filter); any non-zero byte is true, results are 0/1"""
+    r = np.random.default_rng(n)
+    a = (r.random(n) < 0.5).astype(np.uint8) * r.integers(1, 255, n, dtype=np.uint8)
+    b = (r.random(n) < 0.3).astype(np.uint8)
+    da, db = dev(a), dev(b)
+    assert np.array_equal(host(ctx.mask_logic(capi.M_AND, da, db)), ((a != 0) & (b != 0)).astype(np.uint8))
+    assert np.array_equal(host(ctx.mask_logic(capi.M_OR, da, db)), ((a != 0) | (b != 0)).astype(np.uint8))
+    assert np.array_equal(host(ctx.mask_logic(capi.M_NOT, da)), (a == 0).astype(np.uint8))
+    assert np.array_equal(host(ctx.mask_logic(capi.M_AND, da, True)), (a != 0).astype(np.uint8))
+    assert np.array_equal(host(ctx.mask_logic(capi.M_OR, da, False)), (a != 0).astype(np.uint8))
+    assert not host(ctx.mask_logic(capi.M_AND, da, False)).any()
+    if n > 20:
+        with pytest.raises(capi.RfbError) as e:
+            ctx.mask_logic(capi.M_AND, da, db[1:])
+        assert e.value.kind == "length"
+
+
 # ---------------------------------------------------------------- where / gather
 
 @pytest.mark.parametrize("n", [1, 15, 16, 16383, 16384, 16385, 1_000_003])
