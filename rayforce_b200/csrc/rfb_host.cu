@@ -9,6 +9,7 @@
 // Pinned (cudaHostAlloc / rfb_host_pin) payloads are DMA'd directly; pageable payloads still work (the driver stages
 // them) but at a fraction of the PCIe rate — INTEGRATION.md tells the reference side to pin its column blocks.
 #include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <unistd.h>
 
@@ -43,6 +44,15 @@ void *copy_worker(void *a) {
     CopyPool *p = wa->p;
     const int id = wa->id;
     free(wa);
+    // A host that pins its calling thread to one core (the reference pins every executor, core/pool.c:168-219) hands that
+    // one-core affinity to the threads it creates: undo it, or all copiers would share a single core.
+    {
+        cpu_set_t all;
+        CPU_ZERO(&all);
+        const long cores = sysconf(_SC_NPROCESSORS_CONF);
+        for (long c = 0; c < cores && c < CPU_SETSIZE; c++) CPU_SET((int)c, &all);
+        pthread_setaffinity_np(pthread_self(), sizeof(all), &all);
+    }
     unsigned long seen = 0;
     for (;;) {
         pthread_mutex_lock(&p->mu);
