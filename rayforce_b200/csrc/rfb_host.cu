@@ -11,7 +11,6 @@
 #include <pthread.h>
 #include <sched.h>
 #include <stdlib.h>
-#include <sys/mman.h>
 #include <unistd.h>
 
 #include "rfb_common.cuh"
@@ -162,12 +161,6 @@ int rfb_copy_d2h(rfb_ctx_t *ctx, void *dst_host, const void *src_dev, size_t byt
     int rc = ensure_ring(ctx);
     if (rc) return rc;
     CopyPool *pool = pool_of(ctx);
-    // results usually land in freshly mapped host blocks: ask for huge pages before the first touch so that filling them
-    // costs one fault per 2 MiB instead of one per 4 KiB (a hint; ignored where THP is off)
-    {
-        const uintptr_t lo = ((uintptr_t)dst_host + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1), hi = ((uintptr_t)dst_host + bytes) & ~(uintptr_t)((2u << 20) - 1);
-        if (hi > lo) madvise((void *)lo, hi - lo, MADV_HUGEPAGE);
-    }
     const size_t nchunks = (bytes + RFB_HOST_RING_BYTES - 1) / RFB_HOST_RING_BYTES;
     // software pipeline: chunk c's DMA is in flight while chunk c-1 is copied out of its pinned buffer
     for (size_t c = 0; c <= nchunks; c++) {

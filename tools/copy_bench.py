@@ -28,14 +28,3 @@ for kind in ("pageable", "pinned"):
         t2 = time.perf_counter()
         print("%-9s rep %d  h2d %6.1f GB/s   d2h %6.1f GB/s (first rep touches the destination pages)" % (kind, rep, n * 8 / (t1 - t0) / 1e9, n * 8 / (t2 - t1) / 1e9), flush=True)
     assert bool((out == 3).all())
-# fresh destination every time (what an operator result looks like): first-touch cost included
-import mmap
-for rep in range(3):
-    m = mmap.mmap(-1, n * 8)
-    addr = C.addressof(C.c_char.from_buffer(m))
-    t0 = time.perf_counter()
-    capi.check(ctx.lib.rfb_d2h(ctx.h, C.c_void_p(addr), C.c_void_p(dev.data_ptr()), n * 8))
-    ctx.sync()
-    t1 = time.perf_counter()
-    print("fresh mmap destination rep %d  d2h %6.1f GB/s" % (rep, n * 8 / (t1 - t0) / 1e9), flush=True)
-print(open("/sys/kernel/mm/transparent_hugepage/enabled").read().strip())
