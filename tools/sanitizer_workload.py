@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""One small invocation of every kernel family (for compute-sanitizer memcheck / racecheck / synccheck runs)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from rayforce_b200 import Context, capi  # noqa: E402
+
+ctx = Context(0)
+r = np.random.default_rng(1)
+n = 70_003
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+x = dev(r.integers(-1000, 1000, n).astype(np.int64))
+y = dev(r.integers(-1000, 1000, n).astype(np.int64))
+f = dev(r.uniform(-1, 1, n))
+k = dev(r.integers(0, 500, n).astype(np.int64))
+kw = dev(r.integers(-(1 << 60), 1 << 60, n).astype(np.int64))
+k32 = dev(r.integers(0, 5000, n).astype(np.int32))
+ctx.fold(capi.F_ALL, capi.I64, x, n)
+ctx.fold(capi.F_SUM | capi.F_CNT, capi.F64, f, n)
+ctx.filter_fold(capi.LT, capi.I64, x, 10, capi.F_SUM | capi.F_CNT, capi.I64, x, n)
+ctx.filter_fold(capi.GE, capi.I64, x, 10, capi.F_ALL, capi.F64, f, n)
+ctx.fma_fold(capi.F_ALL, f, f, f, n)
+m = ctx.cmp(capi.LT, capi.I64, x, capi.I64, y)
+ids = ctx.where(m)
+ctx.mask_logic(capi.M_AND, m, m)
+ids2 = ctx.cmp_where(capi.GT, capi.I64, x, 0)
+ctx.gather(capi.I64, x, ids)
+ctx.gather_fold(capi.F_ALL, capi.I64, x, ids2, ids2.shape[0])
+ctx.binop(capi.DIV, capi.I64, x, capi.I64, y)
+ctx.binop(capi.FDIV, capi.F64, f, capi.I64, 3)
+ctx.unop_f64(capi.FLOOR, f)
+for keys in (k, kw):
+    g, fi, info = ctx.group_i64(keys)
+    for op in (capi.A_SUM, capi.A_MIN, capi.A_MAX, capi.A_COUNT, capi.A_AVG):
+        ctx.aggr(op, capi.I64, x, g, info.groups)
+    ctx.aggr(capi.A_SUM, capi.F64, f, g, info.groups)
+ctx.group_keys([k, k])
+ctx.group_sum_count(capi.I32, k32, x, 5000)
+ctx.group_sum_count(capi.I64, k, x, 500, capi.LT, capi.I64, x, 100)
+ctx.sort(capi.I64, x)
+ctx.sort(capi.F64, f, True)
+h = r.integers(-1000, 1000, 2_000_000).astype(np.int64)
+ctx.filter_fold_host(capi.LT, capi.I64, h, 10, capi.F_ALL, capi.I64, h, chunk_rows=300_000)
+ctx.sync()
+print("sanitizer workload done, launches:", ctx.launches)
