@@ -5,10 +5,10 @@
 //   rfb_cmp_where_dev   ray_where(ray_<cmp>(x, k)) without ever writing the mask
 //   rfb_gather_dev      filter_collect -> at_ids: out[i] = col[ids[i]]              (core/rayforce.c:1036-1159)
 //
-// Compaction is ONE pass: a chained scan with decoupled look-back.  Tiles take their index from an atomic ticket (so a
-// tile only ever waits on tiles that already started), each CTA counts its selected rows with warp ballots, publishes
-// (AGGREGATE | count) in a 64-bit status word, walks back over its predecessors' words 32 at a time until it meets an
-// INCLUSIVE one, publishes its own inclusive prefix and then writes its row ids at that offset.  Order is preserved:
+// Compaction is ONE pass: a chained scan with decoupled look-back (rfb_scan.cuh).  Each CTA counts its selected rows with
+// warp ballots, publishes (AGGREGATE | count) in a 64-bit status word, walks back over its predecessors' words 32 at a
+// time until it meets an INCLUSIVE one, publishes its own inclusive prefix and then writes its row ids at that offset.
+// Tiles are 16 K rows so that one look-back (a CTA barrier around a chain of L2 round trips) is amortised.  Order is preserved:
 // within a warp the rank of a row is a popcount over the ballot masks of lower rows.  Traffic: mask bytes (or the 8-byte
 // predicate column) read once + 8 bytes written per selected row.
 #include "rfb_scan.cuh"
@@ -85,68 +85,80 @@ k_where_mask(const u8 *__restrict__ mask, i64 n, i64 *__restrict__ ids, TileCtl 
     }
 }
 
-// ---- predicate on a typed column -> ids.  Lane owns R = 16/sizeof(P) consecutive rows per step.
-constexpr int CMP_THREADS = 512;
-constexpr int CMP_WARPS = CMP_THREADS / 32;
+// ---- predicate on a typed column -> ids.  Lane owns R = 16/sizeof(P) consecutive rows per step; a warp walks SUB
+// sub-tiles of J steps each, keeping only the selection bits (J*R per sub-tile), so one look-back serves 16 K rows.
+// The store phase recomputes the in-warp ranks from the same ballots instead of keeping them in registers.
 template <typename P> struct CmpTile {
     static constexpr int R = 16 / (int)sizeof(P);
-    static constexpr int J = 8;
-    static constexpr int WROWS = 32 * R * J;
-    static constexpr int TILE = CMP_WARPS * WROWS;
+    static constexpr int J = (R <= 4) ? 8 : 32 / R;          // J*R <= 32 selection bits per sub-tile
+    static constexpr int SUB = 4;
+    static constexpr int SROWS = 32 * R * J;                 // rows per warp per sub-tile
+    static constexpr int WROWS = SROWS * SUB;
+    static constexpr int TILE = WARPS * WROWS;
 };
 
 template <typename P>
-__global__ void __launch_bounds__(CMP_THREADS, 2)
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
 k_where_cmp(const P *__restrict__ x, PredRange pr, i64 n, bool vec_ok, i64 *__restrict__ ids, TileCtl ctl) {
-    constexpr int R = CmpTile<P>::R, J = CmpTile<P>::J;
-    __shared__ scan::TileSmemT<CMP_WARPS> sm;
+    constexpr int R = CmpTile<P>::R, J = CmpTile<P>::J, SUB = CmpTile<P>::SUB;
+    __shared__ TileSmem sm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 tile = blockIdx.x;
+    const u32 lt = (1u << lane) - 1u;
     const i64 wbase = (i64)tile * CmpTile<P>::TILE + (i64)warp * CmpTile<P>::WROWS;
-    Vec16<P> v[J];
-    const bool full = vec_ok && wbase + CmpTile<P>::WROWS <= n;
-    if (full) {
+    __shared__ u32 bits[SUB][THREADS];   // bit (j*R + e) = row (sub, j, lane, e) selected; thread-private column
+    u32 warp_total = 0;
+#pragma unroll 1
+    for (int s = 0; s < SUB; s++) {
+        const i64 sbase = wbase + (i64)s * CmpTile<P>::SROWS;
+        Vec16<P> v[J];
+        const bool full = vec_ok && sbase + CmpTile<P>::SROWS <= n;
+        if (full) {
 #pragma unroll
-        for (int j = 0; j < J; j++) v[j].raw = ld_stream16(x + wbase + ((i64)j * 32 + lane) * R);
-    } else {
+            for (int j = 0; j < J; j++) v[j].raw = ld_stream16(x + sbase + ((i64)j * 32 + lane) * R);
+        } else {
+#pragma unroll
+            for (int j = 0; j < J; j++)
+#pragma unroll
+                for (int e = 0; e < R; e++) {
+                    const i64 r = sbase + ((i64)j * 32 + lane) * R + e;
+                    v[j].e[e] = r < n ? x[r] : P();
+                }
+        }
+        u32 b = 0;
 #pragma unroll
         for (int j = 0; j < J; j++)
 #pragma unroll
             for (int e = 0; e < R; e++) {
-                const i64 r = wbase + ((i64)j * 32 + lane) * R + e;
-                v[j].e[e] = r < n ? x[r] : P();
+                const i64 r = sbase + ((i64)j * 32 + lane) * R + e;
+                const bool sel = (full || r < n) && pred_test(pred_key<P>(v[j].e[e]), pr);
+                b |= (sel ? 1u : 0u) << (j * R + e);
             }
+        bits[s][threadIdx.x] = b;
+        warp_total += __reduce_add_sync(0xffffffffu, (u32)__popc(b));
     }
-    u32 bits[J], excl[J], warp_total = 0;
+    u64 obase = scan::tile_offsets<WARPS>(ctl, tile, warp_total, sm);
+#pragma unroll 1
+    for (int s = 0; s < SUB; s++) {
+        const i64 sbase = wbase + (i64)s * CmpTile<P>::SROWS;
+        const u32 mybits = bits[s][threadIdx.x];
 #pragma unroll
-    for (int j = 0; j < J; j++) {
-        u32 b = 0;
+        for (int j = 0; j < J; j++) {
+            // rows of step j in row order: lane-major, element-minor -> rank = selected elements of lower lanes + own lower ones
+            u32 before = 0, tot = 0;
 #pragma unroll
-        for (int e = 0; e < R; e++) {
-            const i64 r = wbase + ((i64)j * 32 + lane) * R + e;
-            const bool sel = (full || r < n) && pred_test(pred_key<P>(v[j].e[e]), pr);
-            b |= (sel ? 1u : 0u) << e;
+            for (int e = 0; e < R; e++) {
+                const u32 m = __ballot_sync(0xffffffffu, (mybits >> (j * R + e)) & 1u);
+                before += __popc(m & lt);
+                tot += __popc(m);
+            }
+            i64 *o = ids + obase + before;
+            const i64 r0 = sbase + ((i64)j * 32 + lane) * R;
+#pragma unroll
+            for (int e = 0; e < R; e++)
+                if ((mybits >> (j * R + e)) & 1u) *o++ = r0 + e;
+            obase += tot;
         }
-        bits[j] = b;
-        // rank of this lane's first row: selected rows in lower lanes (any element), via one ballot per element
-        u32 before = 0, tot = 0;
-#pragma unroll
-        for (int e = 0; e < R; e++) {
-            const u32 m = __ballot_sync(0xffffffffu, (b >> e) & 1u);
-            before += __popc(m & ((1u << lane) - 1u));
-            tot += __popc(m);
-        }
-        excl[j] = warp_total + before;
-        warp_total += tot;
-    }
-    const u64 obase = scan::tile_offsets<CMP_WARPS>(ctl, tile, warp_total, sm);
-#pragma unroll
-    for (int j = 0; j < J; j++) {
-        const i64 r0 = wbase + ((i64)j * 32 + lane) * R;
-        i64 *o = ids + obase + excl[j];
-#pragma unroll
-        for (int e = 0; e < R; e++)
-            if ((bits[j] >> e) & 1u) *o++ = r0 + e;
     }
 }
 
@@ -169,7 +181,7 @@ int where_cmp_t(rfb_ctx_t *ctx, const void *x, PredRange pr, i64 n, i64 *ids) {
     TileCtl ctl;
     int rc = prepare_tiles(ctx, tiles, &ctl);
     if (rc) return rc;
-    k_where_cmp<P><<<(unsigned)tiles, CMP_THREADS, 0, ctx->stream>>>((const P *)x, pr, n, aligned16(x), ids, ctl);
+    k_where_cmp<P><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>((const P *)x, pr, n, aligned16(x), ids, ctl);
     RFB_CHECK_LAUNCH(ctx);
     return RFB_OK;
 }
@@ -220,7 +232,7 @@ extern "C" int rfb_where_dev(rfb_ctx_t *ctx, const uint8_t *mask, int64_t n, int
         const i64 tiles = (n + CmpTile<u8>::TILE - 1) / CmpTile<u8>::TILE;
         int rc = prepare_tiles(ctx, tiles, &ctl);
         if (rc) return rc;
-        k_where_cmp<u8><<<(unsigned)tiles, CMP_THREADS, 0, ctx->stream>>>(mask, pr, n, false, ids, ctl);
+        k_where_cmp<u8><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(mask, pr, n, false, ids, ctl);
         RFB_CHECK_LAUNCH(ctx);
     }
     return finish_count(ctx, count);
