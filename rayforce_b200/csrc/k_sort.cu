@@ -10,9 +10,10 @@
 //
 // Per pass:  HIST    G persistent CTAs, CTA b owns the contiguous chunk b of the current sequence: 256-bin counts
 //            SCAN    exclusive scan of the digit-major (256 x G) count matrix  -> first output slot of (digit, chunk)
-//            SCATTER CTA b walks its chunk tile by tile (2048 rows): warp-level multisplit (match.any) ranks rows of equal
-//                    digit in (warp, step, lane) order, warp counts are scanned across the CTA, and a running per-digit
-//                    base carried in shared memory keeps tiles of one chunk in order => stable.
+//            SCATTER CTA b walks its chunk tile by tile (3072 rows): warp-level multisplit (match.any) ranks rows of equal
+//                    digit in (warp, step, lane) order, warp counts are scanned across the CTA, the tile is ordered by
+//                    digit in shared memory and leaves as one contiguous run per digit; a running per-digit base carried
+//                    in shared memory keeps tiles of one chunk in order => stable.
 // One census kernel up front takes the bitwise OR and AND of all keys; a pass whose digit is constant over the column is skipped
 // (e.g. the upper bytes of small integers).  The first executed pass reads the typed column and synthesises the row ids;
 // the last one writes only the permutation.  HBM traffic per executed pass: 8N (hist) + 16N read + 16N written.
@@ -22,8 +23,8 @@ namespace {
 
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
-constexpr int ITEMS = 8;
-constexpr int TILE = THREADS * ITEMS;  // 2048
+constexpr int ITEMS = 12;
+constexpr int TILE = THREADS * ITEMS;  // 3072 rows: 48 KB of staged (key, row id) pairs per CTA
 constexpr int RADIX = 256;
 
 template <typename T> __device__ __forceinline__ u64 sortable(T v);
@@ -122,14 +123,20 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const u32 *bh, i64 *offs, 
     }
 }
 
-// ---- stable scatter of one chunk
+// ---- stable scatter of one chunk.  Each tile is first ordered by digit in shared memory (stable: rank = rows of the same
+// digit in lower warps + lower steps/lanes of the own warp), then streamed out so that the rows of one digit leave as one
+// contiguous run — direct per-lane stores hit up to 32 different sectors per instruction.
 template <typename Src, bool WRITE_KEYS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 3)
 k_scatter(Src src, i64 n, i64 chunk, int shift, const i64 *__restrict__ offs /* [256][G] */, u64 *__restrict__ keys_out,
           i64 *__restrict__ vals_out) {
     __shared__ u32 whist[WARPS][RADIX];
-    __shared__ i64 base[RADIX];    // next free output slot of each digit for this chunk
-    __shared__ i64 tbase[RADIX];   // ... at the start of the current tile
+    __shared__ i64 base[RADIX];     // next free output slot of each digit for this chunk
+    __shared__ u32 dstart[RADIX];   // tile-local position of the first row of each digit
+    __shared__ u32 wsum[WARPS];
+    extern __shared__ u64 stage_dyn[];            // TILE keys then TILE row ids (48 KB: above the static limit)
+    u64 *skeys = stage_dyn;
+    i64 *svals = (i64 *)(stage_dyn + TILE);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 lt = (1u << lane) - 1u;
     base[threadIdx.x] = offs[(i64)threadIdx.x * gridDim.x + blockIdx.x];
@@ -139,15 +146,12 @@ k_scatter(Src src, i64 n, i64 chunk, int shift, const i64 *__restrict__ offs /* 
         for (int w = 0; w < WARPS; w++) whist[w][threadIdx.x] = 0;
         __syncthreads();
         u64 key[ITEMS];
-        i64 val[ITEMS];
         u32 rank[ITEMS];
         const i64 wb = t0 + (i64)warp * (32 * ITEMS);
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
             const i64 i = wb + j * 32 + lane;
-            const bool ok = i < hi;
-            key[j] = ok ? src.key(i) : ~0ULL;
-            val[j] = ok ? src.val(i) : 0;
+            key[j] = i < hi ? src.key(i) : ~0ULL;
         }
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
@@ -163,14 +167,25 @@ k_scatter(Src src, i64 n, i64 chunk, int shift, const i64 *__restrict__ offs /* 
             rank[j] = prior + __popc(peers & lt);
         }
         __syncthreads();
-        {   // thread d: scan digit d's counts over the warps, advance the running base
+        u32 cnt;
+        {   // thread d: digit d's counts over the warps -> exclusive warp offsets; then the tile-local start of each digit
             const int d = threadIdx.x;
-            u32 s = 0;
+            u32 sum = 0;
 #pragma unroll
-            for (int w = 0; w < WARPS; w++) { const u32 c = whist[w][d]; whist[w][d] = s; s += c; }
-            const i64 b = base[d];
-            tbase[d] = b;
-            base[d] = b + s;
+            for (int w = 0; w < WARPS; w++) { const u32 c = whist[w][d]; whist[w][d] = sum; sum += c; }
+            cnt = sum;
+            u32 incl = cnt;
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) {
+                const u32 o = __shfl_up_sync(0xffffffffu, incl, k);
+                if (lane >= k) incl += o;
+            }
+            if (lane == 31) wsum[warp] = incl;
+            __syncthreads();
+            u32 woff = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) woff += (w < warp) ? wsum[w] : 0u;
+            dstart[d] = woff + incl - cnt;
         }
         __syncthreads();
 #pragma unroll
@@ -178,12 +193,22 @@ k_scatter(Src src, i64 n, i64 chunk, int shift, const i64 *__restrict__ offs /* 
             const i64 i = wb + j * 32 + lane;
             if (i < hi) {
                 const u32 d = (u32)(key[j] >> shift) & 255u;
-                const i64 pos = tbase[d] + whist[warp][d] + rank[j];
-                if (WRITE_KEYS) keys_out[pos] = key[j];
-                vals_out[pos] = val[j];
+                const u32 lp = dstart[d] + whist[warp][d] + rank[j];
+                skeys[lp] = key[j];
+                svals[lp] = src.val(i);
             }
         }
         __syncthreads();
+        const int tile_n = (int)((hi - t0) < TILE ? (hi - t0) : TILE);
+        for (int i = threadIdx.x; i < tile_n; i += THREADS) {
+            const u64 k = skeys[i];
+            const u32 d = (u32)(k >> shift) & 255u;
+            const i64 pos = base[d] + (i64)(i - (int)dstart[d]);
+            if (WRITE_KEYS) keys_out[pos] = k;
+            vals_out[pos] = svals[i];
+        }
+        __syncthreads();
+        base[threadIdx.x] += cnt;
     }
 }
 
@@ -199,8 +224,15 @@ int run_pass(rfb_ctx_t *ctx, Src src, i64 n, int G, i64 chunk, int shift, u32 *b
     RFB_CHECK_LAUNCH(ctx);
     k_scan_counts<<<1, 1024, 0, ctx->stream>>>(bh, offs, RADIX * G);
     RFB_CHECK_LAUNCH(ctx);
-    if (last) k_scatter<Src, false><<<G, THREADS, 0, ctx->stream>>>(src, n, chunk, shift, offs, keys_out, vals_out);
-    else k_scatter<Src, true><<<G, THREADS, 0, ctx->stream>>>(src, n, chunk, shift, offs, keys_out, vals_out);
+    constexpr int STAGE_BYTES = TILE * 16;
+    static bool opted_in = false;   // per template instantiation
+    if (!opted_in) {
+        RFB_CUDA(cudaFuncSetAttribute(k_scatter<Src, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
+        RFB_CUDA(cudaFuncSetAttribute(k_scatter<Src, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
+        opted_in = true;
+    }
+    if (last) k_scatter<Src, false><<<G, THREADS, STAGE_BYTES, ctx->stream>>>(src, n, chunk, shift, offs, keys_out, vals_out);
+    else k_scatter<Src, true><<<G, THREADS, STAGE_BYTES, ctx->stream>>>(src, n, chunk, shift, offs, keys_out, vals_out);
     RFB_CHECK_LAUNCH(ctx);
     return RFB_OK;
 }
