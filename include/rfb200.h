@@ -53,8 +53,8 @@ enum { RFB_EQ = 0, RFB_NE = 1, RFB_LT = 2, RFB_GT = 3, RFB_LE = 4, RFB_GE = 5 };
 /* which folds a reduction kernel computes (bit set).  ray_sum/min/max/cnt (core/math.c:1785-2045) */
 enum { RFB_F_SUM = 1, RFB_F_CNT = 2, RFB_F_MIN = 4, RFB_F_MAX = 8, RFB_F_ROWS = 16, RFB_F_ALL = 31 };
 
-/* element-wise arithmetic: ray_add/sub/mul/div/fdiv/mod (core/math.c:2436-2441) */
-enum { RFB_ADD = 0, RFB_SUB = 1, RFB_MUL = 2, RFB_DIV = 3, RFB_FDIV = 4, RFB_MOD = 5 };
+/* element-wise arithmetic: ray_add/sub/mul/div/fdiv/mod/xbar (core/math.c:2436-2442) */
+enum { RFB_ADD = 0, RFB_SUB = 1, RFB_MUL = 2, RFB_DIV = 3, RFB_FDIV = 4, RFB_MOD = 5, RFB_XBAR = 6 };
 enum { RFB_ROUND = 0, RFB_FLOOR = 1, RFB_CEIL = 2 };
 
 /* grouped aggregates: aggr_sum/min/max/count/avg (core/aggr.c:1078-1453, 2013-2133) */

@@ -105,13 +105,14 @@ rfb_obj_p rfb_ray_max(rfb_obj_p x);
 rfb_obj_p rfb_ray_avg(rfb_obj_p x);
 rfb_obj_p rfb_ray_cnt(rfb_obj_p x);
 
-/* ---- element-wise: ray_add/sub/mul/div/fdiv/mod (core/math.c:2436-2441), ray_round/floor/ceil (:2430-2432) */
+/* ---- element-wise: ray_add/sub/mul/div/fdiv/mod/xbar (core/math.c:2436-2442), ray_round/floor/ceil (:2430-2432) */
 rfb_obj_p rfb_ray_add(rfb_obj_p x, rfb_obj_p y);
 rfb_obj_p rfb_ray_sub(rfb_obj_p x, rfb_obj_p y);
 rfb_obj_p rfb_ray_mul(rfb_obj_p x, rfb_obj_p y);
 rfb_obj_p rfb_ray_div(rfb_obj_p x, rfb_obj_p y);
 rfb_obj_p rfb_ray_fdiv(rfb_obj_p x, rfb_obj_p y);
 rfb_obj_p rfb_ray_mod(rfb_obj_p x, rfb_obj_p y);
+rfb_obj_p rfb_ray_xbar(rfb_obj_p x, rfb_obj_p y);
 rfb_obj_p rfb_ray_round(rfb_obj_p x);
 rfb_obj_p rfb_ray_floor(rfb_obj_p x);
 rfb_obj_p rfb_ray_ceil(rfb_obj_p x);

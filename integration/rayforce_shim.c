@@ -42,10 +42,10 @@ static pthread_t owner;
 static int want_stats = 0;
 
 enum { S_EQ, S_NE, S_LT, S_GT, S_LE, S_GE, S_WHERE, S_COLLECT, S_SUM, S_MIN, S_MAX, S_AVG, S_ADD, S_SUB, S_MUL, S_DIV, S_FDIV,
-       S_MOD, S_ROUND, S_FLOOR, S_CEIL, S_INDEX_GROUP, S_AGGR_SUM, S_AGGR_MIN, S_AGGR_MAX, S_AGGR_COUNT, S_AGGR_AVG, S_SORT_ASC,
+       S_MOD, S_XBAR, S_ROUND, S_FLOOR, S_CEIL, S_INDEX_GROUP, S_AGGR_SUM, S_AGGR_MIN, S_AGGR_MAX, S_AGGR_COUNT, S_AGGR_AVG, S_SORT_ASC,
        S_SORT_DESC, S_SELECT, S_N };
 static const char *S_NAME[S_N] = {"ray_eq", "ray_ne", "ray_lt", "ray_gt", "ray_le", "ray_ge", "ray_where", "filter_collect", "ray_sum",
-                                  "ray_min", "ray_max", "ray_avg", "ray_add", "ray_sub", "ray_mul", "ray_div", "ray_fdiv", "ray_mod",
+                                  "ray_min", "ray_max", "ray_avg", "ray_add", "ray_sub", "ray_mul", "ray_div", "ray_fdiv", "ray_mod", "ray_xbar",
                                   "ray_round", "ray_floor", "ray_ceil", "index_group", "aggr_sum", "aggr_min", "aggr_max", "aggr_count",
                                   "aggr_avg", "ray_sort_asc", "ray_sort_desc", "ray_select"};
 static long n_gpu[S_N], n_cpu[S_N];
@@ -102,7 +102,7 @@ static int gpu_ok(void) {
 WRAP2(ray_eq, S_EQ) WRAP2(ray_ne, S_NE) WRAP2(ray_lt, S_LT) WRAP2(ray_gt, S_GT) WRAP2(ray_le, S_LE) WRAP2(ray_ge, S_GE)
 WRAP1(ray_where, S_WHERE) WRAP2(filter_collect, S_COLLECT)
 WRAP1(ray_sum, S_SUM) WRAP1(ray_min, S_MIN) WRAP1(ray_max, S_MAX) WRAP1(ray_avg, S_AVG)
-WRAP2(ray_add, S_ADD) WRAP2(ray_sub, S_SUB) WRAP2(ray_mul, S_MUL) WRAP2(ray_div, S_DIV) WRAP2(ray_fdiv, S_FDIV) WRAP2(ray_mod, S_MOD)
+WRAP2(ray_add, S_ADD) WRAP2(ray_sub, S_SUB) WRAP2(ray_mul, S_MUL) WRAP2(ray_div, S_DIV) WRAP2(ray_fdiv, S_FDIV) WRAP2(ray_mod, S_MOD) WRAP2(ray_xbar, S_XBAR)
 WRAP1(ray_round, S_ROUND) WRAP1(ray_floor, S_FLOOR) WRAP1(ray_ceil, S_CEIL)
 WRAP2(index_group, S_INDEX_GROUP)
 WRAP2(aggr_sum, S_AGGR_SUM) WRAP2(aggr_min, S_AGGR_MIN) WRAP2(aggr_max, S_AGGR_MAX) WRAP2(aggr_count, S_AGGR_COUNT) WRAP2(aggr_avg, S_AGGR_AVG)

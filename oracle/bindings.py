@@ -23,7 +23,7 @@ REF_BIN = os.path.join(HERE, "_ref", "rayforce_ref")
 B8, U8, I16, I32, I64, SYMBOL, DATE, TIME, TIMESTAMP, F64 = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 EQ, NE, LT, GT, LE, GE = range(6)
 SUM, MIN, MAX, CNT, AVG, COUNT = range(6)
-ADD, SUB, MUL, DIV, FDIV, MOD = range(6)
+ADD, SUB, MUL, DIV, FDIV, MOD, XBAR = range(7)
 ROUND, FLOOR, CEIL = range(3)
 ATOM = -1
 NULL_I16 = -(2 ** 15)
@@ -262,7 +262,7 @@ class Reference:
             f.restype = vp
             f.argtypes = [vp]
         for name in ("ray_eq", "ray_ne", "ray_lt", "ray_gt", "ray_le", "ray_ge", "ray_add", "ray_sub", "ray_mul",
-                     "ray_div", "ray_fdiv", "ray_mod", "filter_map", "filter_collect", "index_group", "group_map",
+                     "ray_div", "ray_fdiv", "ray_mod", "ray_xbar", "filter_map", "filter_collect", "index_group", "group_map",
                      "aggr_sum", "aggr_min", "aggr_max", "aggr_count", "aggr_avg", "aggr_first"):
             f = getattr(L, name)
             f.restype = vp
@@ -352,7 +352,7 @@ class Reference:
 
     # ---- numpy-level conveniences mirroring Oracle's API
     _CMP = ["ray_eq", "ray_ne", "ray_lt", "ray_gt", "ray_le", "ray_ge"]
-    _BIN = ["ray_add", "ray_sub", "ray_mul", "ray_div", "ray_fdiv", "ray_mod"]
+    _BIN = ["ray_add", "ray_sub", "ray_mul", "ray_div", "ray_fdiv", "ray_mod", "ray_xbar"]
     _FOLD = ["ray_sum", "ray_min", "ray_max", "ray_cnt", "ray_avg", "ray_count"]
     _AGGR = ["aggr_sum", "aggr_min", "aggr_max", None, "aggr_avg", "aggr_count"]
 

@@ -310,6 +310,7 @@ static int binop_types(int op, int xt, int yt, int *mt, int *ot) {
     int wide = anyf ? RFO_F64 : any64 ? RFO_I64 : RFO_I32; /* usual promotion */
     switch (op) {
         case RFO_ADD: case RFO_SUB: case RFO_MUL: *mt = wide; *ot = wide; return 1;
+        case RFO_XBAR: *mt = wide; *ot = wide; return 1; /* infer_xbar_type core/math.c:225-249, matrix :1637-1700 */
         case RFO_DIV: /* result keeps the LEFT operand's type (infer_div_type), computed in the promoted type */
             *mt = wide; *ot = xt; return 1;
         case RFO_FDIV: *mt = RFO_F64; *ot = RFO_F64; return 1;
@@ -329,6 +330,11 @@ static inline i32 op_i32(int op, i32 x, i32 y) {
     switch (op) {
         case RFO_ADD: return wadd32(x, y); case RFO_SUB: return wsub32(x, y); case RFO_MUL: return wmul32(x, y);
         case RFO_DIV: return y == 0 ? RFO_NULL_I32 : eucl_div32(x, y);
+        case RFO_XBAR: { /* XBARI32 core/ops.h:193-194 */
+            if (y == 0) return RFO_NULL_I32;
+            i32 t = x < 0 ? wsub32(wadd32(x, 1), y) : x;
+            return wmul32(y == -1 ? (i32)(0 - (uint32_t)t) : t / y, y);
+        }
         default: return y == 0 ? RFO_NULL_I32 : eucl_mod32(x, y);
     }
 }
@@ -337,6 +343,11 @@ static inline i64 op_i64(int op, i64 x, i64 y) {
     switch (op) {
         case RFO_ADD: return wadd64(x, y); case RFO_SUB: return wsub64(x, y); case RFO_MUL: return wmul64(x, y);
         case RFO_DIV: return y == 0 ? RFO_NULL_I64 : eucl_div64(x, y);
+        case RFO_XBAR: { /* XBARI64 core/ops.h:195-196 */
+            if (y == 0) return RFO_NULL_I64;
+            i64 t = x < 0 ? wsub64(wadd64(x, 1), y) : x;
+            return wmul64(y == -1 ? (i64)(0 - (u64)t) : t / y, y);
+        }
         default: return y == 0 ? RFO_NULL_I64 : eucl_mod64(x, y);
     }
 }
@@ -345,6 +356,13 @@ static inline f64 op_f64(int op, f64 x, f64 y) {
     switch (op) {
         case RFO_ADD: return x + y; case RFO_SUB: return x - y; case RFO_MUL: return x * y;
         case RFO_DIV: return y == 0.0 ? null_f64() : floor(x / y);                  /* DIVF64 / FEUCL_DIV */
+        case RFO_XBAR: { /* XBARF64 = FLOORF64(x / y) * y, core/ops.h:197,191 */
+            if (y == 0.0) return null_f64(); /* the compiled reference floors with the hardware rounding instruction: inf * 0 = NaN */
+            f64 q = x / y;
+            if (isnan64(q)) return null_f64();
+            f64 t = (f64)f64_to_i64(q);
+            return ((q < 0.0 && t != q) ? t - 1.0 : t) * y;
+        }
         default: return y == 0.0 ? null_f64() : x - floor(x / y) * y;               /* MODF64 / FEUCL_MOD */
     }
 }

@@ -27,7 +27,7 @@ enum { RFO_B8 = 1, RFO_U8 = 2, RFO_I16 = 3, RFO_I32 = 4, RFO_I64 = 5, RFO_SYMBOL
 
 enum { RFO_EQ = 0, RFO_NE = 1, RFO_LT = 2, RFO_GT = 3, RFO_LE = 4, RFO_GE = 5 };           /* core/cmp.c:692-697 */
 enum { RFO_SUM = 0, RFO_MIN = 1, RFO_MAX = 2, RFO_CNT = 3, RFO_AVG = 4, RFO_COUNT = 5 };   /* core/math.c:2388-2445 */
-enum { RFO_ADD = 0, RFO_SUB = 1, RFO_MUL = 2, RFO_DIV = 3, RFO_FDIV = 4, RFO_MOD = 5 };    /* core/math.c:2436-2441 */
+enum { RFO_ADD = 0, RFO_SUB = 1, RFO_MUL = 2, RFO_DIV = 3, RFO_FDIV = 4, RFO_MOD = 5, RFO_XBAR = 6 };    /* core/math.c:2436-2441 */
 enum { RFO_ROUND = 0, RFO_FLOOR = 1, RFO_CEIL = 2 };                                       /* core/math.c:2430-2432 */
 enum { RFO_INDEX_IDS = 0, RFO_INDEX_SHIFT = 1 };                                            /* core/index.h:31-36 */
 

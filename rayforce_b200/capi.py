@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "librfb200.so")
 B8, U8, I16, I32, I64, SYMBOL, DATE, TIME, TIMESTAMP, F64 = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 EQ, NE, LT, GT, LE, GE = range(6)
 F_SUM, F_CNT, F_MIN, F_MAX, F_ROWS, F_ALL = 1, 2, 4, 8, 16, 31
-ADD, SUB, MUL, DIV, FDIV, MOD = range(6)
+ADD, SUB, MUL, DIV, FDIV, MOD, XBAR = range(7)
 ROUND, FLOOR, CEIL = range(3)
 A_SUM, A_MIN, A_MAX, A_COUNT, A_AVG = range(5)
 INDEX_IDS, INDEX_SHIFT = 0, 1

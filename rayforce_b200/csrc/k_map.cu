@@ -278,6 +278,11 @@ __device__ __forceinline__ i32 op_i32(int op, i32 x, i32 y) {
         case RFB_SUB: return (i32)((u32)x - (u32)y);
         case RFB_MUL: return (i32)((u32)x * (u32)y);
         case RFB_DIV: return y == 0 ? NULL_I32 : eucl_div32(x, y);
+        case RFB_XBAR: {  // XBARI32 (core/ops.h:193-194): C truncating division of the shifted value
+            if (y == 0) return NULL_I32;
+            const i32 t = x < 0 ? (i32)((u32)x + 1u - (u32)y) : x;
+            return (i32)((u32)(y == -1 ? (i32)(0u - (u32)t) : t / y) * (u32)y);
+        }
         default: return y == 0 ? NULL_I32 : (i32)((u32)x - (u32)eucl_div32(x, y) * (u32)y);
     }
 }
@@ -288,9 +293,15 @@ __device__ __forceinline__ i64 op_i64(int op, i64 x, i64 y) {
         case RFB_SUB: return (i64)((u64)x - (u64)y);
         case RFB_MUL: return (i64)((u64)x * (u64)y);
         case RFB_DIV: return y == 0 ? NULL_I64 : eucl_div64(x, y);
+        case RFB_XBAR: {  // XBARI64 (core/ops.h:195-196)
+            if (y == 0) return NULL_I64;
+            const i64 t = x < 0 ? (i64)((u64)x + 1ULL - (u64)y) : x;
+            return (i64)((u64)(y == -1 ? (i64)(0ULL - (u64)t) : t / y) * (u64)y);
+        }
         default: return y == 0 ? NULL_I64 : (i64)((u64)x - (u64)eucl_div64(x, y) * (u64)y);
     }
 }
+__device__ __forceinline__ i64 f64_to_i64(f64 x);
 // plain IEEE ops, never contracted into FMAs: the reference materialises every intermediate
 __device__ __forceinline__ f64 op_f64(int op, f64 x, f64 y) {
     if (isnan64(x) || isnan64(y)) return null_f64();
@@ -299,6 +310,13 @@ __device__ __forceinline__ f64 op_f64(int op, f64 x, f64 y) {
         case RFB_SUB: return __dsub_rn(x, y);
         case RFB_MUL: return __dmul_rn(x, y);
         case RFB_DIV: return y == 0.0 ? null_f64() : floor(__ddiv_rn(x, y));
+        case RFB_XBAR: {  // XBARF64 = FLOORF64(x / y) * y (core/ops.h:197,191): floor through an (i64) cast
+            if (y == 0.0) return null_f64();   // the compiled reference yields NaN (inf * 0) for a zero bucket width
+            const f64 q = __ddiv_rn(x, y);
+            if (isnan64(q)) return null_f64();
+            const f64 t = (f64)f64_to_i64(q);
+            return __dmul_rn((q < 0.0 && t != q) ? __dsub_rn(t, 1.0) : t, y);
+        }
         default: return y == 0.0 ? null_f64() : __dsub_rn(x, __dmul_rn(floor(__ddiv_rn(x, y)), y));
     }
 }
@@ -357,7 +375,7 @@ bool binop_types(int op, int xt, int yt, int *mt, int *ot) {
     const bool anyf = (xt == RFB_F64 || yt == RFB_F64), any64 = (xt == RFB_I64 || yt == RFB_I64);
     const int wide = anyf ? RFB_F64 : any64 ? RFB_I64 : RFB_I32;
     switch (op) {
-        case RFB_ADD: case RFB_SUB: case RFB_MUL: *mt = wide; *ot = wide; return true;
+        case RFB_ADD: case RFB_SUB: case RFB_MUL: case RFB_XBAR: *mt = wide; *ot = wide; return true;   // xbar: infer_xbar_type core/math.c:225-249
         case RFB_DIV: *mt = wide; *ot = xt; return true;                    // keeps the LEFT operand's type
         case RFB_FDIV: *mt = RFB_F64; *ot = RFB_F64; return true;
         case RFB_MOD: *mt = wide; *ot = anyf ? RFB_F64 : yt; return true;   // integer % integer: RIGHT operand's type

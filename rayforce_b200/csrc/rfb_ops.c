@@ -469,6 +469,7 @@ obj_p rfb_ray_mul(obj_p x, obj_p y) { return bin_op(RFB_MUL, x, y); }
 obj_p rfb_ray_div(obj_p x, obj_p y) { return bin_op(RFB_DIV, x, y); }
 obj_p rfb_ray_fdiv(obj_p x, obj_p y) { return bin_op(RFB_FDIV, x, y); }
 obj_p rfb_ray_mod(obj_p x, obj_p y) { return bin_op(RFB_MOD, x, y); }
+obj_p rfb_ray_xbar(obj_p x, obj_p y) { return bin_op(RFB_XBAR, x, y); }
 
 static obj_p un_op(int op, obj_p x) {
     if (!G.ready || !x || x->type != RFB_T_F64) return NULL; /* integer / temporal inputs are returned as-is by the CPU body */

@@ -38,7 +38,7 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_kat.js
 UNARY = {"sum": "sum", "avg": "avg", "min": "min", "max": "max", "count": "count", "where": "where", "round": "round",
          "floor": "floor", "ceil": "ceil", "iasc": "iasc", "idesc": "idesc", "asc": "asc", "desc": "desc"}
 BINARY = {"==": "eq", "!=": "ne", "<": "lt", ">": "gt", "<=": "le", ">=": "ge", "+": "add", "-": "sub", "*": "mul",
-          "/": "div", "div": "fdiv", "%": "mod"}
+          "/": "div", "div": "fdiv", "%": "mod", "xbar": "xbar"}
 NUMERIC = {ob.B8, ob.U8, ob.I16, ob.I32, ob.I64, ob.DATE, ob.TIME, ob.TIMESTAMP, ob.F64}
 
 

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 SIZES = [1, 2, 31, 1023, 16385, 200_003]
 CMPS = [ob.EQ, ob.NE, ob.LT, ob.GT, ob.LE, ob.GE]
-ARITH = [ob.ADD, ob.SUB, ob.MUL, ob.DIV, ob.FDIV, ob.MOD]
+ARITH = [ob.ADD, ob.SUB, ob.MUL, ob.DIV, ob.FDIV, ob.MOD, ob.XBAR]
 ALL_T = [ob.U8, ob.I16, ob.I32, ob.I64, ob.F64]
 CMP_T = [ob.I16, ob.I32, ob.I64, ob.F64]      # the reference's vector comparison matrix (core/cmp.c:77-258)
 

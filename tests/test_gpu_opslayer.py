@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 NAME = {"sum": "ray_sum", "avg": "ray_avg", "min": "ray_min", "max": "ray_max", "where": "ray_where", "round": "ray_round",
         "floor": "ray_floor", "ceil": "ray_ceil", "iasc": "ray_sort_asc", "idesc": "ray_sort_desc",
         "eq": "ray_eq", "ne": "ray_ne", "lt": "ray_lt", "gt": "ray_gt", "le": "ray_le", "ge": "ray_ge", "add": "ray_add",
-        "sub": "ray_sub", "mul": "ray_mul", "div": "ray_div", "fdiv": "ray_fdiv", "mod": "ray_mod"}
+        "sub": "ray_sub", "mul": "ray_mul", "div": "ray_div", "fdiv": "ray_fdiv", "mod": "ray_mod", "xbar": "ray_xbar"}
 UNOPS = ("round", "floor", "ceil")
 
 

@@ -11,7 +11,7 @@ from tests.util import rng_col, same_f64, f64_sum_ok
 
 SIZES = [0, 1, 5, 16383, 16384, 16385, 100_003]
 CMPS = [ob.EQ, ob.NE, ob.LT, ob.GT, ob.LE, ob.GE]
-ARITH = [ob.ADD, ob.SUB, ob.MUL, ob.DIV, ob.FDIV, ob.MOD]
+ARITH = [ob.ADD, ob.SUB, ob.MUL, ob.DIV, ob.FDIV, ob.MOD, ob.XBAR]
 NUM = [ob.I32, ob.I64, ob.F64]
 
 
