@@ -151,6 +151,19 @@ int rfb_fold_result(rfb_ctx_t *ctx, rfb_fold_t *out);
 int rfb_filter_fold_dev(rfb_ctx_t *ctx, int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k, int folds,
                         int val_type, const void *val, int64_t n, rfb_fold_t *out);
 
+/* Fused `select {(fold v) from t where (and|or (cmp p1 k1) (cmp p2 k2) ...)}`: up to 4 range predicates over 8-byte columns
+ * (I64-kind or F64), combined with `and` (conjunction != 0) or `or`, tested in the same pass that folds `val`
+ * (I64-kind or F64).  Replaces per-conjunct masks + and_op/or_op (core/logic.c:34-110) + ray_where + filter_collect +
+ * the fold: (npred + 1) x 8 B per row instead.  rows = rows selected (always counted here). */
+typedef struct {
+    int32_t op;          /* RFB_EQ .. RFB_GE */
+    int32_t type;        /* element type of col */
+    const void *col;     /* device pointer */
+    rfb_scalar_t k;
+} rfb_pred_t;
+int rfb_multi_filter_fold_dev(rfb_ctx_t *ctx, int npred, const rfb_pred_t *preds, int conjunction, int folds, int val_type,
+                              const void *val, int64_t n, rfb_fold_t *out);
+
 /* Fused `(fold (+ (* a b) c))` over three F64 columns with the reference's NaN propagation (MULF64/ADDF64,
  * core/ops.h:155,164) and NaN-skipping fold: replaces ray_mul -> ray_add -> ray_sum/ray_cnt. */
 int rfb_fma_fold_dev(rfb_ctx_t *ctx, int folds, const double *a, const double *b, const double *c, int64_t n,

@@ -56,6 +56,11 @@ class Scalar(C.Structure):
         return s
 
 
+class Pred(C.Structure):
+    """rfb_pred_t"""
+    _fields_ = [("op", C.c_int32), ("type", C.c_int32), ("col", C.c_void_p), ("k", Scalar)]
+
+
 class Fold(C.Structure):
     """rfb_fold_t"""
     _fields_ = [("rows", C.c_int64), ("nonnull", C.c_int64), ("sum_i64", C.c_int64), ("sum_f64", C.c_double),
@@ -106,6 +111,7 @@ SIGNATURES = {
     "rfb_fold_dev": (_ci, [_vp, _ci, _ci, _vp, _i64, _P(Fold)]),
     "rfb_fold_result": (_ci, [_vp, _P(Fold)]),
     "rfb_filter_fold_dev": (_ci, [_vp, _ci, _ci, _vp, _P(Scalar), _ci, _ci, _vp, _i64, _P(Fold)]),
+    "rfb_multi_filter_fold_dev": (_ci, [_vp, _ci, _P(Pred), _ci, _ci, _ci, _vp, _i64, _P(Fold)]),
     "rfb_fma_fold_dev": (_ci, [_vp, _ci, _vp, _vp, _vp, _i64, _P(Fold)]),
     "rfb_cmp_dev": (_ci, [_vp, _ci, _ci, _vp, _i64, _P(Scalar), _ci, _vp, _i64, _P(Scalar), _vp]),
     "rfb_mask_logic_dev": (_ci, [_vp, _ci, _vp, _i64, _vp, _i64, C.c_uint8, _vp]),

@@ -539,6 +539,127 @@ extern "C" int rfb_gather_fold_dev(rfb_ctx_t *ctx, int folds, int type, const vo
     return wait_result(ctx, out);
 }
 
+// ------------------------------------------------------------------ compound predicates: (and p1 p2 ..) / (or p1 p2 ..)  + fold
+//
+// `where: (and (< x k1) (>= y k2) ...)` in the reference evaluates every conjunct to a 1 B/row mask, combines them
+// (core/logic.c:34-110), materialises ids and gathers.  Here up to 4 range predicates over 8-byte
+// columns (I64-kind or F64) are tested in the same pass that folds the value column: (npred + 1) x 8 B per row, nothing
+// materialised.  A predicate column that is also the value column is still loaded once.
+
+namespace {
+
+constexpr int MAX_PREDS = 4;
+struct MultiPred {
+    const u64 *col[MAX_PREDS];
+    PredRange pr[MAX_PREDS];
+    u32 is_f64[MAX_PREDS];
+    int npred;
+    int conj;  // 1 = and, 0 = or
+};
+
+__device__ __forceinline__ bool mp_test(u64 raw, const PredRange &pr, u32 is_f64) {
+    const u64 key = is_f64 ? key_of_f64(bits_f64(raw)) : (raw ^ 0x8000000000000000ULL);
+    return pred_test(key, pr);
+}
+
+template <typename V, int FOLDS, int NP>
+__global__ void __launch_bounds__(256, 4)
+k_multi_filter_fold(MultiPred mp, const V *__restrict__ val, i64 n, i64 chunks, int vkind, Partial *partials, u32 *ticket, rfb_fold_t *out) {
+    constexpr int T = 256, UNROLL = (NP >= 3) ? 1 : 2;   // (NP + 1) x UNROLL 16-byte loads in flight per thread
+    constexpr int TILE = T * UNROLL;
+    Acc<V, FOLDS, true, false> acc;
+    acc.init();
+    const i64 tiles = chunks / TILE;
+    for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        Vec16<V> vv[UNROLL];
+        Vec16<u64> pv[UNROLL][NP];
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) {
+            const i64 c = tile * TILE + (i64)j * T + threadIdx.x;
+            vv[j].raw = ld_stream16((const char *)val + c * 16);
+#pragma unroll
+            for (int q = 0; q < NP; q++) pv[j][q].raw = ld_stream16((const char *)mp.col[q] + c * 16);
+        }
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                bool sel = mp.conj != 0;
+#pragma unroll
+                for (int q = 0; q < NP; q++) {
+                    const bool t = mp_test(pv[j][q].e[r], mp.pr[q], mp.is_f64[q]);
+                    sel = mp.conj ? (sel && t) : (sel || t);
+                }
+                acc.take(vv[j].e[r], sel);
+            }
+    }
+    for (i64 r = tiles * TILE * 2 + (i64)blockIdx.x * T + threadIdx.x; r < n; r += (i64)gridDim.x * T) {
+        bool sel = mp.conj != 0;
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+            const bool t = mp_test(ld_stream(mp.col[q] + r), mp.pr[q], mp.is_f64[q]);
+            sel = mp.conj ? (sel && t) : (sel || t);
+        }
+        acc.take(ld_stream(val + r), sel);
+    }
+    typedef typename Acc<V, FOLDS, true, false>::A A;
+    finish_fold<A, FOLDS>((i64)acc.rows, (i64)acc.nonnull, acc.sum, acc.comp, acc.mn, acc.mx, Acc<V, FOLDS, true, false>::min_identity(),
+                          Acc<V, FOLDS, true, false>::max_identity(), vkind, -1, partials, ticket, out);
+}
+
+template <typename V, int FOLDS>
+int launch_multi(rfb_ctx_t *ctx, const MultiPred &mp, const void *val, i64 n, int vkind) {
+    bool vec_ok = aligned16(val);
+    for (int q = 0; q < mp.npred; q++) vec_ok = vec_ok && aligned16(mp.col[q]);
+    const i64 chunks = vec_ok ? n / 2 : 0;
+    const int grid = rfb_grid_for(ctx, vec_ok ? chunks / 2 + 1 : n, 256, 4);
+    if (n / ((i64)grid * 256) >= (1ll << 30)) { rfb_set_error("fold: column of %lld rows is beyond the per-launch limit", (long long)n); return RFB_ERR_ARG; }
+    Scratch s = scratch_of(ctx);
+    switch (mp.npred) {
+        case 1: k_multi_filter_fold<V, FOLDS, 1><<<grid, 256, 0, ctx->stream>>>(mp, (const V *)val, n, chunks, vkind, s.partials, s.ticket, s.result); break;
+        case 2: k_multi_filter_fold<V, FOLDS, 2><<<grid, 256, 0, ctx->stream>>>(mp, (const V *)val, n, chunks, vkind, s.partials, s.ticket, s.result); break;
+        case 3: k_multi_filter_fold<V, FOLDS, 3><<<grid, 256, 0, ctx->stream>>>(mp, (const V *)val, n, chunks, vkind, s.partials, s.ticket, s.result); break;
+        default: k_multi_filter_fold<V, FOLDS, 4><<<grid, 256, 0, ctx->stream>>>(mp, (const V *)val, n, chunks, vkind, s.partials, s.ticket, s.result); break;
+    }
+    RFB_CHECK_LAUNCH(ctx);
+    return RFB_OK;
+}
+
+template <typename V>
+int launch_multi_fs(rfb_ctx_t *ctx, int fs, const MultiPred &mp, const void *val, i64 n, int vkind) {
+    switch (fs) {
+        case FS_SUMCNT: return launch_multi<V, FS_SUMCNT>(ctx, mp, val, n, vkind);
+        case FS_MINMAX: return launch_multi<V, FS_MINMAX>(ctx, mp, val, n, vkind);
+        default: return launch_multi<V, FS_ALL>(ctx, mp, val, n, vkind);
+    }
+}
+
+}  // namespace
+
+extern "C" int rfb_multi_filter_fold_dev(rfb_ctx_t *ctx, int npred, const rfb_pred_t *preds, int conjunction, int folds, int val_type,
+                                         const void *val, int64_t n, rfb_fold_t *out) {
+    RFB_ARG(ctx && preds && npred >= 1 && npred <= MAX_PREDS && n >= 0 && (val || n == 0), "rfb_multi_filter_fold_dev");
+    MultiPred mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.npred = npred;
+    mp.conj = conjunction ? 1 : 0;
+    for (int q = 0; q < npred; q++) {
+        const int pk = rfb_kind_of(preds[q].type);
+        if (pk != K_I64 && pk != K_F64) { rfb_set_error("compound filter: predicate columns must be 8-byte (I64-kind or F64), got type %d", preds[q].type); return RFB_ERR_TYPE; }
+        if (!rfb_make_pred(preds[q].op, preds[q].type, &preds[q].k, &mp.pr[q])) { rfb_set_error("compound filter: unsupported comparison %d on types %d, %d", preds[q].op, preds[q].type, preds[q].k.type); return RFB_ERR_TYPE; }
+        RFB_ARG(preds[q].col || n == 0, "rfb_multi_filter_fold_dev: predicate column");
+        mp.col[q] = (const u64 *)preds[q].col;
+        mp.is_f64[q] = pk == K_F64;
+    }
+    const int fs = foldset_of(folds), vk = rfb_kind_of(val_type);
+    int rc;
+    if (vk == K_I64) rc = launch_multi_fs<i64>(ctx, fs, mp, val, n, vk);
+    else if (vk == K_F64) rc = launch_multi_fs<f64>(ctx, fs, mp, val, n, vk);
+    else { rfb_set_error("compound filter: value column must be I64-kind or F64, got type %d", val_type); return RFB_ERR_TYPE; }
+    if (rc) return rc;
+    return wait_result(ctx, out);
+}
+
 extern "C" int rfb_fold_result(rfb_ctx_t *ctx, rfb_fold_t *out) {
     RFB_ARG(ctx && out, "rfb_fold_result");
     return wait_result(ctx, out);

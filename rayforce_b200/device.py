@@ -126,6 +126,15 @@ class Context:
         check(self.lib.rfb_fold_result(self.h, C.byref(f)))
         return FoldResult(f, type_)
 
+    def multi_filter_fold(self, preds, conjunction: bool, folds: int, val_type: int, val, n: int) -> FoldResult:
+        """preds: [(cmp_op, type, column tensor, constant), ...] combined with and (True) / or (False)"""
+        arr = (capi.Pred * len(preds))()
+        for i, (op, t, col, k) in enumerate(preds):
+            arr[i].op, arr[i].type, arr[i].col, arr[i].k = op, t, _dptr(col), Scalar.of(t, k)
+        f = Fold()
+        check(self.lib.rfb_multi_filter_fold_dev(self.h, len(preds), arr, int(conjunction), folds, val_type, _dptr(val), n, C.byref(f)))
+        return FoldResult(f, val_type)
+
     def fma_fold(self, folds: int, a, b, c, n: int) -> FoldResult:
         f = Fold()
         check(self.lib.rfb_fma_fold_dev(self.h, folds, _dptr(a), _dptr(b), _dptr(c), n, C.byref(f)))

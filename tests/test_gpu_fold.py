@@ -198,6 +198,52 @@ def test_filter_fold_reference_golden_25001_rows(ctx):
     assert (got.rows, got.nonnull, got.sum) == (500, 500, 124750)
 
 
+# ---------------------------------------------------------------- compound predicates (and / or) fused with the fold
+
+@pytest.mark.parametrize("npred", [1, 2, 3, 4])
+@pytest.mark.parametrize("conj", [True, False])
+@pytest.mark.parametrize("vt", [ob.I64, ob.F64])
+@pytest.mark.parametrize("n", [1, 1000, 300_007])
+def test_multi_filter_fold(ctx, oracle, npred, conj, vt, n):
+    """where: (and|or (cmp p1 k1) ...) + fold == per-conjunct masks combined (reference core/logic.c:34-110), where, gather, fold"""
+    r = np.random.default_rng(n + npred)
+    types = [ob.I64, ob.F64, ob.I64, ob.TIMESTAMP][:npred]
+    opsl = [ob.LT, ob.GE, ob.NE, ob.LE][:npred]
+    cols, preds, mask = [], [], None
+    for t, op in zip(types, opsl):
+        c = rng_col(ob.F64 if t == ob.F64 else ob.I64, n, seed=int(r.integers(1 << 30)), null_frac=0.03, lo=-20, hi=20)
+        if t == ob.F64:
+            c = np.round(c)
+        k = 3
+        m = oracle.cmp(op, t, c, t, k) != 0
+        mask = m if mask is None else ((mask & m) if conj else (mask | m))
+        cols.append(c)
+        preds.append((op, t, dev(c), k))
+    val = rng_col(vt, n, seed=99, null_frac=0.02)
+    ids = oracle.where(mask.astype(np.uint8))
+    sel = oracle.at_ids(vt, val, ids)
+    got = ctx.multi_filter_fold(preds, conj, capi.F_ALL, vt, dev(val), n)
+    if vt == ob.F64:
+        assert got.rows == ids.shape[0] and got.nonnull == int(np.count_nonzero(~np.isnan(sel)))
+        assert f64_sum_ok(got.sum, float(oracle.fold(ob.SUM, ob.F64, sel)[0]), oracle.sum_f64_exact(sel))
+        if got.nonnull:
+            assert got.min == float(oracle.fold(ob.MIN, ob.F64, sel)[0]) and got.max == float(oracle.fold(ob.MAX, ob.F64, sel)[0])
+    else:
+        check_fold(got, oracle_folds(oracle, vt, sel), vt, ids.shape[0])
+
+
+def test_multi_filter_fold_value_column_is_a_predicate_column(ctx, oracle):
+    n = 200_001
+    x = rng_col(ob.I64, n, seed=5, null_frac=0.02, lo=-100, hi=100)
+    d = dev(x)
+    got = ctx.multi_filter_fold([(ob.GE, ob.I64, d, -10), (ob.LT, ob.I64, d, 25)], True, capi.F_ALL, ob.I64, d, n)
+    sel = x[(x >= -10) & (x < 25)]
+    check_fold(got, oracle_folds(oracle, ob.I64, sel), ob.I64, sel.shape[0])
+    with pytest.raises(capi.RfbError) as e:
+        ctx.multi_filter_fold([(ob.LT, ob.I32, dev(np.zeros(4, np.int32)), 1)], True, capi.F_SUM, ob.I64, dev(np.zeros(4, np.int64)), 4)
+    assert e.value.kind == "type"
+
+
 # ---------------------------------------------------------------- fused (fold (+ (* a b) c))
 
 @pytest.mark.parametrize("n", [0, 1, 3, 16385, 500_001])

@@ -64,6 +64,9 @@ def main():
         timed("filter_sum_i64_same_col", lambda: ctx.filter_fold(capi.LT, capi.I64, x, K, capi.F_SUM | capi.F_CNT, capi.I64, x, n), 8 * n)
         y = col(capi.I64, 43, 1 << 20)
         timed("filter_sum_i64_two_cols", lambda: ctx.filter_fold(capi.LT, capi.I64, x, K, capi.F_SUM | capi.F_CNT, capi.I64, y, n), 16 * n)
+        timed("and_filter_2cols_sum", lambda: ctx.multi_filter_fold([(capi.LT, capi.I64, x, K), (capi.GE, capi.I64, y, 1 << 19)], True,
+                                                                   capi.F_SUM | capi.F_CNT, capi.I64, y, n), 16 * n,
+              "where (and (< x k1) (>= y k2)), sum y: fused, 16 B/row")
         timed("cmp_lt_mask", lambda: ctx.cmp(capi.LT, capi.I64, x, capi.I64, K), 9 * n, "8 B in + 1 B mask out")
         mask = ctx.cmp(capi.LT, capi.I64, x, capi.I64, K)
         sel = int(ctx.where(mask).shape[0])
