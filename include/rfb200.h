@@ -261,6 +261,22 @@ int rfb_filter_fold_host(rfb_ctx_t *ctx, int cmp_op, int pred_type, const void *
 int rfb_fold_host(rfb_ctx_t *ctx, int folds, int type, const void *x, int64_t n, int64_t chunk_rows, rfb_fold_t *out,
                   int64_t *h2d_bytes);
 
+/* ------------------------------------------------------------------ column files: the reference's on-disk column format
+ * 16-byte object header (mmod 0xfd, type, attrs, len) + raw payload (written by `set`, core/binary.c:264-307; mapped back by
+ * `get`, core/unary.c:60-133).  A splayed table is a directory of these, a parted table a directory per partition.
+ * rfb_column_file_open maps one read-only; `payload` is then a host column for every *_host entry point. */
+typedef struct {
+    int32_t type;
+    int32_t attrs;
+    int64_t len;
+    const void *payload;
+    void *map_base;   /* private: the mapping */
+    size_t map_bytes;
+} rfb_column_file_t;
+int rfb_column_file_open(const char *path, rfb_column_file_t *out);
+int rfb_column_file_close(rfb_column_file_t *f);
+int rfb_column_file_write(const char *path, int type, int attrs, const void *payload, int64_t len);
+
 #ifdef __cplusplus
 }
 #endif

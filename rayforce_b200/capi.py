@@ -61,6 +61,12 @@ class Pred(C.Structure):
     _fields_ = [("op", C.c_int32), ("type", C.c_int32), ("col", C.c_void_p), ("k", Scalar)]
 
 
+class ColumnFile(C.Structure):
+    """rfb_column_file_t"""
+    _fields_ = [("type", C.c_int32), ("attrs", C.c_int32), ("len", C.c_int64), ("payload", C.c_void_p), ("map_base", C.c_void_p),
+                ("map_bytes", C.c_size_t)]
+
+
 class Fold(C.Structure):
     """rfb_fold_t"""
     _fields_ = [("rows", C.c_int64), ("nonnull", C.c_int64), ("sum_i64", C.c_int64), ("sum_f64", C.c_double),
@@ -128,6 +134,9 @@ SIGNATURES = {
     "rfb_aggr_dev": (_ci, [_vp, _ci, _ci, _vp, _vp, _vp, _i64, _i64, _vp]),
     "rfb_group_sum_count_dev": (_ci, [_vp, _ci, _vp, _vp, _i64, _ci, _ci, _vp, _P(Scalar), _i64, _vp, _vp, _vp, _P(_i64)]),
     "rfb_sort_dev": (_ci, [_vp, _ci, _vp, _i64, _ci, _vp]),
+    "rfb_column_file_open": (_ci, [C.c_char_p, _P(ColumnFile)]),
+    "rfb_column_file_close": (_ci, [_P(ColumnFile)]),
+    "rfb_column_file_write": (_ci, [C.c_char_p, _ci, _ci, _vp, _i64]),
     "rfb_filter_fold_host": (_ci, [_vp, _ci, _ci, _vp, _P(Scalar), _ci, _ci, _vp, _i64, _i64, _P(Fold), _P(_i64)]),
     "rfb_fold_host": (_ci, [_vp, _ci, _ci, _vp, _i64, _i64, _P(Fold), _P(_i64)]),
 }

@@ -8,9 +8,12 @@
 //
 // Pinned (cudaHostAlloc / rfb_host_pin) payloads are DMA'd directly; pageable payloads still work (the driver stages
 // them) but at a fraction of the PCIe rate — INTEGRATION.md tells the reference side to pin its column blocks.
+#include <fcntl.h>
 #include <pthread.h>
 #include <sched.h>
 #include <stdlib.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include "rfb_common.cuh"
@@ -198,6 +201,74 @@ void rfb_copy_shutdown(rfb_ctx_t *ctx) {
     }
     for (int i = 0; i < RFB_HOST_RING; i++)
         if (ctx->h_ring[i]) { cudaFreeHost(ctx->h_ring[i]); cudaEventDestroy(ctx->ev_ring[i]); ctx->h_ring[i] = nullptr; }
+}
+
+// ------------------------------------------------------------------ column files (splayed / parted tables on disk)
+//
+// The reference persists a column as its 16-byte object header (mmod = 0xfd MMOD_EXTERNAL_SIMPLE, type, attrs, len)
+// followed by the raw payload (set: core/binary.c:264-307; get mmaps it back: core/unary.c:60-133); a splayed table is a
+// directory of such files, a parted table one directory per partition.  The payload of a mapped file is a valid host
+// column for every *_host entry point: it is pageable memory, so it travels through the copier-thread ring.
+
+
+extern "C" int rfb_column_file_open(const char *path, rfb_column_file_t *out) {
+    RFB_ARG(path && out, "rfb_column_file_open");
+    memset(out, 0, sizeof(*out));
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { rfb_set_error("column file %s: cannot open", path); return RFB_ERR_ARG; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 16) { close(fd); rfb_set_error("column file %s: too short for an object header", path); return RFB_ERR_ARG; }
+    void *base = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (base == MAP_FAILED) { rfb_set_error("column file %s: mmap failed", path); return RFB_ERR_NOMEM; }
+    const unsigned char *h = (const unsigned char *)base;
+    const int type = (signed char)h[2];
+    int64_t len;
+    memcpy(&len, h + 8, 8);
+    const int w = rfb_type_size(type);
+    if (h[0] != 0xfd || w == 0 || len < 0 || (uint64_t)len * (uint64_t)w + 16 > (uint64_t)st.st_size) {
+        rfb_set_error("column file %s: not a simple numeric column (mmod 0x%02x, type %d, len %lld, %lld bytes)", path, h[0], type, (long long)len, (long long)st.st_size);
+        munmap(base, (size_t)st.st_size);
+        return RFB_ERR_TYPE;
+    }
+    out->type = type;
+    out->attrs = h[3];
+    out->len = len;
+    out->payload = h + 16;
+    out->map_base = base;
+    out->map_bytes = (size_t)st.st_size;
+    return RFB_OK;
+}
+
+extern "C" int rfb_column_file_close(rfb_column_file_t *f) {
+    RFB_ARG(f, "rfb_column_file_close");
+    if (f->map_base) munmap(f->map_base, f->map_bytes);
+    memset(f, 0, sizeof(*f));
+    return RFB_OK;
+}
+
+extern "C" int rfb_column_file_write(const char *path, int type, int attrs, const void *payload, int64_t len) {
+    RFB_ARG(path && len >= 0 && (payload || len == 0), "rfb_column_file_write");
+    const int w = rfb_type_size(type);
+    if (!w) { rfb_set_error("column file: unsupported element type %d", type); return RFB_ERR_TYPE; }
+    unsigned char h[16];
+    memset(h, 0, sizeof(h));
+    h[0] = 0xfd;                 // MMOD_EXTERNAL_SIMPLE
+    h[2] = (unsigned char)type;  // order 0, rc 0
+    h[3] = (unsigned char)attrs; // e.g. the reference's ATTR_ASC / ATTR_DISTINCT flags of a sorted key column
+    memcpy(h + 8, &len, 8);
+    const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) { rfb_set_error("column file %s: cannot create", path); return RFB_ERR_ARG; }
+    bool ok = write(fd, h, 16) == 16;
+    const char *p = (const char *)payload;
+    size_t left = (size_t)len * (size_t)w;
+    while (ok && left) {
+        const ssize_t c = write(fd, p, left > (1u << 30) ? (1u << 30) : left);
+        if (c <= 0) ok = false; else { p += c; left -= (size_t)c; }
+    }
+    close(fd);
+    if (!ok) { rfb_set_error("column file %s: short write", path); return RFB_ERR_ARG; }
+    return RFB_OK;
 }
 
 namespace {

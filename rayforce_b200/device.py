@@ -4,6 +4,7 @@ HBM allocations (``data_ptr()`` is handed to the C ABI); host columns are numpy 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -31,6 +32,29 @@ def _hptr(a: np.ndarray) -> int:
     if not a.flags["C_CONTIGUOUS"]:
         raise RfbError(capi.ERR_ARG, "host columns must be contiguous")
     return a.ctypes.data
+
+
+class ColumnFile:
+    """A reference column file mapped read-only; `.array` is a numpy view of the payload (no copy)."""
+
+    def __init__(self, path: str):
+        self.lib = capi.load()
+        self.f = capi.ColumnFile()
+        check(self.lib.rfb_column_file_open(os.fsencode(path), C.byref(self.f)))
+        self.type, self.len, self.attrs = self.f.type, self.f.len, self.f.attrs
+        dt = np.dtype(NP_OF[self.type])
+        buf = (C.c_char * (self.len * dt.itemsize)).from_address(self.f.payload) if self.len else b""
+        self.array = np.frombuffer(buf, dtype=dt)
+
+    def close(self):
+        if self.f.map_base:
+            self.array = None
+            self.lib.rfb_column_file_close(C.byref(self.f))
+
+    @staticmethod
+    def write(path: str, type_: int, arr: np.ndarray, attrs: int = 0):
+        arr = np.ascontiguousarray(arr, NP_OF[type_])
+        check(capi.load().rfb_column_file_write(os.fsencode(path), type_, attrs, arr.ctypes.data, arr.shape[0]))
 
 
 class FoldResult:
