@@ -129,6 +129,8 @@ int rfb_host_free_pinned(void *p);
 /* column shipping: async on the context stream; `pinned` tells whether src/dst is page-locked */
 int rfb_h2d(rfb_ctx_t *ctx, void *dst_dev, const void *src_host, size_t bytes);
 int rfb_d2h(rfb_ctx_t *ctx, void *dst_host, const void *src_dev, size_t bytes);
+/* synchronous device -> host copy through the driver only (no helper threads): returns with the bytes in place */
+int rfb_d2h_sync_plain(rfb_ctx_t *ctx, void *dst_host, const void *src_dev, size_t bytes);
 
 /* deterministic synthetic columns generated in HBM (bench / tests): x[i] = splitmix64(seed, i) % modulus (+ offset),
  * every `null_every`-th element (if > 0) replaced by the type's null.  type: I32, I64 or F64 (F64: value / scale). */

@@ -83,6 +83,11 @@ int64_t rfb_ops_launches(void);       /* kernels launched so far (evidence that 
  * Outside a scope every call ships its operands.  Bind begin/end around ray_select (core/query.c:607). */
 void rfb_ops_scope_begin(void);
 void rfb_ops_scope_end(void);
+/* EXPERIMENTAL, env RFB200_LAZY=1: inside a scope, results of at least RFB200_LAZY_MIN bytes (default 32 MiB) stay on the
+ * device; their host payload pages are protected and filled on the first CPU access (SIGSEGV handler) or at scope end.
+ * out = {results left lazy, faulted in by a CPU access, dropped because the host had already freed them}. */
+void rfb_ops_lazy_stats(long out[3]);
+void rfb_ops_set_lazy(int on, int64_t min_bytes); /* same switch at run time (min_bytes <= 0 keeps the threshold) */
 
 /* ---- predicate scan: ray_eq/ne/lt/gt/le/ge (core/cmp.c:692-697) -> B8 vector */
 rfb_obj_p rfb_ray_eq(rfb_obj_p x, rfb_obj_p y);

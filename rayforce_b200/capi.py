@@ -113,6 +113,7 @@ SIGNATURES = {
     "rfb_host_free_pinned": (_ci, [_vp]),
     "rfb_h2d": (_ci, [_vp, _vp, _vp, _sz]),
     "rfb_d2h": (_ci, [_vp, _vp, _vp, _sz]),
+    "rfb_d2h_sync_plain": (_ci, [_vp, _vp, _vp, _sz]),
     "rfb_fill_splitmix_dev": (_ci, [_vp, _ci, _vp, _i64, _u64, _u64, _i64, _i64, C.c_double]),
     "rfb_fold_dev": (_ci, [_vp, _ci, _ci, _vp, _i64, _P(Fold)]),
     "rfb_fold_result": (_ci, [_vp, _P(Fold)]),

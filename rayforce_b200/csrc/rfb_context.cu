@@ -186,6 +186,15 @@ int rfb_d2h(rfb_ctx_t *ctx, void *dst_host, const void *src_dev, size_t bytes) {
     return RFB_OK;
 }
 
+int rfb_d2h_sync_plain(rfb_ctx_t *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+    RFB_ARG(ctx && (bytes == 0 || (dst_host && src_dev)), "rfb_d2h_sync_plain");
+    if (bytes) {
+        RFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        RFB_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+    }
+    return RFB_OK;
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------ synthetic columns generated in HBM

@@ -8,14 +8,20 @@
 #include "rfb200_ops.h"
 
 #include <math.h>
+#include <signal.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 #include "rfb200.h"
 
 typedef rfb_obj_p obj_p;
+
+/* synchronous, driver-staged copy that involves none of this library's helper threads (safe inside the fault handler) */
+static int rfb_d2h_plain(rfb_ctx_t *ctx, void *dst_host, const void *src_dev, size_t bytes) { return rfb_d2h_sync_plain(ctx, dst_host, src_dev, bytes); }
 
 /* ------------------------------------------------------------------ state */
 
@@ -54,6 +60,11 @@ static void set_err(const char *fmt, ...) {
     va_end(ap);
 }
 const char *rfb_ops_last_error(void) { return G.err; }
+
+/* lazily materialised results (defined further down) */
+static int lazy_on = -1;
+static long lazy_stats[3]; /* registered, faulted in, dropped */
+static void lazy_resolve_all(void);
 
 /* ------------------------------------------------------------------ builtin malloc host (standalone / tests) */
 
@@ -140,10 +151,15 @@ void rfb_ops_shutdown(void) {
 }
 
 void rfb_ops_set_min_rows(int64_t n) { G.min_rows = n; }
+void rfb_ops_lazy_stats(long out[3]) { out[0] = lazy_stats[0]; out[1] = lazy_stats[1]; out[2] = lazy_stats[2]; }
 int64_t rfb_ops_launches(void) { return G.ready ? rfb_launch_count(G.ctx) : 0; }
 void rfb_ops_scope_begin(void) { G.scope_depth++; }
 void rfb_ops_scope_end(void) {
-    if (G.scope_depth > 0 && --G.scope_depth == 0 && G.ready) { rfb_sync(G.ctx); release_columns(); }
+    if (G.scope_depth > 0 && --G.scope_depth == 0 && G.ready) {
+        rfb_sync(G.ctx);
+        if (lazy_on == 1) lazy_resolve_all();
+        release_columns();
+    }
 }
 
 /* 64 strided 8-byte samples + the tail, mixed.  The host may free a vector and get the same block back for a different
@@ -160,6 +176,163 @@ static uint64_t fingerprint(const void *payload, size_t bytes) {
     }
     memcpy(&w, (const char *)payload + bytes - 8, 8);
     return (h ^ w) * 0x94D049BB133111EBULL;
+}
+
+/* ------------------------------------------------------------------ lazily materialised results (opt-in: RFB200_LAZY=1)
+ *
+ * Inside a query scope most operator results are consumed by the next GPU operator (mask -> where -> gather/fold), yet
+ * the evaluator's protocol wants every result as a host object.  With RFB200_LAZY=1 a large result's payload is not
+ * copied back: the pages that belong to it alone are made inaccessible (mprotect PROT_NONE) and the device buffer stays
+ * attached.  The first CPU access faults; the SIGSEGV handler copies the bytes back, re-opens the pages and returns, so
+ * any CPU consumer still sees correct data ("lazily materialised payload").  At the end of the scope every
+ * still-pending result whose pages are still mapped and still protected is materialised; results whose block the host
+ * already unmapped (a dropped >= 32 MB vector in the reference: core/heap.c:291-308) are simply forgotten.
+ * EXPERIMENTAL and off by default: it installs a SIGSEGV handler in the host process. */
+
+#define MAX_LAZY 64
+typedef struct {
+    char *lo, *hi;        /* protected page range (inside the payload) */
+    const char *payload;  /* start of the payload */
+    void *dev;            /* device image of the payload */
+    volatile int state;   /* 0 free, 1 pending, 2 materialised */
+} lazy_t;
+static lazy_t LZ[MAX_LAZY];
+static size_t lazy_min = 32u << 20;
+static volatile int lazy_lock;
+static struct sigaction lazy_old_segv;
+
+static void lazy_invalidate_image(void *dev) {
+    for (int i = 0; i < G.ncols; i++)
+        if (G.cols[i].dev == dev) G.cols[i].host = NULL; /* the host has touched (maybe changed) the bytes */
+}
+
+static void lazy_fill(lazy_t *z) { /* pages -> read/write, bytes <- device */
+    mprotect(z->lo, (size_t)(z->hi - z->lo), PROT_READ | PROT_WRITE);
+    rfb_sync(G.ctx);
+    /* plain synchronous copy: this may run inside the signal handler, keep it free of our own threads and locks */
+    rfb_d2h_plain(G.ctx, z->lo, (const char *)z->dev + (z->lo - z->payload), (size_t)(z->hi - z->lo));
+}
+
+static void lazy_segv(int sig, siginfo_t *si, void *uc) {
+    char *a = (char *)si->si_addr;
+    for (int i = 0; i < MAX_LAZY; i++) {
+        lazy_t *z = &LZ[i];
+        if (z->state == 1 && a >= z->lo && a < z->hi) {
+            while (__sync_lock_test_and_set(&lazy_lock, 1)) { }
+            if (z->state == 1) {
+                lazy_fill(z);
+                lazy_invalidate_image(z->dev);
+                z->state = 2;
+                lazy_stats[1]++;
+            }
+            __sync_lock_release(&lazy_lock);
+            return; /* retry the faulting access */
+        }
+    }
+    /* not ours: hand over to whoever was there before (default action: die with the usual core) */
+    if (lazy_old_segv.sa_flags & SA_SIGINFO) { if (lazy_old_segv.sa_sigaction) { lazy_old_segv.sa_sigaction(sig, si, uc); return; } }
+    else if (lazy_old_segv.sa_handler != SIG_DFL && lazy_old_segv.sa_handler != SIG_IGN) { lazy_old_segv.sa_handler(sig); return; }
+    signal(SIGSEGV, SIG_DFL);
+    raise(SIGSEGV);
+}
+
+static int lazy_handler_installed;
+static int lazy_install(void) {
+    if (lazy_handler_installed) return 1;
+    struct sigaction sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.sa_sigaction = lazy_segv;
+    sa.sa_flags = SA_SIGINFO | SA_NODEFER;
+    sigemptyset(&sa.sa_mask);
+    if (sigaction(SIGSEGV, &sa, &lazy_old_segv) != 0) return 0;
+    lazy_handler_installed = 1;
+    return 1;
+}
+
+static int lazy_enabled(void) {
+    if (lazy_on < 0) {
+        const char *e = getenv("RFB200_LAZY"), *m = getenv("RFB200_LAZY_MIN");
+        lazy_on = (e && e[0] == '1') ? 1 : 0;
+        if (m) lazy_min = (size_t)atoll(m);
+        if (lazy_on && !lazy_install()) lazy_on = 0;
+    }
+    return lazy_on;
+}
+
+void rfb_ops_set_lazy(int on, int64_t min_bytes) {
+    if (G.scope_depth == 0 && lazy_on == 1) lazy_resolve_all();
+    if (min_bytes > 0) lazy_min = (size_t)min_bytes;
+    lazy_on = (on && lazy_install()) ? 1 : 0;
+}
+
+/* is [lo, hi) still one of OUR protected ranges?  (/proc/self/maps: a mapping with no permissions covering it) */
+static int lazy_still_ours(const char *lo, const char *hi) {
+    FILE *f = fopen("/proc/self/maps", "r");
+    if (!f) return 0;
+    char line[512];
+    int ours = 0;
+    while (fgets(line, sizeof(line), f)) {
+        unsigned long a, b;
+        char perms[8];
+        if (sscanf(line, "%lx-%lx %7s", &a, &b, perms) != 3) continue;
+        if ((unsigned long)lo >= a && (unsigned long)hi <= b) { ours = (perms[0] == '-' && perms[1] == '-'); break; }
+    }
+    fclose(f);
+    return ours;
+}
+
+/* forget pending entries that overlap a range the host has handed out again */
+static void lazy_forget_overlaps(const char *lo, const char *hi, lazy_t *except) {
+    for (int i = 0; i < MAX_LAZY; i++) {
+        lazy_t *z = &LZ[i];
+        if (z != except && z->state == 1 && lo < z->hi && hi > z->lo) { z->state = 0; lazy_stats[2]++; }
+    }
+}
+
+/* the device image of a still-pending lazy payload, or NULL */
+static void *lazy_device_image(const void *payload) {
+    for (int i = 0; i < MAX_LAZY; i++)
+        if (LZ[i].state == 1 && LZ[i].payload == (const char *)payload) return LZ[i].dev;
+    return NULL;
+}
+
+/* resolve everything that is still pending (end of the outermost scope, before the device buffers are recycled) */
+static void lazy_resolve_all(void) {
+    for (int i = 0; i < MAX_LAZY; i++) {
+        lazy_t *z = &LZ[i];
+        if (z->state != 1) { z->state = 0; continue; }
+        while (__sync_lock_test_and_set(&lazy_lock, 1)) { }
+        if (z->state == 1) {
+            if (lazy_still_ours(z->lo, z->hi)) lazy_fill(z); else lazy_stats[2]++;
+        }
+        z->state = 0;
+        __sync_lock_release(&lazy_lock);
+    }
+}
+
+/* try to leave `r`'s payload on the device; returns 1 when the result is lazy (edges copied, interior protected) */
+static int lazy_register(obj_p r, size_t bytes, void *dev) {
+    if (!lazy_enabled() || bytes < lazy_min || G.scope_depth < 2) return 0; /* depth 1 = a bare call: would resolve at once */
+    const long pg = sysconf(_SC_PAGESIZE);
+    char *p = (char *)RFB_OBJ_PAYLOAD(r);
+    char *lo = (char *)(((uintptr_t)p + (uintptr_t)pg - 1) & ~(uintptr_t)(pg - 1));
+    char *hi = (char *)(((uintptr_t)p + bytes) & ~(uintptr_t)(pg - 1));
+    if (hi <= lo + 16 * pg) return 0;
+    int slot = -1;
+    for (int i = 0; i < MAX_LAZY; i++)
+        if (LZ[i].state == 0 || LZ[i].state == 2) { slot = i; break; }
+    if (slot < 0) return 0;
+    lazy_forget_overlaps((const char *)r, p + bytes, NULL);
+    /* the partial pages at both ends are shared with neighbours: copy them now */
+    if (lo > p && rfb_d2h_plain(G.ctx, p, dev, (size_t)(lo - p)) != RFB_OK) return 0;
+    if (p + bytes > hi && rfb_d2h_plain(G.ctx, hi, (const char *)dev + (hi - p), (size_t)(p + bytes - hi)) != RFB_OK) return 0;
+    if (mprotect(lo, (size_t)(hi - lo), PROT_NONE) != 0) return 0;
+    lazy_t *z = &LZ[slot];
+    z->lo = lo; z->hi = hi; z->payload = p; z->dev = dev;
+    __sync_synchronize();
+    z->state = 1;
+    lazy_stats[0]++;
+    return 1;
 }
 
 /* a device buffer of at least `bytes` (from the reuse pool when one fits within 2x) */
@@ -205,6 +378,11 @@ static int track(void *dev, size_t bytes, const void *host, int64_t len, int typ
 static void *dev_column(obj_p v) {
     const int w = type_size(v->type);
     const void *payload = RFB_OBJ_PAYLOAD(v);
+    if (lazy_on == 1) {
+        void *img = lazy_device_image(payload);   /* never read a pending payload: that would fault it in */
+        if (img) return img;
+        lazy_forget_overlaps((const char *)v, (const char *)payload + (size_t)v->len * w, NULL);
+    }
     for (int i = 0; i < G.ncols; i++)
         if (G.cols[i].host == payload && G.cols[i].len == v->len && G.cols[i].type == v->type) {
             if (G.cols[i].print == fingerprint(payload, (size_t)v->len * w)) return G.cols[i].dev;
@@ -230,6 +408,11 @@ static void *dev_temp(size_t bytes) {
 static obj_p to_host_vector(int type, int64_t len, void *dev) {
     obj_p r = G.host->vector((int8_t)type, len);
     if (!r || r->type == RFB_T_ERR) return r ? r : G.host->err_limit();
+    if (len > 0 && lazy_register(r, (size_t)len * type_size(type), dev)) {
+        for (int i = 0; i < G.ncols; i++)
+            if (G.cols[i].dev == dev) { G.cols[i].host = NULL; G.cols[i].len = len; G.cols[i].type = type; }   /* found through the lazy table */
+        return r;
+    }
     if (len > 0) {
         if (rfb_d2h(G.ctx, RFB_OBJ_PAYLOAD(r), dev, (size_t)len * type_size(type)) != RFB_OK || rfb_sync(G.ctx) != RFB_OK) {
             set_err("%s", rfb_last_error());

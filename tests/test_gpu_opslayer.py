@@ -209,3 +209,48 @@ def test_scope_does_not_serve_a_stale_image_when_the_host_reuses_a_block(ops):
         C.memmove(a + 16, new.ctypes.data, new.nbytes)
         assert int(ops.value(ops.call("ray_sum", a))[0]) == 499500 * 3
         ops.drop(a)
+
+
+def test_lazily_materialised_results(ops, oracle):
+    """EXPERIMENTAL mode (RFB200_LAZY=1 / rfb_ops_set_lazy): inside a scope large results stay on the device, their host
+    pages are protected and filled on the first CPU access.  GPU consumers must find the device image without touching
+    the host bytes; a CPU reader must still see exactly the reference's bytes."""
+    import ctypes as C
+    n = 2_000_003
+    col = rng_col(ob.I64, n, 21, null_frac=0.01, lo=-1000, hi=1000)
+    x, k = ops.vec(ob.I64, col), ops.atom(ob.I64, 37)
+    stats = (C.c_long * 3)()
+    ops.L.rfb_ops_lazy_stats(stats)
+    before = list(stats)
+    ops.L.rfb_ops_set_lazy.argtypes = [C.c_int, C.c_int64]
+    ops.L.rfb_ops_set_lazy(1, 1 << 20)
+    try:
+        with ops.scope():
+            mask = ops.call("ray_lt", x, k)                 # 2 MB mask: stays on the device
+            ids = ops.call("ray_where", mask)                # consumes the device image of the mask; ~8 MB of ids stay too
+            lazy = ops.call("filter_map", x, ids)
+            got, gt = ops.value(ops.call("ray_sum", lazy))   # consumes the device image of the ids
+            m_want = oracle.cmp(ob.LT, ob.I64, col, ob.I64, 37)
+            i_want = oracle.where(m_want)
+            assert int(got) == int(oracle.fold(ob.SUM, ob.I64, oracle.at_ids(ob.I64, col, i_want))[0])
+            ops.L.rfb_ops_lazy_stats(stats)
+            assert stats[0] - before[0] == 2 and stats[1] - before[1] == 0, list(stats)     # two lazy results, no fault yet
+            i_got, _ = ops.value(ids, drop=False)            # a CPU reader: faults the ids in
+            assert np.array_equal(i_got, i_want)
+            ops.L.rfb_ops_lazy_stats(stats)
+            assert stats[1] - before[1] == 1
+            g2, _ = ops.value(ops.call("ray_sum", lazy))     # ids now come from the (materialised) host copy again
+            assert int(g2) == int(got)
+            ops.drop(lazy)
+        m_got, _ = ops.value(mask)                           # never touched inside the scope: filled at scope end
+        assert np.array_equal(m_got, m_want)
+        ops.drop(ids)
+        # a result dropped by the host before anyone touched it is simply forgotten
+        with ops.scope():
+            t = ops.call("ray_add", x, k)
+            ops.drop(t)
+        ops.L.rfb_ops_lazy_stats(stats)
+        assert stats[0] - before[0] == 3
+    finally:
+        ops.L.rfb_ops_set_lazy(0, 0)
+    ops.drop(x, k)
