@@ -85,8 +85,8 @@ void rfb_ops_scope_begin(void);
 void rfb_ops_scope_end(void);
 /* EXPERIMENTAL, env RFB200_LAZY=1: inside a scope, results of at least RFB200_LAZY_MIN bytes (default 32 MiB) stay on the
  * device; their host payload pages are protected and filled on the first CPU access (SIGSEGV handler) or at scope end.
- * out = {results left lazy, faulted in by a CPU access, dropped because the host had already freed them}. */
-void rfb_ops_lazy_stats(long out[3]);
+ * out = {results left lazy, faulted in by a CPU access, dropped because the host had already freed them, filled at scope end}. */
+void rfb_ops_lazy_stats(long out[4]);
 void rfb_ops_set_lazy(int on, int64_t min_bytes); /* same switch at run time (min_bytes <= 0 keeps the threshold) */
 
 /* ---- predicate scan: ray_eq/ne/lt/gt/le/ge (core/cmp.c:692-697) -> B8 vector */

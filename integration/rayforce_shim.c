@@ -57,6 +57,9 @@ static void print_stats(void) {
             (long long)rfb_ops_launches());
     for (int i = 0; i < S_N; i++)
         if (n_gpu[i] || n_cpu[i]) fprintf(stderr, "[rfb200 shim]   %-16s gpu %8ld   cpu %8ld\n", S_NAME[i], n_gpu[i], n_cpu[i]);
+    long lz[4];
+    rfb_ops_lazy_stats(lz);
+    if (lz[0]) fprintf(stderr, "[rfb200 shim] lazy results: %ld left on the device, %ld faulted in by a CPU access, %ld dropped unread, %ld filled at scope end\n", lz[0], lz[1], lz[2], lz[3]);
 }
 
 static int gpu_ok(void) {

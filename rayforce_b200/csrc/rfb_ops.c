@@ -63,7 +63,7 @@ const char *rfb_ops_last_error(void) { return G.err; }
 
 /* lazily materialised results (defined further down) */
 static int lazy_on = -1;
-static long lazy_stats[3]; /* registered, faulted in, dropped */
+static long lazy_stats[4]; /* registered, faulted in, dropped, filled at scope end */
 static void lazy_resolve_all(void);
 
 /* ------------------------------------------------------------------ builtin malloc host (standalone / tests) */
@@ -151,7 +151,7 @@ void rfb_ops_shutdown(void) {
 }
 
 void rfb_ops_set_min_rows(int64_t n) { G.min_rows = n; }
-void rfb_ops_lazy_stats(long out[3]) { out[0] = lazy_stats[0]; out[1] = lazy_stats[1]; out[2] = lazy_stats[2]; }
+void rfb_ops_lazy_stats(long out[4]) { out[0] = lazy_stats[0]; out[1] = lazy_stats[1]; out[2] = lazy_stats[2]; out[3] = lazy_stats[3]; }
 int64_t rfb_ops_launches(void) { return G.ready ? rfb_launch_count(G.ctx) : 0; }
 void rfb_ops_scope_begin(void) { G.scope_depth++; }
 void rfb_ops_scope_end(void) {
@@ -206,11 +206,12 @@ static void lazy_invalidate_image(void *dev) {
         if (G.cols[i].dev == dev) G.cols[i].host = NULL; /* the host has touched (maybe changed) the bytes */
 }
 
-static void lazy_fill(lazy_t *z) { /* pages -> read/write, bytes <- device */
+static void lazy_fill(lazy_t *z, int in_handler) { /* pages -> read/write, bytes <- device */
     mprotect(z->lo, (size_t)(z->hi - z->lo), PROT_READ | PROT_WRITE);
     rfb_sync(G.ctx);
-    /* plain synchronous copy: this may run inside the signal handler, keep it free of our own threads and locks */
-    rfb_d2h_plain(G.ctx, z->lo, (const char *)z->dev + (z->lo - z->payload), (size_t)(z->hi - z->lo));
+    /* inside the signal handler: plain synchronous copy, free of our own threads and locks; otherwise the fast ring */
+    if (in_handler) rfb_d2h_plain(G.ctx, z->lo, (const char *)z->dev + (z->lo - z->payload), (size_t)(z->hi - z->lo));
+    else { rfb_d2h(G.ctx, z->lo, (const char *)z->dev + (z->lo - z->payload), (size_t)(z->hi - z->lo)); rfb_sync(G.ctx); }
 }
 
 static void lazy_segv(int sig, siginfo_t *si, void *uc) {
@@ -220,7 +221,7 @@ static void lazy_segv(int sig, siginfo_t *si, void *uc) {
         if (z->state == 1 && a >= z->lo && a < z->hi) {
             while (__sync_lock_test_and_set(&lazy_lock, 1)) { }
             if (z->state == 1) {
-                lazy_fill(z);
+                lazy_fill(z, 1);
                 lazy_invalidate_image(z->dev);
                 z->state = 2;
                 lazy_stats[1]++;
@@ -303,7 +304,7 @@ static void lazy_resolve_all(void) {
         if (z->state != 1) { z->state = 0; continue; }
         while (__sync_lock_test_and_set(&lazy_lock, 1)) { }
         if (z->state == 1) {
-            if (lazy_still_ours(z->lo, z->hi)) lazy_fill(z); else lazy_stats[2]++;
+            if (lazy_still_ours(z->lo, z->hi)) { lazy_fill(z, 0); lazy_stats[3]++; } else lazy_stats[2]++;
         }
         z->state = 0;
         __sync_lock_release(&lazy_lock);

@@ -219,7 +219,7 @@ def test_lazily_materialised_results(ops, oracle):
     n = 2_000_003
     col = rng_col(ob.I64, n, 21, null_frac=0.01, lo=-1000, hi=1000)
     x, k = ops.vec(ob.I64, col), ops.atom(ob.I64, 37)
-    stats = (C.c_long * 3)()
+    stats = (C.c_long * 4)()
     ops.L.rfb_ops_lazy_stats(stats)
     before = list(stats)
     ops.L.rfb_ops_set_lazy.argtypes = [C.c_int, C.c_int64]
