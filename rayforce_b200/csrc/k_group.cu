@@ -595,6 +595,18 @@ extern "C" int rfb_aggr_dev(rfb_ctx_t *ctx, int op, int val_type, const void *va
 }
 
 // ------------------------------------------------------------------ fused dense group-by: sum + count [+ where]
+//
+// Three accumulate strategies, picked from the key range found by the scope pass:
+//   range <= KP (8192)        CTA-private accumulators in shared memory, merged once per CTA
+//   range <= MAX_PARTS * KP   two passes over a key-range PARTITIONED copy of the selected rows: the scatter pass splits
+//                             the rows into P = range/KP partitions of (16-bit slot, value) pairs, the accumulate pass
+//                             gives every CTA one partition at a time, whose KP accumulators fit shared memory.  36 B/row
+//                             of streaming traffic instead of two L2 atomics per row (L2 atomics cap at ~175 G/s on B200,
+//                             which is what bounded the 1e5-key config at 12.3 ms per 1e9 rows)
+//   otherwise                 device-wide accumulators updated with L2 atomics
+// Shared-memory accumulators are 32-bit words (sum low / sum high / count): sm_100a has native 32-bit shared atomics
+// (ATOMS.ADD) but implements 64-bit shared adds as a compare-and-swap loop (ATOMS.CAST.SPIN.64).  The 64-bit wrapping
+// sum is kept exact by carrying: the returning add on the low word tells the one row that wrapped it to add 1 to the high word.
 
 namespace {
 
@@ -604,6 +616,29 @@ struct Accums {
     u64 *cnt;         // [range] rows (nulls included: aggr_count counts rows, core/aggr.c:1336-1342)
     u32 *has_null;    // [range] sticky-null marker for the sum (core/aggr.c:1088)
 };
+
+constexpr int KP_LOG = 13, KP = 1 << KP_LOG;   // keys per partition = shared-memory accumulator slots per CTA (96 KB)
+constexpr int MAX_PARTS = 256;
+constexpr int PT = 512;                        // threads per CTA of the accumulate kernels (2 CTAs per SM)
+constexpr int PTILE = PT * 8;                  // rows per tile / work unit: 4 pairs per thread
+constexpr int ST = 256;                        // threads per CTA of the scatter and scope kernels (4 CTAs per SM)
+constexpr int STILE = ST * 8;
+constexpr u32 NULL_FLAG = 0x80000000u;
+
+// two consecutive elements with one vector load (p must be aligned to 2 * sizeof(T))
+template <typename T> __device__ __forceinline__ void ld_pair(const T *p, i64 pair, T &a, T &b) {
+    if constexpr (sizeof(T) == 8) {
+        const vec16 v = ld_stream16(p + 2 * pair);
+        if constexpr (Elem<T>::kind == K_F64) { a = bits_f64(v.lo); b = bits_f64(v.hi); }
+        else { a = (T)v.lo; b = (T)v.hi; }
+    } else {
+        static_assert(sizeof(T) == 4, "pair loads: 4- or 8-byte elements");
+        const u64 w = __ldcs((const unsigned long long *)p + pair);
+        a = (T)(u32)w;
+        b = (T)(u32)(w >> 32);
+    }
+}
+template <typename T> static inline bool pair_aligned(const T *p) { return (((uintptr_t)p) & (2 * sizeof(T) - 1)) == 0; }
 
 template <typename K, typename P, bool HAS_PRED>
 struct FusedSrc {
@@ -615,15 +650,114 @@ struct FusedSrc {
         else return true;
     }
     __device__ __forceinline__ i64 key(i64 i) const { return (i64)ld_stream(keys + i); }
+    __device__ __forceinline__ void key_pair(i64 pair, i64 &a, i64 &b) const {
+        K x, y;
+        ld_pair<K>(keys, pair, x, y);
+        a = (i64)x;
+        b = (i64)y;
+    }
+    __device__ __forceinline__ void selected_pair(i64 pair, bool &a, bool &b) const {
+        if constexpr (HAS_PRED) {
+            P x, y;
+            ld_pair<P>(pred, pair, x, y);
+            a = pred_test(pred_key<P>(x), pr);
+            b = pred_test(pred_key<P>(y), pr);
+        } else { a = b = true; }
+    }
+    bool vec_ok(const i64 *val) const { return pair_aligned(keys) && pair_aligned(val) && (!HAS_PRED || pair_aligned(pred)); }
 };
 
-template <typename FS>
-__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_fused_scope(FS fs, i64 n, i64 *mm) {
+// rows [base, base + 8 * NT) of (key, value, selected): row of (thread, j, h) = base + 2 * (j * NT + thread) + h, so that
+// every load instruction of a warp covers one contiguous, fully used run of bytes
+template <int NT, bool WITH_VAL, typename FS>
+__device__ __forceinline__ void load_tile(const FS &fs, const i64 *__restrict__ val, i64 base, i64 n, bool vec, i64 (&k)[8], i64 (&v)[8], bool (&sel)[8]) {
+    if (vec && base + 8 * NT <= n) {
+        const i64 pbase = base >> 1;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const i64 pair = pbase + j * NT + threadIdx.x;
+            fs.key_pair(pair, k[2 * j], k[2 * j + 1]);
+            if constexpr (WITH_VAL) ld_pair<i64>(val, pair, v[2 * j], v[2 * j + 1]);
+            fs.selected_pair(pair, sel[2 * j], sel[2 * j + 1]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const i64 r = base + 2 * ((j >> 1) * NT + threadIdx.x) + (j & 1);
+            sel[j] = r < n && fs.selected(r);
+            k[j] = r < n ? fs.key(r) : 0;
+            if constexpr (WITH_VAL) v[j] = r < n ? ld_stream(val + r) : 0;
+        }
+    }
+}
+
+// ---- shared-memory accumulators (32-bit words)
+struct SAcc { u32 *lo, *hi, *cnt; };
+
+__device__ __forceinline__ void sacc_add(const SAcc &a, u32 s, i64 v) {
+    if (v == NULL_I64) atomicOr(&a.cnt[s], NULL_FLAG);
+    else {
+        const u32 lo = (u32)(u64)v;
+        u32 hi = (u32)((u64)v >> 32);
+        const u32 old = atomicAdd(&a.lo[s], lo);
+        hi += (u32)((u32)(old + lo) < lo);   // this row wrapped the low word: carry
+        if (hi) atomicAdd(&a.hi[s], hi);
+    }
+    atomicAdd(&a.cnt[s], 1u);
+}
+__device__ __forceinline__ void sacc_zero(const SAcc &a, int slots) {
+    for (int s = threadIdx.x; s < slots; s += blockDim.x) { a.lo[s] = 0; a.hi[s] = 0; a.cnt[s] = 0; }
+}
+// merge into the device-wide accumulators and clear; slot0 = device-wide slot of local slot 0 (a local slot that
+// received rows always maps inside [0, range))
+__device__ __forceinline__ void sacc_flush(const SAcc &a, int slots, i64 slot0, const Accums &ga) {
+    for (int s = threadIdx.x; s < slots; s += blockDim.x) {
+        const u32 c = a.cnt[s];
+        if (!c) continue;
+        const i64 g = slot0 + s;
+        const u64 sum = ((u64)a.hi[s] << 32) | a.lo[s];
+        if (sum) atomicAdd((unsigned long long *)ga.sum + g, (unsigned long long)sum);
+        atomicAdd((unsigned long long *)ga.cnt + g, (unsigned long long)(c & ~NULL_FLAG));
+        if (c & NULL_FLAG) ga.has_null[g] = 1u;
+        a.lo[s] = 0; a.hi[s] = 0; a.cnt[s] = 0;
+    }
+}
+
+// ---- scope: min/max of the selected keys (+ the histogram of absolute key buckets (key >> KP_LOG) mod 256 that sizes the
+// partitions: with at most 256 partitions every partition owns exactly one bucket)
+constexpr int MM_WORDS = 8, HIST_BINS = 257;   // mm[0..7] = {min, max, limit, nonempty, claimed, -, -, -}, then hist[257]
+__global__ void k_fused_scope_init(i64 *mm) {
+    for (int i = threadIdx.x; i < MM_WORDS + HIST_BINS; i += blockDim.x) mm[i] = i == 0 ? RFB_INF_I64 : (i == 1 ? NULL_I64 : 0);
+}
+
+// rank-free counting: one shared-memory atomic per row, except that a warp step whose 32 rows all fall into the same
+// bucket (heavily skewed keys) issues a single one.  (__match_any_sync-based aggregation was measured first: the MATCH
+// instruction runs on the ADU pipe and bounded both this kernel and the scatter pass, profiles/r01_part_groupby.txt)
+__device__ __forceinline__ void hist_add(u32 *sh, u32 b) {
+    const u32 b0 = __shfl_sync(0xffffffffu, b, 0);
+    if (__all_sync(0xffffffffu, b == b0)) { if ((threadIdx.x & 31) == 0) atomicAdd(&sh[b0], 32u); }
+    else atomicAdd(&sh[b], 1u);
+}
+
+template <typename FS, bool HIST>
+__global__ void __launch_bounds__(ST, 4) k_fused_scope(FS fs, i64 n, bool vec, i64 *mm) {
     __shared__ i64 red[32];
+    __shared__ u32 sh[HIST_BINS];
+    if constexpr (HIST) {
+        for (int b = threadIdx.x; b < HIST_BINS; b += ST) sh[b] = 0;
+        __syncthreads();
+    }
     i64 lo = RFB_INF_I64, hi = NULL_I64;
-    for (i64 i = (i64)blockIdx.x * THREADS + threadIdx.x; i < n; i += (i64)gridDim.x * THREADS) {
-        const i64 k = fs.key(i);
-        if (fs.selected(i)) { lo = k < lo ? k : lo; hi = k > hi ? k : hi; }
+    const i64 tiles = (n + STILE - 1) / STILE;
+    for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        i64 k[8], v[8];
+        bool sel[8];
+        load_tile<ST, false>(fs, nullptr, tile * STILE, n, vec, k, v, sel);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (sel[j]) { lo = k[j] < lo ? k[j] : lo; hi = k[j] > hi ? k[j] : hi; }
+            if constexpr (HIST) hist_add(sh, sel[j] ? (u32)(((u64)k[j] >> KP_LOG) & 255u) : 256u);
+        }
     }
     struct Mn { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b < a ? b : a; } };
     struct Mx { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b > a ? b : a; } };
@@ -633,15 +767,16 @@ __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_fused_scope(FS fs, i
         atomicMin((long long *)&mm[0], (long long)lo);
         atomicMax((long long *)&mm[1], (long long)hi);
     }
+    if constexpr (HIST) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < 256; b += ST)
+            if (sh[b]) atomicAdd((unsigned long long *)&mm[MM_WORDS + b], (unsigned long long)sh[b]);
+    }
 }
 
-constexpr int FUSED_PRIV = 1536;   // 28 B x 1536 = 42 KB of CTA-private accumulators (fits the default 48 KB window)
-
-// PRIV (range <= FUSED_PRIV): first-row / sum / count / null-flag slots live in shared memory per CTA and are merged into
-// the device-wide arrays once per CTA; otherwise every row updates the device-wide (L2-resident) arrays directly.
-// first-row claims over a row prefix [r0, r1) only (device-wide path): in the accumulate pass a claim costs one L2 read per
-// row although it can only change anything while a key has not been seen yet; the host extends the prefix until every
-// non-empty slot has been claimed (one short pass for any column whose keys all occur early, e.g. uniform keys).
+// first-row claims over a row prefix [r0, r1) only: in the accumulate pass a claim would cost one L2 read per row although
+// it can only change anything while a key has not been seen yet; the host extends the prefix until every non-empty slot
+// has been claimed (one short pass for any column whose keys all occur early, e.g. uniform keys).
 template <typename FS>
 __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_fused_claim(FS fs, i64 r0, i64 r1, i64 kmin, u64 *first_row) {
     for (i64 i = r0 + (i64)blockIdx.x * THREADS + threadIdx.x; i < r1; i += (i64)gridDim.x * THREADS)
@@ -661,26 +796,15 @@ __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_slot_census(const u6
     if (threadIdx.x == 0) { atomicAdd((unsigned long long *)&mm[3], (unsigned long long)nonempty); atomicAdd((unsigned long long *)&mm[4], (unsigned long long)claimed); }
 }
 
-template <typename FS, bool PRIV>
+// ---- accumulate, strategy 3: device-wide accumulators, two L2 atomics per row
+template <typename FS>
 __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
-k_fused_accum(FS fs, const i64 *__restrict__ val, i64 n, i64 kmin, i64 range, Accums ga) {
+k_fused_accum_l2(FS fs, const i64 *__restrict__ val, i64 n, i64 kmin, Accums a) {
     constexpr int U = 4;
-    extern __shared__ u64 s_fused[];
-    Accums a = ga;
-    if constexpr (PRIV) {
-        a.first_row = s_fused;
-        a.sum = s_fused + range;
-        a.cnt = s_fused + 2 * range;
-        a.has_null = (u32 *)(s_fused + 3 * range);
-        for (i64 s = threadIdx.x; s < range; s += THREADS) { a.first_row[s] = NO_ROW; a.sum[s] = 0; a.cnt[s] = 0; a.has_null[s] = 0; }
-        __syncthreads();
-    }
     const i64 stride = (i64)gridDim.x * THREADS;
-    auto one = [&](i64 i, i64 k, i64 v, bool sel) {
+    auto one = [&](i64 k, i64 v, bool sel) {
         if (!sel) return;
         const i64 s = (i64)((u64)k - (u64)kmin);
-        if constexpr (PRIV) { if (a.first_row[s] > (u64)i) atomicMin((unsigned long long *)&a.first_row[s], (unsigned long long)i); }
-        // (device-wide path: first rows are claimed afterwards on a row prefix, k_fused_claim)
         if (v == NULL_I64) a.has_null[s] = 1u; else atomicAdd((unsigned long long *)a.sum + s, (unsigned long long)v);
         atomicAdd((unsigned long long *)a.cnt + s, 1ULL);
     };
@@ -691,20 +815,160 @@ k_fused_accum(FS fs, const i64 *__restrict__ val, i64 n, i64 kmin, i64 range, Ac
 #pragma unroll
         for (int j = 0; j < U; j++) { k[j] = fs.key(i + j * stride); v[j] = ld_stream(val + i + j * stride); sel[j] = fs.selected(i + j * stride); }
 #pragma unroll
-        for (int j = 0; j < U; j++) one(i + j * stride, k[j], v[j], sel[j]);
+        for (int j = 0; j < U; j++) one(k[j], v[j], sel[j]);
     }
-    for (; i < n; i += stride) one(i, fs.key(i), ld_stream(val + i), fs.selected(i));
-    if constexpr (PRIV) {
+    for (; i < n; i += stride) one(fs.key(i), ld_stream(val + i), fs.selected(i));
+}
+
+// ---- accumulate, strategy 1: range <= KP, CTA-private shared-memory accumulators (3 x 4 B x range, dynamic)
+template <typename FS>
+__global__ void __launch_bounds__(PT, 2)
+k_fused_accum_smem(FS fs, const i64 *__restrict__ val, i64 n, bool vec, i64 kmin, int range, Accums ga) {
+    extern __shared__ u32 s_acc[];
+    const SAcc a{s_acc, s_acc + range, s_acc + 2 * range};
+    sacc_zero(a, range);
+    __syncthreads();
+    const i64 tiles = (n + PTILE - 1) / PTILE;
+    for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        i64 k[8], v[8];
+        bool sel[8];
+        load_tile<PT, true>(fs, val, tile * PTILE, n, vec, k, v, sel);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (sel[j]) sacc_add(a, (u32)((u64)k[j] - (u64)kmin), v[j]);
+    }
+    __syncthreads();
+    sacc_flush(a, range, 0, ga);
+}
+
+// ---- accumulate, strategy 2: partition, then accumulate per partition
+struct PartMeta {          // device copy written by the host after the scope pass
+    u32 off[MAX_PARTS];    // first row of each partition in the partitioned arrays (multiple of 8 rows)
+    u32 cnt[MAX_PARTS];    // rows in each partition
+    u32 ubase[MAX_PARTS + 1];   // prefix of ceil(cnt / PTILE): the accumulate pass's flattened work units
+};
+
+struct ScatterSmem {
+    u64 val[STILE];
+    u16 slot[STILE];
+    u8 part[STILE];
+    u32 cnt[MAX_PARTS], lbase[MAX_PARTS], gbase[MAX_PARTS];
+    u32 wtot[MAX_PARTS / 32];
+    u32 total;
+};
+
+// scatter pass: every tile orders its selected rows by partition in shared memory (a row's rank inside its partition is
+// what the returning shared atomic on the partition's counter hands back), reserves its run in every partition with one
+// global atomic per partition, and writes the runs out contiguously.  Row order inside a partition is not preserved
+// (integer sums and counts do not depend on it; first rows are claimed from the source columns).
+template <typename FS>
+__global__ void __launch_bounds__(ST, 4)
+k_part_scatter(FS fs, const i64 *__restrict__ val, i64 n, bool vec, i64 kbase, u32 *cursor, u64 *__restrict__ out_val, u16 *__restrict__ out_slot) {
+    static_assert(ST == MAX_PARTS, "one thread per partition counter");
+    __shared__ ScatterSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const i64 tiles = (n + STILE - 1) / STILE;
+    sm.cnt[tid] = 0;
+    __syncthreads();
+    for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        i64 k[8], v[8];
+        bool sel[8];
+        load_tile<ST, true>(fs, val, tile * STILE, n, vec, k, v, sel);
+        u32 rel[8], pos[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            rel[j] = sel[j] ? (u32)((u64)k[j] - (u64)kbase) : 0xFFFFFFFFu;
+            const u32 part = sel[j] ? rel[j] >> KP_LOG : 0xFFFFFFFFu;
+            const u32 p0 = __shfl_sync(0xffffffffu, part, 0);
+            if (__all_sync(0xffffffffu, part == p0)) {      // the whole warp step goes to one partition: one atomic
+                u32 b = 0;
+                if (lane == 0 && sel[j]) b = atomicAdd(&sm.cnt[part], 32u);
+                pos[j] = __shfl_sync(0xffffffffu, b, 0) + lane;
+            } else if (sel[j]) pos[j] = atomicAdd(&sm.cnt[part], 1u);
+        }
         __syncthreads();
-        for (i64 s = threadIdx.x; s < range; s += THREADS) {
-            const u64 c = a.cnt[s];
-            if (!c) continue;
-            atomicMin((unsigned long long *)&ga.first_row[s], (unsigned long long)a.first_row[s]);
-            atomicAdd((unsigned long long *)ga.sum + s, (unsigned long long)a.sum[s]);
-            atomicAdd((unsigned long long *)ga.cnt + s, (unsigned long long)c);
-            if (a.has_null[s]) ga.has_null[s] = 1u;
+        const u32 c = sm.cnt[tid];
+        u32 incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) sm.wtot[tid >> 5] = incl;
+        const u32 gb = c ? atomicAdd(&cursor[tid], c) : 0;
+        __syncthreads();
+        u32 before = 0;
+        for (int w = 0; w < (tid >> 5); w++) before += sm.wtot[w];
+        sm.lbase[tid] = before + incl - c;
+        sm.gbase[tid] = gb;
+        sm.cnt[tid] = 0;                                   // for the next tile (no reader left: counts live in registers)
+        if (tid == ST - 1) sm.total = before + incl;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (!sel[j]) continue;
+            const u32 part = rel[j] >> KP_LOG, q = sm.lbase[part] + pos[j];
+            sm.val[q] = (u64)v[j];
+            sm.slot[q] = (u16)(rel[j] & (KP - 1));
+            sm.part[q] = (u8)part;
+        }
+        __syncthreads();
+        const u32 total = sm.total;
+        for (u32 q = tid; q < total; q += ST) {
+            const u32 part = sm.part[q];
+            const u32 g = sm.gbase[part] + (q - sm.lbase[part]);
+            out_val[g] = sm.val[q];
+            out_slot[g] = sm.slot[q];
+        }
+        __syncthreads();
+    }
+}
+
+// accumulate pass: CTA b takes the flattened work units [b*U/G, (b+1)*U/G) (unit = PTILE rows of one partition), keeps the
+// current partition's KP accumulators in shared memory and merges them into the device-wide arrays when the partition changes
+__global__ void __launch_bounds__(PT, 2)
+k_part_accum(const u64 *__restrict__ pv, const u16 *__restrict__ ps, const PartMeta *__restrict__ meta, int P, i64 kbase, i64 kmin, Accums ga) {
+    extern __shared__ u32 s_acc[];
+    const SAcc a{s_acc, s_acc + KP, s_acc + 2 * KP};
+    sacc_zero(a, KP);
+    const u32 U = meta->ubase[P];
+    const u32 u0 = (u32)((u64)blockIdx.x * U / gridDim.x), u1 = (u32)((u64)(blockIdx.x + 1) * U / gridDim.x);
+    int p = 0;
+    while (p + 1 < P && meta->ubase[p + 1] <= u0) p++;
+    __syncthreads();
+    bool dirty = false;
+    for (u32 u = u0; u < u1; u++) {
+        if (meta->ubase[p + 1] <= u) {
+            __syncthreads();
+            if (dirty) sacc_flush(a, KP, (i64)((u64)kbase + (u64)p * KP - (u64)kmin), ga);
+            __syncthreads();
+            dirty = false;
+            while (meta->ubase[p + 1] <= u) p++;
+        }
+        const u32 r0 = (u - meta->ubase[p]) * PTILE, cnt = meta->cnt[p];
+        const u32 rows = cnt - r0 < (u32)PTILE ? cnt - r0 : (u32)PTILE;
+        const u64 base = (u64)meta->off[p] + r0;
+        dirty = true;
+        if (rows == PTILE) {
+            vec16 vv[4];
+            u32 ss[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const u32 q = j * PT + threadIdx.x;
+                vv[j] = ld_stream16(pv + base + 2 * q);
+                ss[j] = __ldcs((const u32 *)(ps + base) + q);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                sacc_add(a, ss[j] & 0xFFFFu, (i64)vv[j].lo);
+                sacc_add(a, ss[j] >> 16, (i64)vv[j].hi);
+            }
+        } else {
+            for (u32 r = threadIdx.x; r < rows; r += PT) sacc_add(a, ps[base + r], (i64)pv[base + r]);
         }
     }
+    __syncthreads();
+    if (dirty) sacc_flush(a, KP, (i64)((u64)kbase + (u64)p * KP - (u64)kmin), ga);
 }
 
 template <typename FS>
@@ -723,27 +987,68 @@ k_fused_emit(FS fs, i64 limit, i64 kmin, Accums a, i64 max_groups, i64 *out_keys
         });
 }
 
+// tuning knobs (environment): RFB_GROUP_STRATEGY = smem | part | l2 forces a strategy where it is applicable;
+// RFB_PART_MIN_ROWS = smallest row count that takes the partitioned strategy
+int group_strategy_forced() {
+    const char *s = getenv("RFB_GROUP_STRATEGY");
+    if (!s) return 0;
+    return !strcmp(s, "smem") ? 1 : (!strcmp(s, "part") ? 2 : (!strcmp(s, "l2") ? 3 : 0));
+}
+i64 part_min_rows() {
+    const char *s = getenv("RFB_PART_MIN_ROWS");
+    return s ? atoll(s) : (1ll << 21);
+}
+
 template <typename FS>
 int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 *out_keys, i64 *out_sums, i64 *out_counts, i64 *groups) {
     i64 *mm = (i64 *)((char *)ctx->d_scratch + 32768);
-    k_scope_init<<<1, 1, 0, ctx->stream>>>(mm);
+    const int forced = group_strategy_forced();
+    const bool part_able = n < 0xFFFF0000ll && (forced == 2 || (forced == 0 && n >= part_min_rows()));   // 32-bit row positions
+    k_fused_scope_init<<<1, 256, 0, ctx->stream>>>(mm);
     RFB_CHECK_LAUNCH(ctx);
     const int grid = rfb_grid_for(ctx, n, THREADS * 4, BLOCKS_PER_SM);
-    k_fused_scope<FS><<<grid, THREADS, 0, ctx->stream>>>(fs, n, mm);
+    const bool vec = fs.vec_ok(val);
+    const int sgrid = rfb_grid_for(ctx, n, STILE, 4);
+    if (part_able) k_fused_scope<FS, true><<<sgrid, ST, 0, ctx->stream>>>(fs, n, vec, mm);
+    else k_fused_scope<FS, false><<<sgrid, ST, 0, ctx->stream>>>(fs, n, vec, mm);
     RFB_CHECK_LAUNCH(ctx);
-    i64 h[2];
-    int rc = d2h_sync(ctx, h, mm, 16);
+    i64 h[MM_WORDS + 256];
+    int rc = d2h_sync(ctx, h, mm, part_able ? sizeof(h) : 16);
     if (rc) return rc;
     if (h[0] > h[1]) { *groups = 0; return RFB_OK; }   // nothing selected
-    const i64 range = (i64)((u64)h[1] - (u64)h[0] + 1);
+    const i64 kmin = h[0], range = (i64)((u64)h[1] - (u64)h[0] + 1);
     if (range <= 0 || range > (1ll << 28)) {
         rfb_set_error("fused group-by: key range %lld is not a dense domain (use rfb_group_i64_dev + rfb_aggr_dev)", (long long)range);
         return RFB_ERR_ARG;
     }
+    const i64 kbase = kmin & ~(i64)(KP - 1);                           // floor to a multiple of KP (two's complement)
+    const i64 P = (i64)(((u64)h[1] - (u64)kbase) >> KP_LOG) + 1;       // partitions of KP consecutive keys
+    int strategy = 3;
+    if (range <= KP && (n >= 65536 || forced == 1)) strategy = 1;
+    else if (part_able && range > KP && P <= MAX_PARTS) strategy = 2;
+    if (forced == 3) strategy = 3;
+
+    PartMeta pm;
+    u64 part_rows = 0;
+    if (strategy == 2) {
+        memset(&pm, 0, sizeof(pm));
+        for (i64 p = 0; p < P; p++) {
+            const u64 c = (u64)h[MM_WORDS + (int)((((u64)kbase >> KP_LOG) + (u64)p) & 255u)];
+            pm.off[p] = (u32)part_rows;
+            pm.cnt[p] = (u32)c;
+            pm.ubase[p + 1] = pm.ubase[p] + (u32)((c + PTILE - 1) / PTILE);
+            part_rows += (c + 7) & ~7ull;
+        }
+        if (part_rows >= 0xFFFFFFF0ull) strategy = 3;
+    }
+
     const i64 tiles_max = (n + scan::RowTile<NUM_J>::TILE - 1) / scan::RowTile<NUM_J>::TILE;
     const size_t b8 = align256((size_t)range * 8), b4 = align256((size_t)range * 4);
+    const size_t acc_bytes = 3 * b8 + b4 + scan::tiles_bytes(tiles_max);
+    const size_t meta_bytes = align256(sizeof(PartMeta)) + align256(MAX_PARTS * 4);
+    const size_t part_bytes = strategy == 2 ? meta_bytes + align256((size_t)part_rows * 8) + align256((size_t)part_rows * 2) : 0;
     void *w;
-    rc = rfb_ensure_work(ctx, 3 * b8 + b4 + scan::tiles_bytes(tiles_max), &w);
+    rc = rfb_ensure_work(ctx, acc_bytes + part_bytes, &w);
     if (rc) return rc;
     Accums a;
     a.first_row = (u64 *)w;
@@ -752,28 +1057,48 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
     a.has_null = (u32 *)((char *)w + 3 * b8);
     RFB_CUDA(cudaMemsetAsync(a.first_row, 0xFF, (size_t)range * 8, ctx->stream));
     RFB_CUDA(cudaMemsetAsync(a.sum, 0, 2 * b8 + b4, ctx->stream));
-    if (range <= FUSED_PRIV && n >= 65536) {
-        k_fused_accum<FS, true><<<grid, THREADS, (size_t)range * 28, ctx->stream>>>(fs, val, n, h[0], range, a);
+    const i64 ptiles = (n + PTILE - 1) / PTILE;
+    const int pgrid = (int)(ptiles < 2ll * ctx->sm_count ? ptiles : 2ll * ctx->sm_count);
+    if (strategy == 1) {
+        const size_t smem = (size_t)range * 12;
+        RFB_CUDA(cudaFuncSetAttribute(k_fused_accum_smem<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, KP * 12));
+        k_fused_accum_smem<FS><<<pgrid, PT, smem, ctx->stream>>>(fs, val, n, vec, kmin, (int)range, a);
+        RFB_CHECK_LAUNCH(ctx);
+    } else if (strategy == 2) {
+        char *pw = (char *)w + acc_bytes;
+        PartMeta *d_meta = (PartMeta *)pw;
+        u32 *cursor = (u32 *)(pw + align256(sizeof(PartMeta)));
+        u64 *pv = (u64 *)(pw + meta_bytes);
+        u16 *ps = (u16 *)(pw + meta_bytes + align256((size_t)part_rows * 8));
+        RFB_CUDA(cudaMemcpyAsync(d_meta, &pm, sizeof(pm), cudaMemcpyHostToDevice, ctx->stream));
+        RFB_CUDA(cudaMemcpyAsync(cursor, pm.off, MAX_PARTS * 4, cudaMemcpyHostToDevice, ctx->stream));
+        k_part_scatter<FS><<<sgrid, ST, 0, ctx->stream>>>(fs, val, n, vec, kbase, cursor, pv, ps);
+        RFB_CHECK_LAUNCH(ctx);
+        RFB_CUDA(cudaFuncSetAttribute(k_part_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, KP * 12));
+        const u32 units = pm.ubase[P];
+        const int agrid = (int)(units < 2u * (u32)ctx->sm_count ? units : 2u * (u32)ctx->sm_count);
+        k_part_accum<<<agrid, PT, KP * 12, ctx->stream>>>(pv, ps, d_meta, (int)P, kbase, kmin, a);
         RFB_CHECK_LAUNCH(ctx);
     } else {
-        k_fused_accum<FS, false><<<grid, THREADS, 0, ctx->stream>>>(fs, val, n, h[0], range, a);
+        k_fused_accum_l2<FS><<<grid, THREADS, 0, ctx->stream>>>(fs, val, n, kmin, a);
         RFB_CHECK_LAUNCH(ctx);
-        i64 r0 = 0, r1 = 32 * range > 65536 ? 32 * range : 65536;
-        while (true) {
-            if (r1 > n) r1 = n;
-            k_fused_claim<FS><<<rfb_grid_for(ctx, r1 - r0, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(fs, r0, r1, h[0], a.first_row);
-            RFB_CHECK_LAUNCH(ctx);
-            if (r1 == n) break;
-            RFB_CUDA(cudaMemsetAsync(mm + 3, 0, 16, ctx->stream));
-            k_slot_census<<<rfb_grid_for(ctx, range, THREADS, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(a.first_row, a.cnt, range, mm);
-            RFB_CHECK_LAUNCH(ctx);
-            i64 census[2];
-            rc = d2h_sync(ctx, census, mm + 3, 16);
-            if (rc) return rc;
-            if (census[0] == census[1]) break;   // every key that occurs has its first row
-            r0 = r1;
-            r1 = r1 * 4;
-        }
+    }
+    // first rows: claimed on a growing row prefix
+    i64 r0 = 0, r1 = 32 * range > 65536 ? 32 * range : 65536;
+    while (true) {
+        if (r1 > n) r1 = n;
+        k_fused_claim<FS><<<rfb_grid_for(ctx, r1 - r0, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(fs, r0, r1, kmin, a.first_row);
+        RFB_CHECK_LAUNCH(ctx);
+        if (r1 == n) break;
+        RFB_CUDA(cudaMemsetAsync(mm + 3, 0, 16, ctx->stream));
+        k_slot_census<<<rfb_grid_for(ctx, range, THREADS, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(a.first_row, a.cnt, range, mm);
+        RFB_CHECK_LAUNCH(ctx);
+        i64 census[2];
+        rc = d2h_sync(ctx, census, mm + 3, 16);
+        if (rc) return rc;
+        if (census[0] == census[1]) break;   // every key that occurs has its first row
+        r0 = r1;
+        r1 = r1 * 4;
     }
     k_max_first<<<rfb_grid_for(ctx, range, THREADS, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(a.first_row, range, mm);
     RFB_CHECK_LAUNCH(ctx);
@@ -784,7 +1109,7 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
     scan::TileCtl ctl;
     rc = scan::prepare_tiles(ctx, (char *)w + 3 * b8 + b4, tiles, ctx->h_count, &ctl);
     if (rc) return rc;
-    k_fused_emit<FS><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(fs, limit, h[0], a, max_groups, out_keys, out_sums, out_counts, ctl);
+    k_fused_emit<FS><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(fs, limit, kmin, a, max_groups, out_keys, out_sums, out_counts, ctl);
     RFB_CHECK_LAUNCH(ctx);
     RFB_CUDA(cudaStreamSynchronize(ctx->stream));
     *groups = *(volatile i64 *)ctx->h_count;

@@ -390,6 +390,62 @@ def test_fused_group_late_first_occurrence(ctx, oracle):
     assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val, wg, wi.groups)[0])
 
 
+@pytest.mark.parametrize("strategy", ["smem", "part", "l2"])
+@pytest.mark.parametrize("key_type", [ob.I64, ob.I32])
+@pytest.mark.parametrize("with_pred", [False, True])
+@pytest.mark.parametrize("n,card,kmin,skew", [
+    (300_007, 3000, -1500, False),         # negative keys; one partition boundary inside the range
+    (1_000_003, 100_000, 17, False),       # config-4 shape: 13 partitions of 8192 keys
+    (1_000_003, 100_000, -8192 * 3 - 5, True),   # skewed (most rows in two keys), partitions of very different sizes
+    (2_500_001, 1_900_000, 5, False),      # ~232 partitions, many slots never hit
+])
+def test_fused_group_strategies(ctx, oracle, monkeypatch, strategy, key_type, with_pred, n, card, kmin, skew):
+    """the three accumulate strategies of the fused group-by (CTA-private shared memory / key-range partitions / L2 atomics)
+    must agree with the oracle bit for bit: wrapping sums of negative and large values (32-bit carry chains in shared
+    memory), sticky nulls, counts, first-occurrence order"""
+    if strategy == "smem" and card > 8192:
+        pytest.skip("shared-memory strategy needs range <= 8192")
+    monkeypatch.setenv("RFB_GROUP_STRATEGY", strategy)
+    r = np.random.default_rng(n + card + (1 if skew else 0))
+    keys64 = r.integers(0, card, n).astype(np.int64)
+    if skew:
+        hot = r.random(n) < 0.8
+        keys64[hot] = np.where(r.random(int(hot.sum())) < 0.5, 3, card - 2)
+    keys64 += kmin
+    val = r.integers(-(1 << 40), 1 << 40, n).astype(np.int64)
+    val[::7] = r.integers(0, 1 << 20, val[::7].shape[0])
+    val[::1013] = np.iinfo(np.int64).max       # sums wrap mod 2^64
+    val[r.random(n) < 0.0002] = ob.NULL_I64
+    keys = keys64.astype(ob.NP_OF[key_type])
+    if with_pred:
+        filt = oracle.where(oracle.cmp(ob.LT, ob.I64, val, ob.I64, 1 << 19))
+        gk, gs, gc = ctx.group_sum_count(key_type, dev(keys), dev(val), card + 5, cmp_op=capi.LT, pred_type=ob.I64, pred=dev(val), k=1 << 19)
+    else:
+        filt = None
+        gk, gs, gc = ctx.group_sum_count(key_type, dev(keys), dev(val), card + 5)
+    wg, wf, wi = oracle.group_i64(keys64, filt)
+    rows = wf if filt is None else filt[wf]
+    assert np.array_equal(host(gk), keys64[rows])
+    assert np.array_equal(host(gs), oracle.aggr(ob.SUM, ob.I64, val, wg, wi.groups, filt)[0])
+    assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val, wg, wi.groups, filt)[0])
+
+
+def test_fused_group_partitioned_unaligned_columns(ctx, oracle, monkeypatch):
+    """columns that start at an odd element (no 16-byte alignment) take the scalar tile loader"""
+    monkeypatch.setenv("RFB_GROUP_STRATEGY", "part")
+    n, card = 400_001, 20_000
+    r = np.random.default_rng(11)
+    keys = r.integers(0, card, n + 1).astype(np.int32)
+    val = r.integers(-1000, 1000, n + 1).astype(np.int64)
+    dk, dv = dev(keys), dev(val)
+    gk, gs, gc = ctx.group_sum_count(ob.I32, dk[1:], dv[1:], card)
+    k64 = keys[1:].astype(np.int64)
+    wg, wf, wi = oracle.group_i64(k64)
+    assert np.array_equal(host(gk), k64[wf])
+    assert np.array_equal(host(gs), oracle.aggr(ob.SUM, ob.I64, val[1:], wg, wi.groups)[0])
+    assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val[1:], wg, wi.groups)[0])
+
+
 def test_fused_group_nothing_selected(ctx):
     keys, val = dev(np.arange(100, dtype=np.int64)), dev(np.arange(100, dtype=np.int64))
     gk, gs, gc = ctx.group_sum_count(ob.I64, keys, val, 10, cmp_op=capi.LT, pred_type=ob.I64, pred=val, k=-5)
