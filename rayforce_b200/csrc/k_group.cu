@@ -642,6 +642,7 @@ template <typename T> static inline bool pair_aligned(const T *p) { return (((ui
 
 template <typename K, typename P, bool HAS_PRED>
 struct FusedSrc {
+    typedef K key_t;
     const K *keys;
     const P *pred;
     PredRange pr;
@@ -723,30 +724,15 @@ __device__ __forceinline__ void sacc_flush(const SAcc &a, int slots, i64 slot0, 
     }
 }
 
-// ---- scope: min/max of the selected keys (+ the histogram of absolute key buckets (key >> KP_LOG) mod 256 that sizes the
-// partitions: with at most 256 partitions every partition owns exactly one bucket)
-constexpr int MM_WORDS = 8, HIST_BINS = 257;   // mm[0..7] = {min, max, limit, nonempty, claimed, -, -, -}, then hist[257]
+// ---- scope: min/max of the selected keys
+constexpr int MM_WORDS = 8;   // mm[0..7] = {min, max, limit, nonempty, claimed, -, -, -}
 __global__ void k_fused_scope_init(i64 *mm) {
-    for (int i = threadIdx.x; i < MM_WORDS + HIST_BINS; i += blockDim.x) mm[i] = i == 0 ? RFB_INF_I64 : (i == 1 ? NULL_I64 : 0);
+    for (int i = threadIdx.x; i < MM_WORDS; i += blockDim.x) mm[i] = i == 0 ? RFB_INF_I64 : (i == 1 ? NULL_I64 : 0);
 }
 
-// rank-free counting: one shared-memory atomic per row, except that a warp step whose 32 rows all fall into the same
-// bucket (heavily skewed keys) issues a single one.  (__match_any_sync-based aggregation was measured first: the MATCH
-// instruction runs on the ADU pipe and bounded both this kernel and the scatter pass, profiles/r01_part_groupby.txt)
-__device__ __forceinline__ void hist_add(u32 *sh, u32 b) {
-    const u32 b0 = __shfl_sync(0xffffffffu, b, 0);
-    if (__all_sync(0xffffffffu, b == b0)) { if ((threadIdx.x & 31) == 0) atomicAdd(&sh[b0], 32u); }
-    else atomicAdd(&sh[b], 1u);
-}
-
-template <typename FS, bool HIST>
+template <typename FS>
 __global__ void __launch_bounds__(ST, 4) k_fused_scope(FS fs, i64 n, bool vec, i64 *mm) {
     __shared__ i64 red[32];
-    __shared__ u32 sh[HIST_BINS];
-    if constexpr (HIST) {
-        for (int b = threadIdx.x; b < HIST_BINS; b += ST) sh[b] = 0;
-        __syncthreads();
-    }
     i64 lo = RFB_INF_I64, hi = NULL_I64;
     const i64 tiles = (n + STILE - 1) / STILE;
     for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -754,10 +740,8 @@ __global__ void __launch_bounds__(ST, 4) k_fused_scope(FS fs, i64 n, bool vec, i
         bool sel[8];
         load_tile<ST, false>(fs, nullptr, tile * STILE, n, vec, k, v, sel);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < 8; j++)
             if (sel[j]) { lo = k[j] < lo ? k[j] : lo; hi = k[j] > hi ? k[j] : hi; }
-            if constexpr (HIST) hist_add(sh, sel[j] ? (u32)(((u64)k[j] >> KP_LOG) & 255u) : 256u);
-        }
     }
     struct Mn { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b < a ? b : a; } };
     struct Mx { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b > a ? b : a; } };
@@ -766,11 +750,6 @@ __global__ void __launch_bounds__(ST, 4) k_fused_scope(FS fs, i64 n, bool vec, i
     if (threadIdx.x == 0) {
         atomicMin((long long *)&mm[0], (long long)lo);
         atomicMax((long long *)&mm[1], (long long)hi);
-    }
-    if constexpr (HIST) {
-        __syncthreads();
-        for (int b = threadIdx.x; b < 256; b += ST)
-            if (sh[b]) atomicAdd((unsigned long long *)&mm[MM_WORDS + b], (unsigned long long)sh[b]);
     }
 }
 
@@ -842,45 +821,69 @@ k_fused_accum_smem(FS fs, const i64 *__restrict__ val, i64 n, bool vec, i64 kmin
 }
 
 // ---- accumulate, strategy 2: partition, then accumulate per partition
-struct PartMeta {          // device copy written by the host after the scope pass
-    u32 off[MAX_PARTS];    // first row of each partition in the partitioned arrays (multiple of 8 rows)
-    u32 cnt[MAX_PARTS];    // rows in each partition
-    u32 ubase[MAX_PARTS + 1];   // prefix of ceil(cnt / PTILE): the accumulate pass's flattened work units
+//
+// A row's partition is its ABSOLUTE key bucket (key >> KP_LOG) mod 256 and its slot the low KP_LOG key bits, so the scatter
+// pass needs no key bounds: it computes min/max itself, and the partitioning is valid iff the keys turn out to span at most
+// 256 buckets (checked afterwards; a row sample decides beforehand whether it is worth trying).  Partition sizes are not
+// known in advance either: partitioned rows live in blocks of PB rows handed out on demand.  cursor[b] counts the rows of
+// bucket b; the tile whose run contains the first row of a block allocates it (one atomic on a block counter) and publishes
+// it in the block table bt[b][i]; tiles that write into a block they did not allocate wait for that word.  The allocator
+// has already passed its cursor atomic and publishes before it waits for anything itself, so the wait cannot deadlock.
+constexpr int PB_LOG = 16, PB = 1 << PB_LOG;   // rows per block; a multiple of PTILE, so an accumulate unit never straddles blocks
+
+struct PartStore {
+    u32 *cursor;       // [MAX_PARTS] rows per bucket
+    u32 *next_block;   // blocks handed out so far
+    u32 *bt;           // [MAX_PARTS][bt_stride] physical block + 1 (0 = not yet allocated)
+    u32 bt_stride;
+    u64 *val;          // [blocks * PB]
+    u16 *slot;         // [blocks * PB]
 };
+
+__device__ __forceinline__ u32 ld_relaxed_u32(const u32 *p) {
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(u32 *p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 struct ScatterSmem {
     u64 val[STILE];
-    u16 slot[STILE];
-    u8 part[STILE];
-    u32 cnt[MAX_PARTS], lbase[MAX_PARTS], gbase[MAX_PARTS];
+    u32 pk[STILE];               // bucket << KP_LOG | slot
+    uint4 desc[MAX_PARTS];       // per bucket: {x: physical - local offset before the block boundary, y: first local index past it, z: offset after it, w: local base}
+    u32 cnt[MAX_PARTS];
     u32 wtot[MAX_PARTS / 32];
     u32 total;
+    i64 red[32];
 };
 
-// scatter pass: every tile orders its selected rows by partition in shared memory (a row's rank inside its partition is
-// what the returning shared atomic on the partition's counter hands back), reserves its run in every partition with one
-// global atomic per partition, and writes the runs out contiguously.  Row order inside a partition is not preserved
-// (integer sums and counts do not depend on it; first rows are claimed from the source columns).
+// scatter pass: every tile orders its selected rows by bucket in shared memory (a row's rank inside its bucket is what the
+// returning shared atomic on the bucket's counter hands back), reserves its run in every bucket with one global atomic per
+// bucket, and writes the runs out contiguously.  Row order inside a bucket is not preserved (integer sums and counts do
+// not depend on it; first rows are claimed from the source columns).
 template <typename FS>
 __global__ void __launch_bounds__(ST, 4)
-k_part_scatter(FS fs, const i64 *__restrict__ val, i64 n, bool vec, i64 kbase, u32 *cursor, u64 *__restrict__ out_val, u16 *__restrict__ out_slot) {
-    static_assert(ST == MAX_PARTS, "one thread per partition counter");
+k_part_scatter(FS fs, const i64 *__restrict__ val, i64 n, bool vec, PartStore ps, i64 *mm) {
+    static_assert(ST == MAX_PARTS, "one thread per bucket counter");
     __shared__ ScatterSmem sm;
     const int tid = threadIdx.x, lane = tid & 31;
     const i64 tiles = (n + STILE - 1) / STILE;
+    typedef typename FS::key_t KT;   // running min/max in the key column's own width (register pressure)
+    KT lo = sizeof(KT) == 4 ? (KT)0x7FFFFFFF : (KT)RFB_INF_I64, hi = sizeof(KT) == 4 ? (KT)NULL_I32 : (KT)NULL_I64;
     sm.cnt[tid] = 0;
     __syncthreads();
     for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         i64 k[8], v[8];
         bool sel[8];
         load_tile<ST, true>(fs, val, tile * STILE, n, vec, k, v, sel);
-        u32 rel[8], pos[8];
+        u32 pk[8], pos[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            rel[j] = sel[j] ? (u32)((u64)k[j] - (u64)kbase) : 0xFFFFFFFFu;
-            const u32 part = sel[j] ? rel[j] >> KP_LOG : 0xFFFFFFFFu;
+            if (sel[j]) { lo = (KT)k[j] < lo ? (KT)k[j] : lo; hi = (KT)k[j] > hi ? (KT)k[j] : hi; }
+            pk[j] = sel[j] ? (u32)((u64)k[j] & ((1u << (KP_LOG + 8)) - 1u)) : 0xFFFFFFFFu;
+            const u32 part = sel[j] ? pk[j] >> KP_LOG : 0xFFFFFFFFu;
             const u32 p0 = __shfl_sync(0xffffffffu, part, 0);
-            if (__all_sync(0xffffffffu, part == p0)) {      // the whole warp step goes to one partition: one atomic
+            if (__all_sync(0xffffffffu, part == p0)) {      // the whole warp step goes to one bucket: one atomic
                 u32 b = 0;
                 if (lane == 0 && sel[j]) b = atomicAdd(&sm.cnt[part], 32u);
                 pos[j] = __shfl_sync(0xffffffffu, b, 0) + lane;
@@ -895,59 +898,126 @@ k_part_scatter(FS fs, const i64 *__restrict__ val, i64 n, bool vec, i64 kbase, u
             if (lane >= d) incl += o;
         }
         if (lane == 31) sm.wtot[tid >> 5] = incl;
-        const u32 gb = c ? atomicAdd(&cursor[tid], c) : 0;
+        // reserve [start, start + c) of bucket `tid`, allocate the block(s) that begin inside the run, look up the two
+        // blocks the run can touch
+        u32 start = 0, phys0 = 0, phys1 = 0;
+        if (c) {
+            start = atomicAdd(&ps.cursor[tid], c);
+            const u32 b0 = start >> PB_LOG, b1 = (start + c - 1) >> PB_LOG;
+            u32 *row = ps.bt + (size_t)tid * ps.bt_stride;
+            if ((start & (PB - 1)) == 0) { phys0 = atomicAdd(ps.next_block, 1u) + 1; st_relaxed_u32(row + b0, phys0); }
+            if (b1 != b0) { phys1 = atomicAdd(ps.next_block, 1u) + 1; st_relaxed_u32(row + b1, phys1); }
+            while (!phys0) phys0 = ld_relaxed_u32(row + b0);
+            if (b1 == b0) phys1 = phys0;
+        }
         __syncthreads();
         u32 before = 0;
         for (int w = 0; w < (tid >> 5); w++) before += sm.wtot[w];
-        sm.lbase[tid] = before + incl - c;
-        sm.gbase[tid] = gb;
-        sm.cnt[tid] = 0;                                   // for the next tile (no reader left: counts live in registers)
+        const u32 lbase = before + incl - c;
+        const u32 in_block = start & (PB - 1), room = PB - in_block;           // rows left in the first block
+        uint4 d;
+        d.x = (phys0 - 1) * (u32)PB + in_block - lbase;
+        d.y = lbase + room;
+        d.z = (phys1 - 1) * (u32)PB - (lbase + room);
+        d.w = lbase;
+        sm.desc[tid] = d;
+        sm.cnt[tid] = 0;                                   // for the next tile (this tile's counts live in registers now)
         if (tid == ST - 1) sm.total = before + incl;
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             if (!sel[j]) continue;
-            const u32 part = rel[j] >> KP_LOG, q = sm.lbase[part] + pos[j];
+            const u32 q = sm.desc[pk[j] >> KP_LOG].w + pos[j];
             sm.val[q] = (u64)v[j];
-            sm.slot[q] = (u16)(rel[j] & (KP - 1));
-            sm.part[q] = (u8)part;
+            sm.pk[q] = pk[j];
         }
         __syncthreads();
         const u32 total = sm.total;
-        for (u32 q = tid; q < total; q += ST) {
-            const u32 part = sm.part[q];
-            const u32 g = sm.gbase[part] + (q - sm.lbase[part]);
-            out_val[g] = sm.val[q];
-            out_slot[g] = sm.slot[q];
+#pragma unroll
+        for (int half = 0; half < 4; half++) {             // 2 independent elements per step: the shared-memory lookups overlap
+            u32 w[2];
+            u64 vv[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const u32 q = (half * 2 + j) * ST + tid;
+                if (q < total) { w[j] = sm.pk[q]; vv[j] = sm.val[q]; }
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const u32 q = (half * 2 + j) * ST + tid;
+                if (q < total) {
+                    const uint4 dd = sm.desc[w[j] >> KP_LOG];
+                    const u32 g = q + (q < dd.y ? dd.x : dd.z);
+                    ps.val[g] = vv[j];
+                    ps.slot[g] = (u16)(w[j] & (KP - 1));
+                }
+            }
         }
         __syncthreads();
     }
+    struct Mn { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b < a ? b : a; } };
+    struct Mx { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b > a ? b : a; } };
+    // (nothing selected: lo > hi in either width, which is all the host tests)
+    const i64 lo64 = block_reduce<i64>((i64)lo, Mn(), RFB_INF_I64, sm.red);
+    const i64 hi64 = block_reduce<i64>((i64)hi, Mx(), NULL_I64, sm.red);
+    if (tid == 0) {
+        atomicMin((long long *)&mm[0], (long long)lo64);
+        atomicMax((long long *)&mm[1], (long long)hi64);
+    }
 }
 
-// accumulate pass: CTA b takes the flattened work units [b*U/G, (b+1)*U/G) (unit = PTILE rows of one partition), keeps the
-// current partition's KP accumulators in shared memory and merges them into the device-wide arrays when the partition changes
+// accumulate pass: partition p = bucket ((kbase >> KP_LOG) + p) mod 256.  CTA b takes the flattened work units
+// [b*U/G, (b+1)*U/G) (unit = PTILE consecutive rows of one partition), keeps the current partition's KP accumulators in
+// shared memory and merges them into the device-wide arrays when the partition changes
 __global__ void __launch_bounds__(PT, 2)
-k_part_accum(const u64 *__restrict__ pv, const u16 *__restrict__ ps, const PartMeta *__restrict__ meta, int P, i64 kbase, i64 kmin, Accums ga) {
+k_part_accum(PartStore ps, int P, i64 kbase, i64 kmin, Accums ga) {
     extern __shared__ u32 s_acc[];
+    __shared__ u32 s_cnt[MAX_PARTS], s_ubase[MAX_PARTS + 1], s_wtot[MAX_PARTS / 32];
     const SAcc a{s_acc, s_acc + KP, s_acc + 2 * KP};
     sacc_zero(a, KP);
-    const u32 U = meta->ubase[P];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const u32 bucket0 = (u32)(((u64)kbase >> KP_LOG) & 255u);
+    u32 c = 0, units = 0, incl = 0;
+    if (tid < MAX_PARTS) {
+        c = tid < P ? ps.cursor[(bucket0 + tid) & 255u] : 0;
+        s_cnt[tid] = c;
+        units = (c + PTILE - 1) / PTILE;
+        incl = units;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_wtot[tid >> 5] = incl;
+    }
+    __syncthreads();
+    if (tid < MAX_PARTS) {
+        u32 before = 0;
+        for (int w = 0; w < (tid >> 5); w++) before += s_wtot[w];
+        s_ubase[tid + 1] = before + incl;
+        if (tid == 0) s_ubase[0] = 0;
+    }
+    __syncthreads();
+    const u32 U = s_ubase[P];
     const u32 u0 = (u32)((u64)blockIdx.x * U / gridDim.x), u1 = (u32)((u64)(blockIdx.x + 1) * U / gridDim.x);
     int p = 0;
-    while (p + 1 < P && meta->ubase[p + 1] <= u0) p++;
-    __syncthreads();
+    while (p + 1 < P && s_ubase[p + 1] <= u0) p++;
     bool dirty = false;
+    u32 have_blk = 0xFFFFFFFFu, phys = 0;   // block-table entry of the (partition, block) the previous unit was in
     for (u32 u = u0; u < u1; u++) {
-        if (meta->ubase[p + 1] <= u) {
+        if (s_ubase[p + 1] <= u) {
             __syncthreads();
             if (dirty) sacc_flush(a, KP, (i64)((u64)kbase + (u64)p * KP - (u64)kmin), ga);
             __syncthreads();
             dirty = false;
-            while (meta->ubase[p + 1] <= u) p++;
+            while (s_ubase[p + 1] <= u) p++;
+            have_blk = 0xFFFFFFFFu;
         }
-        const u32 r0 = (u - meta->ubase[p]) * PTILE, cnt = meta->cnt[p];
+        const u32 r0 = (u - s_ubase[p]) * PTILE, cnt = s_cnt[p];
         const u32 rows = cnt - r0 < (u32)PTILE ? cnt - r0 : (u32)PTILE;
-        const u64 base = (u64)meta->off[p] + r0;
+        const u32 bucket = (bucket0 + p) & 255u;
+        if ((r0 >> PB_LOG) != have_blk) { have_blk = r0 >> PB_LOG; phys = ps.bt[(size_t)bucket * ps.bt_stride + have_blk] - 1; }
+        const u64 base = (u64)phys * PB + (r0 & (PB - 1));
         dirty = true;
         if (rows == PTILE) {
             vec16 vv[4];
@@ -955,8 +1025,8 @@ k_part_accum(const u64 *__restrict__ pv, const u16 *__restrict__ ps, const PartM
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const u32 q = j * PT + threadIdx.x;
-                vv[j] = ld_stream16(pv + base + 2 * q);
-                ss[j] = __ldcs((const u32 *)(ps + base) + q);
+                vv[j] = ld_stream16(ps.val + base + 2 * q);
+                ss[j] = __ldcs((const u32 *)(ps.slot + base) + q);
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -964,11 +1034,28 @@ k_part_accum(const u64 *__restrict__ pv, const u16 *__restrict__ ps, const PartM
                 sacc_add(a, ss[j] >> 16, (i64)vv[j].hi);
             }
         } else {
-            for (u32 r = threadIdx.x; r < rows; r += PT) sacc_add(a, ps[base + r], (i64)pv[base + r]);
+            for (u32 r = threadIdx.x; r < rows; r += PT) sacc_add(a, ps.slot[base + r], (i64)ps.val[base + r]);
         }
     }
     __syncthreads();
     if (dirty) sacc_flush(a, KP, (i64)((u64)kbase + (u64)p * KP - (u64)kmin), ga);
+}
+
+// min/max of the selected keys of the rows [r0, r1): the sample that decides whether the partitioned strategy is tried
+template <typename FS>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_fused_scope_rows(FS fs, i64 r0, i64 r1, i64 *mm) {
+    __shared__ i64 red[32];
+    i64 lo = RFB_INF_I64, hi = NULL_I64;
+    for (i64 i = r0 + (i64)blockIdx.x * THREADS + threadIdx.x; i < r1; i += (i64)gridDim.x * THREADS)
+        if (fs.selected(i)) { const i64 k = fs.key(i); lo = k < lo ? k : lo; hi = k > hi ? k : hi; }
+    struct Mn { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b < a ? b : a; } };
+    struct Mx { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b > a ? b : a; } };
+    lo = block_reduce<i64>(lo, Mn(), RFB_INF_I64, red);
+    hi = block_reduce<i64>(hi, Mx(), NULL_I64, red);
+    if (threadIdx.x == 0) {
+        atomicMin((long long *)&mm[0], (long long)lo);
+        atomicMax((long long *)&mm[1], (long long)hi);
+    }
 }
 
 template <typename FS>
@@ -1003,17 +1090,65 @@ template <typename FS>
 int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 *out_keys, i64 *out_sums, i64 *out_counts, i64 *groups) {
     i64 *mm = (i64 *)((char *)ctx->d_scratch + 32768);
     const int forced = group_strategy_forced();
-    const bool part_able = n < 0xFFFF0000ll && (forced == 2 || (forced == 0 && n >= part_min_rows()));   // 32-bit row positions
-    k_fused_scope_init<<<1, 256, 0, ctx->stream>>>(mm);
-    RFB_CHECK_LAUNCH(ctx);
+    const bool part_able = n < 0xF0000000ll && (forced == 2 || (forced == 0 && n >= part_min_rows()));   // 32-bit row positions
     const int grid = rfb_grid_for(ctx, n, THREADS * 4, BLOCKS_PER_SM);
-    const bool vec = fs.vec_ok(val);
     const int sgrid = rfb_grid_for(ctx, n, STILE, 4);
-    if (part_able) k_fused_scope<FS, true><<<sgrid, ST, 0, ctx->stream>>>(fs, n, vec, mm);
-    else k_fused_scope<FS, false><<<sgrid, ST, 0, ctx->stream>>>(fs, n, vec, mm);
-    RFB_CHECK_LAUNCH(ctx);
-    i64 h[MM_WORDS + 256];
-    int rc = d2h_sync(ctx, h, mm, part_able ? sizeof(h) : 16);
+    const bool vec = fs.vec_ok(val);
+    const i64 tiles_max = (n + scan::RowTile<NUM_J>::TILE - 1) / scan::RowTile<NUM_J>::TILE;
+    auto parts_of = [](i64 kmin, i64 kmax) { return (i64)(((u64)kmax - (u64)(kmin & ~(i64)(KP - 1))) >> KP_LOG) + 1; };
+    i64 h[2];
+    int rc;
+    bool have_scope = false, scattered = false;
+    void *w = nullptr;
+    PartStore ps{};
+    // workspace of the partitioned strategy: accumulators for the largest range it accepts, then the block store
+    const i64 max_range = (i64)MAX_PARTS * KP;
+    const size_t pb8 = align256((size_t)max_range * 8), pb4 = align256((size_t)max_range * 4);
+    const size_t p_acc_bytes = 3 * pb8 + pb4 + scan::tiles_bytes(tiles_max);
+    if (part_able) {
+        // 1. sample: three row windows; only a key range that needs more than one partition and fits MAX_PARTS is worth a scatter
+        k_fused_scope_init<<<1, 32, 0, ctx->stream>>>(mm);
+        RFB_CHECK_LAUNCH(ctx);
+        const i64 win = 65536;
+        const i64 starts[3] = {0, n / 2 > win ? n / 2 : 0, n > win ? n - win : 0};
+        for (int s = 0; s < 3; s++) {
+            const i64 r0 = starts[s], r1 = r0 + win < n ? r0 + win : n;
+            k_fused_scope_rows<FS><<<64, THREADS, 0, ctx->stream>>>(fs, r0, r1, mm);
+            RFB_CHECK_LAUNCH(ctx);
+        }
+        rc = d2h_sync(ctx, h, mm, 16);
+        if (rc) return rc;
+        const bool try_part = h[0] <= h[1] && (forced == 2 || (i64)((u64)h[1] - (u64)h[0]) >= KP) && (u64)h[1] - (u64)h[0] < (u64)max_range &&
+                              parts_of(h[0], h[1]) <= MAX_PARTS;
+        if (try_part) {
+            const u32 blocks = (u32)((n + PB - 1) / PB) + MAX_PARTS + 1;
+            const u32 bt_stride = (u32)((n + PB - 1) / PB) + 1;
+            const size_t bt_bytes = align256((size_t)MAX_PARTS * bt_stride * 4);
+            const size_t ctl_bytes = align256((MAX_PARTS + 1) * 4);
+            rc = rfb_ensure_work(ctx, p_acc_bytes + ctl_bytes + bt_bytes + (size_t)blocks * PB * 10, &w);
+            if (rc) return rc;
+            char *pw = (char *)w + p_acc_bytes;
+            ps.cursor = (u32 *)pw;
+            ps.next_block = ps.cursor + MAX_PARTS;
+            ps.bt = (u32 *)(pw + ctl_bytes);
+            ps.bt_stride = bt_stride;
+            ps.val = (u64 *)(pw + ctl_bytes + bt_bytes);
+            ps.slot = (u16 *)(pw + ctl_bytes + bt_bytes + (size_t)blocks * PB * 8);
+            RFB_CUDA(cudaMemsetAsync(pw, 0, ctl_bytes + bt_bytes, ctx->stream));
+            k_fused_scope_init<<<1, 32, 0, ctx->stream>>>(mm);
+            RFB_CHECK_LAUNCH(ctx);
+            k_part_scatter<FS><<<sgrid, ST, 0, ctx->stream>>>(fs, val, n, vec, ps, mm);
+            RFB_CHECK_LAUNCH(ctx);
+            have_scope = scattered = true;
+        }
+    }
+    if (!have_scope) {
+        k_fused_scope_init<<<1, 32, 0, ctx->stream>>>(mm);
+        RFB_CHECK_LAUNCH(ctx);
+        k_fused_scope<FS><<<sgrid, ST, 0, ctx->stream>>>(fs, n, vec, mm);
+        RFB_CHECK_LAUNCH(ctx);
+    }
+    rc = d2h_sync(ctx, h, mm, 16);
     if (rc) return rc;
     if (h[0] > h[1]) { *groups = 0; return RFB_OK; }   // nothing selected
     const i64 kmin = h[0], range = (i64)((u64)h[1] - (u64)h[0] + 1);
@@ -1021,63 +1156,43 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
         rfb_set_error("fused group-by: key range %lld is not a dense domain (use rfb_group_i64_dev + rfb_aggr_dev)", (long long)range);
         return RFB_ERR_ARG;
     }
-    const i64 kbase = kmin & ~(i64)(KP - 1);                           // floor to a multiple of KP (two's complement)
-    const i64 P = (i64)(((u64)h[1] - (u64)kbase) >> KP_LOG) + 1;       // partitions of KP consecutive keys
+    const i64 kbase = kmin & ~(i64)(KP - 1);            // floor to a multiple of KP (two's complement)
+    const i64 P = parts_of(kmin, h[1]);                 // partitions of KP consecutive keys
     int strategy = 3;
     if (range <= KP && (n >= 65536 || forced == 1)) strategy = 1;
-    else if (part_able && range > KP && P <= MAX_PARTS) strategy = 2;
+    else if (scattered && P <= MAX_PARTS) strategy = 2;
     if (forced == 3) strategy = 3;
 
-    PartMeta pm;
-    u64 part_rows = 0;
-    if (strategy == 2) {
-        memset(&pm, 0, sizeof(pm));
-        for (i64 p = 0; p < P; p++) {
-            const u64 c = (u64)h[MM_WORDS + (int)((((u64)kbase >> KP_LOG) + (u64)p) & 255u)];
-            pm.off[p] = (u32)part_rows;
-            pm.cnt[p] = (u32)c;
-            pm.ubase[p + 1] = pm.ubase[p] + (u32)((c + PTILE - 1) / PTILE);
-            part_rows += (c + 7) & ~7ull;
-        }
-        if (part_rows >= 0xFFFFFFF0ull) strategy = 3;
+    const size_t b8 = strategy == 2 ? pb8 : align256((size_t)range * 8), b4 = strategy == 2 ? pb4 : align256((size_t)range * 4);
+    if (!scattered) {
+        rc = rfb_ensure_work(ctx, 3 * b8 + b4 + scan::tiles_bytes(tiles_max), &w);
+        if (rc) return rc;
     }
-
-    const i64 tiles_max = (n + scan::RowTile<NUM_J>::TILE - 1) / scan::RowTile<NUM_J>::TILE;
-    const size_t b8 = align256((size_t)range * 8), b4 = align256((size_t)range * 4);
-    const size_t acc_bytes = 3 * b8 + b4 + scan::tiles_bytes(tiles_max);
-    const size_t meta_bytes = align256(sizeof(PartMeta)) + align256(MAX_PARTS * 4);
-    const size_t part_bytes = strategy == 2 ? meta_bytes + align256((size_t)part_rows * 8) + align256((size_t)part_rows * 2) : 0;
-    void *w;
-    rc = rfb_ensure_work(ctx, acc_bytes + part_bytes, &w);
-    if (rc) return rc;
     Accums a;
     a.first_row = (u64 *)w;
     a.sum = (u64 *)((char *)w + b8);
     a.cnt = (u64 *)((char *)w + 2 * b8);
     a.has_null = (u32 *)((char *)w + 3 * b8);
+    if (scattered && strategy != 2) {   // the sample misjudged the range: the accumulator layout of the other strategies must fit
+        if (3 * align256((size_t)range * 8) + align256((size_t)range * 4) + scan::tiles_bytes(tiles_max) > ctx->work_bytes) {
+            rc = rfb_ensure_work(ctx, 3 * b8 + b4 + scan::tiles_bytes(tiles_max), &w);
+            if (rc) return rc;
+            a.first_row = (u64 *)w; a.sum = (u64 *)((char *)w + b8); a.cnt = (u64 *)((char *)w + 2 * b8); a.has_null = (u32 *)((char *)w + 3 * b8);
+        }
+    }
     RFB_CUDA(cudaMemsetAsync(a.first_row, 0xFF, (size_t)range * 8, ctx->stream));
-    RFB_CUDA(cudaMemsetAsync(a.sum, 0, 2 * b8 + b4, ctx->stream));
-    const i64 ptiles = (n + PTILE - 1) / PTILE;
-    const int pgrid = (int)(ptiles < 2ll * ctx->sm_count ? ptiles : 2ll * ctx->sm_count);
+    RFB_CUDA(cudaMemsetAsync(a.sum, 0, (size_t)range * 8, ctx->stream));
+    RFB_CUDA(cudaMemsetAsync(a.cnt, 0, (size_t)range * 8, ctx->stream));
+    RFB_CUDA(cudaMemsetAsync(a.has_null, 0, (size_t)range * 4, ctx->stream));
     if (strategy == 1) {
-        const size_t smem = (size_t)range * 12;
+        const i64 ptiles = (n + PTILE - 1) / PTILE;
+        const int pgrid = (int)(ptiles < 2ll * ctx->sm_count ? ptiles : 2ll * ctx->sm_count);
         RFB_CUDA(cudaFuncSetAttribute(k_fused_accum_smem<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, KP * 12));
-        k_fused_accum_smem<FS><<<pgrid, PT, smem, ctx->stream>>>(fs, val, n, vec, kmin, (int)range, a);
+        k_fused_accum_smem<FS><<<pgrid, PT, (size_t)range * 12, ctx->stream>>>(fs, val, n, vec, kmin, (int)range, a);
         RFB_CHECK_LAUNCH(ctx);
     } else if (strategy == 2) {
-        char *pw = (char *)w + acc_bytes;
-        PartMeta *d_meta = (PartMeta *)pw;
-        u32 *cursor = (u32 *)(pw + align256(sizeof(PartMeta)));
-        u64 *pv = (u64 *)(pw + meta_bytes);
-        u16 *ps = (u16 *)(pw + meta_bytes + align256((size_t)part_rows * 8));
-        RFB_CUDA(cudaMemcpyAsync(d_meta, &pm, sizeof(pm), cudaMemcpyHostToDevice, ctx->stream));
-        RFB_CUDA(cudaMemcpyAsync(cursor, pm.off, MAX_PARTS * 4, cudaMemcpyHostToDevice, ctx->stream));
-        k_part_scatter<FS><<<sgrid, ST, 0, ctx->stream>>>(fs, val, n, vec, kbase, cursor, pv, ps);
-        RFB_CHECK_LAUNCH(ctx);
         RFB_CUDA(cudaFuncSetAttribute(k_part_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, KP * 12));
-        const u32 units = pm.ubase[P];
-        const int agrid = (int)(units < 2u * (u32)ctx->sm_count ? units : 2u * (u32)ctx->sm_count);
-        k_part_accum<<<agrid, PT, KP * 12, ctx->stream>>>(pv, ps, d_meta, (int)P, kbase, kmin, a);
+        k_part_accum<<<2 * ctx->sm_count, PT, KP * 12, ctx->stream>>>(ps, (int)P, kbase, kmin, a);
         RFB_CHECK_LAUNCH(ctx);
     } else {
         k_fused_accum_l2<FS><<<grid, THREADS, 0, ctx->stream>>>(fs, val, n, kmin, a);

@@ -430,6 +430,25 @@ def test_fused_group_strategies(ctx, oracle, monkeypatch, strategy, key_type, wi
     assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val, wg, wi.groups, filt)[0])
 
 
+@pytest.mark.parametrize("outlier", [5_000_000, 9000])
+def test_fused_group_sample_misjudges_the_key_range(ctx, oracle, monkeypatch, outlier):
+    """the partitioned strategy is chosen from a row sample (head / middle / tail windows).  Keys outside the windows can
+    widen the range beyond what it can hold (-> the scatter is discarded, device-wide atomics take over) or beyond what
+    the sample promised (-> more partitions than expected): the result must not depend on the guess"""
+    monkeypatch.setenv("RFB_PART_MIN_ROWS", "1000")
+    n = 600_011
+    r = np.random.default_rng(outlier)
+    keys = r.integers(0, 20_000 if outlier > 100_000 else 5000, n).astype(np.int64)
+    keys[100_000] = outlier
+    keys[400_000] = -outlier
+    val = r.integers(-5000, 5000, n).astype(np.int64)
+    gk, gs, gc = ctx.group_sum_count(ob.I64, dev(keys), dev(val), 30_000)
+    wg, wf, wi = oracle.group_i64(keys)
+    assert np.array_equal(host(gk), keys[wf])
+    assert np.array_equal(host(gs), oracle.aggr(ob.SUM, ob.I64, val, wg, wi.groups)[0])
+    assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val, wg, wi.groups)[0])
+
+
 def test_fused_group_partitioned_unaligned_columns(ctx, oracle, monkeypatch):
     """columns that start at an odd element (no 16-byte alignment) take the scalar tile loader"""
     monkeypatch.setenv("RFB_GROUP_STRATEGY", "part")
