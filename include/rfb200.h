@@ -58,7 +58,7 @@ enum { RFB_ADD = 0, RFB_SUB = 1, RFB_MUL = 2, RFB_DIV = 3, RFB_FDIV = 4, RFB_MOD
 enum { RFB_ROUND = 0, RFB_FLOOR = 1, RFB_CEIL = 2 };
 
 /* grouped aggregates: aggr_sum/min/max/count/avg (core/aggr.c:1078-1453, 2013-2133) */
-enum { RFB_A_SUM = 0, RFB_A_MIN = 1, RFB_A_MAX = 2, RFB_A_COUNT = 3, RFB_A_AVG = 4 };
+enum { RFB_A_SUM = 0, RFB_A_MIN = 1, RFB_A_MAX = 2, RFB_A_COUNT = 3, RFB_A_AVG = 4, RFB_A_MED = 5, RFB_A_DEV = 6 };
 
 /* group index kinds (core/index.h:31-36) */
 enum { RFB_INDEX_IDS = 0, RFB_INDEX_SHIFT = 1 };
@@ -226,8 +226,9 @@ int rfb_group_i64_dev(rfb_ctx_t *ctx, const int64_t *keys, const int64_t *filter
 
 /* index_group_list, perfect-hash key-fusion path (core/index.c:2308-2424): groups rows by the TUPLE of `ncols` (<= 8) I64-kind
  * key columns, numbered by first occurrence like the single-key index.  Every column's scope is taken, the tuple is fused
- * into one key sum_c (col_c - min_c) * stride_c and grouped by rfb_group_i64_dev.  RFB_ERR_ARG when the product of the key
- * ranges does not fit 62 bits (the reference then hashes rows and radix-partitions, core/index.c:2556-2729: not built).
+ * into one key sum_c (col_c - min_c) * stride_c and grouped by rfb_group_i64_dev.  When the product of the key
+ * ranges does not fit 62 bits the tuples are grouped by row hash instead (the reference hashes rows and radix-partitions,
+ * core/index.c:2556-2729; the device probes one open-addressing table of representative rows): info->dense = 0, min/max unset.
  * Outputs as rfb_group_i64_dev (info->min/max/range describe the fused key). */
 int rfb_group_keys_i64_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const *cols, const int64_t *filter, int64_t len,
                            int64_t *group_ids, int64_t *first_ids, rfb_group_info_t *info);
@@ -235,8 +236,24 @@ int rfb_group_keys_i64_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const *cols
 /* aggr_sum/min/max/count/avg (core/aggr.c AGGR_ITER :73-161): out[gid] (+)= val[row]; sticky-null sum, +INF-init
  * min, NULL-init max, row count, f64 avg.  out: `groups` elements of rfb_aggr_type(op, val_type). */
 int rfb_aggr_type(int op, int val_type);
+/* op RFB_A_MED = aggr_med (core/aggr.c:2136-2246): median of each group's values in ray_asc order (nulls / NaN sort first and
+ * count as values; I64/TIMESTAMP/F64 values, any other type gives all-null like the reference's default branch).
+ * op RFB_A_DEV = aggr_dev (core/aggr.c:2250-2906): population standard deviation of the non-null values, f64 sums of x and
+ * x*x per group, sqrt(max(sumsq/n - mean^2, 0)); 0 rows -> null, 1 row -> 0. */
 int rfb_aggr_dev(rfb_ctx_t *ctx, int op, int val_type, const void *val, const int64_t *filter,
                  const int64_t *group_ids, int64_t len, int64_t groups, void *out);
+
+/* aggr_row / aggr_collect (core/aggr.c:3021-3136): the rows of every group.  out_rows[len] = row ids (filter[i], or i without
+ * a filter) ordered by group id and, inside a group, by position (the order AGGR_ITER pushes them); offsets[groups+1] = where
+ * each group starts.  aggr_row's list g is out_rows[offsets[g] .. offsets[g+1]); aggr_collect's is rfb_gather_dev of it. */
+int rfb_group_rows_dev(rfb_ctx_t *ctx, const int64_t *group_ids, const int64_t *filter, int64_t len, int64_t groups,
+                       int64_t *out_rows, int64_t *offsets);
+
+/* ray_med (core/math.c:2529-2626): median of a U8 / I16 / I64 vector -> *out (host).  Like the reference it sorts the whole
+ * column (nulls first) but takes the middle of the NON-NULL count, and adds the two middle elements as integers.
+ * ray_dev (core/math.c:2628-2700): sqrt(sum((x - mean)^2) / n) over the non-null values, two passes. */
+int rfb_med_dev(rfb_ctx_t *ctx, int type, const void *x, int64_t n, double *out);
+int rfb_stddev_dev(rfb_ctx_t *ctx, int type, const void *x, int64_t n, double *out);
 
 /* Fused `select {s: (sum v) c: (count v) from t by k [where (cmp p kk)]}` on a dense key domain: one scope pass +
  * one accumulate pass; never materialises group_ids.  keys: I64 or I32 (I32 is a superset of the reference, Q1).

@@ -109,6 +109,9 @@ rfb_obj_p rfb_ray_min(rfb_obj_p x);
 rfb_obj_p rfb_ray_max(rfb_obj_p x);
 rfb_obj_p rfb_ray_avg(rfb_obj_p x);
 rfb_obj_p rfb_ray_cnt(rfb_obj_p x);
+/* ray_med / ray_dev (core/math.c:2529-2700): vector (med: U8/I16/I64 as in the reference), MAPFILTER or MAPGROUP operand */
+rfb_obj_p rfb_ray_med(rfb_obj_p x);
+rfb_obj_p rfb_ray_dev(rfb_obj_p x);
 
 /* ---- element-wise: ray_add/sub/mul/div/fdiv/mod/xbar (core/math.c:2436-2442), ray_round/floor/ceil (:2430-2432) */
 rfb_obj_p rfb_ray_add(rfb_obj_p x, rfb_obj_p y);
@@ -132,6 +135,12 @@ rfb_obj_p rfb_aggr_min(rfb_obj_p val, rfb_obj_p index);
 rfb_obj_p rfb_aggr_max(rfb_obj_p val, rfb_obj_p index);
 rfb_obj_p rfb_aggr_count(rfb_obj_p val, rfb_obj_p index);
 rfb_obj_p rfb_aggr_avg(rfb_obj_p val, rfb_obj_p index);
+/* aggr_med / aggr_dev (core/aggr.c:2136-2906) -> F64 vector; aggr_row / aggr_collect (core/aggr.c:3021-3136) -> LIST of
+ * per-group row-id / value vectors */
+rfb_obj_p rfb_aggr_med(rfb_obj_p val, rfb_obj_p index);
+rfb_obj_p rfb_aggr_stddev(rfb_obj_p val, rfb_obj_p index);   /* the reference's aggr_dev (rfb_aggr_dev names the C ABI's device entry) */
+rfb_obj_p rfb_aggr_row(rfb_obj_p val, rfb_obj_p index);
+rfb_obj_p rfb_aggr_collect(rfb_obj_p val, rfb_obj_p index);
 
 /* ---- key sort: ray_sort_asc/desc (core/sort.c:430,691) = ray_iasc/idesc (core/order.c:32): stable i64 permutation */
 rfb_obj_p rfb_ray_sort_asc(rfb_obj_p x);

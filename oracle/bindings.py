@@ -22,7 +22,7 @@ REF_BIN = os.path.join(HERE, "_ref", "rayforce_ref")
 # reference type codes (core/rayforce.h:50-62)
 B8, U8, I16, I32, I64, SYMBOL, DATE, TIME, TIMESTAMP, F64 = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 EQ, NE, LT, GT, LE, GE = range(6)
-SUM, MIN, MAX, CNT, AVG, COUNT = range(6)
+SUM, MIN, MAX, CNT, AVG, COUNT, MED, DEV = range(8)
 ADD, SUB, MUL, DIV, FDIV, MOD, XBAR = range(7)
 ROUND, FLOOR, CEIL = range(3)
 ATOM = -1
@@ -95,6 +95,11 @@ class Oracle:
         L.rfo_aggr.argtypes = [ci, ci, vp, vp, vp, i64, i64, vp, C.POINTER(ci)]
         L.rfo_sort.restype = ci
         L.rfo_sort.argtypes = [ci, vp, i64, ci, vp]
+        L.rfo_group_rows.restype = ci
+        L.rfo_group_rows.argtypes = [vp, vp, i64, i64, vp, vp]
+        for f in (L.rfo_med, L.rfo_dev):
+            f.restype = ci
+            f.argtypes = [ci, vp, i64, C.POINTER(C.c_double)]
         L.rfo_splitmix64.restype = C.c_uint64
         L.rfo_splitmix64.argtypes = [C.c_uint64, C.c_uint64]
 
@@ -201,6 +206,29 @@ class Oracle:
         dt = NP_OF[ot.value]
         return out.view(np.uint8)[: groups * np.dtype(dt).itemsize].view(dt).copy(), ot.value
 
+    def group_rows(self, gids, groups, filt=None):
+        """aggr_row / aggr_collect layout: (rows grouped by gid in push order, offsets[groups+1])"""
+        gids = np.ascontiguousarray(gids, np.int64)
+        if filt is not None:
+            filt = np.ascontiguousarray(filt, np.int64)
+        rows, offs = np.empty(gids.shape[0], np.int64), np.empty(groups + 1, np.int64)
+        self.L.rfo_group_rows(_ptr(gids), _ptr(filt), gids.shape[0], groups, _ptr(rows), _ptr(offs))
+        return rows, offs
+
+    def med(self, t, x):
+        return self._stat(self.L.rfo_med, t, x)
+
+    def dev(self, t, x):
+        return self._stat(self.L.rfo_dev, t, x)
+
+    def _stat(self, fn, t, x):
+        x = np.ascontiguousarray(x, NP_OF[t])
+        out = C.c_double(0.0)
+        r = fn(t, _ptr(x), x.shape[0], C.byref(out))
+        if r < 0:
+            raise OracleError(r)
+        return out.value
+
     def sort(self, t, x, descending=False):
         x = np.ascontiguousarray(x, NP_OF[t])
         perm = np.empty(x.shape[0], np.int64)
@@ -257,13 +285,14 @@ class Reference:
         L.clone_obj.argtypes = [vp]
         for name in ("ray_sum", "ray_min", "ray_max", "ray_cnt", "ray_avg", "ray_count", "ray_where", "ray_round",
                      "ray_floor", "ray_ceil", "ray_sort_asc", "ray_sort_desc", "ray_iasc", "ray_idesc", "ray_asc",
-                     "ray_desc"):
+                     "ray_desc", "ray_med", "ray_dev"):
             f = getattr(L, name)
             f.restype = vp
             f.argtypes = [vp]
         for name in ("ray_eq", "ray_ne", "ray_lt", "ray_gt", "ray_le", "ray_ge", "ray_add", "ray_sub", "ray_mul",
                      "ray_div", "ray_fdiv", "ray_mod", "ray_xbar", "filter_map", "filter_collect", "index_group", "group_map",
-                     "aggr_sum", "aggr_min", "aggr_max", "aggr_count", "aggr_avg", "aggr_first"):
+                     "aggr_sum", "aggr_min", "aggr_max", "aggr_count", "aggr_avg", "aggr_first", "aggr_med", "aggr_dev",
+                     "aggr_row", "aggr_collect"):
             f = getattr(L, name)
             f.restype = vp
             f.argtypes = [vp, vp]
@@ -353,8 +382,8 @@ class Reference:
     # ---- numpy-level conveniences mirroring Oracle's API
     _CMP = ["ray_eq", "ray_ne", "ray_lt", "ray_gt", "ray_le", "ray_ge"]
     _BIN = ["ray_add", "ray_sub", "ray_mul", "ray_div", "ray_fdiv", "ray_mod", "ray_xbar"]
-    _FOLD = ["ray_sum", "ray_min", "ray_max", "ray_cnt", "ray_avg", "ray_count"]
-    _AGGR = ["aggr_sum", "aggr_min", "aggr_max", None, "aggr_avg", "aggr_count"]
+    _FOLD = ["ray_sum", "ray_min", "ray_max", "ray_cnt", "ray_avg", "ray_count", "ray_med", "ray_dev"]
+    _AGGR = ["aggr_sum", "aggr_min", "aggr_max", None, "aggr_avg", "aggr_count", "aggr_med", "aggr_dev"]
 
     def _bin(self, name, xt, x, yt, y):
         xo, yo = self.operand(xt, x), self.operand(yt, y)
@@ -442,6 +471,25 @@ class Reference:
         if filt is not None:
             self.drop(fo)
         return out
+
+    def group_lists(self, keys, vt, val, filt=None):
+        """index_group(keys, filter) then aggr_row / aggr_collect -> (row-id arrays, value arrays), one per group"""
+        ko, vo = self.vec(I64, keys), self.vec(vt, val)
+        fo = self.NULL_OBJ if filt is None else self.vec(I64, filt)
+        idx = self.call2("index_group", ko, fo)
+        if self.is_err(idx):
+            raise RefError("index_group")
+        out = []
+        for name in ("aggr_row", "aggr_collect"):
+            r = self.call2(name, vo, idx)
+            if self.is_err(r):
+                raise RefError(name)
+            out.append([self.to_numpy(it, drop=False)[0].copy() for it in self.list_items(r)])
+            self.drop(r)
+        self.drop(idx, ko, vo)
+        if filt is not None:
+            self.drop(fo)
+        return out[0], out[1]
 
     def eval(self, src: str):
         return self.L.eval_str(src.encode())

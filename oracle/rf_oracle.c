@@ -606,9 +606,127 @@ int rfo_aggr(int op, int val_type, const void *val, const int64_t *filter, const
             free(c);
             return RFO_OK;
         }
+        case RFO_MED: { /* core/aggr.c:2136-2246: collect the group's values (aggr_collect), sort them like ray_asc (nulls /
+                         * NaN first, they stay in), median as f64; only I64/TIMESTAMP/F64 have a case, the rest gives nulls */
+            f64 *o = out; *out_type = RFO_F64;
+            i64 *rows = (i64 *)malloc((size_t)(len > 0 ? len : 1) * 8), *offs = (i64 *)malloc((size_t)(groups + 1) * 8);
+            rfo_group_rows(gid, filter, len, groups, rows, offs);
+            for (i64 g = 0; g < groups; g++) {
+                i64 l = offs[g + 1] - offs[g];
+                if (l == 0 || !(val_type == RFO_I64 || val_type == RFO_TIMESTAMP || val_type == RFO_F64)) { o[g] = null_f64(); continue; }
+                u64 *v = (u64 *)malloc((size_t)l * 8);
+                i64 *perm = (i64 *)malloc((size_t)l * 8);
+                for (i64 j = 0; j < l; j++) v[j] = ((const u64 *)val)[rows[offs[g] + j]];
+                rfo_sort(val_type, v, l, 0, perm);
+                i64 mid = l / 2;
+                if (val_type == RFO_F64) {
+                    const f64 *f = (const f64 *)v;
+                    o[g] = (l % 2 == 0) ? (f[perm[mid - 1]] + f[perm[mid]]) / 2.0 : f[perm[mid]];
+                } else {
+                    const i64 *x = (const i64 *)v;
+                    o[g] = (l % 2 == 0) ? ((f64)x[perm[mid - 1]] + (f64)x[perm[mid]]) / 2.0 : (f64)x[perm[mid]];
+                }
+                free(v); free(perm);
+            }
+            free(rows); free(offs);
+            return RFO_OK;
+        }
+        case RFO_DEV: { /* core/aggr.c:2250-2330 accumulation (f64 sum, sum of squares, non-null count), :2893-2906 formula */
+            f64 *o = out; *out_type = RFO_F64;
+            if (!(val_type == RFO_I16 || val_type == RFO_I32 || val_type == RFO_DATE || val_type == RFO_TIME ||
+                  val_type == RFO_I64 || val_type == RFO_TIMESTAMP || val_type == RFO_F64)) return RFO_ERR_TYPE;
+            f64 *s = (f64 *)calloc((size_t)(groups > 0 ? groups : 1), 8), *q = (f64 *)calloc((size_t)(groups > 0 ? groups : 1), 8);
+            i64 *c = (i64 *)calloc((size_t)(groups > 0 ? groups : 1), 8);
+            for (i64 i = 0; i < len; i++) {
+                i64 r = ROW(i), g = gid[i];
+                f64 v; int ok;
+                if (k == K_I64) { i64 x = ((const i64 *)val)[r]; ok = x != RFO_NULL_I64; v = (f64)x; }
+                else if (k == K_I32) { i32 x = ((const i32 *)val)[r]; ok = x != RFO_NULL_I32; v = (f64)x; }
+                else if (k == K_I16) { i16 x = ((const i16 *)val)[r]; ok = x != RFO_NULL_I16; v = (f64)x; }
+                else { v = ((const f64 *)val)[r]; ok = !isnan64(v); }
+                if (ok) { s[g] += v; q[g] += v * v; c[g]++; }
+            }
+            for (i64 g = 0; g < groups; g++) {
+                if (c[g] == 0) o[g] = null_f64();
+                else if (c[g] == 1) o[g] = 0.0;
+                else { f64 mean = s[g] / (f64)c[g], var = q[g] / (f64)c[g] - mean * mean; o[g] = var < 0.0 ? 0.0 : sqrt(var); }
+            }
+            free(s); free(q); free(c);
+            return RFO_OK;
+        }
         default: return RFO_ERR_TYPE;
     }
 #undef ROW
+}
+
+/* aggr_row / aggr_collect (core/aggr.c:3021-3136): AGGR_ITER pushes row x (= filter[i] or i) onto list gid[i], i ascending */
+int rfo_group_rows(const int64_t *gid, const int64_t *filter, int64_t len, int64_t groups, int64_t *rows, int64_t *offsets) {
+    for (i64 g = 0; g <= groups; g++) offsets[g] = 0;
+    for (i64 i = 0; i < len; i++) offsets[gid[i] + 1]++;
+    for (i64 g = 0; g < groups; g++) offsets[g + 1] += offsets[g];
+    i64 *cur = (i64 *)malloc((size_t)(groups > 0 ? groups : 1) * 8);
+    for (i64 g = 0; g < groups; g++) cur[g] = offsets[g];
+    for (i64 i = 0; i < len; i++) rows[cur[gid[i]]++] = filter ? filter[i] : i;
+    free(cur);
+    return RFO_OK;
+}
+
+/* ray_med (core/math.c:2529-2626): vector cases exist for U8, I16, I64 only.  l = ray_cnt = NON-NULL count, but the sorted
+ * column keeps its nulls (first): the reference indexes it with l anyway (its own null goldens are commented out,
+ * tests/lang.c:2582-2585).  The two middle elements are added as integers before the division. */
+int rfo_med(int type, const void *x, int64_t n, double *out) {
+    if (!(type == RFO_U8 || type == RFO_I16 || type == RFO_I64)) return RFO_ERR_TYPE;
+    i64 l = 0;
+    for (i64 i = 0; i < n; i++)
+        l += type == RFO_U8 ? 1 : (type == RFO_I16 ? ((const i16 *)x)[i] != RFO_NULL_I16 : ((const i64 *)x)[i] != RFO_NULL_I64);
+    if (l == 0) { *out = null_f64(); return RFO_OK; }
+    i64 *perm = (i64 *)malloc((size_t)n * 8);
+    rfo_sort(type, x, n, 0, perm);
+#define AT(j) (type == RFO_U8 ? (i64)((const u8 *)x)[perm[j]] : type == RFO_I16 ? (i64)((const i16 *)x)[perm[j]] : ((const i64 *)x)[perm[j]])
+    *out = (l % 2 == 0) ? (f64)wadd64(AT(l / 2 - 1), AT(l / 2)) / 2.0 : (f64)AT(l / 2);
+#undef AT
+    free(perm);
+    return RFO_OK;
+}
+
+/* ray_dev (core/math.c:2628-2700): mean = ray_sum / ray_cnt (I32/TIME sums wrap in 32 bits), then
+ * sqrt(sum((x - mean)^2 over non-null) / cnt) (ray_sq_sub_partial :2119-2174).  Types whose ray_sum is a type error
+ * (DATE, TIMESTAMP) are a type error here as well (the reference dereferences the error object there). */
+int rfo_dev(int type, const void *x, int64_t n, double *out) {
+    int k = kind_of(type);
+    i64 sum[1]; int st;
+    if (!k || type == RFO_B8 || type == RFO_SYMBOL) return RFO_ERR_TYPE;
+    if (rfo_fold(RFO_SUM, type, x, n, sum, &st) < 0) return RFO_ERR_TYPE;
+    i64 l = 0;
+    for (i64 i = 0; i < n; i++) {
+        switch (k) {
+            case K_U8: l++; break;
+            case K_I16: l += ((const i16 *)x)[i] != RFO_NULL_I16; break;
+            case K_I32: l += ((const i32 *)x)[i] != RFO_NULL_I32; break;
+            case K_I64: l += ((const i64 *)x)[i] != RFO_NULL_I64; break;
+            default: l += !isnan64(((const f64 *)x)[i]); break;
+        }
+    }
+    if (l == 0) { *out = null_f64(); return RFO_OK; }
+    if (l == 1) { *out = 0.0; return RFO_OK; }
+    f64 mean;
+    if (k == K_F64) { f64 fs; memcpy(&fs, sum, 8); mean = fs / (f64)l; }
+    else if (k == K_I32) { i32 s32; memcpy(&s32, sum, 4); mean = (f64)s32 / (f64)l; }
+    else mean = (f64)sum[0] / (f64)l;
+    f64 acc = 0.0;
+    for (i64 i = 0; i < n; i++) {
+        f64 v; int ok = 1;
+        switch (k) {
+            case K_U8: v = (f64)((const u8 *)x)[i]; break;
+            case K_I16: ok = ((const i16 *)x)[i] != RFO_NULL_I16; v = (f64)((const i16 *)x)[i]; break;
+            case K_I32: ok = ((const i32 *)x)[i] != RFO_NULL_I32; v = (f64)((const i32 *)x)[i]; break;
+            case K_I64: ok = ((const i64 *)x)[i] != RFO_NULL_I64; v = (f64)((const i64 *)x)[i]; break;
+            default: v = ((const f64 *)x)[i]; ok = !isnan64(v); break;
+        }
+        if (ok) { f64 t = v - mean; acc += t * t; }
+    }
+    *out = sqrt(acc / (f64)l);
+    return RFO_OK;
 }
 
 /* ------------------------------------------------------------------ key sort (core/sort.c) */

@@ -198,11 +198,11 @@ int d2h_sync(rfb_ctx_t *ctx, void *dst, const void *src, size_t bytes) {
 
 inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-template <typename Slot, bool INSERT>
-int number_groups(rfb_ctx_t *ctx, KeySrc src, Slot slot, i64 len, i64 slots, u64 *first_row, i64 *gid_of_slot, void *tile_work,
+template <typename Src, typename Slot, bool INSERT>
+int number_groups(rfb_ctx_t *ctx, Src src, Slot slot, i64 len, i64 slots, u64 *first_row, i64 *gid_of_slot, void *tile_work,
                   i64 *mm, i64 *group_ids, i64 *first_ids, i64 *groups) {
     const int grid = rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM);
-    k_claim<KeySrc, Slot, INSERT><<<grid, THREADS, 0, ctx->stream>>>(src, slot, len, first_row);
+    k_claim<Src, Slot, INSERT><<<grid, THREADS, 0, ctx->stream>>>(src, slot, len, first_row);
     RFB_CHECK_LAUNCH(ctx);
     k_max_first<<<rfb_grid_for(ctx, slots, THREADS, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(first_row, slots, mm);
     RFB_CHECK_LAUNCH(ctx);
@@ -213,10 +213,10 @@ int number_groups(rfb_ctx_t *ctx, KeySrc src, Slot slot, i64 len, i64 slots, u64
     scan::TileCtl ctl;
     rc = scan::prepare_tiles(ctx, tile_work, tiles, ctx->h_count, &ctl);
     if (rc) return rc;
-    k_number<KeySrc, Slot><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(src, slot, limit, first_row, gid_of_slot, first_ids, ctl);
+    k_number<Src, Slot><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(src, slot, limit, first_row, gid_of_slot, first_ids, ctl);
     RFB_CHECK_LAUNCH(ctx);
     if (group_ids) {
-        k_assign<KeySrc, Slot><<<grid, THREADS, 0, ctx->stream>>>(src, slot, len, gid_of_slot, group_ids);
+        k_assign<Src, Slot><<<grid, THREADS, 0, ctx->stream>>>(src, slot, len, gid_of_slot, group_ids);
         RFB_CHECK_LAUNCH(ctx);
     }
     RFB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -260,7 +260,7 @@ extern "C" int rfb_group_i64_dev(rfb_ctx_t *ctx, const int64_t *keys, const int6
         u64 *first_row = (u64 *)w;
         i64 *gid_of_slot = (i64 *)((char *)w + b1);
         RFB_CUDA(cudaMemsetAsync(first_row, 0xFF, (size_t)range * 8, ctx->stream));
-        rc = number_groups<DenseSlot, false>(ctx, src, DenseSlot{info->min}, len, range, first_row, gid_of_slot, (char *)w + 2 * b1,
+        rc = number_groups<KeySrc, DenseSlot, false>(ctx, src, DenseSlot{info->min}, len, range, first_row, gid_of_slot, (char *)w + 2 * b1,
                                              mm, group_ids, first_ids, &groups);
         if (rc) return rc;
         info->dense = 1;
@@ -280,7 +280,7 @@ extern "C" int rfb_group_i64_dev(rfb_ctx_t *ctx, const int64_t *keys, const int6
         if (rc) return rc;
         RFB_CUDA(cudaMemsetAsync(first_row, 0xFF, (size_t)(cap + 1) * 8, ctx->stream));
         HashSlot hs{tk, (u64)(cap - 1), cap};
-        rc = number_groups<HashSlot, true>(ctx, src, hs, len, cap + 1, first_row, gid_of_slot, (char *)w + 3 * b1, mm, group_ids,
+        rc = number_groups<KeySrc, HashSlot, true>(ctx, src, hs, len, cap + 1, first_row, gid_of_slot, (char *)w + 3 * b1, mm, group_ids,
                                            first_ids, &groups);
         if (rc) return rc;
         info->dense = 0;
@@ -294,6 +294,49 @@ extern "C" int rfb_group_i64_dev(rfb_ctx_t *ctx, const int64_t *keys, const int6
 
 namespace {
 constexpr int MAX_KEY_COLS = 8;
+
+// ---- row-hash path (core/index.c:2556-2729 hashes every row with hash_index_u64 and groups equal tuples through
+// per-partition open-addressing tables; the device keeps ONE table of representative rows: a slot is claimed with a CAS on
+// the row id and a probe compares the full key tuple of the probing row with the slot's representative)
+struct RowSrc {                      // position i of the (filtered) row sequence -> row id (the "key" of the numbering passes)
+    const i64 *filter;
+    __device__ __forceinline__ i64 operator()(i64 i) const { return filter ? ld_stream(filter + i) : i; }
+};
+struct TupleSlot {
+    const i64 *col[MAX_KEY_COLS];
+    int ncols;
+    i64 *rep;       // [cap] representative row of each slot, NULL_I64 = empty (row ids are >= 0)
+    u64 mask;
+    __device__ __forceinline__ u64 hash(i64 row) const {
+        u64 h = 0x9E3779B97F4A7C15ULL;
+        for (int c = 0; c < ncols; c++) h = mix64(h ^ (u64)__ldg(col[c] + row)) + 0x9E3779B97F4A7C15ULL;
+        return h;
+    }
+    __device__ __forceinline__ bool same(i64 a, i64 b) const {
+        if (a == b) return true;
+        for (int c = 0; c < ncols; c++)
+            if (__ldg(col[c] + a) != __ldg(col[c] + b)) return false;
+        return true;
+    }
+    __device__ __forceinline__ i64 insert(i64 row) const {
+        u64 s = hash(row) & mask;
+        while (true) {
+            i64 cur = (i64)scan::ld_relaxed((const u64 *)&rep[s]);
+            if (cur == NULL_I64) {
+                cur = (i64)atomicCAS((unsigned long long *)&rep[s], (unsigned long long)NULL_I64, (unsigned long long)row);
+                if (cur == NULL_I64) return (i64)s;
+            }
+            if (same(cur, row)) return (i64)s;
+            s = (s + 1) & mask;
+        }
+    }
+    __device__ __forceinline__ i64 operator()(i64 row) const {   // lookup of a tuple known to be present
+        u64 s = hash(row) & mask;
+        while (!same(__ldcg(&rep[s]), row)) s = (s + 1) & mask;
+        return (i64)s;
+    }
+};
+
 struct FuseSpec {
     const i64 *col[MAX_KEY_COLS];
     i64 min[MAX_KEY_COLS];
@@ -323,6 +366,7 @@ extern "C" int rfb_group_keys_i64_dev(rfb_ctx_t *ctx, int ncols, const int64_t *
     f.ncols = ncols;
     i64 *mm = (i64 *)((char *)ctx->d_scratch + 32768);
     unsigned __int128 space = 1;
+    bool hashed = false;
     i64 range[MAX_KEY_COLS];
     for (int c = 0; c < ncols; c++) {   // per-column scope (core/index.c:2308-2340 does the same before fusing)
         KeySrc src{cols[c], filter};
@@ -337,11 +381,38 @@ extern "C" int rfb_group_keys_i64_dev(rfb_ctx_t *ctx, int ncols, const int64_t *
         f.min[c] = h[0];
         const unsigned __int128 r = (unsigned __int128)((u64)h[1] - (u64)h[0]) + 1;
         space *= r;
-        if (space > ((unsigned __int128)1 << 62)) {
-            rfb_set_error("multi-key group-by: the product of the key ranges does not fit 62 bits (row-hash grouping is not built)");
-            return RFB_ERR_ARG;
-        }
+        if (space > ((unsigned __int128)1 << 62)) { hashed = true; space = 1; }   // no perfect hash: group by row hash
         range[c] = (i64)r;
+    }
+    if (hashed) {
+        // rep[cap] | first_row[cap] | gid_of_slot[cap] | tile states.  cap = power of two >= 2*len
+        i64 cap = 1024;
+        while (cap < 2 * len) cap <<= 1;
+        const i64 tiles_max = (len + scan::RowTile<NUM_J>::TILE - 1) / scan::RowTile<NUM_J>::TILE;
+        const size_t b1 = align256((size_t)cap * 8);
+        void *w;
+        int rc = rfb_ensure_work(ctx, 3 * b1 + scan::tiles_bytes(tiles_max), &w);
+        if (rc) return rc;
+        TupleSlot ts;
+        ts.ncols = ncols;
+        for (int c = 0; c < ncols; c++) ts.col[c] = cols[c];
+        ts.rep = (i64 *)w;
+        ts.mask = (u64)(cap - 1);
+        u64 *first_row = (u64 *)((char *)w + b1);
+        i64 *gid_of_slot = (i64 *)((char *)w + 2 * b1);
+        rc = fill<i64>(ctx, ts.rep, cap, NULL_I64);
+        if (rc) return rc;
+        RFB_CUDA(cudaMemsetAsync(first_row, 0xFF, (size_t)cap * 8, ctx->stream));
+        i64 groups = 0;
+        rc = number_groups<RowSrc, TupleSlot, true>(ctx, RowSrc{filter}, ts, len, cap, first_row, gid_of_slot, (char *)w + 3 * b1, mm,
+                                                    group_ids, first_ids, &groups);
+        if (rc) return rc;
+        info->groups = groups;
+        info->dense = 0;
+        info->index_type = RFB_INDEX_IDS;
+        info->min = info->max = NULL_I64;
+        info->range = 0;
+        return RFB_OK;
     }
     i64 stride = 1;
     for (int c = ncols - 1; c >= 0; c--) { f.stride[c] = stride; stride *= range[c]; }
@@ -543,6 +614,8 @@ extern "C" int rfb_aggr_type(int op, int val_type) {
         case RFB_A_MIN: case RFB_A_MAX:
             return (val_type == RFB_I16 || val_type == RFB_I64 || val_type == RFB_TIMESTAMP || val_type == RFB_DATE || val_type == RFB_TIME || val_type == RFB_F64) ? val_type : RFB_ERR_TYPE;
         case RFB_A_AVG: return (val_type == RFB_I16 || k == K_I32 || val_type == RFB_I64 || k == K_F64) ? RFB_F64 : RFB_ERR_TYPE;
+        case RFB_A_MED: return RFB_F64;   // aggr_collect takes every column type; types without a median give nulls (core/aggr.c:2182-2184)
+        case RFB_A_DEV: return (val_type == RFB_I16 || k == K_I32 || val_type == RFB_I64 || val_type == RFB_TIMESTAMP || k == K_F64) ? RFB_F64 : RFB_ERR_TYPE;   // core/aggr.c:2873-2880
         default: return RFB_ERR_TYPE;
     }
 }
@@ -553,6 +626,8 @@ extern "C" int rfb_aggr_dev(rfb_ctx_t *ctx, int op, int val_type, const void *va
     const int ot = rfb_aggr_type(op, val_type);
     if (ot < 0) { rfb_set_error("aggr %d: unsupported value type %d", op, val_type); return RFB_ERR_TYPE; }
     if (groups == 0) return RFB_OK;
+    if (op == RFB_A_MED) return rfb_aggr_med_launch(ctx, val_type, val, filter, group_ids, len, groups, (f64 *)out);
+    if (op == RFB_A_DEV) return rfb_aggr_stddev_launch(ctx, val_type, val, filter, group_ids, len, groups, (f64 *)out);
     const int k = rfb_kind_of(val_type);
     void *w;
     int rc = rfb_ensure_work(ctx, 2 * align256((size_t)groups * 8), &w);

@@ -67,6 +67,10 @@ int rfb_fold_launch(rfb_ctx_t *ctx, int folds, int type, const void *x, i64 n);
 int rfb_filter_fold_launch(rfb_ctx_t *ctx, int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k, int folds,
                            int val_type, const void *val, i64 n);
 
+// k_stats.cu: grouped median / deviation behind rfb_aggr_dev(RFB_A_MED / RFB_A_DEV)
+int rfb_aggr_med_launch(rfb_ctx_t *ctx, int val_type, const void *val, const int64_t *filter, const int64_t *group_ids, int64_t len, int64_t groups, double *out);
+int rfb_aggr_stddev_launch(rfb_ctx_t *ctx, int val_type, const void *val, const int64_t *filter, const int64_t *group_ids, int64_t len, int64_t groups, double *out);
+
 #define RFB_CUDA(call)                                                          \
     do {                                                                        \
         cudaError_t _e = (call);                                                \

@@ -620,6 +620,42 @@ obj_p rfb_ray_max(obj_p x) { return fold_op(F_MAX, x); }
 obj_p rfb_ray_avg(obj_p x) { return fold_op(F_AVG, x); }
 obj_p rfb_ray_cnt(obj_p x) { return fold_op(F_CNT, x); }
 
+/* ---- ray_med / ray_dev (core/math.c:2529-2700): a plain vector, a MAPFILTER pair (the reference collects it first, so does
+ *      the device: gather, then the statistic) or a MAPGROUP pair (-> aggr_med / aggr_dev).  Atoms stay on the CPU body. */
+static obj_p stat_op(int is_dev, obj_p x) {
+    if (!G.ready || !x) return NULL;
+    if (x->type == RFB_T_MAPGROUP && x->len == 2) return aggr_op(is_dev ? RFB_A_DEV : RFB_A_MED, RFB_OBJ_LIST(x)[0], RFB_OBJ_LIST(x)[1]);
+    obj_p col = x, ids = NULL;
+    if (x->type == RFB_T_MAPFILTER && x->len == 2) { col = RFB_OBJ_LIST(x)[0]; ids = RFB_OBJ_LIST(x)[1]; if (!ids || ids->type != RFB_T_I64) return NULL; }
+    if (!is_vec(col)) return NULL;
+    const int t = col->type;
+    if (is_dev) {
+        if (t == RFB_T_B8 || t == RFB_T_SYMBOL) return G.host->err_type();
+        if (t == RFB_T_DATE || t == RFB_T_TIMESTAMP) return NULL;   /* the reference reads a field of ray_sum's error object here: its body, its result */
+    } else if (!(t == RFB_T_U8 || t == RFB_T_I16 || t == RFB_T_I64)) return G.host->err_type();   /* core/math.c:2555-2590 */
+    const int64_t n = ids ? ids->len : col->len;
+    if (too_small(n)) return NULL;
+    call_scope_t sc = enter();
+    obj_p res;
+    double r = 0.0;
+    void *dc = dev_column(col), *di = ids ? dev_column(ids) : NULL, *dx = dc;
+    if (!dc || (ids && !di)) { res = G.host->err_limit(); goto out; }
+    int rc = RFB_OK;
+    if (ids) {
+        dx = dev_temp((size_t)(n > 0 ? n : 1) * type_size(t));
+        if (!dx) { res = G.host->err_limit(); goto out; }
+        rc = rfb_gather_dev(G.ctx, t, dc, (const int64_t *)di, n, dx);
+    }
+    if (!rc) rc = is_dev ? rfb_stddev_dev(G.ctx, t, dx, n, &r) : rfb_med_dev(G.ctx, t, dx, n, &r);
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = make_atom(RFB_T_F64, &r);
+out:
+    leave(sc);
+    return res;
+}
+obj_p rfb_ray_med(obj_p x) { return stat_op(0, x); }
+obj_p rfb_ray_dev(obj_p x) { return stat_op(1, x); }
+
 /* ------------------------------------------------------------------ element-wise */
 
 static obj_p bin_op(int op, obj_p x, obj_p y) {
@@ -740,6 +776,60 @@ obj_p rfb_aggr_min(obj_p v, obj_p i) { return aggr_op(RFB_A_MIN, v, i); }
 obj_p rfb_aggr_max(obj_p v, obj_p i) { return aggr_op(RFB_A_MAX, v, i); }
 obj_p rfb_aggr_count(obj_p v, obj_p i) { return aggr_op(RFB_A_COUNT, v, i); }
 obj_p rfb_aggr_avg(obj_p v, obj_p i) { return aggr_op(RFB_A_AVG, v, i); }
+obj_p rfb_aggr_med(obj_p v, obj_p i) { return aggr_op(RFB_A_MED, v, i); }
+obj_p rfb_aggr_stddev(obj_p v, obj_p i) { return aggr_op(RFB_A_DEV, v, i); }   /* aggr_dev; rfb_aggr_dev is the C ABI's device-layer entry */
+
+/* aggr_row / aggr_collect (core/aggr.c:3021-3136): a LIST with one vector per group — the row ids, or the values, of the
+ * group's rows in row order.  The device orders the rows by group (one stable sort of the group ids), the host slices. */
+static obj_p group_lists(int collect, obj_p val, obj_p index) {
+    if (!G.ready || !index || index->type != RFB_T_LIST || index->len != 7) return NULL;
+    if (collect && !is_vec(val)) return NULL;                  /* ENUM / GUID / LIST / parted columns: CPU body */
+    obj_p *ix = RFB_OBJ_LIST(index);
+    if (!ix[0] || ix[0]->type != -RFB_T_I64 || ix[0]->i64 != RFB_INDEX_IDS) return NULL;
+    obj_p gids = ix[2], filter = ix[5];
+    if (!gids || gids->type != RFB_T_I64) return NULL;
+    const int filtered = !is_null_obj(filter);
+    if (filtered && filter->type != RFB_T_I64) return NULL;
+    const int64_t groups = ix[1]->i64, len = gids->len;
+    if (too_small(len)) return NULL;
+    const int ot = collect ? val->type : RFB_T_I64, w = type_size(ot);
+    call_scope_t sc = enter();
+    obj_p res = NULL;
+    int64_t *offs = NULL;
+    char *flat = NULL;
+    void *dg = dev_column(gids), *df = filtered ? dev_column(filter) : NULL, *dv = collect ? dev_column(val) : NULL;
+    void *drows = dev_temp((size_t)(len > 0 ? len : 1) * 8), *doffs = dev_temp((size_t)(groups + 1) * 8);
+    void *dout = collect ? dev_temp((size_t)(len > 0 ? len : 1) * w) : drows;
+    if (!dg || (filtered && !df) || (collect && !dv) || !drows || !doffs || !dout) { res = G.host->err_limit(); goto out; }
+    int rc = rfb_group_rows_dev(G.ctx, (const int64_t *)dg, (const int64_t *)df, len, groups, (int64_t *)drows, (int64_t *)doffs);
+    if (!rc && collect) rc = rfb_gather_dev(G.ctx, ot, dv, (const int64_t *)drows, len, dout);
+    if (rc) { res = status_to_obj(rc); goto out; }
+    offs = (int64_t *)malloc((size_t)(groups + 1) * 8);
+    flat = (char *)malloc((size_t)(len > 0 ? len : 1) * w);
+    if (!offs || !flat || rfb_d2h(G.ctx, offs, doffs, (size_t)(groups + 1) * 8) != RFB_OK ||
+        (len > 0 && rfb_d2h(G.ctx, flat, dout, (size_t)len * w) != RFB_OK) || rfb_sync(G.ctx) != RFB_OK) { res = G.host->err_limit(); goto out; }
+    res = G.host->vector(RFB_T_LIST, groups);
+    if (!res || res->type == RFB_T_ERR) { res = G.host->err_limit(); goto out; }
+    for (int64_t g = 0; g < groups; g++) {
+        const int64_t c = offs[g + 1] - offs[g];
+        obj_p v = G.host->vector((int8_t)ot, c);
+        if (!v || v->type == RFB_T_ERR) {   /* hand back what exists as a shorter list, like the reference's error idiom (core/aggr.c:389-392) */
+            res->len = g;
+            G.host->drop_obj(res);
+            res = G.host->err_limit();
+            goto out;
+        }
+        if (c > 0) memcpy(RFB_OBJ_PAYLOAD(v), flat + (size_t)offs[g] * w, (size_t)c * w);
+        RFB_OBJ_LIST(res)[g] = v;
+    }
+out:
+    free(offs);
+    free(flat);
+    leave(sc);
+    return res;
+}
+obj_p rfb_aggr_row(obj_p v, obj_p i) { return group_lists(0, v, i); }
+obj_p rfb_aggr_collect(obj_p v, obj_p i) { return group_lists(1, v, i); }
 
 /* ------------------------------------------------------------------ sort */
 

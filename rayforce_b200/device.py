@@ -313,6 +313,26 @@ class _Ops:
         self.sync()
         return out, ot
 
+    def group_rows(self, gids, groups, filt=None):
+        """aggr_row / aggr_collect layout -> (row ids grouped by gid in row order, offsets[groups+1])"""
+        n = gids.shape[0]
+        rows, offs = self._empty(n, capi.I64), self._empty(groups + 1, capi.I64)
+        check(self.lib.rfb_group_rows_dev(self.h, _dptr(gids), _dptr(filt), n, groups, _dptr(rows), _dptr(offs)))
+        self.sync()
+        return rows, offs
+
+    def med(self, t, x) -> float:
+        """ray_med (ungrouped)"""
+        out = C.c_double(0.0)
+        check(self.lib.rfb_med_dev(self.h, t, _dptr(x), x.shape[0], C.byref(out)))
+        return out.value
+
+    def stddev(self, t, x) -> float:
+        """ray_dev (ungrouped)"""
+        out = C.c_double(0.0)
+        check(self.lib.rfb_stddev_dev(self.h, t, _dptr(x), x.shape[0], C.byref(out)))
+        return out.value
+
     def group_sum_count(self, key_type, keys, val, max_groups, cmp_op=None, pred_type=None, pred=None, k=None):
         """fused select {s: (sum v) c: (count v) from t by k [where (cmp p k)]} -> (keys, sums, counts) tensors"""
         n = keys.shape[0]

@@ -284,11 +284,22 @@ def test_group_multi_key_matches_oracle_numbering(ctx, oracle, ncols, filtered, 
     assert np.array_equal(host(gf), wf) and np.array_equal(host(gg), wg)
 
 
-def test_group_multi_key_space_too_large(ctx):
-    a = dev(np.array([0, 1 << 40, 5], np.int64))
-    with pytest.raises(capi.RfbError) as e:
-        ctx.group_keys([a, a, a])
-    assert e.value.kind == "arg"
+@pytest.mark.parametrize("ncols", [2, 4])
+@pytest.mark.parametrize("filtered", [False, True])
+@pytest.mark.parametrize("n", [3, 70_001, 500_003])
+def test_group_multi_key_row_hash_path(ctx, oracle, ncols, filtered, n):
+    """index_group_list when the product of the key ranges does not fit an i64 (reference core/index.c:2556-2729: row
+    hashes + open addressing): tuples are grouped through a table of representative rows; numbering = first occurrence
+    (the reference's order at -c 1)"""
+    r = np.random.default_rng(n * 3 + ncols)
+    pools = [r.integers(-(1 << 61), 1 << 61, 5 + c).astype(np.int64) for c in range(ncols)]     # few distinct, huge ranges
+    cols = [p[r.integers(0, p.shape[0], n)] for p in pools]
+    cols[-1][::5] = ob.NULL_I64                                                                 # a null is a key like any other
+    filt = np.sort(r.choice(n, max(1, n // 3), replace=False)).astype(np.int64) if filtered else None
+    wg, wf, groups = oracle.group_multi(cols, filt)
+    gg, gf, gi = ctx.group_keys([dev(c) for c in cols], dev(filt) if filtered else None)
+    assert gi.groups == groups and (gi.dense == 0 or n < 100)     # (a 1-row filter of 3 rows has key ranges of 1: perfect hash)
+    assert np.array_equal(host(gf), wf) and np.array_equal(host(gg), wg)
 
 
 def test_group_empty(ctx):

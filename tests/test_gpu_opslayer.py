@@ -126,6 +126,21 @@ def test_select_by_operator_sequence(ops, oracle, filtered):
             got, gt = ops.value(ops.call(name, vo, idx))
             want, wt = oracle.aggr(op, ob.I64, val, wg, wi.groups, filt)
             assert gt == wt and (same_f64(got, want) if wt == ob.F64 else np.array_equal(got, want)), name
+        for name, op in (("aggr_med", ob.MED), ("aggr_stddev", ob.DEV)):
+            got, gt = ops.value(ops.call(name, vo, idx))
+            want, wt = oracle.aggr(op, ob.I64, val, wg, wi.groups, filt)
+            assert gt == wt == ob.F64 and same_f64(got, want), name
+        want_rows, want_offs = oracle.group_rows(wg, wi.groups, filt)
+        for name, flat in (("aggr_row", want_rows), ("aggr_collect", val[want_rows])):
+            lst = ops.call(name, vo, idx)
+            its = ops.items(lst)
+            assert ops.type_of(lst) == 0 and len(its) == wi.groups
+            for g in (0, 1, wi.groups // 2, wi.groups - 1):
+                v, vt = ops.value(its[g], drop=False)
+                assert vt == ob.I64 and np.array_equal(v, flat[want_offs[g]:want_offs[g + 1]]), (name, g)
+            ops.drop(lst)                                       # (the builtin host drops a list's items with it)
+        got, gt = ops.value(ops.call("ray_med", lazy))           # (med v) by k: the lazy pair reaches ray_med (core/math.c:2592)
+        assert same_f64(got, oracle.aggr(ob.MED, ob.I64, val, wg, wi.groups, filt)[0])
         got, gt = ops.value(ops.call("ray_sum", lazy))           # FN_AGGR functions receive the lazy pair (eval.c:737)
         assert np.array_equal(got, oracle.aggr(ob.SUM, ob.I64, val, wg, wi.groups, filt)[0])
         ops.drop(lazy, idx)
@@ -254,3 +269,27 @@ def test_lazily_materialised_results(ops, oracle):
     finally:
         ops.L.rfb_ops_set_lazy(0, 0)
     ops.drop(x, k)
+
+
+def test_med_dev_vectors_and_filtered(ops, oracle):
+    """ray_med / ray_dev on plain vectors and on MAPFILTER pairs (the reference collects, then computes: core/math.c:2605-2608)"""
+    n = 120_011
+    x = rng_col(ob.I64, n, 3, null_frac=0.05, lo=-500, hi=500)
+    ids = np.sort(np.random.default_rng(4).choice(n, n // 2, replace=False)).astype(np.int64)
+    xo, io = ops.vec(ob.I64, x), ops.vec(ob.I64, ids)
+    with ops.scope():
+        got, gt = ops.value(ops.call("ray_med", xo))
+        assert gt == ob.F64 and same_f64([got], [oracle.med(ob.I64, x)])
+        got, gt = ops.value(ops.call("ray_dev", xo))
+        assert gt == ob.F64 and abs(got - oracle.dev(ob.I64, x)) <= 1e-12 * abs(got)
+        lazy = ops.call("filter_map", xo, io)
+        got, gt = ops.value(ops.call("ray_med", lazy))
+        assert same_f64([got], [oracle.med(ob.I64, x[ids])])
+        got, gt = ops.value(ops.call("ray_dev", lazy))
+        assert abs(got - oracle.dev(ob.I64, x[ids])) <= 1e-12 * abs(got)
+        ops.drop(lazy)
+    f = ops.vec(ob.F64, np.arange(70_000, dtype=np.float64))
+    with pytest.raises(OpsError) as e:          # ray_med has no F64 vector case in the reference
+        ops.value(ops.call("ray_med", f))
+    assert e.value.kind == "type"
+    ops.drop(xo, io, f)

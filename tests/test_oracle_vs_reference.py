@@ -268,3 +268,93 @@ def test_sort(oracle, reference, t, desc, n):
     assert np.array_equal(oracle.sort(t, col, desc), reference.sort(t, col, desc))
     wide = rng_col(t, n, n + t + 1, null_frac=0.05)
     assert np.array_equal(oracle.sort(t, wide, desc), reference.sort(t, wide, desc))
+
+
+# ---------------------------------------------------------------- med / dev / collect / row
+
+def close_f64(a, b, rel=1e-12):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return a.shape == b.shape and np.array_equal(np.isnan(a), np.isnan(b)) and np.allclose(a[~np.isnan(a)], b[~np.isnan(b)], rtol=rel, atol=0)
+
+
+@pytest.mark.parametrize("t", [ob.U8, ob.I16, ob.I64])
+@pytest.mark.parametrize("n", [1, 2, 5, 1000, 40_001])
+@pytest.mark.parametrize("nulls", [False, True])
+def test_ungrouped_med(oracle, reference, t, n, nulls):
+    """ray_med (core/math.c:2529-2626) incl. its quirk: the middle of the NON-NULL count indexes the column sorted WITH its nulls"""
+    col = rng_col(t, n, n + t, null_frac=0.2 if nulls else 0.0, lo=-50 if t != ob.U8 else 0, hi=50)
+    a, b = oracle.med(t, col), float(reference.fold(ob.MED, t, col)[0])
+    assert same_f64([a], [b])
+
+
+@pytest.mark.parametrize("t", [ob.I32, ob.F64, ob.DATE])
+def test_ungrouped_med_type_errors(oracle, reference, t):
+    col = rng_col(t, 10, 1, lo=0, hi=9)
+    with pytest.raises(ob.OracleError):
+        oracle.med(t, col)
+    with pytest.raises(ob.RefError):
+        reference.fold(ob.MED, t, col)
+
+
+@pytest.mark.parametrize("t", [ob.U8, ob.I16, ob.I32, ob.TIME, ob.I64, ob.F64])
+@pytest.mark.parametrize("n", [1, 2, 7, 1000, 40_001])
+def test_ungrouped_dev(oracle, reference, t, n):
+    """ray_dev (core/math.c:2628-2700): two passes; the sums run in a thread-dependent order in the reference, so the results
+    agree to rounding (exactly on inputs whose partial sums are exact)"""
+    col = rng_col(t, n, n + t, null_frac=0.1, lo=-100 if t != ob.U8 else 0, hi=100)
+    a, b = oracle.dev(t, col), float(reference.fold(ob.DEV, t, col)[0])
+    assert close_f64([a], [b])
+    allnull = np.full(5, np.nan if t == ob.F64 else (0 if t == ob.U8 else np.iinfo(ob.NP_OF[t]).min), ob.NP_OF[t])
+    if t != ob.U8:
+        assert np.isnan(oracle.dev(t, allnull)) and np.isnan(float(reference.fold(ob.DEV, t, allnull)[0]))
+
+
+@pytest.mark.parametrize("n,card", [(9, 3), (20_000, 50), (100_003, 3000)])
+@pytest.mark.parametrize("filtered", [False, True])
+def test_grouped_med_and_dev(oracle, reference, n, card, filtered):
+    r = np.random.default_rng(n + card)
+    keys = r.integers(0, card, n).astype(np.int64)
+    filt = np.sort(r.choice(n, max(1, n // 3), replace=False)).astype(np.int64) if filtered else None
+    if not reference_scope_is_safe(n if filt is None else filt.shape[0], reference.cores):
+        pytest.skip("reference index_scope_i64 reads out of bounds at this length / thread count (Q12)")
+    gids, firsts, info = oracle.group_i64(keys, filt)
+    for vt, ops in ((ob.I64, [ob.MED, ob.DEV]), (ob.F64, [ob.MED, ob.DEV]), (ob.TIMESTAMP, [ob.MED, ob.DEV]), (ob.I32, [ob.MED, ob.DEV]),
+                    (ob.I16, [ob.DEV]), (ob.TIME, [ob.DEV])):
+        val = rng_col(vt, n, vt, null_frac=0.01, lo=-1000, hi=1000)
+        if vt == ob.F64:
+            val = np.round(val * 8) / 8
+        ref = reference.group_aggr(keys, vt, val, ops, filt)
+        for op in ops:
+            want, wt = oracle.aggr(op, vt, val, gids, info.groups, filt)
+            got, gt = ref["results"][op]
+            assert gt == wt == ob.F64
+            assert same_f64(want, got) if op == ob.MED else close_f64(want, got, 1e-9), (op, vt)
+
+
+def test_grouped_dev_type_error(oracle, reference):
+    keys = np.arange(50, dtype=np.int64) % 5
+    val = rng_col(ob.U8, 50, 1, lo=0, hi=9)
+    gids, firsts, info = oracle.group_i64(keys)
+    with pytest.raises(ob.OracleError):
+        oracle.aggr(ob.DEV, ob.U8, val, gids, info.groups)
+    with pytest.raises(ob.RefError):
+        reference.group_aggr(keys, ob.U8, val, [ob.DEV])
+
+
+@pytest.mark.parametrize("filtered", [False, True])
+def test_group_rows_collect(oracle, reference, filtered):
+    """aggr_row / aggr_collect (core/aggr.c:3021-3136): per-group row-id / value lists in push order"""
+    n, card = 20_011, 37
+    r = np.random.default_rng(3)
+    keys = r.integers(0, card, n).astype(np.int64)
+    val = rng_col(ob.I64, n, 5, null_frac=0.01)
+    filt = np.sort(r.choice(n, n // 2, replace=False)).astype(np.int64) if filtered else None
+    if not reference_scope_is_safe(n if filt is None else filt.shape[0], reference.cores):
+        pytest.skip("Q12")
+    gids, firsts, info = oracle.group_i64(keys, filt)
+    rows, offs = oracle.group_rows(gids, info.groups, filt)
+    got_rows, got_vals = reference.group_lists(keys, ob.I64, val, filt)
+    assert len(got_rows) == info.groups
+    for g in range(info.groups):
+        assert np.array_equal(got_rows[g], rows[offs[g]:offs[g + 1]])
+        assert np.array_equal(got_vals[g], val[rows[offs[g]:offs[g + 1]]])
