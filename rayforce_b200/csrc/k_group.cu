@@ -696,8 +696,14 @@ constexpr int KP_LOG = 13, KP = 1 << KP_LOG;   // keys per partition = shared-me
 constexpr int MAX_PARTS = 256;
 constexpr int PT = 512;                        // threads per CTA of the accumulate kernels (2 CTAs per SM)
 constexpr int PTILE = PT * 8;                  // rows per tile / work unit: 4 pairs per thread
-constexpr int ST = 256;                        // threads per CTA of the scatter and scope kernels (4 CTAs per SM)
+constexpr int ST = 256;                        // threads per CTA of the scope kernel (4 CTAs per SM)
 constexpr int STILE = ST * 8;
+#ifndef RFB_SC_T
+#define RFB_SC_T 256      /* measured on B200 (1e9 rows, 1e5 i32 keys): 256 x 8 x 4 CTAs 7.17 ms, 512 x 4 x 3 CTAs 7.55 ms */
+#define RFB_SC_R 8
+#define RFB_SC_CTAS 4
+#endif
+constexpr int SC_T = RFB_SC_T, SC_R = RFB_SC_R, SC_CTAS = RFB_SC_CTAS, SC_TILE = SC_T * SC_R;   // scatter kernel geometry
 constexpr u32 NULL_FLAG = 0x80000000u;
 
 // two consecutive elements with one vector load (p must be aligned to 2 * sizeof(T))
@@ -743,14 +749,15 @@ struct FusedSrc {
     bool vec_ok(const i64 *val) const { return pair_aligned(keys) && pair_aligned(val) && (!HAS_PRED || pair_aligned(pred)); }
 };
 
-// rows [base, base + 8 * NT) of (key, value, selected): row of (thread, j, h) = base + 2 * (j * NT + thread) + h, so that
+// rows [base, base + R * NT) of (key, value, selected): row of (thread, j, h) = base + 2 * (j * NT + thread) + h, so that
 // every load instruction of a warp covers one contiguous, fully used run of bytes
-template <int NT, bool WITH_VAL, typename FS>
-__device__ __forceinline__ void load_tile(const FS &fs, const i64 *__restrict__ val, i64 base, i64 n, bool vec, i64 (&k)[8], i64 (&v)[8], bool (&sel)[8]) {
-    if (vec && base + 8 * NT <= n) {
+template <int NT, bool WITH_VAL, int R, typename FS>
+__device__ __forceinline__ void load_tile(const FS &fs, const i64 *__restrict__ val, i64 base, i64 n, bool vec, i64 (&k)[R], i64 (&v)[R], bool (&sel)[R]) {
+    static_assert(R % 2 == 0, "rows per thread come in pairs");
+    if (vec && base + R * NT <= n) {
         const i64 pbase = base >> 1;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < R / 2; j++) {
             const i64 pair = pbase + j * NT + threadIdx.x;
             fs.key_pair(pair, k[2 * j], k[2 * j + 1]);
             if constexpr (WITH_VAL) ld_pair<i64>(val, pair, v[2 * j], v[2 * j + 1]);
@@ -758,7 +765,7 @@ __device__ __forceinline__ void load_tile(const FS &fs, const i64 *__restrict__ 
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < R; j++) {
             const i64 r = base + 2 * ((j >> 1) * NT + threadIdx.x) + (j & 1);
             sel[j] = r < n && fs.selected(r);
             k[j] = r < n ? fs.key(r) : 0;
@@ -813,7 +820,7 @@ __global__ void __launch_bounds__(ST, 4) k_fused_scope(FS fs, i64 n, bool vec, i
     for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         i64 k[8], v[8];
         bool sel[8];
-        load_tile<ST, false>(fs, nullptr, tile * STILE, n, vec, k, v, sel);
+        load_tile<ST, false, 8>(fs, nullptr, tile * STILE, n, vec, k, v, sel);
 #pragma unroll
         for (int j = 0; j < 8; j++)
             if (sel[j]) { lo = k[j] < lo ? k[j] : lo; hi = k[j] > hi ? k[j] : hi; }
@@ -886,7 +893,7 @@ k_fused_accum_smem(FS fs, const i64 *__restrict__ val, i64 n, bool vec, i64 kmin
     for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         i64 k[8], v[8];
         bool sel[8];
-        load_tile<PT, true>(fs, val, tile * PTILE, n, vec, k, v, sel);
+        load_tile<PT, true, 8>(fs, val, tile * PTILE, n, vec, k, v, sel);
 #pragma unroll
         for (int j = 0; j < 8; j++)
             if (sel[j]) sacc_add(a, (u32)((u64)k[j] - (u64)kmin), v[j]);
@@ -923,8 +930,8 @@ __device__ __forceinline__ u32 ld_relaxed_u32(const u32 *p) {
 __device__ __forceinline__ void st_relaxed_u32(u32 *p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 struct ScatterSmem {
-    u64 val[STILE];
-    u32 pk[STILE];               // bucket << KP_LOG | slot
+    u64 val[SC_TILE];
+    u32 pk[SC_TILE];               // bucket << KP_LOG | slot
     uint4 desc[MAX_PARTS];       // per bucket: {x: physical - local offset before the block boundary, y: first local index past it, z: offset after it, w: local base}
     u32 cnt[MAX_PARTS];
     u32 wtot[MAX_PARTS / 32];
@@ -937,23 +944,23 @@ struct ScatterSmem {
 // bucket, and writes the runs out contiguously.  Row order inside a bucket is not preserved (integer sums and counts do
 // not depend on it; first rows are claimed from the source columns).
 template <typename FS>
-__global__ void __launch_bounds__(ST, 4)
+__global__ void __launch_bounds__(SC_T, SC_CTAS)
 k_part_scatter(FS fs, const i64 *__restrict__ val, i64 n, bool vec, PartStore ps, i64 *mm) {
-    static_assert(ST == MAX_PARTS, "one thread per bucket counter");
+    static_assert(SC_T >= MAX_PARTS, "one thread per bucket counter");
     __shared__ ScatterSmem sm;
     const int tid = threadIdx.x, lane = tid & 31;
-    const i64 tiles = (n + STILE - 1) / STILE;
+    const i64 tiles = (n + SC_TILE - 1) / SC_TILE;
     typedef typename FS::key_t KT;   // running min/max in the key column's own width (register pressure)
     KT lo = sizeof(KT) == 4 ? (KT)0x7FFFFFFF : (KT)RFB_INF_I64, hi = sizeof(KT) == 4 ? (KT)NULL_I32 : (KT)NULL_I64;
-    sm.cnt[tid] = 0;
+    if (tid < MAX_PARTS) sm.cnt[tid] = 0;
     __syncthreads();
     for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        i64 k[8], v[8];
-        bool sel[8];
-        load_tile<ST, true>(fs, val, tile * STILE, n, vec, k, v, sel);
-        u32 pk[8], pos[8];
+        i64 k[SC_R], v[SC_R];
+        bool sel[SC_R];
+        load_tile<SC_T, true, SC_R>(fs, val, tile * SC_TILE, n, vec, k, v, sel);
+        u32 pk[SC_R], pos[SC_R];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < SC_R; j++) {
             if (sel[j]) { lo = (KT)k[j] < lo ? (KT)k[j] : lo; hi = (KT)k[j] > hi ? (KT)k[j] : hi; }
             pk[j] = sel[j] ? (u32)((u64)k[j] & ((1u << (KP_LOG + 8)) - 1u)) : 0xFFFFFFFFu;
             const u32 part = sel[j] ? pk[j] >> KP_LOG : 0xFFFFFFFFu;
@@ -965,42 +972,46 @@ k_part_scatter(FS fs, const i64 *__restrict__ val, i64 n, bool vec, PartStore ps
             } else if (sel[j]) pos[j] = atomicAdd(&sm.cnt[part], 1u);
         }
         __syncthreads();
-        const u32 c = sm.cnt[tid];
-        u32 incl = c;
+        u32 c = 0, incl = 0, start = 0, phys0 = 0, phys1 = 0;
+        if (tid < MAX_PARTS) {
+            c = sm.cnt[tid];
+            incl = c;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        if (lane == 31) sm.wtot[tid >> 5] = incl;
-        // reserve [start, start + c) of bucket `tid`, allocate the block(s) that begin inside the run, look up the two
-        // blocks the run can touch
-        u32 start = 0, phys0 = 0, phys1 = 0;
-        if (c) {
-            start = atomicAdd(&ps.cursor[tid], c);
-            const u32 b0 = start >> PB_LOG, b1 = (start + c - 1) >> PB_LOG;
-            u32 *row = ps.bt + (size_t)tid * ps.bt_stride;
-            if ((start & (PB - 1)) == 0) { phys0 = atomicAdd(ps.next_block, 1u) + 1; st_relaxed_u32(row + b0, phys0); }
-            if (b1 != b0) { phys1 = atomicAdd(ps.next_block, 1u) + 1; st_relaxed_u32(row + b1, phys1); }
-            while (!phys0) phys0 = ld_relaxed_u32(row + b0);
-            if (b1 == b0) phys1 = phys0;
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (lane == 31) sm.wtot[tid >> 5] = incl;
+            // reserve [start, start + c) of bucket `tid`, allocate the block(s) that begin inside the run, look up the two
+            // blocks the run can touch
+            if (c) {
+                start = atomicAdd(&ps.cursor[tid], c);
+                const u32 b0 = start >> PB_LOG, b1 = (start + c - 1) >> PB_LOG;
+                u32 *row = ps.bt + (size_t)tid * ps.bt_stride;
+                if ((start & (PB - 1)) == 0) { phys0 = atomicAdd(ps.next_block, 1u) + 1; st_relaxed_u32(row + b0, phys0); }
+                if (b1 != b0) { phys1 = atomicAdd(ps.next_block, 1u) + 1; st_relaxed_u32(row + b1, phys1); }
+                while (!phys0) phys0 = ld_relaxed_u32(row + b0);
+                if (b1 == b0) phys1 = phys0;
+            }
         }
         __syncthreads();
-        u32 before = 0;
-        for (int w = 0; w < (tid >> 5); w++) before += sm.wtot[w];
-        const u32 lbase = before + incl - c;
-        const u32 in_block = start & (PB - 1), room = PB - in_block;           // rows left in the first block
-        uint4 d;
-        d.x = (phys0 - 1) * (u32)PB + in_block - lbase;
-        d.y = lbase + room;
-        d.z = (phys1 - 1) * (u32)PB - (lbase + room);
-        d.w = lbase;
-        sm.desc[tid] = d;
-        sm.cnt[tid] = 0;                                   // for the next tile (this tile's counts live in registers now)
-        if (tid == ST - 1) sm.total = before + incl;
+        if (tid < MAX_PARTS) {
+            u32 before = 0;
+            for (int w = 0; w < (tid >> 5); w++) before += sm.wtot[w];
+            const u32 lbase = before + incl - c;
+            const u32 in_block = start & (PB - 1), room = PB - in_block;           // rows left in the first block
+            uint4 d;
+            d.x = (phys0 - 1) * (u32)PB + in_block - lbase;
+            d.y = lbase + room;
+            d.z = (phys1 - 1) * (u32)PB - (lbase + room);
+            d.w = lbase;
+            sm.desc[tid] = d;
+            sm.cnt[tid] = 0;                                   // for the next tile (this tile's counts live in registers now)
+            if (tid == MAX_PARTS - 1) sm.total = before + incl;
+        }
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < SC_R; j++) {
             if (!sel[j]) continue;
             const u32 q = sm.desc[pk[j] >> KP_LOG].w + pos[j];
             sm.val[q] = (u64)v[j];
@@ -1009,17 +1020,17 @@ k_part_scatter(FS fs, const i64 *__restrict__ val, i64 n, bool vec, PartStore ps
         __syncthreads();
         const u32 total = sm.total;
 #pragma unroll
-        for (int half = 0; half < 4; half++) {             // 2 independent elements per step: the shared-memory lookups overlap
+        for (int step = 0; step < SC_R / 2; step++) {      // 2 independent elements per step: the shared-memory lookups overlap
             u32 w[2];
             u64 vv[2];
 #pragma unroll
             for (int j = 0; j < 2; j++) {
-                const u32 q = (half * 2 + j) * ST + tid;
+                const u32 q = (step * 2 + j) * SC_T + tid;
                 if (q < total) { w[j] = sm.pk[q]; vv[j] = sm.val[q]; }
             }
 #pragma unroll
             for (int j = 0; j < 2; j++) {
-                const u32 q = (half * 2 + j) * ST + tid;
+                const u32 q = (step * 2 + j) * SC_T + tid;
                 if (q < total) {
                     const uint4 dd = sm.desc[w[j] >> KP_LOG];
                     const u32 g = q + (q < dd.y ? dd.x : dd.z);
@@ -1212,7 +1223,7 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
             RFB_CUDA(cudaMemsetAsync(pw, 0, ctl_bytes + bt_bytes, ctx->stream));
             k_fused_scope_init<<<1, 32, 0, ctx->stream>>>(mm);
             RFB_CHECK_LAUNCH(ctx);
-            k_part_scatter<FS><<<sgrid, ST, 0, ctx->stream>>>(fs, val, n, vec, ps, mm);
+            k_part_scatter<FS><<<rfb_grid_for(ctx, n, SC_TILE, SC_CTAS), SC_T, 0, ctx->stream>>>(fs, val, n, vec, ps, mm);
             RFB_CHECK_LAUNCH(ctx);
             have_scope = scattered = true;
         }
