@@ -10,7 +10,7 @@
 //
 // Per pass:  HIST    G persistent CTAs, CTA b owns the contiguous chunk b of the current sequence: 256-bin counts
 //            SCAN    exclusive scan of the digit-major (256 x G) count matrix  -> first output slot of (digit, chunk)
-//            SCATTER CTA b walks its chunk tile by tile (3072 rows): warp-level multisplit (match.any) ranks rows of equal
+//            SCATTER CTA b walks its chunk tile by tile (3072 rows): warp-level multisplit (per-bit ballots) ranks rows of equal
 //                    digit in (warp, step, lane) order, warp counts are scanned across the CTA, the tile is ordered by
 //                    digit in shared memory and leaves as one contiguous run per digit; a running per-digit base carried
 //                    in shared memory keeps tiles of one chunk in order => stable.
@@ -159,7 +159,15 @@ k_scatter(Src src, i64 n, i64 chunk, int shift, const i64 *__restrict__ offs /* 
             const bool ok = i < hi;
             const u32 d = (u32)(key[j] >> shift) & 255u;
             const u32 vmask = __ballot_sync(0xffffffffu, ok);
-            const u32 peers = __match_any_sync(0xffffffffu, ok ? d : 256u + (u32)lane) & vmask;
+            // lanes holding the same digit: eight ballots (one per digit bit) instead of __match_any_sync — MATCH runs on the
+            // ADU pipe at ~17 cycles per warp instruction on B200 and bounded this kernel; VOTE + LOP3 issue at full rate
+            u32 peers = vmask;
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const bool bit = (d >> b) & 1u;
+                const u32 bal = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? bal : ~bal;
+            }
             const u32 prior = whist[warp][d];
             __syncwarp();
             if (ok && (peers & lt) == 0) whist[warp][d] = prior + __popc(peers);   // lowest peer lane publishes
