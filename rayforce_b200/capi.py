@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librfb200.so")
+LIB_PATH = os.environ.get("RFB200_LIB") or os.path.join(HERE, "librfb200.so")   # RFB200_LIB: an alternative build (kernel-geometry sweeps)
 
 # reference type codes (core/rayforce.h:50-62 of the reference)
 B8, U8, I16, I32, I64, SYMBOL, DATE, TIME, TIMESTAMP, F64 = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
