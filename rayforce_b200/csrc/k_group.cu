@@ -19,6 +19,7 @@
 // Aggregates are per-group accumulators updated with L2 atomics (red.global), finalised by a small per-group kernel
 // (sticky-null sums, +INF/NULL-initialised min/max, f64 averages).
 #include "rfb_scan.cuh"
+#include "rfb_moments.cuh"
 
 namespace {
 
@@ -120,10 +121,10 @@ __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_scope(Src src, i64 n
 // ------------------------------------------------------------------ 2. claim
 
 template <typename Src, typename Slot, bool INSERT>
-__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_claim(Src src, Slot slot, i64 n, u64 *first_row) {
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_claim(Src src, Slot slot, i64 r0, i64 n, u64 *first_row) {   // rows [r0, n)
     constexpr int U = 4;
     const i64 stride = (i64)gridDim.x * THREADS;
-    i64 i = (i64)blockIdx.x * THREADS + threadIdx.x;
+    i64 i = r0 + (i64)blockIdx.x * THREADS + threadIdx.x;
     for (; i + (U - 1) * stride < n; i += U * stride) {
         i64 k[U];
 #pragma unroll
@@ -141,6 +142,15 @@ __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_claim(Src src, Slot 
         if constexpr (INSERT) s = slot.insert(k); else s = slot(k);
         claim_first(first_row, s, i);
     }
+}
+
+// mm[4] = slots whose first row is known
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_claimed_count(const u64 *first_row, i64 slots, i64 *mm) {
+    __shared__ i64 red[32];
+    i64 claimed = 0;
+    for (i64 s = (i64)blockIdx.x * THREADS + threadIdx.x; s < slots; s += (i64)gridDim.x * THREADS) claimed += first_row[s] != NO_ROW;
+    claimed = block_reduce<i64>(claimed, OpAddWrap(), 0, red);
+    if (threadIdx.x == 0) atomicAdd((unsigned long long *)&mm[4], (unsigned long long)claimed);
 }
 
 // max over the claimed first rows (bounds the numbering pass)
@@ -202,8 +212,31 @@ template <typename Src, typename Slot, bool INSERT>
 int number_groups(rfb_ctx_t *ctx, Src src, Slot slot, i64 len, i64 slots, u64 *first_row, i64 *gid_of_slot, void *tile_work,
                   i64 *mm, i64 *group_ids, i64 *first_ids, i64 *groups) {
     const int grid = rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM);
-    k_claim<Src, Slot, INSERT><<<grid, THREADS, 0, ctx->stream>>>(src, slot, len, first_row);
-    RFB_CHECK_LAUNCH(ctx);
+    if constexpr (INSERT) {
+        k_claim<Src, Slot, INSERT><<<grid, THREADS, 0, ctx->stream>>>(src, slot, 0, len, first_row);
+        RFB_CHECK_LAUNCH(ctx);
+    } else {
+        // direct addressing: claims run over a growing row prefix and stop as soon as EVERY slot of the key range has its first
+        // row (low-cardinality keys: all of them show up within the first few thousand rows; claiming over the whole column
+        // would only hammer the same few L2 lines — 100 keys cost 1.1 ms per 1e7 rows that way).  A range with unused
+        // slots never completes and ends up claiming over all rows, as before.
+        i64 r0 = 0, r1 = 32 * slots > 65536 ? 32 * slots : 65536;
+        while (true) {
+            if (r1 > len) r1 = len;
+            k_claim<Src, Slot, INSERT><<<rfb_grid_for(ctx, r1 - r0, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(src, slot, r0, r1, first_row);
+            RFB_CHECK_LAUNCH(ctx);
+            if (r1 == len) break;
+            RFB_CUDA(cudaMemsetAsync(mm + 4, 0, 8, ctx->stream));
+            k_claimed_count<<<rfb_grid_for(ctx, slots, THREADS, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(first_row, slots, mm);
+            RFB_CHECK_LAUNCH(ctx);
+            i64 claimed = 0;
+            int rc2 = d2h_sync(ctx, &claimed, mm + 4, 8);
+            if (rc2) return rc2;
+            if (claimed == slots) break;
+            r0 = r1;
+            r1 = r1 * 4;
+        }
+    }
     k_max_first<<<rfb_grid_for(ctx, slots, THREADS, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(first_row, slots, mm);
     RFB_CHECK_LAUNCH(ctx);
     i64 limit = 0;
@@ -416,14 +449,13 @@ extern "C" int rfb_group_keys_i64_dev(rfb_ctx_t *ctx, int ncols, const int64_t *
     }
     i64 stride = 1;
     for (int c = ncols - 1; c >= 0; c--) { f.stride[c] = stride; stride *= range[c]; }
-    i64 *fused = nullptr;
-    RFB_CUDA(cudaMalloc(&fused, (size_t)len * 8));
+    void *aux;
+    int rc = rfb_ensure_aux(ctx, (size_t)len * 8, &aux);
+    if (rc) return rc;
+    i64 *fused = (i64 *)aux;
     k_fuse_keys<<<rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(f, filter, len, fused);
-    ctx->launches++;
-    int rc = cudaGetLastError() == cudaSuccess ? rfb_group_i64_dev(ctx, fused, nullptr, len, group_ids, first_ids, info) : RFB_ERR_CUDA;
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(fused);
-    return rc;
+    RFB_CHECK_LAUNCH(ctx);
+    return rfb_group_i64_dev(ctx, fused, nullptr, len, group_ids, first_ids, info);
 }
 
 // ------------------------------------------------------------------ grouped aggregates
@@ -439,6 +471,25 @@ struct ValRow {
 __device__ __forceinline__ f64 key_to_f64(u64 k) {  // inverse of f64_sort_key; key 0 = null
     if (k == 0) return null_f64();
     return bits_f64((k & 0x8000000000000000ULL) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k);
+}
+
+// ---- shared-memory accumulators (32-bit words)
+constexpr u32 NULL_FLAG = 0x80000000u;
+struct SAcc { u32 *lo, *hi, *cnt; };
+
+__device__ __forceinline__ void sacc_add(const SAcc &a, u32 s, i64 v) {
+    if (v == NULL_I64) atomicOr(&a.cnt[s], NULL_FLAG);
+    else {
+        const u32 lo = (u32)(u64)v;
+        u32 hi = (u32)((u64)v >> 32);
+        const u32 old = atomicAdd(&a.lo[s], lo);
+        hi += (u32)((u32)(old + lo) < lo);   // this row wrapped the low word: carry
+        if (hi) atomicAdd(&a.hi[s], hi);
+    }
+    atomicAdd(&a.cnt[s], 1u);
+}
+__device__ __forceinline__ void sacc_zero(const SAcc &a, int slots) {
+    for (int s = threadIdx.x; s < slots; s += blockDim.x) { a.lo[s] = 0; a.hi[s] = 0; a.cnt[s] = 0; }
 }
 
 enum { AK_SUM_I64, AK_SUM_I16, AK_SUM_F64, AK_MIN_I64, AK_MAX_I64, AK_MIN_I32, AK_MAX_I32, AK_MIN_I16, AK_MAX_I16, AK_MIN_F64,
@@ -509,6 +560,7 @@ template <int KIND> __device__ __forceinline__ void aggr_merge(void *acc, void *
 }
 
 constexpr int PRIV_GROUPS = 3072;   // CTA-private accumulators in shared memory: 2 x 8 B x 3072 = 48 KB
+constexpr int PRIV32_GROUPS = 4608; // 32-bit-word accumulators (sums, counts, averages of integers): 12 B x 4608 = 54 KB, 4 CTAs per SM
 
 // PRIV: groups <= PRIV_GROUPS.  Every CTA folds its rows into shared-memory accumulators (initialised from the device-wide
 // ones' initial values, which are each operator's identity) and merges them once at the end: the hot atomics never leave
@@ -564,6 +616,67 @@ k_aggr(const V *__restrict__ val, ValRow row, const i64 *__restrict__ gid, i64 n
     }
 }
 
+// PRIV for the kinds whose accumulators are 64-bit integer sums and counts: 32-bit shared atomics with carry (SAcc) instead
+// of 64-bit shared atomicAdd, which sm_100a runs as a compare-and-swap loop.  cnt word: SUM -> sticky-null flag only,
+// COUNT -> rows, AVG -> non-null rows.
+template <int KIND, typename V>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_aggr_priv32(const V *__restrict__ val, ValRow row, const i64 *__restrict__ gid, i64 n, int groups, void *acc, void *aux) {
+    constexpr int U = 4;
+    extern __shared__ u32 s_acc32[];
+    const SAcc a{s_acc32, s_acc32 + groups, s_acc32 + 2 * groups};
+    sacc_zero(a, groups);
+    __syncthreads();
+    auto one = [&](u32 g, V v) {
+        if constexpr (KIND == AK_COUNT) atomicAdd(&a.cnt[g], 1u);
+        else if constexpr (KIND == AK_SUM_I64) {
+            if (v == NULL_I64) atomicOr(&a.cnt[g], NULL_FLAG);
+            else {
+                const u32 lo = (u32)(u64)v;
+                u32 hi = (u32)((u64)v >> 32);
+                const u32 old = atomicAdd(&a.lo[g], lo);
+                hi += (u32)((u32)(old + lo) < lo);
+                if (hi) atomicAdd(&a.hi[g], hi);
+            }
+        } else {   // averages: i64 sum of the non-null values + their count
+            if (!Elem<V>::is_null(v)) sacc_add(a, g, (i64)v);
+        }
+    };
+    const i64 stride = (i64)gridDim.x * THREADS;
+    i64 i = (i64)blockIdx.x * THREADS + threadIdx.x;
+    for (; i + (U - 1) * stride < n; i += U * stride) {
+        i64 g[U];
+        V v[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            g[j] = ld_stream(gid + i + j * stride);
+            if constexpr (KIND == AK_COUNT) v[j] = V();
+            else v[j] = row.filter ? __ldg(val + row(i + j * stride)) : ld_stream(val + i + j * stride);
+        }
+#pragma unroll
+        for (int j = 0; j < U; j++) one((u32)g[j], v[j]);
+    }
+    for (; i < n; i += stride) {
+        V v;
+        if constexpr (KIND == AK_COUNT) v = V();
+        else v = row.filter ? __ldg(val + row(i)) : ld_stream(val + i);
+        one((u32)ld_stream(gid + i), v);
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < groups; g += THREADS) {
+        const u32 c = a.cnt[g];
+        const u64 sum = ((u64)a.hi[g] << 32) | a.lo[g];
+        if constexpr (KIND == AK_COUNT) { if (c) atomicAdd((unsigned long long *)acc + g, (unsigned long long)c); }
+        else if constexpr (KIND == AK_SUM_I64) {
+            if (sum) atomicAdd((unsigned long long *)acc + g, (unsigned long long)sum);
+            if (c & NULL_FLAG) ((u32 *)aux)[g] = 1u;
+        } else if (c) {
+            atomicAdd((unsigned long long *)acc + g, (unsigned long long)sum);
+            atomicAdd((unsigned long long *)aux + g, (unsigned long long)(c & ~NULL_FLAG));
+        }
+    }
+}
+
 template <int KIND> __global__ void k_aggr_final(void *out, const void *acc, const void *aux, i64 groups) {
     for (i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (i64)gridDim.x * blockDim.x) {
         if constexpr (KIND == AK_SUM_I64) { if (((const u32 *)aux)[g]) ((i64 *)out)[g] = NULL_I64; }
@@ -586,6 +699,14 @@ int run_aggr(rfb_ctx_t *ctx, const void *val, const i64 *filter, const i64 *gid,
     if (len > 0) {
         const int grid = rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM);
         // F64 sums stay on the device-wide path (one accumulator per group, like the reference's single running sum)
+        if constexpr (KIND == AK_SUM_I64 || KIND == AK_COUNT || KIND == AK_AVG_I64 || KIND == AK_AVG_I32 || KIND == AK_AVG_I16) {
+            if (groups <= PRIV32_GROUPS && len >= 65536 && len / grid < (1ll << 31)) {
+                RFB_CUDA(cudaFuncSetAttribute(k_aggr_priv32<KIND, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRIV32_GROUPS * 12));
+                k_aggr_priv32<KIND, V><<<grid, THREADS, (size_t)groups * 12, ctx->stream>>>((const V *)val, ValRow{filter}, gid, len, (int)groups, acc, aux);
+                RFB_CHECK_LAUNCH(ctx);
+                goto finalise;
+            }
+        }
         if constexpr (KIND != AK_SUM_F64) {
             if (groups <= PRIV_GROUPS && len >= 65536) {
                 k_aggr<KIND, V, true><<<grid, THREADS, (size_t)groups * 16, ctx->stream>>>((const V *)val, ValRow{filter}, gid, len, groups, acc, aux);
@@ -645,7 +766,14 @@ extern "C" int rfb_aggr_dev(rfb_ctx_t *ctx, int op, int val_type, const void *va
                 RFB_CUDA(cudaMemsetAsync(acc, 0, (size_t)groups * 4, ctx->stream));
                 return run_aggr<AK_SUM_I16, i16>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
             }
-            return run_aggr<AK_SUM_F64, f64>(ctx, val, filter, group_ids, len, groups, out, aux, out);
+            // f64 sums: per-group moments with shared-memory privatisation at low cardinality (rfb_moments.cuh); the count it
+            // also produces lands in the workspace and is not used
+            RFB_CUDA(cudaMemsetAsync(acc, 0, (size_t)groups * 8, ctx->stream));
+            rc = moments::launch<f64, false>(ctx, val, filter, group_ids, len, groups, (f64 *)out, nullptr, (unsigned long long *)acc, (u32 *)aux);
+            if (rc) return rc;
+            k_aggr_final<AK_SUM_F64><<<rfb_grid_for(ctx, groups, 256, 8), 256, 0, ctx->stream>>>(out, out, aux, groups);
+            RFB_CHECK_LAUNCH(ctx);
+            return RFB_OK;
         case RFB_A_MIN:
             if (k == K_I64) { rc = fill<i64>(ctx, (i64 *)out, groups, RFB_INF_I64); if (rc) return rc; return run_aggr<AK_MIN_I64, i64>(ctx, val, filter, group_ids, len, groups, out, aux, out); }
             if (k == K_I32) { rc = fill<i32>(ctx, (i32 *)out, groups, (i32)0x7FFFFFFF); if (rc) return rc; return run_aggr<AK_MIN_I32, i32>(ctx, val, filter, group_ids, len, groups, out, aux, out); }
@@ -665,7 +793,11 @@ extern "C" int rfb_aggr_dev(rfb_ctx_t *ctx, int op, int val_type, const void *va
             if (k == K_I64) return run_aggr<AK_AVG_I64, i64>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
             if (k == K_I32) return run_aggr<AK_AVG_I32, i32>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
             if (k == K_I16) return run_aggr<AK_AVG_I16, i16>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
-            return run_aggr<AK_AVG_F64, f64>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
+            rc = moments::launch<f64, false>(ctx, val, filter, group_ids, len, groups, (f64 *)acc, nullptr, (unsigned long long *)aux, nullptr);
+            if (rc) return rc;
+            k_aggr_final<AK_AVG_F64><<<rfb_grid_for(ctx, groups, 256, 8), 256, 0, ctx->stream>>>(out, acc, aux, groups);
+            RFB_CHECK_LAUNCH(ctx);
+            return RFB_OK;
     }
 }
 
@@ -704,7 +836,6 @@ constexpr int STILE = ST * 8;
 #define RFB_SC_CTAS 4
 #endif
 constexpr int SC_T = RFB_SC_T, SC_R = RFB_SC_R, SC_CTAS = RFB_SC_CTAS, SC_TILE = SC_T * SC_R;   // scatter kernel geometry
-constexpr u32 NULL_FLAG = 0x80000000u;
 
 // two consecutive elements with one vector load (p must be aligned to 2 * sizeof(T))
 template <typename T> __device__ __forceinline__ void ld_pair(const T *p, i64 pair, T &a, T &b) {
@@ -774,23 +905,6 @@ __device__ __forceinline__ void load_tile(const FS &fs, const i64 *__restrict__ 
     }
 }
 
-// ---- shared-memory accumulators (32-bit words)
-struct SAcc { u32 *lo, *hi, *cnt; };
-
-__device__ __forceinline__ void sacc_add(const SAcc &a, u32 s, i64 v) {
-    if (v == NULL_I64) atomicOr(&a.cnt[s], NULL_FLAG);
-    else {
-        const u32 lo = (u32)(u64)v;
-        u32 hi = (u32)((u64)v >> 32);
-        const u32 old = atomicAdd(&a.lo[s], lo);
-        hi += (u32)((u32)(old + lo) < lo);   // this row wrapped the low word: carry
-        if (hi) atomicAdd(&a.hi[s], hi);
-    }
-    atomicAdd(&a.cnt[s], 1u);
-}
-__device__ __forceinline__ void sacc_zero(const SAcc &a, int slots) {
-    for (int s = threadIdx.x; s < slots; s += blockDim.x) { a.lo[s] = 0; a.hi[s] = 0; a.cnt[s] = 0; }
-}
 // merge into the device-wide accumulators and clear; slot0 = device-wide slot of local slot 0 (a local slot that
 // received rows always maps inside [0, range))
 __device__ __forceinline__ void sacc_flush(const SAcc &a, int slots, i64 slot0, const Accums &ga) {

@@ -10,6 +10,7 @@
 // are constant over the column, so G groups cost ceil(log256 G) passes.  Medians need every group's values in ray_asc
 // order: a stable sort by value followed by a stable sort by group id leaves the rows ordered by (group, value).
 #include "rfb_common.cuh"
+#include "rfb_moments.cuh"
 
 namespace {
 
@@ -51,27 +52,8 @@ __global__ void k_fill_f64(f64 *p, i64 n, f64 v) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) p[i] = v;
 }
 
-// ---- deviation: per-group sum, sum of squares (f64, as the reference accumulates them) and non-null count
-template <typename T> __device__ __forceinline__ bool stat_value(T x, f64 &v) {
-    if (Elem<T>::is_null(x)) return false;
-    v = (f64)x;
-    return true;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(THREADS, 4)
-k_group_moments(const T *__restrict__ val, const i64 *__restrict__ filter, const i64 *__restrict__ gid, i64 n, f64 *sum, f64 *sumsq,
-                unsigned long long *cnt) {
-    for (i64 i = (i64)blockIdx.x * THREADS + threadIdx.x; i < n; i += (i64)gridDim.x * THREADS) {
-        const T x = filter ? __ldg(val + ld_stream(filter + i)) : ld_stream(val + i);
-        f64 v;
-        if (!stat_value<T>(x, v)) continue;
-        const i64 g = ld_stream(gid + i);
-        atomicAdd(sum + g, v);
-        atomicAdd(sumsq + g, __dmul_rn(v, v));
-        atomicAdd(cnt + g, 1ULL);
-    }
-}
+// ---- deviation: per-group sum, sum of squares (f64, as the reference accumulates them) and non-null count: rfb_moments.cuh
+template <typename T> __device__ __forceinline__ bool stat_value(T x, f64 &v) { return moments::value_of<T>(x, v); }
 
 // core/aggr.c:2893-2906: 0 rows -> null, 1 row -> 0, else sqrt(max(sumsq/n - mean^2, 0))
 __global__ void __launch_bounds__(THREADS) k_group_stddev(const f64 *sum, const f64 *sumsq, const unsigned long long *cnt, i64 groups, f64 *out) {
@@ -113,14 +95,13 @@ __global__ void __launch_bounds__(THREADS, 4) k_sq_dev(const T *__restrict__ x, 
     if (threadIdx.x == 0) { *out = t; *ticket = 0; }
 }
 
-struct Temp {   // one cudaMalloc'ed block, carved up; freed when it goes out of scope (after the stream has drained)
+struct Temp {   // the context's auxiliary buffer, carved up
     rfb_ctx_t *ctx;
     char *base = nullptr;
-    size_t used = 0, cap = 0;
+    size_t used = 0;
     explicit Temp(rfb_ctx_t *c) : ctx(c) {}
-    int reserve(size_t bytes) { cap = bytes; return cudaMalloc(&base, bytes ? bytes : 256) == cudaSuccess ? RFB_OK : RFB_ERR_CUDA; }
+    int reserve(size_t bytes) { void *p; const int rc = rfb_ensure_aux(ctx, bytes ? bytes : 256, &p); base = (char *)p; return rc; }
     template <typename T> T *take(i64 n) { T *p = (T *)(base + used); used += align256((size_t)(n > 0 ? n : 1) * sizeof(T)); return p; }
-    ~Temp() { if (base) { cudaStreamSynchronize(ctx->stream); cudaFree(base); } }
 };
 
 int take8(rfb_ctx_t *ctx, const void *src, const i64 *idx, i64 n, void *out) {
@@ -196,16 +177,13 @@ int rfb_aggr_stddev_launch(rfb_ctx_t *ctx, int val_type, const void *val, const 
     f64 *sum = (f64 *)w, *sumsq = (f64 *)((char *)w + bg);
     unsigned long long *cnt = (unsigned long long *)((char *)w + 2 * bg);
     RFB_CUDA(cudaMemsetAsync(w, 0, 3 * bg, ctx->stream));
-    if (len > 0) {
-        const int grid = rfb_grid_for(ctx, len, THREADS * 4, 4);
-        switch (rfb_kind_of(val_type)) {
-            case K_I16: k_group_moments<i16><<<grid, THREADS, 0, ctx->stream>>>((const i16 *)val, filter, group_ids, len, sum, sumsq, cnt); break;
-            case K_I32: k_group_moments<i32><<<grid, THREADS, 0, ctx->stream>>>((const i32 *)val, filter, group_ids, len, sum, sumsq, cnt); break;
-            case K_I64: k_group_moments<i64><<<grid, THREADS, 0, ctx->stream>>>((const i64 *)val, filter, group_ids, len, sum, sumsq, cnt); break;
-            default: k_group_moments<f64><<<grid, THREADS, 0, ctx->stream>>>((const f64 *)val, filter, group_ids, len, sum, sumsq, cnt); break;
-        }
-        RFB_CHECK_LAUNCH(ctx);
+    switch (rfb_kind_of(val_type)) {
+        case K_I16: rc = moments::launch<i16, true>(ctx, val, filter, group_ids, len, groups, sum, sumsq, cnt, nullptr); break;
+        case K_I32: rc = moments::launch<i32, true>(ctx, val, filter, group_ids, len, groups, sum, sumsq, cnt, nullptr); break;
+        case K_I64: rc = moments::launch<i64, true>(ctx, val, filter, group_ids, len, groups, sum, sumsq, cnt, nullptr); break;
+        default: rc = moments::launch<f64, true>(ctx, val, filter, group_ids, len, groups, sum, sumsq, cnt, nullptr); break;
     }
+    if (rc) return rc;
     k_group_stddev<<<rfb_grid_for(ctx, groups, THREADS, 8), THREADS, 0, ctx->stream>>>(sum, sumsq, cnt, groups, out);
     RFB_CHECK_LAUNCH(ctx);
     return RFB_OK;

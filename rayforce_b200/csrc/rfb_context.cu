@@ -34,6 +34,22 @@ int rfb_ensure_work(rfb_ctx_t *ctx, size_t bytes, void **out) {
     return RFB_OK;
 }
 
+int rfb_ensure_aux(rfb_ctx_t *ctx, size_t bytes, void **out) {
+    if (bytes > ctx->aux_bytes) {
+        if (ctx->d_aux) {
+            RFB_CUDA(cudaStreamSynchronize(ctx->stream));
+            RFB_CUDA(cudaFree(ctx->d_aux));
+            ctx->d_aux = nullptr;
+            ctx->aux_bytes = 0;
+        }
+        size_t want = bytes + (bytes >> 3) + (1 << 20);
+        RFB_CUDA(cudaMalloc(&ctx->d_aux, want));
+        ctx->aux_bytes = want;
+    }
+    *out = ctx->d_aux;
+    return RFB_OK;
+}
+
 extern "C" {
 
 int rfb_abi_version(void) { return RFB_ABI_VERSION; }
@@ -99,6 +115,7 @@ void rfb_ctx_destroy(rfb_ctx_t *ctx) {
     }
     rfb_copy_shutdown(ctx);
     if (ctx->d_work) cudaFree(ctx->d_work);
+    if (ctx->d_aux) cudaFree(ctx->d_aux);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
