@@ -1016,6 +1016,53 @@ k_fused_accum_smem(FS fs, const i64 *__restrict__ val, i64 n, bool vec, i64 kmin
     sacc_flush(a, range, 0, ga);
 }
 
+// strategy 1 without a scope pass: slot = key mod KP.  Any KP consecutive integers have distinct residues, so when the keys
+// turn out to span fewer than KP values (the kernel finds min/max on the way, a row sample made it likely) the residue IS a
+// perfect hash, and k_mod_remap afterwards moves slot (key mod KP) to slot (key - min).  Saves the 4-8 B/row scope pass.
+template <typename FS>
+__global__ void __launch_bounds__(PT, 2)
+k_fused_accum_mod(FS fs, const i64 *__restrict__ val, i64 n, bool vec, Accums gmod, i64 *mm) {
+    extern __shared__ u32 s_acc[];
+    __shared__ i64 red[32];
+    const SAcc a{s_acc, s_acc + KP, s_acc + 2 * KP};
+    sacc_zero(a, KP);
+    __syncthreads();
+    typedef typename FS::key_t KT;
+    KT lo = sizeof(KT) == 4 ? (KT)0x7FFFFFFF : (KT)RFB_INF_I64, hi = sizeof(KT) == 4 ? (KT)NULL_I32 : (KT)NULL_I64;
+    const i64 tiles = (n + PTILE - 1) / PTILE;
+    for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        i64 k[8], v[8];
+        bool sel[8];
+        load_tile<PT, true, 8>(fs, val, tile * PTILE, n, vec, k, v, sel);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (sel[j]) {
+                lo = (KT)k[j] < lo ? (KT)k[j] : lo;
+                hi = (KT)k[j] > hi ? (KT)k[j] : hi;
+                sacc_add(a, (u32)((u64)k[j] & (KP - 1)), v[j]);
+            }
+    }
+    __syncthreads();
+    sacc_flush(a, KP, 0, gmod);
+    struct Mn { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b < a ? b : a; } };
+    struct Mx { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b > a ? b : a; } };
+    const i64 lo64 = block_reduce<i64>((i64)lo, Mn(), RFB_INF_I64, red);
+    const i64 hi64 = block_reduce<i64>((i64)hi, Mx(), NULL_I64, red);
+    if (threadIdx.x == 0) {
+        atomicMin((long long *)&mm[0], (long long)lo64);
+        atomicMax((long long *)&mm[1], (long long)hi64);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS) k_mod_remap(Accums gmod, i64 kmin, i64 range, Accums a) {
+    for (i64 s = (i64)blockIdx.x * THREADS + threadIdx.x; s < range; s += (i64)gridDim.x * THREADS) {
+        const u64 m = ((u64)kmin + (u64)s) & (KP - 1);
+        a.sum[s] = gmod.sum[m];
+        a.cnt[s] = gmod.cnt[m];
+        a.has_null[s] = gmod.has_null[m];
+    }
+}
+
 // ---- accumulate, strategy 2: partition, then accumulate per partition
 //
 // A row's partition is its ABSOLUTE key bucket (key >> KP_LOG) mod 256 and its slot the low KP_LOG key bits, so the scatter
@@ -1298,9 +1345,10 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
     auto parts_of = [](i64 kmin, i64 kmax) { return (i64)(((u64)kmax - (u64)(kmin & ~(i64)(KP - 1))) >> KP_LOG) + 1; };
     i64 h[2];
     int rc;
-    bool have_scope = false, scattered = false;
+    bool have_scope = false, scattered = false, modded = false;
     void *w = nullptr;
     PartStore ps{};
+    Accums gmod{};
     // workspace of the partitioned strategy: accumulators for the largest range it accepts, then the block store
     const i64 max_range = (i64)MAX_PARTS * KP;
     const size_t pb8 = align256((size_t)max_range * 8), pb4 = align256((size_t)max_range * 4);
@@ -1318,7 +1366,26 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
         }
         rc = d2h_sync(ctx, h, mm, 16);
         if (rc) return rc;
-        const bool try_part = h[0] <= h[1] && (forced == 2 || (i64)((u64)h[1] - (u64)h[0]) >= KP) && (u64)h[1] - (u64)h[0] < (u64)max_range &&
+        const bool try_mod = h[0] <= h[1] && (forced == 0 || forced == 1) && (u64)h[1] - (u64)h[0] < (u64)KP;
+        if (try_mod) {
+            void *aux;
+            rc = rfb_ensure_aux(ctx, (size_t)KP * 20, &aux);
+            if (rc) return rc;
+            gmod.first_row = nullptr;
+            gmod.sum = (u64 *)aux;
+            gmod.cnt = gmod.sum + KP;
+            gmod.has_null = (u32 *)(gmod.cnt + KP);
+            RFB_CUDA(cudaMemsetAsync(aux, 0, (size_t)KP * 20, ctx->stream));
+            k_fused_scope_init<<<1, 32, 0, ctx->stream>>>(mm);
+            RFB_CHECK_LAUNCH(ctx);
+            const i64 ptiles = (n + PTILE - 1) / PTILE;
+            const int pgrid = (int)(ptiles < 2ll * ctx->sm_count ? ptiles : 2ll * ctx->sm_count);
+            RFB_CUDA(cudaFuncSetAttribute(k_fused_accum_mod<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, KP * 12));
+            k_fused_accum_mod<FS><<<pgrid, PT, KP * 12, ctx->stream>>>(fs, val, n, vec, gmod, mm);
+            RFB_CHECK_LAUNCH(ctx);
+            have_scope = modded = true;
+        }
+        const bool try_part = !modded && h[0] <= h[1] && (forced == 2 || (i64)((u64)h[1] - (u64)h[0]) >= KP) && (u64)h[1] - (u64)h[0] < (u64)max_range &&
                               parts_of(h[0], h[1]) <= MAX_PARTS;
         if (try_part) {
             const u32 blocks = (u32)((n + PB - 1) / PB) + MAX_PARTS + 1;
@@ -1384,7 +1451,10 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
     RFB_CUDA(cudaMemsetAsync(a.sum, 0, (size_t)range * 8, ctx->stream));
     RFB_CUDA(cudaMemsetAsync(a.cnt, 0, (size_t)range * 8, ctx->stream));
     RFB_CUDA(cudaMemsetAsync(a.has_null, 0, (size_t)range * 4, ctx->stream));
-    if (strategy == 1) {
+    if (modded && range <= KP) {        // already accumulated by key residue: move the slots into key order
+        k_mod_remap<<<rfb_grid_for(ctx, range, THREADS, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(gmod, kmin, range, a);
+        RFB_CHECK_LAUNCH(ctx);
+    } else if (strategy == 1) {
         const i64 ptiles = (n + PTILE - 1) / PTILE;
         const int pgrid = (int)(ptiles < 2ll * ctx->sm_count ? ptiles : 2ll * ctx->sm_count);
         RFB_CUDA(cudaFuncSetAttribute(k_fused_accum_smem<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, KP * 12));

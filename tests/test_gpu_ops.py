@@ -401,7 +401,7 @@ def test_fused_group_late_first_occurrence(ctx, oracle):
     assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val, wg, wi.groups)[0])
 
 
-@pytest.mark.parametrize("strategy", ["smem", "part", "l2"])
+@pytest.mark.parametrize("strategy", ["smem", "part", "l2", "auto"])
 @pytest.mark.parametrize("key_type", [ob.I64, ob.I32])
 @pytest.mark.parametrize("with_pred", [False, True])
 @pytest.mark.parametrize("n,card,kmin,skew", [
@@ -416,7 +416,10 @@ def test_fused_group_strategies(ctx, oracle, monkeypatch, strategy, key_type, wi
     memory), sticky nulls, counts, first-occurrence order"""
     if strategy == "smem" and card > 8192:
         pytest.skip("shared-memory strategy needs range <= 8192")
-    monkeypatch.setenv("RFB_GROUP_STRATEGY", strategy)
+    if strategy == "auto":      # what a large column gets: strategy picked from a row sample (scope-free residue / partition passes)
+        monkeypatch.setenv("RFB_PART_MIN_ROWS", "1000")
+    else:
+        monkeypatch.setenv("RFB_GROUP_STRATEGY", strategy)
     r = np.random.default_rng(n + card + (1 if skew else 0))
     keys64 = r.integers(0, card, n).astype(np.int64)
     if skew:
