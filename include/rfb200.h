@@ -263,6 +263,21 @@ int rfb_group_sum_count_dev(rfb_ctx_t *ctx, int key_type, const void *keys, cons
                             int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k, int64_t max_groups,
                             int64_t *out_keys, int64_t *out_sums, int64_t *out_counts, int64_t *groups);
 
+/* ------------------------------------------------------------------ device layer: equi-join row matching */
+
+/* ray_find -> index_find_i64 (core/index.c:1507-1574) for ncols == 1, index_left_join_obj (core/index.c:2886-2928) for a
+ * tuple of ncols (<= 8) I64-kind key columns: ids[i] = the FIRST build row whose key (tuple) equals probe row i's, else
+ * NULL_I64.  Keys compare by bit pattern (a null is a key like any other, core/index.c:59-105).  This is the left join's
+ * row index: column c of the joined table is rfb_gather_dev(right column c, ids). */
+int rfb_find_rows_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const *build_cols, int64_t build_len,
+                      const int64_t *const *probe_cols, int64_t probe_len, int64_t *ids);
+
+/* index_inner_join_obj (core/index.c:2930-3000): the matching pairs, probe rows ascending: probe_ids[j], build_ids[j]
+ * (the first build row of probe row probe_ids[j]'s key); both sized probe_len; *count (host) = number of pairs. */
+int rfb_inner_join_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const *build_cols, int64_t build_len,
+                       const int64_t *const *probe_cols, int64_t probe_len, int64_t *probe_ids, int64_t *build_ids,
+                       int64_t *count);
+
 /* ------------------------------------------------------------------ device layer: sort */
 
 /* ray_sort_asc / ray_sort_desc (core/sort.c:430-479, 691-740): stable permutation (I64 row ids).

@@ -142,6 +142,13 @@ rfb_obj_p rfb_aggr_stddev(rfb_obj_p val, rfb_obj_p index);   /* the reference's 
 rfb_obj_p rfb_aggr_row(rfb_obj_p val, rfb_obj_p index);
 rfb_obj_p rfb_aggr_collect(rfb_obj_p val, rfb_obj_p index);
 
+/* ---- equi-join row matching: index_left_join_obj / index_inner_join_obj (core/index.c:2886-3000;
+ *      lcols / rcols = the key column itself when len == 1, else a LIST of len key columns) and ray_find on two I64-kind
+ *      vectors (core/items.c:320-323).  The joined table itself is then built by the reference's join.c from these row ids. */
+rfb_obj_p rfb_index_left_join_obj(rfb_obj_p lcols, rfb_obj_p rcols, int64_t len);
+rfb_obj_p rfb_index_inner_join_obj(rfb_obj_p lcols, rfb_obj_p rcols, int64_t len);
+rfb_obj_p rfb_ray_find(rfb_obj_p x, rfb_obj_p y);
+
 /* ---- key sort: ray_sort_asc/desc (core/sort.c:430,691) = ray_iasc/idesc (core/order.c:32): stable i64 permutation */
 rfb_obj_p rfb_ray_sort_asc(rfb_obj_p x);
 rfb_obj_p rfb_ray_sort_desc(rfb_obj_p x);

@@ -215,6 +215,22 @@ class Oracle:
         self.L.rfo_group_rows(_ptr(gids), _ptr(filt), gids.shape[0], groups, _ptr(rows), _ptr(offs))
         return rows, offs
 
+    def find_rows(self, build_cols, probe_cols):
+        b = [np.ascontiguousarray(c, np.int64) for c in build_cols]
+        p = [np.ascontiguousarray(c, np.int64) for c in probe_cols]
+        ids = np.empty(p[0].shape[0], np.int64)
+        ba = (C.c_void_p * len(b))(*[c.ctypes.data for c in b])
+        pa = (C.c_void_p * len(p))(*[c.ctypes.data for c in p])
+        self.L.rfo_find_rows.restype = C.c_int
+        self.L.rfo_find_rows.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int64, C.POINTER(C.c_void_p), C.c_int64, C.c_void_p]
+        self.L.rfo_find_rows(len(b), ba, b[0].shape[0], pa, p[0].shape[0], _ptr(ids))
+        return ids
+
+    def inner_join(self, build_cols, probe_cols):
+        ids = self.find_rows(build_cols, probe_cols)
+        pi = np.nonzero(ids != NULL_I64)[0].astype(np.int64)
+        return pi, ids[pi]
+
     def med(self, t, x):
         return self._stat(self.L.rfo_med, t, x)
 
@@ -311,6 +327,41 @@ class Reference:
         if arr.shape[0]:
             C.memmove(o + 16, arr.ctypes.data, arr.nbytes)
         return o
+
+    def make_list(self, items):
+        """a reference LIST (type 0) owning the given objects"""
+        o = self.L.vector(0, len(items))
+        for i, it in enumerate(items):
+            C.c_void_p.from_address(o + 16 + 8 * i).value = it
+        return o
+
+    def find(self, x, y):
+        """ray_find(x, y): for every y the first index in x with that value, else null (I64 vectors)"""
+        xo, yo = self.vec(I64, x), self.vec(I64, y)
+        self.L.ray_find.restype, self.L.ray_find.argtypes = C.c_void_p, [C.c_void_p, C.c_void_p]
+        r = self.L.ray_find(xo, yo)
+        if self.is_err(r):
+            raise RefError("ray_find")
+        out = self.to_numpy(r)[0]
+        self.drop(xo, yo)
+        return out
+
+    def join_index(self, lcols, rcols, inner=False):
+        """index_left_join_obj / index_inner_join_obj on lists of I64 key columns (2+ columns: the hashed multi-column path)"""
+        lo, ro = self.make_list([self.vec(I64, c) for c in lcols]), self.make_list([self.vec(I64, c) for c in rcols])
+        f = self.L.index_inner_join_obj if inner else self.L.index_left_join_obj
+        f.restype, f.argtypes = C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int64]
+        r = f(lo, ro, len(lcols))
+        if self.is_err(r):
+            raise RefError("join index")
+        if inner:
+            its = self.list_items(r)
+            out = (self.to_numpy(its[0], drop=False)[0].copy(), self.to_numpy(its[1], drop=False)[0].copy())
+            self.drop(r)
+        else:
+            out = self.to_numpy(r)[0]
+        self.drop(lo, ro)
+        return out
 
     def vec_uninit(self, t, n):
         """reference-owned vector plus a numpy view over its payload (fill in place; no copy)"""

@@ -729,6 +729,54 @@ int rfo_dev(int type, const void *x, int64_t n, double *out) {
     return RFO_OK;
 }
 
+/* ------------------------------------------------------------------ equi-join row matching (core/index.c) */
+
+/* ray_find -> index_find_i64 (core/index.c:1507-1574) and index_left_join_obj (:2886-2928): both keep, per distinct key
+ * (tuple), the first build row (sequential insert, `if slot empty: slot = i`) and answer every probe row with it or NULL.
+ * Restated as: sort the build rows by (tuple, row), binary-search every probe tuple. */
+typedef struct { int ncols; const int64_t *const *cols; } rfo_tuple_ctx;
+static int tuple_cmp(const rfo_tuple_ctx *a, i64 ra, const rfo_tuple_ctx *b, i64 rb) {
+    for (int c = 0; c < a->ncols; c++) {
+        i64 x = a->cols[c][ra], y = b->cols[c][rb];
+        if (x != y) return x < y ? -1 : 1;
+    }
+    return 0;
+}
+int rfo_find_rows(int ncols, const int64_t *const *build, int64_t build_len, const int64_t *const *probe, int64_t probe_len, int64_t *ids) {
+    rfo_tuple_ctx B = {ncols, build}, P = {ncols, probe};
+    i64 *ord = (i64 *)malloc((size_t)(build_len > 0 ? build_len : 1) * 8), *tmp = (i64 *)malloc((size_t)(build_len > 0 ? build_len : 1) * 8);
+    for (i64 i = 0; i < build_len; i++) ord[i] = i;
+    i64 *src = ord, *dst = tmp;                       /* stable merge sort by tuple: equal tuples stay in row order */
+    for (i64 w = 1; w < build_len; w *= 2) {
+        for (i64 lo = 0; lo < build_len; lo += 2 * w) {
+            i64 mid = lo + w < build_len ? lo + w : build_len, hi = lo + 2 * w < build_len ? lo + 2 * w : build_len;
+            i64 a = lo, b = mid, o = lo;
+            while (a < mid && b < hi) dst[o++] = tuple_cmp(&B, src[b], &B, src[a]) < 0 ? src[b++] : src[a++];
+            while (a < mid) dst[o++] = src[a++];
+            while (b < hi) dst[o++] = src[b++];
+        }
+        i64 *t = src; src = dst; dst = t;
+    }
+    for (i64 i = 0; i < probe_len; i++) {
+        i64 lo = 0, hi = build_len;
+        while (lo < hi) { i64 mid = (lo + hi) / 2; if (tuple_cmp(&B, src[mid], &P, i) < 0) lo = mid + 1; else hi = mid; }
+        ids[i] = (lo < build_len && tuple_cmp(&B, src[lo], &P, i) == 0) ? src[lo] : RFO_NULL_I64;
+    }
+    free(ord); free(tmp);
+    return RFO_OK;
+}
+
+/* index_inner_join_obj (core/index.c:2930-3000): the matched probe rows in ascending order with their first build row */
+int64_t rfo_inner_join(int ncols, const int64_t *const *build, int64_t build_len, const int64_t *const *probe, int64_t probe_len,
+                       int64_t *probe_ids, int64_t *build_ids) {
+    i64 *ids = (i64 *)malloc((size_t)(probe_len > 0 ? probe_len : 1) * 8), j = 0;
+    rfo_find_rows(ncols, build, build_len, probe, probe_len, ids);
+    for (i64 i = 0; i < probe_len; i++)
+        if (ids[i] != RFO_NULL_I64) { probe_ids[j] = i; build_ids[j] = ids[i]; j++; }
+    free(ids);
+    return j;
+}
+
 /* ------------------------------------------------------------------ key sort (core/sort.c) */
 
 /* order-preserving map to u64: integers flip the sign bit (core/sort.c:313), doubles core/sort.c:266-285 */

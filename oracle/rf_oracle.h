@@ -104,6 +104,12 @@ int rfo_group_rows(const int64_t *gid, const int64_t *filter, int64_t len, int64
 int rfo_med(int type, const void *x, int64_t n, double *out);
 int rfo_dev(int type, const void *x, int64_t n, double *out);
 
+/* ---- equi-join row matching: ray_find / index_find_i64 (core/index.c:1507-1574), index_left_join_obj (:2886-2928),
+ * index_inner_join_obj (:2930-3000).  ids[i] = first build row with probe row i's key tuple, else NULL_I64. */
+int rfo_find_rows(int ncols, const int64_t *const *build, int64_t build_len, const int64_t *const *probe, int64_t probe_len, int64_t *ids);
+int64_t rfo_inner_join(int ncols, const int64_t *const *build, int64_t build_len, const int64_t *const *probe, int64_t probe_len,
+                       int64_t *probe_ids, int64_t *build_ids);
+
 /* ---- key sort: core/sort.c:183-428 asc, :481-689 desc ---- stable permutation, nulls/NaN first when ascending */
 int rfo_sort(int type, const void *x, int64_t n, int descending, int64_t *perm);
 

@@ -1,0 +1,150 @@
+// k_join.cu — equi-join row matching (sm_100a): SURVEY §8(f) rank 4.
+//
+//   rfb_find_rows_dev    ray_find -> index_find_i64 (reference core/index.c:1507-1574) for one key column and
+//                        index_left_join_obj (core/index.c:2886-2928) for a tuple of key columns: for every probe row the
+//                        FIRST build row with an equal key (tuple), else NULL_I64
+//   rfb_inner_join_dev   index_inner_join_obj (core/index.c:2930-3000): the matching (probe row, build row) pairs in
+//                        ascending probe-row order
+//
+// The reference inserts the build rows sequentially into an open-addressing table that keeps the first row of every key
+// (core/index.c:2905-2909, 1558-1564) and probes it row by row.  The device builds one table of REPRESENTATIVE build rows
+// (a slot is claimed with a 64-bit CAS on the row id; a probe compares the whole key tuple against the slot's
+// representative), keeps min(row) per slot with an atomic minimum — the first row, without the sequential order — and probes
+// it with one thread per probe row.  Keys compare by bit pattern, a null is a key like any other (__index_list_cmp_row,
+// core/index.c:59-105).
+#include "rfb_common.cuh"
+
+namespace {
+
+constexpr int THREADS = 256;
+constexpr int MAX_KEY_COLS = 8;
+
+__host__ __device__ __forceinline__ u64 mix64(u64 z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+struct KeyCols {
+    const i64 *col[MAX_KEY_COLS];
+    int ncols;
+    __device__ __forceinline__ u64 hash(i64 row) const {
+        u64 h = 0x9E3779B97F4A7C15ULL;
+        for (int c = 0; c < ncols; c++) h = mix64(h ^ (u64)__ldg(col[c] + row)) + 0x9E3779B97F4A7C15ULL;
+        return h;
+    }
+};
+__device__ __forceinline__ bool same_tuple(const KeyCols &a, i64 ra, const KeyCols &b, i64 rb) {
+    for (int c = 0; c < a.ncols; c++)
+        if (__ldg(a.col[c] + ra) != __ldg(b.col[c] + rb)) return false;
+    return true;
+}
+
+__device__ __forceinline__ u64 ld_relaxed(const u64 *p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct JoinTable {
+    i64 *rep;       // [cap] representative build row of the slot, NULL_I64 = empty (row ids are >= 0)
+    u64 *first;     // [cap] smallest build row with the slot's key
+    u64 mask;
+};
+
+__global__ void __launch_bounds__(THREADS, 4) k_join_build(KeyCols build, i64 n, JoinTable t) {
+    for (i64 row = (i64)blockIdx.x * THREADS + threadIdx.x; row < n; row += (i64)gridDim.x * THREADS) {
+        u64 s = build.hash(row) & t.mask;
+        while (true) {
+            i64 cur = (i64)ld_relaxed((const u64 *)&t.rep[s]);
+            if (cur == NULL_I64) {
+                cur = (i64)atomicCAS((unsigned long long *)&t.rep[s], (unsigned long long)NULL_I64, (unsigned long long)row);
+                if (cur == NULL_I64) break;
+            }
+            if (cur == row || same_tuple(build, cur, build, row)) break;
+            s = (s + 1) & t.mask;
+        }
+        if (__ldcg(&t.first[s]) > (u64)row) atomicMin((unsigned long long *)&t.first[s], (unsigned long long)row);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 4) k_join_probe(KeyCols build, KeyCols probe, i64 n, JoinTable t, i64 *__restrict__ ids) {
+    for (i64 row = (i64)blockIdx.x * THREADS + threadIdx.x; row < n; row += (i64)gridDim.x * THREADS) {
+        u64 s = probe.hash(row) & t.mask;
+        i64 found = NULL_I64;
+        while (true) {
+            const i64 cur = __ldg(&t.rep[s]);
+            if (cur == NULL_I64) break;
+            if (same_tuple(build, cur, probe, row)) { found = (i64)__ldg(&t.first[s]); break; }
+            s = (s + 1) & t.mask;
+        }
+        __stcs(ids + row, found);
+    }
+}
+
+__global__ void k_fill_i64(i64 *p, i64 n, i64 v) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void __launch_bounds__(THREADS) k_take_i64(const i64 *__restrict__ src, const i64 *__restrict__ idx, i64 n, i64 *__restrict__ out) {
+    for (i64 i = (i64)blockIdx.x * THREADS + threadIdx.x; i < n; i += (i64)gridDim.x * THREADS) out[i] = __ldg(src + ld_stream(idx + i));
+}
+
+inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" int rfb_find_rows_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const *build_cols, int64_t build_len,
+                                 const int64_t *const *probe_cols, int64_t probe_len, int64_t *ids) {
+    RFB_ARG(ctx && ncols >= 1 && ncols <= MAX_KEY_COLS && build_len >= 0 && probe_len >= 0 && build_cols && probe_cols && (ids || probe_len == 0),
+            "rfb_find_rows_dev");
+    for (int c = 0; c < ncols; c++) RFB_ARG((build_cols[c] || build_len == 0) && (probe_cols[c] || probe_len == 0), "rfb_find_rows_dev: key column");
+    if (probe_len == 0) return RFB_OK;
+    if (build_len == 0) {
+        k_fill_i64<<<rfb_grid_for(ctx, probe_len, 256, 8), 256, 0, ctx->stream>>>(ids, probe_len, NULL_I64);
+        RFB_CHECK_LAUNCH(ctx);
+        return RFB_OK;
+    }
+    KeyCols b, p;
+    b.ncols = p.ncols = ncols;
+    for (int c = 0; c < ncols; c++) { b.col[c] = build_cols[c]; p.col[c] = probe_cols[c]; }
+    i64 cap = 1024;
+    while (cap < 2 * build_len) cap <<= 1;          // load factor <= 0.5
+    void *w;
+    const size_t b1 = align256((size_t)cap * 8);
+    int rc = rfb_ensure_work(ctx, 2 * b1, &w);
+    if (rc) return rc;
+    JoinTable t{(i64 *)w, (u64 *)((char *)w + b1), (u64)(cap - 1)};
+    k_fill_i64<<<rfb_grid_for(ctx, cap, 256, 8), 256, 0, ctx->stream>>>(t.rep, cap, NULL_I64);
+    RFB_CHECK_LAUNCH(ctx);
+    RFB_CUDA(cudaMemsetAsync(t.first, 0xFF, (size_t)cap * 8, ctx->stream));
+    k_join_build<<<rfb_grid_for(ctx, build_len, THREADS * 4, 4), THREADS, 0, ctx->stream>>>(b, build_len, t);
+    RFB_CHECK_LAUNCH(ctx);
+    k_join_probe<<<rfb_grid_for(ctx, probe_len, THREADS * 4, 4), THREADS, 0, ctx->stream>>>(b, p, probe_len, t, ids);
+    RFB_CHECK_LAUNCH(ctx);
+    return RFB_OK;
+}
+
+extern "C" int rfb_inner_join_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const *build_cols, int64_t build_len,
+                                  const int64_t *const *probe_cols, int64_t probe_len, int64_t *probe_ids, int64_t *build_ids,
+                                  int64_t *count) {
+    RFB_ARG(ctx && count && probe_len >= 0 && ((probe_ids && build_ids) || probe_len == 0), "rfb_inner_join_dev");
+    *count = 0;
+    if (probe_len == 0) return RFB_OK;
+    void *aux;
+    int rc = rfb_ensure_aux(ctx, (size_t)probe_len * 8, &aux);
+    if (rc) return rc;
+    i64 *ids = (i64 *)aux;
+    rc = rfb_find_rows_dev(ctx, ncols, build_cols, build_len, probe_cols, probe_len, ids);
+    if (rc) return rc;
+    rfb_scalar_t none;
+    memset(&none, 0, sizeof(none));
+    none.type = RFB_I64;
+    none.v.i64 = NULL_I64;
+    rc = rfb_cmp_where_dev(ctx, RFB_NE, RFB_I64, ids, probe_len, &none, probe_ids, count);      // matched probe rows, ascending
+    if (rc) return rc;
+    if (*count > 0) {
+        k_take_i64<<<rfb_grid_for(ctx, *count, THREADS * 4, 8), THREADS, 0, ctx->stream>>>(ids, probe_ids, *count, build_ids);
+        RFB_CHECK_LAUNCH(ctx);
+    }
+    return RFB_OK;
+}

@@ -831,6 +831,71 @@ out:
 obj_p rfb_aggr_row(obj_p v, obj_p i) { return group_lists(0, v, i); }
 obj_p rfb_aggr_collect(obj_p v, obj_p i) { return group_lists(1, v, i); }
 
+/* ------------------------------------------------------------------ equi-join row matching */
+
+static int is_key_vec(obj_p o) { return o && (o->type == RFB_T_I64 || o->type == RFB_T_SYMBOL || o->type == RFB_T_TIMESTAMP); }
+
+/* cols: the key column itself (len == 1) or a LIST of len key columns; all I64-kind vectors of one length */
+static int key_columns(obj_p cols, int64_t len, obj_p *out, int64_t *rows) {
+    if (len < 1 || len > 8 || !cols) return 0;
+    if (len == 1 && is_key_vec(cols)) { out[0] = cols; *rows = cols->len; return 1; }
+    if (cols->type != RFB_T_LIST || cols->len != len) return 0;
+    for (int64_t c = 0; c < len; c++) {
+        obj_p v = RFB_OBJ_LIST(cols)[c];
+        if (!is_key_vec(v) || (c > 0 && v->len != RFB_OBJ_LIST(cols)[0]->len)) return 0;
+        out[c] = v;
+    }
+    *rows = out[0]->len;
+    return 1;
+}
+
+/* index_left_join_obj / index_inner_join_obj (core/index.c:2886-3000): left = probe side, right = build side */
+static obj_p join_index(int inner, obj_p lcols, obj_p rcols, int64_t len) {
+    if (!G.ready) return NULL;
+    obj_p l[8], r[8];
+    int64_t ll = 0, rl = 0;
+    if (!key_columns(lcols, len, l, &ll) || !key_columns(rcols, len, r, &rl)) return NULL;
+    for (int64_t c = 0; c < len; c++)
+        if (l[c]->type != r[c]->type) return NULL;
+    if (too_small(ll) && too_small(rl)) return NULL;
+    if (len == 1 && rl == 0) return NULL;   /* index_find_i64 answers an EMPTY vector (not nulls) when the searched column is empty
+                                               (core/index.c:1512-1513, golden tests/lang.c:5118): the CPU body's quirk, its result */
+    call_scope_t sc = enter();
+    obj_p res = NULL;
+    const void *dl[8], *dr[8];
+    for (int64_t c = 0; c < len; c++) {
+        dl[c] = dev_column(l[c]);
+        dr[c] = dev_column(r[c]);
+        if (!dl[c] || !dr[c]) { res = G.host->err_limit(); goto out; }
+    }
+    void *dids = dev_temp((size_t)(ll > 0 ? ll : 1) * 8), *dbid = inner ? dev_temp((size_t)(ll > 0 ? ll : 1) * 8) : NULL;
+    if (!dids || (inner && !dbid)) { res = G.host->err_limit(); goto out; }
+    if (!inner) {
+        int rc = rfb_find_rows_dev(G.ctx, (int)len, (const int64_t *const *)dr, rl, (const int64_t *const *)dl, ll, (int64_t *)dids);
+        if (rc) { res = status_to_obj(rc); goto out; }
+        res = to_host_vector(RFB_T_I64, ll, dids);
+    } else {
+        int64_t count = 0;
+        int rc = rfb_inner_join_dev(G.ctx, (int)len, (const int64_t *const *)dr, rl, (const int64_t *const *)dl, ll, (int64_t *)dids, (int64_t *)dbid, &count);
+        if (rc) { res = status_to_obj(rc); goto out; }
+        obj_p lids = to_host_vector(RFB_T_I64, count, dids), rids = to_host_vector(RFB_T_I64, count, dbid);
+        res = G.host->vector(RFB_T_LIST, 2);
+        if (!res || res->type == RFB_T_ERR || lids->type == RFB_T_ERR || rids->type == RFB_T_ERR) { res = G.host->err_limit(); goto out; }
+        RFB_OBJ_LIST(res)[0] = lids;
+        RFB_OBJ_LIST(res)[1] = rids;
+    }
+out:
+    leave(sc);
+    return res;
+}
+obj_p rfb_index_left_join_obj(obj_p lcols, obj_p rcols, int64_t len) { return join_index(0, lcols, rcols, len); }
+obj_p rfb_index_inner_join_obj(obj_p lcols, obj_p rcols, int64_t len) { return join_index(1, lcols, rcols, len); }
+/* ray_find(x, y) on two I64-kind vectors of the same type (core/items.c:320-323 -> index_find_i64): the first index of every y in x */
+obj_p rfb_ray_find(obj_p x, obj_p y) {
+    if (!is_key_vec(x) || !is_key_vec(y) || x->type != y->type) return NULL;
+    return join_index(0, y, x, 1);
+}
+
 /* ------------------------------------------------------------------ sort */
 
 static obj_p sort_op(obj_p x, int desc) {

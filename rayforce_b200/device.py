@@ -333,6 +333,27 @@ class _Ops:
         check(self.lib.rfb_stddev_dev(self.h, t, _dptr(x), x.shape[0], C.byref(out)))
         return out.value
 
+    def find_rows(self, build_cols, probe_cols):
+        """ray_find / index_left_join_obj: for every probe row the first build row with an equal key tuple, else NULL_I64"""
+        nb, np_ = build_cols[0].shape[0], probe_cols[0].shape[0]
+        ids = self._empty(np_, capi.I64)
+        b = (C.c_void_p * len(build_cols))(*[_dptr(c) for c in build_cols])
+        p = (C.c_void_p * len(probe_cols))(*[_dptr(c) for c in probe_cols])
+        check(self.lib.rfb_find_rows_dev(self.h, len(build_cols), b, nb, p, np_, _dptr(ids)))
+        self.sync()
+        return ids
+
+    def inner_join(self, build_cols, probe_cols):
+        """index_inner_join_obj -> (probe row ids, build row ids) of the matching pairs"""
+        nb, np_ = build_cols[0].shape[0], probe_cols[0].shape[0]
+        pi, bi = self._empty(np_, capi.I64), self._empty(np_, capi.I64)
+        b = (C.c_void_p * len(build_cols))(*[_dptr(c) for c in build_cols])
+        p = (C.c_void_p * len(probe_cols))(*[_dptr(c) for c in probe_cols])
+        cnt = C.c_int64(0)
+        check(self.lib.rfb_inner_join_dev(self.h, len(build_cols), b, nb, p, np_, _dptr(pi), _dptr(bi), C.byref(cnt)))
+        self.sync()
+        return pi[:cnt.value], bi[:cnt.value]
+
     def group_sum_count(self, key_type, keys, val, max_groups, cmp_op=None, pred_type=None, pred=None, k=None):
         """fused select {s: (sum v) c: (count v) from t by k [where (cmp p k)]} -> (keys, sums, counts) tensors"""
         n = keys.shape[0]

@@ -22,7 +22,8 @@ UNARY = ["ray_where", "ray_sum", "ray_min", "ray_max", "ray_avg", "ray_cnt", "ra
          "ray_sort_asc", "ray_sort_desc", "ray_med", "ray_dev"]
 BINARY = ["ray_eq", "ray_ne", "ray_lt", "ray_gt", "ray_le", "ray_ge", "filter_map", "filter_collect", "ray_add", "ray_sub",
           "ray_mul", "ray_div", "ray_fdiv", "ray_mod", "ray_xbar", "index_group", "group_map", "aggr_sum", "aggr_min", "aggr_max",
-          "aggr_count", "aggr_avg", "aggr_med", "aggr_stddev", "aggr_row", "aggr_collect", "where_lt_sum"]
+          "aggr_count", "aggr_avg", "aggr_med", "aggr_stddev", "aggr_row", "aggr_collect", "ray_find", "where_lt_sum"]
+TERNARY_I64 = ["index_left_join_obj", "index_inner_join_obj"]      # (obj, obj, int64 len)
 
 
 class HostApi(C.Structure):
@@ -74,6 +75,9 @@ class Ops:
         for n in BINARY:
             f = getattr(L, "rfb_" + n)
             f.restype, f.argtypes = C.c_void_p, [C.c_void_p, C.c_void_p]
+        for n in TERNARY_I64:
+            f = getattr(L, "rfb_" + n)
+            f.restype, f.argtypes = C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int64]
         L.rfb_where_fold.restype, L.rfb_where_fold.argtypes = C.c_void_p, [C.POINTER(C.c_void_p), C.c_int64]
         self.NULL = self.host.null_obj
 
@@ -94,6 +98,13 @@ class Ops:
     def obj(self, t, x):
         """numpy array / list -> vector, scalar -> atom"""
         return self.atom(t, x) if np.ndim(x) == 0 else self.vec(t, x)
+
+    def list_of(self, items):
+        """a LIST object owning `items`"""
+        o = self.host.vector(LIST, len(items))
+        for i, it in enumerate(items):
+            C.c_void_p.from_address(o + 16 + 8 * i).value = it
+        return o
 
     def drop(self, *objs):
         for o in objs:

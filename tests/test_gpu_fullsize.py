@@ -121,6 +121,14 @@ def test_group_by_1e9_adds_up_and_first_occurrence_order(ctx, oracle, big):
     assert int(gc2.sum().item()) == tot.rows
     assert wrap(int(gs2.cpu().numpy().astype(object).sum())) == tot.sum
     assert np.array_equal(gk2.cpu().numpy()[:1000], gk.cpu().numpy()[:1000])
+    # two independent accumulate strategies (key-range partitions in shared memory vs device-wide L2 atomics) must agree bit for bit
+    import os
+    os.environ["RFB_GROUP_STRATEGY"] = "l2"
+    try:
+        gk3, gs3, gc3 = ctx.group_sum_count(capi.I32, keys, val, 100_000, capi.GE, capi.I64, val, 0)
+    finally:
+        del os.environ["RFB_GROUP_STRATEGY"]
+    assert torch.equal(gk3, gk2) and torch.equal(gs3, gs2) and torch.equal(gc3, gc2)
     del keys
     torch.cuda.empty_cache()
 

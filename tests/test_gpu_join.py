@@ -1,0 +1,81 @@
+"""GPU parity for the equi-join row matching (k_join.cu) against the CPU oracle (pinned against the compiled
+reference's ray_find / index_left_join_obj / index_inner_join_obj in tests/test_oracle_vs_reference.py): bit-exact row ids."""
+import numpy as np
+import pytest
+
+from oracle import bindings as ob
+from rayforce_b200.ops import Ops, Declined
+from tests.util import dev, host
+
+pytestmark = pytest.mark.gpu
+
+
+def tables(ncols, nb, np_, seed, wide=False):
+    r = np.random.default_rng(seed)
+    scale = (1 << 50) if wide else 1
+    bcols = [(r.integers(-6, 12 + 3 * c, nb) * scale).astype(np.int64) for c in range(ncols)]
+    pcols = [(r.integers(-8, 14 + 3 * c, np_) * scale).astype(np.int64) for c in range(ncols)]
+    if nb > 5:
+        bcols[-1][::7] = ob.NULL_I64
+    if np_ > 5:
+        pcols[-1][::5] = ob.NULL_I64
+    return bcols, pcols
+
+
+@pytest.mark.parametrize("ncols", [1, 2, 5])
+@pytest.mark.parametrize("nb,np_", [(1, 1), (3, 1000), (1000, 3), (70_001, 200_003), (500_000, 100_000)])
+@pytest.mark.parametrize("wide", [False, True])
+def test_find_rows_and_inner_join(ctx, oracle, ncols, nb, np_, wide):
+    bcols, pcols = tables(ncols, nb, np_, ncols * 1000 + nb, wide)
+    want = oracle.find_rows(bcols, pcols)
+    db, dp = [dev(c) for c in bcols], [dev(c) for c in pcols]
+    assert np.array_equal(host(ctx.find_rows(db, dp)), want)
+    pi, bi = ctx.inner_join(db, dp)
+    wpi, wbi = oracle.inner_join(bcols, pcols)
+    assert np.array_equal(host(pi), wpi) and np.array_equal(host(bi), wbi)
+
+
+def test_find_rows_high_cardinality_unique_keys(ctx, oracle):
+    """the published join shape: (nearly) unique keys on both sides (reference docs benchmarks/inner-join.md: ij [id1 id2])"""
+    n = 1_000_003
+    r = np.random.default_rng(9)
+    b1, b2 = r.permutation(n).astype(np.int64), r.integers(0, 1000, n).astype(np.int64)
+    sel = r.integers(0, n, n)
+    p1, p2 = b1[sel].copy(), b2[sel].copy()
+    p2[::3] += 1                                     # a third of the probe rows have no partner
+    want = oracle.find_rows([b1, b2], [p1, p2])
+    got = host(ctx.find_rows([dev(b1), dev(b2)], [dev(p1), dev(p2)]))
+    assert np.array_equal(got, want) and (got == ob.NULL_I64).sum() > n // 4
+
+
+def test_find_rows_empty_sides(ctx):
+    e, x = dev(np.empty(0, np.int64)), dev(np.arange(5, dtype=np.int64))
+    assert host(ctx.find_rows([e], [x])).tolist() == [ob.NULL_I64] * 5
+    assert ctx.find_rows([x], [e]).shape[0] == 0
+    pi, bi = ctx.inner_join([e], [x])
+    assert pi.shape[0] == 0 and bi.shape[0] == 0
+
+
+def test_join_through_the_operator_layer(oracle):
+    """index_left_join_obj / index_inner_join_obj / ray_find with the reference's object layout (lists of key columns)"""
+    ops = Ops.get(0)
+    bcols, pcols = tables(2, 90_001, 150_003, 5)
+    want = oracle.find_rows(bcols, pcols)
+    lo = ops.list_of([ops.vec(ob.I64, c) for c in pcols])
+    ro = ops.list_of([ops.vec(ob.I64, c) for c in bcols])
+    with ops.scope():
+        got, gt = ops.value(ops.call("index_left_join_obj", lo, ro, 2))
+        assert gt == ob.I64 and np.array_equal(got, want)
+        pair = ops.call("index_inner_join_obj", lo, ro, 2)
+        its = ops.items(pair)
+        wpi, wbi = oracle.inner_join(bcols, pcols)
+        assert np.array_equal(ops.value(its[0], drop=False)[0], wpi) and np.array_equal(ops.value(its[1], drop=False)[0], wbi)
+        ops.drop(pair)
+        x, y = ops.vec(ob.I64, bcols[0]), ops.vec(ob.I64, pcols[0])
+        got, gt = ops.value(ops.call("ray_find", x, y))
+        assert np.array_equal(got, oracle.find_rows([bcols[0]], [pcols[0]]))
+        f = ops.vec(ob.F64, np.arange(70_000, dtype=np.float64))
+        with pytest.raises(Declined):                     # other key types stay on the reference's ray_find
+            ops.value(ops.call("ray_find", f, f))
+        ops.drop(x, y, f)
+    ops.drop(lo, ro)

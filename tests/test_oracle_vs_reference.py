@@ -358,3 +358,32 @@ def test_group_rows_collect(oracle, reference, filtered):
     for g in range(info.groups):
         assert np.array_equal(got_rows[g], rows[offs[g]:offs[g + 1]])
         assert np.array_equal(got_vals[g], val[rows[offs[g]:offs[g + 1]]])
+
+
+# ---------------------------------------------------------------- equi-join row matching
+
+@pytest.mark.parametrize("nb,np_,card", [(1, 1, 1), (100, 300, 40), (50_000, 80_000, 20_000), (50_000, 80_000, 10**12)])
+def test_find_single_key(oracle, reference, nb, np_, card):
+    """ray_find -> index_find_i64 (core/index.c:1507-1574): dense (range <= MAX_RANGE) and hashed key domains.  Keys are kept
+    non-negative and non-null: the reference's hash path indexes its table with (i64)key % size (core/hash.c:104)."""
+    r = np.random.default_rng(nb + np_)
+    pool = r.integers(0, card, max(2, nb // 2)).astype(np.int64)
+    build = pool[r.integers(0, pool.shape[0], nb)]
+    probe = np.concatenate([pool[r.integers(0, pool.shape[0], np_ // 2)], r.integers(0, card, np_ - np_ // 2)]).astype(np.int64)
+    assert np.array_equal(oracle.find_rows([build], [probe]), reference.find(build, probe))
+
+
+@pytest.mark.parametrize("ncols", [2, 3])
+@pytest.mark.parametrize("nb,np_", [(10, 30), (40_000, 70_000)])
+def test_join_index_multi_key(oracle, reference, ncols, nb, np_):
+    """index_left_join_obj / index_inner_join_obj (core/index.c:2886-3000), the hashed multi-column path"""
+    r = np.random.default_rng(nb * ncols)
+    bcols = [r.integers(0, 12 + c, nb).astype(np.int64) * (10**9 if c == 0 else 1) for c in range(ncols)]
+    pcols = [r.integers(0, 14 + c, np_).astype(np.int64) * (10**9 if c == 0 else 1) for c in range(ncols)]
+    bcols[-1][::7] = ob.NULL_I64
+    pcols[-1][::5] = ob.NULL_I64                     # nulls are keys like any other (bitwise row compare)
+    want = oracle.find_rows(bcols, pcols)
+    assert np.array_equal(want, reference.join_index(pcols, bcols))
+    pi, bi = oracle.inner_join(bcols, pcols)
+    rl, rr = reference.join_index(pcols, bcols, inner=True)
+    assert np.array_equal(pi, rl[:pi.shape[0]]) and np.array_equal(bi, rr[:bi.shape[0]])
