@@ -77,9 +77,25 @@ def merge_group_partials(keys: torch.Tensor, sums: torch.Tensor, counts: torch.T
     counts).  They are all-gathered in rank order and re-grouped by `regroup(keys_cat, sums_cat, counts_cat)` — on the
     GPUs that is `gpu_regroup(ctx)` below (the group-index + aggregate kernels); first-occurrence numbering over the
     rank-ordered concatenation IS the global first-occurrence order because rank r holds rows before rank r+1."""
-    k = allgather_varlen(keys, group)
-    s = allgather_varlen(sums, group)
-    c = allgather_varlen(counts, group)
+    # one size exchange and ONE data collective: the three columns travel as a [3, cap] block per rank
+    world = dist.get_world_size(group)
+    n = torch.tensor([keys.shape[0]], dtype=torch.int64, device=keys.device)
+    sizes = torch.empty(world, dtype=torch.int64, device=keys.device)
+    dist.all_gather_into_tensor(sizes, n, group=group) if keys.is_cuda else dist.all_gather(list(sizes.split(1)), n, group=group)
+    sizes = [int(v) for v in sizes.cpu()]
+    cap = max(max(sizes), 1)
+    block = torch.zeros((3, cap), dtype=torch.int64, device=keys.device)
+    block[0, : keys.shape[0]] = keys
+    block[1, : sums.shape[0]] = sums
+    block[2, : counts.shape[0]] = counts
+    parts = torch.empty((world, 3, cap), dtype=torch.int64, device=keys.device)
+    if keys.is_cuda:
+        dist.all_gather_into_tensor(parts, block, group=group)
+    else:
+        dist.all_gather(list(parts.unbind(0)), block, group=group)
+    k = torch.cat([parts[r, 0, :sz] for r, sz in enumerate(sizes)])
+    s = torch.cat([parts[r, 1, :sz] for r, sz in enumerate(sizes)])
+    c = torch.cat([parts[r, 2, :sz] for r, sz in enumerate(sizes)])
     return regroup(k, s, c)
 
 
