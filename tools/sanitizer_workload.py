@@ -46,6 +46,39 @@ for keys in (k, kw):
 ctx.group_keys([k, k])
 ctx.group_sum_count(capi.I32, k32, x, 5000)
 ctx.group_sum_count(capi.I64, k, x, 500, capi.LT, capi.I64, x, 100)
+# fused group-by: every accumulate strategy (shared memory / scope-free residue / key-range partitions with the on-demand block
+# store / L2 atomics), with and without a predicate, aligned and unaligned columns
+kbig = dev(r.integers(-3000, 40_000, n + 1).astype(np.int64))
+for strat in ("smem", "part", "l2", None):
+    if strat:
+        os.environ["RFB_GROUP_STRATEGY"] = strat
+    else:
+        os.environ.pop("RFB_GROUP_STRATEGY", None)
+        os.environ["RFB_PART_MIN_ROWS"] = "1000"
+    if strat != "smem":
+        ctx.group_sum_count(capi.I64, kbig[:n], x, 50_000)
+        ctx.group_sum_count(capi.I64, kbig[1:], x, 50_000, capi.LT, capi.I64, x, 100)
+    ctx.group_sum_count(capi.I32, k32, x, 5000)
+    ctx.group_sum_count(capi.I64, k, x, 500, capi.GE, capi.I64, x, -100)
+os.environ.pop("RFB_PART_MIN_ROWS", None)
+# multi-key row hashing, med / dev / row lists, fp64 moments, joins
+wide = [dev(r.integers(0, 7, n).astype(np.int64) << 50), dev(r.integers(0, 9, n).astype(np.int64) << 45)]
+ctx.group_keys(wide)
+g, fi, info = ctx.group_i64(k)
+ctx.aggr(capi.A_MED, capi.I64, x, g, info.groups)
+ctx.aggr(capi.A_MED, capi.F64, f, g, info.groups)
+ctx.aggr(capi.A_DEV, capi.I64, x, g, info.groups)
+ctx.aggr(capi.A_AVG, capi.F64, f, g, info.groups)
+g100 = dev(r.integers(0, 100, n).astype(np.int64))
+ctx.aggr(capi.A_DEV, capi.F64, f, g100, 100)
+ctx.aggr(capi.A_SUM, capi.F64, f, g100, 100)
+ctx.aggr(capi.A_AVG, capi.I64, x, g100, 100)
+ctx.group_rows(g, info.groups)
+ctx.med(capi.I64, x)
+ctx.stddev(capi.I64, x)
+ctx.stddev(capi.F64, f)
+ctx.find_rows([k, y], [k, x])
+ctx.inner_join([kw], [kw])
 ctx.sort(capi.I64, x)
 ctx.sort(capi.F64, f, True)
 h = r.integers(-1000, 1000, 2_000_000).astype(np.int64)
