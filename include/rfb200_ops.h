@@ -54,6 +54,7 @@ typedef rfb_obj_t *rfb_obj_p;
 /* type codes used by this layer (core/rayforce.h:50-95) */
 enum { RFB_T_LIST = 0, RFB_T_B8 = 1, RFB_T_U8 = 2, RFB_T_I16 = 3, RFB_T_I32 = 4, RFB_T_I64 = 5, RFB_T_SYMBOL = 6,
        RFB_T_DATE = 7, RFB_T_TIME = 8, RFB_T_TIMESTAMP = 9, RFB_T_F64 = 10, RFB_T_MAPFILTER = 71, RFB_T_MAPGROUP = 72,
+       RFB_T_PARTED = 77 /* + element type: a list of per-partition vectors (core/rayforce.h:70-82) */,
        RFB_T_NULL = 126, RFB_T_ERR = 127 };
 
 /* What the host (the reference runtime, or the builtin one) provides.  Names follow the reference functions they are
@@ -135,6 +136,9 @@ rfb_obj_p rfb_aggr_min(rfb_obj_p val, rfb_obj_p index);
 rfb_obj_p rfb_aggr_max(rfb_obj_p val, rfb_obj_p index);
 rfb_obj_p rfb_aggr_count(rfb_obj_p val, rfb_obj_p index);
 rfb_obj_p rfb_aggr_avg(rfb_obj_p val, rfb_obj_p index);
+/* (aggr_sum/min/max/avg also take a PARTED column — the per-partition vectors of a parted table, normally mmapped column
+ *  files — with an INDEX_TYPE_PARTEDCOMMON index (PARTED_MAP, core/aggr.c:183-260): every partition is folded on the device
+ *  and the per-partition results are combined, or returned one per partition, exactly as the reference does.) */
 /* aggr_med / aggr_dev (core/aggr.c:2136-2906) -> F64 vector; aggr_row / aggr_collect (core/aggr.c:3021-3136) -> LIST of
  * per-group row-id / value vectors */
 rfb_obj_p rfb_aggr_med(rfb_obj_p val, rfb_obj_p index);

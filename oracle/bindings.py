@@ -206,6 +206,22 @@ class Oracle:
         dt = NP_OF[ot.value]
         return out.view(np.uint8)[: groups * np.dtype(dt).itemsize].view(dt).copy(), ot.value
 
+    def parted_aggr(self, op, vt, parts, combine):
+        """PARTED_MAP without a filter -> (array of 1 or len(parts) values, result type)"""
+        parts = [np.ascontiguousarray(p, NP_OF[vt]) for p in parts]
+        pa = (C.c_void_p * len(parts))(*[p.ctypes.data for p in parts])
+        lens = np.array([p.shape[0] for p in parts], np.int64)
+        out = np.zeros(max(len(parts), 1), np.int64)
+        ot = C.c_int(0)
+        self.L.rfo_parted_aggr.restype = C.c_int
+        self.L.rfo_parted_aggr.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        r = self.L.rfo_parted_aggr(op, vt, len(parts), pa, _ptr(lens), int(combine), _ptr(out), C.byref(ot))
+        if r < 0:
+            raise OracleError(r)
+        dt = np.dtype(NP_OF[ot.value])
+        cnt = 1 if combine else len(parts)
+        return out.view(np.uint8)[: cnt * dt.itemsize].view(dt).copy(), ot.value
+
     def group_rows(self, gids, groups, filt=None):
         """aggr_row / aggr_collect layout: (rows grouped by gid in push order, offsets[groups+1])"""
         gids = np.ascontiguousarray(gids, np.int64)

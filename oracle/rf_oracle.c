@@ -659,6 +659,70 @@ int rfo_aggr(int op, int val_type, const void *val, const int64_t *filter, const
 #undef ROW
 }
 
+/* Parted aggregates: PARTED_MAP (core/aggr.c:183-260) and aggr_avg's parted branch (:2065-2127) with no filter.  Every
+ * partition is aggregated as ONE group by the grouped partial (rfo_aggr with all group ids 0: sticky-null sum, +INF-initialised
+ * min, null-initialised max); combine != 0 (groups == 1) folds the partition values with ADD (sticky) / MIN / MAX (null-skipping)
+ * or sums the avg totals, else out holds one value per partition.  out: I64 / I32 / I16 / F64 entries of *out_type. */
+int rfo_parted_aggr(int op, int val_type, int nparts, const void *const *parts, const int64_t *lens, int combine, void *out, int *out_type) {
+    int k = kind_of(val_type);
+    if (!(k == K_I16 || k == K_I32 || k == K_I64 || k == K_F64)) return RFO_ERR_TYPE;
+    if (!(op == RFO_SUM || op == RFO_MIN || op == RFO_MAX || op == RFO_AVG)) return RFO_ERR_TYPE;
+    if (op == RFO_AVG && val_type == RFO_TIMESTAMP) return RFO_ERR_TYPE;
+    int w = op == RFO_AVG ? 8 : rfo_type_size(val_type);
+    *out_type = op == RFO_AVG || k == K_F64 ? RFO_F64 : (k == K_I64 ? RFO_I64 : (k == K_I32 ? RFO_I32 : RFO_I16));
+    f64 tsum = 0.0; i64 tcnt = 0;
+    for (int p = 0; p < nparts; p++) {
+        i64 n = lens[p];
+        i64 *zeros = (i64 *)calloc((size_t)(n > 0 ? n : 1), 8);
+        char v[8] = {0};
+        int t;
+        if (op == RFO_AVG) {       /* (f64 sum of non-nulls, count): aggr_avg_partial */
+            f64 s = 0.0; i64 c = 0;
+            for (i64 i = 0; i < n; i++) {
+                if (k == K_I64) { i64 x = ((const i64 *)parts[p])[i]; if (x != RFO_NULL_I64) { s += (f64)x; c++; } }
+                else if (k == K_I32) { i32 x = ((const i32 *)parts[p])[i]; if (x != RFO_NULL_I32) { s += (f64)x; c++; } }
+                else if (k == K_I16) { i16 x = ((const i16 *)parts[p])[i]; if (x != RFO_NULL_I16) { s += (f64)x; c++; } }
+                else { f64 x = ((const f64 *)parts[p])[i]; if (!isnan64(x)) { s += x; c++; } }
+            }
+            if (combine) { tsum += s; tcnt += c; }
+            else { f64 a = c == 0 ? null_f64() : s / (f64)c; memcpy((char *)out + (size_t)p * 8, &a, 8); }
+            free(zeros);
+            continue;
+        }
+        /* the partial's value types: DATE/TIME partitions aggregate as their I32 payload, TIMESTAMP as I64 */
+        if ((op == RFO_SUM && val_type == RFO_TIMESTAMP) || ((op == RFO_MIN || op == RFO_MAX) && val_type == RFO_I32)) { free(zeros); return RFO_ERR_TYPE; }
+        int pt = val_type;
+        if (op == RFO_SUM && k == K_I32) {   /* rfo_aggr has no I32 sum driver (the non-parted aggr_sum has none): i32 sticky wrap-around sum */
+            i32 s = 0; int nul = 0;
+            for (i64 i = 0; i < n; i++) { i32 x = ((const i32 *)parts[p])[i]; if (x == RFO_NULL_I32) nul = 1; else s = (i32)((uint32_t)s + (uint32_t)x); }
+            if (nul) s = RFO_NULL_I32;
+            memcpy(v, &s, 4);
+        } else if (rfo_aggr(op, pt, parts[p], NULL, zeros, n, 1, v, &t) < 0) { free(zeros); return RFO_ERR_TYPE; }
+        free(zeros);
+        if (!combine) { memcpy((char *)out + (size_t)p * w, v, (size_t)w); continue; }
+        if (p == 0) { memcpy(out, v, (size_t)w); continue; }
+        if (k == K_F64) {
+            f64 a, b; memcpy(&a, out, 8); memcpy(&b, v, 8);
+            a = op == RFO_SUM ? ((isnan64(a) || isnan64(b)) ? null_f64() : a + b) : (op == RFO_MIN ? min_f64(a, b) : max_f64(a, b));
+            memcpy(out, &a, 8);
+        } else if (k == K_I64) {
+            i64 a, b; memcpy(&a, out, 8); memcpy(&b, v, 8);
+            a = op == RFO_SUM ? ((a == RFO_NULL_I64 || b == RFO_NULL_I64) ? RFO_NULL_I64 : wadd64(a, b)) : (op == RFO_MIN ? min_i64(a, b) : max_i64(a, b));
+            memcpy(out, &a, 8);
+        } else if (k == K_I32) {
+            i32 a, b; memcpy(&a, out, 4); memcpy(&b, v, 4);
+            a = op == RFO_SUM ? ((a == RFO_NULL_I32 || b == RFO_NULL_I32) ? RFO_NULL_I32 : (i32)((uint32_t)a + (uint32_t)b)) : (op == RFO_MIN ? min_i32(a, b) : max_i32(a, b));
+            memcpy(out, &a, 4);
+        } else {
+            i16 a, b; memcpy(&a, out, 2); memcpy(&b, v, 2);
+            a = op == RFO_SUM ? ((a == RFO_NULL_I16 || b == RFO_NULL_I16) ? RFO_NULL_I16 : (i16)((uint16_t)a + (uint16_t)b)) : (op == RFO_MIN ? min_i16(a, b) : max_i16(a, b));
+            memcpy(out, &a, 2);
+        }
+    }
+    if (op == RFO_AVG && combine) { f64 a = tcnt == 0 ? null_f64() : tsum / (f64)tcnt; memcpy(out, &a, 8); }
+    return RFO_OK;
+}
+
 /* aggr_row / aggr_collect (core/aggr.c:3021-3136): AGGR_ITER pushes row x (= filter[i] or i) onto list gid[i], i ascending */
 int rfo_group_rows(const int64_t *gid, const int64_t *filter, int64_t len, int64_t groups, int64_t *rows, int64_t *offsets) {
     for (i64 g = 0; g <= groups; g++) offsets[g] = 0;

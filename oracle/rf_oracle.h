@@ -97,6 +97,10 @@ int rfo_aggr(int op, int val_type, const void *val, const int64_t *filter, const
 
 /* rfo_aggr also takes RFO_MED (aggr_med core/aggr.c:2136-2246) and RFO_DEV (aggr_dev :2250-2906): F64 per group */
 
+/* parted aggregates without a filter: PARTED_MAP (core/aggr.c:183-260), aggr_avg (:2065-2127).  combine: one result over all
+ * partitions (groups == 1) vs one per partition. */
+int rfo_parted_aggr(int op, int val_type, int nparts, const void *const *parts, const int64_t *lens, int combine, void *out, int *out_type);
+
 /* aggr_row / aggr_collect (core/aggr.c:3021-3136): rows[len] = row ids grouped by gid in push order, offsets[groups+1] */
 int rfo_group_rows(const int64_t *gid, const int64_t *filter, int64_t len, int64_t groups, int64_t *rows, int64_t *offsets);
 

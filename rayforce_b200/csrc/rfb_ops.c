@@ -747,7 +747,145 @@ out:
     return res;
 }
 
+/* ---- parted columns: PARTED_MAP (core/aggr.c:183-260) and aggr_avg's parted branch (:2065-2127).
+ * val = list of per-partition vectors; index = [PARTEDCOMMON, groups, -, -, -, filter, -].  Partition values follow the GROUPED
+ * aggregate semantics (aggr_*_partial with one group): sum is sticky-null in the value's own width, min starts at +INF,
+ * max at null, avg = (f64 sum of non-nulls, their count).  groups == 1: combined with ADD (sticky) / MIN / MAX (null-skipping)
+ * / summed totals; otherwise one result per included partition. */
+#define RFB_INDEX_PARTEDCOMMON 2
+typedef struct { int64_t i; double f; int64_t cnt; } part_val_t;
+
+static int parted_fold(int op, int t, obj_p part, obj_p ids, part_val_t *out) {
+    rfb_fold_t f;
+    const int folds = (op == RFB_A_MIN || op == RFB_A_MAX) ? (RFB_F_MIN | RFB_F_MAX) : (RFB_F_SUM | RFB_F_CNT);
+    const int64_t rows = ids ? ids->len : part->len;
+    memset(&f, 0, sizeof(f));
+    if (rows > 0) {
+        void *dc = dev_column(part), *di = ids ? dev_column(ids) : NULL;
+        if (!dc || (ids && !di)) return RFB_ERR_NOMEM;
+        int rc = ids ? rfb_gather_fold_dev(G.ctx, folds, t, dc, (const int64_t *)di, rows, &f) : rfb_fold_dev(G.ctx, folds, t, dc, rows, &f);
+        if (rc) return rc;
+    }
+    const int flt = (t == RFB_T_F64), w = type_size(t);
+    const int64_t null_i = w == 8 ? RFB_NULL_I64 : (w == 4 ? (int64_t)INT32_MIN : (int64_t)INT16_MIN);
+    const int64_t inf_i = w == 8 ? INT64_MAX : (w == 4 ? (int64_t)INT32_MAX : (int64_t)INT16_MAX);
+    out->cnt = f.nonnull;
+    switch (op) {
+        case RFB_A_SUM:   /* sticky: one null makes the partition's sum null */
+            if (flt) out->f = f.nonnull < rows ? NAN : (rows ? f.sum_f64 : 0.0);
+            else if (f.nonnull < rows) out->i = null_i;
+            else out->i = w == 8 ? f.sum_i64 : (w == 4 ? (int64_t)(int32_t)f.sum_i64 : (int64_t)(int16_t)f.sum_i64);
+            break;
+        case RFB_A_MIN:
+            if (flt) out->f = f.nonnull ? f.min_f64 : INFINITY; else out->i = f.nonnull ? f.min_i64 : inf_i;
+            break;
+        case RFB_A_MAX:
+            if (flt) out->f = f.nonnull ? f.max_f64 : NAN; else out->i = f.nonnull ? f.max_i64 : null_i;
+            break;
+        default:          /* avg: f64 sum of the non-null values */
+            out->f = flt ? (f.nonnull ? f.sum_f64 : 0.0) : (double)f.sum_i64;
+            break;
+    }
+    return RFB_OK;
+}
+
+static obj_p parted_aggr(int op, obj_p val, obj_p index) {
+    const int t = val->type - RFB_T_PARTED;
+    if (!(t == RFB_T_I16 || t == RFB_T_I32 || t == RFB_T_I64 || t == RFB_T_F64 || t == RFB_T_DATE || t == RFB_T_TIME || t == RFB_T_TIMESTAMP)) return NULL;
+    if (!(op == RFB_A_SUM || op == RFB_A_MIN || op == RFB_A_MAX || op == RFB_A_AVG)) return NULL;   /* count reads no data; med/dev: CPU body */
+    /* the per-partition partials have no case for these (aggr_sum_partial core/aggr.c:1082-1104, aggr_min/max_partial :1156-1260,
+     * aggr_avg :2021-2027): whatever the reference does with the partial's error stays the CPU body's business */
+    if ((op == RFB_A_AVG || op == RFB_A_SUM) && t == RFB_T_TIMESTAMP) return NULL;
+    if ((op == RFB_A_MIN || op == RFB_A_MAX) && t == RFB_T_I32) return NULL;
+    obj_p *ix = RFB_OBJ_LIST(index);
+    const int64_t n = ix[1]->i64, l = val->len;
+    obj_p filter = is_null_obj(ix[5]) ? NULL : ix[5];
+    const int idfilter = filter && filter->type == RFB_T_PARTED + RFB_T_I64;
+    if (filter && filter->len != l) return NULL;
+    if (op == RFB_A_AVG && filter) return NULL;                  /* aggr_avg hands the filter to its partials: CPU body */
+    if (!filter && n != 1 && n != l) return NULL;
+    int64_t total_rows = 0;
+    for (int64_t i = 0; i < l; i++) {
+        obj_p p = RFB_OBJ_LIST(val)[i];
+        if (!p || p->type != t) return NULL;
+        total_rows += p->len;
+    }
+    if (too_small(total_rows)) return NULL;
+    const int flt = (t == RFB_T_F64), w = type_size(t);
+    const int ot = op == RFB_A_AVG ? RFB_T_F64 : (flt ? RFB_T_F64 : (w == 8 ? RFB_T_I64 : (w == 4 ? RFB_T_I32 : RFB_T_I16)));   /* __v_i64 / __v_i32 / ... */
+    const int64_t null_i = w == 8 ? RFB_NULL_I64 : (w == 4 ? (int64_t)INT32_MIN : (int64_t)INT16_MIN);
+    call_scope_t sc = enter();
+    obj_p res = NULL;
+    part_val_t *pv = (part_val_t *)malloc((size_t)(l > 0 ? l : 1) * sizeof(part_val_t));
+    int64_t m = 0;                                               /* included partitions */
+    if (!pv) { res = G.host->err_limit(); goto out; }
+    for (int64_t i = 0; i < l; i++) {
+        obj_p ids = NULL;
+        if (filter) {
+            obj_p fe = RFB_OBJ_LIST(filter)[i];
+            if (is_null_obj(fe)) continue;
+            if (idfilter) {
+                if (fe->type > 0 && fe->len == 0) continue;
+                if (!(fe->type == -RFB_T_I64 && fe->i64 == -1)) { if (fe->type != RFB_T_I64) { res = NULL; goto out; } ids = fe; }
+            }
+        }
+        int rc = parted_fold(op, t, RFB_OBJ_LIST(val)[i], ids, &pv[m]);
+        if (rc) { res = status_to_obj(rc); goto out; }
+        m++;
+    }
+    const int combine = (n == 1) && (!filter || idfilter);
+    if (!combine && filter && !idfilter && n == 1 && m > 1) { res = NULL; goto out; }      /* the reference would overrun a 1-element result here */
+    const int64_t outn = combine ? 1 : m;
+    res = G.host->vector((int8_t)ot, combine ? 1 : n);
+    if (!res || res->type == RFB_T_ERR) { res = G.host->err_limit(); goto out; }
+    if (!combine && outn > n) { G.host->drop_obj(res); res = NULL; goto out; }
+    char *o = (char *)RFB_OBJ_PAYLOAD(res);
+    if (combine) {
+        part_val_t acc;
+        memset(&acc, 0, sizeof(acc));
+        int64_t cnt = 0;
+        double fsum = 0.0;
+        for (int64_t j = 0; j < m; j++) {
+            const part_val_t *v = &pv[j];
+            if (op == RFB_A_AVG) { fsum += v->f; cnt += v->cnt; continue; }
+            if (j == 0) { acc = *v; continue; }
+            if (flt) {
+                const int an = isnan(acc.f), bn = isnan(v->f);
+                if (op == RFB_A_SUM) acc.f = (an || bn) ? NAN : acc.f + v->f;
+                else if (op == RFB_A_MIN) acc.f = an ? v->f : (bn ? acc.f : (acc.f < v->f ? acc.f : v->f));
+                else acc.f = an ? v->f : (bn ? acc.f : (acc.f > v->f ? acc.f : v->f));
+            } else {
+                const int an = acc.i == null_i, bn = v->i == null_i;
+                if (op == RFB_A_SUM) {
+                    if (an || bn) acc.i = null_i;
+                    else { const uint64_t s = (uint64_t)acc.i + (uint64_t)v->i; acc.i = w == 8 ? (int64_t)s : (w == 4 ? (int64_t)(int32_t)s : (int64_t)(int16_t)s); }
+                } else if (op == RFB_A_MIN) acc.i = an ? v->i : (bn ? acc.i : (acc.i < v->i ? acc.i : v->i));
+                else acc.i = an ? v->i : (bn ? acc.i : (acc.i > v->i ? acc.i : v->i));
+            }
+        }
+        if (op == RFB_A_AVG) { const double a = cnt == 0 ? NAN : fsum / (double)cnt; memcpy(o, &a, 8); }
+        else if (m == 0) memset(o, 0, (size_t)type_size(ot));   /* (no partition included: the reference leaves the slot as allocated) */
+        else if (flt) memcpy(o, &acc.f, 8);
+        else memcpy(o, &acc.i, (size_t)w);
+    } else {
+        for (int64_t j = 0; j < m; j++) {
+            if (op == RFB_A_AVG) { const double a = pv[j].cnt == 0 ? NAN : pv[j].f / (double)pv[j].cnt; memcpy(o + j * 8, &a, 8); }
+            else if (flt) memcpy(o + j * 8, &pv[j].f, 8);
+            else memcpy(o + j * w, &pv[j].i, (size_t)w);
+        }
+    }
+out:
+    free(pv);
+    leave(sc);
+    return res;
+}
+
 static obj_p aggr_op(int op, obj_p val, obj_p index) {
+    if (G.ready && val && index && index->type == RFB_T_LIST && index->len == 7 && val->type > RFB_T_PARTED && val->type <= RFB_T_PARTED + RFB_T_F64) {
+        obj_p *px = RFB_OBJ_LIST(index);
+        if (px[0] && px[0]->type == -RFB_T_I64 && px[0]->i64 == RFB_INDEX_PARTEDCOMMON && px[1] && px[1]->type == -RFB_T_I64) return parted_aggr(op, val, index);
+        return NULL;
+    }
     if (!G.ready || !is_vec(val) || !index || index->type != RFB_T_LIST || index->len != 7) return NULL;
     obj_p *ix = RFB_OBJ_LIST(index);
     if (!ix[0] || ix[0]->type != -RFB_T_I64 || ix[0]->i64 != RFB_INDEX_IDS) return NULL; /* SHIFT / parted / window indices: CPU body */

@@ -106,6 +106,18 @@ class Ops:
             C.c_void_p.from_address(o + 16 + 8 * i).value = it
         return o
 
+    def parted(self, t, parts):
+        """a PARTED column (type 77 + t, core/rayforce.h:70-82): the per-partition vectors of a parted table"""
+        o = self.list_of([self.vec(t, p) for p in parts])
+        C.c_int8.from_address(o + 2).value = 77 + t
+        return o
+
+    def parted_index(self, groups, filt=None):
+        """[INDEX_TYPE_PARTEDCOMMON, groups, -, -, -, filter, -] (core/math.c:1898-1899, core/index.c:1696-1699)"""
+        items = [self.atom(capi.I64, 2), self.atom(capi.I64, groups), self.NULL, self.atom(capi.I64, capi.NULL_I64), self.NULL,
+                 filt if filt is not None else self.NULL, self.NULL]
+        return self.list_of(items)
+
     def drop(self, *objs):
         for o in objs:
             if o:

@@ -293,3 +293,49 @@ def test_med_dev_vectors_and_filtered(ops, oracle):
         ops.value(ops.call("ray_med", f))
     assert e.value.kind == "type"
     ops.drop(xo, io, f)
+
+
+@pytest.mark.parametrize("t", [ob.I64, ob.F64, ob.I32, ob.I16, ob.DATE, ob.TIMESTAMP])
+@pytest.mark.parametrize("combine", [True, False])
+def test_parted_aggregates(ops, oracle, t, combine):
+    """aggr_sum/min/max/avg over a PARTED column (PARTED_MAP, core/aggr.c:183-260): every partition folded on
+    the device, combined or returned per partition; nulls follow the GROUPED semantics (sticky sum)"""
+    r = np.random.default_rng(t)
+    lens = [70_001, 1, 130_000, 65_536]
+    # (I16 sums run in 16 bits in the reference and a running sum that lands exactly on 0x8000 turns sticky-null: an
+    #  order-dependent artefact, see test_aggr — keep 16-bit sums far from wrapping)
+    span = 3 if t == ob.I16 else 500
+    parts = [rng_col(t, n, t * 10 + i, null_frac=0.0 if i % 2 else 0.001, lo=-span, hi=span + 1) for i, n in enumerate(lens)]
+    if t == ob.F64:
+        parts = [np.round(p * 8) / 8 for p in parts]
+    val = ops.parted(t, parts)
+    idx = ops.parted_index(1 if combine else len(parts))
+    with ops.scope():
+        for name, op in (("aggr_sum", ob.SUM), ("aggr_min", ob.MIN), ("aggr_max", ob.MAX), ("aggr_avg", ob.AVG)):
+            try:
+                want, wt = oracle.parted_aggr(op, t, parts, combine)
+            except ob.OracleError:
+                with pytest.raises(Declined):            # combinations the reference's partials have no case for stay on the CPU body
+                    ops.value(ops.call(name, val, idx))
+                continue
+            got, gt = ops.value(ops.call(name, val, idx))
+            assert gt == wt, (name, gt, wt)
+            assert same_f64(np.atleast_1d(got), want) if wt == ob.F64 else np.array_equal(np.atleast_1d(got), want), name
+    ops.drop(val, idx)
+
+
+def test_parted_aggregates_with_partition_filter(ops, oracle):
+    """a parted filter (core/aggr.c:209-243): NULL entry = partition excluded, atom -1 = all its rows, I64 vector = those rows"""
+    parts = [rng_col(ob.I64, n, i, null_frac=0.0, lo=-500, hi=500) for i, n in enumerate([80_000, 90_000, 100_000, 70_000])]
+    ids = np.sort(np.random.default_rng(1).choice(100_000, 30_000, replace=False)).astype(np.int64)
+    val = ops.parted(ob.I64, parts)
+    filt = ops.list_of([ops.NULL, ops.atom(ob.I64, -1), ops.vec(ob.I64, ids), ops.vec(ob.I64, np.empty(0, np.int64))])
+    import ctypes as C
+    C.c_int8.from_address(filt + 2).value = 77 + ob.I64
+    idx = ops.parted_index(1, filt)
+    with ops.scope():
+        got, gt = ops.value(ops.call("aggr_sum", val, idx))
+        assert gt == ob.I64 and int(got[0]) == int(parts[1].sum() + parts[2][ids].sum())
+        got, gt = ops.value(ops.call("aggr_max", val, idx))
+        assert int(got[0]) == max(int(parts[1].max()), int(parts[2][ids].max()))
+    ops.drop(val, idx)

@@ -387,3 +387,33 @@ def test_join_index_multi_key(oracle, reference, ncols, nb, np_):
     pi, bi = oracle.inner_join(bcols, pcols)
     rl, rr = reference.join_index(pcols, bcols, inner=True)
     assert np.array_equal(pi, rl[:pi.shape[0]]) and np.array_equal(bi, rr[:bi.shape[0]])
+
+
+# ---------------------------------------------------------------- parted aggregates
+
+def test_parted_aggregates_through_rayfall(oracle, reference, tmp_path):
+    """PARTED_MAP (core/aggr.c:183-260): a parted table written and re-opened by the reference itself (set-splayed / get-parted,
+    as tests/parted.c does), aggregated over all partitions and per partition; the oracle gets the same columns from numpy"""
+    root = str(tmp_path) + "/"
+    n, days = 2000, 4
+    setup = ('(do (set dbpath "%s") (set n %d)'
+             ' (set gen (fn [day] (let p (format "%%/%%/a/" dbpath (+ 2024.01.01 day)))'
+             '   (let t (table [v f] (list (- (%% (+ (* (til n) 7919) (* day 13)) 1000) 300) (div (as \'F64 (%% (+ (* (til n) 31) day) 640)) 8.0))))'
+             '   (set-splayed p t)))'
+             ' (map gen (til %d)) (set t (get-parted dbpath \'a)) 0)') % (root, n, days)
+    reference.eval(setup)
+    til = np.arange(n, dtype=np.int64)
+    v = [((til * 7919 + d * 13) % 1000 - 300) for d in range(days)]
+    f = [((til * 31 + d) % 640).astype(np.float64) / 8.0 for d in range(days)]
+
+    def ref(expr):
+        return reference.to_numpy(reference.eval(expr))[0]
+
+    for name, op in (("sum", ob.SUM), ("min", ob.MIN), ("max", ob.MAX), ("avg", ob.AVG)):
+        for col, parts, t in (("v", v, ob.I64), ("f", f, ob.F64)):
+            got = ref("(at (select {from: t r: (%s %s)}) 'r)" % (name, col))
+            want, wt = oracle.parted_aggr(op, t, parts, True)
+            assert same_f64(want, got) if wt == ob.F64 else np.array_equal(want, got), (name, col)
+            got = ref("(at (select {from: t by: Date r: (%s %s)}) 'r)" % (name, col))
+            want, wt = oracle.parted_aggr(op, t, parts, False)
+            assert same_f64(want, got) if wt == ob.F64 else np.array_equal(want, got), (name, col, "by Date")
