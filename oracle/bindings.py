@@ -362,6 +362,17 @@ class Reference:
         self.drop(xo, yo)
         return out
 
+    def isin(self, x, y):
+        """ray_in(x, y) on I64 vectors -> B8 mask"""
+        xo, yo = self.vec(I64, x), self.vec(I64, y)
+        self.L.ray_in.restype, self.L.ray_in.argtypes = C.c_void_p, [C.c_void_p, C.c_void_p]
+        r = self.L.ray_in(xo, yo)
+        if self.is_err(r):
+            raise RefError("ray_in")
+        out = self.to_numpy(r)[0]
+        self.drop(xo, yo)
+        return out
+
     def join_index(self, lcols, rcols, inner=False):
         """index_left_join_obj / index_inner_join_obj on lists of I64 key columns (2+ columns: the hashed multi-column path)"""
         lo, ro = self.make_list([self.vec(I64, c) for c in lcols]), self.make_list([self.vec(I64, c) for c in rcols])

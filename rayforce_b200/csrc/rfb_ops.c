@@ -1034,6 +1034,31 @@ obj_p rfb_ray_find(obj_p x, obj_p y) {
     return join_index(0, y, x, 1);
 }
 
+/* ray_in(x, y) on two I64-kind vectors of one type (core/items.c:781-783 -> index_in_i64_i64, core/index.c:1291-1370): mask of the
+ * x values that occur in y = "the first matching row of y exists" */
+obj_p rfb_ray_in(obj_p x, obj_p y) {
+    if (!G.ready || !is_key_vec(x) || !is_key_vec(y) || x->type != y->type) return NULL;
+    if (x->len == 0 || (too_small(x->len) && too_small(y->len))) return NULL;
+    call_scope_t sc = enter();
+    obj_p res;
+    const void *dx = dev_column(x), *dy = dev_column(y);
+    void *dids = dev_temp((size_t)x->len * 8), *dmask = dev_temp((size_t)x->len);
+    if (!dx || !dy || !dids || !dmask) { res = G.host->err_limit(); goto out; }
+    int rc = rfb_find_rows_dev(G.ctx, 1, (const int64_t *const *)&dy, y->len, (const int64_t *const *)&dx, x->len, (int64_t *)dids);
+    if (!rc) {
+        rfb_scalar_t none;
+        memset(&none, 0, sizeof(none));
+        none.type = RFB_T_I64;
+        none.v.i64 = RFB_NULL_I64;
+        rc = rfb_cmp_dev(G.ctx, RFB_NE, RFB_T_I64, dids, x->len, NULL, RFB_T_I64, NULL, -1, &none, (uint8_t *)dmask);
+    }
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = to_host_vector(RFB_T_B8, x->len, dmask);
+out:
+    leave(sc);
+    return res;
+}
+
 /* ------------------------------------------------------------------ sort */
 
 static obj_p sort_op(obj_p x, int desc) {

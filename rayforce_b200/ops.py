@@ -22,7 +22,7 @@ UNARY = ["ray_where", "ray_sum", "ray_min", "ray_max", "ray_avg", "ray_cnt", "ra
          "ray_sort_asc", "ray_sort_desc", "ray_med", "ray_dev"]
 BINARY = ["ray_eq", "ray_ne", "ray_lt", "ray_gt", "ray_le", "ray_ge", "filter_map", "filter_collect", "ray_add", "ray_sub",
           "ray_mul", "ray_div", "ray_fdiv", "ray_mod", "ray_xbar", "index_group", "group_map", "aggr_sum", "aggr_min", "aggr_max",
-          "aggr_count", "aggr_avg", "aggr_med", "aggr_stddev", "aggr_row", "aggr_collect", "ray_find", "where_lt_sum"]
+          "aggr_count", "aggr_avg", "aggr_med", "aggr_stddev", "aggr_row", "aggr_collect", "ray_find", "ray_in", "where_lt_sum"]
 TERNARY_I64 = ["index_left_join_obj", "index_inner_join_obj"]      # (obj, obj, int64 len)
 
 

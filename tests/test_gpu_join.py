@@ -74,6 +74,8 @@ def test_join_through_the_operator_layer(oracle):
         x, y = ops.vec(ob.I64, bcols[0]), ops.vec(ob.I64, pcols[0])
         got, gt = ops.value(ops.call("ray_find", x, y))
         assert np.array_equal(got, oracle.find_rows([bcols[0]], [pcols[0]]))
+        got, gt = ops.value(ops.call("ray_in", y, x))          # mask of the probe keys that occur in the build column
+        assert gt == ob.B8 and np.array_equal(got, (oracle.find_rows([bcols[0]], [pcols[0]]) != ob.NULL_I64).astype(np.uint8))
         f = ops.vec(ob.F64, np.arange(70_000, dtype=np.float64))
         with pytest.raises(Declined):                     # other key types stay on the reference's ray_find
             ops.value(ops.call("ray_find", f, f))

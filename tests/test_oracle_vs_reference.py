@@ -417,3 +417,14 @@ def test_parted_aggregates_through_rayfall(oracle, reference, tmp_path):
             got = ref("(at (select {from: t by: Date r: (%s %s)}) 'r)" % (name, col))
             want, wt = oracle.parted_aggr(op, t, parts, False)
             assert same_f64(want, got) if wt == ob.F64 else np.array_equal(want, got), (name, col, "by Date")
+
+
+@pytest.mark.parametrize("nx,ny,card", [(100, 30, 40), (80_000, 50_000, 20_000), (80_000, 50_000, 10**12)])
+def test_in_single_key(oracle, reference, nx, ny, card):
+    """ray_in -> index_in_i64_i64 (core/index.c:1291-1370) == "ray_find found a row" (non-negative keys: see test_find_single_key)"""
+    r = np.random.default_rng(nx + ny)
+    pool = r.integers(0, card, max(2, ny // 2)).astype(np.int64)
+    y = pool[r.integers(0, pool.shape[0], ny)]
+    x = np.concatenate([pool[r.integers(0, pool.shape[0], nx // 2)], r.integers(0, card, nx - nx // 2)]).astype(np.int64)
+    want = (oracle.find_rows([y], [x]) != ob.NULL_I64).astype(np.uint8)
+    assert np.array_equal(want, reference.isin(x, y).astype(np.uint8))
