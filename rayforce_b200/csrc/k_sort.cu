@@ -10,7 +10,7 @@
 //
 // Per pass:  HIST    G persistent CTAs, CTA b owns the contiguous chunk b of the current sequence: 256-bin counts
 //            SCAN    exclusive scan of the digit-major (256 x G) count matrix  -> first output slot of (digit, chunk)
-//            SCATTER CTA b walks its chunk tile by tile (3072 rows): warp-level multisplit (per-bit ballots) ranks rows of equal
+//            SCATTER CTA b walks its chunk tile by tile (3584 rows): warp-level multisplit (per-bit ballots) ranks rows of equal
 //                    digit in (warp, step, lane) order, warp counts are scanned across the CTA, the tile is ordered by
 //                    digit in shared memory and leaves as one contiguous run per digit; a running per-digit base carried
 //                    in shared memory keeps tiles of one chunk in order => stable.
@@ -23,12 +23,17 @@ namespace {
 
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
+// scatter geometry, measured on B200 (1e8 i64 rows, 8 passes; ITEMS x CTAs/SM x early row-id loads): 12x3x0 13.3 ms (before the
+// cross-tile pipeline), 12x3x1 14.1 (row ids spill), 12x2x0 12.8, 12x2x1 11.7, 14x2x1 11.3, 16x2x1 11.7, 18x2x1 12.2
+#ifndef RFB_SORT_EARLY_RID
+#define RFB_SORT_EARLY_RID 1
+#endif
 #ifndef RFB_SORT_ITEMS
-#define RFB_SORT_ITEMS 12
-#define RFB_SORT_CTAS 3
+#define RFB_SORT_ITEMS 14
+#define RFB_SORT_CTAS 2
 #endif
 constexpr int ITEMS = RFB_SORT_ITEMS;
-constexpr int TILE = THREADS * ITEMS;  // 3072 rows: 48 KB of staged (key, row id) pairs per CTA
+constexpr int TILE = THREADS * ITEMS;  // 3584 rows: 56 KB of staged (key, row id) pairs per CTA
 constexpr int RADIX = 256;
 
 template <typename T> __device__ __forceinline__ u64 sortable(T v);
@@ -145,18 +150,24 @@ k_scatter(Src src, i64 n, i64 chunk, int shift, const i64 *__restrict__ offs /* 
     const u32 lt = (1u << lane) - 1u;
     base[threadIdx.x] = offs[(i64)threadIdx.x * gridDim.x + blockIdx.x];
     const i64 lo = (i64)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    // software pipeline across tiles, without extra registers: a tile's keys are dead once they sit in shared memory, so the
+    // NEXT tile's keys are loaded into the same registers right before the write-out (their latency hides behind it), and the
+    // row ids of the current tile are requested right after the ranking, before the two barriers of the digit scan
+    u64 key[ITEMS];
+    {
+        const i64 wb0 = lo + (i64)warp * (32 * ITEMS);
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            const i64 i = wb0 + j * 32 + lane;
+            key[j] = i < hi ? src.key(i) : ~0ULL;
+        }
+    }
     for (i64 t0 = lo; t0 < hi; t0 += TILE) {
 #pragma unroll
         for (int w = 0; w < WARPS; w++) whist[w][threadIdx.x] = 0;
         __syncthreads();
-        u64 key[ITEMS];
         u32 rank[ITEMS];
         const i64 wb = t0 + (i64)warp * (32 * ITEMS);
-#pragma unroll
-        for (int j = 0; j < ITEMS; j++) {
-            const i64 i = wb + j * 32 + lane;
-            key[j] = i < hi ? src.key(i) : ~0ULL;
-        }
 #pragma unroll
         for (int j = 0; j < ITEMS; j++) {
             const i64 i = wb + j * 32 + lane;
@@ -178,6 +189,14 @@ k_scatter(Src src, i64 n, i64 chunk, int shift, const i64 *__restrict__ offs /* 
             __syncwarp();
             rank[j] = prior + __popc(peers & lt);
         }
+#if RFB_SORT_EARLY_RID
+        i64 rid[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) {
+            const i64 i = wb + j * 32 + lane;
+            rid[j] = i < hi ? src.val(i) : 0;
+        }
+#endif
         __syncthreads();
         u32 cnt;
         {   // thread d: digit d's counts over the warps -> exclusive warp offsets; then the tile-local start of each digit
@@ -207,10 +226,22 @@ k_scatter(Src src, i64 n, i64 chunk, int shift, const i64 *__restrict__ offs /* 
                 const u32 d = (u32)(key[j] >> shift) & 255u;
                 const u32 lp = dstart[d] + whist[warp][d] + rank[j];
                 skeys[lp] = key[j];
-                svals[lp] = src.val(i);   // (loading the row ids up front with the keys was measured: the extra registers spill, 13.3 -> 14.6 ms)
+#if RFB_SORT_EARLY_RID
+                svals[lp] = rid[j];
+#else
+                svals[lp] = src.val(i);
+#endif
             }
         }
         __syncthreads();
+        if (t0 + TILE < hi) {      // next tile's keys
+            const i64 nb = wb + TILE;
+#pragma unroll
+            for (int j = 0; j < ITEMS; j++) {
+                const i64 i = nb + j * 32 + lane;
+                key[j] = i < hi ? src.key(i) : ~0ULL;
+            }
+        }
         const int tile_n = (int)((hi - t0) < TILE ? (hi - t0) : TILE);
         for (int i = threadIdx.x; i < tile_n; i += THREADS) {
             const u64 k = skeys[i];
