@@ -278,6 +278,13 @@ int rfb_inner_join_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const *build_co
                        const int64_t *const *probe_cols, int64_t probe_len, int64_t *probe_ids, int64_t *build_ids,
                        int64_t *count);
 
+/* index_asof_join_obj (core/index.c:3194-3268): ids[i] = the LAST build row with probe row i's key tuple whose time is <= probe
+ * row i's time, else NULL_I64.  The search is the reference's binary search over the key's build rows in row order, so like
+ * there the build rows of one key must be ordered by time.  time_type: I32/DATE/TIME or I64/TIMESTAMP, same on both sides. */
+int rfb_asof_join_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const *build_cols, int time_type, const void *build_time,
+                      int64_t build_len, const int64_t *const *probe_cols, const void *probe_time, int64_t probe_len,
+                      int64_t *ids);
+
 /* ------------------------------------------------------------------ device layer: sort */
 
 /* ray_sort_asc / ray_sort_desc (core/sort.c:430-479, 691-740): stable permutation (I64 row ids).

@@ -43,12 +43,12 @@ static int want_stats = 0;
 
 enum { S_EQ, S_NE, S_LT, S_GT, S_LE, S_GE, S_WHERE, S_COLLECT, S_SUM, S_MIN, S_MAX, S_AVG, S_ADD, S_SUB, S_MUL, S_DIV, S_FDIV,
        S_MOD, S_XBAR, S_ROUND, S_FLOOR, S_CEIL, S_INDEX_GROUP, S_AGGR_SUM, S_AGGR_MIN, S_AGGR_MAX, S_AGGR_COUNT, S_AGGR_AVG, S_SORT_ASC,
-       S_SORT_DESC, S_SELECT, S_MED, S_DEV, S_AGGR_MED, S_AGGR_DEV, S_AGGR_ROW, S_AGGR_COLLECT, S_FIND, S_LEFT_JOIN, S_INNER_JOIN, S_IN, S_N };
+       S_SORT_DESC, S_SELECT, S_MED, S_DEV, S_AGGR_MED, S_AGGR_DEV, S_AGGR_ROW, S_AGGR_COLLECT, S_FIND, S_LEFT_JOIN, S_INNER_JOIN, S_IN, S_ASOF_JOIN, S_N };
 static const char *S_NAME[S_N] = {"ray_eq", "ray_ne", "ray_lt", "ray_gt", "ray_le", "ray_ge", "ray_where", "filter_collect", "ray_sum",
                                   "ray_min", "ray_max", "ray_avg", "ray_add", "ray_sub", "ray_mul", "ray_div", "ray_fdiv", "ray_mod", "ray_xbar",
                                   "ray_round", "ray_floor", "ray_ceil", "index_group", "aggr_sum", "aggr_min", "aggr_max", "aggr_count",
                                   "aggr_avg", "ray_sort_asc", "ray_sort_desc", "ray_select", "ray_med", "ray_dev", "aggr_med", "aggr_dev",
-                                  "aggr_row", "aggr_collect", "ray_find", "index_left_join_obj", "index_inner_join_obj", "ray_in"};
+                                  "aggr_row", "aggr_collect", "ray_find", "index_left_join_obj", "index_inner_join_obj", "ray_in", "index_asof_join_obj"};
 static long n_gpu[S_N], n_cpu[S_N];
 
 static void print_stats(void) {
@@ -124,6 +124,15 @@ WRAP2(ray_find, S_FIND) WRAP2(ray_in, S_IN)
         return __real_##sym(l, r, n);                                      \
     }
 WRAPJ(index_left_join_obj, S_LEFT_JOIN) WRAPJ(index_inner_join_obj, S_INNER_JOIN)
+obj_p __real_index_asof_join_obj(obj_p lc, obj_p lx, obj_p rc, obj_p rx);
+obj_p __wrap_index_asof_join_obj(obj_p lc, obj_p lx, obj_p rc, obj_p rx) {
+    if (gpu_ok()) {
+        obj_p res = (obj_p)rfb_index_asof_join_obj((rfb_obj_p)lc, (rfb_obj_p)lx, (rfb_obj_p)rc, (rfb_obj_p)rx);
+        if (res) { n_gpu[S_ASOF_JOIN]++; return res; }
+    }
+    n_cpu[S_ASOF_JOIN]++;
+    return __real_index_asof_join_obj(lc, lx, rc, rx);
+}
 #define rfb_aggr_dev rfb_aggr_stddev   /* the operator layer's name for the reference's aggr_dev */
 WRAP2(aggr_med, S_AGGR_MED) WRAP2(aggr_dev, S_AGGR_DEV) WRAP2(aggr_row, S_AGGR_ROW) WRAP2(aggr_collect, S_AGGR_COLLECT)
 

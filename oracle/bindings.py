@@ -242,6 +242,20 @@ class Oracle:
         self.L.rfo_find_rows(len(b), ba, b[0].shape[0], pa, p[0].shape[0], _ptr(ids))
         return ids
 
+    def asof_join(self, build_cols, tt, build_time, probe_cols, probe_time):
+        b = [np.ascontiguousarray(c, np.int64) for c in build_cols]
+        p = [np.ascontiguousarray(c, np.int64) for c in probe_cols]
+        bt, pt = np.ascontiguousarray(build_time, NP_OF[tt]), np.ascontiguousarray(probe_time, NP_OF[tt])
+        ids = np.empty(p[0].shape[0], np.int64)
+        ba = (C.c_void_p * len(b))(*[c.ctypes.data for c in b])
+        pa = (C.c_void_p * len(p))(*[c.ctypes.data for c in p])
+        self.L.rfo_asof_join.restype = C.c_int
+        self.L.rfo_asof_join.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_void_p]
+        r = self.L.rfo_asof_join(len(b), ba, tt, _ptr(bt), b[0].shape[0], pa, _ptr(pt), p[0].shape[0], _ptr(ids))
+        if r < 0:
+            raise OracleError(r)
+        return ids
+
     def inner_join(self, build_cols, probe_cols):
         ids = self.find_rows(build_cols, probe_cols)
         pi = np.nonzero(ids != NULL_I64)[0].astype(np.int64)
@@ -360,6 +374,19 @@ class Reference:
             raise RefError("ray_find")
         out = self.to_numpy(r)[0]
         self.drop(xo, yo)
+        return out
+
+    def asof_index(self, lcols, tt, lx, rcols, rx):
+        """index_asof_join_obj(lcols, lxcol, rcols, rxcol) on lists of I64 key columns + a time column on each side"""
+        lo, ro = self.make_list([self.vec(I64, c) for c in lcols]), self.make_list([self.vec(I64, c) for c in rcols])
+        lxo, rxo = self.vec(tt, lx), self.vec(tt, rx)
+        f = self.L.index_asof_join_obj
+        f.restype, f.argtypes = C.c_void_p, [C.c_void_p] * 4
+        r = f(lo, lxo, ro, rxo)
+        if self.is_err(r):
+            raise RefError("index_asof_join_obj")
+        out = self.to_numpy(r)[0]
+        self.drop(lo, ro, lxo, rxo)
         return out
 
     def isin(self, x, y):

@@ -841,6 +841,34 @@ int64_t rfo_inner_join(int ncols, const int64_t *const *build, int64_t build_len
     return j;
 }
 
+/* index_asof_join_obj (core/index.c:3194-3268): per key tuple the build rows in row order (push_raw :3219-3223); per probe row
+ * index_bin_i64 / index_bin_i32 (:3103-3138) over its key's list: the last entry whose time is <= the probe time */
+int rfo_asof_join(int ncols, const int64_t *const *build, int time_type, const void *build_time, int64_t build_len,
+                  const int64_t *const *probe, const void *probe_time, int64_t probe_len, int64_t *ids) {
+    int tk = kind_of(time_type);
+    if (!(tk == K_I64 || tk == K_I32)) return RFO_ERR_TYPE;
+    i64 nb = build_len > 0 ? build_len : 1;
+    i64 *gid = (i64 *)malloc((size_t)nb * 8), *firsts = (i64 *)malloc((size_t)nb * 8), *rows = (i64 *)malloc((size_t)nb * 8);
+    i64 *offs = (i64 *)malloc((size_t)(nb + 1) * 8), *first = (i64 *)malloc((size_t)(probe_len > 0 ? probe_len : 1) * 8), groups = 0;
+    rfo_group_multi(ncols, build, NULL, build_len, gid, firsts, &groups);
+    rfo_group_rows(gid, NULL, build_len, groups, rows, offs);
+    rfo_find_rows(ncols, build, build_len, probe, probe_len, first);
+    for (i64 i = 0; i < probe_len; i++) {
+        ids[i] = RFO_NULL_I64;
+        if (first[i] == RFO_NULL_I64) continue;
+        i64 g = gid[first[i]], base = offs[g], len = offs[g + 1] - base, left = 0, right = len - 1, idx = -1;
+        while (left <= right) {
+            i64 mid = left + (right - left) / 2;
+            int le = tk == K_I64 ? ((const i64 *)build_time)[rows[base + mid]] <= ((const i64 *)probe_time)[i]
+                                 : ((const i32 *)build_time)[rows[base + mid]] <= ((const i32 *)probe_time)[i];
+            if (le) { idx = mid; left = mid + 1; } else right = mid - 1;
+        }
+        if (idx >= 0) ids[i] = rows[base + idx];
+    }
+    free(gid); free(firsts); free(rows); free(offs); free(first);
+    return RFO_OK;
+}
+
 /* ------------------------------------------------------------------ key sort (core/sort.c) */
 
 /* order-preserving map to u64: integers flip the sign bit (core/sort.c:313), doubles core/sort.c:266-285 */

@@ -114,6 +114,10 @@ int rfo_find_rows(int ncols, const int64_t *const *build, int64_t build_len, con
 int64_t rfo_inner_join(int ncols, const int64_t *const *build, int64_t build_len, const int64_t *const *probe, int64_t probe_len,
                        int64_t *probe_ids, int64_t *build_ids);
 
+/* index_asof_join_obj (core/index.c:3194-3268): last build row of the probe row's key with time <= the probe time */
+int rfo_asof_join(int ncols, const int64_t *const *build, int time_type, const void *build_time, int64_t build_len,
+                  const int64_t *const *probe, const void *probe_time, int64_t probe_len, int64_t *ids);
+
 /* ---- key sort: core/sort.c:183-428 asc, :481-689 desc ---- stable permutation, nulls/NaN first when ascending */
 int rfo_sort(int type, const void *x, int64_t n, int descending, int64_t *perm);
 

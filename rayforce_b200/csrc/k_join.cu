@@ -5,6 +5,8 @@
 //                        FIRST build row with an equal key (tuple), else NULL_I64
 //   rfb_inner_join_dev   index_inner_join_obj (core/index.c:2930-3000): the matching (probe row, build row) pairs in
 //                        ascending probe-row order
+//   rfb_asof_join_dev    index_asof_join_obj (core/index.c:3194-3268): per probe row the LAST build row of its key whose
+//                        time is <= the probe row's time (binary search over the key's build rows in row order)
 //
 // The reference inserts the build rows sequentially into an open-addressing table that keeps the first row of every key
 // (core/index.c:2905-2909, 1558-1564) and probes it row by row.  The device builds one table of REPRESENTATIVE build rows
@@ -146,5 +148,68 @@ extern "C" int rfb_inner_join_dev(rfb_ctx_t *ctx, int ncols, const int64_t *cons
         k_take_i64<<<rfb_grid_for(ctx, *count, THREADS * 4, 8), THREADS, 0, ctx->stream>>>(ids, probe_ids, *count, build_ids);
         RFB_CHECK_LAUNCH(ctx);
     }
+    return RFB_OK;
+}
+
+// ------------------------------------------------------------------ asof join
+//
+// The reference keeps, per key tuple, the list of build rows in row order (push_raw, core/index.c:3219-3223) and binary-searches
+// it for the last entry whose time is <= the probe time (index_bin_i64 / index_bin_i32, core/index.c:3103-3138) — the search
+// itself assumes the key's build rows are ordered by time.  The device gets the same lists from the grouping kernels (group
+// the build rows by key tuple, order them by group with the stable sort), finds a probe row's key group through the join
+// table (first build row of the key -> its group id) and runs the identical search.
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(THREADS, 4)
+k_asof_search(const i64 *__restrict__ first, const i64 *__restrict__ gid_of_build, const i64 *__restrict__ rows, const i64 *__restrict__ offsets,
+              const T *__restrict__ build_time, const T *__restrict__ probe_time, i64 n, i64 *__restrict__ ids) {
+    for (i64 i = (i64)blockIdx.x * THREADS + threadIdx.x; i < n; i += (i64)gridDim.x * THREADS) {
+        const i64 f = ld_stream(first + i);
+        i64 found = NULL_I64;
+        if (f != NULL_I64) {
+            const i64 g = __ldg(gid_of_build + f);
+            const i64 base = __ldg(offsets + g), len = __ldg(offsets + g + 1) - base;
+            const T t = ld_stream(probe_time + i);
+            i64 left = 0, right = len - 1, idx = -1;
+            while (left <= right) {
+                const i64 mid = left + (right - left) / 2;
+                if (__ldg(build_time + __ldg(rows + base + mid)) <= t) { idx = mid; left = mid + 1; } else right = mid - 1;
+            }
+            if (idx >= 0) found = __ldg(rows + base + idx);
+        }
+        __stcs(ids + i, found);
+    }
+}
+}  // namespace
+
+extern "C" int rfb_asof_join_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const *build_cols, int time_type, const void *build_time,
+                                 int64_t build_len, const int64_t *const *probe_cols, const void *probe_time, int64_t probe_len, int64_t *ids) {
+    RFB_ARG(ctx && ncols >= 1 && ncols <= MAX_KEY_COLS && build_len >= 0 && probe_len >= 0 && build_cols && probe_cols && (ids || probe_len == 0) &&
+            (build_time || build_len == 0) && (probe_time || probe_len == 0), "rfb_asof_join_dev");
+    const int tk = rfb_kind_of(time_type);
+    if (!(tk == K_I64 || tk == K_I32) || time_type == RFB_SYMBOL) { rfb_set_error("asof join: time column type %d (I32/DATE/TIME or I64/TIMESTAMP)", time_type); return RFB_ERR_TYPE; }
+    if (probe_len == 0) return RFB_OK;
+    if (build_len == 0) {
+        k_fill_i64<<<rfb_grid_for(ctx, probe_len, 256, 8), 256, 0, ctx->stream>>>(ids, probe_len, NULL_I64);
+        RFB_CHECK_LAUNCH(ctx);
+        return RFB_OK;
+    }
+    void *buf;
+    const size_t bb = align256((size_t)build_len * 8), bp = align256((size_t)probe_len * 8);
+    int rc = rfb_ensure_aux2(ctx, 4 * bb + 256 + bp, &buf);
+    if (rc) return rc;
+    i64 *gids = (i64 *)buf, *firsts = (i64 *)((char *)buf + bb), *rows = (i64 *)((char *)buf + 2 * bb), *offsets = (i64 *)((char *)buf + 3 * bb);
+    i64 *first = (i64 *)((char *)buf + 4 * bb + 256);
+    rfb_group_info_t info;
+    rc = rfb_group_keys_i64_dev(ctx, ncols, build_cols, nullptr, build_len, gids, firsts, &info);
+    if (rc) return rc;
+    rc = rfb_group_rows_dev(ctx, gids, nullptr, build_len, info.groups, rows, offsets);
+    if (rc) return rc;
+    rc = rfb_find_rows_dev(ctx, ncols, build_cols, build_len, probe_cols, probe_len, first);
+    if (rc) return rc;
+    const int grid = rfb_grid_for(ctx, probe_len, THREADS * 2, 4);
+    if (tk == K_I64) k_asof_search<i64><<<grid, THREADS, 0, ctx->stream>>>(first, gids, rows, offsets, (const i64 *)build_time, (const i64 *)probe_time, probe_len, ids);
+    else k_asof_search<i32><<<grid, THREADS, 0, ctx->stream>>>(first, gids, rows, offsets, (const i32 *)build_time, (const i32 *)probe_time, probe_len, ids);
+    RFB_CHECK_LAUNCH(ctx);
     return RFB_OK;
 }

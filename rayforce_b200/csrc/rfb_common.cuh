@@ -47,6 +47,8 @@ struct rfb_ctx {
     // temporaries of the median / row-list pipelines): keeps cudaMalloc / cudaFree out of the per-call path
     void *d_aux;
     size_t aux_bytes;
+    void *d_aux2;              // third level: composite entry points (asof join) that call aux-using entry points themselves
+    size_t aux2_bytes;
     // host layer staging
     void *d_stage[2][RFB_STAGE_BUFS];  // [column][ring slot] device staging for chunked column shipping
     size_t stage_bytes;
@@ -62,6 +64,7 @@ void rfb_set_error(const char *fmt, ...);
 int rfb_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 int rfb_ensure_work(rfb_ctx_t *ctx, size_t bytes, void **out);
 int rfb_ensure_aux(rfb_ctx_t *ctx, size_t bytes, void **out);
+int rfb_ensure_aux2(rfb_ctx_t *ctx, size_t bytes, void **out);
 // host<->device copies that pick the fast route for the memory they are given (rfb_host.cu): pinned -> one async DMA;
 // pageable -> copier threads through the pinned ring.  `stream`: where the DMA is enqueued.
 int rfb_copy_h2d(rfb_ctx_t *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t stream);

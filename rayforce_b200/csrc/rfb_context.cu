@@ -50,6 +50,22 @@ int rfb_ensure_aux(rfb_ctx_t *ctx, size_t bytes, void **out) {
     return RFB_OK;
 }
 
+int rfb_ensure_aux2(rfb_ctx_t *ctx, size_t bytes, void **out) {
+    if (bytes > ctx->aux2_bytes) {
+        if (ctx->d_aux2) {
+            RFB_CUDA(cudaStreamSynchronize(ctx->stream));
+            RFB_CUDA(cudaFree(ctx->d_aux2));
+            ctx->d_aux2 = nullptr;
+            ctx->aux2_bytes = 0;
+        }
+        size_t want = bytes + (bytes >> 3) + (1 << 20);
+        RFB_CUDA(cudaMalloc(&ctx->d_aux2, want));
+        ctx->aux2_bytes = want;
+    }
+    *out = ctx->d_aux2;
+    return RFB_OK;
+}
+
 extern "C" {
 
 int rfb_abi_version(void) { return RFB_ABI_VERSION; }
@@ -116,6 +132,7 @@ void rfb_ctx_destroy(rfb_ctx_t *ctx) {
     rfb_copy_shutdown(ctx);
     if (ctx->d_work) cudaFree(ctx->d_work);
     if (ctx->d_aux) cudaFree(ctx->d_aux);
+    if (ctx->d_aux2) cudaFree(ctx->d_aux2);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

@@ -1034,6 +1034,41 @@ obj_p rfb_ray_find(obj_p x, obj_p y) {
     return join_index(0, y, x, 1);
 }
 
+/* index_asof_join_obj(lcols, lxcol, rcols, rxcol) (core/index.c:3194-3268): lists of key columns + the time column of each side */
+obj_p rfb_index_asof_join_obj(obj_p lcols, obj_p lxcol, obj_p rcols, obj_p rxcol) {
+    if (!G.ready || !lcols || !rcols || !lxcol || !rxcol) return NULL;
+    if (lcols->type != RFB_T_LIST || rcols->type != RFB_T_LIST || lcols->len < 1 || lcols->len > 8 || rcols->len != lcols->len) return NULL;
+    const int tt = lxcol->type;
+    if (tt != rxcol->type || !(tt == RFB_T_I64 || tt == RFB_T_TIMESTAMP || tt == RFB_T_I32 || tt == RFB_T_DATE || tt == RFB_T_TIME)) return NULL;
+    obj_p l[8], r[8];
+    int64_t ll = 0, rl = 0;
+    const int64_t len = lcols->len;
+    for (int64_t c = 0; c < len; c++) {
+        l[c] = RFB_OBJ_LIST(lcols)[c];
+        r[c] = RFB_OBJ_LIST(rcols)[c];
+        if (!is_key_vec(l[c]) || !is_key_vec(r[c]) || l[c]->type != r[c]->type || l[c]->len != l[0]->len || r[c]->len != r[0]->len) return NULL;
+    }
+    ll = l[0]->len;
+    rl = r[0]->len;
+    if (lxcol->len != ll || rxcol->len != rl || (too_small(ll) && too_small(rl))) return NULL;
+    call_scope_t sc = enter();
+    obj_p res = NULL;
+    const void *dl[8], *dr[8];
+    for (int64_t c = 0; c < len; c++) {
+        dl[c] = dev_column(l[c]);
+        dr[c] = dev_column(r[c]);
+        if (!dl[c] || !dr[c]) { res = G.host->err_limit(); goto out; }
+    }
+    void *dlx = dev_column(lxcol), *drx = dev_column(rxcol), *dids = dev_temp((size_t)(ll > 0 ? ll : 1) * 8);
+    if (!dlx || !drx || !dids) { res = G.host->err_limit(); goto out; }
+    int rc = rfb_asof_join_dev(G.ctx, (int)len, (const int64_t *const *)dr, tt, drx, rl, (const int64_t *const *)dl, dlx, ll, (int64_t *)dids);
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = to_host_vector(RFB_T_I64, ll, dids);
+out:
+    leave(sc);
+    return res;
+}
+
 /* ray_in(x, y) on two I64-kind vectors of one type (core/items.c:781-783 -> index_in_i64_i64, core/index.c:1291-1370): mask of the
  * x values that occur in y = "the first matching row of y exists" */
 obj_p rfb_ray_in(obj_p x, obj_p y) {

@@ -354,6 +354,16 @@ class _Ops:
         self.sync()
         return pi[:cnt.value], bi[:cnt.value]
 
+    def asof_join(self, build_cols, time_type, build_time, probe_cols, probe_time):
+        """index_asof_join_obj: last build row of the probe row's key with time <= the probe time, else NULL_I64"""
+        nb, np_ = build_cols[0].shape[0], probe_cols[0].shape[0]
+        ids = self._empty(np_, capi.I64)
+        b = (C.c_void_p * len(build_cols))(*[_dptr(c) for c in build_cols])
+        p = (C.c_void_p * len(probe_cols))(*[_dptr(c) for c in probe_cols])
+        check(self.lib.rfb_asof_join_dev(self.h, len(build_cols), b, time_type, _dptr(build_time), nb, p, _dptr(probe_time), np_, _dptr(ids)))
+        self.sync()
+        return ids
+
     def group_sum_count(self, key_type, keys, val, max_groups, cmp_op=None, pred_type=None, pred=None, k=None):
         """fused select {s: (sum v) c: (count v) from t by k [where (cmp p k)]} -> (keys, sums, counts) tensors"""
         n = keys.shape[0]

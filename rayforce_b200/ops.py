@@ -78,6 +78,7 @@ class Ops:
         for n in TERNARY_I64:
             f = getattr(L, "rfb_" + n)
             f.restype, f.argtypes = C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int64]
+        L.rfb_index_asof_join_obj.restype, L.rfb_index_asof_join_obj.argtypes = C.c_void_p, [C.c_void_p] * 4
         L.rfb_where_fold.restype, L.rfb_where_fold.argtypes = C.c_void_p, [C.POINTER(C.c_void_p), C.c_int64]
         self.NULL = self.host.null_obj
 

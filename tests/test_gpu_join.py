@@ -81,3 +81,34 @@ def test_join_through_the_operator_layer(oracle):
             ops.value(ops.call("ray_find", f, f))
         ops.drop(x, y, f)
     ops.drop(lo, ro)
+
+
+def asof_tables(ncols, nb, np_, seed, tt=ob.I64):
+    r = np.random.default_rng(seed)
+    bcols = [r.integers(0, 60 + c, nb).astype(np.int64) for c in range(ncols)]
+    pcols = [r.integers(0, 70 + c, np_).astype(np.int64) for c in range(ncols)]
+    bt = np.sort(r.integers(0, 10_000_000, nb)).astype(ob.NP_OF[tt])
+    pt = r.integers(-10, 10_000_100, np_).astype(ob.NP_OF[tt])
+    return bcols, bt, pcols, pt
+
+
+@pytest.mark.parametrize("ncols", [1, 2, 3])
+@pytest.mark.parametrize("tt", [ob.I64, ob.I32, ob.TIMESTAMP])
+@pytest.mark.parametrize("nb,np_", [(1, 5), (20, 5000), (300_007, 500_003)])
+def test_asof_join(ctx, oracle, ncols, tt, nb, np_):
+    """index_asof_join_obj (core/index.c:3194-3268): last build row of the probe row's key with time <= the probe time"""
+    bcols, bt, pcols, pt = asof_tables(ncols, nb, np_, nb + ncols, tt)
+    want = oracle.asof_join(bcols, tt, bt, pcols, pt)
+    got = ctx.asof_join([dev(c) for c in bcols], tt, dev(bt), [dev(c) for c in pcols], dev(pt))
+    assert np.array_equal(host(got), want)
+
+
+def test_asof_join_through_the_operator_layer(oracle):
+    ops = Ops.get(0)
+    bcols, bt, pcols, pt = asof_tables(2, 120_001, 200_003, 3)
+    lo, ro = ops.list_of([ops.vec(ob.I64, c) for c in pcols]), ops.list_of([ops.vec(ob.I64, c) for c in bcols])
+    lx, rx = ops.vec(ob.I64, pt), ops.vec(ob.I64, bt)
+    with ops.scope():
+        got, gt = ops.value(ops.L.rfb_index_asof_join_obj(lo, lx, ro, rx))
+        assert gt == ob.I64 and np.array_equal(got, oracle.asof_join(bcols, ob.I64, bt, pcols, pt))
+    ops.drop(lo, ro, lx, rx)

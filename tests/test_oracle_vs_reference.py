@@ -428,3 +428,24 @@ def test_in_single_key(oracle, reference, nx, ny, card):
     x = np.concatenate([pool[r.integers(0, pool.shape[0], nx // 2)], r.integers(0, card, nx - nx // 2)]).astype(np.int64)
     want = (oracle.find_rows([y], [x]) != ob.NULL_I64).astype(np.uint8)
     assert np.array_equal(want, reference.isin(x, y).astype(np.uint8))
+
+
+def asof_tables(ncols, nb, np_, seed, tt=ob.I64):
+    """build side sorted by time (asof joins search each key's rows in row order), probe side anywhere in the time range"""
+    r = np.random.default_rng(seed)
+    bcols = [r.integers(0, 6 + c, nb).astype(np.int64) for c in range(ncols)]
+    pcols = [r.integers(0, 7 + c, np_).astype(np.int64) for c in range(ncols)]
+    bt = np.sort(r.integers(0, 1_000_000, nb)).astype(ob.NP_OF[tt])
+    pt = r.integers(-10, 1_000_100, np_).astype(ob.NP_OF[tt])
+    return bcols, bt, pcols, pt
+
+
+@pytest.mark.parametrize("ncols", [1, 2])
+@pytest.mark.parametrize("tt", [ob.I64, ob.I32])
+@pytest.mark.parametrize("nb,np_", [(20, 50), (30_000, 50_000)])
+def test_asof_join_index(oracle, reference, ncols, tt, nb, np_):
+    """index_asof_join_obj (core/index.c:3194-3268)"""
+    bcols, bt, pcols, pt = asof_tables(ncols, nb, np_, nb + ncols, tt)
+    want = oracle.asof_join(bcols, tt, bt, pcols, pt)
+    assert np.array_equal(want, reference.asof_index(pcols, tt, pt, bcols, bt))
+    assert (want != ob.NULL_I64).any() and (want == ob.NULL_I64).any()
