@@ -1288,6 +1288,126 @@ k_part_accum(PartStore ps, int P, i64 kbase, i64 kmin, Accums ga) {
     if (dirty) sacc_flush(a, KP, (i64)((u64)kbase + (u64)p * KP - (u64)kmin), ga);
 }
 
+// ---- the same accumulate pass with the partition data staged by the TMA unit (cp.async.bulk + mbarrier): one CTA per SM,
+// 1024 threads, a 3-stage ring of 40 KB units (4096 values + 4096 slots) next to the 96 KB of accumulators.  Thread 0 issues
+// the bulk copies two units ahead; the consumers wait on the stage's mbarrier phase and read the unit from shared memory.
+// A CTA barrier per unit separates "everyone finished stage s" from "stage s is re-armed".
+constexpr int AT = 1024, ASTAGES = 3;
+struct __align__(16) AccumStage { u64 val[PTILE]; u16 slot[PTILE]; };
+
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(AT, 1)
+k_part_accum_tma(PartStore ps, int P, i64 kbase, i64 kmin, Accums ga) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    AccumStage *stage = (AccumStage *)s_dyn;                                   // ASTAGES x 40 KB
+    u32 *s_acc = (u32 *)(s_dyn + ASTAGES * sizeof(AccumStage));                // lo[KP] | hi[KP] | cnt[KP]
+    __shared__ u64 full[ASTAGES];
+    __shared__ u32 s_cnt[MAX_PARTS], s_ubase[MAX_PARTS + 1], s_wtot[MAX_PARTS / 32];
+    const SAcc a{s_acc, s_acc + KP, s_acc + 2 * KP};
+    sacc_zero(a, KP);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const u32 bucket0 = (u32)(((u64)kbase >> KP_LOG) & 255u);
+    if (tid == 0) {
+        for (int s = 0; s < ASTAGES; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    u32 c = 0, units = 0, incl = 0;
+    if (tid < MAX_PARTS) {
+        c = tid < P ? ps.cursor[(bucket0 + tid) & 255u] : 0;
+        s_cnt[tid] = c;
+        units = (c + PTILE - 1) / PTILE;
+        incl = units;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_wtot[tid >> 5] = incl;
+    }
+    __syncthreads();
+    if (tid < MAX_PARTS) {
+        u32 before = 0;
+        for (int w = 0; w < (tid >> 5); w++) before += s_wtot[w];
+        s_ubase[tid + 1] = before + incl;
+        if (tid == 0) s_ubase[0] = 0;
+    }
+    __syncthreads();
+    const u32 U = s_ubase[P];
+    const u32 u0 = (u32)((u64)blockIdx.x * U / gridDim.x), u1 = (u32)((u64)(blockIdx.x + 1) * U / gridDim.x);
+    // producer state (thread 0 only): partition cursor + cached block-table entry
+    int pp = 0;
+    u32 p_blk = 0xFFFFFFFFu, p_phys = 0;
+    auto issue = [&](u32 u) {
+        while (s_ubase[pp + 1] <= u) { pp++; p_blk = 0xFFFFFFFFu; }
+        const u32 r0 = (u - s_ubase[pp]) * PTILE, cnt = s_cnt[pp];
+        const u32 rows = cnt - r0 < (u32)PTILE ? cnt - r0 : (u32)PTILE, rows_up = (rows + 7u) & ~7u;
+        const u32 bucket = (bucket0 + pp) & 255u;
+        if ((r0 >> PB_LOG) != p_blk) { p_blk = r0 >> PB_LOG; p_phys = ps.bt[(size_t)bucket * ps.bt_stride + p_blk] - 1; }
+        const u64 base = (u64)p_phys * PB + (r0 & (PB - 1));
+        const int s = (int)((u - u0) % ASTAGES);
+        mbar_expect_tx(&full[s], rows_up * 10u);
+        bulk_g2s(stage[s].val, ps.val + base, rows_up * 8u, &full[s]);
+        bulk_g2s(stage[s].slot, ps.slot + base, rows_up * 2u, &full[s]);
+    };
+    if (tid == 0)
+        for (u32 u = u0; u < u1 && u < u0 + (ASTAGES - 1); u++) issue(u);
+    int p = 0;
+    while (p + 1 < P && s_ubase[p + 1] <= u0) p++;
+    bool dirty = false;
+    for (u32 u = u0; u < u1; u++) {
+        const u32 k = u - u0;
+        const int s = (int)(k % ASTAGES);
+        __syncthreads();                                                       // unit u-1 (stage (s+2)%3) fully consumed
+        if (tid == 0 && u + (ASTAGES - 1) < u1) issue(u + (ASTAGES - 1));
+        if (s_ubase[p + 1] <= u) {
+            if (dirty) sacc_flush(a, KP, (i64)((u64)kbase + (u64)p * KP - (u64)kmin), ga);
+            __syncthreads();
+            dirty = false;
+            while (s_ubase[p + 1] <= u) p++;
+        }
+        const u32 r0 = (u - s_ubase[p]) * PTILE, cnt = s_cnt[p];
+        const u32 rows = cnt - r0 < (u32)PTILE ? cnt - r0 : (u32)PTILE;
+        mbar_wait(&full[s], (k / ASTAGES) & 1u);
+        dirty = true;
+        const AccumStage &st = stage[s];
+#pragma unroll
+        for (int j = 0; j < PTILE / (2 * AT); j++) {
+            const u32 q = j * AT + tid;                                        // pair index
+            if (2 * q + 1 < rows) {
+                const ulonglong2 vv = *(const ulonglong2 *)&st.val[2 * q];
+                const u32 ss = *(const u32 *)&st.slot[2 * q];
+                sacc_add(a, ss & 0xFFFFu, (i64)vv.x);
+                sacc_add(a, ss >> 16, (i64)vv.y);
+            } else if (2 * q < rows) sacc_add(a, st.slot[2 * q], (i64)st.val[2 * q]);
+        }
+    }
+    __syncthreads();
+    if (dirty) sacc_flush(a, KP, (i64)((u64)kbase + (u64)p * KP - (u64)kmin), ga);
+}
+
 // min/max of the selected keys of the rows [r0, r1): the sample that decides whether the partitioned strategy is tried
 template <typename FS>
 __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_fused_scope_rows(FS fs, i64 r0, i64 r1, i64 *mm) {
@@ -1461,8 +1581,15 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
         k_fused_accum_smem<FS><<<pgrid, PT, (size_t)range * 12, ctx->stream>>>(fs, val, n, vec, kmin, (int)range, a);
         RFB_CHECK_LAUNCH(ctx);
     } else if (strategy == 2) {
-        RFB_CUDA(cudaFuncSetAttribute(k_part_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, KP * 12));
-        k_part_accum<<<2 * ctx->sm_count, PT, KP * 12, ctx->stream>>>(ps, (int)P, kbase, kmin, a);
+        const char *tma = getenv("RFB_ACCUM_TMA");       // "0": the register-staged kernel (128-bit loads) instead of the TMA ring
+        if (!(tma && tma[0] == '0')) {
+            const size_t smem = ASTAGES * sizeof(AccumStage) + KP * 12;
+            RFB_CUDA(cudaFuncSetAttribute(k_part_accum_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_part_accum_tma<<<ctx->sm_count, AT, smem, ctx->stream>>>(ps, (int)P, kbase, kmin, a);
+        } else {
+            RFB_CUDA(cudaFuncSetAttribute(k_part_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, KP * 12));
+            k_part_accum<<<2 * ctx->sm_count, PT, KP * 12, ctx->stream>>>(ps, (int)P, kbase, kmin, a);
+        }
         RFB_CHECK_LAUNCH(ctx);
     } else {
         k_fused_accum_l2<FS><<<grid, THREADS, 0, ctx->stream>>>(fs, val, n, kmin, a);

@@ -463,6 +463,36 @@ def test_fused_group_sample_misjudges_the_key_range(ctx, oracle, monkeypatch, ou
     assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val, wg, wi.groups)[0])
 
 
+@pytest.mark.parametrize("n,card,kmin,skew", [(1_000_003, 100_000, 17, False), (1_000_003, 100_000, -8192 * 3 - 5, True), (2_500_001, 1_900_000, 5, False),
+                                              (300_007, 9000, -1500, False)])
+@pytest.mark.parametrize("with_pred", [False, True])
+@pytest.mark.parametrize("tma", ["1", "0"])
+def test_fused_group_partitioned_tma_accumulate(ctx, oracle, monkeypatch, n, card, kmin, skew, with_pred, tma):
+    """both variants of the accumulate pass — partition data staged by the TMA unit (cp.async.bulk + mbarrier ring, the default)
+    and by 128-bit register loads (RFB_ACCUM_TMA=0) — against the oracle"""
+    monkeypatch.setenv("RFB_GROUP_STRATEGY", "part")
+    monkeypatch.setenv("RFB_ACCUM_TMA", tma)
+    r = np.random.default_rng(n + card)
+    keys = r.integers(0, card, n).astype(np.int64)
+    if skew:
+        hot = r.random(n) < 0.8
+        keys[hot] = np.where(r.random(int(hot.sum())) < 0.5, 3, card - 2)
+    keys += kmin
+    val = r.integers(-(1 << 40), 1 << 40, n).astype(np.int64)
+    val[r.random(n) < 0.0002] = ob.NULL_I64
+    if with_pred:
+        filt = oracle.where(oracle.cmp(ob.LT, ob.I64, val, ob.I64, 1 << 19))
+        gk, gs, gc = ctx.group_sum_count(ob.I64, dev(keys), dev(val), card + 5, cmp_op=capi.LT, pred_type=ob.I64, pred=dev(val), k=1 << 19)
+    else:
+        filt = None
+        gk, gs, gc = ctx.group_sum_count(ob.I64, dev(keys), dev(val), card + 5)
+    wg, wf, wi = oracle.group_i64(keys, filt)
+    rows = wf if filt is None else filt[wf]
+    assert np.array_equal(host(gk), keys[rows])
+    assert np.array_equal(host(gs), oracle.aggr(ob.SUM, ob.I64, val, wg, wi.groups, filt)[0])
+    assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val, wg, wi.groups, filt)[0])
+
+
 def test_fused_group_partitioned_unaligned_columns(ctx, oracle, monkeypatch):
     """columns that start at an odd element (no 16-byte alignment) take the scalar tile loader"""
     monkeypatch.setenv("RFB_GROUP_STRATEGY", "part")
