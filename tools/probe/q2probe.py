@@ -1,3 +1,5 @@
+"""Probe: wall-clock of the multi-key / low-cardinality grouping entry points at 1e7 rows (the H2O Q2 / Q7 building blocks);
+used while tracking down per-call cudaMalloc jitter and same-address first-row claims.  python tools/probe/q2probe.py"""
 import sys, os, time
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
