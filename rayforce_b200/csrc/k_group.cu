@@ -18,6 +18,8 @@
 //   4. assign    group_ids[row] = gid_of_slot[slot(key_row)]
 // Aggregates are per-group accumulators updated with L2 atomics (red.global), finalised by a small per-group kernel
 // (sticky-null sums, +INF/NULL-initialised min/max, f64 averages).
+#include <type_traits>
+
 #include "rfb_scan.cuh"
 #include "rfb_moments.cuh"
 
@@ -116,6 +118,66 @@ __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_scope(Src src, i64 n
         atomicMin((long long *)&mm[0], (long long)lo);
         atomicMax((long long *)&mm[1], (long long)hi);
     }
+}
+
+// unfiltered, 16-byte aligned key column: two keys per 128-bit load, four loads in flight per thread
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_scope_vec(const i64 *__restrict__ keys, i64 n, i64 *mm) {
+    __shared__ i64 red[32];
+    i64 lo = RFB_INF_I64, hi = NULL_I64;
+    constexpr int U = 4;
+    const i64 pairs = n >> 1, stride = (i64)gridDim.x * THREADS;
+    i64 i = (i64)blockIdx.x * THREADS + threadIdx.x;
+    for (; i + (U - 1) * stride < pairs; i += U * stride) {
+        vec16 v[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) v[j] = ld_stream16(keys + 2 * (i + j * stride));
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const i64 a = (i64)v[j].lo, b = (i64)v[j].hi;
+            lo = a < lo ? a : lo; hi = a > hi ? a : hi;
+            lo = b < lo ? b : lo; hi = b > hi ? b : hi;
+        }
+    }
+    for (; i < pairs; i += stride) {
+        const vec16 v = ld_stream16(keys + 2 * i);
+        const i64 a = (i64)v.lo, b = (i64)v.hi;
+        lo = a < lo ? a : lo; hi = a > hi ? a : hi;
+        lo = b < lo ? b : lo; hi = b > hi ? b : hi;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) { const i64 a = keys[n - 1]; lo = a < lo ? a : lo; hi = a > hi ? a : hi; }
+    struct Mn { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b < a ? b : a; } };
+    struct Mx { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b > a ? b : a; } };
+    lo = block_reduce<i64>(lo, Mn(), RFB_INF_I64, red);
+    hi = block_reduce<i64>(hi, Mx(), NULL_I64, red);
+    if (threadIdx.x == 0) {
+        atomicMin((long long *)&mm[0], (long long)lo);
+        atomicMax((long long *)&mm[1], (long long)hi);
+    }
+}
+
+// group_ids[row] = gid_of_slot[key - min] for an unfiltered dense key column, two rows per 128-bit load / store
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_assign_dense_vec(const i64 *__restrict__ keys, i64 kmin, i64 n, const i64 *__restrict__ gid_of_slot, i64 *__restrict__ group_ids) {
+    constexpr int U = 4;
+    const i64 pairs = n >> 1, stride = (i64)gridDim.x * THREADS;
+    i64 i = (i64)blockIdx.x * THREADS + threadIdx.x;
+    for (; i + (U - 1) * stride < pairs; i += U * stride) {
+        vec16 v[U], g[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) v[j] = ld_stream16(keys + 2 * (i + j * stride));
+#pragma unroll
+        for (int j = 0; j < U; j++) { g[j].lo = (u64)__ldg(&gid_of_slot[(i64)(v[j].lo - (u64)kmin)]); g[j].hi = (u64)__ldg(&gid_of_slot[(i64)(v[j].hi - (u64)kmin)]); }
+#pragma unroll
+        for (int j = 0; j < U; j++) st_stream16(group_ids + 2 * (i + j * stride), g[j]);
+    }
+    for (; i < pairs; i += stride) {
+        const vec16 v = ld_stream16(keys + 2 * i);
+        vec16 g;
+        g.lo = (u64)__ldg(&gid_of_slot[(i64)(v.lo - (u64)kmin)]);
+        g.hi = (u64)__ldg(&gid_of_slot[(i64)(v.hi - (u64)kmin)]);
+        st_stream16(group_ids + 2 * i, g);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) group_ids[n - 1] = gid_of_slot[(i64)((u64)keys[n - 1] - (u64)kmin)];
 }
 
 // ------------------------------------------------------------------ 2. claim
@@ -249,7 +311,14 @@ int number_groups(rfb_ctx_t *ctx, Src src, Slot slot, i64 len, i64 slots, u64 *f
     k_number<Src, Slot><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(src, slot, limit, first_row, gid_of_slot, first_ids, ctl);
     RFB_CHECK_LAUNCH(ctx);
     if (group_ids) {
-        k_assign<Src, Slot><<<grid, THREADS, 0, ctx->stream>>>(src, slot, len, gid_of_slot, group_ids);
+        bool done = false;
+        if constexpr (!INSERT && std::is_same<Src, KeySrc>::value && std::is_same<Slot, DenseSlot>::value) {
+            if (!src.filter && aligned16(src.keys) && aligned16(group_ids)) {
+                k_assign_dense_vec<<<rfb_grid_for(ctx, len, THREADS * 8, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(src.keys, slot.min, len, gid_of_slot, group_ids);
+                done = true;
+            }
+        }
+        if (!done) k_assign<Src, Slot><<<grid, THREADS, 0, ctx->stream>>>(src, slot, len, gid_of_slot, group_ids);
         RFB_CHECK_LAUNCH(ctx);
     }
     RFB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -273,7 +342,8 @@ extern "C" int rfb_group_i64_dev(rfb_ctx_t *ctx, const int64_t *keys, const int6
     i64 *mm = (i64 *)((char *)ctx->d_scratch + 32768);  // {min, max, limit}
     k_scope_init<<<1, 1, 0, ctx->stream>>>(mm);
     RFB_CHECK_LAUNCH(ctx);
-    k_scope<KeySrc><<<rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(src, len, mm);
+    if (!filter && aligned16(keys)) k_scope_vec<<<rfb_grid_for(ctx, len, THREADS * 8, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(keys, len, mm);
+    else k_scope<KeySrc><<<rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(src, len, mm);
     RFB_CHECK_LAUNCH(ctx);
     i64 h[2];
     int rc = d2h_sync(ctx, h, mm, 16);
