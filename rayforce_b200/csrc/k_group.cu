@@ -558,6 +558,24 @@ __device__ __forceinline__ void sacc_add(const SAcc &a, u32 s, i64 v) {
     }
     atomicAdd(&a.cnt[s], 1u);
 }
+// the same for one row per lane of a full warp: when all 32 lanes are selected, non-null and hit the SAME slot (a single-key or
+// heavily skewed column) the warp adds its values with shuffles and issues one atomic set instead of 32 conflicting ones
+__device__ __forceinline__ void sacc_add_warp(const SAcc &a, bool sel, u32 s, i64 v) {
+    const u32 s0 = __shfl_sync(0xffffffffu, s, 0);
+    if (__all_sync(0xffffffffu, sel && s == s0 && v != NULL_I64)) {
+        u64 t = (u64)v;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+        if ((threadIdx.x & 31) == 0) {
+            const u32 lo = (u32)t;
+            u32 hi = (u32)(t >> 32);
+            const u32 old = atomicAdd(&a.lo[s0], lo);
+            hi += (u32)((u32)(old + lo) < lo);
+            if (hi) atomicAdd(&a.hi[s0], hi);
+            atomicAdd(&a.cnt[s0], 32u);
+        }
+    } else if (sel) sacc_add(a, s, v);
+}
 __device__ __forceinline__ void sacc_zero(const SAcc &a, int slots) {
     for (int s = threadIdx.x; s < slots; s += blockDim.x) { a.lo[s] = 0; a.hi[s] = 0; a.cnt[s] = 0; }
 }
@@ -1079,8 +1097,7 @@ k_fused_accum_smem(FS fs, const i64 *__restrict__ val, i64 n, bool vec, i64 kmin
         bool sel[8];
         load_tile<PT, true, 8>(fs, val, tile * PTILE, n, vec, k, v, sel);
 #pragma unroll
-        for (int j = 0; j < 8; j++)
-            if (sel[j]) sacc_add(a, (u32)((u64)k[j] - (u64)kmin), v[j]);
+        for (int j = 0; j < 8; j++) sacc_add_warp(a, sel[j], (u32)((u64)k[j] - (u64)kmin), v[j]);
     }
     __syncthreads();
     sacc_flush(a, range, 0, ga);
@@ -1105,12 +1122,13 @@ k_fused_accum_mod(FS fs, const i64 *__restrict__ val, i64 n, bool vec, Accums gm
         bool sel[8];
         load_tile<PT, true, 8>(fs, val, tile * PTILE, n, vec, k, v, sel);
 #pragma unroll
-        for (int j = 0; j < 8; j++)
+        for (int j = 0; j < 8; j++) {
             if (sel[j]) {
                 lo = (KT)k[j] < lo ? (KT)k[j] : lo;
                 hi = (KT)k[j] > hi ? (KT)k[j] : hi;
-                sacc_add(a, (u32)((u64)k[j] & (KP - 1)), v[j]);
             }
+            sacc_add_warp(a, sel[j], (u32)((u64)k[j] & (KP - 1)), v[j]);
+        }
     }
     __syncthreads();
     sacc_flush(a, KP, 0, gmod);

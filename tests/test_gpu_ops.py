@@ -509,6 +509,38 @@ def test_fused_group_partitioned_unaligned_columns(ctx, oracle, monkeypatch):
     assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val[1:], wg, wi.groups)[0])
 
 
+@pytest.mark.parametrize("card", [1, 2, 3])
+@pytest.mark.parametrize("with_pred", [False, True])
+@pytest.mark.parametrize("auto", [False, True])
+def test_fused_group_single_and_few_keys(ctx, oracle, monkeypatch, card, with_pred, auto):
+    """one to three keys: whole warps hit the same accumulator slot (the warp-aggregated path of the shared-memory strategies);
+    wrapping sums, nulls in some warps only, long runs of one key"""
+    if auto:
+        monkeypatch.setenv("RFB_PART_MIN_ROWS", "1000")
+    n = 400_003
+    r = np.random.default_rng(card)
+    keys = (np.arange(n) // 5000 % card + 7).astype(np.int64)          # runs of 5000 equal keys: most warps are uniform
+    keys[r.random(n) < 0.001] = 7 + card - 1
+    val = r.integers(-(1 << 62), 1 << 62, n).astype(np.int64)
+    val[r.random(n) < 0.00005] = ob.NULL_I64
+    if with_pred:
+        filt = oracle.where(oracle.cmp(ob.LT, ob.I64, val, ob.I64, 1 << 61))
+        gk, gs, gc = ctx.group_sum_count(ob.I64, dev(keys), dev(val), 8, cmp_op=capi.LT, pred_type=ob.I64, pred=dev(val), k=1 << 61)
+    else:
+        filt = None
+        gk, gs, gc = ctx.group_sum_count(ob.I64, dev(keys), dev(val), 8)
+    wg, wf, wi = oracle.group_i64(keys, filt)
+    rows = wf if filt is None else filt[wf]
+    assert np.array_equal(host(gk), keys[rows])
+    assert np.array_equal(host(gs), oracle.aggr(ob.SUM, ob.I64, val, wg, wi.groups, filt)[0])
+    assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val, wg, wi.groups, filt)[0])
+    # no nulls at all: the sums themselves (not the sticky null) are compared
+    val2 = np.where(val == ob.NULL_I64, 5, val)
+    gk, gs, gc = ctx.group_sum_count(ob.I64, dev(keys), dev(val2), 8)
+    wg, wf, wi = oracle.group_i64(keys)
+    assert np.array_equal(host(gs), oracle.aggr(ob.SUM, ob.I64, val2, wg, wi.groups)[0])
+
+
 def test_fused_group_nothing_selected(ctx):
     keys, val = dev(np.arange(100, dtype=np.int64)), dev(np.arange(100, dtype=np.int64))
     gk, gs, gc = ctx.group_sum_count(ob.I64, keys, val, 10, cmp_op=capi.LT, pred_type=ob.I64, pred=val, k=-5)

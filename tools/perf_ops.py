@@ -106,6 +106,10 @@ def main():
         del gids, firsts, k64
         k100 = col(capi.I64, 9, 100)
         timed("group_sum_count_i64keys_100", lambda: ctx.group_sum_count(capi.I64, k100, y, 100), 16 * n, "low cardinality (H2O id1-like)")
+        for card in (1, 2, 8):
+            kc = col(capi.I64, 9, card)
+            timed("group_sum_count_i64keys_%d" % card, lambda: ctx.group_sum_count(capi.I64, kc, y, card), 16 * n, "very low cardinality")
+            del kc
         g100, _, i100 = ctx.group_i64(k100)
         timed("aggr_sum_i64_100", lambda: ctx.aggr(capi.A_SUM, capi.I64, y, g100, i100.groups), 16 * n, "CTA-private 32-bit shared accumulators")
         timed("aggr_avg_i64_100", lambda: ctx.aggr(capi.A_AVG, capi.I64, y, g100, i100.groups), 16 * n)
