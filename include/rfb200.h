@@ -285,6 +285,12 @@ int rfb_asof_join_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const *build_col
                       int64_t build_len, const int64_t *const *probe_cols, const void *probe_time, int64_t probe_len,
                       int64_t *ids);
 
+/* ray_distinct -> index_distinct_i64 (core/index.c:551-607), its direct-addressing branch (key range <= len or <= 2^20): the
+ * distinct keys in ASCENDING order; out must hold min(n, range) entries, *count (host) = how many.  RFB_ERR_ARG when the
+ * range is not dense: the reference's hash branch emits the keys in the slot order of its own table, which a parallel
+ * build cannot reproduce — callers keep that case on the CPU body. */
+int rfb_distinct_i64_dev(rfb_ctx_t *ctx, const int64_t *keys, int64_t n, int64_t *out, int64_t *count);
+
 /* ------------------------------------------------------------------ device layer: sort */
 
 /* ray_sort_asc / ray_sort_desc (core/sort.c:430-479, 691-740): stable permutation (I64 row ids).

@@ -153,6 +153,7 @@ rfb_obj_p rfb_index_left_join_obj(rfb_obj_p lcols, rfb_obj_p rcols, int64_t len)
 rfb_obj_p rfb_index_inner_join_obj(rfb_obj_p lcols, rfb_obj_p rcols, int64_t len);
 rfb_obj_p rfb_index_asof_join_obj(rfb_obj_p lcols, rfb_obj_p lxcol, rfb_obj_p rcols, rfb_obj_p rxcol);   /* core/index.c:3194-3268 */
 rfb_obj_p rfb_ray_find(rfb_obj_p x, rfb_obj_p y);
+rfb_obj_p rfb_ray_distinct(rfb_obj_p x);            /* ray_distinct, dense I64-kind key ranges (core/index.c:551-577): ascending distinct keys */
 rfb_obj_p rfb_ray_in(rfb_obj_p x, rfb_obj_p y);      /* ray_in -> index_in_i64_i64 (core/index.c:1291-1370): B8 mask of the x values present in y */
 
 /* ---- key sort: ray_sort_asc/desc (core/sort.c:430,691) = ray_iasc/idesc (core/order.c:32): stable i64 permutation */

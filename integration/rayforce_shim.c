@@ -43,12 +43,12 @@ static int want_stats = 0;
 
 enum { S_EQ, S_NE, S_LT, S_GT, S_LE, S_GE, S_WHERE, S_COLLECT, S_SUM, S_MIN, S_MAX, S_AVG, S_ADD, S_SUB, S_MUL, S_DIV, S_FDIV,
        S_MOD, S_XBAR, S_ROUND, S_FLOOR, S_CEIL, S_INDEX_GROUP, S_AGGR_SUM, S_AGGR_MIN, S_AGGR_MAX, S_AGGR_COUNT, S_AGGR_AVG, S_SORT_ASC,
-       S_SORT_DESC, S_SELECT, S_MED, S_DEV, S_AGGR_MED, S_AGGR_DEV, S_AGGR_ROW, S_AGGR_COLLECT, S_FIND, S_LEFT_JOIN, S_INNER_JOIN, S_IN, S_ASOF_JOIN, S_N };
+       S_SORT_DESC, S_SELECT, S_MED, S_DEV, S_AGGR_MED, S_AGGR_DEV, S_AGGR_ROW, S_AGGR_COLLECT, S_FIND, S_LEFT_JOIN, S_INNER_JOIN, S_IN, S_ASOF_JOIN, S_DISTINCT, S_N };
 static const char *S_NAME[S_N] = {"ray_eq", "ray_ne", "ray_lt", "ray_gt", "ray_le", "ray_ge", "ray_where", "filter_collect", "ray_sum",
                                   "ray_min", "ray_max", "ray_avg", "ray_add", "ray_sub", "ray_mul", "ray_div", "ray_fdiv", "ray_mod", "ray_xbar",
                                   "ray_round", "ray_floor", "ray_ceil", "index_group", "aggr_sum", "aggr_min", "aggr_max", "aggr_count",
                                   "aggr_avg", "ray_sort_asc", "ray_sort_desc", "ray_select", "ray_med", "ray_dev", "aggr_med", "aggr_dev",
-                                  "aggr_row", "aggr_collect", "ray_find", "index_left_join_obj", "index_inner_join_obj", "ray_in", "index_asof_join_obj"};
+                                  "aggr_row", "aggr_collect", "ray_find", "index_left_join_obj", "index_inner_join_obj", "ray_in", "index_asof_join_obj", "ray_distinct"};
 static long n_gpu[S_N], n_cpu[S_N];
 
 static void print_stats(void) {
@@ -112,7 +112,7 @@ WRAP2(index_group, S_INDEX_GROUP)
 WRAP2(aggr_sum, S_AGGR_SUM) WRAP2(aggr_min, S_AGGR_MIN) WRAP2(aggr_max, S_AGGR_MAX) WRAP2(aggr_count, S_AGGR_COUNT) WRAP2(aggr_avg, S_AGGR_AVG)
 WRAP1(ray_sort_asc, S_SORT_ASC) WRAP1(ray_sort_desc, S_SORT_DESC)
 WRAP1(ray_med, S_MED) WRAP1(ray_dev, S_DEV)
-WRAP2(ray_find, S_FIND) WRAP2(ray_in, S_IN)
+WRAP2(ray_find, S_FIND) WRAP2(ray_in, S_IN) WRAP1(ray_distinct, S_DISTINCT)
 #define WRAPJ(sym, slot)                                                   \
     obj_p __real_##sym(obj_p l, obj_p r, i64_t n);                         \
     obj_p __wrap_##sym(obj_p l, obj_p r, i64_t n) {                        \

@@ -261,6 +261,16 @@ class Oracle:
         pi = np.nonzero(ids != NULL_I64)[0].astype(np.int64)
         return pi, ids[pi]
 
+    def distinct(self, keys):
+        keys = np.ascontiguousarray(keys, np.int64)
+        out = np.empty(max(keys.shape[0], 1), np.int64)
+        self.L.rfo_distinct_i64.restype = C.c_int64
+        self.L.rfo_distinct_i64.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        c = self.L.rfo_distinct_i64(_ptr(keys), keys.shape[0], _ptr(out))
+        if c < 0:
+            raise OracleError(-4)
+        return out[:c].copy()
+
     def med(self, t, x):
         return self._stat(self.L.rfo_med, t, x)
 
@@ -331,7 +341,7 @@ class Reference:
         L.clone_obj.argtypes = [vp]
         for name in ("ray_sum", "ray_min", "ray_max", "ray_cnt", "ray_avg", "ray_count", "ray_where", "ray_round",
                      "ray_floor", "ray_ceil", "ray_sort_asc", "ray_sort_desc", "ray_iasc", "ray_idesc", "ray_asc",
-                     "ray_desc", "ray_med", "ray_dev"):
+                     "ray_desc", "ray_med", "ray_dev", "ray_distinct"):
             f = getattr(L, name)
             f.restype = vp
             f.argtypes = [vp]

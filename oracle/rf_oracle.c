@@ -869,6 +869,23 @@ int rfo_asof_join(int ncols, const int64_t *const *build, int time_type, const v
     return RFO_OK;
 }
 
+/* ray_distinct -> index_distinct_i64 (core/index.c:551-607), direct-addressing branch only (range <= len or <= MAX_RANGE = 2^20):
+ * mark the slots that occur, emit slot + min in ascending order.  Returns the count, or -1 when the range is not dense (the
+ * hash branch's result order is the slot order of the reference's own table: not restated). */
+int64_t rfo_distinct_i64(const int64_t *keys, int64_t n, int64_t *out) {
+    if (n == 0) return 0;
+    i64 mn = keys[0], mx = keys[0];
+    for (i64 i = 1; i < n; i++) { if (keys[i] < mn) mn = keys[i]; if (keys[i] > mx) mx = keys[i]; }
+    i64 range = (i64)((u64)mx - (u64)mn + 1);
+    if (range <= 0 || !(range <= n || range <= (1 << 20))) return -1;
+    u8 *mark = (u8 *)calloc((size_t)range, 1);
+    for (i64 i = 0; i < n; i++) mark[keys[i] - mn] = 1;
+    i64 j = 0;
+    for (i64 s = 0; s < range; s++) if (mark[s]) out[j++] = s + mn;
+    free(mark);
+    return j;
+}
+
 /* ------------------------------------------------------------------ key sort (core/sort.c) */
 
 /* order-preserving map to u64: integers flip the sign bit (core/sort.c:313), doubles core/sort.c:266-285 */

@@ -118,6 +118,9 @@ int64_t rfo_inner_join(int ncols, const int64_t *const *build, int64_t build_len
 int rfo_asof_join(int ncols, const int64_t *const *build, int time_type, const void *build_time, int64_t build_len,
                   const int64_t *const *probe, const void *probe_time, int64_t probe_len, int64_t *ids);
 
+/* ray_distinct -> index_distinct_i64, dense branch (core/index.c:551-577): ascending distinct keys; -1 = not dense */
+int64_t rfo_distinct_i64(const int64_t *keys, int64_t n, int64_t *out);
+
 /* ---- key sort: core/sort.c:183-428 asc, :481-689 desc ---- stable permutation, nulls/NaN first when ascending */
 int rfo_sort(int type, const void *x, int64_t n, int descending, int64_t *perm);
 

@@ -393,6 +393,55 @@ extern "C" int rfb_group_i64_dev(rfb_ctx_t *ctx, const int64_t *keys, const int6
     return RFB_OK;
 }
 
+// ------------------------------------------------------------------ distinct keys (dense domain)
+
+namespace {
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_mark_keys(const i64 *__restrict__ keys, i64 n, i64 kmin, u8 *mark) {
+    for (i64 i = (i64)blockIdx.x * THREADS + threadIdx.x; i < n; i += (i64)gridDim.x * THREADS) {
+        const i64 s = (i64)((u64)ld_stream(keys + i) - (u64)kmin);
+        if (!__ldg(mark + s)) mark[s] = 1;            // plain store: every writer writes the same byte
+    }
+}
+__global__ void __launch_bounds__(THREADS) k_add_const(i64 *p, i64 n, i64 c) {
+    for (i64 i = (i64)blockIdx.x * THREADS + threadIdx.x; i < n; i += (i64)gridDim.x * THREADS) p[i] = (i64)((u64)p[i] + (u64)c);
+}
+}  // namespace
+
+extern "C" int rfb_distinct_i64_dev(rfb_ctx_t *ctx, const int64_t *keys, int64_t n, int64_t *out, int64_t *count) {
+    RFB_ARG(ctx && count && n >= 0 && ((keys && out) || n == 0), "rfb_distinct_i64_dev");
+    *count = 0;
+    if (n == 0) return RFB_OK;
+    i64 *mm = (i64 *)((char *)ctx->d_scratch + 32768);
+    k_scope_init<<<1, 1, 0, ctx->stream>>>(mm);
+    RFB_CHECK_LAUNCH(ctx);
+    if (aligned16(keys)) k_scope_vec<<<rfb_grid_for(ctx, n, THREADS * 8, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(keys, n, mm);
+    else k_scope<KeySrc><<<rfb_grid_for(ctx, n, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(KeySrc{keys, nullptr}, n, mm);
+    RFB_CHECK_LAUNCH(ctx);
+    i64 h[2];
+    int rc = d2h_sync(ctx, h, mm, 16);
+    if (rc) return rc;
+    const i64 range = (i64)((u64)h[1] - (u64)h[0] + 1);
+    // index_distinct_i64's direct-addressing branch (core/index.c:558): range <= len or range <= MAX_RANGE (2^20)
+    if (range <= 0 || !(range <= n || range <= (1ll << 20))) {
+        rfb_set_error("distinct: key range %lld is not dense (the reference's hash branch emits its table's slot order)", (long long)range);
+        return RFB_ERR_ARG;
+    }
+    void *aux;
+    rc = rfb_ensure_aux(ctx, (size_t)range, &aux);
+    if (rc) return rc;
+    u8 *mark = (u8 *)aux;
+    RFB_CUDA(cudaMemsetAsync(mark, 0, (size_t)range, ctx->stream));
+    k_mark_keys<<<rfb_grid_for(ctx, n, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(keys, n, h[0], mark);
+    RFB_CHECK_LAUNCH(ctx);
+    rc = rfb_where_dev(ctx, mark, range, out, count);       // ascending slots of the keys that occur ...
+    if (rc) return rc;
+    if (*count > 0 && h[0] != 0) {                            // ... + min = the keys
+        k_add_const<<<rfb_grid_for(ctx, *count, THREADS * 4, 8), THREADS, 0, ctx->stream>>>(out, *count, h[0]);
+        RFB_CHECK_LAUNCH(ctx);
+    }
+    return RFB_OK;
+}
+
 // ------------------------------------------------------------------ multi-key grouping: perfect-hash key fusion
 
 namespace {

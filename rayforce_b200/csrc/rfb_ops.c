@@ -1094,6 +1094,25 @@ out:
     return res;
 }
 
+/* ray_distinct on an I64-kind vector with a dense key range (core/compose.c:867-872 -> index_distinct_i64): ascending distinct
+ * keys, ATTR_DISTINCT set on the result.  A sparse range (hash branch, slot-order result) is declined to the CPU body. */
+obj_p rfb_ray_distinct(obj_p x) {
+    if (!G.ready || !is_key_vec(x) || too_small(x->len) || x->len == 0) return NULL;
+    call_scope_t sc = enter();
+    obj_p res = NULL;
+    int64_t count = 0;
+    void *dx = dev_column(x), *dout = dev_temp((size_t)x->len * 8);
+    if (!dx || !dout) { res = G.host->err_limit(); goto out; }
+    int rc = rfb_distinct_i64_dev(G.ctx, (const int64_t *)dx, x->len, (int64_t *)dout, &count);
+    if (rc == RFB_ERR_ARG) { res = NULL; goto out; }
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = to_host_vector(x->type, count, dout);
+    if (res && res->type != RFB_T_ERR) res->attrs |= 1;   /* ATTR_DISTINCT (core/ops.h:52) */
+out:
+    leave(sc);
+    return res;
+}
+
 /* ------------------------------------------------------------------ sort */
 
 static obj_p sort_op(obj_p x, int desc) {

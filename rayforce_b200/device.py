@@ -364,6 +364,15 @@ class _Ops:
         self.sync()
         return ids
 
+    def distinct(self, keys):
+        """ray_distinct on a dense I64-kind key column -> the distinct keys, ascending (RfbError kind "arg" when not dense)"""
+        n = keys.shape[0]
+        out = self._empty(n, capi.I64)
+        cnt = C.c_int64(0)
+        check(self.lib.rfb_distinct_i64_dev(self.h, _dptr(keys), n, _dptr(out), C.byref(cnt)))
+        self.sync()
+        return out[:cnt.value]
+
     def group_sum_count(self, key_type, keys, val, max_groups, cmp_op=None, pred_type=None, pred=None, k=None):
         """fused select {s: (sum v) c: (count v) from t by k [where (cmp p k)]} -> (keys, sums, counts) tensors"""
         n = keys.shape[0]

@@ -19,7 +19,7 @@ NP_OF = {capi.B8: np.uint8, capi.U8: np.uint8, capi.I16: np.int16, capi.I32: np.
          capi.TIME: np.int32, capi.I64: np.int64, capi.SYMBOL: np.int64, capi.TIMESTAMP: np.int64, capi.F64: np.float64}
 
 UNARY = ["ray_where", "ray_sum", "ray_min", "ray_max", "ray_avg", "ray_cnt", "ray_round", "ray_floor", "ray_ceil",
-         "ray_sort_asc", "ray_sort_desc", "ray_med", "ray_dev"]
+         "ray_sort_asc", "ray_sort_desc", "ray_med", "ray_dev", "ray_distinct"]
 BINARY = ["ray_eq", "ray_ne", "ray_lt", "ray_gt", "ray_le", "ray_ge", "filter_map", "filter_collect", "ray_add", "ray_sub",
           "ray_mul", "ray_div", "ray_fdiv", "ray_mod", "ray_xbar", "index_group", "group_map", "aggr_sum", "aggr_min", "aggr_max",
           "aggr_count", "aggr_avg", "aggr_med", "aggr_stddev", "aggr_row", "aggr_collect", "ray_find", "ray_in", "where_lt_sum"]

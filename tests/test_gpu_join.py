@@ -112,3 +112,28 @@ def test_asof_join_through_the_operator_layer(oracle):
         got, gt = ops.value(ops.L.rfb_index_asof_join_obj(lo, lx, ro, rx))
         assert gt == ob.I64 and np.array_equal(got, oracle.asof_join(bcols, ob.I64, bt, pcols, pt))
     ops.drop(lo, ro, lx, rx)
+
+
+@pytest.mark.parametrize("n,card,kmin", [(1, 1, 5), (1000, 40, -20), (300_003, 5000, -2500), (50_000, 900_000, 17), (400_001, 100_000, 0)])
+def test_distinct_dense(ctx, oracle, n, card, kmin):
+    keys = (np.random.default_rng(n).integers(0, card, n) + kmin).astype(np.int64)
+    assert np.array_equal(host(ctx.distinct(dev(keys))), oracle.distinct(keys))
+    assert np.array_equal(host(ctx.distinct(dev(np.concatenate([[0], keys]))[1:])), oracle.distinct(keys))     # unaligned column
+
+
+def test_distinct_sparse_range_is_declined(ctx, oracle):
+    from rayforce_b200 import capi
+    keys = (np.random.default_rng(1).integers(0, 1 << 50, 10_000)).astype(np.int64)
+    with pytest.raises(ob.OracleError):
+        oracle.distinct(keys)
+    with pytest.raises(capi.RfbError) as e:
+        ctx.distinct(dev(keys))
+    assert e.value.kind == "arg"
+    ops = Ops.get(0)
+    x = ops.vec(ob.I64, keys)
+    with pytest.raises(Declined):
+        ops.value(ops.call("ray_distinct", x))
+    d = ops.vec(ob.I64, keys % 1000)
+    got, gt = ops.value(ops.call("ray_distinct", d))
+    assert gt == ob.I64 and np.array_equal(got, oracle.distinct(keys % 1000))
+    ops.drop(x, d)

@@ -449,3 +449,13 @@ def test_asof_join_index(oracle, reference, ncols, tt, nb, np_):
     want = oracle.asof_join(bcols, tt, bt, pcols, pt)
     assert np.array_equal(want, reference.asof_index(pcols, tt, pt, bcols, bt))
     assert (want != ob.NULL_I64).any() and (want == ob.NULL_I64).any()
+
+
+@pytest.mark.parametrize("n,card,kmin", [(1, 1, 5), (1000, 40, -20), (200_003, 5000, -2500), (50_000, 900_000, 17)])
+def test_distinct_dense(oracle, reference, n, card, kmin):
+    """ray_distinct -> index_distinct_i64, direct-addressing branch (core/index.c:551-577): ascending distinct keys"""
+    keys = (np.random.default_rng(n).integers(0, card, n) + kmin).astype(np.int64)
+    v = reference.vec(ob.I64, keys)
+    got = reference.to_numpy(reference.call1("ray_distinct", v))[0]
+    reference.drop(v)
+    assert np.array_equal(oracle.distinct(keys), got)
