@@ -1,0 +1,329 @@
+// k_aggr.cu — grouped aggregates (sm_100a): rfb_aggr_dev = aggr_sum/min/max/count/avg (reference core/aggr.c AGGR_ITER :73-161,
+// :1078-1453, :1455-2133) over group ids, plus the dispatch to the median / deviation pipelines of k_stats.cu.  Per-group
+// accumulators: CTA-private shared memory at low cardinality (32-bit words with carry for the 64-bit integer sums,
+// rfb_group.cuh; per-warp fp64 moments, rfb_moments.cuh), device-wide L2 atomics otherwise; finalised by a per-group kernel
+// (sticky-null sums, +INF/NULL-initialised min/max, f64 averages).
+#include "rfb_group.cuh"
+
+
+namespace {
+
+struct ValRow {
+    const i64 *filter;
+    __device__ __forceinline__ i64 operator()(i64 i) const { return filter ? ld_stream(filter + i) : i; }
+};
+
+
+__device__ __forceinline__ f64 key_to_f64(u64 k) {  // inverse of f64_sort_key; key 0 = null
+    if (k == 0) return null_f64();
+    return bits_f64((k & 0x8000000000000000ULL) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k);
+}
+
+enum { AK_SUM_I64, AK_SUM_I16, AK_SUM_F64, AK_MIN_I64, AK_MAX_I64, AK_MIN_I32, AK_MAX_I32, AK_MIN_I16, AK_MAX_I16, AK_MIN_F64,
+       AK_MAX_F64, AK_COUNT, AK_AVG_I64, AK_AVG_I32, AK_AVG_I16, AK_AVG_F64 };
+// 16-bit values have no native atomics: I16 sums accumulate mod 2^32 and min/max in 32-bit slots of the workspace, and the
+// finalise kernel narrows them (a sum mod 2^32 truncated to 16 bits is the reference's 16-bit wrapping sum)
+
+// acc: main accumulator array (typed per kind), aux: null flags (sum) or non-null counts (avg)
+template <int KIND, typename V> __device__ __forceinline__ void aggr_one(void *acc, void *aux, i64 g, V v) {
+    if constexpr (KIND == AK_SUM_I64) {
+        if (v == NULL_I64) ((u32 *)aux)[g] = 1u; else atomicAdd((unsigned long long *)acc + g, (unsigned long long)v);
+    } else if constexpr (KIND == AK_SUM_I16) {
+        if (v == NULL_I16) ((u32 *)aux)[g] = 1u; else atomicAdd((u32 *)acc + g, (u32)(i32)v);
+    } else if constexpr (KIND == AK_SUM_F64) {
+        if (isnan64(v)) ((u32 *)aux)[g] = 1u; else atomicAdd((f64 *)acc + g, v);
+    } else if constexpr (KIND == AK_MIN_I64) {
+        if (v != NULL_I64) atomicMin((long long *)acc + g, (long long)v);
+    } else if constexpr (KIND == AK_MAX_I64) {
+        atomicMax((long long *)acc + g, (long long)v);    // NULL is the minimum: never wins
+    } else if constexpr (KIND == AK_MIN_I32) {
+        if (v != NULL_I32) atomicMin((int *)acc + g, (int)v);
+    } else if constexpr (KIND == AK_MAX_I32) {
+        atomicMax((int *)acc + g, (int)v);
+    } else if constexpr (KIND == AK_MIN_I16) {
+        if (v != NULL_I16) atomicMin((int *)acc + g, (int)v);
+    } else if constexpr (KIND == AK_MAX_I16) {
+        atomicMax((int *)acc + g, (int)v);
+    } else if constexpr (KIND == AK_MIN_F64) {
+        if (!isnan64(v)) atomicMin((unsigned long long *)acc + g, (unsigned long long)f64_sort_key(v));
+    } else if constexpr (KIND == AK_MAX_F64) {
+        atomicMax((unsigned long long *)acc + g, (unsigned long long)f64_sort_key(v));   // NaN -> key 0: never wins
+    } else if constexpr (KIND == AK_COUNT) {
+        atomicAdd((unsigned long long *)acc + g, 1ULL);
+    } else if constexpr (KIND == AK_AVG_I64) {
+        if (v != NULL_I64) { atomicAdd((unsigned long long *)acc + g, (unsigned long long)v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
+    } else if constexpr (KIND == AK_AVG_I32) {
+        if (v != NULL_I32) { atomicAdd((unsigned long long *)acc + g, (unsigned long long)(i64)v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
+    } else if constexpr (KIND == AK_AVG_I16) {
+        if (v != NULL_I16) { atomicAdd((unsigned long long *)acc + g, (unsigned long long)(i64)v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
+    } else if constexpr (KIND == AK_AVG_F64) {
+        if (!isnan64(v)) { atomicAdd((f64 *)acc + g, v); atomicAdd((unsigned long long *)aux + g, 1ULL); }
+    }
+}
+
+// fold one CTA-private slot (shared memory) into the device-wide accumulators
+template <int KIND> __device__ __forceinline__ void aggr_merge(void *acc, void *aux, const void *sacc, const void *saux, i64 g) {
+    if constexpr (KIND == AK_SUM_I64 || KIND == AK_COUNT) {
+        const u64 v = ((const u64 *)sacc)[g];
+        if (v) atomicAdd((unsigned long long *)acc + g, (unsigned long long)v);
+        if (KIND == AK_SUM_I64 && ((const u32 *)saux)[g]) ((u32 *)aux)[g] = 1u;
+    } else if constexpr (KIND == AK_SUM_I16) {
+        const u32 v = ((const u32 *)sacc)[g];
+        if (v) atomicAdd((u32 *)acc + g, v);
+        if (((const u32 *)saux)[g]) ((u32 *)aux)[g] = 1u;
+    } else if constexpr (KIND == AK_MIN_I64) atomicMin((long long *)acc + g, ((const long long *)sacc)[g]);
+    else if constexpr (KIND == AK_MAX_I64) atomicMax((long long *)acc + g, ((const long long *)sacc)[g]);
+    else if constexpr (KIND == AK_MIN_I32 || KIND == AK_MIN_I16) atomicMin((int *)acc + g, ((const int *)sacc)[g]);
+    else if constexpr (KIND == AK_MAX_I32 || KIND == AK_MAX_I16) atomicMax((int *)acc + g, ((const int *)sacc)[g]);
+    else if constexpr (KIND == AK_MIN_F64) atomicMin((unsigned long long *)acc + g, ((const unsigned long long *)sacc)[g]);
+    else if constexpr (KIND == AK_MAX_F64) atomicMax((unsigned long long *)acc + g, ((const unsigned long long *)sacc)[g]);
+    else if constexpr (KIND == AK_AVG_I64 || KIND == AK_AVG_I32 || KIND == AK_AVG_I16) {
+        const u64 c = ((const u64 *)saux)[g];
+        if (c) { atomicAdd((unsigned long long *)acc + g, (unsigned long long)((const u64 *)sacc)[g]); atomicAdd((unsigned long long *)aux + g, (unsigned long long)c); }
+    } else if constexpr (KIND == AK_AVG_F64) {
+        const u64 c = ((const u64 *)saux)[g];
+        if (c) { atomicAdd((f64 *)acc + g, ((const f64 *)sacc)[g]); atomicAdd((unsigned long long *)aux + g, (unsigned long long)c); }
+    }
+}
+
+constexpr int PRIV_GROUPS = 3072;   // CTA-private accumulators in shared memory: 2 x 8 B x 3072 = 48 KB
+constexpr int PRIV32_GROUPS = 4608; // 32-bit-word accumulators (sums, counts, averages of integers): 12 B x 4608 = 54 KB, 4 CTAs per SM
+
+// PRIV: groups <= PRIV_GROUPS.  Every CTA folds its rows into shared-memory accumulators (initialised from the device-wide
+// ones' initial values, which are each operator's identity) and merges them once at the end: the hot atomics never leave
+// the SM, which is what low-cardinality keys (H2O id1-like, 100 groups) need — device-wide atomics serialise per address.
+template <int KIND, typename V, bool PRIV>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_aggr(const V *__restrict__ val, ValRow row, const i64 *__restrict__ gid, i64 n, i64 groups, void *acc, void *aux) {
+    constexpr int U = 4;
+    extern __shared__ u64 s_priv[];
+    void *a = acc, *x = aux;
+    if constexpr (PRIV) {
+        // private slots start at the operator's identity (NOT a copy of the device-wide slots: an early CTA may already
+        // have merged into those)
+        u64 *sa = s_priv, *sx = s_priv + groups;
+        for (i64 g = threadIdx.x; g < groups; g += THREADS) {
+            if constexpr (KIND == AK_MIN_I64) ((i64 *)sa)[g] = RFB_INF_I64;
+            else if constexpr (KIND == AK_MAX_I64) ((i64 *)sa)[g] = NULL_I64;
+            else if constexpr (KIND == AK_MIN_I32) ((i32 *)sa)[g] = (i32)0x7FFFFFFF;
+            else if constexpr (KIND == AK_MAX_I32) ((i32 *)sa)[g] = NULL_I32;
+            else if constexpr (KIND == AK_MIN_I16) ((i32 *)sa)[g] = (i32)0x7FFF;
+            else if constexpr (KIND == AK_MAX_I16) ((i32 *)sa)[g] = (i32)NULL_I16;
+            else if constexpr (KIND == AK_MIN_F64) sa[g] = f64_sort_key(bits_f64(0x7FF0000000000000ULL));
+            else sa[g] = 0;   // sums, counts, averages, MAX_F64 (key 0 = null)
+            sx[g] = 0;
+        }
+        __syncthreads();
+        a = sa;
+        x = sx;
+    }
+    const i64 stride = (i64)gridDim.x * THREADS;
+    i64 i = (i64)blockIdx.x * THREADS + threadIdx.x;
+    for (; i + (U - 1) * stride < n; i += U * stride) {
+        i64 g[U];
+        V v[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            g[j] = ld_stream(gid + i + j * stride);
+            if constexpr (KIND == AK_COUNT) v[j] = V();
+            else v[j] = row.filter ? __ldg(val + row(i + j * stride)) : ld_stream(val + i + j * stride);
+        }
+#pragma unroll
+        for (int j = 0; j < U; j++) aggr_one<KIND, V>(a, x, g[j], v[j]);
+    }
+    for (; i < n; i += stride) {
+        V v;
+        if constexpr (KIND == AK_COUNT) v = V();
+        else v = row.filter ? __ldg(val + row(i)) : ld_stream(val + i);
+        aggr_one<KIND, V>(a, x, ld_stream(gid + i), v);
+    }
+    if constexpr (PRIV) {
+        __syncthreads();
+        for (i64 g = threadIdx.x; g < groups; g += THREADS) aggr_merge<KIND>(acc, aux, a, x, g);
+    }
+}
+
+// PRIV for the kinds whose accumulators are 64-bit integer sums and counts: 32-bit shared atomics with carry (SAcc) instead
+// of 64-bit shared atomicAdd, which sm_100a runs as a compare-and-swap loop.  cnt word: SUM -> sticky-null flag only,
+// COUNT -> rows, AVG -> non-null rows.
+template <int KIND, typename V>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_aggr_priv32(const V *__restrict__ val, ValRow row, const i64 *__restrict__ gid, i64 n, int groups, void *acc, void *aux) {
+    constexpr int U = 4;
+    extern __shared__ u32 s_acc32[];
+    const SAcc a{s_acc32, s_acc32 + groups, s_acc32 + 2 * groups};
+    sacc_zero(a, groups);
+    __syncthreads();
+    auto one = [&](u32 g, V v) {
+        if constexpr (KIND == AK_COUNT) atomicAdd(&a.cnt[g], 1u);
+        else if constexpr (KIND == AK_SUM_I64) {
+            if (v == NULL_I64) atomicOr(&a.cnt[g], NULL_FLAG);
+            else {
+                const u32 lo = (u32)(u64)v;
+                u32 hi = (u32)((u64)v >> 32);
+                const u32 old = atomicAdd(&a.lo[g], lo);
+                hi += (u32)((u32)(old + lo) < lo);
+                if (hi) atomicAdd(&a.hi[g], hi);
+            }
+        } else {   // averages: i64 sum of the non-null values + their count
+            if (!Elem<V>::is_null(v)) sacc_add(a, g, (i64)v);
+        }
+    };
+    const i64 stride = (i64)gridDim.x * THREADS;
+    i64 i = (i64)blockIdx.x * THREADS + threadIdx.x;
+    for (; i + (U - 1) * stride < n; i += U * stride) {
+        i64 g[U];
+        V v[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            g[j] = ld_stream(gid + i + j * stride);
+            if constexpr (KIND == AK_COUNT) v[j] = V();
+            else v[j] = row.filter ? __ldg(val + row(i + j * stride)) : ld_stream(val + i + j * stride);
+        }
+#pragma unroll
+        for (int j = 0; j < U; j++) one((u32)g[j], v[j]);
+    }
+    for (; i < n; i += stride) {
+        V v;
+        if constexpr (KIND == AK_COUNT) v = V();
+        else v = row.filter ? __ldg(val + row(i)) : ld_stream(val + i);
+        one((u32)ld_stream(gid + i), v);
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < groups; g += THREADS) {
+        const u32 c = a.cnt[g];
+        const u64 sum = ((u64)a.hi[g] << 32) | a.lo[g];
+        if constexpr (KIND == AK_COUNT) { if (c) atomicAdd((unsigned long long *)acc + g, (unsigned long long)c); }
+        else if constexpr (KIND == AK_SUM_I64) {
+            if (sum) atomicAdd((unsigned long long *)acc + g, (unsigned long long)sum);
+            if (c & NULL_FLAG) ((u32 *)aux)[g] = 1u;
+        } else if (c) {
+            atomicAdd((unsigned long long *)acc + g, (unsigned long long)sum);
+            atomicAdd((unsigned long long *)aux + g, (unsigned long long)(c & ~NULL_FLAG));
+        }
+    }
+}
+
+template <int KIND> __global__ void k_aggr_final(void *out, const void *acc, const void *aux, i64 groups) {
+    for (i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (i64)gridDim.x * blockDim.x) {
+        if constexpr (KIND == AK_SUM_I64) { if (((const u32 *)aux)[g]) ((i64 *)out)[g] = NULL_I64; }
+        else if constexpr (KIND == AK_SUM_I16) ((i16 *)out)[g] = ((const u32 *)aux)[g] ? NULL_I16 : (i16)(unsigned short)((const u32 *)acc)[g];
+        else if constexpr (KIND == AK_MIN_I16 || KIND == AK_MAX_I16) ((i16 *)out)[g] = (i16)((const i32 *)acc)[g];
+        else if constexpr (KIND == AK_SUM_F64) { if (((const u32 *)aux)[g]) ((f64 *)out)[g] = null_f64(); }
+        else if constexpr (KIND == AK_MIN_F64 || KIND == AK_MAX_F64) ((f64 *)out)[g] = key_to_f64(((const u64 *)acc)[g]);
+        else if constexpr (KIND == AK_AVG_I64 || KIND == AK_AVG_I32 || KIND == AK_AVG_I16) {
+            const i64 c = ((const i64 *)aux)[g];
+            ((f64 *)out)[g] = c == 0 ? null_f64() : __ddiv_rn((f64)((const i64 *)acc)[g], (f64)c);
+        } else if constexpr (KIND == AK_AVG_F64) {
+            const i64 c = ((const i64 *)aux)[g];
+            ((f64 *)out)[g] = c == 0 ? null_f64() : __ddiv_rn(((const f64 *)acc)[g], (f64)c);
+        }
+    }
+}
+
+template <int KIND, typename V>
+int run_aggr(rfb_ctx_t *ctx, const void *val, const i64 *filter, const i64 *gid, i64 len, i64 groups, void *acc, void *aux, void *out) {
+    if (len > 0) {
+        const int grid = rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM);
+        // F64 sums stay on the device-wide path (one accumulator per group, like the reference's single running sum)
+        if constexpr (KIND == AK_SUM_I64 || KIND == AK_COUNT || KIND == AK_AVG_I64 || KIND == AK_AVG_I32 || KIND == AK_AVG_I16) {
+            if (groups <= PRIV32_GROUPS && len >= 65536 && len / grid < (1ll << 31)) {
+                RFB_CUDA(cudaFuncSetAttribute(k_aggr_priv32<KIND, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, PRIV32_GROUPS * 12));
+                k_aggr_priv32<KIND, V><<<grid, THREADS, (size_t)groups * 12, ctx->stream>>>((const V *)val, ValRow{filter}, gid, len, (int)groups, acc, aux);
+                RFB_CHECK_LAUNCH(ctx);
+                goto finalise;
+            }
+        }
+        if constexpr (KIND != AK_SUM_F64) {
+            if (groups <= PRIV_GROUPS && len >= 65536) {
+                k_aggr<KIND, V, true><<<grid, THREADS, (size_t)groups * 16, ctx->stream>>>((const V *)val, ValRow{filter}, gid, len, groups, acc, aux);
+                RFB_CHECK_LAUNCH(ctx);
+                goto finalise;
+            }
+        }
+        k_aggr<KIND, V, false><<<grid, THREADS, 0, ctx->stream>>>((const V *)val, ValRow{filter}, gid, len, groups, acc, aux);
+        RFB_CHECK_LAUNCH(ctx);
+    }
+finalise:
+    k_aggr_final<KIND><<<rfb_grid_for(ctx, groups, 256, 8), 256, 0, ctx->stream>>>(out, acc, aux, groups);
+    RFB_CHECK_LAUNCH(ctx);
+    return RFB_OK;
+}
+
+}  // namespace
+
+extern "C" int rfb_aggr_type(int op, int val_type) {
+    const int k = rfb_kind_of(val_type);
+    if (!k) return RFB_ERR_TYPE;
+    switch (op) {
+        case RFB_A_COUNT: return (k == K_U8 || k == K_I16) ? RFB_ERR_TYPE : RFB_I64;
+        // the non-parted drivers' switch tables: aggr_sum core/aggr.c:1107-1150, aggr_max/min :1152-1315, aggr_avg :2013-2133
+        case RFB_A_SUM: return (val_type == RFB_I16 || val_type == RFB_I64 || k == K_F64) ? val_type : RFB_ERR_TYPE;
+        case RFB_A_MIN: case RFB_A_MAX:
+            return (val_type == RFB_I16 || val_type == RFB_I64 || val_type == RFB_TIMESTAMP || val_type == RFB_DATE || val_type == RFB_TIME || val_type == RFB_F64) ? val_type : RFB_ERR_TYPE;
+        case RFB_A_AVG: return (val_type == RFB_I16 || k == K_I32 || val_type == RFB_I64 || k == K_F64) ? RFB_F64 : RFB_ERR_TYPE;
+        case RFB_A_MED: return RFB_F64;   // aggr_collect takes every column type; types without a median give nulls (core/aggr.c:2182-2184)
+        case RFB_A_DEV: return (val_type == RFB_I16 || k == K_I32 || val_type == RFB_I64 || val_type == RFB_TIMESTAMP || k == K_F64) ? RFB_F64 : RFB_ERR_TYPE;   // core/aggr.c:2873-2880
+        default: return RFB_ERR_TYPE;
+    }
+}
+
+extern "C" int rfb_aggr_dev(rfb_ctx_t *ctx, int op, int val_type, const void *val, const int64_t *filter,
+                            const int64_t *group_ids, int64_t len, int64_t groups, void *out) {
+    RFB_ARG(ctx && len >= 0 && groups >= 0 && ((val && group_ids) || len == 0) && (out || groups == 0), "rfb_aggr_dev");
+    const int ot = rfb_aggr_type(op, val_type);
+    if (ot < 0) { rfb_set_error("aggr %d: unsupported value type %d", op, val_type); return RFB_ERR_TYPE; }
+    if (groups == 0) return RFB_OK;
+    if (op == RFB_A_MED) return rfb_aggr_med_launch(ctx, val_type, val, filter, group_ids, len, groups, (f64 *)out);
+    if (op == RFB_A_DEV) return rfb_aggr_stddev_launch(ctx, val_type, val, filter, group_ids, len, groups, (f64 *)out);
+    const int k = rfb_kind_of(val_type);
+    void *w;
+    int rc = rfb_ensure_work(ctx, 2 * align256((size_t)groups * 8), &w);
+    if (rc) return rc;
+    void *acc = w, *aux = (char *)w + align256((size_t)groups * 8);
+    switch (op) {
+        case RFB_A_COUNT:
+            RFB_CUDA(cudaMemsetAsync(out, 0, (size_t)groups * 8, ctx->stream));
+            return run_aggr<AK_COUNT, i64>(ctx, nullptr, nullptr, group_ids, len, groups, out, aux, out);
+        case RFB_A_SUM:
+            RFB_CUDA(cudaMemsetAsync(out, 0, (size_t)groups * rfb_type_size(val_type), ctx->stream));
+            RFB_CUDA(cudaMemsetAsync(aux, 0, (size_t)groups * 4, ctx->stream));
+            if (k == K_I64) return run_aggr<AK_SUM_I64, i64>(ctx, val, filter, group_ids, len, groups, out, aux, out);
+            if (k == K_I16) {
+                RFB_CUDA(cudaMemsetAsync(acc, 0, (size_t)groups * 4, ctx->stream));
+                return run_aggr<AK_SUM_I16, i16>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
+            }
+            // f64 sums: per-group moments with shared-memory privatisation at low cardinality (rfb_moments.cuh); the count it
+            // also produces lands in the workspace and is not used
+            RFB_CUDA(cudaMemsetAsync(acc, 0, (size_t)groups * 8, ctx->stream));
+            rc = moments::launch<f64, false>(ctx, val, filter, group_ids, len, groups, (f64 *)out, nullptr, (unsigned long long *)acc, (u32 *)aux);
+            if (rc) return rc;
+            k_aggr_final<AK_SUM_F64><<<rfb_grid_for(ctx, groups, 256, 8), 256, 0, ctx->stream>>>(out, out, aux, groups);
+            RFB_CHECK_LAUNCH(ctx);
+            return RFB_OK;
+        case RFB_A_MIN:
+            if (k == K_I64) { rc = fill<i64>(ctx, (i64 *)out, groups, RFB_INF_I64); if (rc) return rc; return run_aggr<AK_MIN_I64, i64>(ctx, val, filter, group_ids, len, groups, out, aux, out); }
+            if (k == K_I32) { rc = fill<i32>(ctx, (i32 *)out, groups, (i32)0x7FFFFFFF); if (rc) return rc; return run_aggr<AK_MIN_I32, i32>(ctx, val, filter, group_ids, len, groups, out, aux, out); }
+            if (k == K_I16) { rc = fill<i32>(ctx, (i32 *)acc, groups, (i32)0x7FFF); if (rc) return rc; return run_aggr<AK_MIN_I16, i16>(ctx, val, filter, group_ids, len, groups, acc, aux, out); }
+            rc = fill<u64>(ctx, (u64 *)acc, groups, f64_sort_key(bits_f64(0x7FF0000000000000ULL)));
+            if (rc) return rc;
+            return run_aggr<AK_MIN_F64, f64>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
+        case RFB_A_MAX:
+            if (k == K_I64) { rc = fill<i64>(ctx, (i64 *)out, groups, NULL_I64); if (rc) return rc; return run_aggr<AK_MAX_I64, i64>(ctx, val, filter, group_ids, len, groups, out, aux, out); }
+            if (k == K_I32) { rc = fill<i32>(ctx, (i32 *)out, groups, NULL_I32); if (rc) return rc; return run_aggr<AK_MAX_I32, i32>(ctx, val, filter, group_ids, len, groups, out, aux, out); }
+            if (k == K_I16) { rc = fill<i32>(ctx, (i32 *)acc, groups, (i32)NULL_I16); if (rc) return rc; return run_aggr<AK_MAX_I16, i16>(ctx, val, filter, group_ids, len, groups, acc, aux, out); }
+            RFB_CUDA(cudaMemsetAsync(acc, 0, (size_t)groups * 8, ctx->stream));
+            return run_aggr<AK_MAX_F64, f64>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
+        default:  // AVG
+            RFB_CUDA(cudaMemsetAsync(acc, 0, (size_t)groups * 8, ctx->stream));
+            RFB_CUDA(cudaMemsetAsync(aux, 0, (size_t)groups * 8, ctx->stream));
+            if (k == K_I64) return run_aggr<AK_AVG_I64, i64>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
+            if (k == K_I32) return run_aggr<AK_AVG_I32, i32>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
+            if (k == K_I16) return run_aggr<AK_AVG_I16, i16>(ctx, val, filter, group_ids, len, groups, acc, aux, out);
+            rc = moments::launch<f64, false>(ctx, val, filter, group_ids, len, groups, (f64 *)acc, nullptr, (unsigned long long *)aux, nullptr);
+            if (rc) return rc;
+            k_aggr_final<AK_AVG_F64><<<rfb_grid_for(ctx, groups, 256, 8), 256, 0, ctx->stream>>>(out, acc, aux, groups);
+            RFB_CHECK_LAUNCH(ctx);
+            return RFB_OK;
+    }
+}

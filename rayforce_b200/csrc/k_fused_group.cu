@@ -1,0 +1,875 @@
+// k_fused_group.cu — rfb_group_sum_count_dev (sm_100a): `select {s: (sum v) c: (count v) from t by k [where ...]}` fused, never
+// materialising group ids.
+#include "rfb_group.cuh"
+
+// ------------------------------------------------------------------ fused dense group-by: sum + count [+ where]
+//
+// Three accumulate strategies, picked from the key range found by the scope pass:
+//   range <= KP (8192)        CTA-private accumulators in shared memory, merged once per CTA
+//   range <= MAX_PARTS * KP   two passes over a key-range PARTITIONED copy of the selected rows: the scatter pass splits
+//                             the rows into P = range/KP partitions of (16-bit slot, value) pairs, the accumulate pass
+//                             gives every CTA one partition at a time, whose KP accumulators fit shared memory.  36 B/row
+//                             of streaming traffic instead of two L2 atomics per row (L2 atomics cap at ~175 G/s on B200,
+//                             which is what bounded the 1e5-key config at 12.3 ms per 1e9 rows)
+//   otherwise                 device-wide accumulators updated with L2 atomics
+// Shared-memory accumulators are 32-bit words (sum low / sum high / count): sm_100a has native 32-bit shared atomics
+// (ATOMS.ADD) but implements 64-bit shared adds as a compare-and-swap loop (ATOMS.CAST.SPIN.64).  The 64-bit wrapping
+// sum is kept exact by carrying: the returning add on the low word tells the one row that wrapped it to add 1 to the high word.
+
+namespace {
+
+struct Accums {
+    u64 *first_row;   // [range]
+    u64 *sum;         // [range] wrapping i64 sums of the non-null values
+    u64 *cnt;         // [range] rows (nulls included: aggr_count counts rows, core/aggr.c:1336-1342)
+    u32 *has_null;    // [range] sticky-null marker for the sum (core/aggr.c:1088)
+};
+
+constexpr int KP_LOG = 13, KP = 1 << KP_LOG;   // keys per partition = shared-memory accumulator slots per CTA (96 KB)
+constexpr int MAX_PARTS = 256;
+constexpr int PT = 512;                        // threads per CTA of the accumulate kernels (2 CTAs per SM)
+constexpr int PTILE = PT * 8;                  // rows per tile / work unit: 4 pairs per thread
+constexpr int ST = 256;                        // threads per CTA of the scope kernel (4 CTAs per SM)
+constexpr int STILE = ST * 8;
+#ifndef RFB_SC_T
+#define RFB_SC_T 256      /* measured on B200 (1e9 rows, 1e5 i32 keys): 256 x 8 x 4 CTAs 7.17 ms, 512 x 4 x 3 CTAs 7.55 ms */
+#define RFB_SC_R 8
+#define RFB_SC_CTAS 4
+#endif
+constexpr int SC_T = RFB_SC_T, SC_R = RFB_SC_R, SC_CTAS = RFB_SC_CTAS, SC_TILE = SC_T * SC_R;   // scatter kernel geometry
+
+// two consecutive elements with one vector load (p must be aligned to 2 * sizeof(T))
+template <typename T> __device__ __forceinline__ void ld_pair(const T *p, i64 pair, T &a, T &b) {
+    if constexpr (sizeof(T) == 8) {
+        const vec16 v = ld_stream16(p + 2 * pair);
+        if constexpr (Elem<T>::kind == K_F64) { a = bits_f64(v.lo); b = bits_f64(v.hi); }
+        else { a = (T)v.lo; b = (T)v.hi; }
+    } else {
+        static_assert(sizeof(T) == 4, "pair loads: 4- or 8-byte elements");
+        const u64 w = __ldcs((const unsigned long long *)p + pair);
+        a = (T)(u32)w;
+        b = (T)(u32)(w >> 32);
+    }
+}
+template <typename T> static inline bool pair_aligned(const T *p) { return (((uintptr_t)p) & (2 * sizeof(T) - 1)) == 0; }
+
+template <typename K, typename P, bool HAS_PRED>
+struct FusedSrc {
+    typedef K key_t;
+    const K *keys;
+    const P *pred;
+    PredRange pr;
+    __device__ __forceinline__ bool selected(i64 i) const {
+        if constexpr (HAS_PRED) return pred_test(pred_key<P>(ld_stream(pred + i)), pr);
+        else return true;
+    }
+    __device__ __forceinline__ i64 key(i64 i) const { return (i64)ld_stream(keys + i); }
+    __device__ __forceinline__ void key_pair(i64 pair, i64 &a, i64 &b) const {
+        K x, y;
+        ld_pair<K>(keys, pair, x, y);
+        a = (i64)x;
+        b = (i64)y;
+    }
+    __device__ __forceinline__ void selected_pair(i64 pair, bool &a, bool &b) const {
+        if constexpr (HAS_PRED) {
+            P x, y;
+            ld_pair<P>(pred, pair, x, y);
+            a = pred_test(pred_key<P>(x), pr);
+            b = pred_test(pred_key<P>(y), pr);
+        } else { a = b = true; }
+    }
+    bool vec_ok(const i64 *val) const { return pair_aligned(keys) && pair_aligned(val) && (!HAS_PRED || pair_aligned(pred)); }
+};
+
+// rows [base, base + R * NT) of (key, value, selected): row of (thread, j, h) = base + 2 * (j * NT + thread) + h, so that
+// every load instruction of a warp covers one contiguous, fully used run of bytes
+template <int NT, bool WITH_VAL, int R, typename FS>
+__device__ __forceinline__ void load_tile(const FS &fs, const i64 *__restrict__ val, i64 base, i64 n, bool vec, i64 (&k)[R], i64 (&v)[R], bool (&sel)[R]) {
+    static_assert(R % 2 == 0, "rows per thread come in pairs");
+    if (vec && base + R * NT <= n) {
+        const i64 pbase = base >> 1;
+#pragma unroll
+        for (int j = 0; j < R / 2; j++) {
+            const i64 pair = pbase + j * NT + threadIdx.x;
+            fs.key_pair(pair, k[2 * j], k[2 * j + 1]);
+            if constexpr (WITH_VAL) ld_pair<i64>(val, pair, v[2 * j], v[2 * j + 1]);
+            fs.selected_pair(pair, sel[2 * j], sel[2 * j + 1]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const i64 r = base + 2 * ((j >> 1) * NT + threadIdx.x) + (j & 1);
+            sel[j] = r < n && fs.selected(r);
+            k[j] = r < n ? fs.key(r) : 0;
+            if constexpr (WITH_VAL) v[j] = r < n ? ld_stream(val + r) : 0;
+        }
+    }
+}
+
+// merge into the device-wide accumulators and clear; slot0 = device-wide slot of local slot 0 (a local slot that
+// received rows always maps inside [0, range))
+__device__ __forceinline__ void sacc_flush(const SAcc &a, int slots, i64 slot0, const Accums &ga) {
+    for (int s = threadIdx.x; s < slots; s += blockDim.x) {
+        const u32 c = a.cnt[s];
+        if (!c) continue;
+        const i64 g = slot0 + s;
+        const u64 sum = ((u64)a.hi[s] << 32) | a.lo[s];
+        if (sum) atomicAdd((unsigned long long *)ga.sum + g, (unsigned long long)sum);
+        atomicAdd((unsigned long long *)ga.cnt + g, (unsigned long long)(c & ~NULL_FLAG));
+        if (c & NULL_FLAG) ga.has_null[g] = 1u;
+        a.lo[s] = 0; a.hi[s] = 0; a.cnt[s] = 0;
+    }
+}
+
+// ---- scope: min/max of the selected keys
+constexpr int MM_WORDS = 8;   // mm[0..7] = {min, max, limit, nonempty, claimed, -, -, -}
+__global__ void k_fused_scope_init(i64 *mm) {
+    for (int i = threadIdx.x; i < MM_WORDS; i += blockDim.x) mm[i] = i == 0 ? RFB_INF_I64 : (i == 1 ? NULL_I64 : 0);
+}
+
+template <typename FS>
+__global__ void __launch_bounds__(ST, 4) k_fused_scope(FS fs, i64 n, bool vec, i64 *mm) {
+    __shared__ i64 red[32];
+    i64 lo = RFB_INF_I64, hi = NULL_I64;
+    const i64 tiles = (n + STILE - 1) / STILE;
+    for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        i64 k[8], v[8];
+        bool sel[8];
+        load_tile<ST, false, 8>(fs, nullptr, tile * STILE, n, vec, k, v, sel);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (sel[j]) { lo = k[j] < lo ? k[j] : lo; hi = k[j] > hi ? k[j] : hi; }
+    }
+    struct Mn { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b < a ? b : a; } };
+    struct Mx { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b > a ? b : a; } };
+    lo = block_reduce<i64>(lo, Mn(), RFB_INF_I64, red);
+    hi = block_reduce<i64>(hi, Mx(), NULL_I64, red);
+    if (threadIdx.x == 0) {
+        atomicMin((long long *)&mm[0], (long long)lo);
+        atomicMax((long long *)&mm[1], (long long)hi);
+    }
+}
+
+// first-row claims over a row prefix [r0, r1) only: in the accumulate pass a claim would cost one L2 read per row although
+// it can only change anything while a key has not been seen yet; the host extends the prefix until every non-empty slot
+// has been claimed (one short pass for any column whose keys all occur early, e.g. uniform keys).
+template <typename FS>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_fused_claim(FS fs, i64 r0, i64 r1, i64 kmin, u64 *first_row) {
+    for (i64 i = r0 + (i64)blockIdx.x * THREADS + threadIdx.x; i < r1; i += (i64)gridDim.x * THREADS)
+        if (fs.selected(i)) claim_first(first_row, (i64)((u64)fs.key(i) - (u64)kmin), i);
+}
+
+// mm[3] = slots with rows, mm[4] = slots whose first row is known
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_slot_census(const u64 *first_row, const u64 *cnt, i64 range, i64 *mm) {
+    __shared__ i64 red[32];
+    i64 nonempty = 0, claimed = 0;
+    for (i64 s = (i64)blockIdx.x * THREADS + threadIdx.x; s < range; s += (i64)gridDim.x * THREADS) {
+        nonempty += cnt[s] != 0;
+        claimed += first_row[s] != NO_ROW;
+    }
+    nonempty = block_reduce<i64>(nonempty, OpAddWrap(), 0, red);
+    claimed = block_reduce<i64>(claimed, OpAddWrap(), 0, red);
+    if (threadIdx.x == 0) { atomicAdd((unsigned long long *)&mm[3], (unsigned long long)nonempty); atomicAdd((unsigned long long *)&mm[4], (unsigned long long)claimed); }
+}
+
+// ---- accumulate, strategy 3: device-wide accumulators, two L2 atomics per row
+template <typename FS>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_fused_accum_l2(FS fs, const i64 *__restrict__ val, i64 n, i64 kmin, Accums a) {
+    constexpr int U = 4;
+    const i64 stride = (i64)gridDim.x * THREADS;
+    auto one = [&](i64 k, i64 v, bool sel) {
+        if (!sel) return;
+        const i64 s = (i64)((u64)k - (u64)kmin);
+        if (v == NULL_I64) a.has_null[s] = 1u; else atomicAdd((unsigned long long *)a.sum + s, (unsigned long long)v);
+        atomicAdd((unsigned long long *)a.cnt + s, 1ULL);
+    };
+    i64 i = (i64)blockIdx.x * THREADS + threadIdx.x;
+    for (; i + (U - 1) * stride < n; i += U * stride) {
+        i64 k[U], v[U];
+        bool sel[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) { k[j] = fs.key(i + j * stride); v[j] = ld_stream(val + i + j * stride); sel[j] = fs.selected(i + j * stride); }
+#pragma unroll
+        for (int j = 0; j < U; j++) one(k[j], v[j], sel[j]);
+    }
+    for (; i < n; i += stride) one(fs.key(i), ld_stream(val + i), fs.selected(i));
+}
+
+// ---- accumulate, strategy 1: range <= KP, CTA-private shared-memory accumulators (3 x 4 B x range, dynamic)
+template <typename FS>
+__global__ void __launch_bounds__(PT, 2)
+k_fused_accum_smem(FS fs, const i64 *__restrict__ val, i64 n, bool vec, i64 kmin, int range, Accums ga) {
+    extern __shared__ u32 s_acc[];
+    const SAcc a{s_acc, s_acc + range, s_acc + 2 * range};
+    sacc_zero(a, range);
+    __syncthreads();
+    const i64 tiles = (n + PTILE - 1) / PTILE;
+    for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        i64 k[8], v[8];
+        bool sel[8];
+        load_tile<PT, true, 8>(fs, val, tile * PTILE, n, vec, k, v, sel);
+#pragma unroll
+        for (int j = 0; j < 8; j++) sacc_add_warp(a, sel[j], (u32)((u64)k[j] - (u64)kmin), v[j]);
+    }
+    __syncthreads();
+    sacc_flush(a, range, 0, ga);
+}
+
+// strategy 1 without a scope pass: slot = key mod KP.  Any KP consecutive integers have distinct residues, so when the keys
+// turn out to span fewer than KP values (the kernel finds min/max on the way, a row sample made it likely) the residue IS a
+// perfect hash, and k_mod_remap afterwards moves slot (key mod KP) to slot (key - min).  Saves the 4-8 B/row scope pass.
+template <typename FS>
+__global__ void __launch_bounds__(PT, 2)
+k_fused_accum_mod(FS fs, const i64 *__restrict__ val, i64 n, bool vec, Accums gmod, i64 *mm) {
+    extern __shared__ u32 s_acc[];
+    __shared__ i64 red[32];
+    const SAcc a{s_acc, s_acc + KP, s_acc + 2 * KP};
+    sacc_zero(a, KP);
+    __syncthreads();
+    typedef typename FS::key_t KT;
+    KT lo = sizeof(KT) == 4 ? (KT)0x7FFFFFFF : (KT)RFB_INF_I64, hi = sizeof(KT) == 4 ? (KT)NULL_I32 : (KT)NULL_I64;
+    const i64 tiles = (n + PTILE - 1) / PTILE;
+    for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        i64 k[8], v[8];
+        bool sel[8];
+        load_tile<PT, true, 8>(fs, val, tile * PTILE, n, vec, k, v, sel);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (sel[j]) {
+                lo = (KT)k[j] < lo ? (KT)k[j] : lo;
+                hi = (KT)k[j] > hi ? (KT)k[j] : hi;
+            }
+            sacc_add_warp(a, sel[j], (u32)((u64)k[j] & (KP - 1)), v[j]);
+        }
+    }
+    __syncthreads();
+    sacc_flush(a, KP, 0, gmod);
+    struct Mn { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b < a ? b : a; } };
+    struct Mx { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b > a ? b : a; } };
+    const i64 lo64 = block_reduce<i64>((i64)lo, Mn(), RFB_INF_I64, red);
+    const i64 hi64 = block_reduce<i64>((i64)hi, Mx(), NULL_I64, red);
+    if (threadIdx.x == 0) {
+        atomicMin((long long *)&mm[0], (long long)lo64);
+        atomicMax((long long *)&mm[1], (long long)hi64);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS) k_mod_remap(Accums gmod, i64 kmin, i64 range, Accums a) {
+    for (i64 s = (i64)blockIdx.x * THREADS + threadIdx.x; s < range; s += (i64)gridDim.x * THREADS) {
+        const u64 m = ((u64)kmin + (u64)s) & (KP - 1);
+        a.sum[s] = gmod.sum[m];
+        a.cnt[s] = gmod.cnt[m];
+        a.has_null[s] = gmod.has_null[m];
+    }
+}
+
+// ---- accumulate, strategy 2: partition, then accumulate per partition
+//
+// A row's partition is its ABSOLUTE key bucket (key >> KP_LOG) mod 256 and its slot the low KP_LOG key bits, so the scatter
+// pass needs no key bounds: it computes min/max itself, and the partitioning is valid iff the keys turn out to span at most
+// 256 buckets (checked afterwards; a row sample decides beforehand whether it is worth trying).  Partition sizes are not
+// known in advance either: partitioned rows live in blocks of PB rows handed out on demand.  cursor[b] counts the rows of
+// bucket b; the tile whose run contains the first row of a block allocates it (one atomic on a block counter) and publishes
+// it in the block table bt[b][i]; tiles that write into a block they did not allocate wait for that word.  The allocator
+// has already passed its cursor atomic and publishes before it waits for anything itself, so the wait cannot deadlock.
+constexpr int PB_LOG = 16, PB = 1 << PB_LOG;   // rows per block; a multiple of PTILE, so an accumulate unit never straddles blocks
+
+struct PartStore {
+    u32 *cursor;       // [MAX_PARTS] rows per bucket
+    u32 *next_block;   // blocks handed out so far
+    u32 *bt;           // [MAX_PARTS][bt_stride] physical block + 1 (0 = not yet allocated)
+    u32 bt_stride;
+    u64 *val;          // [blocks * PB]
+    u16 *slot;         // [blocks * PB]
+};
+
+__device__ __forceinline__ u32 ld_relaxed_u32(const u32 *p) {
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(u32 *p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+struct ScatterSmem {
+    u64 val[SC_TILE];
+    u32 pk[SC_TILE];               // bucket << KP_LOG | slot
+    uint4 desc[MAX_PARTS];       // per bucket: {x: physical - local offset before the block boundary, y: first local index past it, z: offset after it, w: local base}
+    u32 cnt[MAX_PARTS];
+    u32 wtot[MAX_PARTS / 32];
+    u32 total;
+    i64 red[32];
+};
+
+// scatter pass: every tile orders its selected rows by bucket in shared memory (a row's rank inside its bucket is what the
+// returning shared atomic on the bucket's counter hands back), reserves its run in every bucket with one global atomic per
+// bucket, and writes the runs out contiguously.  Row order inside a bucket is not preserved (integer sums and counts do
+// not depend on it; first rows are claimed from the source columns).
+template <typename FS>
+__global__ void __launch_bounds__(SC_T, SC_CTAS)
+k_part_scatter(FS fs, const i64 *__restrict__ val, i64 n, bool vec, PartStore ps, i64 *mm) {
+    static_assert(SC_T >= MAX_PARTS, "one thread per bucket counter");
+    __shared__ ScatterSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const i64 tiles = (n + SC_TILE - 1) / SC_TILE;
+    typedef typename FS::key_t KT;   // running min/max in the key column's own width (register pressure)
+    KT lo = sizeof(KT) == 4 ? (KT)0x7FFFFFFF : (KT)RFB_INF_I64, hi = sizeof(KT) == 4 ? (KT)NULL_I32 : (KT)NULL_I64;
+    if (tid < MAX_PARTS) sm.cnt[tid] = 0;
+    __syncthreads();
+    for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        i64 k[SC_R], v[SC_R];
+        bool sel[SC_R];
+        load_tile<SC_T, true, SC_R>(fs, val, tile * SC_TILE, n, vec, k, v, sel);
+        u32 pk[SC_R], pos[SC_R];
+#pragma unroll
+        for (int j = 0; j < SC_R; j++) {
+            if (sel[j]) { lo = (KT)k[j] < lo ? (KT)k[j] : lo; hi = (KT)k[j] > hi ? (KT)k[j] : hi; }
+            pk[j] = sel[j] ? (u32)((u64)k[j] & ((1u << (KP_LOG + 8)) - 1u)) : 0xFFFFFFFFu;
+            const u32 part = sel[j] ? pk[j] >> KP_LOG : 0xFFFFFFFFu;
+            const u32 p0 = __shfl_sync(0xffffffffu, part, 0);
+            if (__all_sync(0xffffffffu, part == p0)) {      // the whole warp step goes to one bucket: one atomic
+                u32 b = 0;
+                if (lane == 0 && sel[j]) b = atomicAdd(&sm.cnt[part], 32u);
+                pos[j] = __shfl_sync(0xffffffffu, b, 0) + lane;
+            } else if (sel[j]) pos[j] = atomicAdd(&sm.cnt[part], 1u);
+        }
+        __syncthreads();
+        u32 c = 0, incl = 0, start = 0, phys0 = 0, phys1 = 0;
+        if (tid < MAX_PARTS) {
+            c = sm.cnt[tid];
+            incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (lane == 31) sm.wtot[tid >> 5] = incl;
+            // reserve [start, start + c) of bucket `tid`, allocate the block(s) that begin inside the run, look up the two
+            // blocks the run can touch
+            if (c) {
+                start = atomicAdd(&ps.cursor[tid], c);
+                const u32 b0 = start >> PB_LOG, b1 = (start + c - 1) >> PB_LOG;
+                u32 *row = ps.bt + (size_t)tid * ps.bt_stride;
+                if ((start & (PB - 1)) == 0) { phys0 = atomicAdd(ps.next_block, 1u) + 1; st_relaxed_u32(row + b0, phys0); }
+                if (b1 != b0) { phys1 = atomicAdd(ps.next_block, 1u) + 1; st_relaxed_u32(row + b1, phys1); }
+                while (!phys0) phys0 = ld_relaxed_u32(row + b0);
+                if (b1 == b0) phys1 = phys0;
+            }
+        }
+        __syncthreads();
+        if (tid < MAX_PARTS) {
+            u32 before = 0;
+            for (int w = 0; w < (tid >> 5); w++) before += sm.wtot[w];
+            const u32 lbase = before + incl - c;
+            const u32 in_block = start & (PB - 1), room = PB - in_block;           // rows left in the first block
+            uint4 d;
+            d.x = (phys0 - 1) * (u32)PB + in_block - lbase;
+            d.y = lbase + room;
+            d.z = (phys1 - 1) * (u32)PB - (lbase + room);
+            d.w = lbase;
+            sm.desc[tid] = d;
+            sm.cnt[tid] = 0;                                   // for the next tile (this tile's counts live in registers now)
+            if (tid == MAX_PARTS - 1) sm.total = before + incl;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < SC_R; j++) {
+            if (!sel[j]) continue;
+            const u32 q = sm.desc[pk[j] >> KP_LOG].w + pos[j];
+            sm.val[q] = (u64)v[j];
+            sm.pk[q] = pk[j];
+        }
+        __syncthreads();
+        const u32 total = sm.total;
+#pragma unroll
+        for (int step = 0; step < SC_R / 2; step++) {      // 2 independent elements per step: the shared-memory lookups overlap
+            u32 w[2];
+            u64 vv[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const u32 q = (step * 2 + j) * SC_T + tid;
+                if (q < total) { w[j] = sm.pk[q]; vv[j] = sm.val[q]; }
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const u32 q = (step * 2 + j) * SC_T + tid;
+                if (q < total) {
+                    const uint4 dd = sm.desc[w[j] >> KP_LOG];
+                    const u32 g = q + (q < dd.y ? dd.x : dd.z);
+                    ps.val[g] = vv[j];
+                    ps.slot[g] = (u16)(w[j] & (KP - 1));
+                }
+            }
+        }
+        __syncthreads();
+    }
+    struct Mn { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b < a ? b : a; } };
+    struct Mx { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b > a ? b : a; } };
+    // (nothing selected: lo > hi in either width, which is all the host tests)
+    const i64 lo64 = block_reduce<i64>((i64)lo, Mn(), RFB_INF_I64, sm.red);
+    const i64 hi64 = block_reduce<i64>((i64)hi, Mx(), NULL_I64, sm.red);
+    if (tid == 0) {
+        atomicMin((long long *)&mm[0], (long long)lo64);
+        atomicMax((long long *)&mm[1], (long long)hi64);
+    }
+}
+
+// accumulate pass: partition p = bucket ((kbase >> KP_LOG) + p) mod 256.  CTA b takes the flattened work units
+// [b*U/G, (b+1)*U/G) (unit = PTILE consecutive rows of one partition), keeps the current partition's KP accumulators in
+// shared memory and merges them into the device-wide arrays when the partition changes
+__global__ void __launch_bounds__(PT, 2)
+k_part_accum(PartStore ps, int P, i64 kbase, i64 kmin, Accums ga) {
+    extern __shared__ u32 s_acc[];
+    __shared__ u32 s_cnt[MAX_PARTS], s_ubase[MAX_PARTS + 1], s_wtot[MAX_PARTS / 32];
+    const SAcc a{s_acc, s_acc + KP, s_acc + 2 * KP};
+    sacc_zero(a, KP);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const u32 bucket0 = (u32)(((u64)kbase >> KP_LOG) & 255u);
+    u32 c = 0, units = 0, incl = 0;
+    if (tid < MAX_PARTS) {
+        c = tid < P ? ps.cursor[(bucket0 + tid) & 255u] : 0;
+        s_cnt[tid] = c;
+        units = (c + PTILE - 1) / PTILE;
+        incl = units;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_wtot[tid >> 5] = incl;
+    }
+    __syncthreads();
+    if (tid < MAX_PARTS) {
+        u32 before = 0;
+        for (int w = 0; w < (tid >> 5); w++) before += s_wtot[w];
+        s_ubase[tid + 1] = before + incl;
+        if (tid == 0) s_ubase[0] = 0;
+    }
+    __syncthreads();
+    const u32 U = s_ubase[P];
+    const u32 u0 = (u32)((u64)blockIdx.x * U / gridDim.x), u1 = (u32)((u64)(blockIdx.x + 1) * U / gridDim.x);
+    int p = 0;
+    while (p + 1 < P && s_ubase[p + 1] <= u0) p++;
+    bool dirty = false;
+    u32 have_blk = 0xFFFFFFFFu, phys = 0;   // block-table entry of the (partition, block) the previous unit was in
+    for (u32 u = u0; u < u1; u++) {
+        if (s_ubase[p + 1] <= u) {
+            __syncthreads();
+            if (dirty) sacc_flush(a, KP, (i64)((u64)kbase + (u64)p * KP - (u64)kmin), ga);
+            __syncthreads();
+            dirty = false;
+            while (s_ubase[p + 1] <= u) p++;
+            have_blk = 0xFFFFFFFFu;
+        }
+        const u32 r0 = (u - s_ubase[p]) * PTILE, cnt = s_cnt[p];
+        const u32 rows = cnt - r0 < (u32)PTILE ? cnt - r0 : (u32)PTILE;
+        const u32 bucket = (bucket0 + p) & 255u;
+        if ((r0 >> PB_LOG) != have_blk) { have_blk = r0 >> PB_LOG; phys = ps.bt[(size_t)bucket * ps.bt_stride + have_blk] - 1; }
+        const u64 base = (u64)phys * PB + (r0 & (PB - 1));
+        dirty = true;
+        if (rows == PTILE) {
+            vec16 vv[4];
+            u32 ss[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const u32 q = j * PT + threadIdx.x;
+                vv[j] = ld_stream16(ps.val + base + 2 * q);
+                ss[j] = __ldcs((const u32 *)(ps.slot + base) + q);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                sacc_add(a, ss[j] & 0xFFFFu, (i64)vv[j].lo);
+                sacc_add(a, ss[j] >> 16, (i64)vv[j].hi);
+            }
+        } else {
+            for (u32 r = threadIdx.x; r < rows; r += PT) sacc_add(a, ps.slot[base + r], (i64)ps.val[base + r]);
+        }
+    }
+    __syncthreads();
+    if (dirty) sacc_flush(a, KP, (i64)((u64)kbase + (u64)p * KP - (u64)kmin), ga);
+}
+
+// ---- the same accumulate pass with the partition data staged by the TMA unit (cp.async.bulk + mbarrier): one CTA per SM,
+// 1024 threads, a 3-stage ring of 40 KB units (4096 values + 4096 slots) next to the 96 KB of accumulators.  Thread 0 issues
+// the bulk copies two units ahead; the consumers wait on the stage's mbarrier phase and read the unit from shared memory.
+// A CTA barrier per unit separates "everyone finished stage s" from "stage s is re-armed".
+constexpr int AT = 1024, ASTAGES = 3;
+struct __align__(16) AccumStage { u64 val[PTILE]; u16 slot[PTILE]; };
+
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(AT, 1)
+k_part_accum_tma(PartStore ps, int P, i64 kbase, i64 kmin, Accums ga) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    AccumStage *stage = (AccumStage *)s_dyn;                                   // ASTAGES x 40 KB
+    u32 *s_acc = (u32 *)(s_dyn + ASTAGES * sizeof(AccumStage));                // lo[KP] | hi[KP] | cnt[KP]
+    __shared__ u64 full[ASTAGES];
+    __shared__ u32 s_cnt[MAX_PARTS], s_ubase[MAX_PARTS + 1], s_wtot[MAX_PARTS / 32];
+    const SAcc a{s_acc, s_acc + KP, s_acc + 2 * KP};
+    sacc_zero(a, KP);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const u32 bucket0 = (u32)(((u64)kbase >> KP_LOG) & 255u);
+    if (tid == 0) {
+        for (int s = 0; s < ASTAGES; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    u32 c = 0, units = 0, incl = 0;
+    if (tid < MAX_PARTS) {
+        c = tid < P ? ps.cursor[(bucket0 + tid) & 255u] : 0;
+        s_cnt[tid] = c;
+        units = (c + PTILE - 1) / PTILE;
+        incl = units;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_wtot[tid >> 5] = incl;
+    }
+    __syncthreads();
+    if (tid < MAX_PARTS) {
+        u32 before = 0;
+        for (int w = 0; w < (tid >> 5); w++) before += s_wtot[w];
+        s_ubase[tid + 1] = before + incl;
+        if (tid == 0) s_ubase[0] = 0;
+    }
+    __syncthreads();
+    const u32 U = s_ubase[P];
+    const u32 u0 = (u32)((u64)blockIdx.x * U / gridDim.x), u1 = (u32)((u64)(blockIdx.x + 1) * U / gridDim.x);
+    // producer state (thread 0 only): partition cursor + cached block-table entry
+    int pp = 0;
+    u32 p_blk = 0xFFFFFFFFu, p_phys = 0;
+    auto issue = [&](u32 u) {
+        while (s_ubase[pp + 1] <= u) { pp++; p_blk = 0xFFFFFFFFu; }
+        const u32 r0 = (u - s_ubase[pp]) * PTILE, cnt = s_cnt[pp];
+        const u32 rows = cnt - r0 < (u32)PTILE ? cnt - r0 : (u32)PTILE, rows_up = (rows + 7u) & ~7u;
+        const u32 bucket = (bucket0 + pp) & 255u;
+        if ((r0 >> PB_LOG) != p_blk) { p_blk = r0 >> PB_LOG; p_phys = ps.bt[(size_t)bucket * ps.bt_stride + p_blk] - 1; }
+        const u64 base = (u64)p_phys * PB + (r0 & (PB - 1));
+        const int s = (int)((u - u0) % ASTAGES);
+        mbar_expect_tx(&full[s], rows_up * 10u);
+        bulk_g2s(stage[s].val, ps.val + base, rows_up * 8u, &full[s]);
+        bulk_g2s(stage[s].slot, ps.slot + base, rows_up * 2u, &full[s]);
+    };
+    if (tid == 0)
+        for (u32 u = u0; u < u1 && u < u0 + (ASTAGES - 1); u++) issue(u);
+    int p = 0;
+    while (p + 1 < P && s_ubase[p + 1] <= u0) p++;
+    bool dirty = false;
+    for (u32 u = u0; u < u1; u++) {
+        const u32 k = u - u0;
+        const int s = (int)(k % ASTAGES);
+        __syncthreads();                                                       // unit u-1 (stage (s+2)%3) fully consumed
+        if (tid == 0 && u + (ASTAGES - 1) < u1) issue(u + (ASTAGES - 1));
+        if (s_ubase[p + 1] <= u) {
+            if (dirty) sacc_flush(a, KP, (i64)((u64)kbase + (u64)p * KP - (u64)kmin), ga);
+            __syncthreads();
+            dirty = false;
+            while (s_ubase[p + 1] <= u) p++;
+        }
+        const u32 r0 = (u - s_ubase[p]) * PTILE, cnt = s_cnt[p];
+        const u32 rows = cnt - r0 < (u32)PTILE ? cnt - r0 : (u32)PTILE;
+        mbar_wait(&full[s], (k / ASTAGES) & 1u);
+        dirty = true;
+        const AccumStage &st = stage[s];
+#pragma unroll
+        for (int j = 0; j < PTILE / (2 * AT); j++) {
+            const u32 q = j * AT + tid;                                        // pair index
+            if (2 * q + 1 < rows) {
+                const ulonglong2 vv = *(const ulonglong2 *)&st.val[2 * q];
+                const u32 ss = *(const u32 *)&st.slot[2 * q];
+                sacc_add(a, ss & 0xFFFFu, (i64)vv.x);
+                sacc_add(a, ss >> 16, (i64)vv.y);
+            } else if (2 * q < rows) sacc_add(a, st.slot[2 * q], (i64)st.val[2 * q]);
+        }
+    }
+    __syncthreads();
+    if (dirty) sacc_flush(a, KP, (i64)((u64)kbase + (u64)p * KP - (u64)kmin), ga);
+}
+
+// min/max of the selected keys of the rows [r0, r1): the sample that decides whether the partitioned strategy is tried
+template <typename FS>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_fused_scope_rows(FS fs, i64 r0, i64 r1, i64 *mm) {
+    __shared__ i64 red[32];
+    i64 lo = RFB_INF_I64, hi = NULL_I64;
+    for (i64 i = r0 + (i64)blockIdx.x * THREADS + threadIdx.x; i < r1; i += (i64)gridDim.x * THREADS)
+        if (fs.selected(i)) { const i64 k = fs.key(i); lo = k < lo ? k : lo; hi = k > hi ? k : hi; }
+    struct Mn { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b < a ? b : a; } };
+    struct Mx { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b > a ? b : a; } };
+    lo = block_reduce<i64>(lo, Mn(), RFB_INF_I64, red);
+    hi = block_reduce<i64>(hi, Mx(), NULL_I64, red);
+    if (threadIdx.x == 0) {
+        atomicMin((long long *)&mm[0], (long long)lo);
+        atomicMax((long long *)&mm[1], (long long)hi);
+    }
+}
+
+template <typename FS>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_fused_emit(FS fs, i64 limit, i64 kmin, Accums a, i64 max_groups, i64 *out_keys, i64 *out_sums, i64 *out_counts, scan::TileCtl ctl) {
+    __shared__ scan::TileSmem sm;
+    scan::compact_rows<NUM_J>(
+        limit, ctl, sm,
+        [&](i64 r) { return fs.selected(r) && __ldcg(&a.first_row[(i64)((u64)fs.key(r) - (u64)kmin)]) == (u64)r; },
+        [&](i64 r, i64 g) {
+            if (g >= max_groups) return;
+            const i64 k = fs.key(r), s = (i64)((u64)k - (u64)kmin);
+            out_keys[g] = k;
+            out_sums[g] = a.has_null[s] ? NULL_I64 : (i64)a.sum[s];
+            out_counts[g] = (i64)a.cnt[s];
+        });
+}
+
+// tuning knobs (environment): RFB_GROUP_STRATEGY = smem | part | l2 forces a strategy where it is applicable;
+// RFB_PART_MIN_ROWS = smallest row count that takes the partitioned strategy
+int group_strategy_forced() {
+    const char *s = getenv("RFB_GROUP_STRATEGY");
+    if (!s) return 0;
+    return !strcmp(s, "smem") ? 1 : (!strcmp(s, "part") ? 2 : (!strcmp(s, "l2") ? 3 : 0));
+}
+i64 part_min_rows() {
+    const char *s = getenv("RFB_PART_MIN_ROWS");
+    return s ? atoll(s) : (1ll << 21);
+}
+
+template <typename FS>
+int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 *out_keys, i64 *out_sums, i64 *out_counts, i64 *groups) {
+    i64 *mm = (i64 *)((char *)ctx->d_scratch + 32768);
+    const int forced = group_strategy_forced();
+    const bool part_able = n < 0xF0000000ll && (forced == 2 || (forced == 0 && n >= part_min_rows()));   // 32-bit row positions
+    const int grid = rfb_grid_for(ctx, n, THREADS * 4, BLOCKS_PER_SM);
+    const int sgrid = rfb_grid_for(ctx, n, STILE, 4);
+    const bool vec = fs.vec_ok(val);
+    const i64 tiles_max = (n + scan::RowTile<NUM_J>::TILE - 1) / scan::RowTile<NUM_J>::TILE;
+    auto parts_of = [](i64 kmin, i64 kmax) { return (i64)(((u64)kmax - (u64)(kmin & ~(i64)(KP - 1))) >> KP_LOG) + 1; };
+    i64 h[2];
+    int rc;
+    bool have_scope = false, scattered = false, modded = false;
+    void *w = nullptr;
+    PartStore ps{};
+    Accums gmod{};
+    // workspace of the partitioned strategy: accumulators for the largest range it accepts, then the block store
+    const i64 max_range = (i64)MAX_PARTS * KP;
+    const size_t pb8 = align256((size_t)max_range * 8), pb4 = align256((size_t)max_range * 4);
+    const size_t p_acc_bytes = 3 * pb8 + pb4 + scan::tiles_bytes(tiles_max);
+    if (part_able) {
+        // 1. sample: three row windows; only a key range that needs more than one partition and fits MAX_PARTS is worth a scatter
+        k_fused_scope_init<<<1, 32, 0, ctx->stream>>>(mm);
+        RFB_CHECK_LAUNCH(ctx);
+        const i64 win = 65536;
+        const i64 starts[3] = {0, n / 2 > win ? n / 2 : 0, n > win ? n - win : 0};
+        for (int s = 0; s < 3; s++) {
+            const i64 r0 = starts[s], r1 = r0 + win < n ? r0 + win : n;
+            k_fused_scope_rows<FS><<<64, THREADS, 0, ctx->stream>>>(fs, r0, r1, mm);
+            RFB_CHECK_LAUNCH(ctx);
+        }
+        rc = d2h_sync(ctx, h, mm, 16);
+        if (rc) return rc;
+        const bool try_mod = h[0] <= h[1] && (forced == 0 || forced == 1) && (u64)h[1] - (u64)h[0] < (u64)KP;
+        if (try_mod) {
+            void *aux;
+            rc = rfb_ensure_aux(ctx, (size_t)KP * 20, &aux);
+            if (rc) return rc;
+            gmod.first_row = nullptr;
+            gmod.sum = (u64 *)aux;
+            gmod.cnt = gmod.sum + KP;
+            gmod.has_null = (u32 *)(gmod.cnt + KP);
+            RFB_CUDA(cudaMemsetAsync(aux, 0, (size_t)KP * 20, ctx->stream));
+            k_fused_scope_init<<<1, 32, 0, ctx->stream>>>(mm);
+            RFB_CHECK_LAUNCH(ctx);
+            const i64 ptiles = (n + PTILE - 1) / PTILE;
+            const int pgrid = (int)(ptiles < 2ll * ctx->sm_count ? ptiles : 2ll * ctx->sm_count);
+            RFB_CUDA(cudaFuncSetAttribute(k_fused_accum_mod<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, KP * 12));
+            k_fused_accum_mod<FS><<<pgrid, PT, KP * 12, ctx->stream>>>(fs, val, n, vec, gmod, mm);
+            RFB_CHECK_LAUNCH(ctx);
+            have_scope = modded = true;
+        }
+        const bool try_part = !modded && h[0] <= h[1] && (forced == 2 || (i64)((u64)h[1] - (u64)h[0]) >= KP) && (u64)h[1] - (u64)h[0] < (u64)max_range &&
+                              parts_of(h[0], h[1]) <= MAX_PARTS;
+        if (try_part) {
+            const u32 blocks = (u32)((n + PB - 1) / PB) + MAX_PARTS + 1;
+            const u32 bt_stride = (u32)((n + PB - 1) / PB) + 1;
+            const size_t bt_bytes = align256((size_t)MAX_PARTS * bt_stride * 4);
+            const size_t ctl_bytes = align256((MAX_PARTS + 1) * 4);
+            rc = rfb_ensure_work(ctx, p_acc_bytes + ctl_bytes + bt_bytes + (size_t)blocks * PB * 10, &w);
+            if (rc) return rc;
+            char *pw = (char *)w + p_acc_bytes;
+            ps.cursor = (u32 *)pw;
+            ps.next_block = ps.cursor + MAX_PARTS;
+            ps.bt = (u32 *)(pw + ctl_bytes);
+            ps.bt_stride = bt_stride;
+            ps.val = (u64 *)(pw + ctl_bytes + bt_bytes);
+            ps.slot = (u16 *)(pw + ctl_bytes + bt_bytes + (size_t)blocks * PB * 8);
+            RFB_CUDA(cudaMemsetAsync(pw, 0, ctl_bytes + bt_bytes, ctx->stream));
+            k_fused_scope_init<<<1, 32, 0, ctx->stream>>>(mm);
+            RFB_CHECK_LAUNCH(ctx);
+            k_part_scatter<FS><<<rfb_grid_for(ctx, n, SC_TILE, SC_CTAS), SC_T, 0, ctx->stream>>>(fs, val, n, vec, ps, mm);
+            RFB_CHECK_LAUNCH(ctx);
+            have_scope = scattered = true;
+        }
+    }
+    if (!have_scope) {
+        k_fused_scope_init<<<1, 32, 0, ctx->stream>>>(mm);
+        RFB_CHECK_LAUNCH(ctx);
+        k_fused_scope<FS><<<sgrid, ST, 0, ctx->stream>>>(fs, n, vec, mm);
+        RFB_CHECK_LAUNCH(ctx);
+    }
+    rc = d2h_sync(ctx, h, mm, 16);
+    if (rc) return rc;
+    if (h[0] > h[1]) { *groups = 0; return RFB_OK; }   // nothing selected
+    const i64 kmin = h[0], range = (i64)((u64)h[1] - (u64)h[0] + 1);
+    if (range <= 0 || range > (1ll << 28)) {
+        rfb_set_error("fused group-by: key range %lld is not a dense domain (use rfb_group_i64_dev + rfb_aggr_dev)", (long long)range);
+        return RFB_ERR_ARG;
+    }
+    const i64 kbase = kmin & ~(i64)(KP - 1);            // floor to a multiple of KP (two's complement)
+    const i64 P = parts_of(kmin, h[1]);                 // partitions of KP consecutive keys
+    int strategy = 3;
+    if (range <= KP && (n >= 65536 || forced == 1)) strategy = 1;
+    else if (scattered && P <= MAX_PARTS) strategy = 2;
+    if (forced == 3) strategy = 3;
+
+    const size_t b8 = strategy == 2 ? pb8 : align256((size_t)range * 8), b4 = strategy == 2 ? pb4 : align256((size_t)range * 4);
+    if (!scattered) {
+        rc = rfb_ensure_work(ctx, 3 * b8 + b4 + scan::tiles_bytes(tiles_max), &w);
+        if (rc) return rc;
+    }
+    Accums a;
+    a.first_row = (u64 *)w;
+    a.sum = (u64 *)((char *)w + b8);
+    a.cnt = (u64 *)((char *)w + 2 * b8);
+    a.has_null = (u32 *)((char *)w + 3 * b8);
+    if (scattered && strategy != 2) {   // the sample misjudged the range: the accumulator layout of the other strategies must fit
+        if (3 * align256((size_t)range * 8) + align256((size_t)range * 4) + scan::tiles_bytes(tiles_max) > ctx->work_bytes) {
+            rc = rfb_ensure_work(ctx, 3 * b8 + b4 + scan::tiles_bytes(tiles_max), &w);
+            if (rc) return rc;
+            a.first_row = (u64 *)w; a.sum = (u64 *)((char *)w + b8); a.cnt = (u64 *)((char *)w + 2 * b8); a.has_null = (u32 *)((char *)w + 3 * b8);
+        }
+    }
+    RFB_CUDA(cudaMemsetAsync(a.first_row, 0xFF, (size_t)range * 8, ctx->stream));
+    RFB_CUDA(cudaMemsetAsync(a.sum, 0, (size_t)range * 8, ctx->stream));
+    RFB_CUDA(cudaMemsetAsync(a.cnt, 0, (size_t)range * 8, ctx->stream));
+    RFB_CUDA(cudaMemsetAsync(a.has_null, 0, (size_t)range * 4, ctx->stream));
+    if (modded && range <= KP) {        // already accumulated by key residue: move the slots into key order
+        k_mod_remap<<<rfb_grid_for(ctx, range, THREADS, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(gmod, kmin, range, a);
+        RFB_CHECK_LAUNCH(ctx);
+    } else if (strategy == 1) {
+        const i64 ptiles = (n + PTILE - 1) / PTILE;
+        const int pgrid = (int)(ptiles < 2ll * ctx->sm_count ? ptiles : 2ll * ctx->sm_count);
+        RFB_CUDA(cudaFuncSetAttribute(k_fused_accum_smem<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, KP * 12));
+        k_fused_accum_smem<FS><<<pgrid, PT, (size_t)range * 12, ctx->stream>>>(fs, val, n, vec, kmin, (int)range, a);
+        RFB_CHECK_LAUNCH(ctx);
+    } else if (strategy == 2) {
+        const char *tma = getenv("RFB_ACCUM_TMA");       // "0": the register-staged kernel (128-bit loads) instead of the TMA ring
+        if (!(tma && tma[0] == '0')) {
+            const size_t smem = ASTAGES * sizeof(AccumStage) + KP * 12;
+            RFB_CUDA(cudaFuncSetAttribute(k_part_accum_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_part_accum_tma<<<ctx->sm_count, AT, smem, ctx->stream>>>(ps, (int)P, kbase, kmin, a);
+        } else {
+            RFB_CUDA(cudaFuncSetAttribute(k_part_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, KP * 12));
+            k_part_accum<<<2 * ctx->sm_count, PT, KP * 12, ctx->stream>>>(ps, (int)P, kbase, kmin, a);
+        }
+        RFB_CHECK_LAUNCH(ctx);
+    } else {
+        k_fused_accum_l2<FS><<<grid, THREADS, 0, ctx->stream>>>(fs, val, n, kmin, a);
+        RFB_CHECK_LAUNCH(ctx);
+    }
+    // first rows: claimed on a growing row prefix
+    i64 r0 = 0, r1 = 32 * range > 65536 ? 32 * range : 65536;
+    while (true) {
+        if (r1 > n) r1 = n;
+        k_fused_claim<FS><<<rfb_grid_for(ctx, r1 - r0, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(fs, r0, r1, kmin, a.first_row);
+        RFB_CHECK_LAUNCH(ctx);
+        if (r1 == n) break;
+        RFB_CUDA(cudaMemsetAsync(mm + 3, 0, 16, ctx->stream));
+        k_slot_census<<<rfb_grid_for(ctx, range, THREADS, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(a.first_row, a.cnt, range, mm);
+        RFB_CHECK_LAUNCH(ctx);
+        i64 census[2];
+        rc = d2h_sync(ctx, census, mm + 3, 16);
+        if (rc) return rc;
+        if (census[0] == census[1]) break;   // every key that occurs has its first row
+        r0 = r1;
+        r1 = r1 * 4;
+    }
+    k_max_first<<<rfb_grid_for(ctx, range, THREADS, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>(a.first_row, range, mm);
+    RFB_CHECK_LAUNCH(ctx);
+    i64 limit = 0;
+    rc = d2h_sync(ctx, &limit, mm + 2, 8);
+    if (rc) return rc;
+    const i64 tiles = (limit + scan::RowTile<NUM_J>::TILE - 1) / scan::RowTile<NUM_J>::TILE;
+    scan::TileCtl ctl;
+    rc = scan::prepare_tiles(ctx, (char *)w + 3 * b8 + b4, tiles, ctx->h_count, &ctl);
+    if (rc) return rc;
+    k_fused_emit<FS><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(fs, limit, kmin, a, max_groups, out_keys, out_sums, out_counts, ctl);
+    RFB_CHECK_LAUNCH(ctx);
+    RFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *groups = *(volatile i64 *)ctx->h_count;
+    if (*groups > max_groups) {
+        rfb_set_error("fused group-by: %lld groups exceed the output capacity %lld", (long long)*groups, (long long)max_groups);
+        return RFB_ERR_ARG;
+    }
+    return RFB_OK;
+}
+
+template <typename K, typename P>
+int fused_pred(rfb_ctx_t *ctx, const void *keys, const void *pred, PredRange pr, const i64 *val, i64 n, i64 max_groups, i64 *ok,
+               i64 *os, i64 *oc, i64 *groups) {
+    FusedSrc<K, P, true> fs{(const K *)keys, (const P *)pred, pr};
+    return fused_run(ctx, fs, val, n, max_groups, ok, os, oc, groups);
+}
+
+template <typename K>
+int fused_key(rfb_ctx_t *ctx, const void *keys, int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k, const i64 *val,
+              i64 n, i64 max_groups, i64 *ok, i64 *os, i64 *oc, i64 *groups) {
+    if (!pred) {
+        FusedSrc<K, i64, false> fs{(const K *)keys, nullptr, PredRange{0, 0, 0, 0}};
+        return fused_run(ctx, fs, val, n, max_groups, ok, os, oc, groups);
+    }
+    PredRange pr;
+    if (!rfb_make_pred(cmp_op, pred_type, k, &pr)) { rfb_set_error("fused group-by: unsupported predicate types"); return RFB_ERR_TYPE; }
+    switch (rfb_kind_of(pred_type)) {
+        case K_I32: return fused_pred<K, i32>(ctx, keys, pred, pr, val, n, max_groups, ok, os, oc, groups);
+        case K_I64: return fused_pred<K, i64>(ctx, keys, pred, pr, val, n, max_groups, ok, os, oc, groups);
+        case K_F64: return fused_pred<K, f64>(ctx, keys, pred, pr, val, n, max_groups, ok, os, oc, groups);
+        default: rfb_set_error("fused group-by: unsupported predicate column type %d", pred_type); return RFB_ERR_TYPE;
+    }
+}
+
+}  // namespace
+
+extern "C" int rfb_group_sum_count_dev(rfb_ctx_t *ctx, int key_type, const void *keys, const int64_t *val, int64_t n,
+                                       int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k,
+                                       int64_t max_groups, int64_t *out_keys, int64_t *out_sums, int64_t *out_counts,
+                                       int64_t *groups) {
+    RFB_ARG(ctx && groups && n >= 0 && max_groups >= 0 && ((keys && val) || n == 0) && (!pred || k), "rfb_group_sum_count_dev");
+    RFB_ARG((out_keys && out_sums && out_counts) || max_groups == 0, "rfb_group_sum_count_dev: outputs");
+    *groups = 0;
+    if (n == 0) return RFB_OK;
+    switch (rfb_kind_of(key_type)) {
+        case K_I32: return fused_key<i32>(ctx, keys, cmp_op, pred_type, pred, k, val, n, max_groups, out_keys, out_sums, out_counts, groups);
+        case K_I64: return fused_key<i64>(ctx, keys, cmp_op, pred_type, pred, k, val, n, max_groups, out_keys, out_sums, out_counts, groups);
+        default: rfb_set_error("fused group-by: key type %d (I32 or I64 keys)", key_type); return RFB_ERR_TYPE;
+    }
+}
