@@ -24,7 +24,8 @@ namespace {
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
 // scatter geometry, measured on B200 (1e8 i64 rows, 8 passes; ITEMS x CTAs/SM x early row-id loads): 12x3x0 13.3 ms (before the
-// cross-tile pipeline), 12x3x1 14.1 (row ids spill), 12x2x0 12.8, 12x2x1 11.7, 14x2x1 11.3, 16x2x1 11.7, 18x2x1 12.2
+// cross-tile pipeline), 12x3x1 14.1 (row ids spill), 12x2x0 12.8, 12x2x1 11.7, 14x2x1 11.3, 16x2x1 11.7, 18x2x1 12.2;
+// 512-thread CTAs (RFB_SORT_THREADS=512, 64 registers, twice the warps per SM): 7x2 11.5, 6x2 11.8, 8x2 12.2 — no gain
 #ifndef RFB_SORT_EARLY_RID
 #define RFB_SORT_EARLY_RID 1
 #endif
@@ -32,8 +33,12 @@ constexpr int WARPS = THREADS / 32;
 #define RFB_SORT_ITEMS 14
 #define RFB_SORT_CTAS 2
 #endif
+#ifndef RFB_SORT_THREADS
+#define RFB_SORT_THREADS 256
+#endif
+constexpr int SCT = RFB_SORT_THREADS, SWARPS = SCT / 32;   // scatter kernel CTA size (the other kernels use THREADS)
 constexpr int ITEMS = RFB_SORT_ITEMS;
-constexpr int TILE = THREADS * ITEMS;  // 3584 rows: 56 KB of staged (key, row id) pairs per CTA
+constexpr int TILE = SCT * ITEMS;  // 3584 rows: 56 KB of staged (key, row id) pairs per CTA
 constexpr int RADIX = 256;
 
 template <typename T> __device__ __forceinline__ u64 sortable(T v);
@@ -136,19 +141,19 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const u32 *bh, i64 *offs, 
 // digit in lower warps + lower steps/lanes of the own warp), then streamed out so that the rows of one digit leave as one
 // contiguous run — direct per-lane stores hit up to 32 different sectors per instruction.
 template <typename Src, bool WRITE_KEYS>
-__global__ void __launch_bounds__(THREADS, RFB_SORT_CTAS)
+__global__ void __launch_bounds__(SCT, RFB_SORT_CTAS)
 k_scatter(Src src, i64 n, i64 chunk, int shift, const i64 *__restrict__ offs /* [256][G] */, u64 *__restrict__ keys_out,
           i64 *__restrict__ vals_out) {
-    __shared__ u32 whist[WARPS][RADIX];
+    __shared__ u32 whist[SWARPS][RADIX];
     __shared__ i64 base[RADIX];     // next free output slot of each digit for this chunk
     __shared__ u32 dstart[RADIX];   // tile-local position of the first row of each digit
-    __shared__ u32 wsum[WARPS];
+    __shared__ u32 wsum[RADIX / 32];
     extern __shared__ u64 stage_dyn[];            // TILE keys then TILE row ids (48 KB: above the static limit)
     u64 *skeys = stage_dyn;
     i64 *svals = (i64 *)(stage_dyn + TILE);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 lt = (1u << lane) - 1u;
-    base[threadIdx.x] = offs[(i64)threadIdx.x * gridDim.x + blockIdx.x];
+    if (threadIdx.x < RADIX) base[threadIdx.x] = offs[(i64)threadIdx.x * gridDim.x + blockIdx.x];
     const i64 lo = (i64)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
     // software pipeline across tiles, without extra registers: a tile's keys are dead once they sit in shared memory, so the
     // NEXT tile's keys are loaded into the same registers right before the write-out (their latency hides behind it), and the
@@ -163,8 +168,7 @@ k_scatter(Src src, i64 n, i64 chunk, int shift, const i64 *__restrict__ offs /* 
         }
     }
     for (i64 t0 = lo; t0 < hi; t0 += TILE) {
-#pragma unroll
-        for (int w = 0; w < WARPS; w++) whist[w][threadIdx.x] = 0;
+        for (int idx = threadIdx.x; idx < SWARPS * RADIX; idx += SCT) (&whist[0][0])[idx] = 0;
         __syncthreads();
         u32 rank[ITEMS];
         const i64 wb = t0 + (i64)warp * (32 * ITEMS);
@@ -198,25 +202,27 @@ k_scatter(Src src, i64 n, i64 chunk, int shift, const i64 *__restrict__ offs /* 
         }
 #endif
         __syncthreads();
-        u32 cnt;
-        {   // thread d: digit d's counts over the warps -> exclusive warp offsets; then the tile-local start of each digit
+        u32 cnt = 0, incl = 0;
+        if (threadIdx.x < RADIX) {   // thread d: digit d's counts over the warps -> exclusive warp offsets; then the tile-local start of each digit
             const int d = threadIdx.x;
             u32 sum = 0;
 #pragma unroll
-            for (int w = 0; w < WARPS; w++) { const u32 c = whist[w][d]; whist[w][d] = sum; sum += c; }
+            for (int w = 0; w < SWARPS; w++) { const u32 c = whist[w][d]; whist[w][d] = sum; sum += c; }
             cnt = sum;
-            u32 incl = cnt;
+            incl = cnt;
 #pragma unroll
             for (int k = 1; k < 32; k <<= 1) {
                 const u32 o = __shfl_up_sync(0xffffffffu, incl, k);
                 if (lane >= k) incl += o;
             }
             if (lane == 31) wsum[warp] = incl;
-            __syncthreads();
+        }
+        __syncthreads();
+        if (threadIdx.x < RADIX) {
             u32 woff = 0;
 #pragma unroll
-            for (int w = 0; w < WARPS; w++) woff += (w < warp) ? wsum[w] : 0u;
-            dstart[d] = woff + incl - cnt;
+            for (int w = 0; w < RADIX / 32; w++) woff += (w < warp) ? wsum[w] : 0u;
+            dstart[threadIdx.x] = woff + incl - cnt;
         }
         __syncthreads();
 #pragma unroll
@@ -243,7 +249,7 @@ k_scatter(Src src, i64 n, i64 chunk, int shift, const i64 *__restrict__ offs /* 
             }
         }
         const int tile_n = (int)((hi - t0) < TILE ? (hi - t0) : TILE);
-        for (int i = threadIdx.x; i < tile_n; i += THREADS) {
+        for (int i = threadIdx.x; i < tile_n; i += SCT) {
             const u64 k = skeys[i];
             const u32 d = (u32)(k >> shift) & 255u;
             const i64 pos = base[d] + (i64)(i - (int)dstart[d]);
@@ -251,7 +257,7 @@ k_scatter(Src src, i64 n, i64 chunk, int shift, const i64 *__restrict__ offs /* 
             vals_out[pos] = svals[i];
         }
         __syncthreads();
-        base[threadIdx.x] += cnt;
+        if (threadIdx.x < RADIX) base[threadIdx.x] += cnt;
     }
 }
 
@@ -274,8 +280,8 @@ int run_pass(rfb_ctx_t *ctx, Src src, i64 n, int G, i64 chunk, int shift, u32 *b
         RFB_CUDA(cudaFuncSetAttribute(k_scatter<Src, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
         opted_in = true;
     }
-    if (last) k_scatter<Src, false><<<G, THREADS, STAGE_BYTES, ctx->stream>>>(src, n, chunk, shift, offs, keys_out, vals_out);
-    else k_scatter<Src, true><<<G, THREADS, STAGE_BYTES, ctx->stream>>>(src, n, chunk, shift, offs, keys_out, vals_out);
+    if (last) k_scatter<Src, false><<<G, SCT, STAGE_BYTES, ctx->stream>>>(src, n, chunk, shift, offs, keys_out, vals_out);
+    else k_scatter<Src, true><<<G, SCT, STAGE_BYTES, ctx->stream>>>(src, n, chunk, shift, offs, keys_out, vals_out);
     RFB_CHECK_LAUNCH(ctx);
     return RFB_OK;
 }
