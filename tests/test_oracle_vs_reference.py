@@ -459,3 +459,30 @@ def test_distinct_dense(oracle, reference, n, card, kmin):
     got = reference.to_numpy(reference.call1("ray_distinct", v))[0]
     reference.drop(v)
     assert np.array_equal(oracle.distinct(keys), got)
+
+
+@pytest.mark.parametrize("n", [800, 50_000])
+def test_multi_key_group_by_row_hash_path_through_rayfall_select(oracle, reference, n):
+    """the same query with key columns whose ranges do not multiply into an i64 (core/index.c:2556-2729, row hashes): the tuples,
+    their sums and counts must match the oracle's multi-key index + grouped aggregates (compared per key tuple: the reference's
+    group order on this path is its hash tables' order)"""
+    import ctypes as C
+    if not reference_scope_is_safe(n, reference.cores):
+        pytest.skip("Q12")
+    r = np.random.default_rng(n + 1)
+    pa, pb = r.integers(-(1 << 61), 1 << 61, 9).astype(np.int64), r.integers(-(1 << 61), 1 << 61, 11).astype(np.int64)
+    a, b = pa[r.integers(0, 9, n)], pb[r.integers(0, 11, n)]
+    v = r.integers(-50, 50, n)
+    for name, arr in (("mh_a", a), ("mh_b", b), ("mh_v", v)):
+        o = reference.eval("(set %s (til %d))" % (name, n))
+        np.frombuffer((C.c_char * (n * 8)).from_address(o + 16), dtype=np.int64)[:] = arr
+    reference.eval("(set mh_t (table [a b v] (list mh_a mh_b mh_v)))")
+    res = reference.eval("(select {s: (sum v) n: (count v) from: mh_t by: {a: a b: b}})")
+    cols = [reference.to_numpy(x, drop=False)[0] for x in reference.list_items(reference.list_items(res)[1])]
+    gids, firsts, groups = oracle.group_multi([a, b])
+    assert groups == cols[0].shape[0]
+    want = np.stack([a[firsts], b[firsts], oracle.aggr(ob.SUM, ob.I64, v, gids, groups)[0], oracle.aggr(ob.COUNT, ob.I64, v, gids, groups)[0]])
+    got = np.stack(cols)
+    want = want[:, np.lexsort(want[:2][::-1])]
+    got = got[:, np.lexsort(got[:2][::-1])]
+    assert np.array_equal(got, want)
