@@ -295,7 +295,8 @@ struct ScatterSmem {
     u64 val[SC_TILE];
     u32 pk[SC_TILE];               // bucket << KP_LOG | slot
     uint4 desc[MAX_PARTS];       // per bucket: {x: physical - local offset before the block boundary, y: first local index past it, z: offset after it, w: local base}
-    u32 cnt[MAX_PARTS];
+    u32 cnt[2 * MAX_PARTS];      // two counters per bucket (even / odd lanes): halves the same-address conflicts of the ranking atomics
+    u32 lb[2 * MAX_PARTS];       // tile-local base of each (bucket, copy)
     u32 wtot[MAX_PARTS / 32];
     u32 total;
     i64 red[32];
@@ -314,7 +315,7 @@ k_part_scatter(FS fs, const i64 *__restrict__ val, i64 n, bool vec, PartStore ps
     const i64 tiles = (n + SC_TILE - 1) / SC_TILE;
     typedef typename FS::key_t KT;   // running min/max in the key column's own width (register pressure)
     KT lo = sizeof(KT) == 4 ? (KT)0x7FFFFFFF : (KT)RFB_INF_I64, hi = sizeof(KT) == 4 ? (KT)NULL_I32 : (KT)NULL_I64;
-    if (tid < MAX_PARTS) sm.cnt[tid] = 0;
+    if (tid < MAX_PARTS) { sm.cnt[2 * tid] = 0; sm.cnt[2 * tid + 1] = 0; }
     __syncthreads();
     for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         i64 k[SC_R], v[SC_R];
@@ -329,14 +330,19 @@ k_part_scatter(FS fs, const i64 *__restrict__ val, i64 n, bool vec, PartStore ps
             const u32 p0 = __shfl_sync(0xffffffffu, part, 0);
             if (__all_sync(0xffffffffu, part == p0)) {      // the whole warp step goes to one bucket: one atomic
                 u32 b = 0;
-                if (lane == 0 && sel[j]) b = atomicAdd(&sm.cnt[part], 32u);
+                if (lane == 0 && sel[j]) b = atomicAdd(&sm.cnt[2 * part], 32u);
                 pos[j] = __shfl_sync(0xffffffffu, b, 0) + lane;
-            } else if (sel[j]) pos[j] = atomicAdd(&sm.cnt[part], 1u);
+                pk[j] &= ~(1u << 31);                       // (copy 0)
+            } else if (sel[j]) {
+                pos[j] = atomicAdd(&sm.cnt[2 * part + (lane & 1)], 1u);
+                pk[j] |= (u32)(lane & 1) << 31;             // remember the copy for the staging step
+            }
         }
         __syncthreads();
-        u32 c = 0, incl = 0, start = 0, phys0 = 0, phys1 = 0;
+        u32 c = 0, c0 = 0, incl = 0, start = 0, phys0 = 0, phys1 = 0;
         if (tid < MAX_PARTS) {
-            c = sm.cnt[tid];
+            c0 = sm.cnt[2 * tid];
+            c = c0 + sm.cnt[2 * tid + 1];
             incl = c;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -368,16 +374,20 @@ k_part_scatter(FS fs, const i64 *__restrict__ val, i64 n, bool vec, PartStore ps
             d.z = (phys1 - 1) * (u32)PB - (lbase + room);
             d.w = lbase;
             sm.desc[tid] = d;
-            sm.cnt[tid] = 0;                                   // for the next tile (this tile's counts live in registers now)
+            sm.lb[2 * tid] = lbase;
+            sm.lb[2 * tid + 1] = lbase + c0;
+            sm.cnt[2 * tid] = 0;                               // for the next tile (this tile's counts live in registers now)
+            sm.cnt[2 * tid + 1] = 0;
             if (tid == MAX_PARTS - 1) sm.total = before + incl;
         }
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < SC_R; j++) {
             if (!sel[j]) continue;
-            const u32 q = sm.desc[pk[j] >> KP_LOG].w + pos[j];
+            const u32 w = pk[j] & 0x7FFFFFFFu;
+            const u32 q = sm.lb[2 * (w >> KP_LOG) + (pk[j] >> 31)] + pos[j];
             sm.val[q] = (u64)v[j];
-            sm.pk[q] = pk[j];
+            sm.pk[q] = w;
         }
         __syncthreads();
         const u32 total = sm.total;
