@@ -1135,7 +1135,48 @@ obj_p rfb_ray_sort_desc(obj_p x) { return sort_op(x, 1); }
 
 /* ------------------------------------------------------------------ fused query entry points */
 
+/* Plugin mode (reference core/dynlib.c:153-218: `(loadfn "librfb200_ops.so" "rfb_where_lt_sum" 2)` from a STOCK reference
+ * binary, no shim): nobody has called rfb_ops_init.  The first plugin call binds the host API itself from the symbols the
+ * reference exports to plugins (rayforce.syms: vector, i64, clone_obj, drop_obj, __NULL_OBJ; err_* only when the binary was
+ * linked with -rdynamic — otherwise an operand error answers the null object instead of the reference's error object). */
+#include <dlfcn.h>
+static rfb_host_api_t plugin_host;
+static obj_p (*plugin_i64)(int64_t);
+static obj_p (*plugin_err_type)(int8_t, int8_t, uint8_t, uint8_t);
+static obj_p (*plugin_err_length)(uint8_t, uint8_t, uint8_t, uint8_t, int64_t, int64_t);
+static obj_p (*plugin_err_limit)(int64_t);
+static obj_p plugin_atom(int8_t type) {
+    obj_p a = plugin_i64(0);                       /* a 16-byte atom; retype it (atoms of every numeric type share the layout) */
+    if (a) a->type = (int8_t)-type;
+    return a;
+}
+static obj_p plugin_e_type(void) { return plugin_err_type ? plugin_err_type(0, 0, 0, 0) : plugin_host.null_obj; }
+static obj_p plugin_e_length(void) { return plugin_err_length ? plugin_err_length(0, 0, 0, 0, 0, 0) : plugin_host.null_obj; }
+static obj_p plugin_e_limit(void) { return plugin_err_limit ? plugin_err_limit(0) : plugin_host.null_obj; }
+static int plugin_bind(void) {
+    if (G.ready) return 1;
+    void *self = RTLD_DEFAULT;
+    plugin_host.vector = (obj_p(*)(int8_t, int64_t))dlsym(self, "vector");
+    plugin_i64 = (obj_p(*)(int64_t))dlsym(self, "i64");
+    plugin_host.clone_obj = (obj_p(*)(obj_p))dlsym(self, "clone_obj");
+    plugin_host.drop_obj = (void (*)(obj_p))dlsym(self, "drop_obj");
+    plugin_host.null_obj = (obj_p)dlsym(self, "__NULL_OBJ");
+    if (!plugin_host.vector || !plugin_i64 || !plugin_host.clone_obj || !plugin_host.drop_obj || !plugin_host.null_obj) {
+        set_err("plugin mode: the host process does not export vector / i64 / clone_obj / drop_obj / __NULL_OBJ");
+        return 0;
+    }
+    *(void **)&plugin_err_type = dlsym(self, "err_type");
+    *(void **)&plugin_err_length = dlsym(self, "err_length");
+    *(void **)&plugin_err_limit = dlsym(self, "err_limit");
+    plugin_host.atom = plugin_atom;
+    plugin_host.err_type = plugin_e_type;
+    plugin_host.err_length = plugin_e_length;
+    plugin_host.err_limit = plugin_e_limit;
+    return rfb_ops_init(&plugin_host, 0) == 0;
+}
+
 static obj_p where_fold(int op, int what, obj_p pred, obj_p k, obj_p val) {
+    if (!G.ready && !plugin_bind()) return plugin_host.null_obj;   /* no usable GPU: the null object (NULL when not even a host) */
     if (!G.ready || !is_vec(pred) || !is_vec(val) || !is_atom(k)) return G.ready ? G.host->err_type() : NULL;
     if (pred->len != val->len) return G.host->err_length();
     if (op < RFB_EQ || op > RFB_GE || what < F_SUM || what > F_AVG || !fold_type_ok(what, val->type)) return G.host->err_type();
@@ -1158,7 +1199,7 @@ static obj_p where_fold(int op, int what, obj_p pred, obj_p k, obj_p val) {
 obj_p rfb_where_lt_sum(obj_p col, obj_p k) { return where_fold(RFB_LT, F_SUM, col, k, col); }
 
 obj_p rfb_where_fold(obj_p *args, int64_t n) {
-    if (!G.ready) return NULL;
+    if (!G.ready && !plugin_bind()) return plugin_host.null_obj;
     if (n != 5 || !args[0] || !args[1] || args[0]->type != -RFB_T_I64 || args[1]->type != -RFB_T_I64) return G.host->err_type();
     return where_fold((int)args[0]->i64, (int)args[1]->i64, args[2], args[3], args[4]);
 }
