@@ -256,6 +256,29 @@ class Oracle:
             raise OracleError(r)
         return ids
 
+    def window_aggr(self, op, vt, val, right_cols, rtime, left_cols, wlo, whi, jtype):
+        """window join aggregate over a right table ordered by (key, time) -> (array[len(left)], type)"""
+        r = [np.ascontiguousarray(c, np.int64) for c in right_cols]
+        l = [np.ascontiguousarray(c, np.int64) for c in left_cols]
+        ra = (C.c_void_p * len(r))(*[c.ctypes.data for c in r])
+        la = (C.c_void_p * len(l))(*[c.ctypes.data for c in l])
+        ll, rl = l[0].shape[0], r[0].shape[0]
+        first, last = np.empty(max(ll, 1), np.int64), np.empty(max(ll, 1), np.int64)
+        L = self.L
+        L.rfo_window_bounds.restype = C.c_int
+        L.rfo_window_bounds.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int64, C.POINTER(C.c_void_p), C.c_int64, C.c_void_p, C.c_void_p]
+        L.rfo_window_bounds(len(r), ra, rl, la, ll, _ptr(first), _ptr(last))
+        val = np.ascontiguousarray(val, NP_OF[vt])
+        rtime, wlo, whi = (np.ascontiguousarray(a, np.int32) for a in (rtime, wlo, whi))
+        out = np.zeros(max(ll, 1), np.int64)
+        ot = C.c_int(0)
+        L.rfo_window_aggr.restype = C.c_int
+        L.rfo_window_aggr.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        rc = L.rfo_window_aggr(op, vt, _ptr(val), _ptr(rtime), ll, _ptr(first), _ptr(last), _ptr(wlo), _ptr(whi), jtype, _ptr(out), C.byref(ot))
+        if rc < 0:
+            raise OracleError(rc)
+        return out[:ll].view(NP_OF[ot.value]).copy(), ot.value
+
     def inner_join(self, build_cols, probe_cols):
         ids = self.find_rows(build_cols, probe_cols)
         pi = np.nonzero(ids != NULL_I64)[0].astype(np.int64)

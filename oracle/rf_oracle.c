@@ -886,6 +886,82 @@ int64_t rfo_distinct_i64(const int64_t *keys, int64_t n, int64_t *out) {
     return j;
 }
 
+/* Window join (reference core/join.c:358-485 -> index_window_join_obj core/index.c:3287-3346 -> the INDEX_TYPE_WINDOW branch of
+ * AGGR_ITER core/aggr.c:131-160).  The right table is ordered by (key tuple, time) — ray_window_join sorts it with xasc first —
+ * so the rows of one key form one block [first, last]; the index keeps exactly that pair per key (first = the row that created
+ * the slot, last = the latest row seen).  For left row i with window [wlo[i], whi[i]] on a 4-byte time column:
+ *   li = jtype 0 (window-join):  indexr_bin: the last row of the block with time <= wlo, the block's first row if there is none
+ *        jtype 1 (window-join1): indexl_bin: the first row of the block with time >= wlo (the block's first row if none)
+ *   ri = indexr_bin: the last row of the block with time <= whi (the block's first row if none)
+ *   no block, time[li] > whi, or (jtype 1 and time[ri] < wlo)  ->  the aggregate's Null value; else fold val[li..ri] with the
+ *   GROUPED partial of the aggregate (sticky-null sum, +INF-initialised min, null-initialised max, row count).
+ * rfo_window_bounds computes (first, last) per left row; rfo_window_aggr folds.  NOT YET ON THE DEVICE. */
+int rfo_window_bounds(int ncols, const int64_t *const *right, int64_t rl, const int64_t *const *left, int64_t ll, int64_t *first, int64_t *last) {
+    i64 *f = (i64 *)malloc((size_t)(ll > 0 ? ll : 1) * 8);
+    rfo_find_rows(ncols, right, rl, left, ll, f);
+    /* last row of the key = the last right row whose tuple equals the first row's tuple: scan backwards once per distinct first */
+    i64 *lastof = (i64 *)malloc((size_t)(rl > 0 ? rl : 1) * 8);
+    for (i64 r = 0; r < rl; r++) lastof[r] = -1;
+    rfo_tuple_ctx R = {ncols, right};
+    i64 *fr = (i64 *)malloc((size_t)(rl > 0 ? rl : 1) * 8);
+    rfo_find_rows(ncols, right, rl, right, rl, fr);            /* every right row -> first row of its key */
+    for (i64 r = 0; r < rl; r++) lastof[fr[r]] = r;            /* ascending r: the last assignment wins */
+    (void)R;
+    for (i64 i = 0; i < ll; i++) { first[i] = f[i]; last[i] = f[i] == RFO_NULL_I64 ? RFO_NULL_I64 : lastof[f[i]]; }
+    free(f); free(lastof); free(fr);
+    return RFO_OK;
+}
+static i64 bin_r_i32(i32 val, const i32 *vals, i64 offset, i64 len) {   /* core/aggr.c:39-54 */
+    i64 left = 0, right = len - 1, idx = 0;
+    vals += offset;
+    while (left <= right) { i64 mid = left + (right - left) / 2; if (vals[mid] <= val) { idx = mid; left = mid + 1; } else right = mid - 1; }
+    return idx + offset;
+}
+static i64 bin_l_i32(i32 val, const i32 *vals, i64 offset, i64 len) {   /* core/aggr.c:56-72 */
+    i64 left = 0, right = len - 1, idx = 0;
+    vals += offset;
+    while (left <= right) { i64 mid = left + (right - left) / 2; if (vals[mid] < val) left = mid + 1; else { idx = mid; right = mid - 1; } }
+    return idx + offset;
+}
+int rfo_window_aggr(int op, int val_type, const void *val, const int32_t *rtime, int64_t ll, const int64_t *first, const int64_t *last,
+                    const int32_t *wlo, const int32_t *whi, int jtype, void *out, int *out_type) {
+    int k = kind_of(val_type);
+    if (!(k == K_I64 || k == K_F64)) return RFO_ERR_TYPE;
+    if (!(op == RFO_SUM || op == RFO_MIN || op == RFO_MAX || op == RFO_COUNT)) return RFO_ERR_TYPE;
+    *out_type = op == RFO_COUNT ? RFO_I64 : val_type;
+    for (i64 i = 0; i < ll; i++) {
+        i64 li = 0, ri = 0;
+        int none = first[i] == RFO_NULL_I64;
+        if (!none) {
+            i64 fi = first[i], n = last[i] - first[i] + 1;
+            li = jtype == 0 ? bin_r_i32(wlo[i], rtime, fi, n) : bin_l_i32(wlo[i], rtime, fi, n);
+            ri = bin_r_i32(whi[i], rtime, fi, n);
+            if (rtime[li] > whi[i] || (jtype == 1 && rtime[ri] < wlo[i])) none = 1;
+        }
+        if (op == RFO_COUNT) { ((i64 *)out)[i] = none ? 0 : ri - li + 1 > 0 ? ri - li + 1 : 0; continue; }
+        if (k == K_I64) {
+            const i64 *v = (const i64 *)val; i64 a;
+            if (none) a = RFO_NULL_I64;
+            else {
+                a = op == RFO_SUM ? 0 : (op == RFO_MIN ? RFO_INF_I64 : RFO_NULL_I64);
+                for (i64 x = li; x <= ri; x++)
+                    a = op == RFO_SUM ? ((a == RFO_NULL_I64 || v[x] == RFO_NULL_I64) ? RFO_NULL_I64 : wadd64(a, v[x])) : (op == RFO_MIN ? min_i64(a, v[x]) : max_i64(a, v[x]));
+            }
+            ((i64 *)out)[i] = a;
+        } else {
+            const f64 *v = (const f64 *)val; f64 a;
+            if (none) a = null_f64();
+            else {
+                a = op == RFO_SUM ? 0.0 : (op == RFO_MIN ? (f64)INFINITY : null_f64());
+                for (i64 x = li; x <= ri; x++)
+                    a = op == RFO_SUM ? ((isnan64(a) || isnan64(v[x])) ? null_f64() : a + v[x]) : (op == RFO_MIN ? min_f64(a, v[x]) : max_f64(a, v[x]));
+            }
+            ((f64 *)out)[i] = a;
+        }
+    }
+    return RFO_OK;
+}
+
 /* ------------------------------------------------------------------ key sort (core/sort.c) */
 
 /* order-preserving map to u64: integers flip the sign bit (core/sort.c:313), doubles core/sort.c:266-285 */

@@ -121,6 +121,13 @@ int rfo_asof_join(int ncols, const int64_t *const *build, int time_type, const v
 /* ray_distinct -> index_distinct_i64, dense branch (core/index.c:551-577): ascending distinct keys; -1 = not dense */
 int64_t rfo_distinct_i64(const int64_t *keys, int64_t n, int64_t *out);
 
+/* window join (core/join.c:358-485, core/index.c:3287-3346, core/aggr.c:131-160): right table ordered by (key, time); per left row
+ * the [first, last] block of its key, then the aggregate of the rows inside the window [wlo, whi] (jtype 0 = window-join,
+ * 1 = window-join1).  Oracle only so far: the device path is a next step. */
+int rfo_window_bounds(int ncols, const int64_t *const *right, int64_t rl, const int64_t *const *left, int64_t ll, int64_t *first, int64_t *last);
+int rfo_window_aggr(int op, int val_type, const void *val, const int32_t *rtime, int64_t ll, const int64_t *first, const int64_t *last,
+                    const int32_t *wlo, const int32_t *whi, int jtype, void *out, int *out_type);
+
 /* ---- key sort: core/sort.c:183-428 asc, :481-689 desc ---- stable permutation, nulls/NaN first when ascending */
 int rfo_sort(int type, const void *x, int64_t n, int descending, int64_t *perm);
 

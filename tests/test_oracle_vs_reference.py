@@ -486,3 +486,41 @@ def test_multi_key_group_by_row_hash_path_through_rayfall_select(oracle, referen
     want = want[:, np.lexsort(want[:2][::-1])]
     got = got[:, np.lexsort(got[:2][::-1])]
     assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------- window joins (oracle only so far: DESIGN.md §10)
+
+def _set_col(reference, name, arr, t):
+    import ctypes as C
+    n = arr.shape[0]
+    src = {ob.I64: "(til %d)", ob.TIME: "(as 'TIME (til %d))", ob.F64: "(as 'F64 (til %d))"}[t] % n
+    o = reference.eval("(set %s %s)" % (name, src))
+    assert reference.type_of(o) == t
+    np.frombuffer((C.c_char * (n * np.dtype(ob.NP_OF[t]).itemsize)).from_address(o + 16), dtype=ob.NP_OF[t])[:] = arr
+
+
+@pytest.mark.parametrize("nl,nr,lkeys,rkeys,span", [(50, 400, 5, 6, 100_000), (2000, 30_000, 40, 35, 1_000_000), (300, 50, 3, 9, 5_000)])
+@pytest.mark.parametrize("vt", [ob.I64, ob.F64])
+def test_window_join_aggregates_through_rayfall(oracle, reference, nl, nr, lkeys, rkeys, span, vt):
+    """(window-join / window-join1 [Sym Time] intervals trades quotes {r: (agg Bid)}): the reference sorts quotes by (Sym, Time),
+    keeps the [first, last] row block per key and folds the rows inside every trade's window (core/join.c:358-485,
+    core/index.c:3287-3346, core/aggr.c:39-72, 131-160).  Keys missing on either side, windows without rows, nulls in Bid."""
+    r = np.random.default_rng(nl + nr)
+    ls = r.integers(0, lkeys, nl).astype(np.int64)
+    lt = np.sort(r.integers(0, span, nl)).astype(np.int32)
+    rs = r.integers(0, rkeys, nr).astype(np.int64)
+    rt = r.integers(0, span, nr).astype(np.int32)
+    bid = rng_col(vt, nr, 7, null_frac=0.02, lo=-50, hi=50)
+    if vt == ob.F64:
+        bid = np.round(bid * 4) / 4
+    for name, arr, t in (("wj_ls", ls, ob.I64), ("wj_lt", lt, ob.TIME), ("wj_rs", rs, ob.I64), ("wj_rt", rt, ob.TIME), ("wj_bid", bid, vt)):
+        _set_col(reference, name, arr, t)
+    reference.eval("(set wj_trades (table [Sym Time] (list wj_ls wj_lt)))")
+    reference.eval("(set wj_quotes (table [Sym Time Bid] (list wj_rs wj_rt wj_bid)))")
+    reference.eval("(set wj_iv (map-left + [-2000 3000] (at wj_trades 'Time)))")
+    order = np.lexsort((rt, rs))                       # xasc [Sym Time]: stable
+    for fn, jt in (("window-join", 0), ("window-join1", 1)):
+        for name, op in (("min", ob.MIN), ("max", ob.MAX), ("sum", ob.SUM), ("count", ob.COUNT)):
+            got = reference.to_numpy(reference.eval("(at (%s [Sym Time] wj_iv wj_trades wj_quotes {r: (%s Bid)}) 'r)" % (fn, name)))[0]
+            want, wt = oracle.window_aggr(op, vt, bid[order], [rs[order]], rt[order], [ls], lt - 2000, lt + 3000, jt)
+            assert same_f64(want, got) if wt == ob.F64 else np.array_equal(want, got), (fn, name)
