@@ -140,6 +140,7 @@ SIGNATURES = {
     "rfb_inner_join_dev": (_ci, [_vp, _ci, _P(_vp), _i64, _P(_vp), _i64, _vp, _vp, _P(_i64)]),
     "rfb_asof_join_dev": (_ci, [_vp, _ci, _P(_vp), _ci, _vp, _i64, _P(_vp), _vp, _i64, _vp]),
     "rfb_distinct_i64_dev": (_ci, [_vp, _vp, _i64, _vp, _P(_i64)]),
+    "rfb_window_join_dev": (_ci, [_vp, _ci, _P(_vp), _vp, _i64, _P(_vp), _i64, _vp, _vp, _ci, _ci, _ci, _vp, _vp]),
     "rfb_group_sum_count_dev": (_ci, [_vp, _ci, _vp, _vp, _i64, _ci, _ci, _vp, _P(Scalar), _i64, _vp, _vp, _vp, _P(_i64)]),
     "rfb_sort_dev": (_ci, [_vp, _ci, _vp, _i64, _ci, _vp]),
     "rfb_column_file_open": (_ci, [C.c_char_p, _P(ColumnFile)]),

@@ -213,3 +213,113 @@ extern "C" int rfb_asof_join_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const
     RFB_CHECK_LAUNCH(ctx);
     return RFB_OK;
 }
+
+// ------------------------------------------------------------------ window join
+//
+// The reference (core/join.c:358-485) sorts the right table by (key tuple, time), so the rows of one key form one block; its index
+// keeps the block's first and last row per key (core/index.c:3303-3316) and AGGR_ITER's WINDOW branch (core/aggr.c:131-160)
+// binary-searches the block on the 4-byte time column for every left row's window and folds the rows inside it.  The device takes
+// the same sorted right table: the block's first row comes from the join table (first build row of the key), its last row from
+// a gallop + binary search for the last row whose key tuple still equals the first row's, then the reference's two searches
+// (indexr_bin / indexl_bin, core/aggr.c:39-72) and the grouped partial of the aggregate over the window's rows.
+namespace {
+enum { W_SUM = 0, W_MIN = 1, W_MAX = 2, W_COUNT = 3 };
+
+__device__ __forceinline__ i64 bin_r(i32 val, const i32 *__restrict__ t, i64 offset, i64 len) {   // last row with time <= val, else the first
+    i64 left = 0, right = len - 1, idx = 0;
+    while (left <= right) { const i64 mid = left + (right - left) / 2; if (__ldg(t + offset + mid) <= val) { idx = mid; left = mid + 1; } else right = mid - 1; }
+    return idx + offset;
+}
+__device__ __forceinline__ i64 bin_l(i32 val, const i32 *__restrict__ t, i64 offset, i64 len) {   // first row with time >= val, else the first
+    i64 left = 0, right = len - 1, idx = 0;
+    while (left <= right) { const i64 mid = left + (right - left) / 2; if (__ldg(t + offset + mid) < val) left = mid + 1; else { idx = mid; right = mid - 1; } }
+    return idx + offset;
+}
+
+template <int OP, typename V>
+__global__ void __launch_bounds__(THREADS, 4)
+k_window_fold(KeyCols right, i64 rl, const i32 *__restrict__ rtime, const V *__restrict__ val, const i64 *__restrict__ first, const i32 *__restrict__ wlo,
+              const i32 *__restrict__ whi, i64 ll, int jtype, void *out) {
+    for (i64 i = (i64)blockIdx.x * THREADS + threadIdx.x; i < ll; i += (i64)gridDim.x * THREADS) {
+        const i64 f = ld_stream(first + i);
+        bool none = f == NULL_I64;
+        i64 li = 0, ri = -1;
+        if (!none) {
+            // last row of the key's block: gallop, then binary search, on "same key tuple as row f"
+            i64 lo = f, step = 1;
+            while (lo + step < rl && same_tuple(right, f, right, lo + step)) { lo += step; step <<= 1; }
+            i64 hi = lo + step < rl ? lo + step : rl;          // row lo is in the block, row hi (if < rl) is not
+            while (lo + 1 < hi) { const i64 mid = lo + (hi - lo) / 2; if (same_tuple(right, f, right, mid)) lo = mid; else hi = mid; }
+            const i64 n = lo - f + 1;
+            const i32 a = ld_stream(wlo + i), b = ld_stream(whi + i);
+            li = jtype == 0 ? bin_r(a, rtime, f, n) : bin_l(a, rtime, f, n);
+            ri = bin_r(b, rtime, f, n);
+            if (__ldg(rtime + li) > b || (jtype == 1 && __ldg(rtime + ri) < a)) none = true;
+        }
+        if constexpr (OP == W_COUNT) { ((i64 *)out)[i] = none ? 0 : (ri - li + 1 > 0 ? ri - li + 1 : 0); }
+        else if constexpr (Elem<V>::kind == K_F64) {
+            f64 acc = null_f64();
+            if (!none) {
+                acc = OP == W_SUM ? 0.0 : (OP == W_MIN ? bits_f64(0x7FF0000000000000ULL) : null_f64());
+                for (i64 x = li; x <= ri; x++) {
+                    const f64 v = __ldg(val + x);
+                    if (OP == W_SUM) acc = (isnan64(acc) || isnan64(v)) ? null_f64() : acc + v;
+                    else if (OP == W_MIN) acc = OpMinF()(acc, v);
+                    else acc = OpMaxF()(acc, v);
+                }
+            }
+            ((f64 *)out)[i] = acc;
+        } else {
+            i64 acc = NULL_I64;
+            if (!none) {
+                acc = OP == W_SUM ? 0 : (OP == W_MIN ? RFB_INF_I64 : NULL_I64);
+                for (i64 x = li; x <= ri; x++) {
+                    const i64 v = __ldg(val + x);
+                    if (OP == W_SUM) acc = (acc == NULL_I64 || v == NULL_I64) ? NULL_I64 : (i64)((u64)acc + (u64)v);
+                    else if (OP == W_MIN) acc = OpMinI()(acc, v);
+                    else acc = OpMaxI()(acc, v);
+                }
+            }
+            ((i64 *)out)[i] = acc;
+        }
+    }
+}
+
+template <typename V>
+int window_launch(rfb_ctx_t *ctx, int op, KeyCols r, i64 rl, const i32 *rtime, const void *val, const i64 *first, const i32 *wlo, const i32 *whi, i64 ll,
+                  int jtype, void *out) {
+    const int grid = rfb_grid_for(ctx, ll, THREADS, 4);
+    switch (op) {
+        case RFB_A_SUM: k_window_fold<W_SUM, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, wlo, whi, ll, jtype, out); break;
+        case RFB_A_MIN: k_window_fold<W_MIN, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, wlo, whi, ll, jtype, out); break;
+        case RFB_A_MAX: k_window_fold<W_MAX, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, wlo, whi, ll, jtype, out); break;
+        default: k_window_fold<W_COUNT, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, wlo, whi, ll, jtype, out); break;
+    }
+    RFB_CHECK_LAUNCH(ctx);
+    return RFB_OK;
+}
+}  // namespace
+
+extern "C" int rfb_window_join_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const *right_cols, const int32_t *right_time, int64_t right_len,
+                                   const int64_t *const *left_cols, int64_t left_len, const int32_t *win_lo, const int32_t *win_hi, int jtype,
+                                   int op, int val_type, const void *val, void *out) {
+    RFB_ARG(ctx && ncols >= 1 && ncols <= MAX_KEY_COLS && right_len >= 0 && left_len >= 0 && right_cols && left_cols && (jtype == 0 || jtype == 1) &&
+            ((win_lo && win_hi && out) || left_len == 0) && ((right_time && val) || right_len == 0), "rfb_window_join_dev");
+    const int vk = rfb_kind_of(val_type);
+    if (!(vk == K_I64 || vk == K_F64) || val_type == RFB_SYMBOL || !(op == RFB_A_SUM || op == RFB_A_MIN || op == RFB_A_MAX || op == RFB_A_COUNT)) {
+        rfb_set_error("window join: aggregate %d over value type %d (sum / min / max / count of I64-kind or F64 values)", op, val_type);
+        return RFB_ERR_TYPE;
+    }
+    if (left_len == 0) return RFB_OK;
+    void *buf;
+    int rc = rfb_ensure_aux2(ctx, (size_t)left_len * 8, &buf);
+    if (rc) return rc;
+    i64 *first = (i64 *)buf;
+    rc = rfb_find_rows_dev(ctx, ncols, right_cols, right_len, left_cols, left_len, first);
+    if (rc) return rc;
+    KeyCols r;
+    r.ncols = ncols;
+    for (int c = 0; c < ncols; c++) r.col[c] = right_cols[c];
+    if (vk == K_F64) return window_launch<f64>(ctx, op, r, right_len, right_time, val, first, win_lo, win_hi, left_len, jtype, out);
+    return window_launch<i64>(ctx, op, r, right_len, right_time, val, first, win_lo, win_hi, left_len, jtype, out);
+}

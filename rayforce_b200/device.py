@@ -373,6 +373,18 @@ class _Ops:
         self.sync()
         return out[:cnt.value]
 
+    def window_join(self, op, vt, val, right_cols, right_time, left_cols, win_lo, win_hi, jtype):
+        """window-join / window-join1 aggregate over a right table ordered by (key, time) -> (tensor[len(left)], type)"""
+        nr, nl = right_cols[0].shape[0], left_cols[0].shape[0]
+        ot = capi.I64 if op == capi.A_COUNT else vt
+        out = self._empty(nl, ot)
+        r = (C.c_void_p * len(right_cols))(*[_dptr(c) for c in right_cols])
+        l = (C.c_void_p * len(left_cols))(*[_dptr(c) for c in left_cols])
+        check(self.lib.rfb_window_join_dev(self.h, len(right_cols), r, _dptr(right_time), nr, l, nl, _dptr(win_lo), _dptr(win_hi), jtype, op, vt,
+                                           _dptr(val), _dptr(out)))
+        self.sync()
+        return out, ot
+
     def group_sum_count(self, key_type, keys, val, max_groups, cmp_op=None, pred_type=None, pred=None, k=None):
         """fused select {s: (sum v) c: (count v) from t by k [where (cmp p k)]} -> (keys, sums, counts) tensors"""
         n = keys.shape[0]

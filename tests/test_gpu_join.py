@@ -137,3 +137,32 @@ def test_distinct_sparse_range_is_declined(ctx, oracle):
     got, gt = ops.value(ops.call("ray_distinct", d))
     assert gt == ob.I64 and np.array_equal(got, oracle.distinct(keys % 1000))
     ops.drop(x, d)
+
+
+@pytest.mark.parametrize("ncols", [1, 2])
+@pytest.mark.parametrize("vt", [ob.I64, ob.F64])
+@pytest.mark.parametrize("nl,nr,span", [(1, 1, 10), (300, 50, 5_000), (50_000, 400_000, 10_000_000), (200_003, 100_000, 1_000_000)])
+def test_window_join(ctx, oracle, ncols, vt, nl, nr, span):
+    """window-join / window-join1 aggregates (core/join.c:358-485, core/index.c:3287-3346, core/aggr.c:131-160) against the oracle,
+    which is pinned against the reference's own window-join through Rayfall: keys missing on either side, windows without rows,
+    blocks of one row, nulls in the value column (sticky sum)"""
+    from rayforce_b200 import capi
+    from tests.util import rng_col, same_f64
+    r = np.random.default_rng(nl + nr + ncols)
+    lcols = [r.integers(0, 30 + c, nl).astype(np.int64) for c in range(ncols)]
+    rcols = [r.integers(0, 33 + c, nr).astype(np.int64) for c in range(ncols)]
+    lt = np.sort(r.integers(0, span, nl)).astype(np.int32)
+    rt = r.integers(0, span, nr).astype(np.int32)
+    val = rng_col(vt, nr, 7, null_frac=0.01, lo=-50, hi=50)
+    if vt == ob.F64:
+        val = np.round(val * 4) / 4
+    order = np.lexsort([rt] + rcols[::-1])           # the right table ordered by (key tuple, time), as ray_window_join's xasc leaves it
+    rcols, rt, val = [c[order] for c in rcols], rt[order], val[order]
+    wlo, whi = (lt - span // 50).astype(np.int32), (lt + span // 40).astype(np.int32)
+    d = dict(r=[dev(c) for c in rcols], rt=dev(rt), l=[dev(c) for c in lcols], lo=dev(wlo), hi=dev(whi), v=dev(val))
+    for jt in (0, 1):
+        for op, aop in ((ob.SUM, capi.A_SUM), (ob.MIN, capi.A_MIN), (ob.MAX, capi.A_MAX), (ob.COUNT, capi.A_COUNT)):
+            want, wt = oracle.window_aggr(op, vt, val, rcols, rt, lcols, wlo, whi, jt)
+            got, gt = ctx.window_join(aop, vt, d["v"], d["r"], d["rt"], d["l"], d["lo"], d["hi"], jt)
+            assert gt == wt, (op, jt)
+            assert same_f64(host(got), want) if wt == ob.F64 else np.array_equal(host(got), want), (op, jt)
