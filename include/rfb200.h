@@ -296,7 +296,8 @@ int rfb_distinct_i64_dev(rfb_ctx_t *ctx, const int64_t *keys, int64_t n, int64_t
  * rows form one block.  For left row i: the rows of its key's block inside the window [win_lo[i], win_hi[i]] on the 4-byte time
  * column (jtype 0 = window-join: from the last row at or before win_lo; jtype 1 = window-join1: from the first row at or after
  * it) are folded with the GROUPED aggregate: op RFB_A_SUM (sticky null) / MIN / MAX over I64-kind or F64 values -> out[i] of
- * the value type, RFB_A_COUNT -> I64; no block or no row in the window -> null (count: 0). */
+ * the value type, RFB_A_COUNT -> I64, RFB_A_AVG -> F64 (sum of the non-null values in row order / their count); no block or
+ * no row in the window -> null (count: 0). */
 int rfb_window_join_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const *right_cols, const int32_t *right_time, int64_t right_len,
                         const int64_t *const *left_cols, int64_t left_len, const int32_t *win_lo, const int32_t *win_hi, int jtype,
                         int op, int val_type, const void *val, void *out);

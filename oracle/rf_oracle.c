@@ -927,8 +927,8 @@ int rfo_window_aggr(int op, int val_type, const void *val, const int32_t *rtime,
                     const int32_t *wlo, const int32_t *whi, int jtype, void *out, int *out_type) {
     int k = kind_of(val_type);
     if (!(k == K_I64 || k == K_F64)) return RFO_ERR_TYPE;
-    if (!(op == RFO_SUM || op == RFO_MIN || op == RFO_MAX || op == RFO_COUNT)) return RFO_ERR_TYPE;
-    *out_type = op == RFO_COUNT ? RFO_I64 : val_type;
+    if (!(op == RFO_SUM || op == RFO_MIN || op == RFO_MAX || op == RFO_COUNT || op == RFO_AVG)) return RFO_ERR_TYPE;
+    *out_type = op == RFO_COUNT ? RFO_I64 : (op == RFO_AVG ? RFO_F64 : val_type);
     for (i64 i = 0; i < ll; i++) {
         i64 li = 0, ri = 0;
         int none = first[i] == RFO_NULL_I64;
@@ -939,6 +939,16 @@ int rfo_window_aggr(int op, int val_type, const void *val, const int32_t *rtime,
             if (rtime[li] > whi[i] || (jtype == 1 && rtime[ri] < wlo[i])) none = 1;
         }
         if (op == RFO_COUNT) { ((i64 *)out)[i] = none ? 0 : ri - li + 1 > 0 ? ri - li + 1 : 0; continue; }
+        if (op == RFO_AVG) {   /* aggr_avg_partial's WINDOW branch (core/aggr.c:1545-1575) + the final division (:2060) */
+            f64 so = 0.0; i64 co = 0;
+            if (!none)
+                for (i64 x = li; x <= ri; x++) {
+                    if (k == K_I64) { i64 v = ((const i64 *)val)[x]; if (v != RFO_NULL_I64) { so += (f64)v; co++; } }
+                    else { f64 v = ((const f64 *)val)[x]; if (!isnan64(v)) { so += v; co++; } }
+                }
+            ((f64 *)out)[i] = co == 0 ? null_f64() : so / (f64)co;
+            continue;
+        }
         if (k == K_I64) {
             const i64 *v = (const i64 *)val; i64 a;
             if (none) a = RFO_NULL_I64;

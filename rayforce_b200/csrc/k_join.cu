@@ -223,7 +223,7 @@ extern "C" int rfb_asof_join_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const
 // a gallop + binary search for the last row whose key tuple still equals the first row's, then the reference's two searches
 // (indexr_bin / indexl_bin, core/aggr.c:39-72) and the grouped partial of the aggregate over the window's rows.
 namespace {
-enum { W_SUM = 0, W_MIN = 1, W_MAX = 2, W_COUNT = 3 };
+enum { W_SUM = 0, W_MIN = 1, W_MAX = 2, W_COUNT = 3, W_AVG = 4 };
 
 __device__ __forceinline__ i64 bin_r(i32 val, const i32 *__restrict__ t, i64 offset, i64 len) {   // last row with time <= val, else the first
     i64 left = 0, right = len - 1, idx = 0;
@@ -257,7 +257,16 @@ k_window_fold(KeyCols right, i64 rl, const i32 *__restrict__ rtime, const V *__r
             if (__ldg(rtime + li) > b || (jtype == 1 && __ldg(rtime + ri) < a)) none = true;
         }
         if constexpr (OP == W_COUNT) { ((i64 *)out)[i] = none ? 0 : (ri - li + 1 > 0 ? ri - li + 1 : 0); }
-        else if constexpr (Elem<V>::kind == K_F64) {
+        else if constexpr (OP == W_AVG) {      // f64 sum of the window's non-null values in row order / their count (core/aggr.c:1545-1575, :2060)
+            f64 so = 0.0;
+            i64 co = 0;
+            if (!none)
+                for (i64 x = li; x <= ri; x++) {
+                    const V v = __ldg(val + x);
+                    if (!Elem<V>::is_null(v)) { so = __dadd_rn(so, (f64)v); co++; }
+                }
+            ((f64 *)out)[i] = co == 0 ? null_f64() : __ddiv_rn(so, (f64)co);
+        } else if constexpr (Elem<V>::kind == K_F64) {
             f64 acc = null_f64();
             if (!none) {
                 acc = OP == W_SUM ? 0.0 : (OP == W_MIN ? bits_f64(0x7FF0000000000000ULL) : null_f64());
@@ -293,6 +302,7 @@ int window_launch(rfb_ctx_t *ctx, int op, KeyCols r, i64 rl, const i32 *rtime, c
         case RFB_A_SUM: k_window_fold<W_SUM, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, wlo, whi, ll, jtype, out); break;
         case RFB_A_MIN: k_window_fold<W_MIN, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, wlo, whi, ll, jtype, out); break;
         case RFB_A_MAX: k_window_fold<W_MAX, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, wlo, whi, ll, jtype, out); break;
+        case RFB_A_AVG: k_window_fold<W_AVG, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, wlo, whi, ll, jtype, out); break;
         default: k_window_fold<W_COUNT, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, wlo, whi, ll, jtype, out); break;
     }
     RFB_CHECK_LAUNCH(ctx);
@@ -306,8 +316,8 @@ extern "C" int rfb_window_join_dev(rfb_ctx_t *ctx, int ncols, const int64_t *con
     RFB_ARG(ctx && ncols >= 1 && ncols <= MAX_KEY_COLS && right_len >= 0 && left_len >= 0 && right_cols && left_cols && (jtype == 0 || jtype == 1) &&
             ((win_lo && win_hi && out) || left_len == 0) && ((right_time && val) || right_len == 0), "rfb_window_join_dev");
     const int vk = rfb_kind_of(val_type);
-    if (!(vk == K_I64 || vk == K_F64) || val_type == RFB_SYMBOL || !(op == RFB_A_SUM || op == RFB_A_MIN || op == RFB_A_MAX || op == RFB_A_COUNT)) {
-        rfb_set_error("window join: aggregate %d over value type %d (sum / min / max / count of I64-kind or F64 values)", op, val_type);
+    if (!(vk == K_I64 || vk == K_F64) || val_type == RFB_SYMBOL || !(op == RFB_A_SUM || op == RFB_A_MIN || op == RFB_A_MAX || op == RFB_A_COUNT || op == RFB_A_AVG)) {
+        rfb_set_error("window join: aggregate %d over value type %d (sum / min / max / count / avg of I64-kind or F64 values)", op, val_type);
         return RFB_ERR_TYPE;
     }
     if (left_len == 0) return RFB_OK;

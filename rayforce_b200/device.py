@@ -376,7 +376,7 @@ class _Ops:
     def window_join(self, op, vt, val, right_cols, right_time, left_cols, win_lo, win_hi, jtype):
         """window-join / window-join1 aggregate over a right table ordered by (key, time) -> (tensor[len(left)], type)"""
         nr, nl = right_cols[0].shape[0], left_cols[0].shape[0]
-        ot = capi.I64 if op == capi.A_COUNT else vt
+        ot = capi.I64 if op == capi.A_COUNT else (capi.F64 if op == capi.A_AVG else vt)
         out = self._empty(nl, ot)
         r = (C.c_void_p * len(right_cols))(*[_dptr(c) for c in right_cols])
         l = (C.c_void_p * len(left_cols))(*[_dptr(c) for c in left_cols])

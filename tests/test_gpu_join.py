@@ -161,7 +161,7 @@ def test_window_join(ctx, oracle, ncols, vt, nl, nr, span):
     wlo, whi = (lt - span // 50).astype(np.int32), (lt + span // 40).astype(np.int32)
     d = dict(r=[dev(c) for c in rcols], rt=dev(rt), l=[dev(c) for c in lcols], lo=dev(wlo), hi=dev(whi), v=dev(val))
     for jt in (0, 1):
-        for op, aop in ((ob.SUM, capi.A_SUM), (ob.MIN, capi.A_MIN), (ob.MAX, capi.A_MAX), (ob.COUNT, capi.A_COUNT)):
+        for op, aop in ((ob.SUM, capi.A_SUM), (ob.MIN, capi.A_MIN), (ob.MAX, capi.A_MAX), (ob.COUNT, capi.A_COUNT), (ob.AVG, capi.A_AVG)):
             want, wt = oracle.window_aggr(op, vt, val, rcols, rt, lcols, wlo, whi, jt)
             got, gt = ctx.window_join(aop, vt, d["v"], d["r"], d["rt"], d["l"], d["lo"], d["hi"], jt)
             assert gt == wt, (op, jt)

@@ -520,7 +520,7 @@ def test_window_join_aggregates_through_rayfall(oracle, reference, nl, nr, lkeys
     reference.eval("(set wj_iv (map-left + [-2000 3000] (at wj_trades 'Time)))")
     order = np.lexsort((rt, rs))                       # xasc [Sym Time]: stable
     for fn, jt in (("window-join", 0), ("window-join1", 1)):
-        for name, op in (("min", ob.MIN), ("max", ob.MAX), ("sum", ob.SUM), ("count", ob.COUNT)):
+        for name, op in (("min", ob.MIN), ("max", ob.MAX), ("sum", ob.SUM), ("count", ob.COUNT), ("avg", ob.AVG)):
             got = reference.to_numpy(reference.eval("(at (%s [Sym Time] wj_iv wj_trades wj_quotes {r: (%s Bid)}) 'r)" % (fn, name)))[0]
             want, wt = oracle.window_aggr(op, vt, bid[order], [rs[order]], rt[order], [ls], lt - 2000, lt + 3000, jt)
             assert same_f64(want, got) if wt == ob.F64 else np.array_equal(want, got), (fn, name)
