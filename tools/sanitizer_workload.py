@@ -79,6 +79,15 @@ ctx.stddev(capi.I64, x)
 ctx.stddev(capi.F64, f)
 ctx.find_rows([k, y], [k, x])
 ctx.inner_join([kw], [kw])
+# asof / window joins (right side ordered by key, time), distinct
+order = np.lexsort((r.integers(0, 10_000, n), k.cpu().numpy()))
+rk, rtime = dev(k.cpu().numpy()[order]), dev(np.sort(r.integers(0, 10_000, n)).astype(np.int64))
+ctx.asof_join([rk], capi.I64, rtime, [k], dev(r.integers(0, 10_000, n).astype(np.int64)))
+rt32 = dev(np.sort(r.integers(0, 10_000, n)).astype(np.int32))
+wlo = dev(r.integers(0, 9_000, n).astype(np.int32))
+for op in (capi.A_SUM, capi.A_MIN, capi.A_COUNT, capi.A_AVG):
+    ctx.window_join(op, capi.I64, x, [dev(np.sort(k.cpu().numpy()))], rt32, [k], wlo, wlo, 0)
+ctx.distinct(k)
 ctx.sort(capi.I64, x)
 ctx.sort(capi.F64, f, True)
 h = r.integers(-1000, 1000, 2_000_000).astype(np.int64)
