@@ -524,3 +524,26 @@ def test_window_join_aggregates_through_rayfall(oracle, reference, nl, nr, lkeys
             got = reference.to_numpy(reference.eval("(at (%s [Sym Time] wj_iv wj_trades wj_quotes {r: (%s Bid)}) 'r)" % (fn, name)))[0]
             want, wt = oracle.window_aggr(op, vt, bid[order], [rs[order]], rt[order], [ls], lt - 2000, lt + 3000, jt)
             assert same_f64(want, got) if wt == ob.F64 else np.array_equal(want, got), (fn, name)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_join_pins_randomized(oracle, reference, seed):
+    """randomized shapes for the row-matching pins: 1-3 key columns, tiny to mid sizes, low cardinality (many duplicate keys and
+    times), keys missing on either side"""
+    r = np.random.default_rng(seed)
+    nb, np_ = int(r.integers(1, 3000)), int(r.integers(1, 3000))
+    nc, card = int(r.integers(1, 4)), int(r.integers(1, 12))
+    b = [r.integers(0, card, nb).astype(np.int64) for _ in range(nc)]
+    p = [r.integers(0, card + 2, np_).astype(np.int64) for _ in range(nc)]
+    bt, pt = np.sort(r.integers(0, 50, nb)).astype(np.int64), r.integers(-5, 60, np_).astype(np.int64)
+    assert np.array_equal(oracle.asof_join(b, ob.I64, bt, p, pt), reference.asof_index(p, ob.I64, pt, b, bt))
+    if nc >= 2:
+        assert np.array_equal(oracle.find_rows(b, p), reference.join_index(p, b))
+    else:
+        ids = oracle.find_rows(b, p)
+        assert np.array_equal(ids, reference.find(b[0], p[0]))
+        assert np.array_equal((ids != ob.NULL_I64).astype(np.uint8), reference.isin(p[0], b[0]).astype(np.uint8))
+        v = reference.vec(ob.I64, b[0])
+        got = reference.to_numpy(reference.call1("ray_distinct", v))[0]
+        reference.drop(v)
+        assert np.array_equal(oracle.distinct(b[0]), got)
