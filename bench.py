@@ -114,20 +114,57 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------- CPU reference arm
 
+def mem_available_gb() -> float:
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def cpu_sample_rows(full_rows: int, runs: int) -> int:
+    """The CPU arm runs the FULL row count when the host has the memory for the reference's intermediates (8 B column + 1 B
+    mask + 8 B ids and 8 B gathered values per selected row: ~17 GB per 1e9 rows at 50 % selectivity) and the run
+    stays within a few minutes (~4 s per 1e9 rows on 16 cores); otherwise a prefix of 1e8 rows, scaled by the metric's unit."""
+    need_gb = full_rows * 30e-9 + 8
+    if mem_available_gb() >= need_gb and runs * full_rows * 4.5e-9 <= 240:
+        return full_rows
+    return min(full_rows, CPU_SAMPLE_ROWS)
+
+
+def fill_splitmix_host(dst: np.ndarray, seed: int, first_row: int, modulus: int):
+    """dst[i] = splitmix64(seed, first_row + i) mod modulus, in place, numpy in slices on a few threads"""
+    n = dst.shape[0]
+    step = 1 << 24
+
+    def work(lo):
+        hi = min(n, lo + step)
+        dst[lo:hi] = splitmix_column(seed, first_row + lo, hi - lo, modulus)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        list(ex.map(work, range(0, n, step)))
+
+
 def cpu_reference_run(steps: int, warmup: int, sample_rows: int = CPU_SAMPLE_ROWS):
-    """Times the reference's own CPU path on a bounded sample: the Rayfall query
-    (select {s: (sum x) from: t where: (< x k)}) through the reference evaluator compiled from its sources
-    (oracle/_ref/librayforce_ref.so, all host cores).  Falls back to the single-threaded C port (oracle/) when the
-    compiled reference is not present.  -> dict(value, seconds_per_step, kind, cores, sample, check)"""
+    """Times the reference's own CPU path: the Rayfall query (select {s: (sum x) from: t where: (< x k)}) through the
+    reference evaluator compiled from its sources (oracle/_ref/librayforce_ref.so, all host cores).  Falls back to the
+    single-threaded C port (oracle/) when the compiled reference is not present.
+    -> dict(value, seconds_per_step, kind, cores, sample, check)"""
     from oracle import bindings as ob
-    col = splitmix_column(SEED, 0, sample_rows, MODULUS)
-    expect_sum = int(col[col < K_CONST].sum(dtype=np.int64))
     times = []
     if ob.Reference.available():
         R = ob.Reference.get()
         o = R.eval("(set x (til %d))" % sample_rows)
         dst = np.frombuffer((C.c_char * (sample_rows * 8)).from_address(o + 16), dtype=np.int64)
-        dst[:] = col
+        fill_splitmix_host(dst, SEED, 0, MODULUS)
+        expect_sum = 0
+        for lo in range(0, sample_rows, 1 << 26):
+            c = dst[lo:lo + (1 << 26)]
+            expect_sum = (expect_sum + int(c[c < K_CONST].sum(dtype=np.int64))) & 0xFFFFFFFFFFFFFFFF
+        if expect_sum >= 1 << 63:
+            expect_sum -= 1 << 64
         R.eval("(set t (table [x] (list x)))")
         q = "(select {s: (sum x) from: t where: (< x %d)})" % K_CONST
         got = None
@@ -141,9 +178,13 @@ def cpu_reference_run(steps: int, warmup: int, sample_rows: int = CPU_SAMPLE_ROW
             if i >= warmup:
                 times.append(dt)
         kind, cores = "reference", R.cores
+        del dst
         R.eval("(set t 0)")
         R.eval("(set x 0)")
     else:
+        sample_rows = min(sample_rows, CPU_SAMPLE_ROWS)
+        col = splitmix_column(SEED, 0, sample_rows, MODULUS)
+        expect_sum = int(col[col < K_CONST].sum(dtype=np.int64))
         O = ob.Oracle()
         got = None
         for i in range(max(1, warmup // 3) + max(1, steps // 3)):
@@ -159,17 +200,18 @@ def cpu_reference_run(steps: int, warmup: int, sample_rows: int = CPU_SAMPLE_ROW
     if got != expect_sum:
         raise SystemExit("CPU reference arm produced %d, expected %d" % (got, expect_sum))
     sec = statistics.mean(times)
+    what = "the FULL %d-row column" % sample_rows if sample_rows >= 1_000_000_000 else "a %d-row prefix of the same splitmix64 column (scaled by rows/s)" % sample_rows
     return {"value": sample_rows / sec / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": "%d-row prefix of the same splitmix64 column, Rayfall select through the reference evaluator, "
-                      "mean of %d runs (best %.1f ms)" % (sample_rows, len(times), min(times) * 1e3),
-            "seconds_per_step": sec}
+            "sample": "%s, Rayfall select through the reference evaluator, mean of %d runs (best %.1f ms); host MemAvailable %.0f GB"
+                      % (what, len(times), min(times) * 1e3, mem_available_gb()),
+            "seconds_per_step": sec, "rows": sample_rows}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps, args.warmup)
+    r = cpu_reference_run(args.steps, args.warmup, cpu_sample_rows(args.rows, args.steps + args.warmup))
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
@@ -203,6 +245,117 @@ def workload_config(args, world):
             "rows_per_gpu": args.rows, "global_rows": args.rows * world, "selectivity": 0.5,
             "l2_policy": "inputs (8 GB per GPU) far exceed the 126 MB L2; no flush needed",
             "merge": "none (1 GPU)" if world == 1 else "one NCCL all-reduce of (nonnull, sum) per step"}
+
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE configs 3, 4, 5
+
+def peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_extra_configs(ctx, stream, dev, n, rank, world, K, W):
+    """BASELINE.json configs[2..4] on the same box, same process, device-resident, each timed with CUDA events around K steps
+    (max over ranks): fp64 (a*b+c) -> avg; group-by 1e5 int32 keys sum/count; filter + group-by + sum sharded by row range with
+    the NCCL merge.  A step of the group-by configs is the whole rfb_group_sum_count_dev call (sample, scatter, accumulate,
+    first rows, emit, its host synchronisations) — `call_ms`, not one kernel.  -> dict for the JSON line's "configs" key."""
+    import torch
+    import torch.distributed as dist
+    from rayforce_b200 import capi, shard
+    peak, _ = peak_hbm()
+    out = {}
+    first_row = rank * n
+
+    def timed(step):
+        for _ in range(max(W, 3)):
+            res = step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = ctx.launches
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(stream)
+        for _ in range(K):
+            res = step()
+        e.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = s.elapsed_time(e) / K
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, res, (ctx.launches - l0) // K
+
+    def entry(workload, ms, alg_bytes_per_gpu, launches, result, merge):
+        gbs = alg_bytes_per_gpu / (ms * 1e-3) / 1e9
+        return {"workload": workload, "value": n * world / (ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms, "steps": K,
+                "rows_per_gpu": n, "n_gpus": world, "gpu_launches_per_step": int(launches),
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                             "algorithmic_bytes_per_step_per_gpu": alg_bytes_per_gpu, "timed": "whole call (all its kernels and host syncs)"},
+                "merge": merge, "result": result}
+
+    # ---- config 3: (avg (+ (* a b) c)) over three F64 columns, one fused kernel (24 B/row)
+    with torch.cuda.stream(stream):
+        a, b, c = (torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3))
+    for col, seed in ((a, 1), (b, 2), (c, 3)):
+        ctx.fill_splitmix(capi.F64, col, n, shifted_seed(seed, first_row), 1 << 20, 0, 0, float(1 << 20))
+    ctx.sync()
+
+    def step_fma():
+        r = ctx.fma_fold(capi.F_SUM | capi.F_CNT, a, b, c, n)
+        if world == 1:
+            return r.sum / r.nonnull
+        tot = shard.allgather_sum_f64(r.sum, dev)            # fp64 partials added in rank order: independent of the reduction tree
+        cnt = torch.tensor([r.nonnull], dtype=torch.int64, device=dev)
+        dist.all_reduce(cnt)
+        return tot / int(cnt.item())
+    ms, avg, launches = timed(step_fma)
+    assert 0.74 < avg < 0.76, avg                             # E[a*b + c] = 1/4 + 1/2 for uniform [0, 1) columns
+    out["fma_avg"] = entry("(avg (+ (* a b) c)): three F64 columns, splitmix64 / 2^20 in [0, 1), fused k_fma_fold", ms, 24 * n, launches,
+                           {"avg": avg}, "none" if world == 1 else "all-gather of (sum, count) partials, added in rank order")
+    del a, b, c
+
+    # ---- config 4 / 5: group-by 1e5 int32 keys, sum + count of an i64 column; config 5 adds the filter and the multi-GPU merge
+    with torch.cuda.stream(stream):
+        k = torch.empty(n, dtype=torch.int32, device=dev)
+        v = torch.empty(n, dtype=torch.int64, device=dev)
+    ctx.fill_splitmix(capi.I32, k, n, shifted_seed(7, first_row), 100_000, 0, 0)
+    ctx.fill_splitmix(capi.I64, v, n, shifted_seed(9, first_row), 1 << 20, 0, 0)
+    ctx.sync()
+    regroup = shard.gpu_regroup(ctx)
+
+    def grouped(filtered):
+        def step():
+            if filtered:
+                lk, ls, lc = ctx.group_sum_count(capi.I32, k, v, 100_000, capi.LT, capi.I64, v, 1 << 19)
+            else:
+                lk, ls, lc = ctx.group_sum_count(capi.I32, k, v, 100_000)
+            if world > 1:
+                with torch.cuda.stream(stream):
+                    return shard.merge_group_partials(lk, ls, lc, regroup)
+            return lk, ls, lc
+        return step
+    merge = "none" if world == 1 else "one all-gather of every GPU's (key, sum, count) rows + re-group on every rank (NCCL)"
+    with torch.cuda.stream(stream):
+        ms, (gk, gs, gc), launches = timed(grouped(False))
+        groups, rows, total = int(gk.shape[0]), int(gc.sum().item()), int(gs.sum().item())
+    assert groups == 100_000 and rows == n * world, (groups, rows)
+    out["groupby_1e5"] = entry("select {s: (sum v) c: (count v) from t by k}: 1e5 int32 keys (splitmix64 mod 1e5), i64 values < 2^20", ms, 12 * n,
+                               launches, {"groups": groups, "rows": rows, "sum_of_sums": total}, merge)
+    with torch.cuda.stream(stream):
+        ms, (gk, gs, gc), launches = timed(grouped(True))
+        groups, rows, total = int(gk.shape[0]), int(gc.sum().item()), int(gs.sum().item())
+    assert groups == 100_000 and 0.49 * n * world < rows < 0.51 * n * world, (groups, rows)
+    out["filter_groupby_sharded"] = entry("select {s: (sum v) c: (count v) from t by k where (< v 2^19)}: rows sharded by row range over the GPUs", ms,
+                                          12 * n, launches, {"groups": groups, "rows_selected": rows, "sum_of_sums": total}, merge)
+    del k, v
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -327,6 +480,10 @@ def run_gpu_arm(args):
                "ms_per_step": e2e_ms / Ke, "launches_per_step": (ctx.launches - le0) // Ke,
                "api": "rfb_filter_fold_host (pinned host column -> chunked cudaMemcpyAsync + fused kernel -> host result)"}
         del hx, hx_t
+    configs = None
+    if not args.no_configs:
+        del x
+        configs = run_extra_configs(ctx, stream, dev, n, rank, world, max(1, min(K, args.config_steps)), W)
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
@@ -350,11 +507,11 @@ def run_gpu_arm(args):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_scan_fold<i64,i64,SUM|CNT,pred,same-column,null-free predicate>",
                              "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": 8 * n, "peak_source": peak_src},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "configs": configs,
                 "result": {"rows_selected_nonnull": int(first[0]), "sum": int(first[1])}}
         if world == 1 and not args.no_cpu:
             try:
-                r = cpu_reference_run(steps=3, warmup=1)
+                r = cpu_reference_run(steps=3, warmup=1, sample_rows=cpu_sample_rows(n, 4))
                 line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as e:  # the checker is optional at bench time; say so rather than hide it
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
@@ -374,6 +531,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 3-5 (fma->avg, group-by, sharded filter+group-by)")
+    ap.add_argument("--config-steps", type=int, default=10, help="timed steps of each of the configs 3-5")
     ap.add_argument("--ncu-traffic", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)")
     args = ap.parse_args()

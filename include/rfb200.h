@@ -122,6 +122,7 @@ int64_t rfb_launch_count(rfb_ctx_t *ctx);       /* kernels launched through this
 int rfb_dev_alloc(rfb_ctx_t *ctx, size_t bytes, void **dptr);
 int rfb_dev_free(rfb_ctx_t *ctx, void *dptr);
 int rfb_dev_memset(rfb_ctx_t *ctx, void *dptr, int byte, size_t bytes);
+int rfb_dev_mem_info(rfb_ctx_t *ctx, size_t *free_bytes, size_t *total_bytes);   /* cudaMemGetInfo of the context's device */
 int rfb_host_pin(void *p, size_t bytes);        /* cudaHostRegister: column payload stays where the host put it */
 int rfb_host_unpin(void *p);
 int rfb_host_alloc_pinned(size_t bytes, void **p);

@@ -84,6 +84,22 @@ int64_t rfb_ops_launches(void);       /* kernels launched so far (evidence that 
  * Outside a scope every call ships its operands.  Bind begin/end around ray_select (core/query.c:607). */
 void rfb_ops_scope_begin(void);
 void rfb_ops_scope_end(void);
+/* Residency across queries.  With it on, the HBM image of a host vector that outlives the query (a table column, a global:
+ * refcount >= 2, allocated in the host's own heap) stays on the device after the scope ends and is found again by its
+ * (payload pointer, length, type) the next time an operator sees that vector — a column is shipped once, not once per query.
+ * This is only sound when the host reports every free and every in-place modification of its vectors:
+ *     rfb_ops_note_free(obj)    the object `obj` (header address) is being freed / its block reused / reallocated
+ *     rfb_ops_note_write(obj)   the object is about to be modified in place (copy-on-write hit with refcount 1, `and`/`or`
+ *                               folding into their first operand, a CPU body reusing an operand as its result)
+ * integration/rayforce_shim.c binds them to the reference's heap_free, heap_realloc, cow_obj, ray_and / ray_or and the CPU
+ * fallbacks of the wrapped math operators.  Both may be called from any host thread.  Without the hooks leave residency off
+ * (the default): every scope then starts cold.  budget_bytes <= 0 keeps the current budget (default: half the free HBM, or
+ * env RFB200_RESIDENT_MB).  out = {image hits, columns shipped, images forgotten through the hooks, resident MiB}. */
+void rfb_ops_set_residency(int on, int64_t budget_bytes);
+void rfb_ops_note_free(const void *obj);
+void rfb_ops_note_write(const void *obj);
+void rfb_ops_residency_stats(long out[4]);
+
 /* EXPERIMENTAL, env RFB200_LAZY=1: inside a scope, results of at least RFB200_LAZY_MIN bytes (default 32 MiB) stay on the
  * device; their host payload pages are protected and filled on the first CPU access (SIGSEGV handler) or at scope end.
  * out = {results left lazy, faulted in by a CPU access, dropped because the host had already freed them, filled at scope end}. */

@@ -107,6 +107,7 @@ SIGNATURES = {
     "rfb_dev_alloc": (_ci, [_vp, _sz, _P(_vp)]),
     "rfb_dev_free": (_ci, [_vp, _vp]),
     "rfb_dev_memset": (_ci, [_vp, _vp, _ci, _sz]),
+    "rfb_dev_mem_info": (_ci, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
     "rfb_host_pin": (_ci, [_vp, _sz]),
     "rfb_host_unpin": (_ci, [_vp]),
     "rfb_host_alloc_pinned": (_ci, [_sz, _P(_vp)]),

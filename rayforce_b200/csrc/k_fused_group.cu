@@ -1,6 +1,7 @@
 // k_fused_group.cu — rfb_group_sum_count_dev (sm_100a): `select {s: (sum v) c: (count v) from t by k [where ...]}` fused, never
 // materialising group ids.
 #include "rfb_group.cuh"
+#include "rfb_tma.cuh"
 
 // ------------------------------------------------------------------ fused dense group-by: sum + count [+ where]
 //
@@ -16,7 +17,15 @@
 // (ATOMS.ADD) but implements 64-bit shared adds as a compare-and-swap loop (ATOMS.CAST.SPIN.64).  The 64-bit wrapping
 // sum is kept exact by carrying: the returning add on the low word tells the one row that wrapped it to add 1 to the high word.
 
+// k_hash_group.cu: the same query on a sparse key domain (shared-memory open-addressing tables + device-wide merge)
+int rfb_hash_group_sum_count(rfb_ctx_t *ctx, int key_type, const void *keys, const int64_t *val, int64_t n, int cmp_op, int pred_type,
+                             const void *pred, const rfb_scalar_t *k, int64_t max_groups, int64_t *out_keys, int64_t *out_sums,
+                             int64_t *out_counts, int64_t *groups);
+
 namespace {
+
+constexpr int RFB_SPARSE_DOMAIN = 1;              // internal: the dense strategies decline, the caller takes the hash path
+constexpr i64 DENSE_RANGE_MAX = 1ll << 28;        // largest key range addressed directly
 
 struct Accums {
     u64 *first_row;   // [range]
@@ -275,8 +284,9 @@ __global__ void __launch_bounds__(THREADS) k_mod_remap(Accums gmod, i64 kmin, i6
 // has already passed its cursor atomic and publishes before it waits for anything itself, so the wait cannot deadlock.
 constexpr int PB_LOG = 16, PB = 1 << PB_LOG;   // rows per block; a multiple of PTILE, so an accumulate unit never straddles blocks
 
+constexpr int PCUR_STRIDE = 32;   // u32 words between two bucket cursors: one cache line each (atomics on one line serialise in its L2 slice)
 struct PartStore {
-    u32 *cursor;       // [MAX_PARTS] rows per bucket
+    u32 *cursor;       // [MAX_PARTS * PCUR_STRIDE] rows per bucket at [b * PCUR_STRIDE]
     u32 *next_block;   // blocks handed out so far
     u32 *bt;           // [MAX_PARTS][bt_stride] physical block + 1 (0 = not yet allocated)
     u32 bt_stride;
@@ -353,7 +363,7 @@ k_part_scatter(FS fs, const i64 *__restrict__ val, i64 n, bool vec, PartStore ps
             // reserve [start, start + c) of bucket `tid`, allocate the block(s) that begin inside the run, look up the two
             // blocks the run can touch
             if (c) {
-                start = atomicAdd(&ps.cursor[tid], c);
+                start = atomicAdd(&ps.cursor[tid * PCUR_STRIDE], c);
                 const u32 b0 = start >> PB_LOG, b1 = (start + c - 1) >> PB_LOG;
                 u32 *row = ps.bt + (size_t)tid * ps.bt_stride;
                 if ((start & (PB - 1)) == 0) { phys0 = atomicAdd(ps.next_block, 1u) + 1; st_relaxed_u32(row + b0, phys0); }
@@ -437,7 +447,7 @@ k_part_accum(PartStore ps, int P, i64 kbase, i64 kmin, Accums ga) {
     const u32 bucket0 = (u32)(((u64)kbase >> KP_LOG) & 255u);
     u32 c = 0, units = 0, incl = 0;
     if (tid < MAX_PARTS) {
-        c = tid < P ? ps.cursor[(bucket0 + tid) & 255u] : 0;
+        c = tid < P ? ps.cursor[((bucket0 + tid) & 255u) * PCUR_STRIDE] : 0;
         s_cnt[tid] = c;
         units = (c + PTILE - 1) / PTILE;
         incl = units;
@@ -506,30 +516,6 @@ k_part_accum(PartStore ps, int P, i64 kbase, i64 kmin, Accums ga) {
 constexpr int AT = 1024, ASTAGES = 3;
 struct __align__(16) AccumStage { u64 val[PTILE]; u16 slot[PTILE]; };
 
-__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
-                 "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-
 __global__ void __launch_bounds__(AT, 1)
 k_part_accum_tma(PartStore ps, int P, i64 kbase, i64 kmin, Accums ga) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -547,7 +533,7 @@ k_part_accum_tma(PartStore ps, int P, i64 kbase, i64 kmin, Accums ga) {
     }
     u32 c = 0, units = 0, incl = 0;
     if (tid < MAX_PARTS) {
-        c = tid < P ? ps.cursor[(bucket0 + tid) & 255u] : 0;
+        c = tid < P ? ps.cursor[((bucket0 + tid) & 255u) * PCUR_STRIDE] : 0;
         s_cnt[tid] = c;
         units = (c + PTILE - 1) / PTILE;
         incl = units;
@@ -619,6 +605,367 @@ k_part_accum_tma(PartStore ps, int P, i64 kbase, i64 kmin, Accums ga) {
     if (dirty) sacc_flush(a, KP, (i64)((u64)kbase + (u64)p * KP - (u64)kmin), ga);
 }
 
+
+// ---- accumulate, strategy 2n ("narrow"): the same partition + accumulate idea for key ranges of at most 32 partitions, which
+// is what the 1e5-key workload needs.  Three things differ from strategy 2:
+//   * ranking by warp ballots instead of returning shared atomics: a row's rank among the rows of its warp step that go to the
+//     same partition comes from five ballots over the partition bits; only the first lane of each such group touches the
+//     partition's counter (distinct addresses -> one conflict-free atomic per warp step instead of 32 conflicting ones)
+//   * records are PACKED: a 32-bit record holds the slot (KPL bits) and the value (32 - KPL bits) when the value fits, a
+//     64-bit record the slot and a 48-bit signed value: 4 or 8 bytes per row instead of 10, written once and read once
+//   * rows whose value does not fit the record (nulls included) are EXCEPTIONS: appended to a small side list of (key, value)
+//     pairs that a tiny kernel folds with L2 atomics.  A row sample decides which record format is tried; when the guess was
+//     wrong (the list overflows, or the keys span more than 32 partitions) the pass aborts early and the caller falls back.
+constexpr int NP = 32;                          // partitions of the narrow path
+#ifndef RFB_MS_T
+#define RFB_MS_T 256
+#define RFB_MS_R 8
+#define RFB_MS_CTAS 4
+#endif
+constexpr int MS_T = RFB_MS_T, MS_R = RFB_MS_R, MS_CTAS = RFB_MS_CTAS, MS_TILE = MS_T * MS_R, MS_WARPS = MS_T / 32;
+static_assert(MS_TILE <= PB, "a tile's run touches at most two blocks");
+
+template <typename REC, int KPL> struct RecFmt;
+template <int KPL> struct RecFmt<u32, KPL> {
+    static constexpr int VB = 32 - KPL;
+    __host__ __device__ static bool fits(i64 v) { return (u64)v < (1ull << VB); }
+    __device__ __forceinline__ static u32 pack(u32 slot, i64 v) { return (slot << VB) | (u32)v; }
+    __device__ __forceinline__ static u32 slot(u32 r) { return r >> VB; }
+    __device__ __forceinline__ static i64 val(u32 r) { return (i64)(r & ((1u << VB) - 1u)); }
+};
+template <int KPL> struct RecFmt<u64, KPL> {
+    static constexpr int VB = 48;
+    __host__ __device__ static bool fits(i64 v) { return (u64)v + (1ull << 47) < (1ull << 48); }
+    __device__ __forceinline__ static u64 pack(u32 slot, i64 v) { return ((u64)slot << 48) | ((u64)v & 0xFFFFFFFFFFFFull); }
+    __device__ __forceinline__ static u32 slot(u64 r) { return (u32)(r >> 48); }
+    __device__ __forceinline__ static i64 val(u64 r) { return (i64)(r << 16) >> 16; }
+};
+
+// Every tile adds to the cursor of every partition it holds rows for: ~25 atomics per 2048-row tile.  Atomics on one cache line
+// are serialised by the L2 slice that owns it (measured on B200: ~1.2 atomics/ns per line — with all cursors on one line the
+// whole scatter pass ran at the speed of that one slice), so every cursor gets its own 256 bytes.
+constexpr int CUR_STRIDE = 64;                  // u32 words between the cursors of two partitions
+struct RecStore {
+    u32 *cursor;       // [NP * CUR_STRIDE] rows per partition at [p * CUR_STRIDE]
+    u32 *next_block;   // blocks handed out so far
+    u32 *exc_count;    // exceptions appended so far (may run past exc_cap: then the pass is void)
+    u32 *bt;           // [NP][bt_stride] physical block + 1 (0 = not yet allocated)
+    u32 bt_stride;
+    u32 exc_cap;
+    void *rec;         // [blocks * PB] records
+    i64 *exc;          // [exc_cap][2] (key, value)
+};
+
+// ballot of (x & mask) != 0 over the warp.  Written in PTX so that the test stays one LOP3 with a predicate result (the
+// compiler's canonical form of the C expression is shift + and + compare: three ALU instructions per ballot instead of one)
+__device__ __forceinline__ u32 ballot_bits(u32 x, u32 mask) {
+    u32 r;
+    asm volatile("{\n.reg .pred p;\n.reg .b32 t;\nand.b32 t, %1, %2;\nsetp.ne.u32 p, t, 0;\nvote.sync.ballot.b32 %0, p, 0xffffffff;\n}" : "=r"(r) : "r"(x), "r"(mask));
+    return r;
+}
+
+// One tile of the scatter pass: ranking (ballots) -> barrier #1 (the tile's partition counts are final) -> every warp derives the
+// tile-local layout itself (a 32-lane scan, lane = partition) and stages its rows; warp 0 has posted the global reservations
+// of all partitions right after the barrier, so their latency hides behind the staging, and turns them into per-partition
+// output descriptors -> barrier #2 -> all threads write the staged tile out linearly (a byte per staged row names its
+// partition).  Staging area, counters and descriptors are double-buffered: no third barrier before the next tile starts.
+// The kernel takes FULL tiles of 16-byte aligned columns only (vector loads, no bounds tests in the hot loop); the rows past
+// the last full tile go through k_ms_tail, unaligned columns do not take the narrow path at all.
+template <typename FS, typename REC, int KPL>
+__global__ void __launch_bounds__(MS_T, MS_CTAS)
+k_ms_scatter(FS fs, const i64 *__restrict__ val, i64 tiles, RecStore rs, i64 *mm) {
+    typedef RecFmt<REC, KPL> F;
+    constexpr u32 KPN = 1u << KPL;
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    REC (*const s_rec)[MS_TILE] = (REC (*)[MS_TILE])s_dyn;                                   // [2][MS_TILE] staged records (dynamic: 64-bit records exceed 48 KB)
+    u8 (*const s_part)[MS_TILE] = (u8 (*)[MS_TILE])(s_dyn + 2 * MS_TILE * sizeof(REC));      // [2][MS_TILE] partition of every staged record
+    __shared__ u32 s_cnt[2][NP];
+    __shared__ u32 s_wb[MS_WARPS][NP];   // per warp: where its rows of each partition start in the tile's staging area
+    __shared__ uint4 s_desc[2][NP];      // per partition: {x: global - local index before the block boundary, y: first local index past it, z: global - local after it}
+    __shared__ u32 s_total[2];
+    __shared__ u32 s_abort;
+    __shared__ i64 red[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 lt_mask = (1u << lane) - 1u;
+    u32 cb[5];                           // lane L collects the lanes of partition L: cb[b] flips ballot b where bit b of L is clear
+#pragma unroll
+    for (int b = 0; b < 5; b++) cb[b] = ((lane >> b) & 1) ? 0u : 0xFFFFFFFFu;
+    typedef typename FS::key_t KT;
+    KT lo = sizeof(KT) == 4 ? (KT)0x7FFFFFFF : (KT)RFB_INF_I64, hi = sizeof(KT) == 4 ? (KT)NULL_I32 : (KT)NULL_I64;
+    REC *const grec = (REC *)rs.rec;
+    if (tid < 2 * NP) s_cnt[tid >> 5][tid & 31] = 0;
+    if (tid == 0) s_abort = 0;
+    __syncthreads();
+    int buf = 0;
+    for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1) {
+        // rows of this thread: pairs (j2 * MS_T + tid) of the tile, so that every load instruction of a warp covers one
+        // contiguous, fully used run of bytes
+        KT k[MS_R];
+        i64 v[MS_R];
+        bool sel[MS_R];
+        const i64 pbase = tile * (MS_TILE / 2);
+#pragma unroll
+        for (int j2 = 0; j2 < MS_R / 2; j2++) {
+            const i64 pair = pbase + j2 * MS_T + tid;
+            ld_pair<KT>(fs.keys, pair, k[2 * j2], k[2 * j2 + 1]);
+            ld_pair<i64>(val, pair, v[2 * j2], v[2 * j2 + 1]);
+            fs.selected_pair(pair, sel[2 * j2], sel[2 * j2 + 1]);
+        }
+        REC rec[MS_R];
+        u32 pp[MS_R];                    // rank among the warp's rows of the partition << 8 | partition (32 = not staged)
+        u32 exc_mask = 0;                // rows of this thread that go to the side list
+        u32 wcount = 0;                  // rows of partition `lane` this warp has ranked so far in this tile
+#pragma unroll
+        for (int j = 0; j < MS_R; j++) {
+            const KT kj = k[j];
+            lo = (sel[j] && kj < lo) ? kj : lo;
+            hi = (sel[j] && kj > hi) ? kj : hi;
+            const bool ok = sel[j] && F::fits(v[j]);
+            exc_mask |= (u32)(sel[j] && !ok) << j;
+            const u32 kb = (u32)kj;
+            const u32 part = (kb >> KPL) & (NP - 1);
+            rec[j] = F::pack(kb & (KPN - 1u), v[j]);
+            // Ranking by ballots: lane L ends up with the set of lanes whose row goes to partition L (five ballots over the
+            // partition bits, each flipped where L's bit is clear); a row then fetches its own partition's set and running
+            // count from lane `part`.  No shared-memory traffic and no atomics per row.
+            u32 pl = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+            for (int b = 0; b < 5; b++) pl &= ballot_bits(kb, 1u << (KPL + b)) ^ cb[b];
+            const u32 peers = __shfl_sync(0xffffffffu, pl, part);
+            const u32 before = __shfl_sync(0xffffffffu, wcount, part);
+            wcount += __popc(pl);
+            pp[j] = ((before + __popc(peers & lt_mask)) << 8) | (ok ? part : 32u);
+        }
+        u32 wbase = 0;
+        if (wcount) wbase = atomicAdd(&s_cnt[buf][lane], wcount);   // one atomic per (warp, partition) and tile, distinct addresses
+        if (exc_mask) {                                              // rare
+#pragma unroll
+            for (int j = 0; j < MS_R; j++)
+                if (exc_mask & (1u << j)) {
+                    const u32 e = atomicAdd(rs.exc_count, 1u);
+                    if (e < rs.exc_cap) { rs.exc[2 * (size_t)e] = (i64)k[j]; rs.exc[2 * (size_t)e + 1] = v[j]; }
+                }
+        }
+        __syncthreads();                                             // #1: the tile's partition counts are final
+        const u32 c = s_cnt[buf][lane];
+        u32 incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const u32 lbase = incl - c;                                  // where partition `lane` starts in the staging area
+        s_wb[warp][lane] = lbase + wbase;
+        u32 start = 0;
+        if (warp == 0 && c) start = atomicAdd(&rs.cursor[lane * CUR_STRIDE], c);   // reserve [start, start + c) of the partition's stream
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < MS_R; j++)
+            if (!(pp[j] & 32u)) {
+                const u32 q = s_wb[warp][pp[j] & 31u] + (pp[j] >> 8);
+                s_rec[buf][q] = rec[j];
+                s_part[buf][q] = (u8)(pp[j] & 31u);
+            }
+        if (warp == 0) {
+            // blocks of PB records are handed out on demand: the run that contains a block's first record allocates it and
+            // publishes it in the block table, everybody else waits for that word (same protocol as k_part_scatter)
+            u32 phys0 = 1, phys1 = 1;
+            if (c) {
+                const u32 b0 = start >> PB_LOG, b1 = (start + c - 1) >> PB_LOG;
+                u32 *row = rs.bt + (size_t)lane * rs.bt_stride;
+                phys0 = phys1 = 0;
+                if ((start & (PB - 1)) == 0) { phys0 = atomicAdd(rs.next_block, 1u) + 1; st_relaxed_u32(row + b0, phys0); }
+                if (b1 != b0) { phys1 = atomicAdd(rs.next_block, 1u) + 1; st_relaxed_u32(row + b1, phys1); }
+                while (!phys0) phys0 = ld_relaxed_u32(row + b0);
+                if (b1 == b0) phys1 = phys0;
+            }
+            const u32 in_block = start & (PB - 1), room = PB - in_block;
+            uint4 d;
+            d.x = (phys0 - 1) * (u32)PB + in_block - lbase;
+            d.y = lbase + room;
+            d.z = (phys1 - 1) * (u32)PB - (lbase + room);
+            d.w = 0;
+            s_desc[buf][lane] = d;
+            s_cnt[buf ^ 1][lane] = 0;                                // the other buffer: nobody reads it any more, nobody adds before #2
+            if (lane == 31) s_total[buf] = incl;
+            if (lane == 0 && ld_relaxed_u32(rs.exc_count) > rs.exc_cap) s_abort = 1;
+        }
+        __syncthreads();                                             // #2: the tile is staged, ordered by partition
+        const u32 total = s_total[buf];
+#pragma unroll
+        for (int j = 0; j < MS_R; j++) {
+            const u32 q = j * MS_T + tid;
+            if (q < total) {
+                const uint4 d = s_desc[buf][s_part[buf][q]];
+                grec[q + (q < d.y ? d.x : d.z)] = s_rec[buf][q];
+            }
+        }
+        if (s_abort) break;                                          // written before #2, uniform: the record format was a bad guess
+    }
+    struct Mn { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b < a ? b : a; } };
+    struct Mx { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b > a ? b : a; } };
+    const i64 lo64 = block_reduce<i64>((i64)lo, Mn(), RFB_INF_I64, red);
+    const i64 hi64 = block_reduce<i64>((i64)hi, Mx(), NULL_I64, red);
+    if (tid == 0) {
+        atomicMin((long long *)&mm[0], (long long)lo64);
+        atomicMax((long long *)&mm[1], (long long)hi64);
+    }
+}
+
+// the rows past the last full tile: every selected one goes to the side list (fewer than MS_TILE rows, the list holds >= 4096)
+template <typename FS>
+__global__ void __launch_bounds__(THREADS) k_ms_tail(FS fs, const i64 *__restrict__ val, i64 r0, i64 n, RecStore rs, i64 *mm) {
+    for (i64 i = r0 + threadIdx.x; i < n; i += THREADS)
+        if (fs.selected(i)) {
+            const i64 k = fs.key(i);
+            atomicMin((long long *)&mm[0], (long long)k);
+            atomicMax((long long *)&mm[1], (long long)k);
+            const u32 e = atomicAdd(rs.exc_count, 1u);
+            if (e < rs.exc_cap) { rs.exc[2 * (size_t)e] = k; rs.exc[2 * (size_t)e + 1] = val[i]; }
+        }
+}
+
+// non-null values that fit the record: the low word takes the value, a wrap carries into the high word
+__device__ __forceinline__ void sacc_add_small(const SAcc &a, u32 s, i64 v) {
+    const u32 lo = (u32)(u64)v;
+    u32 hi = (u32)((u64)v >> 32);
+    const u32 old = atomicAdd(&a.lo[s], lo);
+    hi += (u32)((u32)(old + lo) < lo);
+    if (hi) atomicAdd(&a.hi[s], hi);
+    atomicAdd(&a.cnt[s], 1u);
+}
+
+// accumulate pass of the narrow path: one CTA per SM, the partition's records staged by the TMA unit (cp.async.bulk into an
+// mbarrier ring) next to the partition's 2^KPL accumulators.  Partition p = absolute bucket ((kbase >> KPL) + p) mod 32.
+constexpr int MS_UNIT = 4096;                   // records per work unit
+template <typename REC> struct MsRing { static constexpr int STAGES = sizeof(REC) == 4 ? 4 : 3; };
+
+template <typename REC, int KPL>
+__global__ void __launch_bounds__(AT, 1)
+k_ms_accum_tma(RecStore rs, int P, i64 kbase, i64 kmin, Accums ga) {
+    typedef RecFmt<REC, KPL> F;
+    constexpr int KPN = 1 << KPL, STAGES = MsRing<REC>::STAGES, PER = MS_UNIT / AT;   // records per thread and unit
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    REC *stage = (REC *)s_dyn;                                                  // STAGES x MS_UNIT records
+    u32 *s_acc = (u32 *)(s_dyn + (size_t)STAGES * MS_UNIT * sizeof(REC));       // lo[KPN] | hi[KPN] | cnt[KPN]
+    __shared__ u64 full[STAGES];
+    __shared__ u32 s_cnt[NP], s_ubase[NP + 1];
+    const SAcc a{s_acc, s_acc + KPN, s_acc + 2 * KPN};
+    sacc_zero(a, KPN);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const u32 bucket0 = (u32)(((u64)kbase >> KPL) & (NP - 1));
+    const REC *const grec = (const REC *)rs.rec;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) {
+        const u32 c = tid < P ? rs.cursor[((bucket0 + tid) & (NP - 1)) * CUR_STRIDE] : 0;
+        s_cnt[tid] = c;
+        u32 incl = (c + MS_UNIT - 1) / MS_UNIT;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        s_ubase[tid + 1] = incl;
+        if (tid == 0) s_ubase[0] = 0;
+    }
+    __syncthreads();
+    const u32 U = s_ubase[P];
+    const u32 u0 = (u32)((u64)blockIdx.x * U / gridDim.x), u1 = (u32)((u64)(blockIdx.x + 1) * U / gridDim.x);
+    int pp = 0;                                   // producer state (thread 0 only)
+    u32 p_blk = 0xFFFFFFFFu, p_phys = 0;
+    auto issue = [&](u32 u) {
+        while (s_ubase[pp + 1] <= u) { pp++; p_blk = 0xFFFFFFFFu; }
+        const u32 r0 = (u - s_ubase[pp]) * MS_UNIT, cnt = s_cnt[pp];
+        const u32 rows = cnt - r0 < (u32)MS_UNIT ? cnt - r0 : (u32)MS_UNIT;
+        const u32 bytes = (rows * (u32)sizeof(REC) + 15u) & ~15u;
+        const u32 bucket = (bucket0 + pp) & (NP - 1);
+        if ((r0 >> PB_LOG) != p_blk) { p_blk = r0 >> PB_LOG; p_phys = rs.bt[(size_t)bucket * rs.bt_stride + p_blk] - 1; }
+        const u64 base = (u64)p_phys * PB + (r0 & (PB - 1));
+        const int s = (int)((u - u0) % STAGES);
+        mbar_expect_tx(&full[s], bytes);
+        bulk_g2s(stage + (size_t)s * MS_UNIT, grec + base, bytes, &full[s]);
+    };
+    if (tid == 0)
+        for (u32 u = u0; u < u1 && u < u0 + (STAGES - 1); u++) issue(u);
+    int p = 0;
+    while (p + 1 < P && s_ubase[p + 1] <= u0) p++;
+    bool dirty = false;
+    for (u32 u = u0; u < u1; u++) {
+        const u32 k = u - u0;
+        const int s = (int)(k % STAGES);
+        __syncthreads();                                                       // unit u-1 fully consumed: its stage may be re-armed
+        if (tid == 0 && u + (STAGES - 1) < u1) issue(u + (STAGES - 1));
+        if (s_ubase[p + 1] <= u) {
+            if (dirty) sacc_flush(a, KPN, (i64)((u64)kbase + (u64)p * KPN - (u64)kmin), ga);
+            __syncthreads();
+            dirty = false;
+            while (s_ubase[p + 1] <= u) p++;
+        }
+        const u32 r0 = (u - s_ubase[p]) * MS_UNIT, cnt = s_cnt[p];
+        const u32 rows = cnt - r0 < (u32)MS_UNIT ? cnt - r0 : (u32)MS_UNIT;
+        mbar_wait(&full[s], (k / STAGES) & 1u);
+        dirty = true;
+        const REC *st = stage + (size_t)s * MS_UNIT;
+        const u32 q0 = (u32)tid * PER;
+        if (q0 + PER <= rows) {
+            REC r[PER];
+            if constexpr (sizeof(REC) == 4) {
+                const uint4 w = *(const uint4 *)(st + q0);
+                r[0] = w.x; r[1] = w.y; r[2] = w.z; r[3] = w.w;
+            } else {
+                const ulonglong2 w0 = *(const ulonglong2 *)(st + q0), w1 = *(const ulonglong2 *)(st + q0 + 2);
+                r[0] = w0.x; r[1] = w0.y; r[2] = w1.x; r[3] = w1.y;
+            }
+#pragma unroll
+            for (int j = 0; j < PER; j++) sacc_add_small(a, F::slot(r[j]), F::val(r[j]));
+        } else {
+            for (u32 q = q0; q < rows && q < q0 + PER; q++) sacc_add_small(a, F::slot(st[q]), F::val(st[q]));
+        }
+    }
+    __syncthreads();
+    if (dirty) sacc_flush(a, KPN, (i64)((u64)kbase + (u64)p * KPN - (u64)kmin), ga);
+}
+static_assert(MS_UNIT / AT == 4, "k_ms_accum_tma reads four records per thread");
+
+// the exception rows of the narrow path: device-wide accumulators, L2 atomics
+__global__ void __launch_bounds__(THREADS) k_ms_exceptions(const i64 *__restrict__ exc, const u32 *__restrict__ exc_count, i64 kmin, Accums a) {
+    const u32 m = *exc_count;
+    for (u32 i = blockIdx.x * THREADS + threadIdx.x; i < m; i += gridDim.x * THREADS) {
+        const i64 k = exc[2 * (size_t)i], v = exc[2 * (size_t)i + 1];
+        const i64 s = (i64)((u64)k - (u64)kmin);
+        if (v == NULL_I64) a.has_null[s] = 1u; else atomicAdd((unsigned long long *)a.sum + s, (unsigned long long)v);
+        atomicAdd((unsigned long long *)a.cnt + s, 1ULL);
+    }
+}
+
+// value census of the rows [r0, r1): how many selected rows do not fit a 19-bit / 20-bit unsigned / 48-bit signed record
+template <typename FS>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_val_census_rows(FS fs, const i64 *__restrict__ val, i64 r0, i64 r1, i64 *out) {
+    __shared__ i64 red[32];
+    i64 c19 = 0, c20 = 0, c48 = 0, rows = 0;
+    for (i64 i = r0 + (i64)blockIdx.x * THREADS + threadIdx.x; i < r1; i += (i64)gridDim.x * THREADS)
+        if (fs.selected(i)) {
+            const i64 v = ld_stream(val + i);
+            rows++;
+            c19 += !RecFmt<u32, 13>::fits(v);
+            c20 += !RecFmt<u32, 12>::fits(v);
+            c48 += !RecFmt<u64, 13>::fits(v);
+        }
+    c19 = block_reduce<i64>(c19, OpAddWrap(), 0, red);
+    c20 = block_reduce<i64>(c20, OpAddWrap(), 0, red);
+    c48 = block_reduce<i64>(c48, OpAddWrap(), 0, red);
+    rows = block_reduce<i64>(rows, OpAddWrap(), 0, red);
+    if (threadIdx.x == 0) {
+        atomicAdd((unsigned long long *)&out[0], (unsigned long long)c19);
+        atomicAdd((unsigned long long *)&out[1], (unsigned long long)c20);
+        atomicAdd((unsigned long long *)&out[2], (unsigned long long)c48);
+        atomicAdd((unsigned long long *)&out[3], (unsigned long long)rows);
+    }
+}
+
 // min/max of the selected keys of the rows [r0, r1): the sample that decides whether the partitioned strategy is tried
 template <typename FS>
 __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM) k_fused_scope_rows(FS fs, i64 r0, i64 r1, i64 *mm) {
@@ -652,23 +999,54 @@ k_fused_emit(FS fs, i64 limit, i64 kmin, Accums a, i64 max_groups, i64 *out_keys
         });
 }
 
-// tuning knobs (environment): RFB_GROUP_STRATEGY = smem | part | l2 forces a strategy where it is applicable;
+// tuning knobs (environment): RFB_GROUP_STRATEGY = smem | part | narrow | l2 | hash forces a strategy where it is applicable;
 // RFB_PART_MIN_ROWS = smallest row count that takes the partitioned strategy
 int group_strategy_forced() {
     const char *s = getenv("RFB_GROUP_STRATEGY");
     if (!s) return 0;
-    return !strcmp(s, "smem") ? 1 : (!strcmp(s, "part") ? 2 : (!strcmp(s, "l2") ? 3 : 0));
+    return !strcmp(s, "smem") ? 1 : (!strcmp(s, "part") ? 2 : (!strcmp(s, "l2") ? 3 : (!strcmp(s, "narrow") ? 4 : (!strcmp(s, "hash") ? 5 : 0))));
 }
 i64 part_min_rows() {
     const char *s = getenv("RFB_PART_MIN_ROWS");
     return s ? atoll(s) : (1ll << 21);
 }
 
+
+// ---- host side of the narrow path
+struct NarrowPlan { int rec_bytes; int kpl; };   // rec_bytes 0 = not applicable
+
+static inline i64 buckets_spanned(i64 kmin, i64 kmax, int kpl) { return (kmax >> kpl) - (kmin >> kpl) + 1; }   // arithmetic shifts: floor
+
+template <typename FS, typename REC, int KPL>
+int ms_scatter_launch(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, const RecStore &rs, i64 *mm) {
+    const size_t smem = 2 * (size_t)MS_TILE * (sizeof(REC) + 1);
+    const i64 tiles = n / MS_TILE;                 // full tiles; the rest goes through the side list
+    if (tiles > 0) {
+        RFB_CUDA(cudaFuncSetAttribute(k_ms_scatter<FS, REC, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_ms_scatter<FS, REC, KPL><<<rfb_grid_for(ctx, tiles * MS_TILE, MS_TILE, MS_CTAS), MS_T, smem, ctx->stream>>>(fs, val, tiles, rs, mm);
+        RFB_CHECK_LAUNCH(ctx);
+    }
+    if (tiles * MS_TILE < n) {
+        k_ms_tail<FS><<<1, THREADS, 0, ctx->stream>>>(fs, val, tiles * MS_TILE, n, rs, mm);
+        RFB_CHECK_LAUNCH(ctx);
+    }
+    return RFB_OK;
+}
+template <typename REC, int KPL>
+int ms_accum_launch(rfb_ctx_t *ctx, const RecStore &rs, int P, i64 kbase, i64 kmin, const Accums &a) {
+    const size_t smem = (size_t)MsRing<REC>::STAGES * MS_UNIT * sizeof(REC) + (size_t)(1 << KPL) * 12;
+    RFB_CUDA(cudaFuncSetAttribute(k_ms_accum_tma<REC, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ms_accum_tma<REC, KPL><<<ctx->sm_count, AT, smem, ctx->stream>>>(rs, P, kbase, kmin, a);
+    RFB_CHECK_LAUNCH(ctx);
+    return RFB_OK;
+}
+
 template <typename FS>
 int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 *out_keys, i64 *out_sums, i64 *out_counts, i64 *groups) {
     i64 *mm = (i64 *)((char *)ctx->d_scratch + 32768);
     const int forced = group_strategy_forced();
-    const bool part_able = n < 0xF0000000ll && (forced == 2 || (forced == 0 && n >= part_min_rows()));   // 32-bit row positions
+    if (forced == 5) return RFB_SPARSE_DOMAIN;
+    const bool part_able = n < 0xF0000000ll && (forced == 2 || forced == 4 || (forced == 0 && n >= part_min_rows()));   // 32-bit row positions
     const int grid = rfb_grid_for(ctx, n, THREADS * 4, BLOCKS_PER_SM);
     const int sgrid = rfb_grid_for(ctx, n, STILE, 4);
     const bool vec = fs.vec_ok(val);
@@ -676,9 +1054,11 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
     auto parts_of = [](i64 kmin, i64 kmax) { return (i64)(((u64)kmax - (u64)(kmin & ~(i64)(KP - 1))) >> KP_LOG) + 1; };
     i64 h[2];
     int rc;
-    bool have_scope = false, scattered = false, modded = false;
+    bool have_scope = false, scattered = false, modded = false, narrowed = false;
     void *w = nullptr;
     PartStore ps{};
+    RecStore rs{};
+    NarrowPlan plan{0, 0};
     Accums gmod{};
     // workspace of the partitioned strategy: accumulators for the largest range it accepts, then the block store
     const i64 max_range = (i64)MAX_PARTS * KP;
@@ -697,6 +1077,7 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
         }
         rc = d2h_sync(ctx, h, mm, 16);
         if (rc) return rc;
+        if (h[0] <= h[1] && (u64)h[1] - (u64)h[0] >= (u64)DENSE_RANGE_MAX) return RFB_SPARSE_DOMAIN;   // no point in a full scope pass
         const bool try_mod = h[0] <= h[1] && (forced == 0 || forced == 1) && (u64)h[1] - (u64)h[0] < (u64)KP;
         if (try_mod) {
             void *aux;
@@ -716,18 +1097,70 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
             RFB_CHECK_LAUNCH(ctx);
             have_scope = modded = true;
         }
-        const bool try_part = !modded && h[0] <= h[1] && (forced == 2 || (i64)((u64)h[1] - (u64)h[0]) >= KP) && (u64)h[1] - (u64)h[0] < (u64)max_range &&
+        // narrow path: at most 32 partitions, packed records chosen from a value census of the same row windows
+        if (!modded && vec && h[0] <= h[1] && (forced == 0 || forced == 4) && (forced == 4 || (i64)((u64)h[1] - (u64)h[0]) >= KP) &&
+            (u64)h[1] - (u64)h[0] < (u64)NP * KP) {
+            i64 *census = mm + 8;
+            RFB_CUDA(cudaMemsetAsync(census, 0, 32, ctx->stream));
+            for (int s = 0; s < 3; s++) {
+                const i64 r0 = starts[s], r1 = r0 + win < n ? r0 + win : n;
+                k_val_census_rows<FS><<<64, THREADS, 0, ctx->stream>>>(fs, val, r0, r1, census);
+                RFB_CHECK_LAUNCH(ctx);
+            }
+            i64 c[4];
+            rc = d2h_sync(ctx, c, census, 32);
+            if (rc) return rc;
+            const i64 tol = c[3] / 64;
+            if (buckets_spanned(h[0], h[1], 12) <= NP && c[1] <= tol) plan = NarrowPlan{4, 12};
+            else if (buckets_spanned(h[0], h[1], 13) <= NP && c[0] <= tol) plan = NarrowPlan{4, 13};
+            else if (buckets_spanned(h[0], h[1], 13) <= NP && c[2] <= tol) plan = NarrowPlan{8, 13};
+        }
+        const i64 hs[2] = {h[0], h[1]};
+        if (plan.rec_bytes) {
+            const u32 blocks = (u32)((n + PB - 1) / PB) + NP + 1;
+            const u32 bt_stride = (u32)((n + PB - 1) / PB) + 1;
+            i64 cap = n / 64 > 4096 ? n / 64 : 4096;
+            if (cap > (1ll << 23)) cap = 1ll << 23;
+            const size_t ctl_bytes = align256((size_t)(NP + 2) * CUR_STRIDE * 4), bt_bytes = align256((size_t)NP * bt_stride * 4);
+            const size_t rec_bytes = align256((size_t)blocks * PB * plan.rec_bytes), exc_bytes = align256((size_t)cap * 16);
+            rc = rfb_ensure_work(ctx, p_acc_bytes + ctl_bytes + bt_bytes + rec_bytes + exc_bytes, &w);
+            if (rc) return rc;
+            char *pw = (char *)w + p_acc_bytes;
+            rs.cursor = (u32 *)pw;
+            rs.next_block = rs.cursor + NP * CUR_STRIDE;
+            rs.exc_count = rs.cursor + (NP + 1) * CUR_STRIDE;
+            rs.bt = (u32 *)(pw + ctl_bytes);
+            rs.bt_stride = bt_stride;
+            rs.exc_cap = (u32)cap;
+            rs.rec = pw + ctl_bytes + bt_bytes;
+            rs.exc = (i64 *)(pw + ctl_bytes + bt_bytes + rec_bytes);
+            RFB_CUDA(cudaMemsetAsync(pw, 0, ctl_bytes + bt_bytes, ctx->stream));
+            k_fused_scope_init<<<1, 32, 0, ctx->stream>>>(mm);
+            RFB_CHECK_LAUNCH(ctx);
+            if (plan.rec_bytes == 4 && plan.kpl == 12) rc = ms_scatter_launch<FS, u32, 12>(ctx, fs, val, n, rs, mm);
+            else if (plan.rec_bytes == 4) rc = ms_scatter_launch<FS, u32, 13>(ctx, fs, val, n, rs, mm);
+            else rc = ms_scatter_launch<FS, u64, 13>(ctx, fs, val, n, rs, mm);
+            if (rc) return rc;
+            u32 exc_n = 0;
+            RFB_CUDA(cudaMemcpyAsync(&exc_n, rs.exc_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            rc = d2h_sync(ctx, h, mm, 16);
+            if (rc) return rc;
+            if (exc_n <= rs.exc_cap && (h[0] > h[1] || buckets_spanned(h[0], h[1], plan.kpl) <= NP)) have_scope = narrowed = true;
+            else if (exc_n <= rs.exc_cap) have_scope = true;     // a complete pass: the key bounds are exact, only the partitioning is void
+            else { h[0] = hs[0]; h[1] = hs[1]; }                 // aborted early: back to what the sample said
+        }
+        const bool try_part = !modded && !narrowed && h[0] <= h[1] && (forced == 2 || (i64)((u64)h[1] - (u64)h[0]) >= KP) && (u64)h[1] - (u64)h[0] < (u64)max_range &&
                               parts_of(h[0], h[1]) <= MAX_PARTS;
         if (try_part) {
             const u32 blocks = (u32)((n + PB - 1) / PB) + MAX_PARTS + 1;
             const u32 bt_stride = (u32)((n + PB - 1) / PB) + 1;
             const size_t bt_bytes = align256((size_t)MAX_PARTS * bt_stride * 4);
-            const size_t ctl_bytes = align256((MAX_PARTS + 1) * 4);
+            const size_t ctl_bytes = align256((size_t)(MAX_PARTS + 1) * PCUR_STRIDE * 4);
             rc = rfb_ensure_work(ctx, p_acc_bytes + ctl_bytes + bt_bytes + (size_t)blocks * PB * 10, &w);
             if (rc) return rc;
             char *pw = (char *)w + p_acc_bytes;
             ps.cursor = (u32 *)pw;
-            ps.next_block = ps.cursor + MAX_PARTS;
+            ps.next_block = ps.cursor + MAX_PARTS * PCUR_STRIDE;
             ps.bt = (u32 *)(pw + ctl_bytes);
             ps.bt_stride = bt_stride;
             ps.val = (u64 *)(pw + ctl_bytes + bt_bytes);
@@ -750,19 +1183,18 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
     if (rc) return rc;
     if (h[0] > h[1]) { *groups = 0; return RFB_OK; }   // nothing selected
     const i64 kmin = h[0], range = (i64)((u64)h[1] - (u64)h[0] + 1);
-    if (range <= 0 || range > (1ll << 28)) {
-        rfb_set_error("fused group-by: key range %lld is not a dense domain (use rfb_group_i64_dev + rfb_aggr_dev)", (long long)range);
-        return RFB_ERR_ARG;
-    }
+    if (range <= 0 || range > DENSE_RANGE_MAX) return RFB_SPARSE_DOMAIN;   // open-addressing tables instead of direct addressing (k_hash_group.cu)
     const i64 kbase = kmin & ~(i64)(KP - 1);            // floor to a multiple of KP (two's complement)
     const i64 P = parts_of(kmin, h[1]);                 // partitions of KP consecutive keys
     int strategy = 3;
-    if (range <= KP && (n >= 65536 || forced == 1)) strategy = 1;
+    if (narrowed) strategy = 4;
+    else if (range <= KP && (n >= 65536 || forced == 1)) strategy = 1;
     else if (scattered && P <= MAX_PARTS) strategy = 2;
     if (forced == 3) strategy = 3;
+    const bool part_layout = strategy == 2 || strategy == 4;   // accumulators sized for the largest range the partitioned passes accept
 
-    const size_t b8 = strategy == 2 ? pb8 : align256((size_t)range * 8), b4 = strategy == 2 ? pb4 : align256((size_t)range * 4);
-    if (!scattered) {
+    const size_t b8 = part_layout ? pb8 : align256((size_t)range * 8), b4 = part_layout ? pb4 : align256((size_t)range * 4);
+    if (!scattered && !plan.rec_bytes) {
         rc = rfb_ensure_work(ctx, 3 * b8 + b4 + scan::tiles_bytes(tiles_max), &w);
         if (rc) return rc;
     }
@@ -771,7 +1203,7 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
     a.sum = (u64 *)((char *)w + b8);
     a.cnt = (u64 *)((char *)w + 2 * b8);
     a.has_null = (u32 *)((char *)w + 3 * b8);
-    if (scattered && strategy != 2) {   // the sample misjudged the range: the accumulator layout of the other strategies must fit
+    if ((scattered || plan.rec_bytes) && !part_layout) {   // the sample misjudged the range: the accumulator layout of the other strategies must fit
         if (3 * align256((size_t)range * 8) + align256((size_t)range * 4) + scan::tiles_bytes(tiles_max) > ctx->work_bytes) {
             rc = rfb_ensure_work(ctx, 3 * b8 + b4 + scan::tiles_bytes(tiles_max), &w);
             if (rc) return rc;
@@ -790,6 +1222,15 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
         const int pgrid = (int)(ptiles < 2ll * ctx->sm_count ? ptiles : 2ll * ctx->sm_count);
         RFB_CUDA(cudaFuncSetAttribute(k_fused_accum_smem<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, KP * 12));
         k_fused_accum_smem<FS><<<pgrid, PT, (size_t)range * 12, ctx->stream>>>(fs, val, n, vec, kmin, (int)range, a);
+        RFB_CHECK_LAUNCH(ctx);
+    } else if (strategy == 4) {
+        const i64 kb = kmin & ~(((i64)1 << plan.kpl) - 1);
+        const int np = (int)buckets_spanned(kmin, h[1], plan.kpl);
+        if (plan.rec_bytes == 4 && plan.kpl == 12) rc = ms_accum_launch<u32, 12>(ctx, rs, np, kb, kmin, a);
+        else if (plan.rec_bytes == 4) rc = ms_accum_launch<u32, 13>(ctx, rs, np, kb, kmin, a);
+        else rc = ms_accum_launch<u64, 13>(ctx, rs, np, kb, kmin, a);
+        if (rc) return rc;
+        k_ms_exceptions<<<rfb_grid_for(ctx, rs.exc_cap, THREADS, 2), THREADS, 0, ctx->stream>>>(rs.exc, rs.exc_count, kmin, a);
         RFB_CHECK_LAUNCH(ctx);
     } else if (strategy == 2) {
         const char *tma = getenv("RFB_ACCUM_TMA");       // "0": the register-staged kernel (128-bit loads) instead of the TMA ring
@@ -877,9 +1318,13 @@ extern "C" int rfb_group_sum_count_dev(rfb_ctx_t *ctx, int key_type, const void 
     RFB_ARG((out_keys && out_sums && out_counts) || max_groups == 0, "rfb_group_sum_count_dev: outputs");
     *groups = 0;
     if (n == 0) return RFB_OK;
+    int rc;
     switch (rfb_kind_of(key_type)) {
-        case K_I32: return fused_key<i32>(ctx, keys, cmp_op, pred_type, pred, k, val, n, max_groups, out_keys, out_sums, out_counts, groups);
-        case K_I64: return fused_key<i64>(ctx, keys, cmp_op, pred_type, pred, k, val, n, max_groups, out_keys, out_sums, out_counts, groups);
+        case K_I32: rc = fused_key<i32>(ctx, keys, cmp_op, pred_type, pred, k, val, n, max_groups, out_keys, out_sums, out_counts, groups); break;
+        case K_I64: rc = fused_key<i64>(ctx, keys, cmp_op, pred_type, pred, k, val, n, max_groups, out_keys, out_sums, out_counts, groups); break;
         default: rfb_set_error("fused group-by: key type %d (I32 or I64 keys)", key_type); return RFB_ERR_TYPE;
     }
+    if (rc == RFB_SPARSE_DOMAIN)
+        rc = rfb_hash_group_sum_count(ctx, key_type, keys, val, n, cmp_op, pred_type, pred, k, max_groups, out_keys, out_sums, out_counts, groups);
+    return rc;
 }

@@ -182,7 +182,16 @@ int rfb_dev_alloc(rfb_ctx_t *ctx, size_t bytes, void **dptr) {
 }
 int rfb_dev_free(rfb_ctx_t *ctx, void *dptr) {
     RFB_ARG(ctx, "rfb_dev_free");
-    if (dptr) RFB_CUDA(cudaFree(dptr));
+    if (dptr) {
+        RFB_CUDA(cudaSetDevice(ctx->device));   /* may be called from a host thread that never touched CUDA */
+        RFB_CUDA(cudaFree(dptr));
+    }
+    return RFB_OK;
+}
+int rfb_dev_mem_info(rfb_ctx_t *ctx, size_t *free_bytes, size_t *total_bytes) {
+    RFB_ARG(ctx && free_bytes && total_bytes, "rfb_dev_mem_info");
+    RFB_CUDA(cudaSetDevice(ctx->device));
+    RFB_CUDA(cudaMemGetInfo(free_bytes, total_bytes));
     return RFB_OK;
 }
 int rfb_dev_memset(rfb_ctx_t *ctx, void *dptr, int byte, size_t bytes) {

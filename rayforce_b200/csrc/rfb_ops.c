@@ -25,14 +25,22 @@ static int rfb_d2h_plain(rfb_ctx_t *ctx, void *dst_host, const void *src_dev, si
 
 /* ------------------------------------------------------------------ state */
 
-#define MAX_COLS 64
+/* A device image of a host vector's payload, or a scratch / result buffer (host == NULL).
+ * Identity of a host vector = (payload pointer, length, type).  That identity is only trustworthy while the host has neither
+ * freed nor modified the object.  The layer learns about both from hooks the binding installs (rfb_ops_note_free /
+ * rfb_ops_note_write: the reference's heap_free, heap_realloc, cow_obj, the in-place CPU bodies of the wrapped math operators and
+ * `and` / `or`, see integration/rayforce_shim.c); the sampled fingerprint stays as a second line of defence.  Entries are found
+ * newest-first, registering a payload forgets every older entry with the same pointer, and nothing is recycled while the
+ * operator call that handed it out is still running (entries are only released at the end of the outermost scope). */
 typedef struct {
-    const void *host; /* payload pointer identity */
+    const void *host; /* payload pointer identity; NULL = scratch */
     int64_t len;
     int type;
     void *dev;
     size_t bytes;
-    uint64_t print; /* fingerprint of sampled payload words: guards against a freed-and-reused host block */
+    uint64_t print;   /* fingerprint of sampled payload words */
+    uint64_t used;    /* LRU clock of the last operator that touched it */
+    int keep;         /* survives the end of its scope: an image of a live host vector, kept resident across queries */
 } col_entry_t;
 
 typedef struct {
@@ -40,16 +48,23 @@ typedef struct {
     size_t bytes;
 } pool_entry_t;
 
+#define POOL_MAX 64
 static struct {
     int ready;
     const rfb_host_api_t *host;
     rfb_ctx_t *ctx;
     int64_t min_rows;
     int scope_depth;
-    col_entry_t cols[MAX_COLS];
-    int ncols;
-    pool_entry_t pool[MAX_COLS]; /* free device buffers kept for reuse */
+    col_entry_t *cols;
+    int ncols, cap;
+    pool_entry_t pool[POOL_MAX]; /* free device buffers kept for reuse */
     int npool;
+    uint64_t clock;
+    int residency;               /* images of live host vectors stay in HBM after the scope ends (needs the hooks) */
+    size_t resident_bytes, resident_budget;
+    uint64_t bloom[4];           /* payload pointers with an entry: lets the free hook leave after one test */
+    volatile int hook_lock;
+    long stat_hits, stat_ships, stat_forgotten;
     char err[256];
 } G;
 
@@ -129,26 +144,95 @@ int rfb_ops_init(const rfb_host_api_t *host, int device) {
     G.host = host;
     const char *e = getenv("RFB200_MIN_ROWS");
     G.min_rows = e ? atoll(e) : 0;
+    size_t free_b = 0, total_b = 0;
+    e = getenv("RFB200_RESIDENT_MB");
+    if (e) G.resident_budget = (size_t)atoll(e) << 20;
+    else if (rfb_dev_mem_info(G.ctx, &free_b, &total_b) == RFB_OK) G.resident_budget = free_b / 2;   /* the other half: results, workspaces */
+    else G.resident_budget = (size_t)32 << 30;
     G.ready = 1;
     return 0;
 }
 
-static void release_columns(void) {
+static unsigned bloom_bit(const void *p) { return (unsigned)((((uintptr_t)p >> 4) * 0x9E3779B97F4A7C15ULL) >> 56); }
+static void bloom_add(const void *p) { const unsigned b = bloom_bit(p); G.bloom[b >> 6] |= 1ULL << (b & 63); }
+static int bloom_has(const void *p) { const unsigned b = bloom_bit(p); return (int)((G.bloom[b >> 6] >> (b & 63)) & 1); }
+
+static void free_buffer(void *dev, size_t bytes) {
+    if (G.npool < POOL_MAX) { G.pool[G.npool].dev = dev; G.pool[G.npool].bytes = bytes; G.npool++; }
+    else rfb_dev_free(G.ctx, dev);
+}
+
+/* end of the outermost scope: scratch buffers go back to the pool; images of live host vectors stay when residency is on,
+ * oldest ones first out when they exceed the budget */
+static void release_columns(int everything) {
+    int w = 0;
+    G.resident_bytes = 0;
+    memset(G.bloom, 0, sizeof(G.bloom));
     for (int i = 0; i < G.ncols; i++) {
-        if (G.npool < MAX_COLS) { G.pool[G.npool].dev = G.cols[i].dev; G.pool[G.npool].bytes = G.cols[i].bytes; G.npool++; }
-        else rfb_dev_free(G.ctx, G.cols[i].dev);
+        col_entry_t *e = &G.cols[i];
+        if (!everything && G.residency && e->host && e->keep) {
+            G.resident_bytes += e->bytes;
+            bloom_add(e->host);
+            G.cols[w++] = *e;
+        } else free_buffer(e->dev, e->bytes);
     }
-    G.ncols = 0;
+    G.ncols = w;
+    while (G.resident_bytes > G.resident_budget && G.ncols > 0) {
+        int lru = 0;
+        for (int i = 1; i < G.ncols; i++)
+            if (G.cols[i].used < G.cols[lru].used) lru = i;
+        G.resident_bytes -= G.cols[lru].bytes;
+        free_buffer(G.cols[lru].dev, G.cols[lru].bytes);
+        G.cols[lru] = G.cols[--G.ncols];
+    }
 }
 
 void rfb_ops_shutdown(void) {
     if (!G.ready) return;
-    release_columns();
+    rfb_sync(G.ctx);
+    release_columns(1);
     for (int i = 0; i < G.npool; i++) rfb_dev_free(G.ctx, G.pool[i].dev);
     G.npool = 0;
+    free(G.cols);
     rfb_ctx_destroy(G.ctx);
     memset(&G, 0, sizeof(G));
 }
+
+void rfb_ops_set_residency(int on, int64_t budget_bytes) {
+    if (!G.ready) return;
+    if (!on && G.residency && G.scope_depth == 0) { rfb_sync(G.ctx); G.residency = 0; release_columns(1); }
+    G.residency = on ? 1 : 0;
+    if (budget_bytes > 0) G.resident_budget = (size_t)budget_bytes;
+}
+void rfb_ops_residency_stats(long out[4]) { out[0] = G.stat_hits; out[1] = G.stat_ships; out[2] = G.stat_forgotten; out[3] = (long)(G.resident_bytes >> 20); }
+
+/* ---- hooks: the host tells the layer that an object is gone or is about to change under its pointer.  Callable from any
+ * host thread (the reference frees temporaries on its pool workers); the operator entry points themselves run on one thread
+ * and never concurrently with a hook (workers only run while that thread waits in the host's pool). */
+static void lazy_on_free(const void *obj);
+static void forget_payload(const void *payload, const col_entry_t *except) {
+    for (int i = G.ncols - 1; i >= 0; i--)
+        if (G.cols[i].host == payload && &G.cols[i] != except) {
+            G.cols[i].host = NULL;           /* now a scratch buffer: released with the scope (never recycled mid-call) */
+            G.cols[i].keep = 0;
+            G.stat_forgotten++;
+            if (G.scope_depth == 0) {        /* between queries: give the memory back right away */
+                G.resident_bytes -= G.cols[i].bytes < G.resident_bytes ? G.cols[i].bytes : G.resident_bytes;
+                free_buffer(G.cols[i].dev, G.cols[i].bytes);
+                G.cols[i] = G.cols[--G.ncols];
+            }
+        }
+}
+void rfb_ops_note_free(const void *obj) {
+    if (!G.ready || !obj) return;
+    const void *payload = (const char *)obj + 16;
+    if (lazy_on == 1) lazy_on_free(obj);
+    if (G.ncols == 0 || !bloom_has(payload)) return;
+    while (__sync_lock_test_and_set(&G.hook_lock, 1)) { }
+    forget_payload(payload, NULL);
+    __sync_lock_release(&G.hook_lock);
+}
+void rfb_ops_note_write(const void *obj) { rfb_ops_note_free(obj); }
 
 void rfb_ops_set_min_rows(int64_t n) { G.min_rows = n; }
 void rfb_ops_lazy_stats(long out[4]) { out[0] = lazy_stats[0]; out[1] = lazy_stats[1]; out[2] = lazy_stats[2]; out[3] = lazy_stats[3]; }
@@ -158,7 +242,7 @@ void rfb_ops_scope_end(void) {
     if (G.scope_depth > 0 && --G.scope_depth == 0 && G.ready) {
         rfb_sync(G.ctx);
         if (lazy_on == 1) lazy_resolve_all();
-        release_columns();
+        release_columns(0);
     }
 }
 
@@ -266,6 +350,24 @@ void rfb_ops_set_lazy(int on, int64_t min_bytes) {
     lazy_on = (on && lazy_install()) ? 1 : 0;
 }
 
+/* the host frees an object whose payload is still pending: nobody ever read it — open the pages again (the allocator is
+ * about to write its own words there) and forget it, without the copy */
+static void lazy_on_free(const void *obj) {
+    const char *payload = (const char *)obj + 16;
+    for (int i = 0; i < MAX_LAZY; i++) {
+        lazy_t *z = &LZ[i];
+        if (z->state == 1 && z->payload == payload) {
+            while (__sync_lock_test_and_set(&lazy_lock, 1)) { }
+            if (z->state == 1) {
+                mprotect(z->lo, (size_t)(z->hi - z->lo), PROT_READ | PROT_WRITE);
+                z->state = 0;
+                lazy_stats[2]++;
+            }
+            __sync_lock_release(&lazy_lock);
+        }
+    }
+}
+
 /* is [lo, hi) still one of OUR protected ranges?  (/proc/self/maps: a mapping with no permissions covering it) */
 static int lazy_still_ours(const char *lo, const char *hi) {
     FILE *f = fopen("/proc/self/maps", "r");
@@ -359,23 +461,28 @@ static void *dev_buffer(size_t bytes, size_t *got) {
     return d;
 }
 
-/* Track a device buffer for the rest of the scope (or this call).  host != NULL registers it as the HBM image of that
- * host payload so later operators find it. */
-static int track(void *dev, size_t bytes, const void *host, int64_t len, int type) {
-    if (G.ncols == MAX_COLS) { /* table full: recycle the oldest entry */
-        rfb_sync(G.ctx);
-        if (G.npool < MAX_COLS) { G.pool[G.npool].dev = G.cols[0].dev; G.pool[G.npool].bytes = G.cols[0].bytes; G.npool++; }
-        else rfb_dev_free(G.ctx, G.cols[0].dev);
-        memmove(&G.cols[0], &G.cols[1], sizeof(col_entry_t) * (MAX_COLS - 1));
-        G.ncols--;
+/* Track a device buffer until the end of the scope (or this call).  host != NULL registers it as the HBM image of that
+ * host payload so later operators find it; every older entry with the same pointer is forgotten first. */
+static col_entry_t *track(void *dev, size_t bytes, const void *host, int64_t len, int type, int keep) {
+    if (G.ncols == G.cap) {
+        const int ncap = G.cap ? 2 * G.cap : 64;
+        col_entry_t *n = (col_entry_t *)realloc(G.cols, (size_t)ncap * sizeof(col_entry_t));
+        if (!n) return NULL;
+        G.cols = n;
+        G.cap = ncap;
     }
+    if (host) { forget_payload(host, NULL); bloom_add(host); }
     col_entry_t *e = &G.cols[G.ncols++];
-    e->host = host; e->len = len; e->type = type; e->dev = dev; e->bytes = bytes;
+    e->host = host; e->len = len; e->type = type; e->dev = dev; e->bytes = bytes; e->used = ++G.clock; e->keep = keep;
     e->print = host ? fingerprint(host, (size_t)len * type_size(type)) : 0;
-    return 0;
+    return e;
 }
 
-/* device image of a host vector's payload: cache hit inside a scope, else one cudaMemcpyAsync */
+/* a host vector whose image may outlive the query: it lives in the reference's own heap (mmod 0xff: not a mapped file, which
+ * can change or be unmapped behind the hooks) and somebody besides the evaluator's stack holds it (a table column, a global) */
+static int worth_keeping(obj_p v) { return G.residency && v->mmod == 0xff && v->rc >= 2; }
+
+/* device image of a host vector's payload: a hit on a live entry, else one cudaMemcpyAsync */
 static void *dev_column(obj_p v) {
     const int w = type_size(v->type);
     const void *payload = RFB_OBJ_PAYLOAD(v);
@@ -384,34 +491,56 @@ static void *dev_column(obj_p v) {
         if (img) return img;
         lazy_forget_overlaps((const char *)v, (const char *)payload + (size_t)v->len * w, NULL);
     }
-    for (int i = 0; i < G.ncols; i++)
-        if (G.cols[i].host == payload && G.cols[i].len == v->len && G.cols[i].type == v->type) {
-            if (G.cols[i].print == fingerprint(payload, (size_t)v->len * w)) return G.cols[i].dev;
-            G.cols[i].host = NULL; /* the block was reused for other data: forget the image (buffer freed at scope end) */
+    for (int i = G.ncols - 1; i >= 0; i--)
+        if (G.cols[i].host == payload) {
+            if (G.cols[i].len == v->len && G.cols[i].type == v->type && G.cols[i].print == fingerprint(payload, (size_t)v->len * w)) {
+                G.cols[i].used = ++G.clock;
+                if (!G.cols[i].keep && worth_keeping(v)) G.cols[i].keep = 1;
+                G.stat_hits++;
+                return G.cols[i].dev;
+            }
+            forget_payload(payload, NULL);   /* same pointer, other shape or other bytes: the block was reused */
+            break;
         }
     size_t got = 0;
     void *d = dev_buffer((size_t)v->len * w, &got);
     if (!d) return NULL;
     if (v->len > 0 && rfb_h2d(G.ctx, d, payload, (size_t)v->len * w) != RFB_OK) { set_err("%s", rfb_last_error()); rfb_dev_free(G.ctx, d); return NULL; }
-    track(d, got, payload, v->len, v->type);
+    if (!track(d, got, payload, v->len, v->type, worth_keeping(v))) { rfb_sync(G.ctx); rfb_dev_free(G.ctx, d); return NULL; }
+    G.stat_ships++;
     return d;
+}
+
+/* is the payload of this vector in HBM already? */
+static int is_resident(obj_p v) {
+    const void *payload = RFB_OBJ_PAYLOAD(v);
+    if (lazy_on == 1 && lazy_device_image(payload)) return 1;
+    for (int i = G.ncols - 1; i >= 0; i--)
+        if (G.cols[i].host == payload) return G.cols[i].len == v->len && G.cols[i].type == v->type;
+    return 0;
 }
 
 /* scratch / result buffer on the device, alive until the end of the scope (or call) */
 static void *dev_temp(size_t bytes) {
     size_t got = 0;
     void *d = dev_buffer(bytes, &got);
-    if (d) track(d, got, NULL, 0, 0);
+    if (d && !track(d, got, NULL, 0, 0, 0)) { rfb_dev_free(G.ctx, d); return NULL; }
     return d;
+}
+
+static col_entry_t *entry_of_dev(void *dev) {
+    for (int i = G.ncols - 1; i >= 0; i--)
+        if (G.cols[i].dev == dev) return &G.cols[i];
+    return NULL;
 }
 
 /* host vector of `type` filled from device memory; the device copy is registered as its HBM image */
 static obj_p to_host_vector(int type, int64_t len, void *dev) {
     obj_p r = G.host->vector((int8_t)type, len);
     if (!r || r->type == RFB_T_ERR) return r ? r : G.host->err_limit();
+    col_entry_t *e = entry_of_dev(dev);
     if (len > 0 && lazy_register(r, (size_t)len * type_size(type), dev)) {
-        for (int i = 0; i < G.ncols; i++)
-            if (G.cols[i].dev == dev) { G.cols[i].host = NULL; G.cols[i].len = len; G.cols[i].type = type; }   /* found through the lazy table */
+        if (e) { forget_payload(RFB_OBJ_PAYLOAD(r), e); e->host = NULL; e->len = len; e->type = type; }   /* found through the lazy table */
         return r;
     }
     if (len > 0) {
@@ -421,11 +550,12 @@ static obj_p to_host_vector(int type, int64_t len, void *dev) {
             return G.host->err_limit();
         }
     }
-    for (int i = 0; i < G.ncols; i++)
-        if (G.cols[i].dev == dev) {
-            G.cols[i].host = RFB_OBJ_PAYLOAD(r); G.cols[i].len = len; G.cols[i].type = type;
-            G.cols[i].print = fingerprint(RFB_OBJ_PAYLOAD(r), (size_t)len * type_size(type));
-        }
+    if (e) {
+        forget_payload(RFB_OBJ_PAYLOAD(r), e);   /* an older vector that lived at this address */
+        e->host = RFB_OBJ_PAYLOAD(r); e->len = len; e->type = type; e->keep = 0;
+        e->print = fingerprint(RFB_OBJ_PAYLOAD(r), (size_t)len * type_size(type));
+        bloom_add(e->host);
+    }
     return r;
 }
 

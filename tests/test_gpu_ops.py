@@ -493,6 +493,144 @@ def test_fused_group_partitioned_tma_accumulate(ctx, oracle, monkeypatch, n, car
     assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val, wg, wi.groups, filt)[0])
 
 
+@pytest.mark.parametrize("mode", ["narrow", "auto"])
+@pytest.mark.parametrize("key_type", [ob.I64, ob.I32])
+@pytest.mark.parametrize("with_pred", [False, True])
+@pytest.mark.parametrize("n,card,kmin,vbits,skew", [
+    (1_000_003, 100_000, 17, 20, False),          # config-4 shape: 25 partitions of 4096 keys, 32-bit records (12-bit slot | 20-bit value)
+    (1_000_003, 100_000, -4096 * 7 - 5, 20, True),  # negative keys, skewed partitions
+    (1_500_001, 250_000, 3, 19, False),           # 31 partitions of 8192 keys, 32-bit records (13 | 19)
+    (1_000_003, 200_000, -70_000, 45, False),     # values need the 64-bit record (16-bit slot field | 48-bit signed value)
+    (300_007, 9000, 5, 20, False),                # a range the one-pass residue strategy would normally take
+])
+def test_fused_group_narrow_records(ctx, oracle, monkeypatch, mode, key_type, with_pred, n, card, kmin, vbits, skew):
+    """<= 32-partition path of the fused group-by: ballot ranking, packed 32/64-bit records, TMA-staged accumulate, and the
+    exception side list (nulls, values that do not fit the record) against the oracle, bit for bit"""
+    if mode == "narrow":
+        monkeypatch.setenv("RFB_GROUP_STRATEGY", "narrow")
+    else:
+        monkeypatch.setenv("RFB_PART_MIN_ROWS", "1000")
+    r = np.random.default_rng(n + card + vbits)
+    keys64 = r.integers(0, card, n).astype(np.int64)
+    if skew:
+        hot = r.random(n) < 0.8
+        keys64[hot] = np.where(r.random(int(hot.sum())) < 0.5, 3, card - 2)
+    keys64 += kmin
+    if vbits > 32:
+        val = r.integers(-(1 << (vbits - 1)), 1 << (vbits - 1), n).astype(np.int64)
+    else:
+        val = r.integers(0, 1 << vbits, n).astype(np.int64)
+    exc = r.random(n) < 0.0005                      # exceptions: nulls, negative and huge values
+    val[exc] = r.choice(np.array([ob.NULL_I64, -1, -(1 << 50), (1 << 62) + 12345, np.iinfo(np.int64).max], dtype=np.int64), int(exc.sum()))
+    keys = keys64.astype(ob.NP_OF[key_type])
+    if with_pred:
+        kk = 1 << (vbits - 1)
+        filt = oracle.where(oracle.cmp(ob.LT, ob.I64, val, ob.I64, kk))
+        gk, gs, gc = ctx.group_sum_count(key_type, dev(keys), dev(val), card + 5, cmp_op=capi.LT, pred_type=ob.I64, pred=dev(val), k=kk)
+    else:
+        filt = None
+        gk, gs, gc = ctx.group_sum_count(key_type, dev(keys), dev(val), card + 5)
+    wg, wf, wi = oracle.group_i64(keys64, filt)
+    rows = wf if filt is None else filt[wf]
+    assert np.array_equal(host(gk), keys64[rows])
+    assert np.array_equal(host(gs), oracle.aggr(ob.SUM, ob.I64, val, wg, wi.groups, filt)[0])
+    assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val, wg, wi.groups, filt)[0])
+
+
+@pytest.mark.parametrize("case", ["values", "keys"])
+def test_fused_group_narrow_sample_misjudges(ctx, oracle, monkeypatch, case):
+    """the record format and the 32-partition span are guessed from three row windows.  Values that only turn wide outside the
+    windows overflow the exception list (the pass aborts, the 256-partition pass takes over); keys outside the windows can
+    span more than 32 partitions (the scatter is void, the exact bounds it found are kept): the result must not change"""
+    monkeypatch.setenv("RFB_PART_MIN_ROWS", "1000")
+    n, card = 1_200_007, 60_000
+    r = np.random.default_rng(77)
+    keys = r.integers(0, card, n).astype(np.int64)
+    val = r.integers(0, 1 << 18, n).astype(np.int64)
+    if case == "values":
+        val[100_000:500_000] = r.integers(-(1 << 60), 1 << 60, 400_000)
+    else:
+        keys[100_000:101_000] += 500_000
+    gk, gs, gc = ctx.group_sum_count(ob.I64, dev(keys), dev(val), card + 1000)
+    wg, wf, wi = oracle.group_i64(keys)
+    assert np.array_equal(host(gk), keys[wf])
+    assert np.array_equal(host(gs), oracle.aggr(ob.SUM, ob.I64, val, wg, wi.groups)[0])
+    assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val, wg, wi.groups)[0])
+
+
+def _sparse_keys(r, n, card, key_type):
+    """`card` distinct keys scattered over the whole key width (no dense domain), drawn uniformly"""
+    if key_type == ob.I32:
+        pool = r.permutation(np.unique(r.integers(-(1 << 31) + 1, 1 << 31, 2 * card).astype(np.int64)))[:card]
+    else:
+        pool = np.unique(r.integers(-(1 << 62), 1 << 62, card).astype(np.int64))
+    return pool[r.integers(0, pool.shape[0], n)]
+
+
+@pytest.mark.parametrize("key_type", [ob.I64, ob.I32])
+@pytest.mark.parametrize("with_pred", [False, True])
+@pytest.mark.parametrize("n,card", [(1, 1), (5000, 7), (700_001, 3000), (2_000_003, 40_000), (1_500_001, 400_000)])
+def test_fused_group_sparse_keys(ctx, oracle, key_type, with_pred, n, card):
+    """sparse key domains (range > 2^28): per-CTA open-addressing tables in shared memory fed by TMA-staged tiles, spills into
+    the device-wide table (the 40k / 400k-key cases overflow the 8192-slot tables many times), groups in first-occurrence
+    order (= the reference at -c 1; at -c N its order is hash-slot order): sums, sticky nulls, counts bit-exact"""
+    r = np.random.default_rng(n + card)
+    card = min(card, n)
+    keys64 = _sparse_keys(r, n, card, key_type)
+    val = r.integers(-(1 << 40), 1 << 40, n).astype(np.int64)
+    val[::1013] = np.iinfo(np.int64).max
+    val[r.random(n) < 0.0003] = ob.NULL_I64
+    keys = keys64.astype(ob.NP_OF[key_type])
+    if with_pred:
+        filt = oracle.where(oracle.cmp(ob.LT, ob.I64, val, ob.I64, 1 << 19))
+        gk, gs, gc = ctx.group_sum_count(key_type, dev(keys), dev(val), card + 5, cmp_op=capi.LT, pred_type=ob.I64, pred=dev(val), k=1 << 19)
+    else:
+        filt = None
+        gk, gs, gc = ctx.group_sum_count(key_type, dev(keys), dev(val), card + 5)
+    wg, wf, wi = oracle.group_i64(keys64, filt)
+    rows = wf if filt is None else filt[wf]
+    assert np.array_equal(host(gk), keys64[rows])
+    assert np.array_equal(host(gs), oracle.aggr(ob.SUM, ob.I64, val, wg, wi.groups, filt)[0])
+    assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val, wg, wi.groups, filt)[0])
+
+
+def test_fused_group_sparse_null_key(ctx):
+    """NULL_I64 as a KEY: the reference's open-addressing table uses it as the empty marker and cannot hold it (core/hash.c:35-56,
+    SURVEY a13); the device gives it a dedicated slot, so it groups like any other key.  Checked against numpy."""
+    n = 300_007
+    r = np.random.default_rng(9)
+    pool = np.unique(r.integers(-(1 << 62), 1 << 62, 50).astype(np.int64))
+    keys = pool[r.integers(0, pool.shape[0], n)]
+    keys[r.integers(1000, n, 40)] = ob.NULL_I64
+    val = r.integers(-1000, 1000, n).astype(np.int64)
+    gk, gs, gc = ctx.group_sum_count(ob.I64, dev(keys), dev(val), 100)
+    uk, first, inv, cnt = np.unique(keys, return_index=True, return_inverse=True, return_counts=True)
+    order = np.argsort(first, kind="stable")                  # first-occurrence order
+    sums = np.zeros(uk.shape[0], np.int64)
+    np.add.at(sums, inv, val)
+    assert np.array_equal(host(gk), uk[order]) and host(gk)[-1] == ob.NULL_I64
+    assert np.array_equal(host(gs), sums[order]) and np.array_equal(host(gc), cnt[order])
+
+
+def test_fused_group_hash_path_on_dense_keys_unaligned_and_overflow(ctx, oracle, monkeypatch):
+    """the hash path forced onto a dense domain must agree with the dense strategies; columns that start at an odd element
+    take the plain-load tile loader instead of the TMA ring; more groups than the output has room for is an error"""
+    monkeypatch.setenv("RFB_GROUP_STRATEGY", "hash")
+    n, card = 600_011, 20_000
+    r = np.random.default_rng(3)
+    keys = r.integers(0, card, n + 1).astype(np.int64)
+    val = r.integers(-1000, 1000, n + 1).astype(np.int64)
+    dk, dv = dev(keys), dev(val)
+    for off in (0, 1):
+        gk, gs, gc = ctx.group_sum_count(ob.I64, dk[off:], dv[off:], card)
+        wg, wf, wi = oracle.group_i64(keys[off:])
+        assert np.array_equal(host(gk), keys[off:][wf])
+        assert np.array_equal(host(gs), oracle.aggr(ob.SUM, ob.I64, val[off:], wg, wi.groups)[0])
+        assert np.array_equal(host(gc), oracle.aggr(ob.COUNT, ob.I64, val[off:], wg, wi.groups)[0])
+    with pytest.raises(capi.RfbError):
+        ctx.group_sum_count(ob.I64, dk, dv, 1000)
+
+
 def test_fused_group_partitioned_unaligned_columns(ctx, oracle, monkeypatch):
     """columns that start at an odd element (no 16-byte alignment) take the scalar tile loader"""
     monkeypatch.setenv("RFB_GROUP_STRATEGY", "part")

@@ -104,6 +104,14 @@ def main():
         timed("aggr_sum_i64_1e5", lambda: ctx.aggr(capi.A_SUM, capi.I64, y, gids, info.groups), 16 * n)
         timed("aggr_avg_i64_1e5", lambda: ctx.aggr(capi.A_AVG, capi.I64, y, gids, info.groups), 16 * n)
         del gids, firsts, k64
+        # sparse key domains (range >> 2^28): shared-memory open-addressing tables + device-wide merge (k_hash_group.cu)
+        for card in (1000, 100_000, 10_000_000):
+            kd = col(capi.I64, 13, card)
+            ks, _ = ctx.binop(capi.MUL, capi.I64, kd, capi.I64, 0x9E3779B97F4A7C1)      # distinct multiples of a large odd constant
+            del kd
+            timed("group_sum_count_sparse_i64keys_%d" % card, lambda: ctx.group_sum_count(capi.I64, ks, y, card), 16 * n,
+                  "sparse keys: per-CTA smem hash tables (TMA-staged tiles) + device-wide merge")
+            del ks
         k100 = col(capi.I64, 9, 100)
         timed("group_sum_count_i64keys_100", lambda: ctx.group_sum_count(capi.I64, k100, y, 100), 16 * n, "low cardinality (H2O id1-like)")
         for card in (1, 2, 8):
