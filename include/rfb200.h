@@ -58,7 +58,8 @@ enum { RFB_ADD = 0, RFB_SUB = 1, RFB_MUL = 2, RFB_DIV = 3, RFB_FDIV = 4, RFB_MOD
 enum { RFB_ROUND = 0, RFB_FLOOR = 1, RFB_CEIL = 2 };
 
 /* grouped aggregates: aggr_sum/min/max/count/avg (core/aggr.c:1078-1453, 2013-2133) */
-enum { RFB_A_SUM = 0, RFB_A_MIN = 1, RFB_A_MAX = 2, RFB_A_COUNT = 3, RFB_A_AVG = 4, RFB_A_MED = 5, RFB_A_DEV = 6 };
+enum { RFB_A_SUM = 0, RFB_A_MIN = 1, RFB_A_MAX = 2, RFB_A_COUNT = 3, RFB_A_AVG = 4, RFB_A_MED = 5, RFB_A_DEV = 6,
+       RFB_A_FIRST = 7, RFB_A_LAST = 8 /* aggr_first / aggr_last (core/aggr.c:441-577, 851-1075) */ };
 
 /* group index kinds (core/index.h:31-36) */
 enum { RFB_INDEX_IDS = 0, RFB_INDEX_SHIFT = 1 };
@@ -241,6 +242,9 @@ int rfb_aggr_type(int op, int val_type);
  * count as values; I64/TIMESTAMP/F64 values, any other type gives all-null like the reference's default branch).
  * op RFB_A_DEV = aggr_dev (core/aggr.c:2250-2906): population standard deviation of the non-null values, f64 sums of x and
  * x*x per group, sqrt(max(sumsq/n - mean^2, 0)); 0 rows -> null, 1 row -> 0. */
+/* op RFB_A_FIRST = aggr_first: the value at each group's first row (null or not: the reference's first_ids fast path);
+ * op RFB_A_LAST = aggr_last: each group's last NON-NULL value, null if none (the reference's single-chunk result; above its
+ * parallel threshold its own answer depends on the thread count). */
 int rfb_aggr_dev(rfb_ctx_t *ctx, int op, int val_type, const void *val, const int64_t *filter,
                  const int64_t *group_ids, int64_t len, int64_t groups, void *out);
 

@@ -250,6 +250,45 @@ finalise:
     return RFB_OK;
 }
 
+// ---- aggr_first / aggr_last (core/aggr.c:441-577, 851-1075): one POSITION per group, then a gather.
+// first: the group's first row, whatever its value (the reference's fast path reads in[first_ids[g]]; every index this
+//        library builds carries first_ids).  last: the group's last NON-NULL value, null when it has none — what the reference
+//        computes for one chunk of rows (aggr_last_partial); with several worker chunks its merge keeps the FIRST chunk's
+//        answer (AGGR_COLLECT `if (out == NULL) out = in`), so above its 16384-row parallel threshold its own result depends
+//        on the thread count.
+template <typename V, bool LAST>
+__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
+k_aggr_pos(const V *__restrict__ val, ValRow row, const i64 *__restrict__ gid, i64 len, u64 *pos) {
+    for (i64 i = (i64)blockIdx.x * THREADS + threadIdx.x; i < len; i += (i64)gridDim.x * THREADS) {
+        const i64 g = ld_stream(gid + i);
+        if constexpr (LAST) {
+            if (Elem<V>::is_null(val[row(i)])) continue;
+            if (__ldcg(&pos[g]) < (u64)(i + 1)) atomicMax((unsigned long long *)&pos[g], (unsigned long long)(i + 1));   // 0 = none yet
+        } else {
+            if (__ldcg(&pos[g]) > (u64)i) atomicMin((unsigned long long *)&pos[g], (unsigned long long)i);
+        }
+    }
+}
+template <typename V, bool LAST>
+__global__ void __launch_bounds__(256) k_aggr_pos_final(const V *__restrict__ val, ValRow row, const u64 *__restrict__ pos, i64 groups, V *out) {
+    for (i64 g = (i64)blockIdx.x * 256 + threadIdx.x; g < groups; g += (i64)gridDim.x * 256) {
+        const u64 p = pos[g];
+        if constexpr (LAST) out[g] = p ? val[row((i64)p - 1)] : Elem<V>::null();
+        else out[g] = p != NO_ROW ? val[row((i64)p)] : Elem<V>::null();
+    }
+}
+template <typename V, bool LAST>
+int run_pos(rfb_ctx_t *ctx, const void *val, const i64 *filter, const i64 *gid, i64 len, i64 groups, u64 *pos, void *out) {
+    RFB_CUDA(cudaMemsetAsync(pos, LAST ? 0 : 0xFF, (size_t)groups * 8, ctx->stream));
+    if (len > 0) {
+        k_aggr_pos<V, LAST><<<rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>((const V *)val, ValRow{filter}, gid, len, pos);
+        RFB_CHECK_LAUNCH(ctx);
+    }
+    k_aggr_pos_final<V, LAST><<<rfb_grid_for(ctx, groups, 256, 8), 256, 0, ctx->stream>>>((const V *)val, ValRow{filter}, pos, groups, (V *)out);
+    RFB_CHECK_LAUNCH(ctx);
+    return RFB_OK;
+}
+
 }  // namespace
 
 extern "C" int rfb_aggr_type(int op, int val_type) {
@@ -263,6 +302,9 @@ extern "C" int rfb_aggr_type(int op, int val_type) {
             return (val_type == RFB_I16 || val_type == RFB_I64 || val_type == RFB_TIMESTAMP || val_type == RFB_DATE || val_type == RFB_TIME || val_type == RFB_F64) ? val_type : RFB_ERR_TYPE;
         case RFB_A_AVG: return (val_type == RFB_I16 || k == K_I32 || val_type == RFB_I64 || k == K_F64) ? RFB_F64 : RFB_ERR_TYPE;
         case RFB_A_MED: return RFB_F64;   // aggr_collect takes every column type; types without a median give nulls (core/aggr.c:2182-2184)
+        case RFB_A_FIRST: return val_type;   // every fixed-width type (core/aggr.c:455-573)
+        // aggr_last has no U8/B8 case, and its I64-kind results are plain I64 vectors (core/aggr.c:904-931: no retyping)
+        case RFB_A_LAST: return k == K_U8 ? RFB_ERR_TYPE : (k == K_I64 ? RFB_I64 : val_type);
         case RFB_A_DEV: return (val_type == RFB_I16 || k == K_I32 || val_type == RFB_I64 || val_type == RFB_TIMESTAMP || k == K_F64) ? RFB_F64 : RFB_ERR_TYPE;   // core/aggr.c:2873-2880
         default: return RFB_ERR_TYPE;
     }
@@ -281,6 +323,16 @@ extern "C" int rfb_aggr_dev(rfb_ctx_t *ctx, int op, int val_type, const void *va
     int rc = rfb_ensure_work(ctx, 2 * align256((size_t)groups * 8), &w);
     if (rc) return rc;
     void *acc = w, *aux = (char *)w + align256((size_t)groups * 8);
+    if (op == RFB_A_FIRST || op == RFB_A_LAST) {
+        const bool last = op == RFB_A_LAST;
+        switch (k) {
+            case K_U8: return run_pos<u8, false>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out);
+            case K_I16: return last ? run_pos<i16, true>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out) : run_pos<i16, false>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out);
+            case K_I32: return last ? run_pos<i32, true>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out) : run_pos<i32, false>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out);
+            case K_I64: return last ? run_pos<i64, true>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out) : run_pos<i64, false>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out);
+            default: return last ? run_pos<f64, true>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out) : run_pos<f64, false>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out);
+        }
+    }
     switch (op) {
         case RFB_A_COUNT:
             RFB_CUDA(cudaMemsetAsync(out, 0, (size_t)groups * 8, ctx->stream));

@@ -65,6 +65,8 @@ template <typename T> static inline bool pair_aligned(const T *p) { return (((ui
 template <typename K, typename P, bool HAS_PRED>
 struct FusedSrc {
     typedef K key_t;
+    typedef P pred_t;
+    static constexpr bool has_pred = HAS_PRED;
     const K *keys;
     const P *pred;
     PredRange pr;
@@ -87,6 +89,7 @@ struct FusedSrc {
             b = pred_test(pred_key<P>(y), pr);
         } else { a = b = true; }
     }
+    bool tma_ok(const i64 *val) const { return aligned16(keys) && aligned16(val) && (!HAS_PRED || aligned16(pred)); }   // bulk copies: 16-byte aligned sources
     bool vec_ok(const i64 *val) const { return pair_aligned(keys) && pair_aligned(val) && (!HAS_PRED || pair_aligned(pred)); }
 };
 
@@ -620,7 +623,7 @@ constexpr int NP = 32;                          // partitions of the narrow path
 #ifndef RFB_MS_T
 #define RFB_MS_T 256
 #define RFB_MS_R 8
-#define RFB_MS_CTAS 4
+#define RFB_MS_CTAS 3
 #endif
 constexpr int MS_T = RFB_MS_T, MS_R = RFB_MS_R, MS_CTAS = RFB_MS_CTAS, MS_TILE = MS_T * MS_R, MS_WARPS = MS_T / 32;
 static_assert(MS_TILE <= PB, "a tile's run touches at most two blocks");
@@ -669,108 +672,97 @@ __device__ __forceinline__ u32 ballot_bits(u32 x, u32 mask) {
 // of all partitions right after the barrier, so their latency hides behind the staging, and turns them into per-partition
 // output descriptors -> barrier #2 -> all threads write the staged tile out linearly (a byte per staged row names its
 // partition).  Staging area, counters and descriptors are double-buffered: no third barrier before the next tile starts.
-// The kernel takes FULL tiles of 16-byte aligned columns only (vector loads, no bounds tests in the hot loop); the rows past
-// the last full tile go through k_ms_tail, unaligned columns do not take the narrow path at all.
+// INPUT is staged by the TMA unit: thread 0 issues the bulk copies of the NEXT tile's key / value / predicate slices into a
+// two-stage shared-memory ring at the top of every tile (its stage was last read before the previous tile's barriers), so
+// the DRAM latency of a whole tile is hidden without holding a single register for it.
+// The kernel takes FULL tiles of 16-byte aligned columns only; the rows past the last full tile go through k_ms_tail,
+// unaligned columns do not take the narrow path at all.
+template <typename FS> struct MsIn {   // one input stage
+    typedef typename FS::key_t KT;
+    typedef typename FS::pred_t PT_;
+    static constexpr size_t KEY_BYTES = MS_TILE * sizeof(KT), VAL_BYTES = MS_TILE * 8, PRED_BYTES = FS::has_pred ? MS_TILE * sizeof(PT_) : 0;
+    static constexpr size_t BYTES = KEY_BYTES + VAL_BYTES + PRED_BYTES;
+};
+
+// Warp roles: MS_WARPS data warps rank, stage and write out rows; one extra CONTROL warp (lane = partition) owns everything
+// that waits on the memory system — the TMA issue, the global reservations of the tile's runs (one atomic per partition), the
+// block-table lookups and the output descriptors.  The write-out of tile i is delayed until after tile i+1's ranking, so the
+// control warp's two dependent L2 round trips overlap a whole tile of data-warp work instead of stalling a barrier.
 template <typename FS, typename REC, int KPL>
-__global__ void __launch_bounds__(MS_T, MS_CTAS)
+__global__ void __launch_bounds__(MS_T + 32, MS_CTAS)
 k_ms_scatter(FS fs, const i64 *__restrict__ val, i64 tiles, RecStore rs, i64 *mm) {
     typedef RecFmt<REC, KPL> F;
+    typedef MsIn<FS> In;
+    typedef typename FS::key_t KT;
+    typedef typename FS::pred_t PT_;
     constexpr u32 KPN = 1u << KPL;
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    REC (*const s_rec)[MS_TILE] = (REC (*)[MS_TILE])s_dyn;                                   // [2][MS_TILE] staged records (dynamic: 64-bit records exceed 48 KB)
-    u8 (*const s_part)[MS_TILE] = (u8 (*)[MS_TILE])(s_dyn + 2 * MS_TILE * sizeof(REC));      // [2][MS_TILE] partition of every staged record
+    unsigned char *const s_in = s_dyn;                                                        // [2] input stages: keys | values | predicate column
+    REC (*const s_rec)[MS_TILE] = (REC (*)[MS_TILE])(s_dyn + 2 * In::BYTES);                  // [2][MS_TILE] staged records
+    u8 (*const s_part)[MS_TILE] = (u8 (*)[MS_TILE])(s_dyn + 2 * In::BYTES + 2 * MS_TILE * sizeof(REC));   // [2][MS_TILE] partition of every staged record
+    __shared__ u64 full[2];
     __shared__ u32 s_cnt[2][NP];
-    __shared__ u32 s_wb[MS_WARPS][NP];   // per warp: where its rows of each partition start in the tile's staging area
+    __shared__ u32 s_wb[MS_WARPS][NP];   // per data warp: where its rows of each partition start in the tile's staging area
     __shared__ uint4 s_desc[2][NP];      // per partition: {x: global - local index before the block boundary, y: first local index past it, z: global - local after it}
     __shared__ u32 s_total[2];
     __shared__ u32 s_abort;
     __shared__ i64 red[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool ctrl = warp == MS_WARPS;
     const u32 lt_mask = (1u << lane) - 1u;
     u32 cb[5];                           // lane L collects the lanes of partition L: cb[b] flips ballot b where bit b of L is clear
 #pragma unroll
     for (int b = 0; b < 5; b++) cb[b] = ((lane >> b) & 1) ? 0u : 0xFFFFFFFFu;
-    typedef typename FS::key_t KT;
     KT lo = sizeof(KT) == 4 ? (KT)0x7FFFFFFF : (KT)RFB_INF_I64, hi = sizeof(KT) == 4 ? (KT)NULL_I32 : (KT)NULL_I64;
     REC *const grec = (REC *)rs.rec;
     if (tid < 2 * NP) s_cnt[tid >> 5][tid & 31] = 0;
-    if (tid == 0) s_abort = 0;
+    if (tid == 0) {
+        s_abort = 0;
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    int buf = 0;
-    for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1) {
-        // rows of this thread: pairs (j2 * MS_T + tid) of the tile, so that every load instruction of a warp covers one
-        // contiguous, fully used run of bytes
-        KT k[MS_R];
-        i64 v[MS_R];
-        bool sel[MS_R];
-        const i64 pbase = tile * (MS_TILE / 2);
-#pragma unroll
-        for (int j2 = 0; j2 < MS_R / 2; j2++) {
-            const i64 pair = pbase + j2 * MS_T + tid;
-            ld_pair<KT>(fs.keys, pair, k[2 * j2], k[2 * j2 + 1]);
-            ld_pair<i64>(val, pair, v[2 * j2], v[2 * j2 + 1]);
-            fs.selected_pair(pair, sel[2 * j2], sel[2 * j2 + 1]);
-        }
-        REC rec[MS_R];
-        u32 pp[MS_R];                    // rank among the warp's rows of the partition << 8 | partition (32 = not staged)
-        u32 exc_mask = 0;                // rows of this thread that go to the side list
-        u32 wcount = 0;                  // rows of partition `lane` this warp has ranked so far in this tile
+    auto issue = [&](i64 tile, int st) {          // one lane: the three slices of one tile
+        unsigned char *dst = s_in + (size_t)st * In::BYTES;
+        mbar_expect_tx(&full[st], (u32)In::BYTES);
+        bulk_g2s(dst, fs.keys + tile * MS_TILE, (u32)In::KEY_BYTES, &full[st]);
+        bulk_g2s(dst + In::KEY_BYTES, val + tile * MS_TILE, (u32)In::VAL_BYTES, &full[st]);
+        if constexpr (FS::has_pred) bulk_g2s(dst + In::KEY_BYTES + In::VAL_BYTES, fs.pred + tile * MS_TILE, (u32)In::PRED_BYTES, &full[st]);
+    };
+    auto write_out = [&](int b) {                 // data warps: the staged tile in buffer b, linearly
+        const u32 total = s_total[b];
 #pragma unroll
         for (int j = 0; j < MS_R; j++) {
-            const KT kj = k[j];
-            lo = (sel[j] && kj < lo) ? kj : lo;
-            hi = (sel[j] && kj > hi) ? kj : hi;
-            const bool ok = sel[j] && F::fits(v[j]);
-            exc_mask |= (u32)(sel[j] && !ok) << j;
-            const u32 kb = (u32)kj;
-            const u32 part = (kb >> KPL) & (NP - 1);
-            rec[j] = F::pack(kb & (KPN - 1u), v[j]);
-            // Ranking by ballots: lane L ends up with the set of lanes whose row goes to partition L (five ballots over the
-            // partition bits, each flipped where L's bit is clear); a row then fetches its own partition's set and running
-            // count from lane `part`.  No shared-memory traffic and no atomics per row.
-            u32 pl = __ballot_sync(0xffffffffu, ok);
-#pragma unroll
-            for (int b = 0; b < 5; b++) pl &= ballot_bits(kb, 1u << (KPL + b)) ^ cb[b];
-            const u32 peers = __shfl_sync(0xffffffffu, pl, part);
-            const u32 before = __shfl_sync(0xffffffffu, wcount, part);
-            wcount += __popc(pl);
-            pp[j] = ((before + __popc(peers & lt_mask)) << 8) | (ok ? part : 32u);
-        }
-        u32 wbase = 0;
-        if (wcount) wbase = atomicAdd(&s_cnt[buf][lane], wcount);   // one atomic per (warp, partition) and tile, distinct addresses
-        if (exc_mask) {                                              // rare
-#pragma unroll
-            for (int j = 0; j < MS_R; j++)
-                if (exc_mask & (1u << j)) {
-                    const u32 e = atomicAdd(rs.exc_count, 1u);
-                    if (e < rs.exc_cap) { rs.exc[2 * (size_t)e] = (i64)k[j]; rs.exc[2 * (size_t)e + 1] = v[j]; }
-                }
-        }
-        __syncthreads();                                             // #1: the tile's partition counts are final
-        const u32 c = s_cnt[buf][lane];
-        u32 incl = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        const u32 lbase = incl - c;                                  // where partition `lane` starts in the staging area
-        s_wb[warp][lane] = lbase + wbase;
-        u32 start = 0;
-        if (warp == 0 && c) start = atomicAdd(&rs.cursor[lane * CUR_STRIDE], c);   // reserve [start, start + c) of the partition's stream
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < MS_R; j++)
-            if (!(pp[j] & 32u)) {
-                const u32 q = s_wb[warp][pp[j] & 31u] + (pp[j] >> 8);
-                s_rec[buf][q] = rec[j];
-                s_part[buf][q] = (u8)(pp[j] & 31u);
+            const u32 q = j * MS_T + tid;
+            if (q < total) {
+                const uint4 d = s_desc[b][s_part[b][q]];
+                grec[q + (q < d.y ? d.x : d.z)] = s_rec[b][q];
             }
-        if (warp == 0) {
-            // blocks of PB records are handed out on demand: the run that contains a block's first record allocates it and
-            // publishes it in the block table, everybody else waits for that word (same protocol as k_part_scatter)
-            u32 phys0 = 1, phys1 = 1;
+        }
+    };
+    if (ctrl && lane == 0 && (i64)blockIdx.x < tiles) issue(blockIdx.x, 0);
+    int buf = 0;
+    u32 it = 0;
+    for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1, it++) {
+        if (ctrl) {
+            // the other input stage was last read before barrier A of the previous tile: refill it now
+            if (lane == 0 && tile + gridDim.x < tiles) issue(tile + gridDim.x, buf ^ 1);
+            __syncthreads();                                         // A: the tile's partition counts are final
+            const u32 c = s_cnt[buf][lane];
+            u32 incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const u32 lbase = incl - c;
+            // reserve [start, start + c) of the partition's stream; blocks of PB records are handed out on demand: the run that
+            // contains a block's first record allocates it and publishes it in the block table, everybody else waits for that
+            // word (same protocol as k_part_scatter)
+            u32 start = 0, phys0 = 1, phys1 = 1;
             if (c) {
+                start = atomicAdd(&rs.cursor[lane * CUR_STRIDE], c);
                 const u32 b0 = start >> PB_LOG, b1 = (start + c - 1) >> PB_LOG;
                 u32 *row = rs.bt + (size_t)lane * rs.bt_stride;
                 phys0 = phys1 = 0;
@@ -786,22 +778,95 @@ k_ms_scatter(FS fs, const i64 *__restrict__ val, i64 tiles, RecStore rs, i64 *mm
             d.z = (phys1 - 1) * (u32)PB - (lbase + room);
             d.w = 0;
             s_desc[buf][lane] = d;
-            s_cnt[buf ^ 1][lane] = 0;                                // the other buffer: nobody reads it any more, nobody adds before #2
+            s_cnt[buf ^ 1][lane] = 0;                                // the next tile's counters: last read before the previous barrier B
             if (lane == 31) s_total[buf] = incl;
             if (lane == 0 && ld_relaxed_u32(rs.exc_count) > rs.exc_cap) s_abort = 1;
-        }
-        __syncthreads();                                             // #2: the tile is staged, ordered by partition
-        const u32 total = s_total[buf];
+            __syncthreads();                                         // B
+        } else {
+            mbar_wait(&full[buf], (it >> 1) & 1u);
+            const unsigned char *in = s_in + (size_t)buf * In::BYTES;
+            const KT *const sk = (const KT *)in;
+            const i64 *const sv = (const i64 *)(in + In::KEY_BYTES);
+            // rows of this thread: pairs (j2 * MS_T + tid) of the tile: conflict-free 8 / 16-byte shared-memory reads
+            KT k[MS_R];
+            i64 v[MS_R];
+            bool sel[MS_R];
 #pragma unroll
-        for (int j = 0; j < MS_R; j++) {
-            const u32 q = j * MS_T + tid;
-            if (q < total) {
-                const uint4 d = s_desc[buf][s_part[buf][q]];
-                grec[q + (q < d.y ? d.x : d.z)] = s_rec[buf][q];
+            for (int j2 = 0; j2 < MS_R / 2; j2++) {
+                const int pair = j2 * MS_T + tid;
+                if constexpr (sizeof(KT) == 4) {
+                    const uint2 w = *(const uint2 *)(sk + 2 * pair);
+                    k[2 * j2] = (KT)w.x; k[2 * j2 + 1] = (KT)w.y;
+                } else {
+                    const ulonglong2 w = *(const ulonglong2 *)(sk + 2 * pair);
+                    k[2 * j2] = (KT)w.x; k[2 * j2 + 1] = (KT)w.y;
+                }
+                const ulonglong2 w = *(const ulonglong2 *)(sv + 2 * pair);
+                v[2 * j2] = (i64)w.x; v[2 * j2 + 1] = (i64)w.y;
+                if constexpr (FS::has_pred) {
+                    const PT_ *const sp = (const PT_ *)(in + In::KEY_BYTES + In::VAL_BYTES);
+                    sel[2 * j2] = pred_test(pred_key<PT_>(sp[2 * pair]), fs.pr);
+                    sel[2 * j2 + 1] = pred_test(pred_key<PT_>(sp[2 * pair + 1]), fs.pr);
+                } else { sel[2 * j2] = sel[2 * j2 + 1] = true; }
             }
+            REC rec[MS_R];
+            u32 pp[MS_R];                    // rank among the warp's rows of the partition << 8 | partition (32 = not staged)
+            u32 exc_mask = 0;                // rows of this thread that go to the side list
+            u32 wcount = 0;                  // rows of partition `lane` this warp has ranked so far in this tile
+#pragma unroll
+            for (int j = 0; j < MS_R; j++) {
+                const KT kj = k[j];
+                lo = (sel[j] && kj < lo) ? kj : lo;
+                hi = (sel[j] && kj > hi) ? kj : hi;
+                const bool ok = sel[j] && F::fits(v[j]);
+                exc_mask |= (u32)(sel[j] && !ok) << j;
+                const u32 kb = (u32)kj;
+                const u32 part = (kb >> KPL) & (NP - 1);
+                rec[j] = F::pack(kb & (KPN - 1u), v[j]);
+                // Ranking by ballots: lane L ends up with the set of lanes whose row goes to partition L (five ballots over
+                // the partition bits, each flipped where L's bit is clear); a row then fetches its own partition's set and
+                // running count from lane `part`.  No shared-memory traffic and no atomics per row.
+                u32 pl = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+                for (int b = 0; b < 5; b++) pl &= ballot_bits(kb, 1u << (KPL + b)) ^ cb[b];
+                const u32 peers = __shfl_sync(0xffffffffu, pl, part);
+                const u32 before = __shfl_sync(0xffffffffu, wcount, part);
+                wcount += __popc(pl);
+                pp[j] = ((before + __popc(peers & lt_mask)) << 8) | (ok ? part : 32u);
+            }
+            u32 wbase = 0;
+            if (wcount) wbase = atomicAdd(&s_cnt[buf][lane], wcount);   // one atomic per (warp, partition) and tile, distinct addresses
+            if (exc_mask) {                                              // rare
+#pragma unroll
+                for (int j = 0; j < MS_R; j++)
+                    if (exc_mask & (1u << j)) {
+                        const u32 e = atomicAdd(rs.exc_count, 1u);
+                        if (e < rs.exc_cap) { rs.exc[2 * (size_t)e] = (i64)k[j]; rs.exc[2 * (size_t)e + 1] = v[j]; }
+                    }
+            }
+            __syncthreads();                                         // A: the tile's partition counts are final
+            const u32 c = s_cnt[buf][lane];
+            u32 incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            s_wb[warp][lane] = incl - c + wbase;                     // start of partition `lane` in the staging area + this warp's offset in it
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < MS_R; j++)
+                if (!(pp[j] & 32u)) {
+                    const u32 q = s_wb[warp][pp[j] & 31u] + (pp[j] >> 8);
+                    s_rec[buf][q] = rec[j];
+                    s_part[buf][q] = (u8)(pp[j] & 31u);
+                }
+            if (it > 0) write_out(buf ^ 1);                          // the PREVIOUS tile: its descriptors were complete at its barrier B
+            __syncthreads();                                         // B: this tile is staged and described
         }
-        if (s_abort) break;                                          // written before #2, uniform: the record format was a bad guess
+        if (s_abort) break;                                          // written before B, uniform: the record format was a bad guess
     }
+    if (!ctrl && it > 0 && !s_abort) write_out(buf ^ 1);             // the last tile
     struct Mn { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b < a ? b : a; } };
     struct Mx { __device__ __forceinline__ i64 operator()(i64 a, i64 b) const { return b > a ? b : a; } };
     const i64 lo64 = block_reduce<i64>((i64)lo, Mn(), RFB_INF_I64, red);
@@ -1019,11 +1084,14 @@ static inline i64 buckets_spanned(i64 kmin, i64 kmax, int kpl) { return (kmax >>
 
 template <typename FS, typename REC, int KPL>
 int ms_scatter_launch(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, const RecStore &rs, i64 *mm) {
-    const size_t smem = 2 * (size_t)MS_TILE * (sizeof(REC) + 1);
+    const size_t smem = 2 * MsIn<FS>::BYTES + 2 * (size_t)MS_TILE * (sizeof(REC) + 1);
     const i64 tiles = n / MS_TILE;                 // full tiles; the rest goes through the side list
     if (tiles > 0) {
         RFB_CUDA(cudaFuncSetAttribute(k_ms_scatter<FS, REC, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_ms_scatter<FS, REC, KPL><<<rfb_grid_for(ctx, tiles * MS_TILE, MS_TILE, MS_CTAS), MS_T, smem, ctx->stream>>>(fs, val, tiles, rs, mm);
+        int per_sm = (int)((size_t)(220 << 10) / (smem + 2048));   // CTAs per SM the shared memory allows
+        if (per_sm > MS_CTAS) per_sm = MS_CTAS;
+        if (per_sm < 1) per_sm = 1;
+        k_ms_scatter<FS, REC, KPL><<<rfb_grid_for(ctx, tiles * MS_TILE, MS_TILE, per_sm), MS_T + 32, smem, ctx->stream>>>(fs, val, tiles, rs, mm);
         RFB_CHECK_LAUNCH(ctx);
     }
     if (tiles * MS_TILE < n) {
@@ -1098,7 +1166,7 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
             have_scope = modded = true;
         }
         // narrow path: at most 32 partitions, packed records chosen from a value census of the same row windows
-        if (!modded && vec && h[0] <= h[1] && (forced == 0 || forced == 4) && (forced == 4 || (i64)((u64)h[1] - (u64)h[0]) >= KP) &&
+        if (!modded && vec && fs.tma_ok(val) && h[0] <= h[1] && (forced == 0 || forced == 4) && (forced == 4 || (i64)((u64)h[1] - (u64)h[0]) >= KP) &&
             (u64)h[1] - (u64)h[0] < (u64)NP * KP) {
             i64 *census = mm + 8;
             RFB_CUDA(cudaMemsetAsync(census, 0, 32, ctx->stream));
