@@ -244,9 +244,14 @@ int rfb_aggr_type(int op, int val_type);
  * x*x per group, sqrt(max(sumsq/n - mean^2, 0)); 0 rows -> null, 1 row -> 0. */
 /* op RFB_A_FIRST = aggr_first: the value at each group's first row (null or not: the reference's first_ids fast path);
  * op RFB_A_LAST = aggr_last: each group's last NON-NULL value, null if none (the reference's single-chunk result; above its
- * parallel threshold its own answer depends on the thread count). */
+ * parallel threshold its own answer depends on the thread count, DESIGN.md Q18: rfb_aggr_last_dev takes the chunk count). */
 int rfb_aggr_dev(rfb_ctx_t *ctx, int op, int val_type, const void *val, const int64_t *filter,
                  const int64_t *group_ids, int64_t len, int64_t groups, void *out);
+/* aggr_last exactly as the reference computes it on `nchunks` worker chunks (core/aggr.c:262-295 aggr_map, AGGR_COLLECT with
+ * `if (out == null) out = in`): per group the last non-null value inside the FIRST chunk of len / nchunks rows that has one.
+ * nchunks = the reference's pool_split_by_mem(len, groups, width) (core/pool.c:450-478); 1 = the group's last non-null value. */
+int rfb_aggr_last_dev(rfb_ctx_t *ctx, int val_type, const void *val, const int64_t *filter, const int64_t *group_ids,
+                      int64_t len, int64_t groups, int64_t nchunks, void *out);
 
 /* aggr_row / aggr_collect (core/aggr.c:3021-3136): the rows of every group.  out_rows[len] = row ids (filter[i], or i without
  * a filter) ordered by group id and, inside a group, by position (the order AGGR_ITER pushes them); offsets[groups+1] = where

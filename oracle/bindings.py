@@ -22,7 +22,7 @@ REF_BIN = os.path.join(HERE, "_ref", "rayforce_ref")
 # reference type codes (core/rayforce.h:50-62)
 B8, U8, I16, I32, I64, SYMBOL, DATE, TIME, TIMESTAMP, F64 = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 EQ, NE, LT, GT, LE, GE = range(6)
-SUM, MIN, MAX, CNT, AVG, COUNT, MED, DEV = range(8)
+SUM, MIN, MAX, CNT, AVG, COUNT, MED, DEV, FIRST, LAST = range(10)
 ADD, SUB, MUL, DIV, FDIV, MOD, XBAR = range(7)
 ROUND, FLOOR, CEIL = range(3)
 ATOM = -1
@@ -206,6 +206,22 @@ class Oracle:
         dt = NP_OF[ot.value]
         return out.view(np.uint8)[: groups * np.dtype(dt).itemsize].view(dt).copy(), ot.value
 
+    def aggr_last(self, vt, val, gids, groups, nchunks=1, filt=None):
+        """aggr_last on `nchunks` worker chunks (core/aggr.c:851-1075) -> (array[groups], result type)"""
+        val = np.ascontiguousarray(val, NP_OF[vt])
+        gids = np.ascontiguousarray(gids, np.int64)
+        if filt is not None:
+            filt = np.ascontiguousarray(filt, np.int64)
+        out = np.zeros(max(groups, 1), np.int64)
+        ot = C.c_int(0)
+        self.L.rfo_aggr_last.restype = C.c_int
+        self.L.rfo_aggr_last.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(C.c_int)]
+        r = self.L.rfo_aggr_last(vt, _ptr(val), _ptr(filt), _ptr(gids), gids.shape[0], groups, nchunks, _ptr(out), C.byref(ot))
+        if r < 0:
+            raise OracleError(r)
+        dt = NP_OF[ot.value]
+        return out.view(np.uint8)[: groups * np.dtype(dt).itemsize].view(dt).copy(), ot.value
+
     def parted_aggr(self, op, vt, parts, combine):
         """PARTED_MAP without a filter -> (array of 1 or len(parts) values, result type)"""
         parts = [np.ascontiguousarray(p, NP_OF[vt]) for p in parts]
@@ -370,7 +386,7 @@ class Reference:
             f.argtypes = [vp]
         for name in ("ray_eq", "ray_ne", "ray_lt", "ray_gt", "ray_le", "ray_ge", "ray_add", "ray_sub", "ray_mul",
                      "ray_div", "ray_fdiv", "ray_mod", "ray_xbar", "filter_map", "filter_collect", "index_group", "group_map",
-                     "aggr_sum", "aggr_min", "aggr_max", "aggr_count", "aggr_avg", "aggr_first", "aggr_med", "aggr_dev",
+                     "aggr_sum", "aggr_min", "aggr_max", "aggr_count", "aggr_avg", "aggr_first", "aggr_last", "aggr_med", "aggr_dev",
                      "aggr_row", "aggr_collect"):
             f = getattr(L, name)
             f.restype = vp
@@ -521,7 +537,7 @@ class Reference:
     _CMP = ["ray_eq", "ray_ne", "ray_lt", "ray_gt", "ray_le", "ray_ge"]
     _BIN = ["ray_add", "ray_sub", "ray_mul", "ray_div", "ray_fdiv", "ray_mod", "ray_xbar"]
     _FOLD = ["ray_sum", "ray_min", "ray_max", "ray_cnt", "ray_avg", "ray_count", "ray_med", "ray_dev"]
-    _AGGR = ["aggr_sum", "aggr_min", "aggr_max", None, "aggr_avg", "aggr_count", "aggr_med", "aggr_dev"]
+    _AGGR = ["aggr_sum", "aggr_min", "aggr_max", None, "aggr_avg", "aggr_count", "aggr_med", "aggr_dev", "aggr_first", "aggr_last"]
 
     def _bin(self, name, xt, x, yt, y):
         xo, yo = self.operand(xt, x), self.operand(yt, y)

@@ -522,6 +522,8 @@ int rfo_group_multi(int ncols, const int64_t *const *cols, const int64_t *filter
 
 /* ------------------------------------------------------------------ grouped aggregates (core/aggr.c) */
 
+int rfo_aggr_last(int val_type, const void *val, const int64_t *filter, const int64_t *gid, int64_t len, int64_t groups,
+                  int64_t nchunks, void *out, int *out_type);
 int rfo_aggr(int op, int val_type, const void *val, const int64_t *filter, const int64_t *gid, int64_t len,
              int64_t groups, void *out, int *out_type) {
     int k = kind_of(val_type);
@@ -654,9 +656,63 @@ int rfo_aggr(int op, int val_type, const void *val, const int64_t *filter, const
             free(s); free(q); free(c);
             return RFO_OK;
         }
+        case RFO_FIRST: { /* aggr_first, core/aggr.c:441-577: the index carries first_ids (every index built on this path does), so
+                           * the result is the value AT the group's first row, null or not, in the value's own type */
+            int w = rfo_type_size(val_type);
+            *out_type = val_type;
+            char *seen = (char *)calloc((size_t)(groups > 0 ? groups : 1), 1);
+            for (i64 i = 0; i < len; i++) {
+                i64 g = gid[i];
+                if (!seen[g]) { seen[g] = 1; memcpy((char *)out + (size_t)g * w, (const char *)val + (size_t)ROW(i) * w, (size_t)w); }
+            }
+            free(seen);
+            return RFO_OK;
+        }
+        case RFO_LAST: return rfo_aggr_last(val_type, val, filter, gid, len, groups, 1, out, out_type);
         default: return RFO_ERR_TYPE;
     }
 #undef ROW
+}
+
+/* aggr_last, core/aggr.c:851-1075: aggr_last_partial (:851-893) keeps, per group, the last NON-NULL value of its chunk of rows
+ * (null when the chunk has none); aggr_map (:262-295) cuts the rows into `nchunks` runs of len / nchunks rows (the last takes the
+ * remainder) and AGGR_COLLECT merges the partials in chunk order with `if (out == null) out = in` — a group's answer is its last
+ * non-null value inside the FIRST chunk that has one.  nchunks = pool_split_by_mem(len, groups, width) (core/pool.c:450-478):
+ * 1 below 16384 rows, else the executor count capped by 64 MiB / (groups * width).  No U8/B8 case; the partials are vectors of
+ * the value's own type, so is the result. */
+int rfo_aggr_last(int val_type, const void *val, const int64_t *filter, const int64_t *gid, int64_t len, int64_t groups,
+                  int64_t nchunks, void *out, int *out_type) {
+    int k = kind_of(val_type);
+    if (!k || k == K_U8) return RFO_ERR_TYPE;
+    int w = rfo_type_size(val_type);
+    *out_type = val_type;
+    if (nchunks < 1) nchunks = 1;
+    i64 chunk = len / nchunks;
+    char *has = (char *)calloc((size_t)(groups > 0 ? groups : 1), 1), *tmp_has = (char *)malloc((size_t)(groups > 0 ? groups : 1));
+    char *tmp = (char *)malloc((size_t)(groups > 0 ? groups : 1) * (size_t)w);
+    for (i64 g = 0; g < groups; g++) {   /* typed nulls */
+        if (k == K_I64) ((i64 *)out)[g] = RFO_NULL_I64;
+        else if (k == K_I32) ((i32 *)out)[g] = RFO_NULL_I32;
+        else if (k == K_I16) ((i16 *)out)[g] = RFO_NULL_I16;
+        else ((f64 *)out)[g] = null_f64();
+    }
+    for (i64 c = 0; c < nchunks; c++) {
+        i64 lo = c * chunk, hi = c == nchunks - 1 ? len : lo + chunk;
+        memset(tmp_has, 0, (size_t)(groups > 0 ? groups : 1));
+        for (i64 i = lo; i < hi; i++) {
+            i64 r = filter ? filter[i] : i, g = gid[i];
+            int nul;
+            if (k == K_I64) nul = ((const i64 *)val)[r] == RFO_NULL_I64;
+            else if (k == K_I32) nul = ((const i32 *)val)[r] == RFO_NULL_I32;
+            else if (k == K_I16) nul = ((const i16 *)val)[r] == RFO_NULL_I16;
+            else nul = isnan64(((const f64 *)val)[r]);
+            if (!nul) { tmp_has[g] = 1; memcpy(tmp + (size_t)g * w, (const char *)val + (size_t)r * w, (size_t)w); }
+        }
+        for (i64 g = 0; g < groups; g++)
+            if (!has[g] && tmp_has[g]) { has[g] = 1; memcpy((char *)out + (size_t)g * w, tmp + (size_t)g * w, (size_t)w); }
+    }
+    free(has); free(tmp_has); free(tmp);
+    return RFO_OK;
 }
 
 /* Parted aggregates: PARTED_MAP (core/aggr.c:183-260) and aggr_avg's parted branch (:2065-2127) with no filter.  Every

@@ -26,7 +26,7 @@ enum { RFO_B8 = 1, RFO_U8 = 2, RFO_I16 = 3, RFO_I32 = 4, RFO_I64 = 5, RFO_SYMBOL
        RFO_TIMESTAMP = 9, RFO_F64 = 10 };
 
 enum { RFO_EQ = 0, RFO_NE = 1, RFO_LT = 2, RFO_GT = 3, RFO_LE = 4, RFO_GE = 5 };           /* core/cmp.c:692-697 */
-enum { RFO_SUM = 0, RFO_MIN = 1, RFO_MAX = 2, RFO_CNT = 3, RFO_AVG = 4, RFO_COUNT = 5, RFO_MED = 6, RFO_DEV = 7 };   /* core/math.c:2388-2445, :2529-2700 */
+enum { RFO_SUM = 0, RFO_MIN = 1, RFO_MAX = 2, RFO_CNT = 3, RFO_AVG = 4, RFO_COUNT = 5, RFO_MED = 6, RFO_DEV = 7, RFO_FIRST = 8, RFO_LAST = 9 };   /* core/math.c:2388-2445, :2529-2700 */
 enum { RFO_ADD = 0, RFO_SUB = 1, RFO_MUL = 2, RFO_DIV = 3, RFO_FDIV = 4, RFO_MOD = 5, RFO_XBAR = 6 };    /* core/math.c:2436-2441 */
 enum { RFO_ROUND = 0, RFO_FLOOR = 1, RFO_CEIL = 2 };                                       /* core/math.c:2430-2432 */
 enum { RFO_INDEX_IDS = 0, RFO_INDEX_SHIFT = 1 };                                            /* core/index.h:31-36 */
@@ -95,7 +95,12 @@ int rfo_group_multi(int ncols, const int64_t *const *cols, const int64_t *filter
 int rfo_aggr(int op, int val_type, const void *val, const int64_t *filter, const int64_t *group_ids, int64_t len,
              int64_t groups, void *out, int *out_type);
 
-/* rfo_aggr also takes RFO_MED (aggr_med core/aggr.c:2136-2246) and RFO_DEV (aggr_dev :2250-2906): F64 per group */
+/* rfo_aggr also takes RFO_MED (aggr_med core/aggr.c:2136-2246) and RFO_DEV (aggr_dev :2250-2906): F64 per group;
+ * RFO_FIRST (aggr_first :441-577, first_ids fast path: the value at the group's first row) and RFO_LAST (= rfo_aggr_last, 1 chunk) */
+/* aggr_last (core/aggr.c:851-1075) as the reference computes it on `nchunks` worker chunks: the last non-null value of the group
+ * inside the first chunk that has one */
+int rfo_aggr_last(int val_type, const void *val, const int64_t *filter, const int64_t *group_ids, int64_t len, int64_t groups,
+                  int64_t nchunks, void *out, int *out_type);
 
 /* parted aggregates without a filter: PARTED_MAP (core/aggr.c:183-260), aggr_avg (:2065-2127).  combine: one result over all
  * partitions (groups == 1) vs one per partition. */

@@ -17,7 +17,7 @@ EQ, NE, LT, GT, LE, GE = range(6)
 F_SUM, F_CNT, F_MIN, F_MAX, F_ROWS, F_ALL = 1, 2, 4, 8, 16, 31
 ADD, SUB, MUL, DIV, FDIV, MOD, XBAR = range(7)
 ROUND, FLOOR, CEIL = range(3)
-A_SUM, A_MIN, A_MAX, A_COUNT, A_AVG, A_MED, A_DEV = range(7)
+A_SUM, A_MIN, A_MAX, A_COUNT, A_AVG, A_MED, A_DEV, A_FIRST, A_LAST = range(9)
 INDEX_IDS, INDEX_SHIFT = 0, 1
 M_AND, M_OR, M_NOT = 0, 1, 2
 OK, ERR_TYPE, ERR_LENGTH, ERR_CUDA, ERR_ARG, ERR_NOMEM = 0, -1, -2, -3, -4, -5
@@ -134,6 +134,7 @@ SIGNATURES = {
     "rfb_group_keys_i64_dev": (_ci, [_vp, _ci, _P(_vp), _vp, _i64, _vp, _vp, _P(GroupInfo)]),
     "rfb_aggr_type": (_ci, [_ci, _ci]),
     "rfb_aggr_dev": (_ci, [_vp, _ci, _ci, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "rfb_aggr_last_dev": (_ci, [_vp, _ci, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "rfb_group_rows_dev": (_ci, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "rfb_med_dev": (_ci, [_vp, _ci, _vp, _i64, _P(C.c_double)]),
     "rfb_stddev_dev": (_ci, [_vp, _ci, _vp, _i64, _P(C.c_double)]),

@@ -256,14 +256,23 @@ finalise:
 //        computes for one chunk of rows (aggr_last_partial); with several worker chunks its merge keeps the FIRST chunk's
 //        answer (AGGR_COLLECT `if (out == NULL) out = in`), so above its 16384-row parallel threshold its own result depends
 //        on the thread count.
+// LAST over worker chunks: position key = chunk << 40 | (2^40 - 1 - row), minimised: the first chunk with a non-null value wins,
+// inside it the last row.  chunk = row / chunk_rows capped at nchunks - 1 (the last chunk takes the remainder rows).
+constexpr u64 POS_MASK = (1ull << 40) - 1;
 template <typename V, bool LAST>
 __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
-k_aggr_pos(const V *__restrict__ val, ValRow row, const i64 *__restrict__ gid, i64 len, u64 *pos) {
+k_aggr_pos(const V *__restrict__ val, ValRow row, const i64 *__restrict__ gid, i64 len, i64 chunk_rows, i64 nchunks, u64 *pos) {
     for (i64 i = (i64)blockIdx.x * THREADS + threadIdx.x; i < len; i += (i64)gridDim.x * THREADS) {
         const i64 g = ld_stream(gid + i);
         if constexpr (LAST) {
             if (Elem<V>::is_null(val[row(i)])) continue;
-            if (__ldcg(&pos[g]) < (u64)(i + 1)) atomicMax((unsigned long long *)&pos[g], (unsigned long long)(i + 1));   // 0 = none yet
+            u64 c = 0;
+            if (nchunks > 1) {
+                c = len < (1ll << 32) ? (u64)((u32)i / (u32)chunk_rows) : (u64)i / (u64)chunk_rows;
+                if (c > (u64)(nchunks - 1)) c = (u64)(nchunks - 1);
+            }
+            const u64 key = (c << 40) | (POS_MASK - (u64)i);
+            if (__ldcg(&pos[g]) > key) atomicMin((unsigned long long *)&pos[g], (unsigned long long)key);
         } else {
             if (__ldcg(&pos[g]) > (u64)i) atomicMin((unsigned long long *)&pos[g], (unsigned long long)i);
         }
@@ -273,20 +282,32 @@ template <typename V, bool LAST>
 __global__ void __launch_bounds__(256) k_aggr_pos_final(const V *__restrict__ val, ValRow row, const u64 *__restrict__ pos, i64 groups, V *out) {
     for (i64 g = (i64)blockIdx.x * 256 + threadIdx.x; g < groups; g += (i64)gridDim.x * 256) {
         const u64 p = pos[g];
-        if constexpr (LAST) out[g] = p ? val[row((i64)p - 1)] : Elem<V>::null();
-        else out[g] = p != NO_ROW ? val[row((i64)p)] : Elem<V>::null();
+        if (p == NO_ROW) out[g] = Elem<V>::null();
+        else out[g] = val[row(LAST ? (i64)(POS_MASK - (p & POS_MASK)) : (i64)p)];
     }
 }
 template <typename V, bool LAST>
-int run_pos(rfb_ctx_t *ctx, const void *val, const i64 *filter, const i64 *gid, i64 len, i64 groups, u64 *pos, void *out) {
-    RFB_CUDA(cudaMemsetAsync(pos, LAST ? 0 : 0xFF, (size_t)groups * 8, ctx->stream));
+int run_pos(rfb_ctx_t *ctx, const void *val, const i64 *filter, const i64 *gid, i64 len, i64 groups, i64 nchunks, u64 *pos, void *out) {
+    if (len >= (1ll << 40)) { rfb_set_error("aggr_first / aggr_last: more than 2^40 rows"); return RFB_ERR_ARG; }
+    if (nchunks < 1 || len / nchunks == 0) nchunks = 1;
+    RFB_CUDA(cudaMemsetAsync(pos, 0xFF, (size_t)groups * 8, ctx->stream));
     if (len > 0) {
-        k_aggr_pos<V, LAST><<<rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>((const V *)val, ValRow{filter}, gid, len, pos);
+        k_aggr_pos<V, LAST><<<rfb_grid_for(ctx, len, THREADS * 4, BLOCKS_PER_SM), THREADS, 0, ctx->stream>>>((const V *)val, ValRow{filter}, gid, len, len / nchunks, nchunks, pos);
         RFB_CHECK_LAUNCH(ctx);
     }
     k_aggr_pos_final<V, LAST><<<rfb_grid_for(ctx, groups, 256, 8), 256, 0, ctx->stream>>>((const V *)val, ValRow{filter}, pos, groups, (V *)out);
     RFB_CHECK_LAUNCH(ctx);
     return RFB_OK;
+}
+
+int pos_dispatch(rfb_ctx_t *ctx, bool last, int k, const void *val, const i64 *filter, const i64 *gid, i64 len, i64 groups, i64 nchunks, u64 *pos, void *out) {
+    switch (k) {
+        case K_U8: return run_pos<u8, false>(ctx, val, filter, gid, len, groups, 1, pos, out);
+        case K_I16: return last ? run_pos<i16, true>(ctx, val, filter, gid, len, groups, nchunks, pos, out) : run_pos<i16, false>(ctx, val, filter, gid, len, groups, 1, pos, out);
+        case K_I32: return last ? run_pos<i32, true>(ctx, val, filter, gid, len, groups, nchunks, pos, out) : run_pos<i32, false>(ctx, val, filter, gid, len, groups, 1, pos, out);
+        case K_I64: return last ? run_pos<i64, true>(ctx, val, filter, gid, len, groups, nchunks, pos, out) : run_pos<i64, false>(ctx, val, filter, gid, len, groups, 1, pos, out);
+        default: return last ? run_pos<f64, true>(ctx, val, filter, gid, len, groups, nchunks, pos, out) : run_pos<f64, false>(ctx, val, filter, gid, len, groups, 1, pos, out);
+    }
 }
 
 }  // namespace
@@ -303,8 +324,7 @@ extern "C" int rfb_aggr_type(int op, int val_type) {
         case RFB_A_AVG: return (val_type == RFB_I16 || k == K_I32 || val_type == RFB_I64 || k == K_F64) ? RFB_F64 : RFB_ERR_TYPE;
         case RFB_A_MED: return RFB_F64;   // aggr_collect takes every column type; types without a median give nulls (core/aggr.c:2182-2184)
         case RFB_A_FIRST: return val_type;   // every fixed-width type (core/aggr.c:455-573)
-        // aggr_last has no U8/B8 case, and its I64-kind results are plain I64 vectors (core/aggr.c:904-931: no retyping)
-        case RFB_A_LAST: return k == K_U8 ? RFB_ERR_TYPE : (k == K_I64 ? RFB_I64 : val_type);
+        case RFB_A_LAST: return k == K_U8 ? RFB_ERR_TYPE : val_type;   // aggr_last has no U8/B8 case (core/aggr.c:904-931)
         case RFB_A_DEV: return (val_type == RFB_I16 || k == K_I32 || val_type == RFB_I64 || val_type == RFB_TIMESTAMP || k == K_F64) ? RFB_F64 : RFB_ERR_TYPE;   // core/aggr.c:2873-2880
         default: return RFB_ERR_TYPE;
     }
@@ -323,16 +343,36 @@ extern "C" int rfb_aggr_dev(rfb_ctx_t *ctx, int op, int val_type, const void *va
     int rc = rfb_ensure_work(ctx, 2 * align256((size_t)groups * 8), &w);
     if (rc) return rc;
     void *acc = w, *aux = (char *)w + align256((size_t)groups * 8);
-    if (op == RFB_A_FIRST || op == RFB_A_LAST) {
-        const bool last = op == RFB_A_LAST;
-        switch (k) {
-            case K_U8: return run_pos<u8, false>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out);
-            case K_I16: return last ? run_pos<i16, true>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out) : run_pos<i16, false>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out);
-            case K_I32: return last ? run_pos<i32, true>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out) : run_pos<i32, false>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out);
-            case K_I64: return last ? run_pos<i64, true>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out) : run_pos<i64, false>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out);
-            default: return last ? run_pos<f64, true>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out) : run_pos<f64, false>(ctx, val, filter, group_ids, len, groups, (u64 *)acc, out);
+    // 1e4 .. 2.6e5 groups of i64 values: sum / avg through the key-range partition passes of the fused group-by (group id = key)
+    if ((op == RFB_A_SUM || op == RFB_A_AVG) && k == K_I64 && !filter && groups > PRIV32_GROUPS && len >= 65536) {
+        const size_t g8 = align256((size_t)groups * 8);
+        rc = rfb_ensure_work(ctx, 3 * g8 + rfb_narrow_sums_bytes(len), &w);
+        if (rc) return rc;
+        acc = w; aux = (char *)w + g8;
+        void *third = (char *)w + 2 * g8, *store = (char *)w + 3 * g8;
+        bool done = false;
+        if (op == RFB_A_SUM) {       // sums straight into `out`, sticky-null flags in aux, row counts (unused) in the third array
+            RFB_CUDA(cudaMemsetAsync(out, 0, (size_t)groups * 8, ctx->stream));
+            RFB_CUDA(cudaMemsetAsync(aux, 0, 2 * g8, ctx->stream));
+            rc = rfb_narrow_sums(ctx, group_ids, (const i64 *)val, len, groups, store, (u64 *)out, (u64 *)third, (u32 *)aux, true, &done);
+            if (rc) return rc;
+            if (done) {
+                k_aggr_final<AK_SUM_I64><<<rfb_grid_for(ctx, groups, 256, 8), 256, 0, ctx->stream>>>(out, out, aux, groups);
+                RFB_CHECK_LAUNCH(ctx);
+                return RFB_OK;
+            }
+        } else {                     // sums in acc, non-null counts in aux, null flags (unused) in the third array
+            RFB_CUDA(cudaMemsetAsync(acc, 0, 3 * g8, ctx->stream));
+            rc = rfb_narrow_sums(ctx, group_ids, (const i64 *)val, len, groups, store, (u64 *)acc, (u64 *)aux, (u32 *)third, false, &done);
+            if (rc) return rc;
+            if (done) {
+                k_aggr_final<AK_AVG_I64><<<rfb_grid_for(ctx, groups, 256, 8), 256, 0, ctx->stream>>>(out, acc, aux, groups);
+                RFB_CHECK_LAUNCH(ctx);
+                return RFB_OK;
+            }
         }
     }
+    if (op == RFB_A_FIRST || op == RFB_A_LAST) return pos_dispatch(ctx, op == RFB_A_LAST, k, val, filter, group_ids, len, groups, 1, (u64 *)acc, out);
     switch (op) {
         case RFB_A_COUNT:
             RFB_CUDA(cudaMemsetAsync(out, 0, (size_t)groups * 8, ctx->stream));
@@ -378,4 +418,15 @@ extern "C" int rfb_aggr_dev(rfb_ctx_t *ctx, int op, int val_type, const void *va
             RFB_CHECK_LAUNCH(ctx);
             return RFB_OK;
     }
+}
+
+extern "C" int rfb_aggr_last_dev(rfb_ctx_t *ctx, int val_type, const void *val, const int64_t *filter, const int64_t *group_ids,
+                                 int64_t len, int64_t groups, int64_t nchunks, void *out) {
+    RFB_ARG(ctx && len >= 0 && groups >= 0 && ((val && group_ids) || len == 0) && (out || groups == 0), "rfb_aggr_last_dev");
+    if (rfb_aggr_type(RFB_A_LAST, val_type) < 0) { rfb_set_error("aggr_last: unsupported value type %d", val_type); return RFB_ERR_TYPE; }
+    if (groups == 0) return RFB_OK;
+    void *w;
+    int rc = rfb_ensure_work(ctx, align256((size_t)groups * 8), &w);
+    if (rc) return rc;
+    return pos_dispatch(ctx, true, rfb_kind_of(val_type), val, filter, group_ids, len, groups, nchunks, (u64 *)w, out);
 }

@@ -682,6 +682,9 @@ template <typename FS> struct MsIn {   // one input stage
     typedef typename FS::pred_t PT_;
     static constexpr size_t KEY_BYTES = MS_TILE * sizeof(KT), VAL_BYTES = MS_TILE * 8, PRED_BYTES = FS::has_pred ? MS_TILE * sizeof(PT_) : 0;
     static constexpr size_t BYTES = KEY_BYTES + VAL_BYTES + PRED_BYTES;
+    // a predicate on the aggregated column itself (`where (< v k)` next to `(sum v)`) reads the staged values: no third slice
+    __host__ __device__ static bool pred_is_val(const FS &fs, const i64 *val) { return FS::has_pred && sizeof(PT_) == 8 && (const void *)fs.pred == (const void *)val; }
+    __host__ __device__ static size_t bytes(const FS &fs, const i64 *val) { return pred_is_val(fs, val) ? KEY_BYTES + VAL_BYTES : BYTES; }
 };
 
 // Warp roles: MS_WARPS data warps rank, stage and write out rows; one extra CONTROL warp (lane = partition) owns everything
@@ -697,9 +700,11 @@ k_ms_scatter(FS fs, const i64 *__restrict__ val, i64 tiles, RecStore rs, i64 *mm
     typedef typename FS::pred_t PT_;
     constexpr u32 KPN = 1u << KPL;
     extern __shared__ __align__(16) unsigned char s_dyn[];
+    const bool pred_alias = In::pred_is_val(fs, val);
+    const size_t in_bytes = In::bytes(fs, val);
     unsigned char *const s_in = s_dyn;                                                        // [2] input stages: keys | values | predicate column
-    REC (*const s_rec)[MS_TILE] = (REC (*)[MS_TILE])(s_dyn + 2 * In::BYTES);                  // [2][MS_TILE] staged records
-    u8 (*const s_part)[MS_TILE] = (u8 (*)[MS_TILE])(s_dyn + 2 * In::BYTES + 2 * MS_TILE * sizeof(REC));   // [2][MS_TILE] partition of every staged record
+    REC (*const s_rec)[MS_TILE] = (REC (*)[MS_TILE])(s_dyn + 2 * in_bytes);                   // [2][MS_TILE] staged records
+    u8 (*const s_part)[MS_TILE] = (u8 (*)[MS_TILE])(s_dyn + 2 * in_bytes + 2 * MS_TILE * sizeof(REC));   // [2][MS_TILE] partition of every staged record
     __shared__ u64 full[2];
     __shared__ u32 s_cnt[2][NP];
     __shared__ u32 s_wb[MS_WARPS][NP];   // per data warp: where its rows of each partition start in the tile's staging area
@@ -724,11 +729,12 @@ k_ms_scatter(FS fs, const i64 *__restrict__ val, i64 tiles, RecStore rs, i64 *mm
     }
     __syncthreads();
     auto issue = [&](i64 tile, int st) {          // one lane: the three slices of one tile
-        unsigned char *dst = s_in + (size_t)st * In::BYTES;
-        mbar_expect_tx(&full[st], (u32)In::BYTES);
+        unsigned char *dst = s_in + (size_t)st * in_bytes;
+        mbar_expect_tx(&full[st], (u32)in_bytes);
         bulk_g2s(dst, fs.keys + tile * MS_TILE, (u32)In::KEY_BYTES, &full[st]);
         bulk_g2s(dst + In::KEY_BYTES, val + tile * MS_TILE, (u32)In::VAL_BYTES, &full[st]);
-        if constexpr (FS::has_pred) bulk_g2s(dst + In::KEY_BYTES + In::VAL_BYTES, fs.pred + tile * MS_TILE, (u32)In::PRED_BYTES, &full[st]);
+        if constexpr (FS::has_pred)
+            if (!pred_alias) bulk_g2s(dst + In::KEY_BYTES + In::VAL_BYTES, fs.pred + tile * MS_TILE, (u32)In::PRED_BYTES, &full[st]);
     };
     auto write_out = [&](int b) {                 // data warps: the staged tile in buffer b, linearly
         const u32 total = s_total[b];
@@ -784,7 +790,7 @@ k_ms_scatter(FS fs, const i64 *__restrict__ val, i64 tiles, RecStore rs, i64 *mm
             __syncthreads();                                         // B
         } else {
             mbar_wait(&full[buf], (it >> 1) & 1u);
-            const unsigned char *in = s_in + (size_t)buf * In::BYTES;
+            const unsigned char *in = s_in + (size_t)buf * in_bytes;
             const KT *const sk = (const KT *)in;
             const i64 *const sv = (const i64 *)(in + In::KEY_BYTES);
             // rows of this thread: pairs (j2 * MS_T + tid) of the tile: conflict-free 8 / 16-byte shared-memory reads
@@ -804,7 +810,7 @@ k_ms_scatter(FS fs, const i64 *__restrict__ val, i64 tiles, RecStore rs, i64 *mm
                 const ulonglong2 w = *(const ulonglong2 *)(sv + 2 * pair);
                 v[2 * j2] = (i64)w.x; v[2 * j2 + 1] = (i64)w.y;
                 if constexpr (FS::has_pred) {
-                    const PT_ *const sp = (const PT_ *)(in + In::KEY_BYTES + In::VAL_BYTES);
+                    const PT_ *const sp = (const PT_ *)(in + In::KEY_BYTES + (pred_alias ? 0 : In::VAL_BYTES));
                     sel[2 * j2] = pred_test(pred_key<PT_>(sp[2 * pair]), fs.pr);
                     sel[2 * j2 + 1] = pred_test(pred_key<PT_>(sp[2 * pair + 1]), fs.pr);
                 } else { sel[2 * j2] = sel[2 * j2 + 1] = true; }
@@ -903,13 +909,27 @@ __device__ __forceinline__ void sacc_add_small(const SAcc &a, u32 s, i64 v) {
 // accumulate pass of the narrow path: one CTA per SM, the partition's records staged by the TMA unit (cp.async.bulk into an
 // mbarrier ring) next to the partition's 2^KPL accumulators.  Partition p = absolute bucket ((kbase >> KPL) + p) mod 32.
 constexpr int MS_UNIT = 4096;                   // records per work unit
-template <typename REC> struct MsRing { static constexpr int STAGES = sizeof(REC) == 4 ? 4 : 3; };
+// Geometry of the accumulate pass.  The pass is bound by shared-memory atomics (two per record, ~3.5-way bank conflicts on random
+// slots) and by the latency of the returning one: two 512-thread CTAs per SM (each with its own copy of the partition's
+// accumulators and a 3-stage ring) hide it better than one 1024-thread CTA — measured 1.49 -> 1.19 ms per 1e9 records.
+#ifndef RFB_MSA_T
+#define RFB_MSA_T 512
+#define RFB_MSA_CTAS 2
+#define RFB_MSA_STAGES 3
+#endif
+// 8192-slot partitions (96 KB of accumulators) leave room for one CTA per SM only: 1024 threads, 4 / 3 stages.
+template <typename REC, int KPL> struct MsaCfg {
+    static constexpr bool TWO = KPL <= 12 && RFB_MSA_CTAS > 1;
+    static constexpr int T = TWO ? RFB_MSA_T : 1024, CTAS = TWO ? RFB_MSA_CTAS : 1;
+    static constexpr int STAGES = TWO ? RFB_MSA_STAGES : (sizeof(REC) == 4 ? 4 : 3);
+};
 
 template <typename REC, int KPL>
-__global__ void __launch_bounds__(AT, 1)
+__global__ void __launch_bounds__((MsaCfg<REC, KPL>::T), (MsaCfg<REC, KPL>::CTAS))
 k_ms_accum_tma(RecStore rs, int P, i64 kbase, i64 kmin, Accums ga) {
     typedef RecFmt<REC, KPL> F;
-    constexpr int KPN = 1 << KPL, STAGES = MsRing<REC>::STAGES, PER = MS_UNIT / AT;   // records per thread and unit
+    constexpr int KPN = 1 << KPL, STAGES = MsaCfg<REC, KPL>::STAGES, MSA_T = MsaCfg<REC, KPL>::T, PER = 4;   // records per thread and step
+    static_assert(MS_UNIT % (MSA_T * PER) == 0, "whole steps of four records per thread");
     extern __shared__ __align__(16) unsigned char s_dyn[];
     REC *stage = (REC *)s_dyn;                                                  // STAGES x MS_UNIT records
     u32 *s_acc = (u32 *)(s_dyn + (size_t)STAGES * MS_UNIT * sizeof(REC));       // lo[KPN] | hi[KPN] | cnt[KPN]
@@ -974,7 +994,8 @@ k_ms_accum_tma(RecStore rs, int P, i64 kbase, i64 kmin, Accums ga) {
         mbar_wait(&full[s], (k / STAGES) & 1u);
         dirty = true;
         const REC *st = stage + (size_t)s * MS_UNIT;
-        const u32 q0 = (u32)tid * PER;
+#pragma unroll
+        for (u32 q0 = (u32)tid * PER; q0 < (u32)MS_UNIT; q0 += MSA_T * PER)
         if (q0 + PER <= rows) {
             REC r[PER];
             if constexpr (sizeof(REC) == 4) {
@@ -993,16 +1014,16 @@ k_ms_accum_tma(RecStore rs, int P, i64 kbase, i64 kmin, Accums ga) {
     __syncthreads();
     if (dirty) sacc_flush(a, KPN, (i64)((u64)kbase + (u64)p * KPN - (u64)kmin), ga);
 }
-static_assert(MS_UNIT / AT == 4, "k_ms_accum_tma reads four records per thread");
+
 
 // the exception rows of the narrow path: device-wide accumulators, L2 atomics
-__global__ void __launch_bounds__(THREADS) k_ms_exceptions(const i64 *__restrict__ exc, const u32 *__restrict__ exc_count, i64 kmin, Accums a) {
+__global__ void __launch_bounds__(THREADS) k_ms_exceptions(const i64 *__restrict__ exc, const u32 *__restrict__ exc_count, i64 kmin, Accums a, bool nulls_count) {
     const u32 m = *exc_count;
     for (u32 i = blockIdx.x * THREADS + threadIdx.x; i < m; i += gridDim.x * THREADS) {
         const i64 k = exc[2 * (size_t)i], v = exc[2 * (size_t)i + 1];
         const i64 s = (i64)((u64)k - (u64)kmin);
         if (v == NULL_I64) a.has_null[s] = 1u; else atomicAdd((unsigned long long *)a.sum + s, (unsigned long long)v);
-        atomicAdd((unsigned long long *)a.cnt + s, 1ULL);
+        if (v != NULL_I64 || nulls_count) atomicAdd((unsigned long long *)a.cnt + s, 1ULL);
     }
 }
 
@@ -1084,7 +1105,7 @@ static inline i64 buckets_spanned(i64 kmin, i64 kmax, int kpl) { return (kmax >>
 
 template <typename FS, typename REC, int KPL>
 int ms_scatter_launch(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, const RecStore &rs, i64 *mm) {
-    const size_t smem = 2 * MsIn<FS>::BYTES + 2 * (size_t)MS_TILE * (sizeof(REC) + 1);
+    const size_t smem = 2 * MsIn<FS>::bytes(fs, val) + 2 * (size_t)MS_TILE * (sizeof(REC) + 1);
     const i64 tiles = n / MS_TILE;                 // full tiles; the rest goes through the side list
     if (tiles > 0) {
         RFB_CUDA(cudaFuncSetAttribute(k_ms_scatter<FS, REC, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1102,9 +1123,10 @@ int ms_scatter_launch(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, const RecSto
 }
 template <typename REC, int KPL>
 int ms_accum_launch(rfb_ctx_t *ctx, const RecStore &rs, int P, i64 kbase, i64 kmin, const Accums &a) {
-    const size_t smem = (size_t)MsRing<REC>::STAGES * MS_UNIT * sizeof(REC) + (size_t)(1 << KPL) * 12;
+    typedef MsaCfg<REC, KPL> C;
+    const size_t smem = (size_t)C::STAGES * MS_UNIT * sizeof(REC) + (size_t)(1 << KPL) * 12;
     RFB_CUDA(cudaFuncSetAttribute(k_ms_accum_tma<REC, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_ms_accum_tma<REC, KPL><<<ctx->sm_count, AT, smem, ctx->stream>>>(rs, P, kbase, kmin, a);
+    k_ms_accum_tma<REC, KPL><<<ctx->sm_count * C::CTAS, C::T, smem, ctx->stream>>>(rs, P, kbase, kmin, a);
     RFB_CHECK_LAUNCH(ctx);
     return RFB_OK;
 }
@@ -1298,7 +1320,7 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
         else if (plan.rec_bytes == 4) rc = ms_accum_launch<u32, 13>(ctx, rs, np, kb, kmin, a);
         else rc = ms_accum_launch<u64, 13>(ctx, rs, np, kb, kmin, a);
         if (rc) return rc;
-        k_ms_exceptions<<<rfb_grid_for(ctx, rs.exc_cap, THREADS, 2), THREADS, 0, ctx->stream>>>(rs.exc, rs.exc_count, kmin, a);
+        k_ms_exceptions<<<rfb_grid_for(ctx, rs.exc_cap, THREADS, 2), THREADS, 0, ctx->stream>>>(rs.exc, rs.exc_count, kmin, a, true);
         RFB_CHECK_LAUNCH(ctx);
     } else if (strategy == 2) {
         const char *tma = getenv("RFB_ACCUM_TMA");       // "0": the register-staged kernel (128-bit loads) instead of the TMA ring
@@ -1376,7 +1398,92 @@ int fused_key(rfb_ctx_t *ctx, const void *keys, int cmp_op, int pred_type, const
     }
 }
 
+// carve the narrow path's block store out of a workspace region
+size_t narrow_store_bytes(i64 n, int rec_bytes) {
+    const u32 blocks = (u32)((n + PB - 1) / PB) + NP + 1, bt_stride = (u32)((n + PB - 1) / PB) + 1;
+    i64 cap = n / 64 > 4096 ? n / 64 : 4096;
+    if (cap > (1ll << 23)) cap = 1ll << 23;
+    return align256((size_t)(NP + 2) * CUR_STRIDE * 4) + align256((size_t)NP * bt_stride * 4) + align256((size_t)blocks * PB * rec_bytes) + align256((size_t)cap * 16);
+}
+int narrow_store_init(rfb_ctx_t *ctx, char *pw, i64 n, int rec_bytes, RecStore *rs) {
+    const u32 blocks = (u32)((n + PB - 1) / PB) + NP + 1, bt_stride = (u32)((n + PB - 1) / PB) + 1;
+    i64 cap = n / 64 > 4096 ? n / 64 : 4096;
+    if (cap > (1ll << 23)) cap = 1ll << 23;
+    const size_t ctl_bytes = align256((size_t)(NP + 2) * CUR_STRIDE * 4), bt_bytes = align256((size_t)NP * bt_stride * 4);
+    const size_t rec_total = align256((size_t)blocks * PB * rec_bytes);
+    rs->cursor = (u32 *)pw;
+    rs->next_block = rs->cursor + NP * CUR_STRIDE;
+    rs->exc_count = rs->cursor + (NP + 1) * CUR_STRIDE;
+    rs->bt = (u32 *)(pw + ctl_bytes);
+    rs->bt_stride = bt_stride;
+    rs->exc_cap = (u32)cap;
+    rs->rec = pw + ctl_bytes + bt_bytes;
+    rs->exc = (i64 *)(pw + ctl_bytes + bt_bytes + rec_total);
+    RFB_CUDA(cudaMemsetAsync(pw, 0, ctl_bytes + bt_bytes, ctx->stream));
+    return RFB_OK;
+}
+
 }  // namespace
+
+// ---- grouped sums over DENSE group ids through the narrow partitioned passes (rfb_aggr_dev at 1e4 .. 2.6e5 groups: two
+// shared-memory atomics per row in the accumulate pass instead of two L2 atomics).  sum / cnt / has_null are the caller's
+// zero-initialised device-wide arrays of `groups` slots; cnt counts the rows of each group (nulls_count) or its non-null rows.
+// *done = false: not applicable (small input, too many groups, unaligned columns, values that fit no record format) — nothing
+// was written, the caller takes its own path.
+size_t rfb_narrow_sums_bytes(i64 n) { return narrow_store_bytes(n, 8); }
+
+int rfb_narrow_sums(rfb_ctx_t *ctx, const i64 *gid, const i64 *val, i64 n, i64 groups, void *work, u64 *sum, u64 *cnt, u32 *has_null,
+                    bool nulls_count, bool *done) {
+    *done = false;
+    const int forced = group_strategy_forced();
+    if (forced == 3 || n < part_min_rows() || n >= 0xF0000000ll || groups > ((i64)NP << 13) || !aligned16(gid) || !aligned16(val)) return RFB_OK;
+    typedef FusedSrc<i64, i64, false> FS;
+    FS fs{gid, nullptr, PredRange{0, 0, 0, 0}};
+    i64 *mm = (i64 *)((char *)ctx->d_scratch + 32768), *census = mm + 8;
+    RFB_CUDA(cudaMemsetAsync(census, 0, 32, ctx->stream));
+    const i64 win = 65536;
+    const i64 starts[3] = {0, n / 2 > win ? n / 2 : 0, n > win ? n - win : 0};
+    for (int s = 0; s < 3; s++) {
+        const i64 r0 = starts[s], r1 = r0 + win < n ? r0 + win : n;
+        k_val_census_rows<FS><<<64, THREADS, 0, ctx->stream>>>(fs, val, r0, r1, census);
+        RFB_CHECK_LAUNCH(ctx);
+    }
+    i64 c[4], h[2];
+    int rc = d2h_sync(ctx, c, census, 32);
+    if (rc) return rc;
+    const i64 tol = c[3] / 64;
+    NarrowPlan plan{0, 0};
+    if (groups <= ((i64)NP << 12) && c[1] <= tol) plan = NarrowPlan{4, 12};
+    else if (c[0] <= tol) plan = NarrowPlan{4, 13};
+    else if (c[2] <= tol) plan = NarrowPlan{8, 13};
+    else return RFB_OK;
+    RecStore rs{};
+    rc = narrow_store_init(ctx, (char *)work, n, plan.rec_bytes, &rs);
+    if (rc) return rc;
+    k_fused_scope_init<<<1, 32, 0, ctx->stream>>>(mm);
+    RFB_CHECK_LAUNCH(ctx);
+    if (plan.rec_bytes == 4 && plan.kpl == 12) rc = ms_scatter_launch<FS, u32, 12>(ctx, fs, val, n, rs, mm);
+    else if (plan.rec_bytes == 4) rc = ms_scatter_launch<FS, u32, 13>(ctx, fs, val, n, rs, mm);
+    else rc = ms_scatter_launch<FS, u64, 13>(ctx, fs, val, n, rs, mm);
+    if (rc) return rc;
+    u32 exc_n = 0;
+    RFB_CUDA(cudaMemcpyAsync(&exc_n, rs.exc_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = d2h_sync(ctx, h, mm, 16);
+    if (rc) return rc;
+    if (exc_n > rs.exc_cap) return RFB_OK;               // the sample misjudged the values: aborted early, nothing accumulated yet
+    if (h[0] <= h[1] && (h[0] < 0 || h[1] >= groups)) { rfb_set_error("grouped aggregate: group id outside [0, %lld)", (long long)groups); return RFB_ERR_ARG; }
+    Accums a;
+    a.first_row = nullptr; a.sum = sum; a.cnt = cnt; a.has_null = has_null;
+    const int np = (int)((groups + ((i64)1 << plan.kpl) - 1) >> plan.kpl);
+    if (plan.rec_bytes == 4 && plan.kpl == 12) rc = ms_accum_launch<u32, 12>(ctx, rs, np, 0, 0, a);
+    else if (plan.rec_bytes == 4) rc = ms_accum_launch<u32, 13>(ctx, rs, np, 0, 0, a);
+    else rc = ms_accum_launch<u64, 13>(ctx, rs, np, 0, 0, a);
+    if (rc) return rc;
+    k_ms_exceptions<<<rfb_grid_for(ctx, rs.exc_cap, THREADS, 2), THREADS, 0, ctx->stream>>>(rs.exc, rs.exc_count, 0, a, nulls_count);
+    RFB_CHECK_LAUNCH(ctx);
+    *done = true;
+    return RFB_OK;
+}
 
 extern "C" int rfb_group_sum_count_dev(rfb_ctx_t *ctx, int key_type, const void *keys, const int64_t *val, int64_t n,
                                        int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k,

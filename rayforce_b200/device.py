@@ -313,6 +313,16 @@ class _Ops:
         self.sync()
         return out, ot
 
+    def aggr_last(self, vt, val, gids, groups, nchunks=1, filt=None):
+        """aggr_last as the reference computes it on `nchunks` worker chunks -> (tensor[groups], result type)"""
+        ot = self.lib.rfb_aggr_type(capi.A_LAST, vt)
+        if ot < 0:
+            raise RfbError(ot, "aggr_last: unsupported value type %d" % vt)
+        out = self._empty(groups, ot)
+        check(self.lib.rfb_aggr_last_dev(self.h, vt, _dptr(val), _dptr(filt), _dptr(gids), gids.shape[0], groups, nchunks, _dptr(out)))
+        self.sync()
+        return out, ot
+
     def group_rows(self, gids, groups, filt=None):
         """aggr_row / aggr_collect layout -> (row ids grouped by gid in row order, offsets[groups+1])"""
         n = gids.shape[0]

@@ -335,6 +335,58 @@ def test_aggr(ctx, oracle, op, vt, filtered, card):
     assert same_f64(host(got), want, zero_sign=False) if wt == ob.F64 else np.array_equal(host(got), want)
 
 
+@pytest.mark.parametrize("vt", [ob.I64, ob.F64, ob.I32, ob.I16, ob.TIME, ob.TIMESTAMP, ob.DATE, ob.U8])
+@pytest.mark.parametrize("filtered", [False, True])
+@pytest.mark.parametrize("n,card", [(9, 3), (16_385, 100), (200_003, 5000)])
+def test_aggr_first_last(ctx, oracle, vt, filtered, n, card):
+    """aggr_first (value at the group's first row, nulls included) and aggr_last (last non-null value of the first worker chunk
+    that has one, for 1 / 3 / 16 chunks: the reference's answer at 1 / 3 / 16 executors) against the oracle, which is pinned
+    against the compiled reference in tests/test_oracle_vs_reference.py::test_grouped_first_and_last"""
+    r = np.random.default_rng(n + vt)
+    keys = r.integers(0, card, n).astype(np.int64)
+    val = rng_col(vt, n, seed=vt + 5, null_frac=0.4, lo=-1000 if vt != ob.U8 else 0, hi=1000 if vt != ob.U8 else 200)
+    filt = np.sort(r.choice(n, max(1, n // 2), replace=False)).astype(np.int64) if filtered else None
+    wg, wf, wi = oracle.group_i64(keys, filt)
+    want, wt = oracle.aggr(ob.FIRST, vt, val, wg, wi.groups, filt)
+    got, gt = ctx.aggr(capi.A_FIRST, vt, dev(val), dev(wg), wi.groups, dev(filt) if filtered else None)
+    assert gt == wt and (same_f64(host(got), want, zero_sign=False) if wt == ob.F64 else np.array_equal(host(got), want))
+    if vt == ob.U8:
+        with pytest.raises(capi.RfbError):
+            ctx.aggr(capi.A_LAST, vt, dev(val), dev(wg), wi.groups)
+        return
+    for chunks in (1, 3, 16):
+        want, wt = oracle.aggr_last(vt, val, wg, wi.groups, chunks, filt)
+        got, gt = ctx.aggr_last(vt, dev(val), dev(wg), wi.groups, chunks, dev(filt) if filtered else None)
+        assert gt == wt and (same_f64(host(got), want, zero_sign=False) if wt == ob.F64 else np.array_equal(host(got), want)), chunks
+    want, _ = oracle.aggr(ob.LAST, vt, val, wg, wi.groups, filt)
+    got, _ = ctx.aggr(capi.A_LAST, vt, dev(val), dev(wg), wi.groups, dev(filt) if filtered else None)
+    assert same_f64(host(got), want, zero_sign=False) if wt == ob.F64 else np.array_equal(host(got), want)
+
+
+@pytest.mark.parametrize("op", [ob.SUM, ob.AVG])
+@pytest.mark.parametrize("card,vbits,nulls", [(100_000, 20, 0.0005), (250_000, 19, 0.0), (60_000, 45, 0.0005), (20_000, 62, 0.0), (100_000, 20, 0.2)])
+def test_aggr_through_partition_passes(ctx, oracle, monkeypatch, op, card, vbits, nulls):
+    """aggr_sum / aggr_avg of i64 values at 1e4 .. 2.6e5 groups take the narrow partition passes of the fused group-by (group id
+    = key; packed 32 / 64-bit records, nulls and wide values through the exception list); values that fit no record format
+    (62 bits) and null-heavy columns fall back to the device-wide atomics: same bits either way"""
+    if op == ob.AVG and vbits > 45:
+        pytest.skip("the oracle averages in f64 like the reference: only sums below 2^53 are order-free")
+    monkeypatch.setenv("RFB_PART_MIN_ROWS", "1000")
+    n = 1_200_007
+    r = np.random.default_rng(card + vbits)
+    gid = r.integers(0, card, n).astype(np.int64)
+    gid[:card] = np.arange(card)                     # every group occurs
+    val = r.integers(-(1 << (vbits - 1)), 1 << (vbits - 1), n).astype(np.int64) if vbits > 32 else r.integers(0, 1 << vbits, n).astype(np.int64)
+    val[r.random(n) < nulls] = ob.NULL_I64
+    want, wt = oracle.aggr(op, ob.I64, val, gid, card)
+    launches = ctx.launches
+    got, gt = ctx.aggr(A_OF[op], ob.I64, dev(val), dev(gid), card)
+    assert gt == wt
+    assert same_f64(host(got), want, zero_sign=False) if wt == ob.F64 else np.array_equal(host(got), want)
+    if vbits <= 45 and nulls < 0.01:
+        assert ctx.launches - launches >= 8          # census x3, scatter, (tail), accumulate, exceptions, finalise: the partition path ran
+
+
 def test_aggr_sticky_null_and_all_null_group(ctx, oracle):
     # grouped sum over [1 0Nl | 3 4] -> [0Nl 7]; count -> [2 2]; avg -> [1.0 3.5]; min/max -> [1 3]/[1 4]  (SURVEY §8a probes)
     gid = np.array([0, 0, 1, 1, 2], np.int64)

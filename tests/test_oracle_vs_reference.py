@@ -331,6 +331,49 @@ def test_grouped_med_and_dev(oracle, reference, n, card, filtered):
             assert same_f64(want, got) if op == ob.MED else close_f64(want, got, 1e-9), (op, vt)
 
 
+def ref_aggr_chunks(rows, groups, width, cores):
+    """pool_split_by_mem (core/pool.c:450-478): how many worker chunks aggr_map cuts `rows` rows into"""
+    if rows < 16384 or rows <= cores:
+        return 1
+    mem = groups * width
+    if mem > (64 << 20):
+        return 1
+    return max(1, min(cores, (64 << 20) // mem)) if mem > 0 else cores
+
+
+@pytest.mark.parametrize("n,card", [(9, 3), (16000, 100), (20_000, 50), (100_003, 3000), (300_007, 70_000)])
+@pytest.mark.parametrize("filtered", [False, True])
+def test_grouped_first_and_last(oracle, reference, n, card, filtered):
+    """aggr_first = the value at the group's first row (first_ids fast path, nulls included); aggr_last = the last non-null
+    value inside the first WORKER CHUNK that has one (AGGR_COLLECT keeps the first non-null partial): above 16384 rows the
+    reference's own answer depends on its executor count, which the oracle takes as a parameter"""
+    r = np.random.default_rng(n * 7 + card)
+    keys = r.integers(0, card, n).astype(np.int64)
+    filt = np.sort(r.choice(n, max(1, n // 3), replace=False)).astype(np.int64) if filtered else None
+    rows = n if filt is None else filt.shape[0]
+    if not reference_scope_is_safe(rows, reference.cores):
+        pytest.skip("reference index_scope_i64 reads out of bounds at this length / thread count (Q12)")
+    gids, firsts, info = oracle.group_i64(keys, filt)
+    for vt in (ob.I64, ob.F64, ob.I32, ob.I16, ob.TIME, ob.TIMESTAMP, ob.DATE, ob.U8):
+        val = rng_col(vt, n, vt + 3, null_frac=0.3, lo=-1000 if vt != ob.U8 else 0, hi=1000 if vt != ob.U8 else 200)
+        ops = [ob.FIRST] if vt == ob.U8 else [ob.FIRST, ob.LAST]
+        ref = reference.group_aggr(keys, vt, val, ops, filt)
+        want, wt = oracle.aggr(ob.FIRST, vt, val, gids, info.groups, filt)
+        got, gt = ref["results"][ob.FIRST]
+        if not info.dense:
+            want, got = np.sort(want), np.sort(got)
+        assert gt == wt and (same_f64(want, got, zero_sign=False) if wt == ob.F64 else np.array_equal(want, got)), vt
+        if vt == ob.U8:
+            continue
+        chunks = ref_aggr_chunks(rows, info.groups, np.dtype(ob.NP_OF[vt]).itemsize, reference.cores)
+        want, wt = oracle.aggr_last(vt, val, gids, info.groups, chunks, filt)
+        got, gt = ref["results"][ob.LAST]
+        if not info.dense:
+            want, got = np.sort(want), np.sort(got)
+        assert gt == wt, (vt, gt, wt)
+        assert same_f64(want, got, zero_sign=False) if wt == ob.F64 else np.array_equal(want, got), (vt, chunks)
+
+
 def test_grouped_dev_type_error(oracle, reference):
     keys = np.arange(50, dtype=np.int64) % 5
     val = rng_col(ob.U8, 50, 1, lo=0, hi=9)
