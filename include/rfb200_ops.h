@@ -68,6 +68,8 @@ typedef struct rfb_host_api {
     rfb_obj_p (*err_length)(void);                 /* core/error.h:88 err_length(0,0,0,0,0,0) */
     rfb_obj_p (*err_limit)(void);                  /* core/error.h:92 err_limit(0): allocation / device failure */
     rfb_obj_p null_obj;                            /* &__NULL_OBJ (core/ops.c:33-36) */
+    int64_t (*executors)(void);                    /* pool_get_executors_count(pool_get()) (core/pool.c:486); NULL = 1.  aggr_last's
+                                                      answer depends on how many worker chunks the reference would use (Q18) */
 } rfb_host_api_t;
 
 /* Bind the layer to a host and a GPU.  Fails (non-zero) when no CUDA device is usable: there is no CPU fallback inside
@@ -78,6 +80,10 @@ const rfb_host_api_t *rfb_ops_builtin_host(void); /* malloc-based host for stand
 const char *rfb_ops_last_error(void);
 void rfb_ops_set_min_rows(int64_t n); /* vectors shorter than this are DECLINED (default: env RFB200_MIN_ROWS or 0) */
 int64_t rfb_ops_launches(void);       /* kernels launched so far (evidence that the GPU path ran) */
+/* Cost gate (default on; env RFB200_GATE=0): OUTSIDE a query scope the single-touch element-wise operators (comparisons, arithmetic,
+ * round/floor/ceil, not, and/or) are declined when no vector operand is in HBM and none is a column worth keeping there — shipping the
+ * operands in and the result out over PCIe costs more than the reference's CPU loop over the same bytes. */
+void rfb_ops_set_gate(int on);
 
 /* Query scope: between begin and end a host column is shipped to HBM once (cudaMemcpyAsync) and reused by every
  * operator that sees the same (payload pointer, length, type); results produced on the device stay resident too.
@@ -161,6 +167,25 @@ rfb_obj_p rfb_aggr_med(rfb_obj_p val, rfb_obj_p index);
 rfb_obj_p rfb_aggr_stddev(rfb_obj_p val, rfb_obj_p index);   /* the reference's aggr_dev (rfb_aggr_dev names the C ABI's device entry) */
 rfb_obj_p rfb_aggr_row(rfb_obj_p val, rfb_obj_p index);
 rfb_obj_p rfb_aggr_collect(rfb_obj_p val, rfb_obj_p index);
+
+/* aggr_first (core/aggr.c:441-577, indices with first_ids) / aggr_last (core/aggr.c:897-1075) -> vector of val's type */
+rfb_obj_p rfb_aggr_first(rfb_obj_p val, rfb_obj_p index);
+rfb_obj_p rfb_aggr_last(rfb_obj_p val, rfb_obj_p index);
+/* index_group_list (core/index.c:2731-2793): keys = LIST of 2..8 I64-kind key columns -> the same 7-element index as index_group */
+rfb_obj_p rfb_index_group_list(rfb_obj_p keys, rfb_obj_p filter);
+
+/* ---- masks: one fold step of the special forms `and` / `or` (core/logic.c:89-264: res = res OP next, in place in res's payload;
+ *      1 = done on the device, 0 = declined, < 0 = device failure) and ray_not (core/order.c:422-443) */
+int rfb_mask_logic_inplace(int is_or, rfb_obj_p res, rfb_obj_p next);
+rfb_obj_p rfb_ray_not(rfb_obj_p x);
+
+/* ---- materialise / order: at_ids (core/rayforce.c:1100-1201; ids = bare host array of row ids), ray_asc / ray_desc
+ *      (core/order.c:74-244: sorted values), ray_xasc / ray_xdesc (core/order.c:246-420: a table ordered by one or several columns) */
+rfb_obj_p rfb_at_ids(rfb_obj_p obj, const int64_t *ids, int64_t len);
+rfb_obj_p rfb_ray_asc(rfb_obj_p x);
+rfb_obj_p rfb_ray_desc(rfb_obj_p x);
+rfb_obj_p rfb_ray_xasc(rfb_obj_p table, rfb_obj_p by);
+rfb_obj_p rfb_ray_xdesc(rfb_obj_p table, rfb_obj_p by);
 
 /* ---- equi-join row matching: index_left_join_obj / index_inner_join_obj (core/index.c:2886-3000;
  *      lcols / rcols = the key column itself when len == 1, else a LIST of len key columns) and ray_find on two I64-kind

@@ -24,6 +24,8 @@
 #include "core/rayforce.h"
 #include "core/error.h"
 #include "core/ops.h"
+#include "core/eval.h"
+#include "core/pool.h"
 
 #include "rfb200_ops.h"
 
@@ -35,6 +37,7 @@ static void h_drop(rfb_obj_p o) { drop_obj((obj_p)o); }
 static rfb_obj_p h_err_type(void) { return (rfb_obj_p)err_type(0, 0, 0, 0); }
 static rfb_obj_p h_err_length(void) { return (rfb_obj_p)err_length(0, 0, 0, 0, 0, 0); }
 static rfb_obj_p h_err_limit(void) { return (rfb_obj_p)err_limit(0); }
+static int64_t h_executors(void) { return (int64_t)pool_get_executors_count(pool_get()); }
 static rfb_host_api_t host_api;
 
 static int state = 0; /* 0 = not tried, 1 = GPU layer bound, -1 = unavailable (CPU bodies only) */
@@ -43,12 +46,15 @@ static int want_stats = 0;
 
 enum { S_EQ, S_NE, S_LT, S_GT, S_LE, S_GE, S_WHERE, S_COLLECT, S_SUM, S_MIN, S_MAX, S_AVG, S_ADD, S_SUB, S_MUL, S_DIV, S_FDIV,
        S_MOD, S_XBAR, S_ROUND, S_FLOOR, S_CEIL, S_INDEX_GROUP, S_AGGR_SUM, S_AGGR_MIN, S_AGGR_MAX, S_AGGR_COUNT, S_AGGR_AVG, S_SORT_ASC,
-       S_SORT_DESC, S_SELECT, S_MED, S_DEV, S_AGGR_MED, S_AGGR_DEV, S_AGGR_ROW, S_AGGR_COLLECT, S_FIND, S_LEFT_JOIN, S_INNER_JOIN, S_IN, S_ASOF_JOIN, S_DISTINCT, S_N };
+       S_SORT_DESC, S_SELECT, S_MED, S_DEV, S_AGGR_MED, S_AGGR_DEV, S_AGGR_ROW, S_AGGR_COLLECT, S_FIND, S_LEFT_JOIN, S_INNER_JOIN, S_IN, S_ASOF_JOIN, S_DISTINCT,
+       S_AND, S_OR, S_NOT, S_AT_IDS, S_ASC, S_DESC, S_XASC, S_XDESC, S_AGGR_FIRST, S_AGGR_LAST, S_GROUP_LIST, S_N };
 static const char *S_NAME[S_N] = {"ray_eq", "ray_ne", "ray_lt", "ray_gt", "ray_le", "ray_ge", "ray_where", "filter_collect", "ray_sum",
                                   "ray_min", "ray_max", "ray_avg", "ray_add", "ray_sub", "ray_mul", "ray_div", "ray_fdiv", "ray_mod", "ray_xbar",
                                   "ray_round", "ray_floor", "ray_ceil", "index_group", "aggr_sum", "aggr_min", "aggr_max", "aggr_count",
                                   "aggr_avg", "ray_sort_asc", "ray_sort_desc", "ray_select", "ray_med", "ray_dev", "aggr_med", "aggr_dev",
-                                  "aggr_row", "aggr_collect", "ray_find", "index_left_join_obj", "index_inner_join_obj", "ray_in", "index_asof_join_obj", "ray_distinct"};
+                                  "aggr_row", "aggr_collect", "ray_find", "index_left_join_obj", "index_inner_join_obj", "ray_in", "index_asof_join_obj", "ray_distinct",
+                                  "ray_and", "ray_or", "ray_not", "at_ids", "ray_asc", "ray_desc", "ray_xasc", "ray_xdesc", "aggr_first", "aggr_last",
+                                  "index_group_list"};
 static long n_gpu[S_N], n_cpu[S_N];
 
 static void print_stats(void) {
@@ -60,6 +66,10 @@ static void print_stats(void) {
         if (n_gpu[i] || n_cpu[i]) fprintf(stderr, "[rfb200 shim]   %-16s gpu %8ld   cpu %8ld\n", S_NAME[i], n_gpu[i], n_cpu[i]);
     long lz[4];
     rfb_ops_lazy_stats(lz);
+    long rs[4];
+    rfb_ops_residency_stats(rs);
+    fprintf(stderr, "[rfb200 shim] HBM residency: %ld operand images found in HBM, %ld columns shipped, %ld images dropped by the free / write hooks, %ld MiB resident\n",
+            rs[0], rs[1], rs[2], rs[3]);
     if (lz[0]) fprintf(stderr, "[rfb200 shim] lazy results: %ld left on the device, %ld faulted in by a CPU access, %ld dropped unread, %ld filled at scope end\n", lz[0], lz[1], lz[2], lz[3]);
 }
 
@@ -70,8 +80,16 @@ static int gpu_ok(void) {
         host_api.vector = h_vector; host_api.atom = h_atom; host_api.clone_obj = h_clone; host_api.drop_obj = h_drop;
         host_api.err_type = h_err_type; host_api.err_length = h_err_length; host_api.err_limit = h_err_limit;
         host_api.null_obj = (rfb_obj_p)NULL_OBJ;
+        host_api.executors = h_executors;
         if (d && d[0] == '1') state = -1;
-        else if (rfb_ops_init(&host_api, 0) == 0) { state = 1; owner = pthread_self(); }
+        else if (rfb_ops_init(&host_api, 0) == 0) {
+            state = 1;
+            owner = pthread_self();
+            /* this binding reports every free / in-place write (heap_free, heap_realloc, cow_obj, the CPU fallbacks below), so
+             * column images may stay in HBM across queries; RFB200_RESIDENT=0 keeps every query cold */
+            const char *r = getenv("RFB200_RESIDENT");
+            rfb_ops_set_residency(!(r && r[0] == '0'), 0);
+        }
         else {
             state = -1;
             fprintf(stderr, "[rfb200 shim] GPU layer unavailable (%s): using the reference CPU bodies\n", rfb_ops_last_error());
@@ -146,3 +164,72 @@ obj_p __wrap_ray_select(obj_p obj) {
     if (on) rfb_ops_scope_end();
     return r;
 }
+
+/* ---- residency hooks: the layer keeps HBM images of host vectors keyed by their payload address; the reference tells it when
+ * an address stops meaning what it meant.  heap_free / heap_realloc see every internal block going away (drop_obj ends there),
+ * cow_obj returning its argument means "about to be modified in place". */
+nil_t __real_heap_free(raw_p ptr);
+nil_t __wrap_heap_free(raw_p ptr) {
+    if (state == 1 && ptr) rfb_ops_note_free(ptr);
+    __real_heap_free(ptr);
+}
+raw_p __real_heap_realloc(raw_p ptr, i64_t size);
+raw_p __wrap_heap_realloc(raw_p ptr, i64_t size) {
+    if (state == 1 && ptr) rfb_ops_note_free(ptr);
+    return __real_heap_realloc(ptr, size);
+}
+obj_p __real_cow_obj(obj_p obj);
+obj_p __wrap_cow_obj(obj_p obj) {
+    obj_p r = __real_cow_obj(obj);
+    if (state == 1 && r == obj) rfb_ops_note_write(obj);
+    return r;
+}
+
+WRAP1(ray_not, S_NOT) WRAP1(ray_asc, S_ASC) WRAP1(ray_desc, S_DESC) WRAP2(ray_xasc, S_XASC) WRAP2(ray_xdesc, S_XDESC)
+WRAP2(aggr_first, S_AGGR_FIRST) WRAP2(aggr_last, S_AGGR_LAST) WRAP2(index_group_list, S_GROUP_LIST)
+
+obj_p __real_at_ids(obj_p obj, i64_t ids[], i64_t len);
+obj_p __wrap_at_ids(obj_p obj, i64_t ids[], i64_t len) {
+    if (gpu_ok()) {
+        obj_p r = (obj_p)rfb_at_ids((rfb_obj_p)obj, (const int64_t *)ids, len);
+        if (r) { n_gpu[S_AT_IDS]++; return r; }
+    }
+    n_cpu[S_AT_IDS]++;
+    return __real_at_ids(obj, ids, len);
+}
+
+/* `and` / `or` are special forms (core/logic.c:89-264): they evaluate their operands one by one and fold each into the first
+ * result IN PLACE.  The wrapper keeps that protocol — same evaluation order, same in-place result object — and offers every
+ * (B8 vector, B8 vector | b8 atom) step to the device; any other step goes through the reference's own body on the two
+ * already-evaluated operands (values other than LISTs and symbol atoms evaluate to themselves, core/eval.c:884-893). */
+obj_p __real_ray_and(obj_p *x, i64_t n);
+obj_p __real_ray_or(obj_p *x, i64_t n);
+static obj_p logic_fold(int is_or, obj_p *x, i64_t n) {
+    const int slot = is_or ? S_OR : S_AND;
+    if (!gpu_ok() || n < 2) { n_cpu[slot]++; return is_or ? __real_ray_or(x, n) : __real_ray_and(x, n); }
+    obj_p res = eval(x[0]);
+    if (IS_ERR(res)) return res;
+    int on_gpu = 0;
+    for (i64_t i = 1; i < n; i++) {
+        obj_p next = eval(x[i]);
+        if (IS_ERR(next)) { drop_obj(res); return next; }
+        if (res->type == -TYPE_B8 && next->type == TYPE_B8) { obj_p t = res; res = next; next = t; }   /* core/logic.c:178-182 */
+        if (rfb_mask_logic_inplace(is_or, (rfb_obj_p)res, (rfb_obj_p)next) == 1) { on_gpu = 1; drop_obj(next); continue; }
+        if (res->type == TYPE_LIST || res->type == -TYPE_SYMBOL || next->type == TYPE_LIST || next->type == -TYPE_SYMBOL) {
+            drop_obj(res);                             /* would be evaluated a second time: the reference's answer for these is a type error */
+            drop_obj(next);
+            return err_type(0, 0, 0, 0);
+        }
+        rfb_ops_note_write(res);                       /* the CPU body folds into res's payload */
+        obj_p pair[2] = {res, next};
+        obj_p r = is_or ? __real_ray_or(pair, 2) : __real_ray_and(pair, 2);   /* takes its own references, returns one to res (or an error) */
+        drop_obj(res);
+        drop_obj(next);
+        if (IS_ERR(r)) return r;
+        res = r;
+    }
+    if (on_gpu) n_gpu[slot]++; else n_cpu[slot]++;
+    return res;
+}
+obj_p __wrap_ray_and(obj_p *x, i64_t n) { return logic_fold(0, x, n); }
+obj_p __wrap_ray_or(obj_p *x, i64_t n) { return logic_fold(1, x, n); }

@@ -80,6 +80,8 @@ const char *rfb_ops_last_error(void) { return G.err; }
 static int lazy_on = -1;
 static long lazy_stats[4]; /* registered, faulted in, dropped, filled at scope end */
 static void lazy_resolve_all(void);
+static int lazy_backed_by(const void *dev);
+static void lazy_resolve_dev(const void *dev);
 
 /* ------------------------------------------------------------------ builtin malloc host (standalone / tests) */
 
@@ -131,7 +133,7 @@ static obj_p bh_err_length(void) { bh_last_err = "length"; return &bh_err; }
 static obj_p bh_err_limit(void) { bh_last_err = "limit"; return &bh_err; }
 const char *rfb_ops_builtin_last_error(void) { return bh_last_err; }
 
-static const rfb_host_api_t builtin_host = {bh_vector, bh_atom, bh_clone, bh_drop, bh_err_type, bh_err_length, bh_err_limit, &bh_null};
+static const rfb_host_api_t builtin_host = {bh_vector, bh_atom, bh_clone, bh_drop, bh_err_type, bh_err_length, bh_err_limit, &bh_null, NULL};
 const rfb_host_api_t *rfb_ops_builtin_host(void) { return &builtin_host; }
 
 /* ------------------------------------------------------------------ init / scope / device columns */
@@ -170,11 +172,17 @@ static void release_columns(int everything) {
     memset(G.bloom, 0, sizeof(G.bloom));
     for (int i = 0; i < G.ncols; i++) {
         col_entry_t *e = &G.cols[i];
-        if (!everything && G.residency && e->host && e->keep) {
+        /* with the hooks bound, a result the host has not read yet (lazy) keeps its device buffer: the host frees it (no copy
+         * at all), reads it (filled by the fault) or the budget pushes it out (filled first) */
+        const int pending = !everything && G.residency && lazy_on == 1 && lazy_backed_by(e->dev);
+        if (!everything && G.residency && ((e->host && e->keep) || pending)) {
             G.resident_bytes += e->bytes;
-            bloom_add(e->host);
+            if (e->host) bloom_add(e->host);
             G.cols[w++] = *e;
-        } else free_buffer(e->dev, e->bytes);
+        } else {
+            if (lazy_on == 1) lazy_resolve_dev(e->dev);
+            free_buffer(e->dev, e->bytes);
+        }
     }
     G.ncols = w;
     while (G.resident_bytes > G.resident_budget && G.ncols > 0) {
@@ -182,6 +190,7 @@ static void release_columns(int everything) {
         for (int i = 1; i < G.ncols; i++)
             if (G.cols[i].used < G.cols[lru].used) lru = i;
         G.resident_bytes -= G.cols[lru].bytes;
+        if (lazy_on == 1) lazy_resolve_dev(G.cols[lru].dev);
         free_buffer(G.cols[lru].dev, G.cols[lru].bytes);
         G.cols[lru] = G.cols[--G.ncols];
     }
@@ -190,6 +199,7 @@ static void release_columns(int everything) {
 void rfb_ops_shutdown(void) {
     if (!G.ready) return;
     rfb_sync(G.ctx);
+    if (lazy_on == 1) lazy_resolve_all();
     release_columns(1);
     for (int i = 0; i < G.npool; i++) rfb_dev_free(G.ctx, G.pool[i].dev);
     G.npool = 0;
@@ -200,7 +210,7 @@ void rfb_ops_shutdown(void) {
 
 void rfb_ops_set_residency(int on, int64_t budget_bytes) {
     if (!G.ready) return;
-    if (!on && G.residency && G.scope_depth == 0) { rfb_sync(G.ctx); G.residency = 0; release_columns(1); }
+    if (!on && G.residency && G.scope_depth == 0) { rfb_sync(G.ctx); if (lazy_on == 1) lazy_resolve_all(); G.residency = 0; release_columns(1); }
     G.residency = on ? 1 : 0;
     if (budget_bytes > 0) G.resident_budget = (size_t)budget_bytes;
 }
@@ -241,7 +251,7 @@ void rfb_ops_scope_begin(void) { G.scope_depth++; }
 void rfb_ops_scope_end(void) {
     if (G.scope_depth > 0 && --G.scope_depth == 0 && G.ready) {
         rfb_sync(G.ctx);
-        if (lazy_on == 1) lazy_resolve_all();
+        if (lazy_on == 1 && !G.residency) lazy_resolve_all();   /* without the hooks nothing may stay pending past the query */
         release_columns(0);
     }
 }
@@ -399,6 +409,26 @@ static void *lazy_device_image(const void *payload) {
     return NULL;
 }
 
+/* is a still-pending lazy payload backed by this device buffer? */
+static int lazy_backed_by(const void *dev) {
+    for (int i = 0; i < MAX_LAZY; i++)
+        if (LZ[i].state == 1 && LZ[i].dev == dev) return 1;
+    return 0;
+}
+/* the device buffer is about to be recycled: materialise what still hangs on it */
+static void lazy_resolve_dev(const void *dev) {
+    for (int i = 0; i < MAX_LAZY; i++) {
+        lazy_t *z = &LZ[i];
+        if (z->state != 1 || z->dev != dev) continue;
+        while (__sync_lock_test_and_set(&lazy_lock, 1)) { }
+        if (z->state == 1) {
+            if (lazy_still_ours(z->lo, z->hi)) { lazy_fill(z, 0); lazy_stats[3]++; } else lazy_stats[2]++;
+            z->state = 0;
+        }
+        __sync_lock_release(&lazy_lock);
+    }
+}
+
 /* resolve everything that is still pending (end of the outermost scope, before the device buffers are recycled) */
 static void lazy_resolve_all(void) {
     for (int i = 0; i < MAX_LAZY; i++) {
@@ -415,7 +445,7 @@ static void lazy_resolve_all(void) {
 
 /* try to leave `r`'s payload on the device; returns 1 when the result is lazy (edges copied, interior protected) */
 static int lazy_register(obj_p r, size_t bytes, void *dev) {
-    if (!lazy_enabled() || bytes < lazy_min || G.scope_depth < 2) return 0; /* depth 1 = a bare call: would resolve at once */
+    if (!lazy_enabled() || bytes < lazy_min || (G.scope_depth < 2 && !G.residency)) return 0; /* depth 1 without the hooks = a bare call: would resolve at once */
     const long pg = sysconf(_SC_PAGESIZE);
     char *p = (char *)RFB_OBJ_PAYLOAD(r);
     char *lo = (char *)(((uintptr_t)p + (uintptr_t)pg - 1) & ~(uintptr_t)(pg - 1));
@@ -482,20 +512,20 @@ static col_entry_t *track(void *dev, size_t bytes, const void *host, int64_t len
  * can change or be unmapped behind the hooks) and somebody besides the evaluator's stack holds it (a table column, a global) */
 static int worth_keeping(obj_p v) { return G.residency && v->mmod == 0xff && v->rc >= 2; }
 
-/* device image of a host vector's payload: a hit on a live entry, else one cudaMemcpyAsync */
-static void *dev_column(obj_p v) {
-    const int w = type_size(v->type);
-    const void *payload = RFB_OBJ_PAYLOAD(v);
+/* device image of a host payload (the payload of vector `v`, or a bare array the reference hands over — at_ids' row ids):
+ * a hit on a live entry, else one cudaMemcpyAsync */
+static void *dev_payload(const void *payload, int64_t len, int type, int keep) {
+    const int w = type_size(type);
     if (lazy_on == 1) {
         void *img = lazy_device_image(payload);   /* never read a pending payload: that would fault it in */
         if (img) return img;
-        lazy_forget_overlaps((const char *)v, (const char *)payload + (size_t)v->len * w, NULL);
+        lazy_forget_overlaps((const char *)payload - 16, (const char *)payload + (size_t)len * w, NULL);
     }
     for (int i = G.ncols - 1; i >= 0; i--)
         if (G.cols[i].host == payload) {
-            if (G.cols[i].len == v->len && G.cols[i].type == v->type && G.cols[i].print == fingerprint(payload, (size_t)v->len * w)) {
+            if (G.cols[i].len == len && G.cols[i].type == type && G.cols[i].print == fingerprint(payload, (size_t)len * w)) {
                 G.cols[i].used = ++G.clock;
-                if (!G.cols[i].keep && worth_keeping(v)) G.cols[i].keep = 1;
+                if (!G.cols[i].keep && keep) G.cols[i].keep = 1;
                 G.stat_hits++;
                 return G.cols[i].dev;
             }
@@ -503,16 +533,18 @@ static void *dev_column(obj_p v) {
             break;
         }
     size_t got = 0;
-    void *d = dev_buffer((size_t)v->len * w, &got);
+    void *d = dev_buffer((size_t)len * w, &got);
     if (!d) return NULL;
-    if (v->len > 0 && rfb_h2d(G.ctx, d, payload, (size_t)v->len * w) != RFB_OK) { set_err("%s", rfb_last_error()); rfb_dev_free(G.ctx, d); return NULL; }
-    if (!track(d, got, payload, v->len, v->type, worth_keeping(v))) { rfb_sync(G.ctx); rfb_dev_free(G.ctx, d); return NULL; }
+    if (len > 0 && rfb_h2d(G.ctx, d, payload, (size_t)len * w) != RFB_OK) { set_err("%s", rfb_last_error()); rfb_dev_free(G.ctx, d); return NULL; }
+    if (!track(d, got, payload, len, type, keep)) { rfb_sync(G.ctx); rfb_dev_free(G.ctx, d); return NULL; }
     G.stat_ships++;
     return d;
 }
+static void *dev_column(obj_p v) { return dev_payload(RFB_OBJ_PAYLOAD(v), v->len, v->type, worth_keeping(v)); }
 
 /* is the payload of this vector in HBM already? */
 static int is_resident(obj_p v) {
+    if (!v || v->type <= 0) return 0;
     const void *payload = RFB_OBJ_PAYLOAD(v);
     if (lazy_on == 1 && lazy_device_image(payload)) return 1;
     for (int i = G.ncols - 1; i >= 0; i--)
@@ -534,28 +566,35 @@ static col_entry_t *entry_of_dev(void *dev) {
     return NULL;
 }
 
-/* host vector of `type` filled from device memory; the device copy is registered as its HBM image */
-static obj_p to_host_vector(int type, int64_t len, void *dev) {
-    obj_p r = G.host->vector((int8_t)type, len);
-    if (!r || r->type == RFB_T_ERR) return r ? r : G.host->err_limit();
+/* the payload of host vector `r` (len elements of `type`) becomes the content of device buffer `dev`: copied back now, or left
+ * lazy; `dev` is registered as the payload's HBM image, whatever lived at that address before is forgotten */
+static int fill_host_vector(obj_p r, int type, int64_t len, void *dev) {
     col_entry_t *e = entry_of_dev(dev);
     if (len > 0 && lazy_register(r, (size_t)len * type_size(type), dev)) {
         if (e) { forget_payload(RFB_OBJ_PAYLOAD(r), e); e->host = NULL; e->len = len; e->type = type; }   /* found through the lazy table */
-        return r;
+        return RFB_OK;
     }
     if (len > 0) {
         if (rfb_d2h(G.ctx, RFB_OBJ_PAYLOAD(r), dev, (size_t)len * type_size(type)) != RFB_OK || rfb_sync(G.ctx) != RFB_OK) {
             set_err("%s", rfb_last_error());
-            G.host->drop_obj(r);
-            return G.host->err_limit();
+            return RFB_ERR_CUDA;
         }
     }
     if (e) {
         forget_payload(RFB_OBJ_PAYLOAD(r), e);   /* an older vector that lived at this address */
-        e->host = RFB_OBJ_PAYLOAD(r); e->len = len; e->type = type; e->keep = 0;
+        e->host = RFB_OBJ_PAYLOAD(r); e->len = len; e->type = type;
+        e->keep = G.residency;   /* with the hooks bound a result's image lives until the host frees or rewrites the vector */
         e->print = fingerprint(RFB_OBJ_PAYLOAD(r), (size_t)len * type_size(type));
         bloom_add(e->host);
     }
+    return RFB_OK;
+}
+
+/* host vector of `type` filled from device memory; the device copy is registered as its HBM image */
+static obj_p to_host_vector(int type, int64_t len, void *dev) {
+    obj_p r = G.host->vector((int8_t)type, len);
+    if (!r || r->type == RFB_T_ERR) return r ? r : G.host->err_limit();
+    if (fill_host_vector(r, type, len, dev) != RFB_OK) { G.host->drop_obj(r); return G.host->err_limit(); }
     return r;
 }
 
@@ -578,6 +617,21 @@ static int is_num_type(int t) { return type_size(t) != 0; }
 static int is_vec(obj_p o) { return o && o->type > 0 && is_num_type(o->type); }
 static int is_atom(obj_p o) { return o && o->type < 0 && is_num_type(-o->type); }
 static int too_small(int64_t n) { return n < G.min_rows; }
+
+/* Cost gate for the single-touch element-wise operators (comparisons, arithmetic, round/floor/ceil, not): their result goes
+ * back over PCIe, so when NO vector operand is in HBM yet and none is a column worth keeping there (a table column / global
+ * that later queries will touch again), shipping operands in and the result out costs more than the reference's CPU loop over
+ * the same bytes — such calls are declined.  Inside a query scope everything is taken: the result feeds the next operator on
+ * the device (mask -> where -> gather / fold).  RFB200_GATE=0 switches the gate off. */
+static int gate_state = -1;
+void rfb_ops_set_gate(int on) { gate_state = on ? 1 : 0; }
+static int gated_out(obj_p x, obj_p y) {
+    if (gate_state < 0) { const char *e = getenv("RFB200_GATE"); gate_state = (e && e[0] == '0') ? 0 : 1; }
+    if (!gate_state || G.scope_depth > 0) return 0;
+    const int xv = x && x->type > 0, yv = y && y->type > 0;
+    if ((xv && (is_resident(x) || worth_keeping(x))) || (yv && (is_resident(y) || worth_keeping(y)))) return 0;
+    return 1;
+}
 
 static rfb_scalar_t scalar_of(obj_p a) {
     rfb_scalar_t s;
@@ -608,7 +662,7 @@ static obj_p cmp_op(int op, obj_p x, obj_p y) {
     if (!(xv || yv) || !((xv || is_atom(x)) && (yv || is_atom(y)))) return NULL; /* atoms only, lists, tables, enums... */
     const int64_t n = xv ? x->len : y->len;
     if (xv && yv && x->len != y->len) return G.host->err_length();
-    if (too_small(n)) return NULL;
+    if (too_small(n) || gated_out(x, y)) return NULL;
     call_scope_t sc = enter();
     obj_p res = NULL;
     const int xt = xv ? x->type : -x->type, yt = yv ? y->type : -y->type;
@@ -797,7 +851,7 @@ static obj_p bin_op(int op, obj_p x, obj_p y) {
     if (ot < 0) return NULL; /* the reference's matrix is wider (dates, times, u8...): leave those to the CPU body */
     if (xv && yv && x->len != y->len) return G.host->err_length();
     const int64_t n = xv ? x->len : y->len;
-    if (too_small(n)) return NULL;
+    if (too_small(n) || gated_out(x, y)) return NULL;
     call_scope_t sc = enter();
     obj_p res;
     rfb_scalar_t xs, ys;
@@ -823,7 +877,7 @@ obj_p rfb_ray_xbar(obj_p x, obj_p y) { return bin_op(RFB_XBAR, x, y); }
 
 static obj_p un_op(int op, obj_p x) {
     if (!G.ready || !x || x->type != RFB_T_F64) return NULL; /* integer / temporal inputs are returned as-is by the CPU body */
-    if (too_small(x->len)) return NULL;
+    if (too_small(x->len) || gated_out(x, NULL)) return NULL;
     call_scope_t sc = enter();
     obj_p res;
     void *dx = dev_column(x), *dout = dev_temp((size_t)(x->len > 0 ? x->len : 1) * 8);
@@ -1262,6 +1316,270 @@ out:
 }
 obj_p rfb_ray_sort_asc(obj_p x) { return sort_op(x, 0); }
 obj_p rfb_ray_sort_desc(obj_p x) { return sort_op(x, 1); }
+
+
+/* ------------------------------------------------------------------ masks: and / or / not (core/logic.c:34-264, core/order.c:422-443) */
+
+/* One step of the reference's `and` / `or` fold: res = res OP next, IN PLACE in res's payload like and_op_partial / or_op_partial
+ * (core/logic.c:34-86) — res is a B8 vector, next a B8 vector of the same length or a b8 atom.  1 = done on the device (res's
+ * payload now holds the result and its HBM image is registered, so the ray_where that follows ships nothing), 0 = declined,
+ * < 0 = device failure (res untouched).  The binding evaluates the operands itself (ray_and / ray_or are special forms). */
+int rfb_mask_logic_inplace(int is_or, obj_p res, obj_p next) {
+    if (!G.ready || !res || !next || res->type != RFB_T_B8) return 0;
+    const int nv = next->type == RFB_T_B8;
+    if (!nv && next->type != -RFB_T_B8) return 0;
+    if (nv && next->len != res->len) return 0;       /* the reference answers a type error: its body, its error object */
+    if (too_small(res->len) || res->len == 0) return 0;
+    if (gated_out(res, nv ? next : NULL)) return 0;   /* cost gate: a bare CPU-side mask pair */
+    call_scope_t sc = enter();
+    int done = -1;
+    void *da = dev_column(res), *db = nv ? dev_column(next) : NULL, *dout = dev_temp((size_t)res->len);
+    if (da && (!nv || db) && dout &&
+        rfb_mask_logic_dev(G.ctx, is_or ? RFB_M_OR : RFB_M_AND, (const uint8_t *)da, res->len, (const uint8_t *)db, nv ? res->len : -1,
+                           nv ? 0 : next->u8, (uint8_t *)dout) == RFB_OK) {
+        if (lazy_on == 1) lazy_on_free(res);          /* a still-pending lazy payload is being replaced: open its pages first */
+        if (fill_host_vector(res, RFB_T_B8, res->len, dout) == RFB_OK) done = 1;
+    }
+    leave(sc);
+    return done;
+}
+
+obj_p rfb_ray_not(obj_p x) {
+    if (!G.ready || !x || x->type != RFB_T_B8) return NULL;      /* atoms and type errors: CPU body */
+    if (too_small(x->len) || x->len >= (1ll << 31) || gated_out(x, NULL)) return NULL;   /* (the reference's loop counter is 32 bits wide) */
+    call_scope_t sc = enter();
+    obj_p res;
+    void *dx = dev_column(x), *dout = dev_temp((size_t)(x->len > 0 ? x->len : 1));
+    if (!dx || !dout) { res = G.host->err_limit(); goto out; }
+    int rc = rfb_mask_logic_dev(G.ctx, RFB_M_NOT, (const uint8_t *)dx, x->len, NULL, -1, 0, (uint8_t *)dout);
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = to_host_vector(RFB_T_B8, x->len, dout);
+out:
+    leave(sc);
+    return res;
+}
+
+/* ------------------------------------------------------------------ at_ids, ray_asc / ray_desc, ray_xasc / ray_xdesc */
+
+#define RFB_T_TABLE 98   /* core/rayforce.h:85: a 2-list [column names (SYMBOL vector), LIST of columns] */
+
+/* a table whose columns are all fixed-width vectors of one length */
+static int is_flat_table(obj_p t, int64_t *rows) {
+    if (!t || t->type != RFB_T_TABLE || t->len != 2) return 0;
+    obj_p names = RFB_OBJ_LIST(t)[0], cols = RFB_OBJ_LIST(t)[1];
+    if (!names || names->type != RFB_T_SYMBOL || !cols || cols->type != RFB_T_LIST || cols->len != names->len || cols->len == 0) return 0;
+    for (int64_t c = 0; c < cols->len; c++) {
+        obj_p v = RFB_OBJ_LIST(cols)[c];
+        if (!is_vec(v) || v->len != RFB_OBJ_LIST(cols)[0]->len) return 0;
+    }
+    *rows = RFB_OBJ_LIST(cols)[0]->len;
+    return 1;
+}
+
+/* out column = col[ids] on the device -> new host vector of col's type */
+static obj_p gather_column(obj_p col, const void *dids, int64_t m) {
+    void *dc = dev_column(col), *dout = dev_temp((size_t)(m > 0 ? m : 1) * type_size(col->type));
+    if (!dc || !dout) return G.host->err_limit();
+    int rc = rfb_gather_dev(G.ctx, col->type, dc, (const int64_t *)dids, m, dout);
+    if (rc) return status_to_obj(rc);
+    return to_host_vector(col->type, m, dout);
+}
+
+/* table(names, [col[ids] for every column]) (at_ids TYPE_TABLE branch, core/rayforce.c:1184-1201) */
+static obj_p gather_table(obj_p t, const void *dids, int64_t m) {
+    obj_p names = RFB_OBJ_LIST(t)[0], cols = RFB_OBJ_LIST(t)[1];
+    obj_p out = G.host->vector(RFB_T_LIST, cols->len);
+    if (!out || out->type == RFB_T_ERR) return G.host->err_limit();
+    for (int64_t c = 0; c < cols->len; c++) RFB_OBJ_LIST(out)[c] = G.host->null_obj;
+    for (int64_t c = 0; c < cols->len; c++) {
+        obj_p v = gather_column(RFB_OBJ_LIST(cols)[c], dids, m);
+        if (!v || v->type == RFB_T_ERR) { G.host->drop_obj(out); return v ? v : G.host->err_limit(); }
+        RFB_OBJ_LIST(out)[c] = v;
+    }
+    obj_p res = G.host->vector(RFB_T_LIST, 2);
+    if (!res || res->type == RFB_T_ERR) { G.host->drop_obj(out); return G.host->err_limit(); }
+    RFB_OBJ_LIST(res)[0] = G.host->clone_obj(names);
+    RFB_OBJ_LIST(res)[1] = out;
+    res->type = RFB_T_TABLE;
+    return res;
+}
+
+/* at_ids(obj, ids, len) (core/rayforce.c:1100-1201): obj[ids] for a fixed-width vector or a table of such columns.  `ids` is a bare
+ * host array — normally the payload of a row-id vector this layer produced (ray_where, a sort permutation), whose HBM image is
+ * then found by its address.  No bounds checks, like the reference (its callers check). */
+obj_p rfb_at_ids(obj_p obj, const int64_t *ids, int64_t len) {
+    if (!G.ready || !obj || !ids || len < 0) return NULL;
+    int64_t rows = 0;
+    const int tab = is_flat_table(obj, &rows);
+    if (!tab && !is_vec(obj)) return NULL;             /* GUID / LIST / ENUM / parted: CPU body */
+    if (too_small(len)) return NULL;
+    call_scope_t sc = enter();
+    obj_p res;
+    void *di = dev_payload(ids, len, RFB_T_I64, 0);
+    if (!di) { res = G.host->err_limit(); goto out; }
+    res = tab ? gather_table(obj, di, len) : gather_column(obj, di, len);
+out:
+    leave(sc);
+    return res;
+}
+
+#define RFB_ATTR_DISTINCT 1
+#define RFB_ATTR_ASC 2
+#define RFB_ATTR_DESC 4
+
+/* ray_asc / ray_desc (core/order.c:74-244): the sorted VALUES of a fixed-width vector = stable key sort + gather, both on the
+ * device; the result carries ATTR_ASC / ATTR_DESC and keeps ATTR_DISTINCT */
+static obj_p sorted_values(obj_p x, int desc) {
+    if (!G.ready || !is_vec(x) || x->type == RFB_T_SYMBOL) return NULL;            /* symbols order by their strings: CPU body */
+    if (x->attrs & (RFB_ATTR_ASC | RFB_ATTR_DESC)) return NULL;                    /* clone / reverse shortcuts (core/order.c:79-83) */
+    if (too_small(x->len)) return NULL;
+    call_scope_t sc = enter();
+    obj_p res;
+    void *dx = dev_column(x), *dp = dev_temp((size_t)(x->len > 0 ? x->len : 1) * 8);
+    if (!dx || !dp) { res = G.host->err_limit(); goto out; }
+    int rc = rfb_sort_dev(G.ctx, x->type, dx, x->len, desc, (int64_t *)dp);
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = gather_column(x, dp, x->len);
+    if (res && res->type != RFB_T_ERR) res->attrs |= (uint8_t)((desc ? RFB_ATTR_DESC : RFB_ATTR_ASC) | (x->attrs & RFB_ATTR_DISTINCT));
+out:
+    leave(sc);
+    return res;
+}
+obj_p rfb_ray_asc(obj_p x) { return sorted_values(x, 0); }
+obj_p rfb_ray_desc(obj_p x) { return sorted_values(x, 1); }
+
+/* ray_xasc / ray_xdesc (core/order.c:246-420): a table ordered by one column (y = symbol atom) or by several (y = symbol vector:
+ * one stable sort per key column from the last to the first, each on the column as reordered so far — the same composition of
+ * permutations, all on the device), then every column gathered by the final permutation. */
+static obj_p sorted_table(obj_p x, obj_p y, int desc) {
+    if (!G.ready || !y) return NULL;
+    int64_t rows = 0;
+    if (!is_flat_table(x, &rows)) return NULL;
+    const int atom = y->type == -RFB_T_SYMBOL;
+    if (!atom && !(y->type == RFB_T_SYMBOL && y->len >= 1 && y->len <= 16)) return NULL;
+    if (too_small(rows) || rows == 0) return NULL;
+    obj_p names = RFB_OBJ_LIST(x)[0], cols = RFB_OBJ_LIST(x)[1], key[16];
+    const int64_t nk = atom ? 1 : y->len;
+    for (int64_t k = 0; k < nk; k++) {
+        const int64_t sym = atom ? y->i64 : ((const int64_t *)RFB_OBJ_PAYLOAD(y))[k];
+        key[k] = NULL;
+        for (int64_t c = 0; c < names->len; c++)
+            if (((const int64_t *)RFB_OBJ_PAYLOAD(names))[c] == sym) { key[k] = RFB_OBJ_LIST(cols)[c]; break; }
+        if (!key[k] || key[k]->type == RFB_T_SYMBOL) return NULL;                  /* unknown column / symbol keys: CPU body */
+        if (atom && key[k]->attrs != 0) return NULL;                               /* ray_iasc's attribute shortcuts */
+    }
+    call_scope_t sc = enter();
+    obj_p res;
+    void *perm = NULL;
+    int rc = RFB_OK;
+    for (int64_t k = nk - 1; k >= 0 && !rc; k--) {
+        void *dk = dev_column(key[k]), *local = dev_temp((size_t)rows * 8);
+        if (!dk || !local) { res = G.host->err_limit(); goto out; }
+        if (!perm) {                                   /* first pass: the column as it stands */
+            rc = rfb_sort_dev(G.ctx, key[k]->type, dk, rows, desc, (int64_t *)local);
+            perm = local;
+        } else {                                       /* the column reordered so far, its stable order, composed: perm = perm[local] */
+            void *re = dev_temp((size_t)rows * type_size(key[k]->type)), *np = dev_temp((size_t)rows * 8);
+            if (!re || !np) { res = G.host->err_limit(); goto out; }
+            rc = rfb_gather_dev(G.ctx, key[k]->type, dk, (const int64_t *)perm, rows, re);
+            if (!rc) rc = rfb_sort_dev(G.ctx, key[k]->type, re, rows, desc, (int64_t *)local);
+            if (!rc) rc = rfb_gather_dev(G.ctx, RFB_T_I64, perm, (const int64_t *)local, rows, np);
+            perm = np;
+        }
+    }
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = gather_table(x, perm, rows);
+out:
+    leave(sc);
+    return res;
+}
+obj_p rfb_ray_xasc(obj_p x, obj_p y) { return sorted_table(x, y, 0); }
+obj_p rfb_ray_xdesc(obj_p x, obj_p y) { return sorted_table(x, y, 1); }
+
+/* ------------------------------------------------------------------ aggr_first / aggr_last, index_group_list */
+
+/* the reference's pool_split_by_mem (core/pool.c:450-478): the number of worker chunks aggr_map cuts `rows` rows into */
+static int64_t aggr_chunks(int64_t rows, int64_t groups, int width) {
+    const int64_t threads = G.host->executors ? G.host->executors() : 1;
+    if (rows < 16384 || rows <= threads) return 1;
+    const int64_t mem = groups * width;
+    if (mem > (64ll << 20)) return 1;
+    if (mem > 0 && (64ll << 20) / mem < threads) return (64ll << 20) / mem < 1 ? 1 : (64ll << 20) / mem;
+    return threads;
+}
+
+static obj_p first_last(int last, obj_p val, obj_p index) {
+    if (!G.ready || !is_vec(val) || !index || index->type != RFB_T_LIST || index->len != 7) return NULL;
+    obj_p *ix = RFB_OBJ_LIST(index);
+    if (!ix[0] || ix[0]->type != -RFB_T_I64 || ix[0]->i64 != RFB_INDEX_IDS || !ix[1] || ix[1]->type != -RFB_T_I64) return NULL;
+    obj_p gids = ix[2], filter = ix[5], firsts = ix[6];
+    if (!gids || gids->type != RFB_T_I64) return NULL;
+    const int filtered = !is_null_obj(filter);
+    if (filtered && filter->type != RFB_T_I64) return NULL;
+    /* aggr_first without first_ids takes the partial path (first NON-null value per chunk, core/aggr.c:394-439): CPU body */
+    if (!last && (is_null_obj(firsts) || firsts->type != RFB_T_I64)) return NULL;
+    if (last && (val->type == RFB_T_B8 || val->type == RFB_T_U8)) return G.host->err_type();      /* core/aggr.c:904-1075: no case */
+    const int64_t groups = ix[1]->i64, len = gids->len;
+    if (too_small(len)) return NULL;
+    call_scope_t sc = enter();
+    obj_p res;
+    void *dv = dev_column(val), *dg = dev_column(gids), *df = filtered ? dev_column(filter) : NULL;
+    void *dout = dev_temp((size_t)(groups > 0 ? groups : 1) * 8);
+    if (!dv || !dg || (filtered && !df) || !dout) { res = G.host->err_limit(); goto out; }
+    int rc = last ? rfb_aggr_last_dev(G.ctx, val->type, dv, (const int64_t *)df, (const int64_t *)dg, len, groups,
+                                      aggr_chunks(len, groups, type_size(val->type)), dout)
+                  : rfb_aggr_dev(G.ctx, RFB_A_FIRST, val->type, dv, (const int64_t *)df, (const int64_t *)dg, len, groups, dout);
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = to_host_vector(val->type, groups, dout);
+out:
+    leave(sc);
+    return res;
+}
+obj_p rfb_aggr_first(obj_p v, obj_p i) { return first_last(0, v, i); }
+obj_p rfb_aggr_last(obj_p v, obj_p i) { return first_last(1, v, i); }
+
+/* index_group_list (core/index.c:2731-2793): group rows by the tuple of 2..8 I64-kind key columns -> the reference's 7-element
+ * index [IDS, groups, group_ids, null, null, filter, first_ids], groups numbered by first occurrence (the reference's own order
+ * on one worker; with several its radix path numbers them by partition, SURVEY Q9 — results are compared as sets there). */
+obj_p rfb_index_group_list(obj_p keys, obj_p filter) {
+    if (!G.ready || !keys || keys->type != RFB_T_LIST || keys->len < 2 || keys->len > 8) return NULL;   /* 1 column: index_group (wrapped itself) */
+    const int filtered = !is_null_obj(filter);
+    if (filtered && filter->type != RFB_T_I64) return NULL;
+    obj_p *kc = RFB_OBJ_LIST(keys);
+    for (int64_t c = 0; c < keys->len; c++)
+        if (!is_key_vec(kc[c]) || kc[c]->len != kc[0]->len) return NULL;
+    const int64_t len = filtered ? filter->len : kc[0]->len;
+    if (too_small(len) || len == 0) return NULL;
+    call_scope_t sc = enter();
+    obj_p res = NULL, gids = NULL, firsts = NULL;
+    rfb_group_info_t info;
+    const void *dk[8];
+    for (int64_t c = 0; c < keys->len; c++) { dk[c] = dev_column(kc[c]); if (!dk[c]) { res = G.host->err_limit(); goto out; } }
+    void *df = filtered ? dev_column(filter) : NULL, *dg = dev_temp((size_t)len * 8), *dfi = dev_temp((size_t)len * 8);
+    if ((filtered && !df) || !dg || !dfi) { res = G.host->err_limit(); goto out; }
+    int rc = rfb_group_keys_i64_dev(G.ctx, (int)keys->len, (const int64_t *const *)dk, (const int64_t *)df, len, (int64_t *)dg, (int64_t *)dfi, &info);
+    if (rc) { res = status_to_obj(rc); goto out; }
+    gids = to_host_vector(RFB_T_I64, len, dg);
+    firsts = to_host_vector(RFB_T_I64, info.groups, dfi);
+    res = G.host->vector(RFB_T_LIST, 7);
+    if (!res || res->type == RFB_T_ERR || !gids || !firsts || gids->type == RFB_T_ERR || firsts->type == RFB_T_ERR) {
+        if (res && res->type != RFB_T_ERR) { res->len = 0; G.host->drop_obj(res); }
+        if (gids && gids->type != RFB_T_ERR) G.host->drop_obj(gids);
+        if (firsts && firsts->type != RFB_T_ERR) G.host->drop_obj(firsts);
+        res = G.host->err_limit();
+        goto out;
+    }
+    RFB_OBJ_LIST(res)[0] = i64_atom(RFB_INDEX_IDS);
+    RFB_OBJ_LIST(res)[1] = i64_atom(info.groups);
+    RFB_OBJ_LIST(res)[2] = gids;
+    RFB_OBJ_LIST(res)[3] = i64_atom(RFB_NULL_I64);
+    RFB_OBJ_LIST(res)[4] = G.host->null_obj;
+    RFB_OBJ_LIST(res)[5] = filtered ? G.host->clone_obj(filter) : G.host->null_obj;
+    RFB_OBJ_LIST(res)[6] = firsts;
+out:
+    leave(sc);
+    return res;
+}
 
 /* ------------------------------------------------------------------ fused query entry points */
 

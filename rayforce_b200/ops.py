@@ -19,10 +19,11 @@ NP_OF = {capi.B8: np.uint8, capi.U8: np.uint8, capi.I16: np.int16, capi.I32: np.
          capi.TIME: np.int32, capi.I64: np.int64, capi.SYMBOL: np.int64, capi.TIMESTAMP: np.int64, capi.F64: np.float64}
 
 UNARY = ["ray_where", "ray_sum", "ray_min", "ray_max", "ray_avg", "ray_cnt", "ray_round", "ray_floor", "ray_ceil",
-         "ray_sort_asc", "ray_sort_desc", "ray_med", "ray_dev", "ray_distinct"]
+         "ray_sort_asc", "ray_sort_desc", "ray_med", "ray_dev", "ray_distinct", "ray_not", "ray_asc", "ray_desc"]
 BINARY = ["ray_eq", "ray_ne", "ray_lt", "ray_gt", "ray_le", "ray_ge", "filter_map", "filter_collect", "ray_add", "ray_sub",
           "ray_mul", "ray_div", "ray_fdiv", "ray_mod", "ray_xbar", "index_group", "group_map", "aggr_sum", "aggr_min", "aggr_max",
-          "aggr_count", "aggr_avg", "aggr_med", "aggr_stddev", "aggr_row", "aggr_collect", "ray_find", "ray_in", "where_lt_sum"]
+          "aggr_count", "aggr_avg", "aggr_med", "aggr_stddev", "aggr_row", "aggr_collect", "ray_find", "ray_in", "where_lt_sum",
+          "aggr_first", "aggr_last", "index_group_list", "ray_xasc", "ray_xdesc"]
 TERNARY_I64 = ["index_left_join_obj", "index_inner_join_obj"]      # (obj, obj, int64 len)
 
 
@@ -30,7 +31,7 @@ class HostApi(C.Structure):
     _fields_ = [("vector", C.CFUNCTYPE(C.c_void_p, C.c_int8, C.c_int64)), ("atom", C.CFUNCTYPE(C.c_void_p, C.c_int8)),
                 ("clone_obj", C.CFUNCTYPE(C.c_void_p, C.c_void_p)), ("drop_obj", C.CFUNCTYPE(None, C.c_void_p)),
                 ("err_type", C.CFUNCTYPE(C.c_void_p)), ("err_length", C.CFUNCTYPE(C.c_void_p)),
-                ("err_limit", C.CFUNCTYPE(C.c_void_p)), ("null_obj", C.c_void_p)]
+                ("err_limit", C.CFUNCTYPE(C.c_void_p)), ("null_obj", C.c_void_p), ("executors", C.c_void_p)]
 
 
 class OpsError(Exception):
@@ -80,6 +81,10 @@ class Ops:
             f.restype, f.argtypes = C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int64]
         L.rfb_index_asof_join_obj.restype, L.rfb_index_asof_join_obj.argtypes = C.c_void_p, [C.c_void_p] * 4
         L.rfb_where_fold.restype, L.rfb_where_fold.argtypes = C.c_void_p, [C.POINTER(C.c_void_p), C.c_int64]
+        L.rfb_at_ids.restype, L.rfb_at_ids.argtypes = C.c_void_p, [C.c_void_p, C.c_void_p, C.c_int64]
+        L.rfb_mask_logic_inplace.restype, L.rfb_mask_logic_inplace.argtypes = C.c_int, [C.c_int, C.c_void_p, C.c_void_p]
+        L.rfb_ops_set_gate.argtypes = [C.c_int]
+        L.rfb_ops_set_gate(0)     # tests call single operators on cold vectors: no cost gate
         self.NULL = self.host.null_obj
 
     # ---- objects
@@ -118,6 +123,16 @@ class Ops:
         items = [self.atom(capi.I64, 2), self.atom(capi.I64, groups), self.NULL, self.atom(capi.I64, capi.NULL_I64), self.NULL,
                  filt if filt is not None else self.NULL, self.NULL]
         return self.list_of(items)
+
+    def table(self, names, cols):
+        """a TABLE (type 98, core/rayforce.c:325-334): [SYMBOL vector of column names (symbol ids), LIST of column vectors]"""
+        o = self.list_of([self.vec(capi.SYMBOL, np.asarray(names, np.int64)), self.list_of(cols)])
+        C.c_int8.from_address(o + 2).value = 98
+        return o
+
+    @staticmethod
+    def attrs_of(o):
+        return C.c_uint8.from_address(o + 3).value
 
     def drop(self, *objs):
         for o in objs:

@@ -1,0 +1,86 @@
+"""Driver-visible proof of the drop-in boundary: the reference's UNMODIFIED objects linked with
+integration/rayforce_shim.c (ld --wrap) run on the GPU box —
+  * the reference's own test runner (tests/main.c, 185 tests) passes through the binding, with every wrapped operator family
+    served by device kernels at least once,
+  * a Rayfall script gives byte-identical output through the stock CLI and through the drop-in CLI,
+  * the stock binary loads the fused entry point as a plugin (loadfn) and gets the same answer as its own select.
+The binaries are built by oracle/Makefile in the authoring container (they need the reference sources) and travel with the repo
+snapshot (oracle/_ref is git-ignored, not gpurun-ignored); nothing here reads /root/reference."""
+import os
+import re
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+def need(name):
+    p = os.path.join(REF, name)
+    if not os.path.exists(p):
+        pytest.skip("%s was not built (make -C oracle ref dropin needs the reference sources)" % name)
+    return p
+
+
+def run(cmd, env=None, timeout=1500):
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
+    return r.returncode, r.stdout.decode(errors="replace"), r.stderr.decode(errors="replace")
+
+
+def shim_stats(err):
+    """{operator: (gpu calls, cpu calls)} from the RFB200_SHIM_STATS=1 report"""
+    out = {}
+    for m in re.finditer(r"\[rfb200 shim\]\s+(\w+)\s+gpu\s+(\d+)\s+cpu\s+(\d+)", err):
+        out[m.group(1)] = (int(m.group(2)), int(m.group(3)))
+    return out
+
+
+def test_reference_test_runner_passes_through_the_dropin():
+    exe = need("rayforce_tests_dropin")
+    rc, out, err = run([exe], {"RFB200_SHIM_STATS": "1"})
+    assert rc == 0, out[-3000:] + err[-3000:]
+    assert "All tests passed!" in out, out[-3000:]
+    st = shim_stats(err)
+    m = re.search(r"handled on the GPU: (\d+), on the reference CPU bodies: (\d+), kernels launched: (\d+)", err)
+    assert m and int(m.group(1)) > 2000 and int(m.group(3)) > 2000, err[-3000:]
+    families = ["ray_eq", "ray_lt", "ray_gt", "ray_where", "filter_collect", "ray_sum", "ray_min", "ray_max", "ray_avg", "ray_add", "ray_sub",
+                "ray_mul", "ray_div", "ray_fdiv", "ray_mod", "ray_xbar", "index_group", "aggr_sum", "aggr_min", "aggr_max", "aggr_count",
+                "aggr_avg", "ray_sort_asc", "ray_sort_desc", "ray_med", "ray_dev", "ray_find", "ray_in", "ray_distinct", "ray_asc", "ray_desc",
+                "ray_not", "ray_xasc", "ray_xdesc", "at_ids", "aggr_first"]
+    idle = [f for f in families if st.get(f, (0, 0))[0] == 0]
+    assert not idle, "wrapped operators the reference's tests never reached on the GPU: %r\n%s" % (idle, err[-4000:])
+
+
+def test_rayfall_script_output_is_identical_stock_vs_dropin():
+    stock, dropin = need("rayforce_ref"), need("rayforce_dropin")
+    script = os.path.join("integration", "demo", "parity.rfl")
+    rc0, out0, err0 = run([stock, "-f", script])
+    rc1, out1, err1 = run([dropin, "-f", script], {"RFB200_SHIM_STATS": "1"})
+    assert rc0 == 0 and rc1 == 0, (err0[-2000:], err1[-2000:])
+    lines0 = [l for l in out0.splitlines() if " : " in l]
+    lines1 = [l for l in out1.splitlines() if " : " in l]
+    assert len(lines0) >= 20
+    for a, b in zip(lines0, lines1):
+        assert a == b, "stock:  %s\ndropin: %s" % (a, b)
+    assert len(lines0) == len(lines1)
+    st = shim_stats(err1)
+    want = ("ray_and", "ray_or", "ray_not", "ray_where", "ray_sum", "index_group", "index_group_list", "aggr_sum", "aggr_first", "aggr_last",
+            "ray_asc", "ray_desc", "ray_xasc", "ray_xdesc", "ray_sort_asc")
+    idle = [fam for fam in want if st.get(fam, (0, 0))[0] == 0]
+    assert not idle, "never ran on the GPU: %r" % idle
+    m = re.search(r"HBM residency: (\d+) operand images found in HBM, (\d+) columns shipped", err1)
+    assert m and int(m.group(1)) > 0, err1[-2000:]
+
+
+def test_stock_binary_loads_the_fused_entry_point_as_a_plugin():
+    stock = need("rayforce_ref")
+    rc, out, err = run([stock, "-f", os.path.join("integration", "demo", "plugin.rfl")])
+    assert rc == 0, err[-2000:]
+    a = re.search(r"plugin\s+\(sum x\) where \(< x 500000\) : (\d+)", out)
+    b = re.search(r"select\s+\(sum x\) where \(< x 500000\) : \[(\d+)\]", out)
+    assert a and b and a.group(1) == b.group(1), out

@@ -4,6 +4,7 @@ tests/sort.c of the reference) through the operators `ray_sum`, `ray_lt`, `ray_a
 would call them; the second block walks the operator sequences of SURVEY §3.1-3.4 (select where / by, avg of an
 expression, iasc) and compares every intermediate object with the oracle."""
 import collections
+import ctypes as C
 
 import numpy as np
 import pytest
@@ -339,3 +340,135 @@ def test_parted_aggregates_with_partition_filter(ops, oracle):
         got, gt = ops.value(ops.call("aggr_max", val, idx))
         assert int(got[0]) == max(int(parts[1].max()), int(parts[2][ids].max()))
     ops.drop(val, idx)
+
+
+# ---------------------------------------------------------------- round 2: masks, at_ids, sorted values / tables, first / last, multi-key index
+
+def test_mask_logic_in_place_and_not(ops, oracle):
+    """`and` / `or` fold into their first operand in place (core/logic.c:34-86); ray_not makes a new mask (core/order.c:422-443)"""
+    n = 300_011
+    r = np.random.default_rng(3)
+    a, b = (r.random(n) < 0.3).astype(np.uint8), (r.random(n) < 0.6).astype(np.uint8)
+    for is_or, fn in ((0, np.logical_and), (1, np.logical_or)):
+        ao, bo = ops.vec(ob.B8, a), ops.vec(ob.B8, b)
+        assert ops.L.rfb_mask_logic_inplace(is_or, ao, bo) == 1
+        got, gt = ops.value(ao, drop=False)
+        assert gt == ob.B8 and np.array_equal(got, fn(a, b).astype(np.uint8))
+        assert np.array_equal(ops.value(bo, drop=False)[0], b)                   # the right operand is untouched
+        ids, _ = ops.value(ops.call("ray_where", ao))                            # the updated mask is what ray_where sees
+        assert np.array_equal(ids, np.flatnonzero(fn(a, b)))
+        for atom in (0, 1):
+            co, k = ops.vec(ob.B8, a), ops.atom(ob.B8, atom)
+            assert ops.L.rfb_mask_logic_inplace(is_or, co, k) == 1
+            assert np.array_equal(ops.value(co, drop=False)[0], fn(a, np.full(n, atom)).astype(np.uint8))
+            ops.drop(co, k)
+        short = ops.vec(ob.B8, b[:10])
+        assert ops.L.rfb_mask_logic_inplace(is_or, ao, short) == 0               # length mismatch: the CPU body's type error
+        ops.drop(ao, bo, short)
+    ao = ops.vec(ob.B8, a)
+    got, gt = ops.value(ops.call("ray_not", ao))
+    assert gt == ob.B8 and np.array_equal(got, (a == 0).astype(np.uint8))
+    i64v = ops.vec(ob.I64, np.arange(5))
+    with pytest.raises(Declined):
+        ops.value(ops.call("ray_not", i64v))
+    ops.drop(ao, i64v)
+
+
+@pytest.mark.parametrize("t", [ob.I64, ob.F64, ob.I32, ob.I16, ob.U8, ob.TIMESTAMP, ob.DATE])
+def test_sorted_values_asc_desc(ops, oracle, t):
+    """ray_asc / ray_desc (core/order.c:74-244) = x[ray_sort_asc(x)] with ATTR_ASC / ATTR_DESC set and ATTR_DISTINCT kept"""
+    n = 100_003
+    x = rng_col(t, n, seed=t + 40, null_frac=0.02, lo=-500 if t != ob.U8 else 0, hi=500 if t != ob.U8 else 200)
+    xo = ops.vec(t, x)
+    for name, desc, attr in (("ray_asc", 0, 2), ("ray_desc", 1, 4)):
+        r = ops.call(name, xo)
+        assert ops.attrs_of(r) == attr
+        got, gt = ops.value(r)
+        want = x[oracle.sort(t, x, desc)]
+        assert gt == t and (same_f64(got, want) if t == ob.F64 else np.array_equal(got, want)), name
+    ops.drop(xo)
+    s = ops.vec(ob.SYMBOL, np.arange(10))
+    with pytest.raises(Declined):                                                # symbols order by their strings: CPU body
+        ops.value(ops.call("ray_asc", s))
+    ops.drop(s)
+
+
+def test_at_ids_vector_and_table(ops, oracle):
+    """at_ids (core/rayforce.c:1100-1201): a vector, or every column of a table, gathered by a bare array of row ids"""
+    n, m = 200_003, 70_001
+    r = np.random.default_rng(8)
+    a, b, c = rng_col(ob.I64, n, 1, null_frac=0.01, lo=-9, hi=9), rng_col(ob.F64, n, 2, null_frac=0.01, lo=0, hi=1), rng_col(ob.I16, n, 3, lo=-9, hi=9)
+    ids = r.integers(0, n, m).astype(np.int64)
+    ao, bo, co, io = ops.vec(ob.I64, a), ops.vec(ob.F64, b), ops.vec(ob.I16, c), ops.vec(ob.I64, ids)
+    got, gt = ops.value(ops.L.rfb_at_ids(ao, io + 16, m))
+    assert gt == ob.I64 and np.array_equal(got, a[ids])
+    t = ops.table([11, 22, 33], [ao, bo, co])                                    # (the table owns the columns from here on)
+    res = ops.L.rfb_at_ids(t, io + 16, m)
+    assert ops.type_of(res) == 98
+    names, cols = ops.items(res)
+    assert np.array_equal(ops.value(names, drop=False)[0], [11, 22, 33])
+    for col, want, wt in zip(ops.items(cols), (a, b, c), (ob.I64, ob.F64, ob.I16)):
+        v, vt = ops.value(col, drop=False)
+        assert vt == wt and (same_f64(v, want[ids]) if wt == ob.F64 else np.array_equal(v, want[ids]))
+    ops.drop(res, t, io)
+
+
+@pytest.mark.parametrize("desc", [0, 1])
+def test_table_sorted_by_one_and_several_columns(ops, oracle, desc):
+    """ray_xasc / ray_xdesc (core/order.c:246-420): y = symbol atom -> one stable sort; y = symbol vector -> one stable sort per
+    key from the last to the first, each on the column as reordered so far"""
+    n = 150_007
+    r = np.random.default_rng(5 + desc)
+    k1, k2 = r.integers(0, 7, n).astype(np.int64), r.integers(-50, 50, n).astype(np.int32)
+    v = rng_col(ob.F64, n, 4, null_frac=0.01, lo=0, hi=1)
+    t = ops.table([101, 102, 103], [ops.vec(ob.I64, k1), ops.vec(ob.I32, k2), ops.vec(ob.F64, v)])
+    name = "ray_xdesc" if desc else "ray_xasc"
+    one = ops.atom(ob.SYMBOL, 102)
+    C.c_int8.from_address(one + 2).value = -ob.SYMBOL
+    res = ops.call(name, t, one)
+    perm = oracle.sort(ob.I32, k2, desc)
+    for col, want in zip(ops.items(ops.items(res)[1]), (k1, k2, v)):
+        got = ops.value(col, drop=False)[0]
+        assert same_f64(got, want[perm]) if want.dtype == np.float64 else np.array_equal(got, want[perm])
+    ops.drop(res)
+    by = ops.vec(ob.SYMBOL, np.array([101, 102], np.int64))
+    res = ops.call(name, t, by)
+    perm = np.arange(n)
+    for col, ct in ((k2, ob.I32), (k1, ob.I64)):                                 # last key first, stable
+        perm = perm[oracle.sort(ct, col[perm], desc)]
+    for col, want in zip(ops.items(ops.items(res)[1]), (k1, k2, v)):
+        got = ops.value(col, drop=False)[0]
+        assert same_f64(got, want[perm]) if want.dtype == np.float64 else np.array_equal(got, want[perm])
+    missing = ops.atom(ob.SYMBOL, 999)
+    C.c_int8.from_address(missing + 2).value = -ob.SYMBOL
+    with pytest.raises(Declined):                                                # unknown column: the CPU body's error
+        ops.value(ops.call(name, t, missing))
+    ops.drop(res, by, one, missing, t)
+
+
+@pytest.mark.parametrize("filtered", [False, True])
+def test_aggr_first_last_and_multi_key_index(ops, oracle, filtered):
+    n = 120_011
+    r = np.random.default_rng(17)
+    ka, kb = r.integers(0, 40, n).astype(np.int64), (r.integers(0, 25, n) * 1000).astype(np.int64)
+    val = rng_col(ob.I64, n, 6, null_frac=0.3, lo=-100, hi=100)
+    filt = np.sort(r.choice(n, n // 3, replace=False)).astype(np.int64) if filtered else None
+    wg, wf, groups = oracle.group_multi([ka, kb], filt)
+    keys = ops.list_of([ops.vec(ob.I64, ka), ops.vec(ob.I64, kb)])
+    vo = ops.vec(ob.I64, val)
+    fo = ops.vec(ob.I64, filt) if filtered else ops.NULL
+    with ops.scope():
+        idx = ops.call("index_group_list", keys, fo)
+        it = ops.items(idx)
+        assert ops.len_of(idx) == 7 and int(ops.value(it[1], drop=False)[0]) == groups
+        assert np.array_equal(ops.value(it[2], drop=False)[0], wg) and np.array_equal(ops.value(it[6], drop=False)[0], wf)
+        got, gt = ops.value(ops.call("aggr_sum", vo, idx))
+        assert np.array_equal(got, oracle.aggr(ob.SUM, ob.I64, val, wg, groups, filt)[0])
+        got, gt = ops.value(ops.call("aggr_first", vo, idx))
+        assert gt == ob.I64 and np.array_equal(got, oracle.aggr(ob.FIRST, ob.I64, val, wg, groups, filt)[0])
+        got, gt = ops.value(ops.call("aggr_last", vo, idx))                      # builtin host: one executor -> one chunk
+        assert gt == ob.I64 and np.array_equal(got, oracle.aggr(ob.LAST, ob.I64, val, wg, groups, filt)[0])
+        ops.drop(idx)
+    ops.drop(keys, vo)
+    if filtered:
+        ops.drop(fo)
