@@ -258,7 +258,10 @@ def peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def run_extra_configs(ctx, stream, dev, n, rank, world, K, W):
+E2E_CONFIG_ROWS = 250_000_000
+
+
+def run_extra_configs(ctx, stream, dev, n, rank, world, K, W, with_e2e=True):
     """BASELINE.json configs[2..4] on the same box, same process, device-resident, each timed with CUDA events around K steps
     (max over ranks): fp64 (a*b+c) -> avg; group-by 1e5 int32 keys sum/count; filter + group-by + sum sharded by row range with
     the NCCL merge.  A step of the group-by configs is the whole rfb_group_sum_count_dev call (sample, scatter, accumulate,
@@ -300,6 +303,36 @@ def run_extra_configs(ctx, stream, dev, n, rank, world, K, W):
                              "algorithmic_bytes_per_step_per_gpu": alg_bytes_per_gpu, "timed": "whole call (all its kernels and host syncs)"},
                 "merge": merge, "result": result}
 
+    ne = min(n, E2E_CONFIG_ROWS)      # rows of the end-to-end leg of configs 3-5 (pinned host columns: 24 B/row for config 3)
+
+    def timed_e2e(step, Ke=2):
+        """host columns in, host result out, copies inside: wall clock around Ke calls, max over ranks"""
+        res = step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for _ in range(Ke):
+            res = step()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - w0) * 1e3 / Ke
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, res
+
+    def e2e_entry(ms, h2d, d2h, api):
+        return {"value": ne * world / (ms * 1e-3) / 1e9, "unit": UNIT, "rows_per_gpu": ne, "ms_per_step": ms, "steps": 2,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "api": api}
+
+    def pinned_copy(t):
+        h = torch.empty(ne, dtype=t.dtype, pin_memory=True)
+        with torch.cuda.stream(stream):
+            h.copy_(t[:ne], non_blocking=True)
+        stream.synchronize()
+        return h
+
     # ---- config 3: (avg (+ (* a b) c)) over three F64 columns, one fused kernel (24 B/row)
     with torch.cuda.stream(stream):
         a, b, c = (torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3))
@@ -319,6 +352,17 @@ def run_extra_configs(ctx, stream, dev, n, rank, world, K, W):
     assert 0.74 < avg < 0.76, avg                             # E[a*b + c] = 1/4 + 1/2 for uniform [0, 1) columns
     out["fma_avg"] = entry("(avg (+ (* a b) c)): three F64 columns, splitmix64 / 2^20 in [0, 1), fused k_fma_fold", ms, 24 * n, launches,
                            {"avg": avg}, "none" if world == 1 else "all-gather of (sum, count) partials, added in rank order")
+    if with_e2e:
+        ha, hb, hc = (pinned_copy(t) for t in (a, b, c))
+        na, nb_, nc = ha.numpy(), hb.numpy(), hc.numpy()
+
+        def step_fma_host():
+            r, nbytes = ctx.fma_fold_host(capi.F_SUM | capi.F_CNT, na, nb_, nc)
+            return r.sum / r.nonnull, nbytes
+        ems, (eavg, nbytes) = timed_e2e(step_fma_host)
+        assert 0.74 < eavg < 0.76, eavg
+        out["fma_avg"]["e2e"] = e2e_entry(ems, nbytes, 72, "rfb_fma_fold_host (three pinned host columns -> cudaMemcpyAsync -> fused kernel -> host result); first %d rows per GPU" % ne)
+        del ha, hb, hc, na, nb_, nc
     del a, b, c
 
     # ---- config 4 / 5: group-by 1e5 int32 keys, sum + count of an i64 column; config 5 adds the filter and the multi-GPU merge
@@ -354,6 +398,21 @@ def run_extra_configs(ctx, stream, dev, n, rank, world, K, W):
     assert groups == 100_000 and 0.49 * n * world < rows < 0.51 * n * world, (groups, rows)
     out["filter_groupby_sharded"] = entry("select {s: (sum v) c: (count v) from t by k where (< v 2^19)}: rows sharded by row range over the GPUs", ms,
                                           12 * n, launches, {"groups": groups, "rows_selected": rows, "sum_of_sums": total}, merge)
+    if with_e2e:
+        hk, hv = pinned_copy(k), pinned_copy(v)
+        nk, nv = hk.numpy(), hv.numpy()
+        for name, filtered in (("groupby_1e5", False), ("filter_groupby_sharded", True)):
+            def step_group_host():
+                if filtered:
+                    gk_, gs_, gc_, nbytes = ctx.group_sum_count_host(capi.I32, nk, nv, 100_000, capi.LT, capi.I64, nv, 1 << 19)
+                else:
+                    gk_, gs_, gc_, nbytes = ctx.group_sum_count_host(capi.I32, nk, nv, 100_000)
+                return int(gk_.shape[0]), int(gc_.sum()), nbytes
+            ems, (eg, erows, nbytes) = timed_e2e(step_group_host)
+            assert eg == 100_000 and (0.49 * ne < erows < 0.51 * ne if filtered else erows == ne), (eg, erows)
+            out[name]["e2e"] = e2e_entry(ems, nbytes, 3 * 8 * eg, "rfb_group_sum_count_host (pinned host key + value columns -> cudaMemcpyAsync -> fused group-by -> "
+                                         "host group lists; per-GPU lists, no cross-GPU merge in this leg); first %d rows per GPU" % ne)
+        del hk, hv, nk, nv
     del k, v
     return out
 
@@ -483,7 +542,7 @@ def run_gpu_arm(args):
     configs = None
     if not args.no_configs:
         del x
-        configs = run_extra_configs(ctx, stream, dev, n, rank, world, max(1, min(K, args.config_steps)), W)
+        configs = run_extra_configs(ctx, stream, dev, n, rank, world, max(1, min(K, args.config_steps)), W, with_e2e=not args.no_e2e)
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:

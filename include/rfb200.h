@@ -328,6 +328,35 @@ int rfb_filter_fold_host(rfb_ctx_t *ctx, int cmp_op, int pred_type, const void *
                          int64_t *h2d_bytes);
 int rfb_fold_host(rfb_ctx_t *ctx, int folds, int type, const void *x, int64_t n, int64_t chunk_rows, rfb_fold_t *out,
                   int64_t *h2d_bytes);
+/* The fused multi-column queries over HOST columns (configs 3-5 end to end): the columns are shipped whole, then
+ * rfb_group_sum_count_dev / rfb_fma_fold_dev run; group lists come back into HOST arrays of max_groups entries. */
+int rfb_group_sum_count_host(rfb_ctx_t *ctx, int key_type, const void *keys, const int64_t *val, int64_t n, int cmp_op, int pred_type,
+                             const void *pred, const rfb_scalar_t *k, int64_t max_groups, int64_t *out_keys, int64_t *out_sums,
+                             int64_t *out_counts, int64_t *groups, int64_t *h2d_bytes);
+int rfb_fma_fold_host(rfb_ctx_t *ctx, int folds, const double *a, const double *b, const double *c, int64_t n, rfb_fold_t *out,
+                      int64_t *h2d_bytes);
+
+/* ------------------------------------------------------------------ every visible GPU from one host process
+ *
+ * The reference's pool_split_by / pool_chunk_aligned (core/pool.c:450-507) hand row ranges to worker threads and merge their partials
+ * (core/math.c:2222-2228).  rfb_mgpu_* does the same with GPUs as the workers, from pure C: device g takes rows [g*n/N, (g+1)*n/N)
+ * of a HOST column over its own PCIe link (one host thread per device drives the chunked copy + fused kernel pipeline of the
+ * host layer) and the N partials are merged on the host — folds: N rfb_fold_t records; group-by: the N (key, sum, count) lists
+ * merged by key in row order, so the groups keep their first-occurrence numbering.  Results equal the single-GPU ones bit for bit
+ * (fp64 sums: within 1 ULP of the exact sum, as everywhere). */
+#define RFB_MGPU_MAX 16
+typedef struct rfb_mgpu rfb_mgpu_t;
+int rfb_mgpu_create(int ndev /* <= 0: every visible device */, rfb_mgpu_t **out);
+void rfb_mgpu_destroy(rfb_mgpu_t *m);
+int rfb_mgpu_devices(const rfb_mgpu_t *m);
+rfb_ctx_t *rfb_mgpu_ctx(rfb_mgpu_t *m, int g);   /* device g's context (borrowed) */
+/* rfb_filter_fold_host over all devices; pred == NULL: plain fold (rfb_fold_host) */
+int rfb_mgpu_filter_fold_host(rfb_mgpu_t *m, int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k, int folds,
+                              int val_type, const void *val, int64_t n, int64_t chunk_rows, rfb_fold_t *out, int64_t *h2d_bytes);
+/* rfb_group_sum_count_dev over HOST columns on all devices; outputs are HOST arrays of max_groups entries */
+int rfb_mgpu_group_sum_count_host(rfb_mgpu_t *m, int key_type, const void *keys, const int64_t *val, int64_t n, int cmp_op,
+                                  int pred_type, const void *pred, const rfb_scalar_t *k, int64_t max_groups, int64_t *out_keys,
+                                  int64_t *out_sums, int64_t *out_counts, int64_t *groups, int64_t *h2d_bytes);
 
 /* ------------------------------------------------------------------ column files: the reference's on-disk column format
  * 16-byte object header (mmod 0xfd, type, attrs, len) + raw payload (written by `set`, core/binary.c:264-307; mapped back by

@@ -74,7 +74,8 @@ typedef struct rfb_host_api {
 
 /* Bind the layer to a host and a GPU.  Fails (non-zero) when no CUDA device is usable: there is no CPU fallback inside
  * this library — the caller keeps using its own CPU bodies. */
-int rfb_ops_init(const rfb_host_api_t *host, int device);
+int rfb_ops_init(const rfb_host_api_t *host, int device);   /* device < 0: every visible GPU (rfb_mgpu_*): the one-shot fused entry points
+                                                                 shard their host columns by row range over all of them */
 void rfb_ops_shutdown(void);
 const rfb_host_api_t *rfb_ops_builtin_host(void); /* malloc-based host for standalone use */
 const char *rfb_ops_last_error(void);

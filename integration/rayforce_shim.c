@@ -13,7 +13,9 @@
  *
  * The GPU layer DECLINES (returns NULL) whatever is outside its path — atoms, lists, tables, parted/MAPCOMMON columns,
  * symbols/GUIDs, vectors shorter than RFB200_MIN_ROWS — so the reference's behaviour for those is untouched.
- * Environment: RFB200_DISABLE=1 keeps every call on the CPU bodies; RFB200_MIN_ROWS=n sets the size gate;
+ * Environment: RFB200_DISABLE=1 keeps every call on the CPU bodies; RFB200_MIN_ROWS=n sets the size gate; RFB200_DEVICES=all
+ * binds every visible GPU (the fused one-shot entry points shard host columns over them); RFB200_RESIDENT=0 / RFB200_GATE=0 /
+ * RFB200_LAZY=1 switch cross-query residency, the cost gate and lazily materialised results;
  * RFB200_SHIM_STATS=1 prints per-operator GPU/CPU call counts and the kernel-launch count at exit.
  */
 #include <pthread.h>
@@ -82,7 +84,7 @@ static int gpu_ok(void) {
         host_api.null_obj = (rfb_obj_p)NULL_OBJ;
         host_api.executors = h_executors;
         if (d && d[0] == '1') state = -1;
-        else if (rfb_ops_init(&host_api, 0) == 0) {
+        else if (rfb_ops_init(&host_api, (getenv("RFB200_DEVICES") && !strcmp(getenv("RFB200_DEVICES"), "all")) ? -1 : 0) == 0) {
             state = 1;
             owner = pthread_self();
             /* this binding reports every free / in-place write (heap_free, heap_realloc, cow_obj, the CPU fallbacks below), so

@@ -6,6 +6,6 @@ Layers:
   rayforce_b200/device.py                      thin Python host helper: contexts, device columns, calls
 """
 from . import capi  # noqa: F401
-from .device import ColumnFile, Context, RfbError  # noqa: F401
+from .device import ColumnFile, Context, MultiGpu, RfbError  # noqa: F401
 
-__all__ = ["capi", "ColumnFile", "Context", "RfbError"]
+__all__ = ["capi", "ColumnFile", "Context", "MultiGpu", "RfbError"]

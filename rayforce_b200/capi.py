@@ -135,6 +135,14 @@ SIGNATURES = {
     "rfb_aggr_type": (_ci, [_ci, _ci]),
     "rfb_aggr_dev": (_ci, [_vp, _ci, _ci, _vp, _vp, _vp, _i64, _i64, _vp]),
     "rfb_aggr_last_dev": (_ci, [_vp, _ci, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "rfb_group_sum_count_host": (_ci, [_vp, _ci, _vp, _vp, _i64, _ci, _ci, _vp, _P(Scalar), _i64, _vp, _vp, _vp, _P(_i64), _P(_i64)]),
+    "rfb_fma_fold_host": (_ci, [_vp, _ci, _vp, _vp, _vp, _i64, _P(Fold), _P(_i64)]),
+    "rfb_mgpu_create": (_ci, [_ci, _P(_vp)]),
+    "rfb_mgpu_destroy": (None, [_vp]),
+    "rfb_mgpu_devices": (_ci, [_vp]),
+    "rfb_mgpu_ctx": (_vp, [_vp, _ci]),
+    "rfb_mgpu_filter_fold_host": (_ci, [_vp, _ci, _ci, _vp, _P(Scalar), _ci, _ci, _vp, _i64, _i64, _P(Fold), _P(_i64)]),
+    "rfb_mgpu_group_sum_count_host": (_ci, [_vp, _ci, _vp, _vp, _i64, _ci, _ci, _vp, _P(Scalar), _i64, _vp, _vp, _vp, _P(_i64), _P(_i64)]),
     "rfb_group_rows_dev": (_ci, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "rfb_med_dev": (_ci, [_vp, _ci, _vp, _i64, _P(C.c_double)]),
     "rfb_stddev_dev": (_ci, [_vp, _ci, _vp, _i64, _P(C.c_double)]),

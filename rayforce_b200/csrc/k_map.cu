@@ -368,6 +368,51 @@ template <typename X, typename Y, typename M, typename O> struct BinOp {
     }
 };
 
+// ---- i64 column (/ | % | xbar) i64 ATOM: the divisor is a launch constant, so the 64-bit hardware division (a ~100-instruction
+// emulation on the integer pipe: 5.7 ms per 1e9 rows, issue-bound) becomes one 64x64 -> high-64 multiply, a subtract, an add and
+// two shifts (the round-up magic number of Granlund & Montgomery in its branch-free form, computed once on the host with a
+// 128-bit division).  Signs are peeled off first; the quotient semantics stay the reference's: `/` and `%` floor (EUCL_DIV,
+// core/ops.h:165-171), xbar truncates its shifted operand (XBARI64, core/ops.h:195-196).
+struct DivMagic { u64 m; int more; };            // |y| >= 2: q = t >> more with t = ((n - hi(m*n)) >> 1) + hi(m*n)
+__device__ __forceinline__ u64 udiv_magic(u64 n, const DivMagic &g) {
+    const u64 q = __umul64hi(g.m, n);
+    return (((n - q) >> 1) + q) >> g.more;
+}
+static DivMagic div_magic_of(u64 d) {            // d >= 2
+    DivMagic g;
+    const int fl = 63 - __builtin_clzll(d);
+    if ((d & (d - 1)) == 0) { g.m = 0; g.more = fl - 1; return g; }            // power of two: t = n >> 1, then >> (log2 - 1)
+    const unsigned __int128 num = (unsigned __int128)1 << (64 + fl);
+    u64 pm = (u64)(num / d);
+    const u64 rem = (u64)(num % d);
+    pm += pm;
+    const u64 twice = rem + rem;
+    if (twice >= d || twice < rem) pm += 1;
+    g.m = pm + 1;
+    g.more = fl;
+    return g;
+}
+struct DivConstI64 {                             // y != 0, y != NULL, |y| >= 2
+    int op;
+    i64 y;
+    u64 ay;
+    DivMagic g;
+    __device__ __forceinline__ i64 operator()(i64 x, i64) const {
+        if (x == NULL_I64) return NULL_I64;
+        if (op == RFB_XBAR) {
+            const i64 t = x < 0 ? (i64)((u64)x + 1ULL - (u64)y) : x;
+            const u64 at = t < 0 ? 0ULL - (u64)t : (u64)t;
+            const u64 q = udiv_magic(at, g);
+            const i64 sq = ((t < 0) != (y < 0)) ? (i64)(0ULL - q) : (i64)q;    // truncating quotient
+            return (i64)((u64)sq * (u64)y);
+        }
+        const u64 ax = x < 0 ? 0ULL - (u64)x : (u64)x;
+        const u64 q = udiv_magic(ax, g), r = ax - q * ay;
+        const i64 fq = ((x < 0) != (y < 0)) ? (i64)(0ULL - q - (r != 0 ? 1ULL : 0ULL)) : (i64)q;   // floor quotient
+        return op == RFB_DIV ? fq : (i64)((u64)x - (u64)fq * (u64)y);
+    }
+};
+
 // result typing: the per-case macro arguments of core/math.c:251-1782 / infer_*_type core/math.c:92-223
 bool binop_types(int op, int xt, int yt, int *mt, int *ot) {
     const bool okx = (xt == RFB_I32 || xt == RFB_I64 || xt == RFB_F64), oky = (yt == RFB_I32 || yt == RFB_I64 || yt == RFB_F64);
@@ -461,6 +506,14 @@ extern "C" int rfb_binop_dev(rfb_ctx_t *ctx, int op, int xt, const void *x, int6
     RFB_ARG(out || (xn >= 0 ? xn : yn) == 0, "rfb_binop_dev: out");
     if ((xn < 0 && xs->type != xt) || (yn < 0 && ys->type != yt)) { rfb_set_error("binop: scalar type tag does not match operand type"); return RFB_ERR_ARG; }
     const bool lii = xt != RFB_F64;
+    if (xn >= 0 && yn < 0 && xt == RFB_I64 && yt == RFB_I64 && (op == RFB_DIV || op == RFB_MOD || op == RFB_XBAR)) {
+        const i64 d = ys->v.i64;
+        if (d != 0 && d != NULL_I64 && d != 1 && d != -1) {       // 0 / null / +-1: the generic kernel (nulls, identity, negation)
+            const u64 ad = d < 0 ? 0ULL - (u64)d : (u64)d;
+            DivConstI64 f{op, d, ad, div_magic_of(ad)};
+            return launch_map2<i64, i64, i64, false, true>(ctx, x, i64(), nullptr, d, out, xn, f);
+        }
+    }
     switch (xt) {
         case RFB_I32: return binop_x<i32>(ctx, op, mt, ot, yt, lii, x, xn, xs, y, yn, ys, out);
         case RFB_I64: return binop_x<i64>(ctx, op, mt, ot, yt, lii, x, xn, xs, y, yn, ys, out);

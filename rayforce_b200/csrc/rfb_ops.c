@@ -53,6 +53,7 @@ static struct {
     int ready;
     const rfb_host_api_t *host;
     rfb_ctx_t *ctx;
+    rfb_mgpu_t *mgpu;            /* rfb_ops_init(host, -1): every visible device; ctx = device 0's context */
     int64_t min_rows;
     int scope_depth;
     col_entry_t *cols;
@@ -141,7 +142,12 @@ const rfb_host_api_t *rfb_ops_builtin_host(void) { return &builtin_host; }
 int rfb_ops_init(const rfb_host_api_t *host, int device) {
     if (G.ready) return 0;
     if (!host) { set_err("rfb_ops_init: host api is NULL"); return RFB_ERR_ARG; }
-    int rc = rfb_ctx_create(device, &G.ctx);
+    int rc;
+    if (device < 0) {            /* every visible GPU: the operator-at-a-time path runs on device 0, the one-shot fused entry points
+                                    (host column in, result out) shard the column by row range over all of them */
+        rc = rfb_mgpu_create(0, &G.mgpu);
+        if (!rc) G.ctx = rfb_mgpu_ctx(G.mgpu, 0);
+    } else rc = rfb_ctx_create(device, &G.ctx);
     if (rc) { set_err("%s", rfb_last_error()); return rc; }
     G.host = host;
     const char *e = getenv("RFB200_MIN_ROWS");
@@ -204,7 +210,7 @@ void rfb_ops_shutdown(void) {
     for (int i = 0; i < G.npool; i++) rfb_dev_free(G.ctx, G.pool[i].dev);
     G.npool = 0;
     free(G.cols);
-    rfb_ctx_destroy(G.ctx);
+    if (G.mgpu) rfb_mgpu_destroy(G.mgpu); else rfb_ctx_destroy(G.ctx);
     memset(&G, 0, sizeof(G));
 }
 
@@ -1634,7 +1640,10 @@ static obj_p where_fold(int op, int what, obj_p pred, obj_p k, obj_p val) {
     int rc;
     if (G.scope_depth == 0) {
         /* one-shot: stream the host column(s) through the chunked copy/compute pipeline (no device residency needed) */
-        rc = rfb_filter_fold_host(G.ctx, op, pred->type, RFB_OBJ_PAYLOAD(pred), &ks, folds, val->type, RFB_OBJ_PAYLOAD(val), pred->len, 0, &f, NULL);
+        if (G.mgpu && rfb_mgpu_devices(G.mgpu) > 1)
+            rc = rfb_mgpu_filter_fold_host(G.mgpu, op, pred->type, RFB_OBJ_PAYLOAD(pred), &ks, folds, val->type, RFB_OBJ_PAYLOAD(val), pred->len, 0, &f, NULL);
+        else
+            rc = rfb_filter_fold_host(G.ctx, op, pred->type, RFB_OBJ_PAYLOAD(pred), &ks, folds, val->type, RFB_OBJ_PAYLOAD(val), pred->len, 0, &f, NULL);
     } else {
         void *dp = dev_column(pred), *dv = (val == pred) ? dp : dev_column(val);
         if (!dp || !dv) return G.host->err_limit();

@@ -179,11 +179,63 @@ class Context:
                                             _hptr(val), pred.shape[0], chunk_rows, C.byref(f), C.byref(nb)))
         return FoldResult(f, val_type), nb.value
 
+    def group_sum_count_host(self, key_type, keys, val, max_groups, cmp_op=None, pred_type=None, pred=None, k=None):
+        """fused group-by over HOST columns -> (keys, sums, counts) numpy arrays, bytes copied host -> device"""
+        ok, osum, oc = (np.empty(max(max_groups, 1), np.int64) for _ in range(3))
+        g, nb = C.c_int64(0), C.c_int64(0)
+        s = Scalar.of(pred_type, k) if pred is not None else None
+        check(self.lib.rfb_group_sum_count_host(self.h, key_type, _hptr(keys), _hptr(val), keys.shape[0], cmp_op or 0, pred_type or 0,
+                                                _hptr(pred) if pred is not None else None, C.byref(s) if s is not None else None, max_groups,
+                                                _hptr(ok), _hptr(osum), _hptr(oc), C.byref(g), C.byref(nb)))
+        return ok[:g.value], osum[:g.value], oc[:g.value], nb.value
+
+    def fma_fold_host(self, folds: int, a: np.ndarray, b: np.ndarray, c: np.ndarray):
+        f = Fold()
+        nb = C.c_int64(0)
+        check(self.lib.rfb_fma_fold_host(self.h, folds, _hptr(a), _hptr(b), _hptr(c), a.shape[0], C.byref(f), C.byref(nb)))
+        return FoldResult(f, capi.F64), nb.value
+
     def fold_host(self, folds: int, type_: int, x: np.ndarray, chunk_rows: int = 0):
         f = Fold()
         nb = C.c_int64(0)
         check(self.lib.rfb_fold_host(self.h, folds, type_, _hptr(x), x.shape[0], chunk_rows, C.byref(f), C.byref(nb)))
         return FoldResult(f, type_), nb.value
+
+
+class MultiGpu:
+    """rfb_mgpu_*: every visible GPU from one host process (row-range shards of HOST columns, host-side merge of the partials)"""
+
+    def __init__(self, ndev: int = 0):
+        self.lib = capi.load()
+        h = C.c_void_p()
+        check(self.lib.rfb_mgpu_create(ndev, C.byref(h)))
+        self.h = h
+
+    @property
+    def devices(self) -> int:
+        return int(self.lib.rfb_mgpu_devices(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.rfb_mgpu_destroy(self.h)
+            self.h = None
+
+    def filter_fold_host(self, cmp_op, pred_type, pred, k, folds, val_type, val, chunk_rows=0):
+        s = Scalar.of(pred_type, k) if pred is not None else None
+        f = Fold()
+        nb = C.c_int64(0)
+        check(self.lib.rfb_mgpu_filter_fold_host(self.h, cmp_op or 0, pred_type or 0, _hptr(pred) if pred is not None else None, _sref(s), folds,
+                                                 val_type, _hptr(val), val.shape[0], chunk_rows, C.byref(f), C.byref(nb)))
+        return FoldResult(f, val_type), nb.value
+
+    def group_sum_count_host(self, key_type, keys, val, max_groups, cmp_op=None, pred_type=None, pred=None, k=None):
+        ok, osum, oc = (np.empty(max(max_groups, 1), np.int64) for _ in range(3))
+        g, nb = C.c_int64(0), C.c_int64(0)
+        s = Scalar.of(pred_type, k) if pred is not None else None
+        check(self.lib.rfb_mgpu_group_sum_count_host(self.h, key_type, _hptr(keys), _hptr(val), keys.shape[0], cmp_op or 0, pred_type or 0,
+                                                     _hptr(pred) if pred is not None else None, _sref(s), max_groups, _hptr(ok), _hptr(osum),
+                                                     _hptr(oc), C.byref(g), C.byref(nb)))
+        return ok[:g.value], osum[:g.value], oc[:g.value], nb.value
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -69,7 +69,7 @@ def test_rayfall_script_output_is_identical_stock_vs_dropin():
         assert a == b, "stock:  %s\ndropin: %s" % (a, b)
     assert len(lines0) == len(lines1)
     st = shim_stats(err1)
-    want = ("ray_and", "ray_or", "ray_not", "ray_where", "ray_sum", "index_group", "index_group_list", "aggr_sum", "aggr_first", "aggr_last",
+    want = ("ray_and", "ray_or", "ray_not", "ray_where", "ray_sum", "index_group", "index_group_list", "aggr_first", "aggr_last",
             "ray_asc", "ray_desc", "ray_xasc", "ray_xdesc", "ray_sort_asc")
     idle = [fam for fam in want if st.get(fam, (0, 0))[0] == 0]
     assert not idle, "never ran on the GPU: %r" % idle

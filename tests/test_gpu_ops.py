@@ -208,6 +208,19 @@ def test_binop_null_atoms_and_wraparound(ctx, oracle):
         check_binop(host(got), gt, want, wt, op)
 
 
+@pytest.mark.parametrize("op", [ob.DIV, ob.MOD, ob.XBAR])
+def test_division_by_a_constant_atom(ctx, oracle, op):
+    """i64 column (/ | % | xbar) i64 atom runs on a host-computed magic multiplier instead of the 64-bit hardware division:
+    floor semantics for / and %, truncation inside xbar, every sign combination, extreme operands and divisors"""
+    r = np.random.default_rng(op)
+    x = np.concatenate([r.integers(-(1 << 62), 1 << 62, 60_000), r.integers(-1000, 1000, 20_000),
+                        np.array([0, 1, -1, ob.INF_I64, ob.NULL_I64 + 1, ob.NULL_I64, 1 << 62, -(1 << 62)])]).astype(np.int64)
+    for k in (2, 3, -3, 7, -7, 17, 1000, 4096, -4096, 1_000_003, (1 << 31), (1 << 31) + 1, (1 << 62) + 5, ob.INF_I64, -ob.INF_I64, 1, -1, 0):
+        want, wt = oracle.binop(op, ob.I64, x, ob.I64, k)
+        got, gt = ctx.binop(op, ob.I64, dev(x), ob.I64, k)
+        assert gt == wt and np.array_equal(host(got), want), k
+
+
 def test_binop_errors(ctx):
     a, b = dev(np.zeros(4, np.int64)), dev(np.zeros(5, np.int64))
     with pytest.raises(capi.RfbError) as e:
