@@ -119,6 +119,9 @@ int rfb_ctx_set_result_ptr(rfb_ctx_t *ctx, void *device_visible);
 int rfb_ctx_sm_count(rfb_ctx_t *ctx);
 int rfb_sync(rfb_ctx_t *ctx);
 int64_t rfb_launch_count(rfb_ctx_t *ctx);       /* kernels launched through this context so far */
+/* The tuning knobs (RFB_GROUP_STRATEGY, RFB_PART_MIN_ROWS, RFB_ACCUM_TMA) are read from the environment once, on first
+ * use — never on the per-call path.  A host that changes them afterwards calls this to have them read again. */
+void rfb_options_reload(void);
 
 int rfb_dev_alloc(rfb_ctx_t *ctx, size_t bytes, void **dptr);
 int rfb_dev_free(rfb_ctx_t *ctx, void *dptr);

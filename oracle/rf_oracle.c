@@ -4,7 +4,7 @@
  *
  * Parity status: PINNED — checked against golden vectors transcribed from the reference's tests
  * (tests/golden/reference_kat.json) and differentially against the reference compiled from source
- * (oracle/_ref/librayforce_ref.so) by tests/test_oracle_pinning.py.
+ * (oracle/_ref/librayforce_ref.so) by tests/test_oracle_golden.py and tests/test_oracle_vs_reference.py.
  *
  * All citations are paths inside the reference tree (commit 2151d51d).
  */

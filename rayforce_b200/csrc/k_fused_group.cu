@@ -1085,17 +1085,10 @@ k_fused_emit(FS fs, i64 limit, i64 kmin, Accums a, i64 max_groups, i64 *out_keys
         });
 }
 
-// tuning knobs (environment): RFB_GROUP_STRATEGY = smem | part | narrow | l2 | hash forces a strategy where it is applicable;
-// RFB_PART_MIN_ROWS = smallest row count that takes the partitioned strategy
-int group_strategy_forced() {
-    const char *s = getenv("RFB_GROUP_STRATEGY");
-    if (!s) return 0;
-    return !strcmp(s, "smem") ? 1 : (!strcmp(s, "part") ? 2 : (!strcmp(s, "l2") ? 3 : (!strcmp(s, "narrow") ? 4 : (!strcmp(s, "hash") ? 5 : 0))));
-}
-i64 part_min_rows() {
-    const char *s = getenv("RFB_PART_MIN_ROWS");
-    return s ? atoll(s) : (1ll << 21);
-}
+// tuning knobs (environment, read once — rfb_options_reload() re-reads them): RFB_GROUP_STRATEGY = smem | part | narrow | l2 | hash
+// forces a strategy where it is applicable; RFB_PART_MIN_ROWS = smallest row count that takes the partitioned strategy
+int group_strategy_forced() { return rfb_options()->group_strategy; }
+i64 part_min_rows() { return rfb_options()->part_min_rows; }
 
 
 // ---- host side of the narrow path
@@ -1323,8 +1316,7 @@ int fused_run(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, i64 max_groups, i64 
         k_ms_exceptions<<<rfb_grid_for(ctx, rs.exc_cap, THREADS, 2), THREADS, 0, ctx->stream>>>(rs.exc, rs.exc_count, kmin, a, true);
         RFB_CHECK_LAUNCH(ctx);
     } else if (strategy == 2) {
-        const char *tma = getenv("RFB_ACCUM_TMA");       // "0": the register-staged kernel (128-bit loads) instead of the TMA ring
-        if (!(tma && tma[0] == '0')) {
+        if (rfb_options()->accum_tma) {                  // RFB_ACCUM_TMA=0: the register-staged kernel (128-bit loads) instead of the TMA ring
             const size_t smem = ASTAGES * sizeof(AccumStage) + KP * 12;
             RFB_CUDA(cudaFuncSetAttribute(k_part_accum_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_part_accum_tma<<<ctx->sm_count, AT, smem, ctx->stream>>>(ps, (int)P, kbase, kmin, a);

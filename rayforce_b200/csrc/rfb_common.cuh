@@ -79,6 +79,10 @@ int rfb_filter_fold_launch(rfb_ctx_t *ctx, int cmp_op, int pred_type, const void
 int rfb_aggr_med_launch(rfb_ctx_t *ctx, int val_type, const void *val, const int64_t *filter, const int64_t *group_ids, int64_t len, int64_t groups, double *out);
 int rfb_aggr_stddev_launch(rfb_ctx_t *ctx, int val_type, const void *val, const int64_t *filter, const int64_t *group_ids, int64_t len, int64_t groups, double *out);
 
+// run-time tuning knobs: read from the environment ONCE (first use), never on the per-call path; rfb_options_reload() re-reads them
+struct rfb_options_t { int loaded; int group_strategy; i64 part_min_rows; int accum_tma; };
+const rfb_options_t *rfb_options();
+
 // k_fused_group.cu: per-group integer sums + counts over dense group ids through the narrow partitioned passes
 size_t rfb_narrow_sums_bytes(i64 n);
 int rfb_narrow_sums(rfb_ctx_t *ctx, const i64 *gid, const i64 *val, i64 n, i64 groups, void *work, u64 *sum, u64 *cnt, u32 *has_null,

@@ -66,6 +66,23 @@ int rfb_ensure_aux2(rfb_ctx_t *ctx, size_t bytes, void **out) {
     return RFB_OK;
 }
 
+static rfb_options_t g_options;
+extern "C" void rfb_options_reload(void) {
+    rfb_options_t o;
+    const char *s = getenv("RFB_GROUP_STRATEGY");
+    o.group_strategy = !s ? 0 : (!strcmp(s, "smem") ? 1 : (!strcmp(s, "part") ? 2 : (!strcmp(s, "l2") ? 3 : (!strcmp(s, "narrow") ? 4 : (!strcmp(s, "hash") ? 5 : 0)))));
+    s = getenv("RFB_PART_MIN_ROWS");
+    o.part_min_rows = s ? atoll(s) : (1ll << 21);
+    s = getenv("RFB_ACCUM_TMA");
+    o.accum_tma = !(s && s[0] == '0');
+    o.loaded = 1;
+    g_options = o;
+}
+const rfb_options_t *rfb_options() {
+    if (!g_options.loaded) rfb_options_reload();
+    return &g_options;
+}
+
 extern "C" {
 
 int rfb_abi_version(void) { return RFB_ABI_VERSION; }
@@ -103,6 +120,14 @@ int rfb_ctx_create(int device, rfb_ctx_t **out) {
     RFB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->own_stream = true;
     RFB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    // d_scratch layout (64 KB): [0, 256) fold ticket | [256, 32768) per-CTA fold partials, 48 B each, grids of at most 4 CTAs per SM
+    // (k_fold.cu) | [32768, 40960) grouping scope / limit / census words (k_group.cu, k_fused_group.cu, k_hash_group.cu) |
+    // [40960, 65536) k_stats.cu partials + ticket + result.  The partials region bounds the SM count this build accepts.
+    if (256 + (size_t)prop.multiProcessorCount * 4 * 48 > 32768) {
+        rfb_set_error("device %d has %d SMs: the per-CTA partials of the fold kernels would overrun their scratch region", device, prop.multiProcessorCount);
+        free(ctx);
+        return RFB_ERR_CUDA;
+    }
     ctx->scratch_bytes = 1 << 16;
     RFB_CUDA(cudaMalloc(&ctx->d_scratch, ctx->scratch_bytes));
     RFB_CUDA(cudaMemset(ctx->d_scratch, 0, ctx->scratch_bytes));

@@ -924,7 +924,13 @@ obj_p rfb_index_group(obj_p keys, obj_p filter) {
     gids = to_host_vector(RFB_T_I64, len, dg);
     firsts = to_host_vector(RFB_T_I64, info.groups, dfi);
     res = G.host->vector(RFB_T_LIST, 7);
-    if (!res || res->type == RFB_T_ERR || gids->type == RFB_T_ERR || firsts->type == RFB_T_ERR) { res = G.host->err_limit(); goto out; }
+    if (!res || res->type == RFB_T_ERR || !gids || !firsts || gids->type == RFB_T_ERR || firsts->type == RFB_T_ERR) {
+        if (res && res->type != RFB_T_ERR) { res->len = 0; G.host->drop_obj(res); }
+        if (gids && gids->type != RFB_T_ERR) G.host->drop_obj(gids);
+        if (firsts && firsts->type != RFB_T_ERR) G.host->drop_obj(firsts);
+        res = G.host->err_limit();
+        goto out;
+    }
     RFB_OBJ_LIST(res)[0] = i64_atom(RFB_INDEX_IDS);
     RFB_OBJ_LIST(res)[1] = i64_atom(info.groups);
     RFB_OBJ_LIST(res)[2] = gids;
@@ -1079,6 +1085,7 @@ static obj_p aggr_op(int op, obj_p val, obj_p index) {
     if (!G.ready || !is_vec(val) || !index || index->type != RFB_T_LIST || index->len != 7) return NULL;
     obj_p *ix = RFB_OBJ_LIST(index);
     if (!ix[0] || ix[0]->type != -RFB_T_I64 || ix[0]->i64 != RFB_INDEX_IDS) return NULL; /* SHIFT / parted / window indices: CPU body */
+    if (!ix[1] || ix[1]->type != -RFB_T_I64) return NULL;
     obj_p gids = ix[2], filter = ix[5];
     if (!gids || gids->type != RFB_T_I64) return NULL;
     const int filtered = !is_null_obj(filter);
@@ -1208,7 +1215,13 @@ static obj_p join_index(int inner, obj_p lcols, obj_p rcols, int64_t len) {
         if (rc) { res = status_to_obj(rc); goto out; }
         obj_p lids = to_host_vector(RFB_T_I64, count, dids), rids = to_host_vector(RFB_T_I64, count, dbid);
         res = G.host->vector(RFB_T_LIST, 2);
-        if (!res || res->type == RFB_T_ERR || lids->type == RFB_T_ERR || rids->type == RFB_T_ERR) { res = G.host->err_limit(); goto out; }
+        if (!res || res->type == RFB_T_ERR || !lids || !rids || lids->type == RFB_T_ERR || rids->type == RFB_T_ERR) {
+            if (res && res->type != RFB_T_ERR) { res->len = 0; G.host->drop_obj(res); }
+            if (lids && lids->type != RFB_T_ERR) G.host->drop_obj(lids);
+            if (rids && rids->type != RFB_T_ERR) G.host->drop_obj(rids);
+            res = G.host->err_limit();
+            goto out;
+        }
         RFB_OBJ_LIST(res)[0] = lids;
         RFB_OBJ_LIST(res)[1] = rids;
     }

@@ -357,6 +357,7 @@ class _Ops:
 
     def aggr(self, op, vt, val, gids, groups, filt=None):
         """aggr_sum/min/max/count/avg -> (tensor[groups], result type)"""
+        self.lib.rfb_options_reload()      # tests / sweeps switch strategies through the environment between calls
         ot = self.lib.rfb_aggr_type(op, vt)
         if ot < 0:
             raise RfbError(ot, "aggr %d: unsupported value type %d" % (op, vt))
@@ -449,6 +450,7 @@ class _Ops:
 
     def group_sum_count(self, key_type, keys, val, max_groups, cmp_op=None, pred_type=None, pred=None, k=None):
         """fused select {s: (sum v) c: (count v) from t by k [where (cmp p k)]} -> (keys, sums, counts) tensors"""
+        self.lib.rfb_options_reload()      # tests / sweeps switch strategies through the environment between calls
         n = keys.shape[0]
         ok, osum, oc = (self._empty(max_groups, capi.I64) for _ in range(3))
         g = C.c_int64(0)

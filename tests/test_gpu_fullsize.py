@@ -63,7 +63,7 @@ def test_filter_sum_1e9_partition_identity_and_oracle_windows(ctx, oracle, big):
         assert got.min == int(oracle.fold(ob.MIN, ob.I64, sel)[0]) and got.max == int(oracle.fold(ob.MAX, ob.I64, sel)[0])
         acc_rows += got.rows
         acc_sum += got.sum
-    assert acc_rows > 0 and wrap(acc_sum) == wrap(acc_sum)
+    assert acc_rows > 0 and acc_sum != 0
 
 
 def test_host_layer_equals_device_layer_on_2e8_rows(ctx, big):
