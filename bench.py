@@ -239,12 +239,17 @@ def ncu_traffic_bytes(rows):
     return None, None
 
 
-def workload_config(args, world):
+MERGE_TEXT = {"peer": "one 32-thread kernel per step over NVLink peer mailboxes (rfb_fold_allreduce_peers: P2P stores + sequence flags, "
+                      "merged (nonnull, sum) written straight into mapped host memory); NCCL carries the group-by merges of configs 4-5",
+              "nccl": "one NCCL all-reduce of (nonnull, sum) per step + device-to-host copy"}
+
+
+def workload_config(args, world, merge_mode="nccl"):
     return {"workload": "select {s: (sum x) from: t where: (< x k)}: int64 column, x = splitmix64(42, row) mod 2^40, "
                         "k = 2^39 (50%% selectivity), %d rows per GPU sharded by row range" % args.rows,
             "rows_per_gpu": args.rows, "global_rows": args.rows * world, "selectivity": 0.5,
             "l2_policy": "inputs (8 GB per GPU) far exceed the 126 MB L2; no flush needed",
-            "merge": "none (1 GPU)" if world == 1 else "one NCCL all-reduce of (nonnull, sum) per step"}
+            "merge": "none (1 GPU)" if world == 1 else MERGE_TEXT.get(merge_mode, merge_mode)}
 
 
 
@@ -447,8 +452,33 @@ def run_gpu_arm(args):
     ctx.fill_splitmix(capi.I64, x, n, shifted_seed(SEED, rank * n), MODULUS)
     ctx.sync()
 
+    # N > 1: the final merge of the per-GPU (count, sum) partials.  Default: one 32-thread kernel over NVLink peer mailboxes
+    # (rfb_fold_allreduce_peers: P2P stores + sequence flags, merged result straight into mapped host memory).  --merge nccl,
+    # or a box without CUDA IPC, takes the NCCL all-reduce + device-to-host copy instead.
+    merge_mode = "none (1 GPU)"
+    if world > 1:
+        merge_mode = "nccl"
+        if args.merge == "peer":
+            try:
+                ctx.peer_mailbox_setup(rank, world)
+                merge_mode = "peer"
+            except Exception as e:                                 # noqa: BLE001
+                if rank == 0:
+                    print("peer mailboxes unavailable (%s): NCCL all-reduce" % e, file=sys.stderr)
+            flag = torch.tensor([1 if merge_mode == "peer" else 0], dtype=torch.int64, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)            # all ranks or none
+            merge_mode = "peer" if int(flag.item()) == 1 else "nccl"
+
     def step_resident(ev_s=None, ev_e=None):
         """one pass, column resident in HBM -> (rows, sum) on the host"""
+        if world > 1 and merge_mode == "peer":
+            if ev_s is not None:
+                ev_s.record(stream)
+            ctx.filter_fold_async(capi.LT, capi.I64, x, K_CONST, capi.F_SUM | capi.F_CNT, capi.I64, x, n)
+            if ev_e is not None:
+                ev_e.record(stream)
+            r = ctx.fold_allreduce_peers(capi.I64)
+            return r.nonnull, r.sum
         if world == 1:
             if ev_s is not None:
                 ev_s.record(stream)
@@ -562,7 +592,7 @@ def run_gpu_arm(args):
         traffic, traffic_src = (args.ncu_traffic, "--ncu-traffic") if args.ncu_traffic else ncu_traffic_bytes(n)
         line = {"metric": METRIC, "value": n * world * K / (total_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
                 "steps": K, "warmup": max(W, 3), "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": workload_config(args, world),
+                "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": workload_config(args, world, merge_mode),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_scan_fold<i64,i64,SUM|CNT,pred,same-column,null-free predicate>",
                              "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": 8 * n, "peak_source": peak_src},
@@ -590,6 +620,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--merge", choices=["peer", "nccl"], default="peer", help="N > 1: how the per-GPU (count, sum) partials are merged each step")
     ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 3-5 (fma->avg, group-by, sharded filter+group-by)")
     ap.add_argument("--config-steps", type=int, default=10, help="timed steps of each of the configs 3-5")
     ap.add_argument("--ncu-traffic", type=float, default=None,

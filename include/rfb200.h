@@ -331,6 +331,24 @@ int rfb_filter_fold_host(rfb_ctx_t *ctx, int cmp_op, int pred_type, const void *
                          int64_t *h2d_bytes);
 int rfb_fold_host(rfb_ctx_t *ctx, int folds, int type, const void *x, int64_t n, int64_t chunk_rows, rfb_fold_t *out,
                   int64_t *h2d_bytes);
+/* ------------------------------------------------------------------ one process per GPU: the final merge over NVLink peer memory
+ *
+ * the only exchange of the path is the final merge of the per-GPU partial aggregates.  For ungrouped folds that is a
+ * 72-byte record per GPU; an NCCL all-reduce + device-to-host copy + host synchronisation costs more than the merge is worth
+ * (~80 us next to a 1.1 ms scan).  Instead every rank owns a small mailbox in its HBM, exported to the peers with CUDA IPC:
+ *     rfb_peer_mailbox_create(ctx, handle)         allocate it, return its 64-byte IPC handle (exchange the handles of all ranks
+ *                                                  by any means: torch.distributed all_gather, MPI, a file)
+ *     rfb_peer_mailbox_bind(ctx, rank, world, h)   h = world x 64 bytes, the handles in rank order: maps every peer's mailbox
+ *     rfb_fold_allreduce_peers(ctx, type, out)     after an asynchronous fold launch (out == NULL form of rfb_fold_dev /
+ *                                                  rfb_filter_fold_dev / ...) on this context: ONE 32-thread kernel pushes this
+ *                                                  rank's partial into every peer's mailbox (P2P stores over NVLink + a sequence
+ *                                                  flag), waits for the peers' partials, folds them in rank order and reports
+ *                                                  the merged rfb_fold_t where a single-GPU fold reports.  Every rank must call
+ *                                                  it the same number of times.  Bit-identical on all ranks. */
+int rfb_peer_mailbox_create(rfb_ctx_t *ctx, void *ipc_handle_64);
+int rfb_peer_mailbox_bind(rfb_ctx_t *ctx, int rank, int world, const void *handles);
+int rfb_fold_allreduce_peers(rfb_ctx_t *ctx, int val_type, rfb_fold_t *out);
+
 /* The fused multi-column queries over HOST columns (configs 3-5 end to end): the columns are shipped whole, then
  * rfb_group_sum_count_dev / rfb_fma_fold_dev run; group lists come back into HOST arrays of max_groups entries. */
 int rfb_group_sum_count_host(rfb_ctx_t *ctx, int key_type, const void *keys, const int64_t *val, int64_t n, int cmp_op, int pred_type,

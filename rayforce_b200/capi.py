@@ -138,6 +138,9 @@ SIGNATURES = {
     "rfb_group_sum_count_host": (_ci, [_vp, _ci, _vp, _vp, _i64, _ci, _ci, _vp, _P(Scalar), _i64, _vp, _vp, _vp, _P(_i64), _P(_i64)]),
     "rfb_fma_fold_host": (_ci, [_vp, _ci, _vp, _vp, _vp, _i64, _P(Fold), _P(_i64)]),
     "rfb_options_reload": (None, []),
+    "rfb_peer_mailbox_create": (_ci, [_vp, _vp]),
+    "rfb_peer_mailbox_bind": (_ci, [_vp, _ci, _ci, _vp]),
+    "rfb_fold_allreduce_peers": (_ci, [_vp, _ci, _P(Fold)]),
     "rfb_mgpu_create": (_ci, [_ci, _P(_vp)]),
     "rfb_mgpu_destroy": (None, [_vp]),
     "rfb_mgpu_devices": (_ci, [_vp]),

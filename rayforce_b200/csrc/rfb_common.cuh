@@ -58,6 +58,11 @@ struct rfb_ctx {
     int ring_next;
     void *copy_pool;
     cudaEvent_t ev_copy[RFB_STAGE_BUFS], ev_kernel[RFB_STAGE_BUFS];
+    // peer mailboxes (k_peer.cu): the one-shot all-reduce of fold results over NVLink P2P stores
+    void *mbox;                // own mailbox (device memory, exported to the peers through CUDA IPC)
+    void *mbox_peer[16];       // every rank's mailbox as mapped into this process ([rank] = own)
+    int mbox_rank, mbox_world;
+    unsigned long long mbox_seq;
 };
 
 void rfb_set_error(const char *fmt, ...);
@@ -70,6 +75,7 @@ int rfb_ensure_aux2(rfb_ctx_t *ctx, size_t bytes, void **out);
 int rfb_copy_h2d(rfb_ctx_t *ctx, void *dst_dev, const void *src_host, size_t bytes, cudaStream_t stream);
 int rfb_copy_d2h(rfb_ctx_t *ctx, void *dst_host, const void *src_dev, size_t bytes, cudaStream_t stream);
 void rfb_copy_shutdown(rfb_ctx_t *ctx);
+void rfb_peer_mailbox_release(rfb_ctx_t *ctx);   // k_peer.cu
 // launch-only entry points of k_fold.cu: the result lands in h_result[result_slot] once the stream drains
 int rfb_fold_launch(rfb_ctx_t *ctx, int folds, int type, const void *x, i64 n);
 int rfb_filter_fold_launch(rfb_ctx_t *ctx, int cmp_op, int pred_type, const void *pred, const rfb_scalar_t *k, int folds,

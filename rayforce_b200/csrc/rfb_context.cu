@@ -155,6 +155,7 @@ void rfb_ctx_destroy(rfb_ctx_t *ctx) {
         cudaEventDestroy(ctx->ev_kernel[i]);
     }
     rfb_copy_shutdown(ctx);
+    rfb_peer_mailbox_release(ctx);
     if (ctx->d_work) cudaFree(ctx->d_work);
     if (ctx->d_aux) cudaFree(ctx->d_aux);
     if (ctx->d_aux2) cudaFree(ctx->d_aux2);

@@ -150,6 +150,23 @@ class Context:
         check(self.lib.rfb_fold_result(self.h, C.byref(f)))
         return FoldResult(f, type_)
 
+    def peer_mailbox_setup(self, rank: int, world: int, group=None) -> None:
+        """one process per GPU: create this rank's mailbox, exchange the CUDA IPC handles over torch.distributed, map the peers'"""
+        import torch.distributed as dist
+        h = (C.c_char * 64)()
+        check(self.lib.rfb_peer_mailbox_create(self.h, h))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h.raw), group=group)
+        blob = b"".join(handles)
+        check(self.lib.rfb_peer_mailbox_bind(self.h, rank, world, C.c_char_p(blob)))
+        dist.barrier(group=group)                      # every mailbox is mapped everywhere before the first exchange
+
+    def fold_allreduce_peers(self, type_: int) -> FoldResult:
+        """after an *_async fold launch: the merged result of all ranks (one tiny kernel over NVLink peer memory)"""
+        f = Fold()
+        check(self.lib.rfb_fold_allreduce_peers(self.h, type_, C.byref(f)))
+        return FoldResult(f, type_)
+
     def multi_filter_fold(self, preds, conjunction: bool, folds: int, val_type: int, val, n: int) -> FoldResult:
         """preds: [(cmp_op, type, column tensor, constant), ...] combined with and (True) / or (False)"""
         arr = (capi.Pred * len(preds))()

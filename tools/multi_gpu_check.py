@@ -52,12 +52,26 @@ def main():
         # --- filter + fold, merged with one all-reduce
         r = ctx.filter_fold(capi.LT, capi.I64, x, K, capi.F_ALL, capi.I64, x, n)
         merged = shard.allreduce_fold_i64(r.rows, r.nonnull, r.sum, r.min, r.max, dev)
+        # --- the same merge as ONE tiny kernel over NVLink peer mailboxes (rfb_fold_allreduce_peers), three times in a row
+        peer_ok = True
+        try:
+            ctx.peer_mailbox_setup(rank, world)
+            for _ in range(3):
+                ctx.filter_fold_async(capi.LT, capi.I64, x, K, capi.F_ALL, capi.I64, x, n)
+                pr = ctx.fold_allreduce_peers(capi.I64)
+                peer_ok &= (pr.rows, pr.nonnull, pr.sum, pr.min, pr.max) == tuple(merged)
+        except Exception as e:                                   # CUDA IPC not available in this sandbox: reported, not fatal
+            peer_ok = None
+            peer_err = str(e)
         # --- filter + group-by + sum/count, merged with one all-gather-v and a re-group on every rank
         lk, ls, lc = ctx.group_sum_count(capi.I64, k, v, 100_000, capi.LT, capi.I64, v, KV)
         mk, ms, mc = shard.merge_group_partials(lk, ls, lc, shard.gpu_regroup(ctx))
         torch.cuda.synchronize()
     ok = True
-    report = {"world": world, "rows_per_gpu": n, "merged_fold": list(merged), "groups": int(mk.shape[0])}
+    report = {"world": world, "rows_per_gpu": n, "merged_fold": list(merged), "groups": int(mk.shape[0]), "peer_mailbox_allreduce_equal": peer_ok}
+    if peer_ok is None:
+        report["peer_mailbox_error"] = peer_err
+    ok &= peer_ok is not False
     # every rank must hold the same merged result
     sig = torch.tensor([merged[2], int(ms.sum().item()), int(mc.sum().item()), int(mk[:100].sum().item())], dtype=torch.int64, device=dev)
     sigs = [torch.empty_like(sig) for _ in range(world)]
