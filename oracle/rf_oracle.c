@@ -933,7 +933,33 @@ int64_t rfo_distinct_i64(const int64_t *keys, int64_t n, int64_t *out) {
     i64 mn = keys[0], mx = keys[0];
     for (i64 i = 1; i < n; i++) { if (keys[i] < mn) mn = keys[i]; if (keys[i] > mx) mx = keys[i]; }
     i64 range = (i64)((u64)mx - (u64)mn + 1);
-    if (range <= 0 || !(range <= n || range <= (1 << 20))) return -1;
+    if (range <= 0 || !(range <= n || range <= (1 << 20))) {
+        /* hash branch (core/index.c:579-603): an open-addressing table of next_prime(ceil(n / 0.75)) slots (core/hash.c:35-55,
+         * ops_next_prime core/ops.c:66-88), slot = key % size with linear probing (ht_oa_tab_next, core/hash.c:129-148), rows
+         * inserted in row order, nulls skipped; the result is the table read in SLOT order.  The start slot is a signed C
+         * remainder: negative keys index before the table in the reference (Q17) — not restated: -2. */
+        i64 size = (i64)ceil((f64)n / 0.75);
+        for (;; size++) {
+            int prime = size > 1;
+            if (size > 3 && (size % 2 == 0 || size % 3 == 0)) prime = 0;
+            for (i64 d = 5; prime && d * d <= size; d += 6) if (size % d == 0 || size % (d + 2) == 0) prime = 0;
+            if (prime) break;
+        }
+        i64 *tab = (i64 *)malloc((size_t)size * 8);
+        for (i64 s = 0; s < size; s++) tab[s] = RFO_NULL_I64;
+        for (i64 i = 0; i < n; i++) {
+            i64 k = keys[i];
+            if (k == RFO_NULL_I64) continue;
+            if (k < 0) { free(tab); return -2; }
+            i64 s = k % size;
+            while (tab[s] != RFO_NULL_I64 && tab[s] != k) s = (s + 1) % size;
+            tab[s] = k;
+        }
+        i64 j = 0;
+        for (i64 s = 0; s < size; s++) if (tab[s] != RFO_NULL_I64) out[j++] = tab[s];
+        free(tab);
+        return j;
+    }
     u8 *mark = (u8 *)calloc((size_t)range, 1);
     for (i64 i = 0; i < n; i++) mark[keys[i] - mn] = 1;
     i64 j = 0;

@@ -1297,8 +1297,77 @@ out:
     return res;
 }
 
+/* ray_distinct, hash branch (core/index.c:579-603).  The reference inserts the rows in row order into an open-addressing table of
+ * next_prime(ceil(len / 0.75)) slots (slot = key % size, linear probing, core/hash.c:35-55, :129-148) and returns the table in SLOT
+ * order.  The device finds the distinct keys in first-occurrence order (the sparse grouping path); which slot each of them ends up
+ * in only depends on that order, so the host replays the insertions of the DISTINCT keys (not of the rows) over a sparse image of
+ * the table and orders the keys by slot.  Negative keys (the reference indexes before its table for them) and nulls (skipped
+ * there, after a scope pass that wraps) stay on the CPU body. */
+typedef struct { int64_t slot, key; } slot_key_t;
+static int cmp_slot_key(const void *a, const void *b) {
+    const int64_t x = ((const slot_key_t *)a)->slot, y = ((const slot_key_t *)b)->slot;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+static int is_prime_i64(int64_t x) {   /* ops_is_prime, core/ops.c:66-81 */
+    if (x <= 1) return 0;
+    if (x <= 3) return 1;
+    if (x % 2 == 0 || x % 3 == 0) return 0;
+    for (int64_t i = 5; i * i <= x; i += 6)
+        if (x % i == 0 || x % (i + 2) == 0) return 0;
+    return 1;
+}
+static obj_p distinct_sparse(obj_p x, void *dx) {
+    const int64_t n = x->len;
+    obj_p res = NULL;
+    rfb_group_info_t info;
+    int64_t *hk = NULL, *occ = NULL;
+    slot_key_t *sk = NULL;
+    void *dg = dev_temp((size_t)n * 8), *dfi = dev_temp((size_t)n * 8);
+    if (!dg || !dfi) return G.host->err_limit();
+    int rc = rfb_group_i64_dev(G.ctx, (const int64_t *)dx, NULL, n, (int64_t *)dg, (int64_t *)dfi, &info);
+    if (rc) return status_to_obj(rc);
+    const int64_t g = info.groups;
+    if (g > n / 2 + 1024) return NULL;                 /* nearly all rows distinct: the replay is the reference's own work */
+    void *dk = dev_temp((size_t)(g > 0 ? g : 1) * 8);
+    if (!dk) return G.host->err_limit();
+    rc = rfb_gather_dev(G.ctx, RFB_T_I64, dx, (const int64_t *)dfi, g, dk);
+    if (rc) return status_to_obj(rc);
+    hk = (int64_t *)malloc((size_t)(g > 0 ? g : 1) * 8);
+    if (!hk || rfb_d2h(G.ctx, hk, dk, (size_t)g * 8) != RFB_OK || rfb_sync(G.ctx) != RFB_OK) { res = G.host->err_limit(); goto done; }
+    for (int64_t i = 0; i < g; i++)
+        if (hk[i] < 0) { res = NULL; goto done; }      /* negative or null keys: CPU body */
+    int64_t size = (int64_t)ceil((double)n / 0.75);
+    while (!is_prime_i64(size)) size++;
+    /* sparse image of the table: an open-addressing set of the occupied slot numbers */
+    int64_t cap = 16;
+    while (cap < 4 * g) cap <<= 1;
+    occ = (int64_t *)malloc((size_t)cap * 8);
+    sk = (slot_key_t *)malloc((size_t)(g > 0 ? g : 1) * sizeof(slot_key_t));
+    if (!occ || !sk) { res = G.host->err_limit(); goto done; }
+    for (int64_t i = 0; i < cap; i++) occ[i] = -1;
+    for (int64_t i = 0; i < g; i++) {
+        int64_t s = hk[i] % size;
+        for (;;) {                                     /* first free slot at or after s (distinct keys never match an occupant) */
+            uint64_t h = ((uint64_t)s * 0x9E3779B97F4A7C15ULL) >> 20 & (uint64_t)(cap - 1);
+            while (occ[h] != -1 && occ[h] != s) h = (h + 1) & (uint64_t)(cap - 1);
+            if (occ[h] == -1) { occ[h] = s; break; }
+            s = (s + 1) % size;
+        }
+        sk[i].slot = s;
+        sk[i].key = hk[i];
+    }
+    qsort(sk, (size_t)g, sizeof(slot_key_t), cmp_slot_key);
+    res = G.host->vector((int8_t)x->type, g);
+    if (!res || res->type == RFB_T_ERR) { res = res ? res : G.host->err_limit(); goto done; }
+    for (int64_t i = 0; i < g; i++) ((int64_t *)RFB_OBJ_PAYLOAD(res))[i] = sk[i].key;
+    res->attrs |= 1;   /* ATTR_DISTINCT */
+done:
+    free(hk); free(occ); free(sk);
+    return res;
+}
+
 /* ray_distinct on an I64-kind vector with a dense key range (core/compose.c:867-872 -> index_distinct_i64): ascending distinct
- * keys, ATTR_DISTINCT set on the result.  A sparse range (hash branch, slot-order result) is declined to the CPU body. */
+ * keys, ATTR_DISTINCT set on the result.  A sparse range takes distinct_sparse above (the reference's hash branch, slot order). */
 obj_p rfb_ray_distinct(obj_p x) {
     if (!G.ready || !is_key_vec(x) || too_small(x->len) || x->len == 0) return NULL;
     call_scope_t sc = enter();
@@ -1307,7 +1376,7 @@ obj_p rfb_ray_distinct(obj_p x) {
     void *dx = dev_column(x), *dout = dev_temp((size_t)x->len * 8);
     if (!dx || !dout) { res = G.host->err_limit(); goto out; }
     int rc = rfb_distinct_i64_dev(G.ctx, (const int64_t *)dx, x->len, (int64_t *)dout, &count);
-    if (rc == RFB_ERR_ARG) { res = NULL; goto out; }
+    if (rc == RFB_ERR_ARG) { res = distinct_sparse(x, dx); goto out; }
     if (rc) { res = status_to_obj(rc); goto out; }
     res = to_host_vector(x->type, count, dout);
     if (res && res->type != RFB_T_ERR) res->attrs |= 1;   /* ATTR_DISTINCT (core/ops.h:52) */

@@ -472,3 +472,24 @@ def test_aggr_first_last_and_multi_key_index(ops, oracle, filtered):
     ops.drop(keys, vo)
     if filtered:
         ops.drop(fo)
+
+
+@pytest.mark.parametrize("n,card", [(1000, 37), (30_000, 5000), (400_003, 60_000)])
+def test_distinct_sparse_range_keeps_the_reference_slot_order(ops, oracle, n, card):
+    """ray_distinct's hash branch (core/index.c:579-603): the distinct keys in the SLOT order of the reference's open-addressing
+    table (next_prime(ceil(len / 0.75)) slots, key % size, linear probing, rows inserted in row order)"""
+    r = np.random.default_rng(n + card)
+    pool = r.integers(0, 1 << 62, card).astype(np.int64)
+    keys = pool[r.integers(0, card, n)]
+    keys[0], keys[-1] = 0, (1 << 62) + 12345
+    ko = ops.vec(ob.I64, keys)
+    res = ops.call("ray_distinct", ko)
+    assert ops.attrs_of(res) & 1
+    got, gt = ops.value(res)
+    assert gt == ob.I64 and np.array_equal(got, oracle.distinct(keys))
+    neg = keys.copy()
+    neg[5] = -7                                                                  # negative keys: the CPU body's (out-of-table) business
+    no = ops.vec(ob.I64, neg)
+    with pytest.raises(Declined):
+        ops.value(ops.call("ray_distinct", no))
+    ops.drop(ko, no)

@@ -494,6 +494,20 @@ def test_asof_join_index(oracle, reference, ncols, tt, nb, np_):
     assert (want != ob.NULL_I64).any() and (want == ob.NULL_I64).any()
 
 
+@pytest.mark.parametrize("n,card", [(5, 5), (6, 4), (100, 37), (1000, 900), (30_000, 5000), (200_003, 150_000)])
+def test_distinct_sparse_hash_branch(oracle, reference, n, card):
+    """ray_distinct -> index_distinct_i64, hash branch (core/index.c:579-603): range > len and > 2^20 -> an open-addressing table of
+    next_prime(ceil(len / 0.75)) slots, rows inserted in row order, the result is the table in SLOT order (non-negative keys)"""
+    r = np.random.default_rng(n + card)
+    pool = r.integers(0, 1 << 62, card).astype(np.int64)
+    keys = pool[r.integers(0, card, n)]
+    keys[0], keys[-1] = 0, (1 << 62) + 12345                       # force a huge range
+    v = reference.vec(ob.I64, keys)
+    got = reference.to_numpy(reference.call1("ray_distinct", v))[0]
+    reference.drop(v)
+    assert np.array_equal(oracle.distinct(keys), got)
+
+
 @pytest.mark.parametrize("n,card,kmin", [(1, 1, 5), (1000, 40, -20), (200_003, 5000, -2500), (50_000, 900_000, 17)])
 def test_distinct_dense(oracle, reference, n, card, kmin):
     """ray_distinct -> index_distinct_i64, direct-addressing branch (core/index.c:551-577): ascending distinct keys"""
