@@ -315,6 +315,11 @@ int rfb_window_join_dev(rfb_ctx_t *ctx, int ncols, const int64_t *const *right_c
                         const int64_t *const *left_cols, int64_t left_len, const int32_t *win_lo, const int32_t *win_hi, int jtype,
                         int op, int val_type, const void *val, void *out);
 
+/* The aggregate alone, for an index that already holds every left row's block [first[i], last[i]] of the sorted right table
+ * (first[i] == NULL_I64: the key has no block): what aggr_* receive from the reference's own index_window_join_obj. */
+int rfb_window_aggr_dev(rfb_ctx_t *ctx, const int32_t *right_time, const int64_t *first, const int64_t *last, int64_t left_len,
+                        const int32_t *win_lo, const int32_t *win_hi, int jtype, int op, int val_type, const void *val, void *out);
+
 /* ------------------------------------------------------------------ device layer: sort */
 
 /* ray_sort_asc / ray_sort_desc (core/sort.c:430-479, 691-740): stable permutation (I64 row ids).

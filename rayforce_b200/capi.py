@@ -137,6 +137,7 @@ SIGNATURES = {
     "rfb_aggr_last_dev": (_ci, [_vp, _ci, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "rfb_group_sum_count_host": (_ci, [_vp, _ci, _vp, _vp, _i64, _ci, _ci, _vp, _P(Scalar), _i64, _vp, _vp, _vp, _P(_i64), _P(_i64)]),
     "rfb_fma_fold_host": (_ci, [_vp, _ci, _vp, _vp, _vp, _i64, _P(Fold), _P(_i64)]),
+    "rfb_window_aggr_dev": (_ci, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _ci, _ci, _ci, _vp, _vp]),
     "rfb_options_reload": (None, []),
     "rfb_peer_mailbox_create": (_ci, [_vp, _vp]),
     "rfb_peer_mailbox_bind": (_ci, [_vp, _ci, _ci, _vp]),

@@ -238,18 +238,22 @@ __device__ __forceinline__ i64 bin_l(i32 val, const i32 *__restrict__ t, i64 off
 
 template <int OP, typename V>
 __global__ void __launch_bounds__(THREADS, 4)
-k_window_fold(KeyCols right, i64 rl, const i32 *__restrict__ rtime, const V *__restrict__ val, const i64 *__restrict__ first, const i32 *__restrict__ wlo,
-              const i32 *__restrict__ whi, i64 ll, int jtype, void *out) {
+k_window_fold(KeyCols right, i64 rl, const i32 *__restrict__ rtime, const V *__restrict__ val, const i64 *__restrict__ first, const i64 *__restrict__ last,
+              const i32 *__restrict__ wlo, const i32 *__restrict__ whi, i64 ll, int jtype, void *out) {
     for (i64 i = (i64)blockIdx.x * THREADS + threadIdx.x; i < ll; i += (i64)gridDim.x * THREADS) {
         const i64 f = ld_stream(first + i);
         bool none = f == NULL_I64;
         i64 li = 0, ri = -1;
         if (!none) {
-            // last row of the key's block: gallop, then binary search, on "same key tuple as row f"
-            i64 lo = f, step = 1;
-            while (lo + step < rl && same_tuple(right, f, right, lo + step)) { lo += step; step <<= 1; }
-            i64 hi = lo + step < rl ? lo + step : rl;          // row lo is in the block, row hi (if < rl) is not
-            while (lo + 1 < hi) { const i64 mid = lo + (hi - lo) / 2; if (same_tuple(right, f, right, mid)) lo = mid; else hi = mid; }
+            i64 lo = f;
+            if (last) lo = ld_stream(last + i);                // the reference's index carries the block's last row
+            else {
+                // last row of the key's block: gallop, then binary search, on "same key tuple as row f"
+                i64 step = 1;
+                while (lo + step < rl && same_tuple(right, f, right, lo + step)) { lo += step; step <<= 1; }
+                i64 hi = lo + step < rl ? lo + step : rl;      // row lo is in the block, row hi (if < rl) is not
+                while (lo + 1 < hi) { const i64 mid = lo + (hi - lo) / 2; if (same_tuple(right, f, right, mid)) lo = mid; else hi = mid; }
+            }
             const i64 n = lo - f + 1;
             const i32 a = ld_stream(wlo + i), b = ld_stream(whi + i);
             li = jtype == 0 ? bin_r(a, rtime, f, n) : bin_l(a, rtime, f, n);
@@ -295,15 +299,15 @@ k_window_fold(KeyCols right, i64 rl, const i32 *__restrict__ rtime, const V *__r
 }
 
 template <typename V>
-int window_launch(rfb_ctx_t *ctx, int op, KeyCols r, i64 rl, const i32 *rtime, const void *val, const i64 *first, const i32 *wlo, const i32 *whi, i64 ll,
-                  int jtype, void *out) {
+int window_launch(rfb_ctx_t *ctx, int op, KeyCols r, i64 rl, const i32 *rtime, const void *val, const i64 *first, const i64 *last, const i32 *wlo,
+                  const i32 *whi, i64 ll, int jtype, void *out) {
     const int grid = rfb_grid_for(ctx, ll, THREADS, 4);
     switch (op) {
-        case RFB_A_SUM: k_window_fold<W_SUM, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, wlo, whi, ll, jtype, out); break;
-        case RFB_A_MIN: k_window_fold<W_MIN, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, wlo, whi, ll, jtype, out); break;
-        case RFB_A_MAX: k_window_fold<W_MAX, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, wlo, whi, ll, jtype, out); break;
-        case RFB_A_AVG: k_window_fold<W_AVG, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, wlo, whi, ll, jtype, out); break;
-        default: k_window_fold<W_COUNT, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, wlo, whi, ll, jtype, out); break;
+        case RFB_A_SUM: k_window_fold<W_SUM, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, last, wlo, whi, ll, jtype, out); break;
+        case RFB_A_MIN: k_window_fold<W_MIN, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, last, wlo, whi, ll, jtype, out); break;
+        case RFB_A_MAX: k_window_fold<W_MAX, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, last, wlo, whi, ll, jtype, out); break;
+        case RFB_A_AVG: k_window_fold<W_AVG, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, last, wlo, whi, ll, jtype, out); break;
+        default: k_window_fold<W_COUNT, V><<<grid, THREADS, 0, ctx->stream>>>(r, rl, rtime, (const V *)val, first, last, wlo, whi, ll, jtype, out); break;
     }
     RFB_CHECK_LAUNCH(ctx);
     return RFB_OK;
@@ -330,6 +334,23 @@ extern "C" int rfb_window_join_dev(rfb_ctx_t *ctx, int ncols, const int64_t *con
     KeyCols r;
     r.ncols = ncols;
     for (int c = 0; c < ncols; c++) r.col[c] = right_cols[c];
-    if (vk == K_F64) return window_launch<f64>(ctx, op, r, right_len, right_time, val, first, win_lo, win_hi, left_len, jtype, out);
-    return window_launch<i64>(ctx, op, r, right_len, right_time, val, first, win_lo, win_hi, left_len, jtype, out);
+    if (vk == K_F64) return window_launch<f64>(ctx, op, r, right_len, right_time, val, first, nullptr, win_lo, win_hi, left_len, jtype, out);
+    return window_launch<i64>(ctx, op, r, right_len, right_time, val, first, nullptr, win_lo, win_hi, left_len, jtype, out);
+}
+
+// the aggregate alone, over an index that already holds every left row's block [first, last] (NULL_I64 = no block): what aggr_*
+// receive from the reference's index_window_join_obj (core/index.c:3287-3346, AGGR_ITER's WINDOW branch core/aggr.c:131-160)
+extern "C" int rfb_window_aggr_dev(rfb_ctx_t *ctx, const int32_t *right_time, const int64_t *first, const int64_t *last, int64_t left_len,
+                                   const int32_t *win_lo, const int32_t *win_hi, int jtype, int op, int val_type, const void *val, void *out) {
+    RFB_ARG(ctx && left_len >= 0 && (jtype == 0 || jtype == 1) && ((first && last && win_lo && win_hi && out && right_time && val) || left_len == 0), "rfb_window_aggr_dev");
+    const int vk = rfb_kind_of(val_type);
+    if (!(vk == K_I64 || vk == K_F64) || val_type == RFB_SYMBOL || !(op == RFB_A_SUM || op == RFB_A_MIN || op == RFB_A_MAX || op == RFB_A_COUNT || op == RFB_A_AVG)) {
+        rfb_set_error("window aggregate %d over value type %d (sum / min / max / count / avg of I64-kind or F64 values)", op, val_type);
+        return RFB_ERR_TYPE;
+    }
+    if (left_len == 0) return RFB_OK;
+    KeyCols r;
+    r.ncols = 0;
+    if (vk == K_F64) return window_launch<f64>(ctx, op, r, 0, right_time, val, first, last, win_lo, win_hi, left_len, jtype, out);
+    return window_launch<i64>(ctx, op, r, 0, right_time, val, first, last, win_lo, win_hi, left_len, jtype, out);
 }

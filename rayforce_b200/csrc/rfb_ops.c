@@ -1076,6 +1076,51 @@ out:
     return res;
 }
 
+/* aggr_* over the WINDOW index of a window join (index_window_join_obj, core/index.c:3287-3346: [WINDOW, left rows, left time,
+ * right time, [window lo, window hi], LIST of one [first, last] vector per left row or null, jtype]): AGGR_ITER's WINDOW branch
+ * (core/aggr.c:131-160) on the device.  The per-row block bounds are flattened into two arrays on the host (the index keeps
+ * them as one small object per row), everything else is column payloads. */
+#define RFB_INDEX_WINDOW 3
+static obj_p window_aggr(int op, obj_p val, obj_p index) {
+    if (!(op == RFB_A_SUM || op == RFB_A_MIN || op == RFB_A_MAX || op == RFB_A_COUNT || op == RFB_A_AVG)) return NULL;
+    obj_p *ix = RFB_OBJ_LIST(index);
+    if (!ix[1] || ix[1]->type != -RFB_T_I64 || !ix[3] || !ix[4] || !ix[5] || !ix[6] || ix[6]->type != -RFB_T_I64) return NULL;
+    obj_p rtime = ix[3], win = ix[4], blocks = ix[5];
+    const int64_t ll = ix[1]->i64, jtype = ix[6]->i64;
+    if (rtime->type <= 0 || type_size(rtime->type) != 4 || win->type != RFB_T_LIST || win->len != 2 || blocks->type != RFB_T_LIST || blocks->len != ll) return NULL;
+    obj_p wlo = RFB_OBJ_LIST(win)[0], whi = RFB_OBJ_LIST(win)[1];
+    if (!wlo || !whi || wlo->type <= 0 || whi->type <= 0 || type_size(wlo->type) != 4 || type_size(whi->type) != 4 || wlo->len != ll || whi->len != ll) return NULL;
+    if (!(jtype == 0 || jtype == 1) || !is_vec(val) || val->len != rtime->len) return NULL;
+    const int vt = val->type;
+    if (!(vt == RFB_T_I64 || vt == RFB_T_TIMESTAMP || vt == RFB_T_F64)) return NULL;   /* other value types: CPU body */
+    const int ot = rfb_aggr_type(op, vt);
+    if (ot < 0) return G.host->err_type();
+    if (too_small(ll) || ll == 0) return NULL;
+    int64_t *fl = (int64_t *)malloc((size_t)ll * 16);
+    if (!fl) return G.host->err_limit();
+    for (int64_t i = 0; i < ll; i++) {
+        obj_p b = RFB_OBJ_LIST(blocks)[i];
+        if (is_null_obj(b)) { fl[i] = RFB_NULL_I64; fl[ll + i] = RFB_NULL_I64; continue; }
+        if (b->type != RFB_T_I64 || b->len != 2) { free(fl); return NULL; }
+        fl[i] = ((const int64_t *)RFB_OBJ_PAYLOAD(b))[0];
+        fl[ll + i] = ((const int64_t *)RFB_OBJ_PAYLOAD(b))[1];
+    }
+    call_scope_t sc = enter();
+    obj_p res;
+    void *dv = dev_column(val), *dt = dev_column(rtime), *dlo = dev_column(wlo), *dhi = dev_column(whi);
+    void *dfl = dev_temp((size_t)ll * 16), *dout = dev_temp((size_t)ll * 8);
+    if (!dv || !dt || !dlo || !dhi || !dfl || !dout || rfb_h2d(G.ctx, dfl, fl, (size_t)ll * 16) != RFB_OK) { res = G.host->err_limit(); goto out; }
+    int rc = rfb_window_aggr_dev(G.ctx, (const int32_t *)dt, (const int64_t *)dfl, (const int64_t *)dfl + ll, ll, (const int32_t *)dlo, (const int32_t *)dhi,
+                                 (int)jtype, op, vt, dv, dout);
+    if (!rc) rc = rfb_sync(G.ctx);                     /* fl is read by an asynchronous copy */
+    if (rc) { res = status_to_obj(rc); goto out; }
+    res = to_host_vector(ot, ll, dout);
+out:
+    leave(sc);
+    free(fl);
+    return res;
+}
+
 static obj_p aggr_op(int op, obj_p val, obj_p index) {
     if (G.ready && val && index && index->type == RFB_T_LIST && index->len == 7 && val->type > RFB_T_PARTED && val->type <= RFB_T_PARTED + RFB_T_F64) {
         obj_p *px = RFB_OBJ_LIST(index);
@@ -1084,7 +1129,8 @@ static obj_p aggr_op(int op, obj_p val, obj_p index) {
     }
     if (!G.ready || !is_vec(val) || !index || index->type != RFB_T_LIST || index->len != 7) return NULL;
     obj_p *ix = RFB_OBJ_LIST(index);
-    if (!ix[0] || ix[0]->type != -RFB_T_I64 || ix[0]->i64 != RFB_INDEX_IDS) return NULL; /* SHIFT / parted / window indices: CPU body */
+    if (ix[0] && ix[0]->type == -RFB_T_I64 && ix[0]->i64 == RFB_INDEX_WINDOW) return window_aggr(op, val, index);
+    if (!ix[0] || ix[0]->type != -RFB_T_I64 || ix[0]->i64 != RFB_INDEX_IDS) return NULL; /* SHIFT / parted indices: CPU body */
     if (!ix[1] || ix[1]->type != -RFB_T_I64) return NULL;
     obj_p gids = ix[2], filter = ix[5];
     if (!gids || gids->type != RFB_T_I64) return NULL;
