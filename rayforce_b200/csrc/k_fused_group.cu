@@ -691,6 +691,8 @@ template <typename FS> struct MsIn {   // one input stage
 // that waits on the memory system — the TMA issue, the global reservations of the tile's runs (one atomic per partition), the
 // block-table lookups and the output descriptors.  The write-out of tile i is delayed until after tile i+1's ranking, so the
 // control warp's two dependent L2 round trips overlap a whole tile of data-warp work instead of stalling a barrier.
+// The data warps and the control warp meet at two barriers per tile.  Both roles reach the SAME two __syncthreads() instructions
+// (the role-specific work sits between them): compute-sanitizer synccheck rejects barriers taken from different code paths.
 template <typename FS, typename REC, int KPL>
 __global__ void __launch_bounds__(MS_T + 32, MS_CTAS)
 k_ms_scatter(FS fs, const i64 *__restrict__ val, i64 tiles, RecStore rs, i64 *mm) {
@@ -750,11 +752,81 @@ k_ms_scatter(FS fs, const i64 *__restrict__ val, i64 tiles, RecStore rs, i64 *mm
     if (ctrl && lane == 0 && (i64)blockIdx.x < tiles) issue(blockIdx.x, 0);
     int buf = 0;
     u32 it = 0;
+    // data warps, first half of a tile: wait for the staged input, rank the thread's MS_R rows among the rows of their partition
+    // inside the warp, reserve the warp's runs in the tile's staging area (wbase), send misfits to the side list
+    auto rank_tile = [&](REC (&rec)[MS_R], u32 (&pp)[MS_R], u32 &wbase) {
+        mbar_wait(&full[buf], (it >> 1) & 1u);
+        const unsigned char *in = s_in + (size_t)buf * in_bytes;
+        const KT *const sk = (const KT *)in;
+        const i64 *const sv = (const i64 *)(in + In::KEY_BYTES);
+        // rows of this thread: pairs (j2 * MS_T + tid) of the tile: conflict-free 8 / 16-byte shared-memory reads
+        KT k[MS_R];
+        i64 v[MS_R];
+        bool sel[MS_R];
+#pragma unroll
+        for (int j2 = 0; j2 < MS_R / 2; j2++) {
+            const int pair = j2 * MS_T + tid;
+            if constexpr (sizeof(KT) == 4) {
+                const uint2 w = *(const uint2 *)(sk + 2 * pair);
+                k[2 * j2] = (KT)w.x; k[2 * j2 + 1] = (KT)w.y;
+            } else {
+                const ulonglong2 w = *(const ulonglong2 *)(sk + 2 * pair);
+                k[2 * j2] = (KT)w.x; k[2 * j2 + 1] = (KT)w.y;
+            }
+            const ulonglong2 w = *(const ulonglong2 *)(sv + 2 * pair);
+            v[2 * j2] = (i64)w.x; v[2 * j2 + 1] = (i64)w.y;
+            if constexpr (FS::has_pred) {
+                const PT_ *const sp = (const PT_ *)(in + In::KEY_BYTES + (pred_alias ? 0 : In::VAL_BYTES));
+                sel[2 * j2] = pred_test(pred_key<PT_>(sp[2 * pair]), fs.pr);
+                sel[2 * j2 + 1] = pred_test(pred_key<PT_>(sp[2 * pair + 1]), fs.pr);
+            } else { sel[2 * j2] = sel[2 * j2 + 1] = true; }
+        }
+        u32 exc_mask = 0;                // rows of this thread that go to the side list
+        u32 wcount = 0;                  // rows of partition `lane` this warp has ranked so far in this tile
+#pragma unroll
+        for (int j = 0; j < MS_R; j++) {
+            const KT kj = k[j];
+            lo = (sel[j] && kj < lo) ? kj : lo;
+            hi = (sel[j] && kj > hi) ? kj : hi;
+            const bool ok = sel[j] && F::fits(v[j]);
+            exc_mask |= (u32)(sel[j] && !ok) << j;
+            const u32 kb = (u32)kj;
+            const u32 part = (kb >> KPL) & (NP - 1);
+            rec[j] = F::pack(kb & (KPN - 1u), v[j]);
+            // Ranking by ballots: lane L ends up with the set of lanes whose row goes to partition L (five ballots over
+            // the partition bits, each flipped where L's bit is clear); a row then fetches its own partition's set and
+            // running count from lane `part`.  No shared-memory traffic and no atomics per row.
+            u32 pl = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+            for (int b = 0; b < 5; b++) pl &= ballot_bits(kb, 1u << (KPL + b)) ^ cb[b];
+            const u32 peers = __shfl_sync(0xffffffffu, pl, part);
+            const u32 before = __shfl_sync(0xffffffffu, wcount, part);
+            wcount += __popc(pl);
+            pp[j] = ((before + __popc(peers & lt_mask)) << 8) | (ok ? part : 32u);
+        }
+        if (wcount) wbase = atomicAdd(&s_cnt[buf][lane], wcount);   // one atomic per (warp, partition) and tile, distinct addresses
+        if (exc_mask) {                                              // rare
+#pragma unroll
+            for (int j = 0; j < MS_R; j++)
+                if (exc_mask & (1u << j)) {
+                    const u32 e = atomicAdd(rs.exc_count, 1u);
+                    if (e < rs.exc_cap) { rs.exc[2 * (size_t)e] = (i64)k[j]; rs.exc[2 * (size_t)e + 1] = v[j]; }
+                }
+        }
+    };
     for (i64 tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1, it++) {
+        // both roles walk the same two barriers per tile (one __syncthreads() instruction each, reached by the whole block)
+        REC rec[MS_R];
+        u32 pp[MS_R];                        // rank among the warp's rows of the partition << 8 | partition (32 = not staged)
+        u32 wbase = 0;
         if (ctrl) {
             // the other input stage was last read before barrier A of the previous tile: refill it now
             if (lane == 0 && tile + gridDim.x < tiles) issue(tile + gridDim.x, buf ^ 1);
-            __syncthreads();                                         // A: the tile's partition counts are final
+        } else {
+            rank_tile(rec, pp, wbase);
+        }
+        __syncthreads();                                             // A: the tile's partition counts are final
+        if (ctrl) {
             const u32 c = s_cnt[buf][lane];
             u32 incl = c;
 #pragma unroll
@@ -774,6 +846,9 @@ k_ms_scatter(FS fs, const i64 *__restrict__ val, i64 tiles, RecStore rs, i64 *mm
                 phys0 = phys1 = 0;
                 if ((start & (PB - 1)) == 0) { phys0 = atomicAdd(rs.next_block, 1u) + 1; st_relaxed_u32(row + b0, phys0); }
                 if (b1 != b0) { phys1 = atomicAdd(rs.next_block, 1u) + 1; st_relaxed_u32(row + b1, phys1); }
+                // (measured: caching the partition's last block in the lane to skip this second dependent L2 round trip makes the
+                // whole pass 3 % SLOWER, 5.27 -> 5.43 ms — the control warp then reaches barrier B early and the data warps' write-out
+                // loses the overlap with it)
                 while (!phys0) phys0 = ld_relaxed_u32(row + b0);
                 if (b1 == b0) phys1 = phys0;
             }
@@ -787,70 +862,7 @@ k_ms_scatter(FS fs, const i64 *__restrict__ val, i64 tiles, RecStore rs, i64 *mm
             s_cnt[buf ^ 1][lane] = 0;                                // the next tile's counters: last read before the previous barrier B
             if (lane == 31) s_total[buf] = incl;
             if (lane == 0 && ld_relaxed_u32(rs.exc_count) > rs.exc_cap) s_abort = 1;
-            __syncthreads();                                         // B
         } else {
-            mbar_wait(&full[buf], (it >> 1) & 1u);
-            const unsigned char *in = s_in + (size_t)buf * in_bytes;
-            const KT *const sk = (const KT *)in;
-            const i64 *const sv = (const i64 *)(in + In::KEY_BYTES);
-            // rows of this thread: pairs (j2 * MS_T + tid) of the tile: conflict-free 8 / 16-byte shared-memory reads
-            KT k[MS_R];
-            i64 v[MS_R];
-            bool sel[MS_R];
-#pragma unroll
-            for (int j2 = 0; j2 < MS_R / 2; j2++) {
-                const int pair = j2 * MS_T + tid;
-                if constexpr (sizeof(KT) == 4) {
-                    const uint2 w = *(const uint2 *)(sk + 2 * pair);
-                    k[2 * j2] = (KT)w.x; k[2 * j2 + 1] = (KT)w.y;
-                } else {
-                    const ulonglong2 w = *(const ulonglong2 *)(sk + 2 * pair);
-                    k[2 * j2] = (KT)w.x; k[2 * j2 + 1] = (KT)w.y;
-                }
-                const ulonglong2 w = *(const ulonglong2 *)(sv + 2 * pair);
-                v[2 * j2] = (i64)w.x; v[2 * j2 + 1] = (i64)w.y;
-                if constexpr (FS::has_pred) {
-                    const PT_ *const sp = (const PT_ *)(in + In::KEY_BYTES + (pred_alias ? 0 : In::VAL_BYTES));
-                    sel[2 * j2] = pred_test(pred_key<PT_>(sp[2 * pair]), fs.pr);
-                    sel[2 * j2 + 1] = pred_test(pred_key<PT_>(sp[2 * pair + 1]), fs.pr);
-                } else { sel[2 * j2] = sel[2 * j2 + 1] = true; }
-            }
-            REC rec[MS_R];
-            u32 pp[MS_R];                    // rank among the warp's rows of the partition << 8 | partition (32 = not staged)
-            u32 exc_mask = 0;                // rows of this thread that go to the side list
-            u32 wcount = 0;                  // rows of partition `lane` this warp has ranked so far in this tile
-#pragma unroll
-            for (int j = 0; j < MS_R; j++) {
-                const KT kj = k[j];
-                lo = (sel[j] && kj < lo) ? kj : lo;
-                hi = (sel[j] && kj > hi) ? kj : hi;
-                const bool ok = sel[j] && F::fits(v[j]);
-                exc_mask |= (u32)(sel[j] && !ok) << j;
-                const u32 kb = (u32)kj;
-                const u32 part = (kb >> KPL) & (NP - 1);
-                rec[j] = F::pack(kb & (KPN - 1u), v[j]);
-                // Ranking by ballots: lane L ends up with the set of lanes whose row goes to partition L (five ballots over
-                // the partition bits, each flipped where L's bit is clear); a row then fetches its own partition's set and
-                // running count from lane `part`.  No shared-memory traffic and no atomics per row.
-                u32 pl = __ballot_sync(0xffffffffu, ok);
-#pragma unroll
-                for (int b = 0; b < 5; b++) pl &= ballot_bits(kb, 1u << (KPL + b)) ^ cb[b];
-                const u32 peers = __shfl_sync(0xffffffffu, pl, part);
-                const u32 before = __shfl_sync(0xffffffffu, wcount, part);
-                wcount += __popc(pl);
-                pp[j] = ((before + __popc(peers & lt_mask)) << 8) | (ok ? part : 32u);
-            }
-            u32 wbase = 0;
-            if (wcount) wbase = atomicAdd(&s_cnt[buf][lane], wcount);   // one atomic per (warp, partition) and tile, distinct addresses
-            if (exc_mask) {                                              // rare
-#pragma unroll
-                for (int j = 0; j < MS_R; j++)
-                    if (exc_mask & (1u << j)) {
-                        const u32 e = atomicAdd(rs.exc_count, 1u);
-                        if (e < rs.exc_cap) { rs.exc[2 * (size_t)e] = (i64)k[j]; rs.exc[2 * (size_t)e + 1] = v[j]; }
-                    }
-            }
-            __syncthreads();                                         // A: the tile's partition counts are final
             const u32 c = s_cnt[buf][lane];
             u32 incl = c;
 #pragma unroll
@@ -868,8 +880,8 @@ k_ms_scatter(FS fs, const i64 *__restrict__ val, i64 tiles, RecStore rs, i64 *mm
                     s_part[buf][q] = (u8)(pp[j] & 31u);
                 }
             if (it > 0) write_out(buf ^ 1);                          // the PREVIOUS tile: its descriptors were complete at its barrier B
-            __syncthreads();                                         // B: this tile is staged and described
         }
+        __syncthreads();                                             // B: this tile is staged and described
         if (s_abort) break;                                          // written before B, uniform: the record format was a bad guess
     }
     if (!ctrl && it > 0 && !s_abort) write_out(buf ^ 1);             // the last tile

@@ -92,5 +92,28 @@ ctx.sort(capi.I64, x)
 ctx.sort(capi.F64, f, True)
 h = r.integers(-1000, 1000, 2_000_000).astype(np.int64)
 ctx.filter_fold_host(capi.LT, capi.I64, h, 10, capi.F_ALL, capi.I64, h, chunk_rows=300_000)
+# round 2: narrow (<= 32-partition, ballot-ranked, TMA-staged) group-by passes with packed 32 / 64-bit records and the exception
+# list, sparse-key hash path, grouped sums through the partition passes, aggr_first / aggr_last, constant-divisor division
+os.environ["RFB_PART_MIN_ROWS"] = "1000"
+nn = 300_007
+kn = dev(r.integers(0, 100_000, nn).astype(np.int32))
+vn = r.integers(0, 1 << 20, nn).astype(np.int64)
+vn[::997] = capi.NULL_I64
+vn = dev(vn)
+ctx.group_sum_count(capi.I32, kn, vn, 100_008)
+ctx.group_sum_count(capi.I32, kn, vn, 100_008, capi.LT, capi.I64, vn, 1 << 19)
+vw = dev(r.integers(-(1 << 44), 1 << 44, nn).astype(np.int64))
+ctx.group_sum_count(capi.I64, dev(r.integers(-70_000, 130_000, nn).astype(np.int64)), vw, 200_008)
+os.environ["RFB_GROUP_STRATEGY"] = "hash"
+ctx.group_sum_count(capi.I64, dev((r.integers(0, 5000, nn).astype(np.int64)) * 0x9E3779B97F4A7C1), vn, 5008)
+os.environ.pop("RFB_GROUP_STRATEGY", None)
+gn = dev(r.integers(0, 60_000, nn).astype(np.int64))
+ctx.aggr(capi.A_SUM, capi.I64, vn, gn, 60_000)
+ctx.aggr(capi.A_AVG, capi.I64, vw, gn, 60_000)
+os.environ.pop("RFB_PART_MIN_ROWS", None)
+ctx.aggr(capi.A_FIRST, capi.I64, x, g, info.groups)
+ctx.aggr_last(capi.F64, f, g, info.groups, 8)
+for op in (capi.DIV, capi.MOD, capi.XBAR):
+    ctx.binop(op, capi.I64, x, capi.I64, -7)
 ctx.sync()
 print("sanitizer workload done, launches:", ctx.launches)
