@@ -19,6 +19,7 @@
  * RFB200_SHIM_STATS=1 prints per-operator GPU/CPU call counts and the kernel-launch count at exit.
  */
 #include <pthread.h>
+#include <time.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -58,6 +59,12 @@ static const char *S_NAME[S_N] = {"ray_eq", "ray_ne", "ray_lt", "ray_gt", "ray_l
                                   "ray_and", "ray_or", "ray_not", "at_ids", "ray_asc", "ray_desc", "ray_xasc", "ray_xdesc", "aggr_first", "aggr_last",
                                   "index_group_list"};
 static long n_gpu[S_N], n_cpu[S_N];
+static double t_gpu[S_N], t_cpu[S_N];   /* wall milliseconds per family (only measured with RFB200_SHIM_STATS=1) */
+static double now_ms(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 
 static void print_stats(void) {
     long g = 0, c = 0;
@@ -65,7 +72,7 @@ static void print_stats(void) {
     fprintf(stderr, "[rfb200 shim] operator calls handled on the GPU: %ld, on the reference CPU bodies: %ld, kernels launched: %lld\n", g, c,
             (long long)rfb_ops_launches());
     for (int i = 0; i < S_N; i++)
-        if (n_gpu[i] || n_cpu[i]) fprintf(stderr, "[rfb200 shim]   %-16s gpu %8ld   cpu %8ld\n", S_NAME[i], n_gpu[i], n_cpu[i]);
+        if (n_gpu[i] || n_cpu[i]) fprintf(stderr, "[rfb200 shim]   %-16s gpu %8ld   cpu %8ld   ms on gpu %10.2f   ms on cpu %10.2f\n", S_NAME[i], n_gpu[i], n_cpu[i], t_gpu[i], t_cpu[i]);
     long lz[4];
     rfb_ops_lazy_stats(lz);
     long rs[4];
@@ -73,6 +80,12 @@ static void print_stats(void) {
     fprintf(stderr, "[rfb200 shim] HBM residency: %ld operand images found in HBM, %ld columns shipped, %ld images dropped by the free / write hooks, %ld MiB resident\n",
             rs[0], rs[1], rs[2], rs[3]);
     if (lz[0]) fprintf(stderr, "[rfb200 shim] lazy results: %ld left on the device, %ld faulted in by a CPU access, %ld dropped unread, %ld filled at scope end\n", lz[0], lz[1], lz[2], lz[3]);
+}
+
+static int stats_on(void) {
+    static int known = -1;
+    if (known < 0) known = getenv("RFB200_SHIM_STATS") != NULL;
+    return known;
 }
 
 static int gpu_ok(void) {
@@ -105,22 +118,28 @@ static int gpu_ok(void) {
 #define WRAP1(sym, slot)                                                   \
     obj_p __real_##sym(obj_p x);                                           \
     obj_p __wrap_##sym(obj_p x) {                                          \
+        const double t0 = stats_on() ? now_ms() : 0.0;                     \
         if (gpu_ok()) {                                                    \
             obj_p r = (obj_p)rfb_##sym((rfb_obj_p)x);                      \
-            if (r) { n_gpu[slot]++; return r; }                            \
+            if (r) { n_gpu[slot]++; if (want_stats) t_gpu[slot] += now_ms() - t0; return r; } \
         }                                                                  \
         n_cpu[slot]++;                                                     \
-        return __real_##sym(x);                                            \
+        obj_p c = __real_##sym(x);                                         \
+        if (want_stats) t_cpu[slot] += now_ms() - t0;                      \
+        return c;                                                          \
     }
 #define WRAP2(sym, slot)                                                   \
     obj_p __real_##sym(obj_p x, obj_p y);                                  \
     obj_p __wrap_##sym(obj_p x, obj_p y) {                                 \
+        const double t0 = stats_on() ? now_ms() : 0.0;                     \
         if (gpu_ok()) {                                                    \
             obj_p r = (obj_p)rfb_##sym((rfb_obj_p)x, (rfb_obj_p)y);        \
-            if (r) { n_gpu[slot]++; return r; }                            \
+            if (r) { n_gpu[slot]++; if (want_stats) t_gpu[slot] += now_ms() - t0; return r; } \
         }                                                                  \
         n_cpu[slot]++;                                                     \
-        return __real_##sym(x, y);                                         \
+        obj_p c = __real_##sym(x, y);                                      \
+        if (want_stats) t_cpu[slot] += now_ms() - t0;                      \
+        return c;                                                          \
     }
 
 WRAP2(ray_eq, S_EQ) WRAP2(ray_ne, S_NE) WRAP2(ray_lt, S_LT) WRAP2(ray_gt, S_GT) WRAP2(ray_le, S_LE) WRAP2(ray_ge, S_GE)
@@ -160,10 +179,12 @@ WRAP2(aggr_med, S_AGGR_MED) WRAP2(aggr_dev, S_AGGR_DEV) WRAP2(aggr_row, S_AGGR_R
 obj_p __real_ray_select(obj_p obj);
 obj_p __wrap_ray_select(obj_p obj) {
     const int on = gpu_ok();
+    const double t0 = stats_on() ? now_ms() : 0.0;
     if (on) rfb_ops_scope_begin();
     n_cpu[S_SELECT]++;
     obj_p r = __real_ray_select(obj);
     if (on) rfb_ops_scope_end();
+    if (want_stats) t_cpu[S_SELECT] += now_ms() - t0;   /* the whole query, operators included */
     return r;
 }
 

@@ -56,11 +56,17 @@ def test_reference_test_runner_passes_through_the_dropin():
     assert not idle, "wrapped operators the reference's tests never reached on the GPU: %r\n%s" % (idle, err[-4000:])
 
 
-def test_rayfall_script_output_is_identical_stock_vs_dropin():
+@pytest.mark.parametrize("lazy", [False, True])
+def test_rayfall_script_output_is_identical_stock_vs_dropin(lazy):
+    """lazy = results stay on the device until the host reads them (page-protected payloads, RFB200_LAZY=1; here from 16 KB up so
+    that most intermediates of the script go through it): same bytes on stdout either way"""
     stock, dropin = need("rayforce_ref"), need("rayforce_dropin")
     script = os.path.join("integration", "demo", "parity.rfl")
     rc0, out0, err0 = run([stock, "-f", script])
-    rc1, out1, err1 = run([dropin, "-f", script], {"RFB200_SHIM_STATS": "1"})
+    env = {"RFB200_SHIM_STATS": "1"}
+    if lazy:
+        env.update({"RFB200_LAZY": "1", "RFB200_LAZY_MIN": "16384"})
+    rc1, out1, err1 = run([dropin, "-f", script], env)
     assert rc0 == 0 and rc1 == 0, (err0[-2000:], err1[-2000:])
     lines0 = [l for l in out0.splitlines() if " : " in l]
     lines1 = [l for l in out1.splitlines() if " : " in l]
@@ -75,6 +81,9 @@ def test_rayfall_script_output_is_identical_stock_vs_dropin():
     assert not idle, "never ran on the GPU: %r" % idle
     m = re.search(r"HBM residency: (\d+) operand images found in HBM, (\d+) columns shipped", err1)
     assert m and int(m.group(1)) > 0, err1[-2000:]
+    if lazy:
+        m = re.search(r"lazy results: (\d+) left on the device, (\d+) faulted in by a CPU access, (\d+) dropped unread", err1)
+        assert m and int(m.group(1)) > 20 and int(m.group(3)) > 0, err1[-2000:]
 
 
 def test_stock_binary_loads_the_fused_entry_point_as_a_plugin():
