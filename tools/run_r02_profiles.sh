@@ -15,4 +15,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ma
 ( for mode in "" "RFB200_LAZY=1"; do echo "=== rayforce_bench_dropin $mode RFB200_MIN_ROWS=65536"; env $mode RFB200_SHIM_STATS=1 RFB200_MIN_ROWS=65536 timeout 600 oracle/_ref/rayforce_bench_dropin 2>&1 | sed 's/\x1b\[[0-9;]*m//g' | grep -E "Results|Min Time|Avg Time|shim\] (operator|HBM|lazy)"; done; echo "=== rayforce_bench_ref"; timeout 600 oracle/_ref/rayforce_bench_ref 2>&1 | sed 's/\x1b\[[0-9;]*m//g' | grep -E "Results|Min Time|Avg Time" ) > gpurun_out/r02_make_bench_1e7.txt
 ( echo "=== stock"; timeout 900 oracle/_ref/rayforce_ref -f integration/demo/queries.rfl; for mode in "" "RFB200_LAZY=1"; do echo "=== drop-in $mode"; env $mode RFB200_SHIM_STATS=1 timeout 900 oracle/_ref/rayforce_dropin -f integration/demo/queries.rfl; done ) > gpurun_out/r02_dropin_demo_1e8.txt 2>&1
 timeout 1200 python tools/sanitizer_workload.py > /dev/null 2>&1 && ( for t in memcheck racecheck synccheck; do echo "=== compute-sanitizer --tool $t"; timeout 1500 compute-sanitizer --tool $t python tools/sanitizer_workload.py 2>&1 | tail -4; done ) > gpurun_out/r02_compute_sanitizer.txt
-ls -la gpurun_out | tail -20
+timeout 1500 python bench.py > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err
+timeout 1500 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench_reference_arm.err
+ls -la gpurun_out | tail -24
