@@ -266,7 +266,7 @@ def peak_hbm():
 E2E_CONFIG_ROWS = 250_000_000
 
 
-def run_extra_configs(ctx, stream, dev, n, rank, world, K, W, with_e2e=True):
+def run_extra_configs(ctx, stream, dev, n, rank, world, K, W, with_e2e=True, merge_mode="nccl"):
     """BASELINE.json configs[2..4] on the same box, same process, device-resident, each timed with CUDA events around K steps
     (max over ranks): fp64 (a*b+c) -> avg; group-by 1e5 int32 keys sum/count; filter + group-by + sum sharded by row range with
     the NCCL merge.  A step of the group-by configs is the whole rfb_group_sum_count_dev call (sample, scatter, accumulate,
@@ -346,6 +346,10 @@ def run_extra_configs(ctx, stream, dev, n, rank, world, K, W, with_e2e=True):
     ctx.sync()
 
     def step_fma():
+        if world > 1 and merge_mode == "peer":               # error-free (hi, lo) partial sums folded in rank order by one tiny kernel
+            ctx.fma_fold_async(capi.F_SUM | capi.F_CNT, a, b, c, n)
+            m = ctx.fold_allreduce_peers(capi.F64)
+            return m.sum / m.nonnull
         r = ctx.fma_fold(capi.F_SUM | capi.F_CNT, a, b, c, n)
         if world == 1:
             return r.sum / r.nonnull
@@ -356,7 +360,8 @@ def run_extra_configs(ctx, stream, dev, n, rank, world, K, W, with_e2e=True):
     ms, avg, launches = timed(step_fma)
     assert 0.74 < avg < 0.76, avg                             # E[a*b + c] = 1/4 + 1/2 for uniform [0, 1) columns
     out["fma_avg"] = entry("(avg (+ (* a b) c)): three F64 columns, splitmix64 / 2^20 in [0, 1), fused k_fma_fold", ms, 24 * n, launches,
-                           {"avg": avg}, "none" if world == 1 else "all-gather of (sum, count) partials, added in rank order")
+                           {"avg": avg}, "none" if world == 1 else ("peer mailboxes: (hi, lo) partial sums folded in rank order by one 32-thread kernel" if merge_mode == "peer"
+                                                                   else "all-gather of (sum, count) partials, added in rank order"))
     if with_e2e:
         ha, hb, hc = (pinned_copy(t) for t in (a, b, c))
         na, nb_, nc = ha.numpy(), hb.numpy(), hc.numpy()
@@ -572,7 +577,7 @@ def run_gpu_arm(args):
     configs = None
     if not args.no_configs:
         del x
-        configs = run_extra_configs(ctx, stream, dev, n, rank, world, max(1, min(K, args.config_steps)), W, with_e2e=not args.no_e2e)
+        configs = run_extra_configs(ctx, stream, dev, n, rank, world, max(1, min(K, args.config_steps)), W, with_e2e=not args.no_e2e, merge_mode=merge_mode)
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:

@@ -176,6 +176,10 @@ class Context:
         check(self.lib.rfb_multi_filter_fold_dev(self.h, len(preds), arr, int(conjunction), folds, val_type, _dptr(val), n, C.byref(f)))
         return FoldResult(f, val_type)
 
+    def fma_fold_async(self, folds: int, a, b, c, n: int) -> None:
+        """enqueue only; collect with fold_result() or fold_allreduce_peers()"""
+        check(self.lib.rfb_fma_fold_dev(self.h, folds, _dptr(a), _dptr(b), _dptr(c), n, None))
+
     def fma_fold(self, folds: int, a, b, c, n: int) -> FoldResult:
         f = Fold()
         check(self.lib.rfb_fma_fold_dev(self.h, folds, _dptr(a), _dptr(b), _dptr(c), n, C.byref(f)))
