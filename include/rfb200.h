@@ -205,9 +205,13 @@ int rfb_gather_dev(rfb_ctx_t *ctx, int type, const void *col, const int64_t *ids
 int rfb_gather_fold_dev(rfb_ctx_t *ctx, int folds, int type, const void *col, const int64_t *ids, int64_t m,
                         rfb_fold_t *out);
 
-/* ray_add..ray_mod -> binop_map (core/math.c:2280-2345) for I32/I64/F64 operands (vector or atom).
- * rfb_binop_type answers the result element type (infer_math_type & co, core/math.c:92-223) or RFB_ERR_TYPE. */
+/* ray_add..ray_xbar -> binop_map (core/math.c:2280-2345), vector or atom operands, over the reference's full type matrix
+ * (ray_add_partial .. ray_xbar_partial, core/math.c:251-1782): B8 / U8 / I16 / I32 / I64 / DATE / TIME / TIMESTAMP / F64 operands
+ * incl. the unit conversions (DATE + TIME -> TIMESTAMP ...).  rfb_binop_type answers the result element type for I32/I64/F64
+ * operands (infer_math_type & co, core/math.c:92-249) or RFB_ERR_TYPE; rfb_binop_type_form answers it for any operand types and
+ * one operand form (0 vector-vector, 1 vector-atom, 2 atom-vector) — RFB_ERR_TYPE exactly where the reference has no case. */
 int rfb_binop_type(int op, int xt, int yt);
+int rfb_binop_type_form(int op, int form, int xt, int yt);
 int rfb_binop_dev(rfb_ctx_t *ctx, int op, int xt, const void *x, int64_t xn, const rfb_scalar_t *xs, int yt,
                   const void *y, int64_t yn, const rfb_scalar_t *ys, void *out);
 /* ray_round / ray_floor / ray_ceil -> unop_map (core/math.c:2047-2117, 2233-2278) */

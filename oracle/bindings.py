@@ -85,6 +85,8 @@ class Oracle:
         L.rfo_sum_f64_exact.argtypes = [vp, i64]
         L.rfo_binop_type.restype = ci
         L.rfo_binop_type.argtypes = [ci, ci, ci]
+        L.rfo_binop_form.restype = ci
+        L.rfo_binop_form.argtypes = [ci, ci, ci, ci]
         L.rfo_binop.restype = i64
         L.rfo_binop.argtypes = [ci, ci, vp, i64, ci, vp, i64, vp, C.POINTER(ci)]
         L.rfo_unop_f64.restype = ci
@@ -145,10 +147,15 @@ class Oracle:
     def binop_type(self, op, xt, yt):
         return self.L.rfo_binop_type(op, xt, yt)
 
+    def binop_form(self, op, form, xt, yt):
+        return self.L.rfo_binop_form(op, form, xt, yt)
+
     def binop(self, op, xt, x, yt, y):
         xa, xn = _operand(x, xt)
         ya, yn = _operand(y, yt)
         ot = self.L.rfo_binop_type(op, xt, yt)
+        if ot < 0:      # outside I32/I64/F64: the full type matrix, per operand form
+            ot = self.binop_form(op, 0 if xn >= 0 and yn >= 0 else 1 if xn >= 0 else 2, xt, yt)
         if ot < 0:
             raise OracleError(ot)
         n = xn if xn >= 0 else (yn if yn >= 0 else 1)
@@ -374,6 +381,10 @@ class Reference:
         L.i32.argtypes = [C.c_int32]
         L.f64.restype = vp
         L.f64.argtypes = [C.c_double]
+        for name, ct in (("b8", C.c_uint8), ("u8", C.c_uint8), ("i16", C.c_int16), ("adate", C.c_int32), ("atime", C.c_int32),
+                         ("timestamp", C.c_int64)):       # atom constructors, core/rayforce.c:150-235
+            f = getattr(L, name)
+            f.restype, f.argtypes = vp, [ct]
         L.drop_obj.restype = None
         L.drop_obj.argtypes = [vp]
         L.clone_obj.restype = vp
@@ -480,6 +491,9 @@ class Reference:
             return self.L.i32(int(v))
         if t == F64:
             return self.L.f64(float(v))
+        ctor = {B8: "b8", U8: "u8", I16: "i16", DATE: "adate", TIME: "atime", TIMESTAMP: "timestamp"}.get(t)
+        if ctor:
+            return getattr(self.L, ctor)(int(v))
         raise RefError("atom type %d" % t)
 
     def operand(self, t, a):

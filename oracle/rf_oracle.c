@@ -378,9 +378,143 @@ static inline f64 op_fdiv(int left_is_int, f64 x, f64 y) {
     return x / y;
 }
 
+/* ---- the full type matrix (U8 / I16 / B8 / DATE / TIME / TIMESTAMP operands): every case of ray_add_partial .. ray_xbar_partial
+ * (core/math.c:251-1782) is  out[i] = mt_to_ot(OP(lt_to_mt(x[i]), rt_to_mt(y[i])))  (__BINOP_V_V / _V_A / _A_V, core/math.c:55-90);
+ * binop_matrix.inc lists (lt, rt, ot, mt, OP family) per (operator, form, operand types) and the type binop_map gives the result
+ * vector.  The conversions are the <from>_to_<to> helpers of core/ops.h:218-277, the operators core/ops.h:125-197. */
+typedef struct { int8_t op, form, xt, yt, lt, rt, ot, mt, fam, vt; int line; } binop_case_t;
+static const binop_case_t BINOP_CASES[] = {
+#include "binop_matrix.inc"
+};
+static const binop_case_t *binop_case(int op, int form, int xt, int yt) {
+    for (size_t i = 0; i < sizeof(BINOP_CASES) / sizeof(BINOP_CASES[0]); i++) {
+        const binop_case_t *c = &BINOP_CASES[i];
+        if (c->op == op && c->form == form && c->xt == xt && c->yt == yt) return c;
+    }
+    return NULL;
+}
+int rfo_binop_form(int op, int form, int xt, int yt) {
+    const binop_case_t *c = binop_case(op, form, xt, yt);
+    return c ? c->vt : RFO_ERR_TYPE;
+}
+typedef struct { i64 i; f64 f; } bval_t;   /* .i for every integer kind (the exact value of its C type), .f for F64 */
+static int null_width(int kind) {          /* 0: no null (B8 / U8); else the width of the integer whose minimum is the null */
+    switch (kind) {
+        case RFO_I16: return 16;
+        case RFO_I32: case RFO_DATE: case RFO_TIME: return 32;
+        case RFO_I64: case RFO_TIMESTAMP: return 64;
+        default: return 0;
+    }
+}
+static int is_null_int(int kind, i64 v) {
+    switch (null_width(kind)) {
+        case 16: return v == RFO_NULL_I16;
+        case 32: return v == RFO_NULL_I32;
+        case 64: return v == RFO_NULL_I64;
+        default: return 0;
+    }
+}
+static bval_t bload(int kind, const void *p, i64 i) {
+    bval_t v = {0, 0.0};
+    switch (kind_of(kind)) {
+        case K_U8: v.i = ((const u8 *)p)[i]; break;
+        case K_I16: v.i = ((const i16 *)p)[i]; break;
+        case K_I32: v.i = ((const i32 *)p)[i]; break;
+        case K_I64: v.i = ((const i64 *)p)[i]; break;
+        default: v.f = ((const f64 *)p)[i]; break;
+    }
+    return v;
+}
+static void bstore(int kind, void *p, i64 i, bval_t v) {
+    switch (kind_of(kind)) {
+        case K_U8: ((u8 *)p)[i] = (u8)v.i; break;
+        case K_I16: ((i16 *)p)[i] = (i16)v.i; break;
+        case K_I32: ((i32 *)p)[i] = (i32)v.i; break;
+        case K_I64: ((i64 *)p)[i] = v.i; break;
+        default: ((f64 *)p)[i] = v.f; break;
+    }
+}
+#define NANOS_PER_DAY 86400000000000LL   /* core/temporal.h:39-40 */
+#define NANOS_PER_MILLI 1000000LL
+static bval_t bconv(int from, int to, bval_t v) {   /* <from>_to_<to>, core/ops.h:218-277 */
+    bval_t r = {0, 0.0};
+    if (from == to) return v;
+    if (from == RFO_F64) {
+        if (null_width(to) == 64) r.i = f64_to_i64(v.f); else r.i = f64_to_i32(v.f);
+        return r;
+    }
+    if (from == RFO_B8) v.i = (v.i != 0);                                   /* b8_to_i64 */
+    if (to == RFO_F64) { r.f = is_null_int(from, v.i) ? null_f64() : (f64)v.i; return r; }
+    if (to == RFO_B8) { r.i = (v.i != 0 && v.i != RFO_NULL_I64); return r; } /* i64_to_b8 */
+    if (is_null_int(from, v.i)) {
+        switch (null_width(to)) {
+            case 16: r.i = RFO_NULL_I16; return r;
+            case 32: r.i = RFO_NULL_I32; return r;
+            case 64: r.i = RFO_NULL_I64; return r;
+            default: r.i = (u8)v.i; return r;
+        }
+    }
+    if (from == RFO_DATE && to == RFO_TIMESTAMP) { r.i = wmul64(NANOS_PER_DAY, v.i); return r; }
+    if (from == RFO_TIME && to == RFO_TIMESTAMP) { r.i = wmul64(NANOS_PER_MILLI, v.i); return r; }
+    if (from == RFO_TIMESTAMP && to == RFO_DATE) { r.i = (i32)(v.i / NANOS_PER_DAY); return r; }
+    if (from == RFO_TIMESTAMP && to == RFO_TIME) { r.i = (i32)(v.i % NANOS_PER_DAY / NANOS_PER_MILLI); return r; }
+    switch (null_width(to)) {
+        case 16: r.i = (i16)v.i; break;
+        case 32: r.i = (i32)v.i; break;
+        case 64: r.i = v.i; break;
+        default: r.i = (u8)v.i; break;
+    }
+    return r;
+}
+static inline u8 op_u8(int op, u8 x, u8 y) {     /* core/ops.h:125-130: no nulls, division by zero gives 0 */
+    switch (op) {
+        case RFO_ADD: return (u8)(x + y); case RFO_SUB: return (u8)(x - y); case RFO_MUL: return (u8)(x * y);
+        case RFO_DIV: return y == 0 ? 0 : (u8)(x / y);
+        default: return y == 0 ? 0 : (u8)(x % y);
+    }
+}
+static inline i16 op_i16(int op, i16 x, i16 y) { /* core/ops.h:136-140: computed in int, narrowed */
+    if (x == RFO_NULL_I16 || y == RFO_NULL_I16) return RFO_NULL_I16;
+    switch (op) {
+        case RFO_ADD: return (i16)(x + y); case RFO_SUB: return (i16)(x - y); case RFO_MUL: return (i16)(x * y);
+        case RFO_DIV: return y == 0 ? RFO_NULL_I16 : (i16)eucl_div32(x, y);
+        default: return y == 0 ? RFO_NULL_I16 : (i16)eucl_mod32(x, y);
+    }
+}
+static int64_t binop_matrix(const binop_case_t *c, const void *x, i64 xn, const void *y, i64 yn, void *out, int *out_type) {
+    const i64 n = xn >= 0 ? xn : yn;
+    *out_type = c->vt;
+    for (i64 i = 0; i < n; i++) {
+        const bval_t a = bconv(c->lt, c->mt, bload(c->lt, x, xn >= 0 ? i : 0));
+        const bval_t b = bconv(c->rt, c->mt, bload(c->rt, y, yn >= 0 ? i : 0));
+        bval_t r = {0, 0.0};
+        if (c->mt == RFO_F64) {
+            if (c->op == RFO_FDIV) r.f = op_fdiv(c->fam == RFO_I64, a.f, b.f);   /* FDIVI64 on converted doubles vs FDIVF64 */
+            else r.f = op_f64(c->op, a.f, b.f);
+        } else {
+            switch (c->fam) {
+                case RFO_U8: r.i = op_u8(c->op, (u8)a.i, (u8)b.i); break;
+                case RFO_I16: r.i = op_i16(c->op, (i16)a.i, (i16)b.i); break;
+                case RFO_I32: r.i = op_i32(c->op, (i32)a.i, (i32)b.i); break;
+                default: r.i = op_i64(c->op, a.i, b.i); break;
+            }
+        }
+        bstore(c->ot, out, i, bconv(c->mt, c->ot, r));
+    }
+    return n;
+}
+static int plain_num(int t) { return t == RFO_I32 || t == RFO_I64 || t == RFO_F64; }
+
 int64_t rfo_binop(int op, int xt, const void *x, int64_t xn, int yt, const void *y, int64_t yn, void *out,
                   int *out_type) {
     int mt, ot;
+    if (!(plain_num(xt) && plain_num(yt))) {
+        if (xn < 0 && yn < 0) return RFO_ERR_TYPE; /* atom op atom: no vector form */
+        const binop_case_t *c = binop_case(op, xn >= 0 ? (yn >= 0 ? 0 : 1) : 2, xt, yt);
+        if (!c) return RFO_ERR_TYPE;
+        if (xn >= 0 && yn >= 0 && xn != yn) return RFO_ERR_LENGTH;
+        return binop_matrix(c, x, xn, y, yn, out, out_type);
+    }
     if (!binop_types(op, xt, yt, &mt, &ot)) return RFO_ERR_TYPE;
     if (xn >= 0 && yn >= 0 && xn != yn) return RFO_ERR_LENGTH; /* core/math.c:2287-2289 */
     i64 n = xn >= 0 ? xn : (yn >= 0 ? yn : 1);

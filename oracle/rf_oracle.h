@@ -66,6 +66,9 @@ double rfo_sum_f64_exact(const double *x, int64_t n);
  * Supported element types: I32, I64, F64 on either side (vector or atom).  *out_type receives the result type;
  * out must hold max(xn,yn,1) elements of it.  rfo_binop_type alone answers "what type would it be". */
 int rfo_binop_type(int op, int xt, int yt);
+/* the full type matrix of core/math.c:251-1782 (U8 / I16 / B8 / DATE / TIME / TIMESTAMP operands too): result vector type for
+ * form 0 vector-vector, 1 vector-atom, 2 atom-vector, or RFO_ERR_TYPE when the reference has no such case. */
+int rfo_binop_form(int op, int form, int xt, int yt);
 int64_t rfo_binop(int op, int xt, const void *x, int64_t xn, int yt, const void *y, int64_t yn, void *out,
                   int *out_type);
 int rfo_unop_f64(int op, const double *x, int64_t n, double *out); /* round/floor/ceil core/math.c:2047-2117 */

@@ -128,6 +128,7 @@ SIGNATURES = {
     "rfb_gather_dev": (_ci, [_vp, _ci, _vp, _vp, _i64, _vp]),
     "rfb_gather_fold_dev": (_ci, [_vp, _ci, _ci, _vp, _vp, _i64, _P(Fold)]),
     "rfb_binop_type": (_ci, [_ci, _ci, _ci]),
+    "rfb_binop_type_form": (_ci, [_ci, _ci, _ci, _ci]),
     "rfb_binop_dev": (_ci, [_vp, _ci, _ci, _vp, _i64, _P(Scalar), _ci, _vp, _i64, _P(Scalar), _vp]),
     "rfb_unop_f64_dev": (_ci, [_vp, _ci, _vp, _i64, _vp]),
     "rfb_group_i64_dev": (_ci, [_vp, _vp, _vp, _i64, _vp, _vp, _P(GroupInfo)]),

@@ -853,8 +853,10 @@ static obj_p bin_op(int op, obj_p x, obj_p y) {
     const int xv = is_vec(x), yv = is_vec(y);
     if (!(xv || yv) || !((xv || is_atom(x)) && (yv || is_atom(y)))) return NULL;
     const int xt = xv ? x->type : -x->type, yt = yv ? y->type : -y->type;
-    const int ot = rfb_binop_type(op, xt, yt);
-    if (ot < 0) return NULL; /* the reference's matrix is wider (dates, times, u8...): leave those to the CPU body */
+    /* the reference's full type matrix (core/math.c:251-1782): U8 / I16 / DATE / TIME / TIMESTAMP operands included; where it has
+     * no case (DATE * DATE ...) its own body raises the type error */
+    const int ot = rfb_binop_type_form(op, xv ? (yv ? 0 : 1) : 2, xt, yt);
+    if (ot < 0) return NULL;
     if (xv && yv && x->len != y->len) return G.host->err_length();
     const int64_t n = xv ? x->len : y->len;
     if (too_small(n) || gated_out(x, y)) return NULL;

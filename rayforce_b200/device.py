@@ -341,9 +341,11 @@ class _Ops:
 
     def binop(self, op, xt, x, yt, y):
         """ray_add/sub/mul/div/fdiv/mod -> (tensor, result type)"""
-        ot = self.binop_type(op, xt, yt)
         xp, xn, xs = _operand(x, xt)
         yp, yn, ys = _operand(y, yt)
+        ot = self.lib.rfb_binop_type_form(op, 0 if xn >= 0 and yn >= 0 else 1 if xn >= 0 else 2, xt, yt)
+        if ot < 0:
+            raise RfbError(ot, "binop %d: unsupported operand types %d, %d" % (op, xt, yt))
         if xn >= 0 and yn >= 0 and xn != yn:
             check(self.lib.rfb_binop_dev(self.h, op, xt, xp, xn, _sref(xs), yt, yp, yn, _sref(ys), None))
         out = self._empty(xn if xn >= 0 else yn, ot)

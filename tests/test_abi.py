@@ -39,7 +39,12 @@ def test_abi_version_and_type_tables():
     assert lib.rfb_binop_type(capi.DIV, capi.I32, capi.F64) == capi.I32      # `/` keeps the left operand's type
     assert lib.rfb_binop_type(capi.FDIV, capi.I64, capi.I64) == capi.F64
     assert lib.rfb_binop_type(capi.MOD, capi.I64, capi.I32) == capi.I32      # `%` takes the right operand's type
-    assert lib.rfb_binop_type(capi.ADD, capi.U8, capi.I64) == capi.ERR_TYPE
+    assert lib.rfb_binop_type(capi.ADD, capi.U8, capi.I64) == capi.ERR_TYPE  # the plain-numeric typing rule; the full matrix is per form:
+    assert lib.rfb_binop_type_form(capi.ADD, 0, capi.U8, capi.I64) == capi.I64
+    assert lib.rfb_binop_type_form(capi.ADD, 0, capi.DATE, capi.TIME) == capi.TIMESTAMP   # core/math.c: date + time -> timestamp
+    assert lib.rfb_binop_type_form(capi.SUB, 1, capi.TIMESTAMP, capi.TIMESTAMP) == capi.I64
+    assert lib.rfb_binop_type_form(capi.MUL, 0, capi.DATE, capi.DATE) == capi.ERR_TYPE
+    assert lib.rfb_binop_type_form(capi.ADD, 2, capi.I32, capi.I64) == lib.rfb_binop_type(capi.ADD, capi.I32, capi.I64)
     assert lib.rfb_aggr_type(capi.A_AVG, capi.I64) == capi.F64
     assert lib.rfb_aggr_type(capi.A_MIN, capi.I32) == capi.ERR_TYPE           # grouped min/max has no I32 case
     assert lib.rfb_aggr_type(capi.A_SUM, capi.TIMESTAMP) == capi.ERR_TYPE

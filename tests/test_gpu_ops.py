@@ -8,7 +8,7 @@ import pytest
 
 from oracle import bindings as ob
 from rayforce_b200 import capi
-from tests.util import dev, host, rng_col, same_f64
+from tests.util import ALL_ARITH_TYPES, dev, host, rng_col, same_f64, typed_col
 
 pytestmark = pytest.mark.gpu
 
@@ -221,13 +221,69 @@ def test_division_by_a_constant_atom(ctx, oracle, op):
         assert gt == wt and np.array_equal(host(got), want), k
 
 
+@pytest.mark.parametrize("op", ARITH)
+@pytest.mark.parametrize("xt", ALL_ARITH_TYPES)
+def test_binop_full_type_matrix(ctx, oracle, op, xt):
+    """every (operator, operand types, form) case of the reference outside I32/I64/F64 x I32/I64/F64 (core/math.c:251-1782: B8 /
+    U8 / I16 / DATE / TIME / TIMESTAMP operands, unit conversions included): k_binop_typed against the pinned matrix restatement,
+    a type error exactly where the reference has no case; lengths straddle the vector tile and leave a scalar tail"""
+    plain = (ob.I32, ob.I64, ob.F64)
+    for yt in ALL_ARITH_TYPES:
+        if xt in plain and yt in plain:
+            continue
+        for n in (4_099, 70_001):
+            x, y = typed_col(xt, n, 11 + n), typed_col(yt, n, 12 + n)
+            dx, dy = dev(x), dev(y)
+            for form, (a, b, da, db) in ((0, (x, y, dx, dy)), (1, (x, y[5], dx, y[5])), (1, (x, y[0], dx, y[0])), (1, (x, y[3], dx, y[3])),
+                                         (2, (x[5], y, x[5], dy)), (2, (x[0], y, x[0], dy)), (2, (x[3], y, x[3], dy))):
+                want_t = oracle.binop_form(op, form, xt, yt)
+                assert ctx.lib.rfb_binop_type_form(op, form, xt, yt) == (want_t if want_t >= 0 else capi.ERR_TYPE)
+                if want_t < 0:
+                    with pytest.raises(capi.RfbError) as e:
+                        ctx.binop(op, xt, da, yt, db)
+                    assert e.value.kind == "type"
+                    continue
+                want, wt = oracle.binop(op, xt, a, yt, b)
+                got, gt = ctx.binop(op, xt, da, yt, db)
+                got = host(got)
+                assert gt == wt == want_t, (op, form, xt, yt)
+                if wt == ob.F64:
+                    assert same_f64(got, want, zero_sign=False, max_ulp=1 if op == ob.FDIV else 0), (op, form, xt, yt)
+                else:
+                    assert np.array_equal(got, want), (op, form, xt, yt, np.flatnonzero(got != want)[:8])
+
+
+@pytest.mark.parametrize("op", [ob.DIV, ob.MOD, ob.XBAR])
+def test_timestamp_division_by_a_constant_atom(ctx, oracle, op):
+    """TIMESTAMP (/ | % | xbar) by an I64 / TIMESTAMP atom shares the magic-multiplier kernel of i64 by an atom"""
+    x = typed_col(ob.TIMESTAMP, 50_021, 3)
+    for yt in (ob.I64, ob.TIMESTAMP):
+        if oracle.binop_form(op, 1, ob.TIMESTAMP, yt) < 0:
+            continue
+        for k in (60_000_000_000, 86_400_000_000_000, -7, 3, 1, -1, 0, ob.NULL_I64):
+            want, wt = oracle.binop(op, ob.TIMESTAMP, x, yt, k)
+            got, gt = ctx.binop(op, ob.TIMESTAMP, dev(x), yt, k)
+            assert gt == wt and np.array_equal(host(got), want), (yt, k)
+
+
+def test_binop_unaligned_typed_operands(ctx, oracle):
+    """operand views that are not 16-byte aligned take the scalar path of k_binop_typed"""
+    n = 30_001
+    x, y = typed_col(ob.TIMESTAMP, n + 1, 5), typed_col(ob.TIME, n + 3, 6)
+    dx, dy = dev(x)[1:], dev(y)[3:]
+    for op in (ob.ADD, ob.SUB):
+        want, wt = oracle.binop(op, ob.TIMESTAMP, x[1:], ob.TIME, y[3:])
+        got, gt = ctx.binop(op, ob.TIMESTAMP, dx, ob.TIME, dy)
+        assert gt == wt == ob.TIMESTAMP and np.array_equal(host(got), want)
+
+
 def test_binop_errors(ctx):
     a, b = dev(np.zeros(4, np.int64)), dev(np.zeros(5, np.int64))
     with pytest.raises(capi.RfbError) as e:
         ctx.binop(ob.ADD, ob.I64, a, ob.I64, b)
     assert e.value.kind == "length"
     with pytest.raises(capi.RfbError) as e:
-        ctx.binop(ob.ADD, ob.U8, dev(np.zeros(4, np.uint8)), ob.I64, a)
+        ctx.binop(ob.MUL, ob.DATE, dev(np.zeros(4, np.int32)), ob.DATE, dev(np.zeros(4, np.int32)))   # no such case in the reference's matrix
     assert e.value.kind == "type"
 
 

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import bindings as ob
-from tests.util import rng_col, same_f64, f64_sum_ok
+from tests.util import rng_col, same_f64, f64_sum_ok, ALL_ARITH_TYPES, typed_col
 
 SIZES = [0, 1, 5, 16383, 16384, 16385, 100_003]
 CMPS = [ob.EQ, ob.NE, ob.LT, ob.GT, ob.LE, ob.GE]
@@ -138,6 +138,46 @@ def test_binop(oracle, reference, op, xt, yt):
             assert same_f64(o, r, zero_sign=False, max_ulp=1 if op in (ob.FDIV, ob.DIV, ob.MOD) else 0), (op, xt, yt)
         else:
             assert np.array_equal(o, r), (op, xt, yt, np.ndim(a), np.ndim(b))
+
+
+@pytest.mark.parametrize("op", ARITH)
+@pytest.mark.parametrize("xt", ALL_ARITH_TYPES)
+def test_binop_type_matrix(oracle, reference, op, xt):
+    """Every (operator, operand types, form) case of core/math.c:251-1782 outside I32/I64/F64 x I32/I64/F64: the oracle's matrix
+    restatement (oracle/binop_matrix.inc) against the compiled reference — same result type, same bytes, and a type error exactly
+    where the reference has no case."""
+    n = 4_099
+    for yt in ALL_ARITH_TYPES:
+        if xt in NUM and yt in NUM:
+            continue
+        x, y = typed_col(xt, n, 11), typed_col(yt, n, 12)
+        for form, (a, b) in ((0, (x, y)), (1, (x, y[5])), (1, (x, y[0])), (1, (x, y[3])), (2, (x[5], y)), (2, (x[0], y)), (2, (x[3], y))):
+            want_t = oracle.binop_form(op, form, xt, yt)
+            try:
+                r, rt = reference.binop(op, xt, a, yt, b)
+            except Exception:
+                r, rt = None, -1
+            if want_t < 0:
+                # no kernel case in the reference: it raises a type error too.  One exception (core/math.c:996-997): B8 * I64
+                # writes 1-byte results into the 8-byte vector binop_map allocated — no defined result, left out of the matrix
+                assert r is None or (op, xt, yt) == (ob.MUL, ob.B8, ob.I64), (op, form, xt, yt)
+                continue
+            o, ot = oracle.binop(op, xt, a, yt, b)
+            assert r is not None, (op, form, xt, yt)
+            assert ot == rt == want_t, (op, form, xt, yt, ot, rt)
+            if ot == ob.F64:
+                assert same_f64(o, r, zero_sign=False, max_ulp=1 if op in (ob.FDIV, ob.DIV, ob.MOD) else 0), (op, form, xt, yt)
+            else:
+                assert np.array_equal(o, r), (op, form, xt, yt, o[:20], r[:20], np.flatnonzero(o != r)[:10])
+
+
+def test_binop_matrix_agrees_with_plain_numeric_rules(oracle):
+    """inside I32/I64/F64 the generated matrix and the hand-written typing rules (pinned in test_binop) must say the same"""
+    for op in ARITH:
+        for xt in NUM:
+            for yt in NUM:
+                for form in (0, 1, 2):
+                    assert oracle.binop_form(op, form, xt, yt) == oracle.binop_type(op, xt, yt), (op, form, xt, yt)
 
 
 @pytest.mark.parametrize("op", [ob.ROUND, ob.FLOOR, ob.CEIL])

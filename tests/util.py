@@ -71,3 +71,30 @@ def same_f64(a, b, zero_sign=True, max_ulp=0) -> bool:
     if not np.array_equal(a[~fin], b[~fin]):
         return False
     return bool(np.all(np.abs(a[fin] - b[fin]) <= max_ulp * np.spacing(np.abs(b[fin]))))
+
+
+ALL_ARITH_TYPES = [ob.B8, ob.U8, ob.I16, ob.I32, ob.I64, ob.DATE, ob.TIME, ob.TIMESTAMP, ob.F64]
+
+
+def typed_col(t, n, seed):
+    """small magnitudes (so products stay meaningful), zeros (division), nulls, and a few extreme values per type"""
+    if t == ob.B8:
+        return (np.random.default_rng(seed).integers(0, 2, n)).astype(np.uint8)
+    if t == ob.U8:
+        a = rng_col(t, n, seed, lo=0, hi=256)
+        a[::17] = 0
+        return a
+    if t == ob.TIMESTAMP:
+        a = rng_col(t, n, seed, null_frac=0.04, lo=-3 * 86_400_000_000_000, hi=40 * 86_400_000_000_000)
+    elif t == ob.TIME:
+        a = rng_col(t, n, seed, null_frac=0.04, lo=-1000, hi=86_400_000)
+    else:
+        a = rng_col(t, n, seed, null_frac=0.04, lo=-50, hi=50)
+        if t == ob.F64:
+            a = np.round(a * 4) / 4
+    a[::17] = 0
+    if t != ob.F64:
+        info = np.iinfo(a.dtype)
+        a[5::1013] = info.max
+        a[7::1013] = info.min + 1
+    return a

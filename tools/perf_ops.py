@@ -36,7 +36,7 @@ def main():
         return x
 
     def timed(name, fn, alg_bytes, note=""):
-        if args.only and args.only not in name:
+        if args.only and not any(o in name for o in args.only.split(",")):
             return
         for _ in range(2):
             fn()
@@ -80,6 +80,13 @@ def main():
         timed("add_i64_vv", lambda: ctx.binop(capi.ADD, capi.I64, x, capi.I64, y), 24 * n)
         timed("mul_i64_va", lambda: ctx.binop(capi.MUL, capi.I64, x, capi.I64, 3), 16 * n)
         timed("div_i64_va", lambda: ctx.binop(capi.DIV, capi.I64, x, capi.I64, 7), 16 * n)
+        # the typed matrix kernels (k_binop_typed): the I64 / I32 payloads reinterpreted as TIMESTAMP / TIME columns
+        tcol = col(capi.I32, 44, 86_400_000)
+        timed("add_timestamp_time_vv", lambda: ctx.binop(capi.ADD, capi.TIMESTAMP, x, capi.TIME, tcol), 20 * n, "timestamp + time (ms -> ns): 8 + 4 in, 8 out")
+        timed("sub_timestamp_timestamp_vv", lambda: ctx.binop(capi.SUB, capi.TIMESTAMP, x, capi.TIMESTAMP, y), 24 * n)
+        timed("xbar_timestamp_va", lambda: ctx.binop(capi.XBAR, capi.TIMESTAMP, x, capi.I64, 60_000_000_000), 16 * n, "generic 64-bit division inside the typed kernel")
+        timed("xbar_time_va", lambda: ctx.binop(capi.XBAR, capi.TIME, tcol, capi.I32, 60_000), 8 * n)
+        del tcol
         del x
         # config 3: fp64 a*b+c -> avg
         a, b, c = col(capi.F64, 1, 1 << 20, 0, float(1 << 20)), col(capi.F64, 2, 1 << 20, 0, float(1 << 20)), col(capi.F64, 3, 1 << 20, 0, float(1 << 20))
@@ -97,6 +104,18 @@ def main():
         timed("group_sum_count_i32keys_1e5", lambda: ctx.group_sum_count(capi.I32, k32, y, 100_000), 12 * n, "config 4 fused (2 passes over keys)")
         timed("group_sum_count_i32keys_1e5_where", lambda: ctx.group_sum_count(capi.I32, k32, y, 100_000, capi.LT, capi.I64, y, 1 << 19), 12 * n)
         del k32
+        # config 4's contention variant: Zipf-like keys, P(k) ~ 1 / k over [0, 1e5) (k = floor(1e5^u) - 1, u uniform)
+        if not args.only or "zipf" in args.only.split(","):
+            kz = torch.empty(n, dtype=torch.int32, device=dev)
+            step = 1 << 26
+            for i0 in range(0, n, step):
+                m = min(step, n - i0)
+                u = torch.rand(m, device=dev, dtype=torch.float64)
+                kz[i0:i0 + m] = (torch.pow(100_000.0, u).to(torch.int64) - 1).clamp_(0, 99_999).to(torch.int32)
+                del u
+            torch.cuda.synchronize()
+            timed("group_sum_count_i32keys_1e5_zipf", lambda: ctx.group_sum_count(capi.I32, kz, y, 100_000), 12 * n, "config 4, Zipf(1) keys: hot keys contend")
+            del kz
         k64 = col(capi.I64, 7, 100_000)
         timed("group_sum_count_i64keys_1e5", lambda: ctx.group_sum_count(capi.I64, k64, y, 100_000), 16 * n)
         timed("index_group_i64_dense_1e5", lambda: ctx.group_i64(k64), 16 * n, "scope + claim + number + assign (group_ids written)")
