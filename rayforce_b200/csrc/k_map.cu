@@ -9,110 +9,9 @@
 // (tile*TILE + j*THREADS + t)*R .. +R, so every load instruction of a warp touches one contiguous 512-byte span (and the
 // narrower operand a contiguous 512/k span).  All loads of a tile are issued before the first use (UNROLL vectors in
 // flight per operand per thread) and bypass L1 allocation.  Grid = SM count x resident CTAs, grid-stride over tiles.
-#include "rfb_common.cuh"
+#include "rfb_map.cuh"
 
 namespace {
-
-constexpr int THREADS = 256;
-constexpr int BLOCKS_PER_SM = 4;
-
-template <int BYTES> struct RawVec;
-template <> struct RawVec<16> { typedef vec16 type; };
-template <> struct RawVec<8> { typedef u64 type; };
-template <> struct RawVec<4> { typedef u32 type; };
-template <> struct RawVec<2> { typedef unsigned short type; };
-template <> struct RawVec<1> { typedef u8 type; };
-
-// R consecutive elements of T moved with one load/store of R*sizeof(T) bytes
-template <typename T, int R> union Pack {
-    typename RawVec<R * (int)sizeof(T)>::type raw;
-    T e[R];
-    __device__ __forceinline__ Pack() {}
-};
-template <typename T, int R> __device__ __forceinline__ void ld_pack(Pack<T, R> &p, const T *src) {
-    if constexpr (R * sizeof(T) == 16) p.raw = ld_stream16(src);
-    else p.raw = __ldcs(reinterpret_cast<const typename RawVec<R * (int)sizeof(T)>::type *>(src));
-}
-template <typename T, int R> __device__ __forceinline__ void st_pack(T *dst, const Pack<T, R> &p) {
-    if constexpr (R * sizeof(T) == 16) st_stream16(dst, p.raw);
-    else __stcs(reinterpret_cast<typename RawVec<R * (int)sizeof(T)>::type *>(dst), p.raw);
-}
-
-template <int A, int B> struct MaxI { static constexpr int v = A > B ? A : B; };
-template <bool C, typename A, typename B> struct Sel { typedef A type; };
-template <typename A, typename B> struct Sel<false, A, B> { typedef B type; };
-
-// Generic two-input map.  F: out = f(x, y).  XA / YA: that side is an atom (broadcast), passed by value.
-template <typename X, typename Y, typename O, bool XA, bool YA, typename F>
-__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
-k_map2(const X *__restrict__ x, X xa, const Y *__restrict__ y, Y ya, O *__restrict__ out, i64 n, bool vec_ok, F f) {
-    constexpr int WX = XA ? 1 : (int)sizeof(X), WY = YA ? 1 : (int)sizeof(Y);
-    constexpr int R = 16 / MaxI<MaxI<WX, WY>::v, (int)sizeof(O)>::v;   // rows per lane
-    constexpr int UNROLL = 4;
-    constexpr i64 TILE = (i64)THREADS * UNROLL * R;                     // rows per tile
-    const i64 nvec = vec_ok ? (n / TILE) * TILE : 0;
-    for (i64 base = (i64)blockIdx.x * TILE; base < nvec; base += (i64)gridDim.x * TILE) {
-        typedef typename Sel<XA, u8, X>::type XV;  // an atom side needs no registers: its pack degenerates to bytes
-        typedef typename Sel<YA, u8, Y>::type YV;
-        Pack<XV, R> px[UNROLL];
-        Pack<YV, R> py[UNROLL];
-#pragma unroll
-        for (int j = 0; j < UNROLL; j++) {
-            const i64 r = base + ((i64)j * THREADS + threadIdx.x) * R;
-            if constexpr (!XA) ld_pack<X, R>(px[j], x + r);
-            if constexpr (!YA) ld_pack<Y, R>(py[j], y + r);
-        }
-#pragma unroll
-        for (int j = 0; j < UNROLL; j++) {
-            const i64 r = base + ((i64)j * THREADS + threadIdx.x) * R;
-            Pack<O, R> po;
-#pragma unroll
-            for (int e = 0; e < R; e++) {
-                X a; Y b;
-                if constexpr (XA) a = xa; else a = px[j].e[e];
-                if constexpr (YA) b = ya; else b = py[j].e[e];
-                po.e[e] = f(a, b);
-            }
-            st_pack<O, R>(out + r, po);
-        }
-    }
-    // tail (and everything when a pointer is not 16-byte aligned)
-    for (i64 r = nvec + (i64)blockIdx.x * THREADS + threadIdx.x; r < n; r += (i64)gridDim.x * THREADS)
-        out[r] = f(XA ? xa : ld_stream(x + r), YA ? ya : ld_stream(y + r));
-}
-
-template <typename X, typename O, typename F>
-__global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
-k_map1(const X *__restrict__ x, O *__restrict__ out, i64 n, bool vec_ok, F f) {
-    constexpr int R = 16 / MaxI<(int)sizeof(X), (int)sizeof(O)>::v;
-    constexpr int UNROLL = 8;
-    constexpr i64 TILE = (i64)THREADS * UNROLL * R;
-    const i64 nvec = vec_ok ? (n / TILE) * TILE : 0;
-    for (i64 base = (i64)blockIdx.x * TILE; base < nvec; base += (i64)gridDim.x * TILE) {
-        Pack<X, R> px[UNROLL];
-#pragma unroll
-        for (int j = 0; j < UNROLL; j++) ld_pack<X, R>(px[j], x + base + ((i64)j * THREADS + threadIdx.x) * R);
-#pragma unroll
-        for (int j = 0; j < UNROLL; j++) {
-            Pack<O, R> po;
-#pragma unroll
-            for (int e = 0; e < R; e++) po.e[e] = f(px[j].e[e]);
-            st_pack<O, R>(out + base + ((i64)j * THREADS + threadIdx.x) * R, po);
-        }
-    }
-    for (i64 r = nvec + (i64)blockIdx.x * THREADS + threadIdx.x; r < n; r += (i64)gridDim.x * THREADS) out[r] = f(ld_stream(x + r));
-}
-
-
-template <typename X, typename Y, typename O, bool XA, bool YA, typename F>
-int launch_map2(rfb_ctx_t *ctx, const void *x, X xa, const void *y, Y ya, void *out, i64 n, F f) {
-    if (n == 0) return RFB_OK;
-    const bool vec_ok = (XA || aligned16(x)) && (YA || aligned16(y)) && aligned16(out);
-    const int grid = rfb_grid_for(ctx, n, THREADS * 8, BLOCKS_PER_SM);
-    k_map2<X, Y, O, XA, YA, F><<<grid, THREADS, 0, ctx->stream>>>((const X *)x, xa, (const Y *)y, ya, (O *)out, n, vec_ok, f);
-    RFB_CHECK_LAUNCH(ctx);
-    return RFB_OK;
-}
 
 // ------------------------------------------------------------------ comparisons
 
@@ -259,86 +158,6 @@ extern "C" int rfb_cmp_dev(rfb_ctx_t *ctx, int op, int xt, const void *x, int64_
 // ------------------------------------------------------------------ arithmetic
 
 namespace {
-
-// null-propagating scalar ops in each computation type (core/ops.h:153-177)
-__device__ __forceinline__ i64 eucl_div64(i64 x, i64 y) {
-    if (y == -1) return (i64)(0 - (u64)x);
-    const i64 q = x / y, r = x - q * y;
-    return q - ((((x < 0) != (y < 0)) && r != 0) ? 1 : 0);
-}
-__device__ __forceinline__ i32 eucl_div32(i32 x, i32 y) {
-    if (y == -1) return (i32)(0 - (u32)x);
-    const i32 q = x / y, r = x - q * y;
-    return q - ((((x < 0) != (y < 0)) && r != 0) ? 1 : 0);
-}
-__device__ __forceinline__ i32 op_i32(int op, i32 x, i32 y) {
-    if (x == NULL_I32 || y == NULL_I32) return NULL_I32;
-    switch (op) {
-        case RFB_ADD: return (i32)((u32)x + (u32)y);
-        case RFB_SUB: return (i32)((u32)x - (u32)y);
-        case RFB_MUL: return (i32)((u32)x * (u32)y);
-        case RFB_DIV: return y == 0 ? NULL_I32 : eucl_div32(x, y);
-        case RFB_XBAR: {  // XBARI32 (core/ops.h:193-194): C truncating division of the shifted value
-            if (y == 0) return NULL_I32;
-            const i32 t = x < 0 ? (i32)((u32)x + 1u - (u32)y) : x;
-            return (i32)((u32)(y == -1 ? (i32)(0u - (u32)t) : t / y) * (u32)y);
-        }
-        default: return y == 0 ? NULL_I32 : (i32)((u32)x - (u32)eucl_div32(x, y) * (u32)y);
-    }
-}
-__device__ __forceinline__ i64 op_i64(int op, i64 x, i64 y) {
-    if (x == NULL_I64 || y == NULL_I64) return NULL_I64;
-    switch (op) {
-        case RFB_ADD: return (i64)((u64)x + (u64)y);
-        case RFB_SUB: return (i64)((u64)x - (u64)y);
-        case RFB_MUL: return (i64)((u64)x * (u64)y);
-        case RFB_DIV: return y == 0 ? NULL_I64 : eucl_div64(x, y);
-        case RFB_XBAR: {  // XBARI64 (core/ops.h:195-196)
-            if (y == 0) return NULL_I64;
-            const i64 t = x < 0 ? (i64)((u64)x + 1ULL - (u64)y) : x;
-            return (i64)((u64)(y == -1 ? (i64)(0ULL - (u64)t) : t / y) * (u64)y);
-        }
-        default: return y == 0 ? NULL_I64 : (i64)((u64)x - (u64)eucl_div64(x, y) * (u64)y);
-    }
-}
-__device__ __forceinline__ i64 f64_to_i64(f64 x);
-// plain IEEE ops, never contracted into FMAs: the reference materialises every intermediate
-__device__ __forceinline__ f64 op_f64(int op, f64 x, f64 y) {
-    if (isnan64(x) || isnan64(y)) return null_f64();
-    switch (op) {
-        case RFB_ADD: return __dadd_rn(x, y);
-        case RFB_SUB: return __dsub_rn(x, y);
-        case RFB_MUL: return __dmul_rn(x, y);
-        case RFB_DIV: return y == 0.0 ? null_f64() : floor(__ddiv_rn(x, y));
-        case RFB_XBAR: {  // XBARF64 = FLOORF64(x / y) * y (core/ops.h:197,191): floor through an (i64) cast
-            if (y == 0.0) return null_f64();   // the compiled reference yields NaN (inf * 0) for a zero bucket width
-            const f64 q = __ddiv_rn(x, y);
-            if (isnan64(q)) return null_f64();
-            const f64 t = (f64)f64_to_i64(q);
-            return __dmul_rn((q < 0.0 && t != q) ? __dsub_rn(t, 1.0) : t, y);
-        }
-        default: return y == 0.0 ? null_f64() : __dsub_rn(x, __dmul_rn(floor(__ddiv_rn(x, y)), y));
-    }
-}
-__device__ __forceinline__ f64 op_fdiv(bool left_is_int, f64 x, f64 y) {
-    if (left_is_int) {  // FDIVI64 applied to converted doubles (core/ops.h:173): null test against (double)INT64_MIN
-        const f64 nul = -9223372036854775808.0;
-        if (y == 0.0 || x == nul || y == nul || isnan64(y)) return null_f64();
-        return __ddiv_rn(x, y);
-    }
-    if (y == 0.0 || isnan64(x) || isnan64(y)) return null_f64();
-    return __ddiv_rn(x, y);
-}
-// f64 -> integer with the x86 cvttsd2si behaviour the reference compiles to: NaN / out of range -> INT_MIN (= null)
-__device__ __forceinline__ i64 f64_to_i64(f64 x) {
-    if (isnan64(x) || !(x > -9223372036854775808.0 && x < 9223372036854775808.0)) return NULL_I64;
-    return (i64)x;
-}
-__device__ __forceinline__ i32 f64_to_i32(f64 x) {
-    if (isnan64(x) || !(x > -2147483649.0 && x < 2147483648.0)) return NULL_I32;
-    return (i32)x;
-}
-__device__ __forceinline__ i32 i64_to_i32(i64 x) { return x == NULL_I64 ? NULL_I32 : (i32)x; }
 
 template <typename M> struct Conv;  // widen an operand into computation type M
 template <> struct Conv<i32> { template <typename T> __device__ __forceinline__ static i32 of(T v) { return (i32)v; } };
@@ -488,207 +307,17 @@ int binop_x(rfb_ctx_t *ctx, int op, int mt, int ot, int yt, bool lii, const void
     }
 }
 
-// ---- the full type matrix (B8 / U8 / I16 / DATE / TIME / TIMESTAMP operands).  Every case of ray_add_partial .. ray_xbar_partial
-// (core/math.c:251-1782) has the shape  out[i] = mt_to_ot(OP(lt_to_mt(x[i]), rt_to_mt(y[i])))  (core/math.c:55-90); binop_matrix.inc
-// (tools/gen_binop_matrix.py) lists (lt, rt, ot, mt, OP family) per (operator, form, operand types) and the element type
-// binop_map gives the result vector (infer_*_type, core/math.c:92-249).  One kernel per STORAGE triple (22 of them); the
-// conversions (core/ops.h:218-277) are folded on the host into a null pair + unit scale + width per operand, and the operator
-// family / operator are warp-uniform switches — the kernels stay HBM streams.
-struct BinCase { signed char op, form, xt, yt, lt, rt, ot, mt, fam, vt; int line; };
-const BinCase BINOP_CASES[] = {
-#include "binop_matrix.inc"
-};
-const BinCase *binop_case(int op, int form, int xt, int yt) {
-    for (const BinCase &c : BINOP_CASES)
-        if (c.op == op && c.form == form && c.xt == xt && c.yt == yt) return &c;
-    return nullptr;
-}
+}  // namespace
+
+namespace {
 inline bool plain_num(int t) { return t == RFB_I32 || t == RFB_I64 || t == RFB_F64; }
-inline int null_width(int kind) {      // 0: no null (B8 / U8), else the width of the integer whose minimum is the null
-    switch (kind) {
-        case RFB_I16: return 16;
-        case RFB_I32: case RFB_DATE: case RFB_TIME: return 32;
-        case RFB_I64: case RFB_TIMESTAMP: return 64;
-        default: return 0;
-    }
-}
-inline i64 null_of_width(int w) { return w == 16 ? (i64)NULL_I16 : w == 32 ? (i64)NULL_I32 : NULL_I64; }
-
-struct InConv {          // <from>_to_<mt> for an integer source
-    i64 src_null, dst_null, scale;
-    int has_null, is_b8, width;        // width of mt: 8 (u8) / 16 / 32 / 64; 0 = mt is F64
-};
-__device__ __forceinline__ i64 narrow_to(i64 v, int width) {
-    switch (width) {
-        case 8: return (i64)(u8)v;
-        case 16: return (i64)(i16)v;
-        case 32: return (i64)(i32)v;
-        default: return v;
-    }
-}
-struct TypedBinOp {
-    int op, fam, mt_f64, fdiv_int;     // fdiv_int: FDIVI64 applied to converted doubles (core/ops.h:173)
-    InConv cx, cy;
-    i64 mt_null, ot_null;              // integer mt -> integer ot
-    int mt_has_null, ot_width, ot_b8;  // ot_width 0 = ot is F64
-    template <typename T> __device__ __forceinline__ void in(const InConv &c, T raw, i64 &iv, f64 &fv) const {
-        if constexpr (Elem<T>::kind == K_F64) { fv = raw; iv = 0; }     // an F64 operand only ever meets an F64 mt
-        else {
-            i64 v = (i64)raw;
-            if (c.is_b8) v = (v != 0);
-            const bool nul = c.has_null && v == c.src_null;
-            if (c.width == 0) { fv = nul ? null_f64() : (f64)v; iv = 0; }
-            else { iv = nul ? c.dst_null : narrow_to((i64)((u64)v * (u64)c.scale), c.width); fv = 0.0; }
-        }
-    }
-    template <typename X, typename Y, typename O> __device__ __forceinline__ O apply(X a, Y b) const {
-        i64 xi, yi; f64 xf, yf;
-        in(cx, a, xi, xf);
-        in(cy, b, yi, yf);
-        if (mt_f64) {
-            const f64 r = op == RFB_FDIV ? op_fdiv(fdiv_int != 0, xf, yf) : op_f64(op, xf, yf);
-            if constexpr (Elem<O>::kind == K_F64) return r;
-            else if constexpr (sizeof(O) == 8) return (O)f64_to_i64(r);
-            else return (O)f64_to_i32(r);
-        }
-        i64 r;
-        switch (fam) {
-            case RFB_U8: {             // core/ops.h:125-130: no nulls, x / 0 = 0
-                const u32 x = (u32)(u8)xi, y = (u32)(u8)yi;
-                switch (op) {
-                    case RFB_ADD: r = (u8)(x + y); break;
-                    case RFB_SUB: r = (u8)(x - y); break;
-                    case RFB_MUL: r = (u8)(x * y); break;
-                    case RFB_DIV: r = y == 0 ? 0 : (u8)(x / y); break;
-                    default: r = y == 0 ? 0 : (u8)(x % y); break;
-                }
-                break;
-            }
-            case RFB_I16: {            // core/ops.h:136-140: computed in int, narrowed
-                const i32 x = (i32)xi, y = (i32)yi;
-                if (x == NULL_I16 || y == NULL_I16) { r = NULL_I16; break; }
-                switch (op) {
-                    case RFB_ADD: r = (i16)(x + y); break;
-                    case RFB_SUB: r = (i16)(x - y); break;
-                    case RFB_MUL: r = (i16)(x * y); break;
-                    case RFB_DIV: r = y == 0 ? (i64)NULL_I16 : (i64)(i16)eucl_div32(x, y); break;
-                    default: r = y == 0 ? (i64)NULL_I16 : (i64)(i16)(x - eucl_div32(x, y) * y); break;
-                }
-                break;
-            }
-            case RFB_I32: r = (i64)op_i32(op, (i32)xi, (i32)yi); break;
-            default: r = op_i64(op, xi, yi); break;
-        }
-        if constexpr (Elem<O>::kind == K_F64) return (O)0;   // integer mt with an F64 result does not occur in the matrix
-        else {
-            if (ot_b8) return (O)(r != 0 && r != NULL_I64);
-            if (mt_has_null && r == mt_null) return (O)ot_null;
-            return (O)r;                                      // narrowing store = the reference's (i32_t) / (i16_t) cast
-        }
-    }
-};
-
-// X, Y, O: storage types.  An atom side (xp / yp == nullptr) is broadcast from xa / ya.
-template <typename X, typename Y, typename O>
-__global__ void __launch_bounds__(THREADS, 2)       // 128 registers: the warp-uniform switches do not spill; 2 x 256 threads x 4 x 16 B per operand in flight
-k_binop_typed(const X *__restrict__ xp, X xa, const Y *__restrict__ yp, Y ya, O *__restrict__ out, i64 n, bool vec_ok, TypedBinOp f) {
-    constexpr int R = 16 / MaxI<MaxI<(int)sizeof(X), (int)sizeof(Y)>::v, (int)sizeof(O)>::v;
-    constexpr int UNROLL = 4;
-    constexpr i64 TILE = (i64)THREADS * UNROLL * R;
-    const i64 nvec = vec_ok ? (n / TILE) * TILE : 0;
-    for (i64 base = (i64)blockIdx.x * TILE; base < nvec; base += (i64)gridDim.x * TILE) {
-        Pack<X, R> px[UNROLL];
-        Pack<Y, R> py[UNROLL];
-#pragma unroll
-        for (int j = 0; j < UNROLL; j++) {
-            const i64 r = base + ((i64)j * THREADS + threadIdx.x) * R;
-            if (xp) ld_pack<X, R>(px[j], xp + r);
-            if (yp) ld_pack<Y, R>(py[j], yp + r);
-        }
-#pragma unroll
-        for (int j = 0; j < UNROLL; j++) {
-            const i64 r = base + ((i64)j * THREADS + threadIdx.x) * R;
-            Pack<O, R> po;
-#pragma unroll
-            for (int e = 0; e < R; e++) po.e[e] = f.template apply<X, Y, O>(xp ? px[j].e[e] : xa, yp ? py[j].e[e] : ya);
-            st_pack<O, R>(out + r, po);
-        }
-    }
-    for (i64 r = nvec + (i64)blockIdx.x * THREADS + threadIdx.x; r < n; r += (i64)gridDim.x * THREADS)
-        out[r] = f.template apply<X, Y, O>(xp ? ld_stream(xp + r) : xa, yp ? ld_stream(yp + r) : ya);
-}
-
-InConv in_conv(int from, int mt) {
-    InConv c;
-    c.is_b8 = from == RFB_B8;
-    c.has_null = null_width(from) != 0;
-    c.src_null = c.has_null ? null_of_width(null_width(from)) : 0;
-    c.width = mt == RFB_F64 ? 0 : (null_width(mt) ? null_width(mt) : 8);
-    c.dst_null = null_width(mt) ? null_of_width(null_width(mt)) : 0;
-    c.scale = (from == RFB_DATE && mt == RFB_TIMESTAMP) ? 86400000000000LL          // date_to_timestamp, core/ops.h:264
-              : (from == RFB_TIME && mt == RFB_TIMESTAMP) ? 1000000LL : 1;          // time_to_timestamp, core/ops.h:269
-    return c;
-}
-template <typename T> T scalar_raw(const rfb_scalar_t *s) {      // the atom's payload read at the operand's storage width
-    if (!s) return T();
-    if constexpr (Elem<T>::kind == K_F64) return s->v.f64;
-    else if constexpr (sizeof(T) == 8) return (T)s->v.i64;
-    else if constexpr (sizeof(T) == 4) return (T)s->v.i32;
-    else if constexpr (sizeof(T) == 2) return (T)s->v.i16;
-    else return (T)s->v.u8;
-}
-template <typename X, typename Y, typename O>
-int launch_typed(rfb_ctx_t *ctx, const TypedBinOp &f, const void *x, i64 xn, const rfb_scalar_t *xs, const void *y, i64 yn,
-                 const rfb_scalar_t *ys, void *out) {
-    const i64 n = xn >= 0 ? xn : yn;
-    if (n == 0) return RFB_OK;
-    const X *xp = xn >= 0 ? (const X *)x : nullptr;
-    const Y *yp = yn >= 0 ? (const Y *)y : nullptr;
-    const bool vec_ok = (!xp || aligned16(xp)) && (!yp || aligned16(yp)) && aligned16(out);
-    const int grid = rfb_grid_for(ctx, n, THREADS * 8, 2);
-    k_binop_typed<X, Y, O><<<grid, THREADS, 0, ctx->stream>>>(xp, xn >= 0 ? X() : scalar_raw<X>(xs), yp, yn >= 0 ? Y() : scalar_raw<Y>(ys),
-                                                              (O *)out, n, vec_ok, f);
-    RFB_CHECK_LAUNCH(ctx);
-    return RFB_OK;
-}
-inline int storage_code(int kind) {    // 1 u8, 2 i16, 3 i32, 4 i64, 5 f64
-    switch (rfb_kind_of(kind)) { case K_U8: return 1; case K_I16: return 2; case K_I32: return 3; case K_I64: return 4; default: return 5; }
-}
-int binop_matrix(rfb_ctx_t *ctx, const BinCase &c, const void *x, i64 xn, const rfb_scalar_t *xs, const void *y, i64 yn,
-                 const rfb_scalar_t *ys, void *out) {
-    TypedBinOp f;
-    f.op = c.op; f.fam = c.fam; f.mt_f64 = c.mt == RFB_F64; f.fdiv_int = c.fam == RFB_I64;
-    f.cx = in_conv(c.lt, c.mt); f.cy = in_conv(c.rt, c.mt);
-    f.mt_has_null = null_width(c.mt) != 0;
-    f.mt_null = f.mt_has_null ? null_of_width(null_width(c.mt)) : 0;
-    f.ot_width = c.ot == RFB_F64 ? 0 : (null_width(c.ot) ? null_width(c.ot) : 8);
-    f.ot_null = null_width(c.ot) ? null_of_width(null_width(c.ot)) : 0;
-    f.ot_b8 = c.ot == RFB_B8;
-    if ((c.mt == RFB_TIMESTAMP && (c.ot == RFB_DATE || c.ot == RFB_TIME)) || (c.mt != RFB_F64 && c.ot == RFB_F64) ||
-        (c.mt != RFB_F64 && (c.lt == RFB_F64 || c.rt == RFB_F64))) {
-        rfb_set_error("binop: conversion of case core/math.c:%d is not built", c.line);
-        return RFB_ERR_TYPE;
-    }
-#define TYPED(SX, SY, SO, X, Y, O) \
-    if (sx == SX && sy == SY && so == SO) return launch_typed<X, Y, O>(ctx, f, x, xn, xs, y, yn, ys, out);
-    const int sx = storage_code(c.lt), sy = storage_code(c.rt), so = storage_code(c.ot);
-    TYPED(5, 2, 5, f64, i16, f64) TYPED(5, 1, 5, f64, u8, f64) TYPED(2, 5, 5, i16, f64, f64) TYPED(2, 2, 2, i16, i16, i16)
-    TYPED(2, 3, 3, i16, i32, i32) TYPED(2, 4, 4, i16, i64, i64) TYPED(3, 5, 3, i32, f64, i32) TYPED(3, 2, 3, i32, i16, i32)
-    TYPED(3, 3, 3, i32, i32, i32) TYPED(3, 3, 4, i32, i32, i64) TYPED(3, 4, 3, i32, i64, i32) TYPED(3, 4, 4, i32, i64, i64)
-    TYPED(3, 1, 3, i32, u8, i32) TYPED(4, 2, 4, i64, i16, i64) TYPED(4, 3, 3, i64, i32, i32) TYPED(4, 3, 4, i64, i32, i64)
-    TYPED(4, 4, 4, i64, i64, i64) TYPED(4, 1, 4, i64, u8, i64) TYPED(1, 5, 5, u8, f64, f64) TYPED(1, 3, 3, u8, i32, i32)
-    TYPED(1, 4, 4, u8, i64, i64) TYPED(1, 1, 1, u8, u8, u8)
-#undef TYPED
-    rfb_set_error("binop: no kernel for the storage widths of case core/math.c:%d", c.line);
-    return RFB_ERR_TYPE;
-}
-
+inline bool is_i64_like(int t) { return t == RFB_I64 || t == RFB_TIMESTAMP; }
 }  // namespace
 
 // result vector type per operand form (0 vector-vector, 1 vector-atom, 2 atom-vector) over the reference's full type matrix
 extern "C" int rfb_binop_type_form(int op, int form, int xt, int yt) {
     if (plain_num(xt) && plain_num(yt)) return rfb_binop_type(op, xt, yt);
-    const BinCase *c = binop_case(op, form, xt, yt);
+    const rfb_bincase_t *c = rfb_binop_case(op, form, xt, yt);
     return c ? c->vt : RFB_ERR_TYPE;
 }
 
@@ -703,14 +332,14 @@ extern "C" int rfb_binop_dev(rfb_ctx_t *ctx, int op, int xt, const void *x, int6
     int mt, ot;
     if (!(plain_num(xt) && plain_num(yt))) {       // the full type matrix
         if (xn < 0 && yn < 0) { rfb_set_error("binop: both operands are atoms; the operator layer folds constants on the host"); return RFB_ERR_ARG; }
-        const BinCase *c = binop_case(op, xn >= 0 ? (yn >= 0 ? 0 : 1) : 2, xt, yt);
+        const rfb_bincase_t *c = rfb_binop_case(op, xn >= 0 ? (yn >= 0 ? 0 : 1) : 2, xt, yt);
         if (!c) { rfb_set_error("binop %d: unsupported operand types %d, %d", op, xt, yt); return RFB_ERR_TYPE; }
         if (xn >= 0 && yn >= 0 && xn != yn) { rfb_set_error("binop: vector lengths differ (%lld vs %lld)", (long long)xn, (long long)yn); return RFB_ERR_LENGTH; }
         RFB_ARG((xn >= 0 ? (x || xn == 0) : xs != nullptr) && (yn >= 0 ? (y || yn == 0) : ys != nullptr), "rfb_binop_dev: operands");
         RFB_ARG(out || (xn >= 0 ? xn : yn) == 0, "rfb_binop_dev: out");
         if ((xn < 0 && xs->type != xt) || (yn < 0 && ys->type != yt)) { rfb_set_error("binop: scalar type tag does not match operand type"); return RFB_ERR_ARG; }
-        if (c->form == 1 && c->fam == RFB_I64 && null_width(c->lt) == 64 && null_width(c->rt) == 64 && null_width(c->mt) == 64 &&
-            null_width(c->ot) == 64 && (op == RFB_DIV || op == RFB_MOD || op == RFB_XBAR)) {
+        if (c->form == 1 && c->fam == RFB_I64 && is_i64_like(c->lt) && is_i64_like(c->rt) && is_i64_like(c->mt) && is_i64_like(c->ot) &&
+            (op == RFB_DIV || op == RFB_MOD || op == RFB_XBAR)) {
             const i64 d = ys->v.i64;   // timestamp xbar / div / mod by a constant: the same 64-bit kernel as i64 by an atom
             if (d != 0 && d != NULL_I64 && d != 1 && d != -1) {
                 const u64 ad = d < 0 ? 0ULL - (u64)d : (u64)d;
@@ -718,7 +347,7 @@ extern "C" int rfb_binop_dev(rfb_ctx_t *ctx, int op, int xt, const void *x, int6
                 return launch_map2<i64, i64, i64, false, true>(ctx, x, i64(), nullptr, d, out, xn, f);
             }
         }
-        return binop_matrix(ctx, *c, x, xn, xs, y, yn, ys, out);
+        return rfb_binop_matrix_dev(ctx, *c, x, xn, xs, y, yn, ys, out);
     }
     if (!binop_types(op, xt, yt, &mt, &ot)) { rfb_set_error("binop %d: unsupported operand types %d, %d", op, xt, yt); return RFB_ERR_TYPE; }
     if (xn >= 0 && yn >= 0 && xn != yn) { rfb_set_error("binop: vector lengths differ (%lld vs %lld)", (long long)xn, (long long)yn); return RFB_ERR_LENGTH; }

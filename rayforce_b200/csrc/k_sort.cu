@@ -286,8 +286,285 @@ int run_pass(rfb_ctx_t *ctx, Src src, i64 n, int G, i64 chunk, int shift, u32 *b
     return RFB_OK;
 }
 
+// =====================================================================================================================
+// Single-sweep passes ("onesweep"): what sorts run on for n < 2^32 rows.
+//   k_os_hist   ONE read of the typed column: the 256-bin histogram of every key byte (global digit counts of all passes).
+//   k_os_scan   exclusive scan per pass -> where each digit's run starts in that pass's output.
+//   k_os_pass   per executed pass: tiles are claimed in order from an atomic counter; a tile ranks its rows (ballot multisplit),
+//               publishes its 256 digit counts as (tag | AGGREGATE | count) words, resolves its exclusive prefix per digit by
+//               decoupled look-back over the preceding tiles' words (thread d chases digit d) while the other warps already
+//               order the tile by digit in shared memory, publishes (INCLUSIVE | prefix + count) and streams the tile out as
+//               one contiguous run per digit.  No per-pass histogram kernel, no (256 x chunks) offset matrix: a pass reads
+//               its input once.  Tiles leave in tile order within a digit and rows keep their order inside a tile => stable.
+// Row ids travel as 32-bit words between passes (12 B per row moved instead of 16); the last pass widens them into `perm`.
+// A pass whose digit is constant over the column (one histogram bin holds every row) is skipped, as before.
+// Per executed pass: 12N read + 12N written (first pass: sizeof(T) N read; last pass: 8N written).
+#ifndef RFB_OS_ITEMS
+#define RFB_OS_ITEMS 16
+#define RFB_OS_CTAS 3
+#endif
+constexpr int OS_T = 256, OS_W = OS_T / 32, OS_ITEMS = RFB_OS_ITEMS, OS_TILE = OS_T * OS_ITEMS;
+constexpr u64 OS_AGG = 1ULL << 54, OS_INC = 2ULL << 54, OS_FLAGS = 3ULL << 54, OS_COUNT = (1ULL << 54) - 1;
+
+template <typename T> struct OsColumnSrc {      // first pass: the typed column; the row id is the row number
+    const T *col;
+    u64 flip;
+    __device__ __forceinline__ u64 key(i64 i) const { return sortable<T>(ld_stream(col + i)) ^ flip; }
+    __device__ __forceinline__ u32 rid(i64 i) const { return (u32)i; }
+};
+struct OsPairSrc {                              // later passes: the previous pass's (key, 32-bit row id) pairs
+    const u64 *keys;
+    const u32 *rids;
+    __device__ __forceinline__ u64 key(i64 i) const { return ld_stream(keys + i); }
+    __device__ __forceinline__ u32 rid(i64 i) const { return ld_stream(rids + i); }
+};
+
 template <typename T>
-int sort_t(rfb_ctx_t *ctx, const void *x, i64 n, int descending, i64 *perm) {
+__global__ void __launch_bounds__(THREADS, 4) k_os_hist(OsColumnSrc<T> src, i64 n, unsigned long long *ghist /* [NPASS][256] */) {
+    constexpr int NPASS = (int)sizeof(T);
+    __shared__ u32 h[NPASS][RADIX];
+    for (int i = threadIdx.x; i < NPASS * RADIX; i += THREADS) (&h[0][0])[i] = 0;
+    __syncthreads();
+    constexpr int U = 4;
+    const i64 stride = (i64)gridDim.x * THREADS;
+    // whole warps stay in the loop (the votes below need all 32 lanes): iterate on the warp's first row
+    for (i64 w0 = (i64)blockIdx.x * THREADS + (threadIdx.x & ~31); w0 < n; w0 += U * stride) {
+        u64 k[U];
+        bool ok[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const i64 i = w0 + j * stride + (threadIdx.x & 31);
+            ok[j] = i < n;
+            k[j] = ok[j] ? src.key(i) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+#pragma unroll
+            for (int p = 0; p < NPASS; p++) {
+                const u32 d = (u32)(k[j] >> (8 * p)) & 255u;
+                // a byte that is the same in all 32 rows (the upper bytes of small integers) would be a 32-way same-address atomic
+                const u32 d0 = __shfl_sync(0xffffffffu, d, 0);
+                if (__all_sync(0xffffffffu, ok[j] && d == d0)) { if ((threadIdx.x & 31) == 0) atomicAdd(&h[p][d], 32u); }
+                else if (ok[j]) atomicAdd(&h[p][d], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NPASS * RADIX; i += THREADS) {
+        const u32 c = (&h[0][0])[i];
+        if (c) atomicAdd(&ghist[i], (unsigned long long)c);
+    }
+}
+
+__global__ void __launch_bounds__(RADIX) k_os_scan(const unsigned long long *ghist, i64 *gbase) {
+    __shared__ i64 wtot[RADIX / 32];
+    const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
+    const i64 c = (i64)ghist[blockIdx.x * RADIX + d];
+    i64 incl = c;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) {
+        const i64 o = __shfl_up_sync(0xffffffffu, incl, k);
+        if (lane >= k) incl += o;
+    }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    i64 woff = 0;
+    for (int w = 0; w < warp; w++) woff += wtot[w];
+    gbase[blockIdx.x * RADIX + d] = woff + incl - c;
+}
+
+template <typename Src, bool LAST>
+__global__ void __launch_bounds__(OS_T, RFB_OS_CTAS)
+k_os_pass(Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *__restrict__ gbase /* [256] */, unsigned long long *__restrict__ status /* [tiles][256] */,
+          u32 *__restrict__ tile_counter, u64 *__restrict__ keys_out, u32 *__restrict__ rids_out, i64 *__restrict__ perm_out) {
+    __shared__ u32 whist[OS_W][RADIX];
+    __shared__ i64 base[RADIX];     // output slot of the tile-local position 0 of each digit's run
+    __shared__ u32 dstart[RADIX];
+    __shared__ u32 wsum[RADIX / 32];
+    __shared__ u32 s_tile;
+    extern __shared__ u64 stage_dyn[];            // OS_TILE keys then OS_TILE 32-bit row ids
+    u64 *skeys = stage_dyn;
+    u32 *srids = (u32 *)(stage_dyn + OS_TILE);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lt = (1u << lane) - 1u;
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+        for (int idx = threadIdx.x; idx < OS_W * RADIX; idx += OS_T) (&whist[0][0])[idx] = 0;
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= tiles) break;
+        const i64 t0 = (i64)tile * OS_TILE;
+        const i64 wb = t0 + (i64)warp * (32 * OS_ITEMS);
+        u64 key[OS_ITEMS];
+#pragma unroll
+        for (int j = 0; j < OS_ITEMS; j++) {
+            const i64 i = wb + j * 32 + lane;
+            key[j] = i < n ? src.key(i) : ~0ULL;
+        }
+        u32 rid[OS_ITEMS];
+#pragma unroll
+        for (int j = 0; j < OS_ITEMS; j++) {
+            const i64 i = wb + j * 32 + lane;
+            rid[j] = i < n ? src.rid(i) : 0u;
+        }
+        // rank of a row among the rows of its warp with the same digit, in (step, lane) order: the lanes holding the same digit
+        // come from eight ballots; the lowest of them adds the group's size to the warp's counter with a returning atomic (the
+        // counter's value before = rows of that digit in earlier steps) and hands the answer to its peers with a shuffle
+        u32 rank[OS_ITEMS];
+#pragma unroll
+        for (int j = 0; j < OS_ITEMS; j++) {
+            const i64 i = wb + j * 32 + lane;
+            const bool ok = i < n;
+            const u32 d = (u32)(key[j] >> shift) & 255u;
+            u32 peers = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const bool bit = (d >> b) & 1u;
+                const u32 bal = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? bal : ~bal;
+            }
+            const int leader = ok ? __ffs(peers) - 1 : lane;
+            u32 prior = 0;
+            if (ok && lane == leader) prior = atomicAdd(&whist[warp][d], (u32)__popc(peers));
+            prior = __shfl_sync(0xffffffffu, prior, leader);
+            rank[j] = prior + __popc(peers & lt);
+        }
+        __syncthreads();
+        // thread d: digit d's counts over the warps -> exclusive warp offsets, tile count, tile-local start of the digit's run
+        const int d = threadIdx.x;
+        u32 cnt = 0;
+#pragma unroll
+        for (int w = 0; w < OS_W; w++) { const u32 c = whist[w][d]; whist[w][d] = cnt; cnt += c; }
+        u32 incl = cnt;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const u32 o = __shfl_up_sync(0xffffffffu, incl, k);
+            if (lane >= k) incl += o;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        unsigned long long *mine = status + (size_t)tile * RADIX + d;
+        *(volatile unsigned long long *)mine = tag | (tile == 0 ? OS_INC : OS_AGG) | (u64)cnt;
+        __syncthreads();
+        u32 woff = 0;
+#pragma unroll
+        for (int w = 0; w < RADIX / 32; w++) woff += (w < warp) ? wsum[w] : 0u;
+        const u32 ds = woff + incl - cnt;
+        dstart[d] = ds;
+        __syncthreads();
+        // order the tile by digit in shared memory ...
+#pragma unroll
+        for (int j = 0; j < OS_ITEMS; j++) {
+            const i64 i = wb + j * 32 + lane;
+            if (i < n) {
+                const u32 dj = (u32)(key[j] >> shift) & 255u;
+                const u32 lp = dstart[dj] + whist[warp][dj] + rank[j];
+                skeys[lp] = key[j];
+                srids[lp] = rid[j];
+            }
+        }
+        // ... then resolve digit d's exclusive prefix over the preceding tiles (their words have had the whole ordering step to land)
+        u64 excl = 0;
+        if (tile > 0) {
+            const volatile unsigned long long *st = status + (size_t)(tile - 1) * RADIX + d;
+            for (;;) {
+                const u64 v = *st;
+                if ((v & ~(OS_FLAGS | OS_COUNT)) != tag || (v & OS_FLAGS) == 0) continue;     // not published in this pass yet
+                excl += v & OS_COUNT;
+                if ((v & OS_FLAGS) == OS_INC) break;
+                st -= RADIX;
+            }
+            *(volatile unsigned long long *)mine = tag | OS_INC | (excl + cnt);
+        }
+        base[d] = gbase[d] + (i64)excl - (i64)ds;
+        __syncthreads();
+        const int tile_n = (int)((n - t0) < OS_TILE ? (n - t0) : OS_TILE);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < tile_n; i += OS_T) {
+            const u64 k = skeys[i];
+            const i64 pos = base[(u32)(k >> shift) & 255u] + i;
+            if (LAST) perm_out[pos] = (i64)srids[i];
+            else { keys_out[pos] = k; rids_out[pos] = srids[i]; }
+        }
+        // the next round's first barrier (after whist is zeroed) also orders these reads of the stage before its next writes
+    }
+}
+
+template <typename Src>
+int os_run_pass(rfb_ctx_t *ctx, Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *gbase, unsigned long long *status, u32 *counter,
+                u64 *keys_out, u32 *rids_out, i64 *perm_out, bool last) {
+    constexpr int STAGE_BYTES = OS_TILE * 12;
+    static bool opted_in = false;   // per template instantiation
+    if (!opted_in) {
+        RFB_CUDA(cudaFuncSetAttribute(k_os_pass<Src, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
+        RFB_CUDA(cudaFuncSetAttribute(k_os_pass<Src, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
+        opted_in = true;
+    }
+    const u32 resident = (u32)ctx->sm_count * RFB_OS_CTAS;
+    const u32 grid = tiles < resident ? tiles : resident;
+    if (last) k_os_pass<Src, true><<<grid, OS_T, STAGE_BYTES, ctx->stream>>>(src, n, tiles, shift, tag, gbase, status, counter, keys_out, rids_out, perm_out);
+    else k_os_pass<Src, false><<<grid, OS_T, STAGE_BYTES, ctx->stream>>>(src, n, tiles, shift, tag, gbase, status, counter, keys_out, rids_out, perm_out);
+    RFB_CHECK_LAUNCH(ctx);
+    return RFB_OK;
+}
+
+template <typename T>
+int sort_onesweep(rfb_ctx_t *ctx, const void *x, i64 n, int descending, i64 *perm) {
+    constexpr int NPASS = (int)sizeof(T);
+    const u64 width_mask = NPASS == 8 ? ~0ULL : ((1ULL << (8 * NPASS)) - 1);
+    OsColumnSrc<T> col{(const T *)x, descending ? width_mask : 0ULL};
+    const u32 tiles = (u32)((n + OS_TILE - 1) / OS_TILE);
+    // workspace: ghist[8][256] u64 | gbase[8][256] i64 | counters[8] u32 | status[tiles][256] u64 | keysA[n] | keysB[n] | ridsA[n] | ridsB[n]
+    const size_t b_hist = 8 * RADIX * 8, b_base = 8 * RADIX * 8, b_cnt = 256, b_status = align256((size_t)tiles * RADIX * 8),
+                 b_k = align256((size_t)n * 8), b_r = align256((size_t)n * 4);
+    void *w;
+    int rc = rfb_ensure_work(ctx, b_hist + b_base + b_cnt + b_status + 2 * b_k + 2 * b_r, &w);
+    if (rc) return rc;
+    char *p = (char *)w;
+    unsigned long long *ghist = (unsigned long long *)p; p += b_hist;
+    i64 *gbase = (i64 *)p; p += b_base;
+    u32 *counters = (u32 *)p; p += b_cnt;
+    unsigned long long *status = (unsigned long long *)p; p += b_status;
+    u64 *keysA = (u64 *)p; p += b_k;
+    u64 *keysB = (u64 *)p; p += b_k;
+    u32 *ridsA = (u32 *)p; p += b_r;
+    u32 *ridsB = (u32 *)p;
+    RFB_CUDA(cudaMemsetAsync(w, 0, b_hist + b_base + b_cnt + b_status, ctx->stream));
+    k_os_hist<T><<<rfb_grid_for(ctx, n, THREADS * 4, 4), THREADS, 0, ctx->stream>>>(col, n, ghist);
+    RFB_CHECK_LAUNCH(ctx);
+    k_os_scan<<<NPASS, RADIX, 0, ctx->stream>>>(ghist, gbase);
+    RFB_CHECK_LAUNCH(ctx);
+    static thread_local unsigned long long hh[8 * RADIX];
+    RFB_CUDA(cudaMemcpyAsync(hh, ghist, (size_t)NPASS * RADIX * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    int passes[8], np = 0;
+    for (int q = 0; q < NPASS; q++) {
+        bool constant = false;
+        for (int d = 0; d < RADIX; d++) if (hh[q * RADIX + d] == (unsigned long long)n) { constant = true; break; }
+        if (!constant) passes[np++] = q;
+    }
+    if (np == 0) {  // all keys equal: the identity permutation (stable)
+        k_iota<<<rfb_grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(perm, n);
+        RFB_CHECK_LAUNCH(ctx);
+        return RFB_OK;
+    }
+    u64 *kin = nullptr, *kout = keysA;
+    u32 *rin = nullptr, *rout = ridsA;
+    for (int q = 0; q < np; q++) {
+        const bool last = (q == np - 1);
+        const int shift = 8 * passes[q];
+        const u64 tag = (u64)(q + 1) << 56;
+        const i64 *gb = gbase + passes[q] * RADIX;
+        if (q == 0) rc = os_run_pass(ctx, col, n, tiles, shift, tag, gb, status, counters + q, kout, rout, perm, last);
+        else rc = os_run_pass(ctx, OsPairSrc{kin, rin}, n, tiles, shift, tag, gb, status, counters + q, kout, rout, perm, last);
+        if (rc) return rc;
+        kin = kout; kout = (kout == keysA) ? keysB : keysA;
+        rin = rout; rout = (rout == ridsA) ? ridsB : ridsA;
+    }
+    return RFB_OK;
+}
+
+template <typename T>
+int sort_lsd(rfb_ctx_t *ctx, const void *x, i64 n, int descending, i64 *perm) {
     constexpr int NPASS = (int)sizeof(T);
     const u64 width_mask = NPASS == 8 ? ~0ULL : ((1ULL << (8 * NPASS)) - 1);
     ColumnSrc<T> col{(const T *)x, descending ? width_mask : 0ULL};
@@ -337,6 +614,13 @@ int sort_t(rfb_ctx_t *ctx, const void *x, i64 n, int descending, i64 *perm) {
         vout = (vout == perm) ? valsA : perm;
     }
     return RFB_OK;
+}
+
+// the single-sweep passes carry 32-bit row ids; longer columns (and RFB_SORT_ALGO=lsd) take the histogram + scatter passes
+template <typename T>
+int sort_t(rfb_ctx_t *ctx, const void *x, i64 n, int descending, i64 *perm) {
+    if (n < (1ll << 32) && rfb_options()->sort_algo == 0) return sort_onesweep<T>(ctx, x, n, descending, perm);
+    return sort_lsd<T>(ctx, x, n, descending, perm);
 }
 
 }  // namespace

@@ -86,7 +86,7 @@ int rfb_aggr_med_launch(rfb_ctx_t *ctx, int val_type, const void *val, const int
 int rfb_aggr_stddev_launch(rfb_ctx_t *ctx, int val_type, const void *val, const int64_t *filter, const int64_t *group_ids, int64_t len, int64_t groups, double *out);
 
 // run-time tuning knobs: read from the environment ONCE (first use), never on the per-call path; rfb_options_reload() re-reads them
-struct rfb_options_t { int loaded; int group_strategy; i64 part_min_rows; int accum_tma; };
+struct rfb_options_t { int loaded; int group_strategy; i64 part_min_rows; int accum_tma; int sort_algo; };
 const rfb_options_t *rfb_options();
 
 // k_fused_group.cu: per-group integer sums + counts over dense group ids through the narrow partitioned passes

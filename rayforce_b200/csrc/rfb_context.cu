@@ -75,6 +75,8 @@ extern "C" void rfb_options_reload(void) {
     o.part_min_rows = s ? atoll(s) : (1ll << 21);
     s = getenv("RFB_ACCUM_TMA");
     o.accum_tma = !(s && s[0] == '0');
+    s = getenv("RFB_SORT_ALGO");
+    o.sort_algo = (s && !strcmp(s, "lsd")) ? 1 : 0;       // 0: single-sweep passes (default), 1: histogram + scatter passes
     o.loaded = 1;
     g_options = o;
 }

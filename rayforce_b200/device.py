@@ -485,6 +485,7 @@ class _Ops:
     def sort(self, t, x, descending=False):
         """ray_sort_asc / ray_sort_desc -> i64 permutation"""
         perm = self._empty(x.shape[0], capi.I64)
+        self.lib.rfb_options_reload()      # tests / sweeps switch the pass structure (RFB_SORT_ALGO) between calls
         check(self.lib.rfb_sort_dev(self.h, t, _dptr(x), x.shape[0], int(descending), _dptr(perm)))
         self.sync()
         return perm

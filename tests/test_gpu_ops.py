@@ -832,6 +832,22 @@ def test_sort_wide_keys(ctx, oracle, desc):
     assert np.array_equal(host(ctx.sort(ob.F64, dev(f), desc)), oracle.sort(ob.F64, f, desc))
 
 
+@pytest.mark.parametrize("algo", ["lsd", "onesweep"])
+@pytest.mark.parametrize("desc", [False, True])
+def test_sort_pass_structures_agree(ctx, oracle, monkeypatch, algo, desc):
+    """both pass structures (single-sweep passes with decoupled look-back: the default; histogram + scatter passes: what columns of
+    2^32 rows and more take) against the oracle, at sizes that span many tiles, with heavy duplicates (stability) and with digit
+    columns that are constant (skipped passes)"""
+    monkeypatch.setenv("RFB_SORT_ALGO", algo)
+    r = np.random.default_rng(17)
+    n = 1_000_003
+    for col, t in ((r.integers(-5, 5, n).astype(np.int64), ob.I64), (r.integers(-(1 << 62), 1 << 62, n).astype(np.int64), ob.I64),
+                   (r.integers(0, 1 << 20, n).astype(np.int64) << 24, ob.I64), (r.integers(-30000, 30000, n).astype(np.int32), ob.I32),
+                   (np.round(r.standard_normal(n) * 100) / 4, ob.F64), (r.integers(0, 256, n).astype(np.uint8), ob.U8),
+                   (r.integers(-300, 300, n).astype(np.int16), ob.I16)):
+        assert np.array_equal(host(ctx.sort(t, dev(col), desc)), oracle.sort(t, col, desc)), (algo, t)
+
+
 def test_sort_reference_goldens(ctx):
     # SURVEY §8a probes of the reference: NaN first, -0.0 before +0.0; both directions stable
     f = np.array([1.0, np.nan, -0.0, 0.0, -1.0])

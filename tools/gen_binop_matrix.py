@@ -3,6 +3,7 @@
 and, for each, the four type roles of its kernel macro — from the switch tables of core/math.c (ray_add_partial ..
 ray_xbar_partial, core/math.c:251-1782), and write it as a C table:
     rayforce_b200/csrc/binop_matrix.inc     (the device layer's dispatch: rfb_binop_dev / rfb_binop_type_form)
+    rayforce_b200/csrc/binop_kernels.inc    (the kernel instantiations that dispatch needs)
     oracle/binop_matrix.inc                 (the oracle's restatement: rfo_binop_form)
 Every case of the reference has the shape  out[i] = mt_to_ot(OP(lt_to_mt(x[i]), rt_to_mt(y[i])))  (__BINOP_V_V / _V_A / _A_V,
 core/math.c:43-90) with (lt, rt, ot, mt, OP) spelled out per case; the table records exactly those five facts per case — typing
@@ -97,7 +98,17 @@ def main():
     for rel in (("rayforce_b200", "csrc", "binop_matrix.inc"), ("oracle", "binop_matrix.inc")):
         with open(os.path.join(ROOT, *rel), "w") as f:
             f.write(body)
-    print("%d cases, %d dropped" % (len(rows), dropped))
+    # the device layer instantiates one kernel per (operand storage, operand storage, result storage, operator family, operator)
+    # that occurs outside I32/I64/F64 x I32/I64/F64 (those keep k_map.cu's kernels)
+    store = {1: "u8", 2: "u8", 3: "i16", 4: "i32", 5: "i64", 7: "i32", 8: "i32", 9: "i64", 10: "f64"}
+    plain = (TYPE["I32"], TYPE["I64"], TYPE["F64"])
+    kernels = sorted({(store[r[4]], store[r[5]], store[r[6]], r[8], r[0]) for r in rows if not (r[2] in plain and r[3] in plain)})
+    with open(os.path.join(ROOT, "rayforce_b200", "csrc", "binop_kernels.inc"), "w") as f:
+        f.write("/* GENERATED by tools/gen_binop_matrix.py: TYPED(x storage, y storage, result storage, operator family, operator) for every\n"
+                " * combination the reference's type matrix needs outside I32/I64/F64 operands — %d kernels */\n" % len(kernels))
+        for k in kernels:
+            f.write("TYPED(%s, %s, %s, %d, %d)\n" % k)
+    print("%d cases, %d dropped, %d kernels" % (len(rows), dropped, len(kernels)))
 
 
 if __name__ == "__main__":

@@ -142,12 +142,17 @@ def main():
         timed("aggr_avg_i64_100", lambda: ctx.aggr(capi.A_AVG, capi.I64, y, g100, i100.groups), 16 * n)
         timed("aggr_dev_i64_100", lambda: ctx.aggr(capi.A_DEV, capi.I64, y, g100, i100.groups), 16 * n, "f64 L2 atomics")
         del k100, g100
-    if n <= 250_000_000 or args.only == "sort":
+    if n <= 250_000_000 or "sort" in args.only.split(","):
         with torch.cuda.stream(st):
             ks = col(capi.I64, 11, 0)
             timed("sort_i64_full_width", lambda: ctx.sort(capi.I64, ks), 8 * n, "8 radix passes")
             k40 = col(capi.I64, 11, 1 << 32)
             timed("sort_i64_32bit_range", lambda: ctx.sort(capi.I64, k40), 8 * n, "4 passes (constant digits skipped)")
+            del k40
+            kf = col(capi.F64, 12, 1 << 40, 0, 1024.0)
+            timed("sort_f64", lambda: ctx.sort(capi.F64, kf), 8 * n)
+            k32 = col(capi.I32, 13, 0)
+            timed("sort_i32", lambda: ctx.sort(capi.I32, k32), 4 * n, "4 passes")
     ctx.close()
 
 
