@@ -17,7 +17,7 @@
 // One census kernel up front takes the bitwise OR and AND of all keys; a pass whose digit is constant over the column is skipped
 // (e.g. the upper bytes of small integers).  The first executed pass reads the typed column and synthesises the row ids;
 // the last one writes only the permutation.  HBM traffic per executed pass: 8N (hist) + 16N read + 16N written.
-#include "rfb_common.cuh"
+#include "rfb_tma.cuh"
 
 namespace {
 
@@ -299,22 +299,41 @@ int run_pass(rfb_ctx_t *ctx, Src src, i64 n, int G, i64 chunk, int shift, u32 *b
 // Row ids travel as 32-bit words between passes (12 B per row moved instead of 16); the last pass widens them into `perm`.
 // A pass whose digit is constant over the column (one histogram bin holds every row) is skipped, as before.
 // Per executed pass: 12N read + 12N written (first pass: sizeof(T) N read; last pass: 8N written).
+#ifndef RFB_OS_MATCH
+#define RFB_OS_MATCH 0
+#endif
+#ifndef RFB_OS_LB
+#define RFB_OS_LB 4
+#endif
+#ifndef RFB_OS_STAGE_RIDS
+#define RFB_OS_STAGE_RIDS 1
+#endif
+constexpr int OS_LB = RFB_OS_LB;
 #ifndef RFB_OS_ITEMS
 #define RFB_OS_ITEMS 16
-#define RFB_OS_CTAS 3
+#define RFB_OS_CTAS 2
 #endif
 constexpr int OS_T = 256, OS_W = OS_T / 32, OS_ITEMS = RFB_OS_ITEMS, OS_TILE = OS_T * OS_ITEMS;
 constexpr u64 OS_AGG = 1ULL << 54, OS_INC = 2ULL << 54, OS_FLAGS = 3ULL << 54, OS_COUNT = (1ULL << 54) - 1;
 
 template <typename T> struct OsColumnSrc {      // first pass: the typed column; the row id is the row number
+    typedef T raw_t;
+    static constexpr bool HAS_RIDS = false;
     const T *col;
     u64 flip;
-    __device__ __forceinline__ u64 key(i64 i) const { return sortable<T>(ld_stream(col + i)) ^ flip; }
+    __host__ __device__ __forceinline__ const T *raw(i64 i) const { return col + i; }
+    __device__ __forceinline__ u64 key_of(T v) const { return sortable<T>(v) ^ flip; }
+    __device__ __forceinline__ u64 key(i64 i) const { return key_of(ld_stream(col + i)); }
     __device__ __forceinline__ u32 rid(i64 i) const { return (u32)i; }
 };
 struct OsPairSrc {                              // later passes: the previous pass's (key, 32-bit row id) pairs
+    typedef u64 raw_t;
+    static constexpr bool HAS_RIDS = RFB_OS_STAGE_RIDS != 0;
     const u64 *keys;
     const u32 *rids;
+    __host__ __device__ __forceinline__ const u64 *raw(i64 i) const { return keys + i; }
+    __host__ __device__ __forceinline__ const u32 *raw_rids(i64 i) const { return rids + i; }
+    __device__ __forceinline__ u64 key_of(u64 v) const { return v; }
     __device__ __forceinline__ u64 key(i64 i) const { return ld_stream(keys + i); }
     __device__ __forceinline__ u32 rid(i64 i) const { return ld_stream(rids + i); }
 };
@@ -376,36 +395,72 @@ __global__ void __launch_bounds__(RADIX) k_os_scan(const unsigned long long *ghi
 template <typename Src, bool LAST>
 __global__ void __launch_bounds__(OS_T, RFB_OS_CTAS)
 k_os_pass(Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *__restrict__ gbase /* [256] */, unsigned long long *__restrict__ status /* [tiles][256] */,
-          u32 *__restrict__ tile_counter, u64 *__restrict__ keys_out, u32 *__restrict__ rids_out, i64 *__restrict__ perm_out) {
+          u32 *__restrict__ tile_counter, u64 *__restrict__ keys_out, u32 *__restrict__ rids_out, i64 *__restrict__ perm_out, bool staged) {
+    typedef typename Src::raw_t raw_t;
     __shared__ u32 whist[OS_W][RADIX];
     __shared__ i64 base[RADIX];     // output slot of the tile-local position 0 of each digit's run
     __shared__ u32 dstart[RADIX];
     __shared__ u32 wsum[RADIX / 32];
-    __shared__ u32 s_tile;
-    extern __shared__ u64 stage_dyn[];            // OS_TILE keys then OS_TILE 32-bit row ids
+    __shared__ u32 s_tile[2];
+    __shared__ __align__(8) u64 full;             // mbarrier: the staged keys of the NEXT tile have landed
+    extern __shared__ __align__(16) u64 stage_dyn[];   // OS_TILE sorted keys | staged raw keys | sorted 32-bit row ids | staged row ids
     u64 *skeys = stage_dyn;
-    u32 *srids = (u32 *)(stage_dyn + OS_TILE);
+    const raw_t *inkeys = (const raw_t *)(stage_dyn + OS_TILE);
+    u32 *srids = (u32 *)(stage_dyn + 2 * OS_TILE);
+    const u32 *inrids = srids + OS_TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 lt = (1u << lane) - 1u;
-    for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    // A tile's keys are staged by the TMA unit (one cp.async.bulk, completion counted on `full`) while the PREVIOUS tile is
+    // ranked, ordered and written out: thread 0 claims the next tile and issues its copy as soon as every warp has moved the
+    // current tile's keys from the stage into registers.  Only whole tiles of a 16-byte aligned source are staged.
+    if (threadIdx.x == 0) {
+        mbar_init(&full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const u32 t = atomicAdd(tile_counter, 1u);
+        s_tile[0] = t;
+        if (staged && t < tiles && (i64)(t + 1) * OS_TILE <= n) {
+            mbar_expect_tx(&full, OS_TILE * (u32)(sizeof(raw_t) + (Src::HAS_RIDS ? 4 : 0)));
+            bulk_g2s((void *)inkeys, src.raw((i64)t * OS_TILE), OS_TILE * (u32)sizeof(raw_t), &full);
+            if constexpr (Src::HAS_RIDS) bulk_g2s((void *)inrids, src.raw_rids((i64)t * OS_TILE), OS_TILE * 4u, &full);
+        }
+    }
+    u32 phase = 0;
+    for (u32 it = 0;; it++) {
         for (int idx = threadIdx.x; idx < OS_W * RADIX; idx += OS_T) (&whist[0][0])[idx] = 0;
         __syncthreads();
-        const u32 tile = s_tile;
+        const u32 tile = s_tile[it & 1];
         if (tile >= tiles) break;
         const i64 t0 = (i64)tile * OS_TILE;
         const i64 wb = t0 + (i64)warp * (32 * OS_ITEMS);
         u64 key[OS_ITEMS];
-#pragma unroll
-        for (int j = 0; j < OS_ITEMS; j++) {
-            const i64 i = wb + j * 32 + lane;
-            key[j] = i < n ? src.key(i) : ~0ULL;
-        }
         u32 rid[OS_ITEMS];
+        if (staged && t0 + OS_TILE <= n) {
+            mbar_wait(&full, phase & 1u);
+            phase++;
 #pragma unroll
-        for (int j = 0; j < OS_ITEMS; j++) {
-            const i64 i = wb + j * 32 + lane;
-            rid[j] = i < n ? src.rid(i) : 0u;
+            for (int j = 0; j < OS_ITEMS; j++) {
+                const int li = warp * (32 * OS_ITEMS) + j * 32 + lane;
+                key[j] = src.key_of(inkeys[li]);
+                if constexpr (Src::HAS_RIDS) rid[j] = inrids[li];
+                else rid[j] = src.rid(t0 + li);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < OS_ITEMS; j++) {
+                const i64 i = wb + j * 32 + lane;
+                key[j] = i < n ? src.key(i) : ~0ULL;
+                rid[j] = i < n ? src.rid(i) : 0u;
+            }
+        }
+        __syncthreads();                          // the stage is free again
+        if (threadIdx.x == 0) {
+            const u32 t = atomicAdd(tile_counter, 1u);
+            s_tile[(it + 1) & 1] = t;
+            if (staged && t < tiles && (i64)(t + 1) * OS_TILE <= n) {
+                mbar_expect_tx(&full, OS_TILE * (u32)(sizeof(raw_t) + (Src::HAS_RIDS ? 4 : 0)));
+                bulk_g2s((void *)inkeys, src.raw((i64)t * OS_TILE), OS_TILE * (u32)sizeof(raw_t), &full);
+                if constexpr (Src::HAS_RIDS) bulk_g2s((void *)inrids, src.raw_rids((i64)t * OS_TILE), OS_TILE * 4u, &full);
+            }
         }
         // rank of a row among the rows of its warp with the same digit, in (step, lane) order: the lanes holding the same digit
         // come from eight ballots; the lowest of them adds the group's size to the warp's counter with a returning atomic (the
@@ -416,6 +471,9 @@ k_os_pass(Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *__restrict__
             const i64 i = wb + j * 32 + lane;
             const bool ok = i < n;
             const u32 d = (u32)(key[j] >> shift) & 255u;
+#if RFB_OS_MATCH
+            const u32 peers = __match_any_sync(0xffffffffu, ok ? d : (0x100u | (u32)lane));   // ADU pipe: ~17 cycles per warp instruction per SM
+#else
             u32 peers = __ballot_sync(0xffffffffu, ok);
 #pragma unroll
             for (int b = 0; b < 8; b++) {
@@ -423,6 +481,7 @@ k_os_pass(Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *__restrict__
                 const u32 bal = __ballot_sync(0xffffffffu, bit);
                 peers &= bit ? bal : ~bal;
             }
+#endif
             const int leader = ok ? __ffs(peers) - 1 : lane;
             u32 prior = 0;
             if (ok && lane == leader) prior = atomicAdd(&whist[warp][d], (u32)__popc(peers));
@@ -465,13 +524,24 @@ k_os_pass(Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *__restrict__
         // ... then resolve digit d's exclusive prefix over the preceding tiles (their words have had the whole ordering step to land)
         u64 excl = 0;
         if (tile > 0) {
-            const volatile unsigned long long *st = status + (size_t)(tile - 1) * RADIX + d;
-            for (;;) {
-                const u64 v = *st;
-                if ((v & ~(OS_FLAGS | OS_COUNT)) != tag || (v & OS_FLAGS) == 0) continue;     // not published in this pass yet
-                excl += v & OS_COUNT;
-                if ((v & OS_FLAGS) == OS_INC) break;
-                st -= RADIX;
+            // OS_LB predecessor words per round trip (independent loads), consumed nearest first; a word that is not there yet
+            // ends the batch and the walk resumes from it
+            i64 pt = (i64)tile - 1;
+            for (bool done = false; !done;) {
+                u64 v[OS_LB];
+#pragma unroll
+                for (int k = 0; k < OS_LB; k++)
+                    v[k] = pt - k >= 0 ? *(const volatile unsigned long long *)(status + (size_t)(pt - k) * RADIX + d) : (tag | OS_INC);
+                int used = 0;
+#pragma unroll
+                for (int k = 0; k < OS_LB; k++) {
+                    if (done || used != k) continue;
+                    if ((v[k] & ~(OS_FLAGS | OS_COUNT)) != tag || (v[k] & OS_FLAGS) == 0) continue;   // not published in this pass yet
+                    excl += v[k] & OS_COUNT;
+                    used = k + 1;
+                    done = (v[k] & OS_FLAGS) == OS_INC;
+                }
+                pt -= used;
             }
             *(volatile unsigned long long *)mine = tag | OS_INC | (excl + cnt);
         }
@@ -485,14 +555,15 @@ k_os_pass(Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *__restrict__
             if (LAST) perm_out[pos] = (i64)srids[i];
             else { keys_out[pos] = k; rids_out[pos] = srids[i]; }
         }
-        // the next round's first barrier (after whist is zeroed) also orders these reads of the stage before its next writes
+        // the next round's first barrier (after whist is zeroed) also orders these reads of the sorted stage before its next writes
     }
 }
 
 template <typename Src>
 int os_run_pass(rfb_ctx_t *ctx, Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *gbase, unsigned long long *status, u32 *counter,
                 u64 *keys_out, u32 *rids_out, i64 *perm_out, bool last) {
-    constexpr int STAGE_BYTES = OS_TILE * 12;
+    constexpr int STAGE_BYTES = OS_TILE * (RFB_OS_STAGE_RIDS ? 24 : 20);      // sorted keys + staged raw keys + sorted row ids (+ staged row ids)
+    const bool staged = aligned16(src.raw(0));
     static bool opted_in = false;   // per template instantiation
     if (!opted_in) {
         RFB_CUDA(cudaFuncSetAttribute(k_os_pass<Src, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
@@ -501,8 +572,8 @@ int os_run_pass(rfb_ctx_t *ctx, Src src, i64 n, u32 tiles, int shift, u64 tag, c
     }
     const u32 resident = (u32)ctx->sm_count * RFB_OS_CTAS;
     const u32 grid = tiles < resident ? tiles : resident;
-    if (last) k_os_pass<Src, true><<<grid, OS_T, STAGE_BYTES, ctx->stream>>>(src, n, tiles, shift, tag, gbase, status, counter, keys_out, rids_out, perm_out);
-    else k_os_pass<Src, false><<<grid, OS_T, STAGE_BYTES, ctx->stream>>>(src, n, tiles, shift, tag, gbase, status, counter, keys_out, rids_out, perm_out);
+    if (last) k_os_pass<Src, true><<<grid, OS_T, STAGE_BYTES, ctx->stream>>>(src, n, tiles, shift, tag, gbase, status, counter, keys_out, rids_out, perm_out, staged);
+    else k_os_pass<Src, false><<<grid, OS_T, STAGE_BYTES, ctx->stream>>>(src, n, tiles, shift, tag, gbase, status, counter, keys_out, rids_out, perm_out, staged);
     RFB_CHECK_LAUNCH(ctx);
     return RFB_OK;
 }
