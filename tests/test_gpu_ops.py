@@ -120,6 +120,30 @@ def test_where(ctx, oracle, n, frac):
     assert np.array_equal(host(ctx.where(dev(mask))), oracle.where(mask))
 
 
+@pytest.mark.parametrize("n", [8191, 16384, 16385, 3_000_017, 40_000_003])
+def test_compaction_with_drifting_selectivity(ctx, oracle, n):
+    """the compaction kernels at sizes around one tile and over thousands of tiles, with a selectivity that drifts between 0 and 1
+    along the column (empty and full tiles, long look-back chains); the count and every id are checked"""
+    r = np.random.default_rng(n % 1000)
+    frac = r.random(n // 50_000 + 1).repeat(50_000)[:n]           # selectivity drifts between 0 and 1 along the column
+    mask = (r.random(n) < frac).astype(np.uint8)
+    mask[: min(n, 20_000)] = 0
+    mask[-min(n, 9_000):] = 1
+    want = np.flatnonzero(mask).astype(np.int64)
+    assert np.array_equal(host(ctx.where(dev(mask))), want)
+    x = np.where(mask != 0, 3, 5).astype(np.int64)
+    x[::97] = ob.NULL_I64
+    want = oracle.where(oracle.cmp(ob.LT, ob.I64, x, ob.I64, 4)) if n <= 3_000_017 else np.flatnonzero(x < 4).astype(np.int64)
+    assert np.array_equal(host(ctx.cmp_where(ob.LT, ob.I64, dev(x), 4)), want)
+    x32 = x.astype(np.int32)
+    x32[::97] = ob.NULL_I32
+    assert np.array_equal(host(ctx.cmp_where(ob.LT, ob.I32, dev(x32), 4)), want)
+    del x32
+    xf = np.where(mask != 0, 3.0, 5.0)
+    xf[::97] = np.nan
+    assert np.array_equal(host(ctx.cmp_where(ob.LT, ob.F64, dev(xf), 4.0)), want)
+
+
 def test_where_unaligned_mask(ctx, oracle):
     mask = (np.random.default_rng(5).random(100_003) < 0.3).astype(np.uint8)
     assert np.array_equal(host(ctx.where(dev(mask)[5:])), oracle.where(mask[5:]))
