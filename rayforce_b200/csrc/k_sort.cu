@@ -305,6 +305,9 @@ int run_pass(rfb_ctx_t *ctx, Src src, i64 n, int G, i64 chunk, int shift, u32 *b
 #ifndef RFB_OS_LB
 #define RFB_OS_LB 4
 #endif
+#ifndef RFB_OS_CTAS32
+#define RFB_OS_CTAS32 3       // CTAs per SM of the passes over 32-bit key words
+#endif
 #ifndef RFB_OS_SLEEP
 #define RFB_OS_SLEEP 0
 #endif
@@ -320,25 +323,34 @@ constexpr int OS_LB = RFB_OS_LB;
 constexpr int OS_T = 256, OS_W = OS_T / 32, OS_ITEMS = RFB_OS_ITEMS, OS_TILE = OS_T * OS_ITEMS;
 constexpr u64 OS_AGG = 1ULL << 54, OS_INC = 2ULL << 54, OS_FLAGS = 3ULL << 54, OS_COUNT = (1ULL << 54) - 1;
 
+// the key word a column travels as between passes: 32 bits for columns of up to 4 bytes (8 B per row moved, three CTAs per SM)
+template <typename T> struct OsKey { typedef u64 type; };
+template <> struct OsKey<u8> { typedef u32 type; };
+template <> struct OsKey<i16> { typedef u32 type; };
+template <> struct OsKey<i32> { typedef u32 type; };
+
 template <typename T> struct OsColumnSrc {      // first pass: the typed column; the row id is the row number
     typedef T raw_t;
+    typedef typename OsKey<T>::type key_t;
     static constexpr bool HAS_RIDS = false;
     const T *col;
     u64 flip;
     __host__ __device__ __forceinline__ const T *raw(i64 i) const { return col + i; }
-    __device__ __forceinline__ u64 key_of(T v) const { return sortable<T>(v) ^ flip; }
-    __device__ __forceinline__ u64 key(i64 i) const { return key_of(ld_stream(col + i)); }
+    __device__ __forceinline__ key_t key_of(T v) const { return (key_t)(sortable<T>(v) ^ flip); }
+    __device__ __forceinline__ key_t key(i64 i) const { return key_of(ld_stream(col + i)); }
+    __device__ __forceinline__ u64 key64(i64 i) const { return sortable<T>(ld_stream(col + i)) ^ flip; }
     __device__ __forceinline__ u32 rid(i64 i) const { return (u32)i; }
 };
-struct OsPairSrc {                              // later passes: the previous pass's (key, 32-bit row id) pairs
-    typedef u64 raw_t;
+template <typename K> struct OsPairSrc {        // later passes: the previous pass's (key, 32-bit row id) pairs
+    typedef K raw_t;
+    typedef K key_t;
     static constexpr bool HAS_RIDS = RFB_OS_STAGE_RIDS != 0;
-    const u64 *keys;
+    const K *keys;
     const u32 *rids;
-    __host__ __device__ __forceinline__ const u64 *raw(i64 i) const { return keys + i; }
+    __host__ __device__ __forceinline__ const K *raw(i64 i) const { return keys + i; }
     __host__ __device__ __forceinline__ const u32 *raw_rids(i64 i) const { return rids + i; }
-    __device__ __forceinline__ u64 key_of(u64 v) const { return v; }
-    __device__ __forceinline__ u64 key(i64 i) const { return ld_stream(keys + i); }
+    __device__ __forceinline__ K key_of(K v) const { return v; }
+    __device__ __forceinline__ K key(i64 i) const { return ld_stream(keys + i); }
     __device__ __forceinline__ u32 rid(i64 i) const { return ld_stream(rids + i); }
 };
 
@@ -358,7 +370,7 @@ __global__ void __launch_bounds__(THREADS, 4) k_os_hist(OsColumnSrc<T> src, i64 
         for (int j = 0; j < U; j++) {
             const i64 i = w0 + j * stride + (threadIdx.x & 31);
             ok[j] = i < n;
-            k[j] = ok[j] ? src.key(i) : 0;
+            k[j] = ok[j] ? src.key64(i) : 0;
         }
 #pragma unroll
         for (int j = 0; j < U; j++) {
@@ -397,19 +409,20 @@ __global__ void __launch_bounds__(RADIX) k_os_scan(const unsigned long long *ghi
 }
 
 template <typename Src, bool LAST>
-__global__ void __launch_bounds__(OS_T, RFB_OS_CTAS)
+__global__ void __launch_bounds__(OS_T, (sizeof(typename Src::key_t) == 4 ? RFB_OS_CTAS32 : RFB_OS_CTAS))
 k_os_pass(Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *__restrict__ gbase /* [256] */, unsigned long long *__restrict__ status /* [tiles][256] */,
-          u32 *__restrict__ tile_counter, u64 *__restrict__ keys_out, u32 *__restrict__ rids_out, i64 *__restrict__ perm_out, bool staged) {
+          u32 *__restrict__ tile_counter, typename Src::key_t *__restrict__ keys_out, u32 *__restrict__ rids_out, i64 *__restrict__ perm_out, bool staged) {
     typedef typename Src::raw_t raw_t;
+    typedef typename Src::key_t K;
     __shared__ u32 whist[OS_W][RADIX];
     __shared__ i64 base[RADIX];     // output slot of the tile-local position 0 of each digit's run
     __shared__ u32 wsum[RADIX / 32];
     __shared__ u32 s_tile[2];
     __shared__ __align__(8) u64 full;             // mbarrier: the staged keys of the NEXT tile have landed
-    extern __shared__ __align__(16) u64 stage_dyn[];   // OS_TILE sorted keys | staged raw keys | sorted 32-bit row ids | staged row ids
-    u64 *skeys = stage_dyn;
-    const raw_t *inkeys = (const raw_t *)(stage_dyn + OS_TILE);
-    u32 *srids = (u32 *)(stage_dyn + 2 * OS_TILE);
+    extern __shared__ __align__(16) unsigned char stage_raw[];   // OS_TILE sorted keys | staged raw keys | sorted 32-bit row ids | staged row ids
+    K *skeys = (K *)stage_raw;
+    const raw_t *inkeys = (const raw_t *)(stage_raw + OS_TILE * sizeof(K));
+    u32 *srids = (u32 *)(stage_raw + 2 * OS_TILE * sizeof(K));   // (the staged raw keys are never wider than K)
     const u32 *inrids = srids + OS_TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 lt = (1u << lane) - 1u;
@@ -435,7 +448,7 @@ k_os_pass(Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *__restrict__
         if (tile >= tiles) break;
         const i64 t0 = (i64)tile * OS_TILE;
         const i64 wb = t0 + (i64)warp * (32 * OS_ITEMS);
-        u64 key[OS_ITEMS];
+        K key[OS_ITEMS];
         u32 rid[OS_ITEMS];
         if (staged && t0 + OS_TILE <= n) {
             mbar_wait(&full, phase & 1u);
@@ -451,7 +464,7 @@ k_os_pass(Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *__restrict__
 #pragma unroll
             for (int j = 0; j < OS_ITEMS; j++) {
                 const i64 i = wb + j * 32 + lane;
-                key[j] = i < n ? src.key(i) : ~0ULL;
+                key[j] = i < n ? src.key(i) : (K)~0ULL;
                 rid[j] = i < n ? src.rid(i) : 0u;
             }
         }
@@ -555,7 +568,7 @@ k_os_pass(Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *__restrict__
         const int tile_n = (int)((n - t0) < OS_TILE ? (n - t0) : OS_TILE);
 #pragma unroll 4
         for (int i = threadIdx.x; i < tile_n; i += OS_T) {
-            const u64 k = skeys[i];
+            const K k = skeys[i];
             const i64 pos = base[(u32)(k >> shift) & 255u] + i;
             if (LAST) perm_out[pos] = (i64)srids[i];
             else { keys_out[pos] = k; rids_out[pos] = srids[i]; }
@@ -566,8 +579,10 @@ k_os_pass(Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *__restrict__
 
 template <typename Src>
 int os_run_pass(rfb_ctx_t *ctx, Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *gbase, unsigned long long *status, u32 *counter,
-                u64 *keys_out, u32 *rids_out, i64 *perm_out, bool last) {
-    constexpr int STAGE_BYTES = OS_TILE * (RFB_OS_STAGE_RIDS ? 24 : 20);      // sorted keys + staged raw keys + sorted row ids (+ staged row ids)
+                typename Src::key_t *keys_out, u32 *rids_out, i64 *perm_out, bool last) {
+    constexpr int KB = (int)sizeof(typename Src::key_t);
+    constexpr int STAGE_BYTES = OS_TILE * (2 * KB + (RFB_OS_STAGE_RIDS ? 8 : 4));   // sorted keys + staged raw keys + sorted row ids (+ staged row ids)
+    constexpr int CTAS = KB == 4 ? RFB_OS_CTAS32 : RFB_OS_CTAS;
     const bool staged = aligned16(src.raw(0));
     static bool opted_in = false;   // per template instantiation
     if (!opted_in) {
@@ -575,7 +590,7 @@ int os_run_pass(rfb_ctx_t *ctx, Src src, i64 n, u32 tiles, int shift, u64 tag, c
         RFB_CUDA(cudaFuncSetAttribute(k_os_pass<Src, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_BYTES));
         opted_in = true;
     }
-    const u32 resident = (u32)ctx->sm_count * RFB_OS_CTAS;
+    const u32 resident = (u32)ctx->sm_count * CTAS;
     const u32 grid = tiles < resident ? tiles : resident;
     if (last) k_os_pass<Src, true><<<grid, OS_T, STAGE_BYTES, ctx->stream>>>(src, n, tiles, shift, tag, gbase, status, counter, keys_out, rids_out, perm_out, staged);
     else k_os_pass<Src, false><<<grid, OS_T, STAGE_BYTES, ctx->stream>>>(src, n, tiles, shift, tag, gbase, status, counter, keys_out, rids_out, perm_out, staged);
@@ -587,11 +602,12 @@ template <typename T>
 int sort_onesweep(rfb_ctx_t *ctx, const void *x, i64 n, int descending, i64 *perm) {
     constexpr int NPASS = (int)sizeof(T);
     const u64 width_mask = NPASS == 8 ? ~0ULL : ((1ULL << (8 * NPASS)) - 1);
+    typedef typename OsKey<T>::type K;
     OsColumnSrc<T> col{(const T *)x, descending ? width_mask : 0ULL};
     const u32 tiles = (u32)((n + OS_TILE - 1) / OS_TILE);
     // workspace: ghist[8][256] u64 | gbase[8][256] i64 | counters[8] u32 | status[tiles][256] u64 | keysA[n] | keysB[n] | ridsA[n] | ridsB[n]
     const size_t b_hist = 8 * RADIX * 8, b_base = 8 * RADIX * 8, b_cnt = 256, b_status = align256((size_t)tiles * RADIX * 8),
-                 b_k = align256((size_t)n * 8), b_r = align256((size_t)n * 4);
+                 b_k = align256((size_t)n * sizeof(K)), b_r = align256((size_t)n * 4);
     void *w;
     int rc = rfb_ensure_work(ctx, b_hist + b_base + b_cnt + b_status + 2 * b_k + 2 * b_r, &w);
     if (rc) return rc;
@@ -600,8 +616,8 @@ int sort_onesweep(rfb_ctx_t *ctx, const void *x, i64 n, int descending, i64 *per
     i64 *gbase = (i64 *)p; p += b_base;
     u32 *counters = (u32 *)p; p += b_cnt;
     unsigned long long *status = (unsigned long long *)p; p += b_status;
-    u64 *keysA = (u64 *)p; p += b_k;
-    u64 *keysB = (u64 *)p; p += b_k;
+    K *keysA = (K *)p; p += b_k;
+    K *keysB = (K *)p; p += b_k;
     u32 *ridsA = (u32 *)p; p += b_r;
     u32 *ridsB = (u32 *)p;
     RFB_CUDA(cudaMemsetAsync(w, 0, b_hist + b_base + b_cnt + b_status, ctx->stream));
@@ -623,7 +639,7 @@ int sort_onesweep(rfb_ctx_t *ctx, const void *x, i64 n, int descending, i64 *per
         RFB_CHECK_LAUNCH(ctx);
         return RFB_OK;
     }
-    u64 *kin = nullptr, *kout = keysA;
+    K *kin = nullptr, *kout = keysA;
     u32 *rin = nullptr, *rout = ridsA;
     for (int q = 0; q < np; q++) {
         const bool last = (q == np - 1);
@@ -631,7 +647,7 @@ int sort_onesweep(rfb_ctx_t *ctx, const void *x, i64 n, int descending, i64 *per
         const u64 tag = (u64)(q + 1) << 56;
         const i64 *gb = gbase + passes[q] * RADIX;
         if (q == 0) rc = os_run_pass(ctx, col, n, tiles, shift, tag, gb, status, counters + q, kout, rout, perm, last);
-        else rc = os_run_pass(ctx, OsPairSrc{kin, rin}, n, tiles, shift, tag, gb, status, counters + q, kout, rout, perm, last);
+        else rc = os_run_pass(ctx, OsPairSrc<K>{kin, rin}, n, tiles, shift, tag, gb, status, counters + q, kout, rout, perm, last);
         if (rc) return rc;
         kin = kout; kout = (kout == keysA) ? keysB : keysA;
         rin = rout; rout = (rout == ridsA) ? ridsB : ridsA;
