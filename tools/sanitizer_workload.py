@@ -115,5 +115,27 @@ ctx.aggr(capi.A_FIRST, capi.I64, x, g, info.groups)
 ctx.aggr_last(capi.F64, f, g, info.groups, 8)
 for op in (capi.DIV, capi.MOD, capi.XBAR):
     ctx.binop(op, capi.I64, x, capi.I64, -7)
+# round 2, later: single-sweep sort passes (TMA-staged tiles, decoupled look-back) for 64- and 32-bit key words, both directions;
+# the histogram + scatter passes they replace; the typed arithmetic kernels (temporal units, narrow integers, B8)
+for col, t in ((kw, capi.I64), (k32, capi.I32), (f, capi.F64), (dev(r.integers(0, 200, n).astype(np.uint8)), capi.U8)):
+    ctx.sort(t, col)
+    ctx.sort(t, col, True)
+os.environ["RFB_SORT_ALGO"] = "lsd"
+ctx.sort(capi.I64, kw)
+os.environ.pop("RFB_SORT_ALGO", None)
+ts = dev(r.integers(0, 1 << 50, n).astype(np.int64))
+tm = dev(r.integers(0, 86_400_000, n).astype(np.int32))
+dt = dev(r.integers(0, 20_000, n).astype(np.int32))
+i16 = dev(r.integers(-300, 300, n).astype(np.int16))
+u8 = dev(r.integers(0, 256, n).astype(np.uint8))
+ctx.binop(capi.ADD, capi.TIMESTAMP, ts, capi.TIME, tm)
+ctx.binop(capi.ADD, capi.DATE, dt, capi.TIME, tm)
+ctx.binop(capi.SUB, capi.TIMESTAMP, ts, capi.TIMESTAMP, ts)
+ctx.binop(capi.XBAR, capi.TIMESTAMP, ts, capi.I64, 60_000_000_000)
+ctx.binop(capi.XBAR, capi.TIME, tm, capi.I32, 60_000)
+ctx.binop(capi.MUL, capi.I16, i16, capi.I16, i16)
+ctx.binop(capi.DIV, capi.U8, u8, capi.U8, u8)
+ctx.binop(capi.ADD, capi.U8, u8, capi.F64, 2.5)
+ctx.binop(capi.MOD, capi.I16, i16, capi.I64, 7)
 ctx.sync()
 print("sanitizer workload done, launches:", ctx.launches)
