@@ -383,6 +383,18 @@ def run_extra_configs(ctx, stream, dev, n, rank, world, K, W, with_e2e=True, mer
     ctx.fill_splitmix(capi.I64, v, n, shifted_seed(9, first_row), 1 << 20, 0, 0)
     ctx.sync()
     regroup = shard.gpu_regroup(ctx)
+    # N > 1: the exchange step of the group-by.  Default (--merge peer): every rank's (key, sum, count) lists are read in place over
+    # NVLink peer memory by the merge kernels (rfb_group_merge_peers); --merge nccl, or no CUDA IPC: all-gather + re-group.
+    group_peer = False
+    if world > 1 and merge_mode == "peer":
+        try:
+            ctx.peer_groups_setup(rank, world, 1 << 18)
+            group_peer = True
+        except Exception as e:
+            print("[bench] group exchange buffers unavailable (%s); NCCL all-gather instead" % e, file=sys.stderr)
+        flag = torch.tensor([1 if group_peer else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)            # all ranks or none
+        group_peer = int(flag.item()) == 1
 
     def grouped(filtered):
         def step():
@@ -392,10 +404,14 @@ def run_extra_configs(ctx, stream, dev, n, rank, world, K, W, with_e2e=True, mer
                 lk, ls, lc = ctx.group_sum_count(capi.I32, k, v, 100_000)
             if world > 1:
                 with torch.cuda.stream(stream):
+                    if group_peer:
+                        return shard.merge_group_partials_peers(ctx, lk, ls, lc, 1 << 18, regroup)
                     return shard.merge_group_partials(lk, ls, lc, regroup)
             return lk, ls, lc
         return step
-    merge = "none" if world == 1 else "one all-gather of every GPU's (key, sum, count) rows + re-group on every rank (NCCL)"
+    merge = "none" if world == 1 else ("every GPU's (key, sum, count) rows read in place over NVLink peer memory by the merge kernels (rfb_group_merge_peers): "
+                                       "direct-address fold + compaction in global first-occurrence order on every rank, no collective" if group_peer
+                                       else "one all-gather of every GPU's (key, sum, count) rows + re-group on every rank (NCCL)")
     with torch.cuda.stream(stream):
         ms, (gk, gs, gc), launches = timed(grouped(False))
         groups, rows, total = int(gk.shape[0]), int(gc.sum().item()), int(gs.sum().item())

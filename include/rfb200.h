@@ -355,6 +355,22 @@ int rfb_fold_host(rfb_ctx_t *ctx, int folds, int type, const void *x, int64_t n,
  *                                                  the merged rfb_fold_t where a single-GPU fold reports.  Every rank must call
  *                                                  it the same number of times.  Bit-identical on all ranks. */
 int rfb_peer_mailbox_create(rfb_ctx_t *ctx, void *ipc_handle_64);
+/* The exchange step of a group-by sharded by row range (`select {(sum v) (count v)} by k`), over NVLink peer memory:
+ *     rfb_peer_groups_create(ctx, capacity, h)     this rank's exchange buffer (two halves of capacity (key, sum, count) rows) and
+ *                                                  its CUDA IPC handle; rfb_peer_groups_bind maps every peer's (handles in rank order)
+ *     rfb_group_merge_peers(ctx, keys, sums, counts, n_local, out_keys, out_sums, out_counts, max_groups, &groups)
+ *                                                  keys / sums / counts: this rank's result of rfb_group_sum_count_dev (device, local
+ *                                                  first-occurrence order).  Publishes them, meets the peers (sequence flags), folds
+ *                                                  all ranks' lists read IN PLACE over NVLink into direct-address tables (wrapping
+ *                                                  sums with the sticky null of ADDI64, counts, first position) and emits the groups
+ *                                                  in GLOBAL first-occurrence order (rank r holds rows before rank r + 1).  Every rank
+ *                                                  must call it the same number of times and ends with the same lists.  Dense key
+ *                                                  domains (kmax - kmin < 2^24); RFB_ERR_TYPE for a wider one — the caller then
+ *                                                  gathers the lists and re-groups them (rfb_group_i64_dev + rfb_aggr_dev). */
+int rfb_peer_groups_create(rfb_ctx_t *ctx, int64_t capacity, void *ipc_handle_64);
+int rfb_peer_groups_bind(rfb_ctx_t *ctx, int rank, int world, const void *handles);
+int rfb_group_merge_peers(rfb_ctx_t *ctx, const int64_t *keys, const int64_t *sums, const int64_t *counts, int64_t n_local,
+                          int64_t *out_keys, int64_t *out_sums, int64_t *out_counts, int64_t max_groups, int64_t *groups);
 int rfb_peer_mailbox_bind(rfb_ctx_t *ctx, int rank, int world, const void *handles);
 int rfb_fold_allreduce_peers(rfb_ctx_t *ctx, int val_type, rfb_fold_t *out);
 

@@ -63,6 +63,12 @@ struct rfb_ctx {
     void *mbox_peer[16];       // every rank's mailbox as mapped into this process ([rank] = own)
     int mbox_rank, mbox_world;
     unsigned long long mbox_seq;
+    // group exchange buffers (k_peer.cu): every rank's partial (key, sum, count) lists, read by the peers over NVLink
+    void *gx;                  // own buffer (device memory, exported through CUDA IPC): 2 halves x (header + 3 x capacity words)
+    void *gx_peer[16];
+    i64 gx_cap;
+    int gx_rank, gx_world;
+    unsigned long long gx_seq;
 };
 
 void rfb_set_error(const char *fmt, ...);

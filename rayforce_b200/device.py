@@ -167,6 +167,25 @@ class Context:
         check(self.lib.rfb_fold_allreduce_peers(self.h, type_, C.byref(f)))
         return FoldResult(f, type_)
 
+    def peer_groups_setup(self, rank: int, world: int, capacity: int, group=None) -> None:
+        """one process per GPU: this rank's group exchange buffer (capacity rows), IPC handles exchanged over torch.distributed"""
+        import torch.distributed as dist
+        h = (C.c_char * 64)()
+        check(self.lib.rfb_peer_groups_create(self.h, capacity, h))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h.raw), group=group)
+        check(self.lib.rfb_peer_groups_bind(self.h, rank, world, C.c_char_p(b"".join(handles))))
+        dist.barrier(group=group)
+
+    def group_merge_peers(self, keys, sums, counts, max_groups: int):
+        """the merged (keys, sums, counts) of all ranks' group lists in global first-occurrence order, over NVLink peer memory;
+        raises RfbError(kind 'type') for a key domain that is not dense (the caller then gathers and re-groups)"""
+        ok, os_, oc = self._empty(max_groups, capi.I64), self._empty(max_groups, capi.I64), self._empty(max_groups, capi.I64)
+        g = C.c_int64(0)
+        check(self.lib.rfb_group_merge_peers(self.h, _dptr(keys), _dptr(sums), _dptr(counts), keys.shape[0], _dptr(ok), _dptr(os_), _dptr(oc),
+                                             max_groups, C.byref(g)))
+        return ok[:g.value], os_[:g.value], oc[:g.value]
+
     def multi_filter_fold(self, preds, conjunction: bool, folds: int, val_type: int, val, n: int) -> FoldResult:
         """preds: [(cmp_op, type, column tensor, constant), ...] combined with and (True) / or (False)"""
         arr = (capi.Pred * len(preds))()

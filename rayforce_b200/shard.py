@@ -99,6 +99,20 @@ def merge_group_partials(keys: torch.Tensor, sums: torch.Tensor, counts: torch.T
     return regroup(k, s, c)
 
 
+def merge_group_partials_peers(ctx, keys: torch.Tensor, sums: torch.Tensor, counts: torch.Tensor, max_groups: int,
+                               regroup: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], Sequence[torch.Tensor]], group=None):
+    """The same merge over NVLink peer memory (rfb_group_merge_peers: every rank's lists are read in place by the merge kernels,
+    no collective).  `ctx.peer_groups_setup` must have bound the exchange buffers.  A key domain that is not dense is declined
+    by every rank alike; they then take the all-gather + re-group route above."""
+    from .capi import RfbError
+    try:
+        return ctx.group_merge_peers(keys, sums, counts, max_groups)
+    except RfbError as e:
+        if e.kind != "type":
+            raise
+    return merge_group_partials(keys, sums, counts, regroup, group)
+
+
 def gpu_regroup(ctx):
     """regroup callback running on the GPU through the C ABI: rfb_group_i64_dev + rfb_aggr_dev(sum) + rfb_gather_dev"""
     from . import capi

@@ -28,3 +28,4 @@ def test_sharded_results_equal_the_single_gpu_results_over_nccl():
     assert rep["ok"] and rep["world"] == world and rep["group_rows_equal"] and rep["groups"] == 100_000
     assert rep["merged_fold"] == rep["single_gpu_fold"]
     assert rep["peer_mailbox_allreduce_equal"] is True, rep        # the NVLink mailbox merge gives the NCCL merge's bits
+    assert rep["peer_group_merge_equal"] is True, rep              # so does the group-by merge over peer memory (rfb_group_merge_peers)

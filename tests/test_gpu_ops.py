@@ -830,6 +830,46 @@ def test_fused_group_nothing_selected(ctx):
     assert gk.shape[0] == 0
 
 
+def test_group_merge_over_peer_memory_single_rank(ctx):
+    """rfb_group_merge_peers with a world of one (the exchange buffer bound to itself): the publish / meet / fold / emit kernels on a
+    list WITH repeated keys, so the merge has real work — first-occurrence order, wrapping sums, the sticky null of ADDI64, counts;
+    three rounds reuse both halves of the buffer; a wide key domain is declined; an oversized list fails instead of hanging.
+    (The multi-rank form is tests/test_gpu_nccl.py.)"""
+    import ctypes as C
+    h = (C.c_char * 64)()
+    capi.check(ctx.lib.rfb_peer_groups_create(ctx.h, 50_000, h))
+    capi.check(ctx.lib.rfb_peer_groups_bind(ctx.h, 0, 1, C.c_char_p(bytes(h.raw))))
+    r = np.random.default_rng(4)
+    for rnd in range(3):
+        n = 40_000 - rnd
+        keys = r.integers(-700, 9_000, n).astype(np.int64)
+        sums = r.integers(-(1 << 62), 1 << 62, n).astype(np.int64)
+        sums[::13] = ob.NULL_I64
+        counts = r.integers(0, 1000, n).astype(np.int64)
+        gk, gs, gc = ctx.group_merge_peers(dev(keys), dev(sums), dev(counts), 20_000)
+        uk, first, inv = np.unique(keys, return_index=True, return_inverse=True)
+        order = np.argsort(first, kind="stable")
+        want_k = uk[order]
+        tot = np.zeros(uk.shape[0], np.uint64)
+        np.add.at(tot, inv, np.where(sums == ob.NULL_I64, 0, sums).astype(np.uint64))
+        nul = np.zeros(uk.shape[0], bool)
+        np.logical_or.at(nul, inv, sums == ob.NULL_I64)
+        want_s = np.where(nul, np.int64(ob.NULL_I64), tot.astype(np.int64))[order]
+        cnt = np.zeros(uk.shape[0], np.int64)
+        np.add.at(cnt, inv, counts)
+        assert np.array_equal(host(gk), want_k) and np.array_equal(host(gs), want_s) and np.array_equal(host(gc), cnt[order])
+    wide = dev(np.array([0, 1 << 40], np.int64))
+    with pytest.raises(capi.RfbError) as e:
+        ctx.group_merge_peers(wide, wide, wide, 16)
+    assert e.value.kind == "type"
+    big = dev(np.arange(50_001, dtype=np.int64))
+    with pytest.raises(capi.RfbError) as e:
+        ctx.group_merge_peers(big, big, big, 60_000)
+    assert e.value.kind == "arg"
+    gk, gs, gc = ctx.group_merge_peers(dev(np.array([5, 3, 5], np.int64)), dev(np.array([1, 2, 3], np.int64)), dev(np.array([1, 1, 1], np.int64)), 16)
+    assert host(gk).tolist() == [5, 3] and host(gs).tolist() == [4, 2] and host(gc).tolist() == [2, 1]      # still usable after the failures
+
+
 # ---------------------------------------------------------------- key sort
 
 @pytest.mark.parametrize("t", ALL_T + [ob.TIMESTAMP])

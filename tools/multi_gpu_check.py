@@ -66,12 +66,36 @@ def main():
         # --- filter + group-by + sum/count, merged with one all-gather-v and a re-group on every rank
         lk, ls, lc = ctx.group_sum_count(capi.I64, k, v, 100_000, capi.LT, capi.I64, v, KV)
         mk, ms, mc = shard.merge_group_partials(lk, ls, lc, shard.gpu_regroup(ctx))
+        # --- the same merge over NVLink peer memory (rfb_group_merge_peers), three times in a row (both halves of the exchange
+        #     buffers and their reuse), plus a list with null sums and keys only some ranks hold
+        peer_group_ok = True
+        try:
+            ctx.peer_groups_setup(rank, world, 1 << 18)
+            for _ in range(3):
+                pk, ps, pc = ctx.group_merge_peers(lk, ls, lc, 1 << 18)
+                peer_group_ok &= bool(torch.equal(pk, mk) and torch.equal(ps, ms) and torch.equal(pc, mc))
+            ok2 = torch.arange(1000 * rank, 1000 * rank + 3000, dtype=torch.int64, device=dev).flip(0).contiguous()     # overlapping key ranges
+            os2 = torch.full_like(ok2, 7 + rank)
+            os2[::5] = capi.NULL_I64 if rank % 2 == 0 else 3
+            oc2 = torch.full_like(ok2, 2)
+            pk, ps, pc = ctx.group_merge_peers(ok2, os2, oc2, 1 << 18)
+            wk, ws, wc = shard.merge_group_partials(ok2, os2, oc2, shard.gpu_regroup(ctx))
+            peer_group_ok &= bool(torch.equal(pk, wk) and torch.equal(ps, ws) and torch.equal(pc, wc))
+            wide = torch.tensor([0, 1 << 40], dtype=torch.int64, device=dev)                                               # not a dense domain: declined by all ranks
+            pk, ps, pc = shard.merge_group_partials_peers(ctx, wide, wide, wide, 1 << 18, shard.gpu_regroup(ctx))
+            peer_group_ok &= int(pk.shape[0]) == 2 and int(pc[1].item()) == world * (1 << 40)
+        except Exception as e:
+            peer_group_ok = None
+            peer_group_err = str(e)
         torch.cuda.synchronize()
     ok = True
     report = {"world": world, "rows_per_gpu": n, "merged_fold": list(merged), "groups": int(mk.shape[0]), "peer_mailbox_allreduce_equal": peer_ok}
+    report["peer_group_merge_equal"] = peer_group_ok
     if peer_ok is None:
         report["peer_mailbox_error"] = peer_err
-    ok &= peer_ok is not False
+    if peer_group_ok is None:
+        report["peer_group_merge_error"] = peer_group_err
+    ok &= peer_ok is not False and peer_group_ok is not False
     # every rank must hold the same merged result
     sig = torch.tensor([merged[2], int(ms.sum().item()), int(mc.sum().item()), int(mk[:100].sum().item())], dtype=torch.int64, device=dev)
     sigs = [torch.empty_like(sig) for _ in range(world)]
