@@ -625,8 +625,15 @@ constexpr int NP = 32;                          // partitions of the narrow path
 #define RFB_MS_R 8
 #define RFB_MS_CTAS 3
 #endif
-constexpr int MS_T = RFB_MS_T, MS_R = RFB_MS_R, MS_CTAS = RFB_MS_CTAS, MS_TILE = MS_T * MS_R, MS_WARPS = MS_T / 32;
-static_assert(MS_TILE <= PB, "a tile's run touches at most two blocks");
+constexpr int MS_T = RFB_MS_T, MS_CTAS = RFB_MS_CTAS, MS_WARPS = MS_T / 32;
+// rows per thread by key width: 8-byte keys (i64 columns, group ids in rfb_narrow_sums) take 6 — their two 16 B/row input stages
+// plus the staging area then fit three CTAs per SM like the 4-byte keys' (8 rows: 2 CTAs; measured 6.56 -> 6.14 ms per 1e9 rows,
+// aggr_sum / aggr_avg over group ids 6.42 -> 6.01 ms; 4-byte keys with 6 rows: 5.37 -> 5.61 ms)
+#ifndef RFB_MS_R8
+#define RFB_MS_R8 6
+#endif
+template <typename KT> struct MsGeom { static constexpr int R = sizeof(KT) == 8 ? RFB_MS_R8 : RFB_MS_R, TILE = MS_T * R; };
+static_assert(MS_T * RFB_MS_R <= PB && MS_T * RFB_MS_R8 <= PB, "a tile's run touches at most two blocks");
 
 template <typename REC, int KPL> struct RecFmt;
 template <int KPL> struct RecFmt<u32, KPL> {
@@ -680,6 +687,7 @@ __device__ __forceinline__ u32 ballot_bits(u32 x, u32 mask) {
 template <typename FS> struct MsIn {   // one input stage
     typedef typename FS::key_t KT;
     typedef typename FS::pred_t PT_;
+    static constexpr int MS_TILE = MsGeom<KT>::TILE;
     static constexpr size_t KEY_BYTES = MS_TILE * sizeof(KT), VAL_BYTES = MS_TILE * 8, PRED_BYTES = FS::has_pred ? MS_TILE * sizeof(PT_) : 0;
     static constexpr size_t BYTES = KEY_BYTES + VAL_BYTES + PRED_BYTES;
     // a predicate on the aggregated column itself (`where (< v k)` next to `(sum v)`) reads the staged values: no third slice
@@ -701,6 +709,7 @@ k_ms_scatter(FS fs, const i64 *__restrict__ val, i64 tiles, RecStore rs, i64 *mm
     typedef typename FS::key_t KT;
     typedef typename FS::pred_t PT_;
     constexpr u32 KPN = 1u << KPL;
+    constexpr int MS_R = MsGeom<KT>::R, MS_TILE = MsGeom<KT>::TILE;
     extern __shared__ __align__(16) unsigned char s_dyn[];
     const bool pred_alias = In::pred_is_val(fs, val);
     const size_t in_bytes = In::bytes(fs, val);
@@ -1110,6 +1119,7 @@ static inline i64 buckets_spanned(i64 kmin, i64 kmax, int kpl) { return (kmax >>
 
 template <typename FS, typename REC, int KPL>
 int ms_scatter_launch(rfb_ctx_t *ctx, FS fs, const i64 *val, i64 n, const RecStore &rs, i64 *mm) {
+    constexpr int MS_TILE = MsGeom<typename FS::key_t>::TILE;
     const size_t smem = 2 * MsIn<FS>::bytes(fs, val) + 2 * (size_t)MS_TILE * (sizeof(REC) + 1);
     const i64 tiles = n / MS_TILE;                 // full tiles; the rest goes through the side list
     if (tiles > 0) {
