@@ -912,6 +912,25 @@ def test_sort_pass_structures_agree(ctx, oracle, monkeypatch, algo, desc):
         assert np.array_equal(host(ctx.sort(t, dev(col), desc)), oracle.sort(t, col, desc)), (algo, t)
 
 
+@pytest.mark.parametrize("desc", [False, True])
+def test_sort_narrow_windows_of_wide_columns(ctx, oracle, desc):
+    """8-byte columns whose varying bytes fit a 32-bit window travel as 32-bit key words (window at byte 0, in the middle, at the
+    top; exactly 4 varying bytes; 5 varying bytes take the 64-bit words again); doubles of a narrow range do the same"""
+    r = np.random.default_rng(23)
+    n = 300_017
+    cols = [(r.integers(0, 60_000, n).astype(np.int64), ob.I64),
+            (r.integers(0, 1 << 32, n).astype(np.int64), ob.I64),
+            (r.integers(0, 1 << 33, n).astype(np.int64), ob.I64),
+            ((r.integers(0, 1 << 30, n).astype(np.int64) << 16) + 77, ob.I64),
+            (np.int64(1_700_000_000_000_000_000) + r.integers(0, 3_000_000_000, n).astype(np.int64), ob.TIMESTAMP),
+            (-(r.integers(1, 1 << 28, n).astype(np.int64) << 32), ob.I64),
+            (r.integers(0, 1000, n).astype(np.float64), ob.F64),
+            (1e6 + r.integers(0, 4000, n) / 8.0, ob.F64)]
+    for col, t in cols:
+        col[::1001] = col[0]                               # duplicates: stability
+        assert np.array_equal(host(ctx.sort(t, dev(col), desc)), oracle.sort(t, col, desc)), t
+
+
 def test_sort_reference_goldens(ctx):
     # SURVEY §8a probes of the reference: NaN first, -0.0 before +0.0; both directions stable
     f = np.array([1.0, np.nan, -0.0, 0.0, -1.0])

@@ -137,5 +137,16 @@ ctx.binop(capi.MUL, capi.I16, i16, capi.I16, i16)
 ctx.binop(capi.DIV, capi.U8, u8, capi.U8, u8)
 ctx.binop(capi.ADD, capi.U8, u8, capi.F64, 2.5)
 ctx.binop(capi.MOD, capi.I16, i16, capi.I64, 7)
+# the group-by exchange over peer memory with a world of one (publish / meet / fold / emit), 8-byte keys through the narrow passes
+import ctypes as C  # noqa: E402
+hnd = (C.c_char * 64)()
+capi.check(ctx.lib.rfb_peer_groups_create(ctx.h, 100_000, hnd))
+capi.check(ctx.lib.rfb_peer_groups_bind(ctx.h, 0, 1, C.c_char_p(bytes(hnd.raw))))
+mk = dev(r.integers(-50, 20_000, 60_000).astype(np.int64))
+ctx.group_merge_peers(mk, x[:60_000].contiguous(), y[:60_000].contiguous(), 30_000)
+ctx.group_merge_peers(mk, x[:60_000].contiguous(), y[:60_000].contiguous(), 30_000)
+os.environ["RFB_PART_MIN_ROWS"] = "1000"
+ctx.group_sum_count(capi.I64, dev(r.integers(0, 100_000, nn).astype(np.int64)), vn, 100_008)
+os.environ.pop("RFB_PART_MIN_ROWS", None)
 ctx.sync()
 print("sanitizer workload done, launches:", ctx.launches)
