@@ -25,11 +25,18 @@ constexpr int BLOCKS_PER_SM = 4;
 // The ids of one warp-step (<= 512) are staged in shared memory in output order and written out by the whole warp as
 // contiguous 256-byte stores: writing them straight from the lanes touches 32 different sectors per instruction (each lane
 // owns a ~64-byte run), which quadrupled the L2 write transactions.
-constexpr int MASK_J = 4;
-constexpr int MASK_TILE = THREADS * 16 * MASK_J;  // 16384 rows per tile
+// Tile size: one look-back per tile (a CTA barrier around a chain of L2 round trips) is the kernels' fixed cost, so long columns
+// take LARGE tiles (mask: 48 K rows, MASK_J = 12; typed predicate: 24 sub-tiles = 96 K rows of an 8-byte column) — measured per
+// 1e9 rows: where 1.42 -> 1.10 ms, cmp+where 2.49 -> 1.98 ms (0.93 of the HBM peak) against the 16 K-row tiles, which columns that
+// would not fill the GPU with large tiles keep (mask J = 2 / 4 / 8 / 12: 1.73 / 1.42 / 1.17 / 1.10 ms; SUB = 2 / 4 / 8 / 16 / 24 / 40:
+// 2.95 / 2.49 / 2.15 / 2.03 / 1.98 / 2.00 ms).
+constexpr int MASK_J_SMALL = 4, MASK_J_LARGE = 12, CMP_SUB_SMALL = 4, CMP_SUB_LARGE = 24;
+template <int MASK_J> struct MaskTile { static constexpr int TILE = THREADS * 16 * MASK_J; };
 
+template <int MASK_J>
 __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
 k_where_mask(const u8 *__restrict__ mask, i64 n, i64 *__restrict__ ids, TileCtl ctl) {
+    constexpr int MASK_TILE = MaskTile<MASK_J>::TILE;
     __shared__ TileSmem sm;
     __shared__ i64 stage[WARPS][512];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -88,31 +95,32 @@ k_where_mask(const u8 *__restrict__ mask, i64 n, i64 *__restrict__ ids, TileCtl 
 // ---- predicate on a typed column -> ids.  Lane owns R = 16/sizeof(P) consecutive rows per step; a warp walks SUB
 // sub-tiles of J steps each, keeping only the selection bits (J*R per sub-tile), so one look-back serves 16 K rows.
 // The store phase recomputes the in-warp ranks from the same ballots instead of keeping them in registers.
-template <typename P> struct CmpTile {
+template <typename P, int SUB_> struct CmpTile {
     static constexpr int R = 16 / (int)sizeof(P);
     static constexpr int J = (R <= 4) ? 8 : 32 / R;          // J*R <= 32 selection bits per sub-tile
-    static constexpr int SUB = 4;
+    static constexpr int SUB = SUB_;
     static constexpr int SROWS = 32 * R * J;                 // rows per warp per sub-tile
     static constexpr int WROWS = SROWS * SUB;
     static constexpr int TILE = WARPS * WROWS;
 };
 
-template <typename P>
+template <typename P, int SUBT>
 __global__ void __launch_bounds__(THREADS, BLOCKS_PER_SM)
 k_where_cmp(const P *__restrict__ x, PredRange pr, i64 n, bool vec_ok, i64 *__restrict__ ids, TileCtl ctl) {
-    constexpr int R = CmpTile<P>::R, J = CmpTile<P>::J, SUB = CmpTile<P>::SUB;
+    typedef CmpTile<P, SUBT> CT;
+    constexpr int R = CT::R, J = CT::J, SUB = CT::SUB;
     __shared__ TileSmem sm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 tile = blockIdx.x;
     const u32 lt = (1u << lane) - 1u;
-    const i64 wbase = (i64)tile * CmpTile<P>::TILE + (i64)warp * CmpTile<P>::WROWS;
+    const i64 wbase = (i64)tile * CT::TILE + (i64)warp * CT::WROWS;
     __shared__ u32 bits[SUB][THREADS];   // bit (j*R + e) = row (sub, j, lane, e) selected; thread-private column
     u32 warp_total = 0;
 #pragma unroll 1
     for (int s = 0; s < SUB; s++) {
-        const i64 sbase = wbase + (i64)s * CmpTile<P>::SROWS;
+        const i64 sbase = wbase + (i64)s * CT::SROWS;
         Vec16<P> v[J];
-        const bool full = vec_ok && sbase + CmpTile<P>::SROWS <= n;
+        const bool full = vec_ok && sbase + CT::SROWS <= n;
         if (full) {
 #pragma unroll
             for (int j = 0; j < J; j++) v[j].raw = ld_stream16(x + sbase + ((i64)j * 32 + lane) * R);
@@ -140,7 +148,7 @@ k_where_cmp(const P *__restrict__ x, PredRange pr, i64 n, bool vec_ok, i64 *__re
     u64 obase = scan::tile_offsets<WARPS>(ctl, tile, warp_total, sm);
 #pragma unroll 1
     for (int s = 0; s < SUB; s++) {
-        const i64 sbase = wbase + (i64)s * CmpTile<P>::SROWS;
+        const i64 sbase = wbase + (i64)s * CT::SROWS;
         const u32 mybits = bits[s][threadIdx.x];
 #pragma unroll
         for (int j = 0; j < J; j++) {
@@ -175,15 +183,23 @@ int finish_count(rfb_ctx_t *ctx, i64 *count) {
     return RFB_OK;
 }
 
-template <typename P>
-int where_cmp_t(rfb_ctx_t *ctx, const void *x, PredRange pr, i64 n, i64 *ids) {
-    const i64 tiles = (n + CmpTile<P>::TILE - 1) / CmpTile<P>::TILE;
+template <typename P, int SUB>
+int where_cmp_launch(rfb_ctx_t *ctx, const void *x, PredRange pr, i64 n, i64 *ids) {
+    const i64 tiles = (n + CmpTile<P, SUB>::TILE - 1) / CmpTile<P, SUB>::TILE;
     TileCtl ctl;
     int rc = prepare_tiles(ctx, tiles, &ctl);
     if (rc) return rc;
-    k_where_cmp<P><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>((const P *)x, pr, n, aligned16(x), ids, ctl);
+    k_where_cmp<P, SUB><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>((const P *)x, pr, n, aligned16(x), ids, ctl);
     RFB_CHECK_LAUNCH(ctx);
     return RFB_OK;
+}
+// large tiles when they still give every SM several rounds of CTAs
+inline bool large_tiles(const rfb_ctx_t *ctx, i64 n, i64 large_tile) { return n / large_tile >= (i64)ctx->sm_count * BLOCKS_PER_SM * 2; }
+
+template <typename P>
+int where_cmp_t(rfb_ctx_t *ctx, const void *x, PredRange pr, i64 n, i64 *ids) {
+    if (large_tiles(ctx, n, CmpTile<P, CMP_SUB_LARGE>::TILE)) return where_cmp_launch<P, CMP_SUB_LARGE>(ctx, x, pr, n, ids);
+    return where_cmp_launch<P, CMP_SUB_SMALL>(ctx, x, pr, n, ids);
 }
 
 // ---- gather
@@ -221,18 +237,21 @@ extern "C" int rfb_where_dev(rfb_ctx_t *ctx, const uint8_t *mask, int64_t n, int
     if (n == 0) return RFB_OK;
     TileCtl ctl;
     if (aligned16(mask)) {
-        const i64 tiles = (n + MASK_TILE - 1) / MASK_TILE;
+        const bool large = large_tiles(ctx, n, MaskTile<MASK_J_LARGE>::TILE);
+        const i64 tile = large ? MaskTile<MASK_J_LARGE>::TILE : MaskTile<MASK_J_SMALL>::TILE;
+        const i64 tiles = (n + tile - 1) / tile;
         int rc = prepare_tiles(ctx, tiles, &ctl);
         if (rc) return rc;
-        k_where_mask<<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(mask, n, ids, ctl);
+        if (large) k_where_mask<MASK_J_LARGE><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(mask, n, ids, ctl);
+        else k_where_mask<MASK_J_SMALL><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(mask, n, ids, ctl);
         RFB_CHECK_LAUNCH(ctx);
     } else {
         // unaligned payload: treat the bytes as a U8 column and select != 0 with the typed kernel's scalar path
         PredRange pr = make_pred_range(RFB_NE, key_of_i64(0));
-        const i64 tiles = (n + CmpTile<u8>::TILE - 1) / CmpTile<u8>::TILE;
+        const i64 tiles = (n + CmpTile<u8, CMP_SUB_SMALL>::TILE - 1) / CmpTile<u8, CMP_SUB_SMALL>::TILE;
         int rc = prepare_tiles(ctx, tiles, &ctl);
         if (rc) return rc;
-        k_where_cmp<u8><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(mask, pr, n, false, ids, ctl);
+        k_where_cmp<u8, CMP_SUB_SMALL><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(mask, pr, n, false, ids, ctl);
         RFB_CHECK_LAUNCH(ctx);
     }
     return finish_count(ctx, count);
