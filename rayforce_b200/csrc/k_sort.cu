@@ -306,7 +306,7 @@ int run_pass(rfb_ctx_t *ctx, Src src, i64 n, int G, i64 chunk, int shift, u32 *b
 #define RFB_OS_LB 4
 #endif
 #ifndef RFB_OS_CTAS32
-#define RFB_OS_CTAS32 3       // CTAs per SM of the passes over 32-bit key words
+#define RFB_OS_CTAS32 2       // CTAs per SM of the passes over 32-bit key words (16 x 3 / 20 x 2 / 24 x 2 / 20 x 3 / 12 x 4: i32 3.66 / 3.46 / 3.26 / 3.65 / 4.41 ms per 1e8 rows)
 #endif
 #ifndef RFB_OS_SLEEP
 #define RFB_OS_SLEEP 0
@@ -320,7 +320,12 @@ constexpr int OS_LB = RFB_OS_LB;
 #define RFB_OS_ITEMS 16
 #define RFB_OS_CTAS 2
 #endif
-constexpr int OS_T = 256, OS_W = OS_T / 32, OS_ITEMS = RFB_OS_ITEMS, OS_TILE = OS_T * OS_ITEMS;
+constexpr int OS_T = 256, OS_W = OS_T / 32;
+#ifndef RFB_OS_ITEMS32
+#define RFB_OS_ITEMS32 24     // 32-bit key words: 6144-row tiles (96 KB of stages, 2 CTAs per SM)
+#endif
+// rows per thread (tile = 256 x ITEMS rows) by key word
+template <typename K> struct OsGeom { static constexpr int ITEMS = sizeof(K) == 4 ? RFB_OS_ITEMS32 : RFB_OS_ITEMS, TILE = OS_T * ITEMS; };
 constexpr u64 OS_AGG = 1ULL << 54, OS_INC = 2ULL << 54, OS_FLAGS = 3ULL << 54, OS_COUNT = (1ULL << 54) - 1;
 
 // the key word a column travels as between passes: 32 bits for columns of up to 4 bytes (8 B per row moved, three CTAs per SM)
@@ -417,6 +422,7 @@ k_os_pass(Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *__restrict__
           u32 *__restrict__ tile_counter, typename Src::key_t *__restrict__ keys_out, u32 *__restrict__ rids_out, i64 *__restrict__ perm_out, bool staged) {
     typedef typename Src::raw_t raw_t;
     typedef typename Src::key_t K;
+    constexpr int OS_ITEMS = OsGeom<K>::ITEMS, OS_TILE = OsGeom<K>::TILE;
     __shared__ u32 whist[OS_W][RADIX];
     __shared__ i64 base[RADIX];     // output slot of the tile-local position 0 of each digit's run
     __shared__ u32 wsum[RADIX / 32];
@@ -583,7 +589,7 @@ k_os_pass(Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *__restrict__
 template <typename Src>
 int os_run_pass(rfb_ctx_t *ctx, Src src, i64 n, u32 tiles, int shift, u64 tag, const i64 *gbase, unsigned long long *status, u32 *counter,
                 typename Src::key_t *keys_out, u32 *rids_out, i64 *perm_out, bool last) {
-    constexpr int KB = (int)sizeof(typename Src::key_t), RB = (int)sizeof(typename Src::raw_t);
+    constexpr int KB = (int)sizeof(typename Src::key_t), RB = (int)sizeof(typename Src::raw_t), OS_TILE = OsGeom<typename Src::key_t>::TILE;
     constexpr int STAGE_BYTES = OS_TILE * (KB + RB + (Src::HAS_RIDS ? 8 : 4));   // sorted keys + staged raw keys + sorted row ids (+ staged row ids)
     constexpr int CTAS = KB == 4 ? RFB_OS_CTAS32 : RFB_OS_CTAS;
     const bool staged = aligned16(src.raw(0));
@@ -603,8 +609,9 @@ int os_run_pass(rfb_ctx_t *ctx, Src src, i64 n, u32 tiles, int shift, u64 tag, c
 
 // the executed passes over key words of type K (`base`: the key byte that became byte 0 of the word)
 template <typename T, typename K>
-int os_passes(rfb_ctx_t *ctx, const T *x, u64 flip, i64 n, u32 tiles, const int *passes, int np, int base, const i64 *gbase, unsigned long long *status,
+int os_passes(rfb_ctx_t *ctx, const T *x, u64 flip, i64 n, const int *passes, int np, int base, const i64 *gbase, unsigned long long *status,
               u32 *counters, void *keys_a, void *keys_b, u32 *ridsA, u32 *ridsB, i64 *perm) {
+    const u32 tiles = (u32)((n + OsGeom<K>::TILE - 1) / OsGeom<K>::TILE);
     OsColumnSrc<T, K> col{x, flip, 8 * base};
     K *keysA = (K *)keys_a, *keysB = (K *)keys_b;
     K *kin = nullptr, *kout = keysA;
@@ -630,7 +637,8 @@ int sort_onesweep(rfb_ctx_t *ctx, const void *x, i64 n, int descending, i64 *per
     const u64 width_mask = NPASS == 8 ? ~0ULL : ((1ULL << (8 * NPASS)) - 1);
     typedef typename OsKey<T>::type K;
     const u64 flip = descending ? width_mask : 0ULL;
-    const u32 tiles = (u32)((n + OS_TILE - 1) / OS_TILE);
+    constexpr int MIN_TILE = OS_T * (RFB_OS_ITEMS < RFB_OS_ITEMS32 ? RFB_OS_ITEMS : RFB_OS_ITEMS32);
+    const u32 tiles = (u32)((n + MIN_TILE - 1) / MIN_TILE);             // status words: sized for the smaller tile
     // workspace: ghist[8][256] u64 | gbase[8][256] i64 | counters[8] u32 | status[tiles][256] u64 | keysA[n] | keysB[n] | ridsA[n] | ridsB[n]
     const size_t b_hist = 8 * RADIX * 8, b_base = 8 * RADIX * 8, b_cnt = 256, b_status = align256((size_t)tiles * RADIX * 8),
                  b_k = align256((size_t)n * sizeof(K)), b_r = align256((size_t)n * 4);
@@ -668,8 +676,8 @@ int sort_onesweep(rfb_ctx_t *ctx, const void *x, i64 n, int descending, i64 *per
     // an 8-byte column whose varying bytes fit a 32-bit window (ids, dates, small integers, doubles of a narrow range) travels as
     // 32-bit key words like the narrow types: 8 B per row moved and three CTAs per SM instead of 12 B and two
     if (sizeof(K) == 8 && passes[np - 1] - passes[0] < 4)
-        return os_passes<T, u32>(ctx, (const T *)x, flip, n, tiles, passes, np, passes[0], gbase, status, counters, keysA, keysB, ridsA, ridsB, perm);
-    return os_passes<T, K>(ctx, (const T *)x, flip, n, tiles, passes, np, 0, gbase, status, counters, keysA, keysB, ridsA, ridsB, perm);
+        return os_passes<T, u32>(ctx, (const T *)x, flip, n, passes, np, passes[0], gbase, status, counters, keysA, keysB, ridsA, ridsB, perm);
+    return os_passes<T, K>(ctx, (const T *)x, flip, n, passes, np, 0, gbase, status, counters, keysA, keysB, ridsA, ridsB, perm);
 }
 
 template <typename T>

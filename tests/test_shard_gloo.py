@@ -69,6 +69,13 @@ def worker(rank, port, n, out_dir):
     ls = O.aggr(ob.SUM, ob.I64, val[lo:hi], gids, info.groups)[0]
     lc = O.aggr(ob.COUNT, ob.I64, val[lo:hi], gids, info.groups)[0]
     mk, ms, mc = shard.merge_group_partials(torch.from_numpy(lk), torch.from_numpy(ls), torch.from_numpy(lc), oracle_regroup(O))
+    # the peer-memory route declines a key domain that is not dense (every rank alike) and lands on the same all-gather merge
+    class Declines:
+        def group_merge_peers(self, *a):
+            from rayforce_b200 import capi
+            raise capi.RfbError(capi.ERR_TYPE, "not a dense domain")
+    pk, ps, pc = shard.merge_group_partials_peers(Declines(), torch.from_numpy(lk), torch.from_numpy(ls), torch.from_numpy(lc), 1 << 10, oracle_regroup(O))
+    assert torch.equal(pk, mk) and torch.equal(ps, ms) and torch.equal(pc, mc)
     var = shard.allgather_varlen(torch.arange(rank * 3 + 1, dtype=torch.int64))
     np.savez(os.path.join(out_dir, "r%d.npz" % rank), res=np.array(res, dtype=object), empty=np.array(empty, dtype=object), fsum=fsum,
              mk=mk.numpy(), ms=ms.numpy(), mc=mc.numpy(), var=var.numpy())
