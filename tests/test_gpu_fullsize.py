@@ -148,3 +148,43 @@ def test_sort_2e8_is_a_stable_sorted_permutation(ctx, desc):
     chk = torch.zeros(n, dtype=torch.int8, device="cuda")
     chk[perm] = 1
     assert int(chk.sum(dtype=torch.int64).item()) == n, "not a permutation"
+
+
+def test_where_and_cmp_where_1e9_large_tiles(ctx, big):
+    """the compaction kernels at the size where they take their LARGE tiles (96 K rows per tile for an 8-byte predicate column, 48 K
+    mask bytes): every id against torch.nonzero, on the full column"""
+    k = 1 << 39
+    ids = ctx.cmp_where(capi.LT, capi.I64, big, k)                  # nulls (INT64_MIN) compare below k: selected, like the reference
+    want = torch.nonzero(big < k).flatten()
+    assert ids.shape[0] == want.shape[0] and torch.equal(ids, want)
+    del ids
+    mask = (big < k).to(torch.uint8) * 7                             # any non-zero byte selects
+    ids = ctx.where(mask)
+    assert torch.equal(ids, want)
+    del ids, want, mask
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("desc", [False, True])
+def test_sort_wide_keys_1e8_and_narrow_window(ctx, desc):
+    """full-width 64-bit keys (eight single-sweep passes over 64-bit key words) and 32-bit-window keys at an offset (four passes over
+    32-bit key words, 6144-row tiles): sorted, stable, a permutation"""
+    n = 100_000_000
+    for modulus, shift in ((0, 0), (1 << 31, 20)):
+        k = torch.empty(n, dtype=torch.int64, device="cuda")
+        ctx.fill_splitmix(capi.I64, k, n, 13, modulus, 0, 0)
+        if shift:
+            k <<= shift
+        k[::3] = k[1]                                                # a third of the rows share one key: stability
+        perm = ctx.sort(capi.I64, k, desc)
+        sk = k[perm]
+        d_ok = (sk[1:] <= sk[:-1]) if desc else (sk[1:] >= sk[:-1])
+        assert bool(d_ok.all()), "keys not ordered along the permutation"
+        ties = sk[1:] == sk[:-1]
+        assert bool((perm[1:][ties] > perm[:-1][ties]).all()), "equal keys must keep their original order (stable)"
+        chk = torch.zeros(n, dtype=torch.int8, device="cuda")
+        chk[perm] = 1
+        assert int(chk.sum(dtype=torch.int64).item()) == n, "not a permutation"
+        del k, perm, sk, chk, d_ok, ties
+        torch.cuda.empty_cache()
+

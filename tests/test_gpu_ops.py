@@ -912,6 +912,17 @@ def test_sort_pass_structures_agree(ctx, oracle, monkeypatch, algo, desc):
         assert np.array_equal(host(ctx.sort(t, dev(col), desc)), oracle.sort(t, col, desc)), (algo, t)
 
 
+@pytest.mark.parametrize("n", [4095, 4096, 4097, 6143, 6144, 6145, 12288, 24577, 49_153])
+def test_sort_around_tile_boundaries(ctx, oracle, n):
+    """lengths around the tiles of the single-sweep passes (4096 rows for 64-bit key words, 6144 for 32-bit ones): the last tile is
+    the only one that is not staged by the TMA unit"""
+    r = np.random.default_rng(n)
+    for col, t in ((r.integers(-(1 << 62), 1 << 62, n).astype(np.int64), ob.I64), (r.integers(-(1 << 30), 1 << 30, n).astype(np.int32), ob.I32),
+                   (r.integers(0, 1 << 20, n).astype(np.int64), ob.I64), (r.standard_normal(n), ob.F64), (r.integers(-300, 300, n).astype(np.int16), ob.I16)):
+        assert np.array_equal(host(ctx.sort(t, dev(col))), oracle.sort(t, col, False)), t
+        assert np.array_equal(host(ctx.sort(t, dev(col), True)), oracle.sort(t, col, True)), t
+
+
 @pytest.mark.parametrize("desc", [False, True])
 def test_sort_narrow_windows_of_wide_columns(ctx, oracle, desc):
     """8-byte columns whose varying bytes fit a 32-bit window travel as 32-bit key words (window at byte 0, in the middle, at the
