@@ -28,9 +28,9 @@ constexpr int BLOCKS_PER_SM = 4;
 // Tile size: one look-back per tile (a CTA barrier around a chain of L2 round trips) is the kernels' fixed cost, so long columns
 // take LARGE tiles (mask: 48 K rows, MASK_J = 12; typed predicate: 24 sub-tiles = 96 K rows of an 8-byte column) — measured per
 // 1e9 rows: where 1.42 -> 1.10 ms, cmp+where 2.49 -> 1.98 ms (0.93 of the HBM peak) against the 16 K-row tiles, which columns that
-// would not fill the GPU with large tiles keep (mask J = 2 / 4 / 8 / 12: 1.73 / 1.42 / 1.17 / 1.10 ms; SUB = 2 / 4 / 8 / 16 / 24 / 40:
+// would not fill the GPU with large tiles keep, with a 32 K-row tier in between (mask J = 2 / 4 / 8 / 12: 1.73 / 1.42 / 1.17 / 1.10 ms; SUB = 2 / 4 / 8 / 16 / 24 / 40:
 // 2.95 / 2.49 / 2.15 / 2.03 / 1.98 / 2.00 ms).
-constexpr int MASK_J_SMALL = 4, MASK_J_LARGE = 12, CMP_SUB_SMALL = 4, CMP_SUB_LARGE = 24;
+constexpr int MASK_J_SMALL = 4, MASK_J_MEDIUM = 8, MASK_J_LARGE = 12, CMP_SUB_SMALL = 4, CMP_SUB_MEDIUM = 8, CMP_SUB_LARGE = 24;
 template <int MASK_J> struct MaskTile { static constexpr int TILE = THREADS * 16 * MASK_J; };
 
 template <int MASK_J>
@@ -199,6 +199,7 @@ inline bool large_tiles(const rfb_ctx_t *ctx, i64 n, i64 large_tile) { return n 
 template <typename P>
 int where_cmp_t(rfb_ctx_t *ctx, const void *x, PredRange pr, i64 n, i64 *ids) {
     if (large_tiles(ctx, n, CmpTile<P, CMP_SUB_LARGE>::TILE)) return where_cmp_launch<P, CMP_SUB_LARGE>(ctx, x, pr, n, ids);
+    if (large_tiles(ctx, n, CmpTile<P, CMP_SUB_MEDIUM>::TILE)) return where_cmp_launch<P, CMP_SUB_MEDIUM>(ctx, x, pr, n, ids);
     return where_cmp_launch<P, CMP_SUB_SMALL>(ctx, x, pr, n, ids);
 }
 
@@ -237,12 +238,13 @@ extern "C" int rfb_where_dev(rfb_ctx_t *ctx, const uint8_t *mask, int64_t n, int
     if (n == 0) return RFB_OK;
     TileCtl ctl;
     if (aligned16(mask)) {
-        const bool large = large_tiles(ctx, n, MaskTile<MASK_J_LARGE>::TILE);
-        const i64 tile = large ? MaskTile<MASK_J_LARGE>::TILE : MaskTile<MASK_J_SMALL>::TILE;
+        const int tier = large_tiles(ctx, n, MaskTile<MASK_J_LARGE>::TILE) ? 2 : large_tiles(ctx, n, MaskTile<MASK_J_MEDIUM>::TILE) ? 1 : 0;
+        const i64 tile = tier == 2 ? MaskTile<MASK_J_LARGE>::TILE : tier == 1 ? MaskTile<MASK_J_MEDIUM>::TILE : MaskTile<MASK_J_SMALL>::TILE;
         const i64 tiles = (n + tile - 1) / tile;
         int rc = prepare_tiles(ctx, tiles, &ctl);
         if (rc) return rc;
-        if (large) k_where_mask<MASK_J_LARGE><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(mask, n, ids, ctl);
+        if (tier == 2) k_where_mask<MASK_J_LARGE><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(mask, n, ids, ctl);
+        else if (tier == 1) k_where_mask<MASK_J_MEDIUM><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(mask, n, ids, ctl);
         else k_where_mask<MASK_J_SMALL><<<(unsigned)tiles, THREADS, 0, ctx->stream>>>(mask, n, ids, ctl);
         RFB_CHECK_LAUNCH(ctx);
     } else {
