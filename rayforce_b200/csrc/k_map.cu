@@ -232,6 +232,40 @@ struct DivConstI64 {                             // y != 0, y != NULL, |y| >= 2
     }
 };
 
+// the same for the 32-bit operator family (DIVI32 / MODI32 / XBARI32: TIME / DATE / I32 columns by a constant — `xbar time 60000`
+// is THE temporal bucketing operation): |t| < 2^31 is widened, divided with the 64-bit magic number and narrowed; the 32-bit
+// wrap-around of `x + 1 - y` inside xbar happens before the widening, as in the reference's int arithmetic
+struct DivConstI32 {                             // y != 0, y != NULL_I32, |y| >= 2
+    int op;
+    i32 y;
+    u64 ay;
+    DivMagic g;
+    __device__ __forceinline__ i32 operator()(i32 x, i32) const {
+        if (x == NULL_I32) return NULL_I32;
+        if (op == RFB_XBAR) {
+            const i32 t = x < 0 ? (i32)((u32)x + 1u - (u32)y) : x;
+            const u64 at = t < 0 ? 0ULL - (u64)(i64)t : (u64)t;
+            const u64 q = udiv_magic(at, g);
+            const i32 sq = ((t < 0) != (y < 0)) ? (i32)(0u - (u32)q) : (i32)(u32)q;      // truncating quotient
+            return (i32)((u32)sq * (u32)y);
+        }
+        const u64 ax = x < 0 ? 0ULL - (u64)(i64)x : (u64)x;
+        const u64 q = udiv_magic(ax, g), r = ax - q * ay;
+        const i32 fq = ((x < 0) != (y < 0)) ? (i32)(0u - (u32)q - (r != 0 ? 1u : 0u)) : (i32)(u32)q;   // floor quotient
+        return op == RFB_DIV ? fq : (i32)((u32)x - (u32)fq * (u32)y);
+    }
+};
+
+// a 32-bit column by an I64 atom (`xbar time 60000`: the literal is an i64): the reference widens the column (i32_to_i64 keeps
+// nullness), works in the 64-bit family and narrows the result (i64_to_time ...: nullness, then an (i32) cast)
+struct DivConstI64Narrow {
+    DivConstI64 f;
+    __device__ __forceinline__ i32 operator()(i32 x, i32) const {
+        const i64 r = f(x == NULL_I32 ? NULL_I64 : (i64)x, 0);
+        return r == NULL_I64 ? NULL_I32 : (i32)r;
+    }
+};
+
 // result typing: the per-case macro arguments of core/math.c:251-1782 / infer_*_type core/math.c:92-223
 bool binop_types(int op, int xt, int yt, int *mt, int *ot) {
     const bool okx = (xt == RFB_I32 || xt == RFB_I64 || xt == RFB_F64), oky = (yt == RFB_I32 || yt == RFB_I64 || yt == RFB_F64);
@@ -312,6 +346,7 @@ int binop_x(rfb_ctx_t *ctx, int op, int mt, int ot, int yt, bool lii, const void
 namespace {
 inline bool plain_num(int t) { return t == RFB_I32 || t == RFB_I64 || t == RFB_F64; }
 inline bool is_i64_like(int t) { return t == RFB_I64 || t == RFB_TIMESTAMP; }
+inline bool is_i32_like(int t) { return t == RFB_I32 || t == RFB_DATE || t == RFB_TIME; }
 }  // namespace
 
 // result vector type per operand form (0 vector-vector, 1 vector-atom, 2 atom-vector) over the reference's full type matrix
@@ -347,6 +382,25 @@ extern "C" int rfb_binop_dev(rfb_ctx_t *ctx, int op, int xt, const void *x, int6
                 return launch_map2<i64, i64, i64, false, true>(ctx, x, i64(), nullptr, d, out, xn, f);
             }
         }
+        if (c->form == 1 && c->fam == RFB_I32 && is_i32_like(c->lt) && is_i32_like(c->mt) && is_i32_like(c->ot) &&
+            (is_i32_like(c->rt) || is_i64_like(c->rt)) && (op == RFB_DIV || op == RFB_MOD || op == RFB_XBAR)) {
+            // the atom as the kernel would see it: rt_to_mt keeps nullness and narrows (i64_to_time ..., core/ops.h:247-252)
+            const i32 d = is_i32_like(c->rt) ? ys->v.i32 : (ys->v.i64 == NULL_I64 ? NULL_I32 : (i32)ys->v.i64);
+            if (d != 0 && d != NULL_I32 && d != 1 && d != -1) {
+                const u64 ad = d < 0 ? 0ULL - (u64)(i64)d : (u64)d;
+                DivConstI32 f{op, d, ad, div_magic_of(ad)};
+                return launch_map2<i32, i32, i32, false, true>(ctx, x, i32(), nullptr, d, out, xn, f);
+            }
+        }
+        if (c->form == 1 && c->fam == RFB_I64 && is_i32_like(c->lt) && c->mt == RFB_I64 && is_i64_like(c->rt) && is_i32_like(c->ot) &&
+            (op == RFB_DIV || op == RFB_MOD || op == RFB_XBAR)) {
+            const i64 d = ys->v.i64;
+            if (d != 0 && d != NULL_I64 && d != 1 && d != -1) {
+                const u64 ad = d < 0 ? 0ULL - (u64)d : (u64)d;
+                DivConstI64Narrow f{DivConstI64{op, d, ad, div_magic_of(ad)}};
+                return launch_map2<i32, i32, i32, false, true>(ctx, x, i32(), nullptr, 0, out, xn, f);
+            }
+        }
         return rfb_binop_matrix_dev(ctx, *c, x, xn, xs, y, yn, ys, out);
     }
     if (!binop_types(op, xt, yt, &mt, &ot)) { rfb_set_error("binop %d: unsupported operand types %d, %d", op, xt, yt); return RFB_ERR_TYPE; }
@@ -362,6 +416,14 @@ extern "C" int rfb_binop_dev(rfb_ctx_t *ctx, int op, int xt, const void *x, int6
             const u64 ad = d < 0 ? 0ULL - (u64)d : (u64)d;
             DivConstI64 f{op, d, ad, div_magic_of(ad)};
             return launch_map2<i64, i64, i64, false, true>(ctx, x, i64(), nullptr, d, out, xn, f);
+        }
+    }
+    if (xn >= 0 && yn < 0 && xt == RFB_I32 && yt == RFB_I32 && (op == RFB_DIV || op == RFB_MOD || op == RFB_XBAR)) {
+        const i32 d = ys->v.i32;
+        if (d != 0 && d != NULL_I32 && d != 1 && d != -1) {
+            const u64 ad = d < 0 ? 0ULL - (u64)(i64)d : (u64)d;
+            DivConstI32 f{op, d, ad, div_magic_of(ad)};
+            return launch_map2<i32, i32, i32, false, true>(ctx, x, i32(), nullptr, d, out, xn, f);
         }
     }
     switch (xt) {

@@ -290,6 +290,29 @@ def test_timestamp_division_by_a_constant_atom(ctx, oracle, op):
             assert gt == wt and np.array_equal(host(got), want), (yt, k)
 
 
+@pytest.mark.parametrize("op", [ob.DIV, ob.MOD, ob.XBAR])
+@pytest.mark.parametrize("xt", [ob.TIME, ob.DATE, ob.I32])
+def test_32bit_division_by_a_constant_atom(ctx, oracle, op, xt):
+    """TIME / DATE / I32 columns (/ | % | xbar) by an I32 / I64 atom: the 32-bit operator family on the magic-multiplier kernel
+    (`xbar time 60000`); every sign combination, extreme operands, divisors up to 2^31 - 1, the atoms the generic kernel keeps"""
+    r = np.random.default_rng(op * 10 + xt)
+    x = np.concatenate([r.integers(-(1 << 31) + 1, (1 << 31) - 1, 60_000), r.integers(-1000, 1000, 20_000),
+                        np.array([0, 1, -1, (1 << 31) - 1, -(1 << 31) + 1, ob.NULL_I32, 86_399_999, -86_400_000])]).astype(np.int32)
+    for yt in (ob.I32, ob.I64):
+        if oracle.binop_form(op, 1, xt, yt) < 0:
+            continue
+        for k in (60_000, 1000, 7, -7, 3, -3, 4096, -4096, 86_400_000, (1 << 31) - 1, -((1 << 31) - 1), 2, -2, 1, -1, 0, ob.NULL_I32 if yt == ob.I32 else ob.NULL_I64):
+            want, wt = oracle.binop(op, xt, x, yt, k)
+            got, gt = ctx.binop(op, xt, dev(x), yt, k)
+            assert gt == wt and np.array_equal(host(got), want), (yt, k, np.flatnonzero(host(got) != want)[:5])
+    if xt == ob.TIME:                # an I64 atom beyond 32 bits is narrowed like i64_to_time does it
+        for k in ((1 << 32) + 60_000, -(1 << 40) + 17):
+            if oracle.binop_form(op, 1, xt, ob.I64) >= 0:
+                want, wt = oracle.binop(op, xt, x, ob.I64, k)
+                got, gt = ctx.binop(op, xt, dev(x), ob.I64, k)
+                assert gt == wt and np.array_equal(host(got), want), k
+
+
 def test_binop_unaligned_typed_operands(ctx, oracle):
     """operand views that are not 16-byte aligned take the scalar path of k_binop_typed"""
     n = 30_001

@@ -86,6 +86,7 @@ def main():
         timed("sub_timestamp_timestamp_vv", lambda: ctx.binop(capi.SUB, capi.TIMESTAMP, x, capi.TIMESTAMP, y), 24 * n)
         timed("xbar_timestamp_va", lambda: ctx.binop(capi.XBAR, capi.TIMESTAMP, x, capi.I64, 60_000_000_000), 16 * n, "generic 64-bit division inside the typed kernel")
         timed("xbar_time_va", lambda: ctx.binop(capi.XBAR, capi.TIME, tcol, capi.I32, 60_000), 8 * n)
+        timed("xbar_time_i64atom", lambda: ctx.binop(capi.XBAR, capi.TIME, tcol, capi.I64, 60_000), 8 * n, "`xbar time 60000`: the literal is an i64 atom")
         del tcol
         del x
         # config 3: fp64 a*b+c -> avg
