@@ -66,6 +66,13 @@ static double now_ms(void) {
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
+/* RFB200_SHIM_TRACE=<ms>: report every GPU-served operator call that took longer (first-touch shipments, fault-ins) */
+static void trace_slow(int slot, double dt) {
+    static double limit = -2.0;
+    if (limit < -1.0) { const char *e = getenv("RFB200_SHIM_TRACE"); limit = e ? atof(e) : -1.0; }
+    if (limit >= 0.0 && dt >= limit) fprintf(stderr, "[rfb200 shim] slow call: %-16s %10.2f ms\n", S_NAME[slot], dt);
+}
+
 static void print_stats(void) {
     long g = 0, c = 0;
     for (int i = 0; i < S_N; i++) { g += n_gpu[i]; c += n_cpu[i]; }
@@ -121,7 +128,7 @@ static int gpu_ok(void) {
         const double t0 = stats_on() ? now_ms() : 0.0;                     \
         if (gpu_ok()) {                                                    \
             obj_p r = (obj_p)rfb_##sym((rfb_obj_p)x);                      \
-            if (r) { n_gpu[slot]++; if (want_stats) t_gpu[slot] += now_ms() - t0; return r; } \
+            if (r) { n_gpu[slot]++; if (want_stats) { const double dt = now_ms() - t0; t_gpu[slot] += dt; trace_slow(slot, dt); } return r; } \
         }                                                                  \
         n_cpu[slot]++;                                                     \
         obj_p c = __real_##sym(x);                                         \
@@ -134,7 +141,7 @@ static int gpu_ok(void) {
         const double t0 = stats_on() ? now_ms() : 0.0;                     \
         if (gpu_ok()) {                                                    \
             obj_p r = (obj_p)rfb_##sym((rfb_obj_p)x, (rfb_obj_p)y);        \
-            if (r) { n_gpu[slot]++; if (want_stats) t_gpu[slot] += now_ms() - t0; return r; } \
+            if (r) { n_gpu[slot]++; if (want_stats) { const double dt = now_ms() - t0; t_gpu[slot] += dt; trace_slow(slot, dt); } return r; } \
         }                                                                  \
         n_cpu[slot]++;                                                     \
         obj_p c = __real_##sym(x, y);                                      \

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
+#include <time.h>
 #include <unistd.h>
 
 #include "rfb200.h"
@@ -278,6 +279,24 @@ static uint64_t fingerprint(const void *payload, size_t bytes) {
     return (h ^ w) * 0x94D049BB133111EBULL;
 }
 
+/* RFB200_OPS_TRACE=<ms>: report the layer's own slow steps (column shipments, device allocations, lazy fault-ins, kernels) */
+static double ops_now_ms(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+static double ops_trace_limit(void) {
+    static double limit = -2.0;
+    if (limit < -1.0) { const char *e = getenv("RFB200_OPS_TRACE"); limit = e ? atof(e) : -1.0; }
+    return limit;
+}
+static void ops_trace(const char *what, double t0, size_t bytes) {
+    const double limit = ops_trace_limit();
+    if (limit < 0.0) return;
+    const double dt = ops_now_ms() - t0;
+    if (dt >= limit) fprintf(stderr, "[rfb200 ops] %-22s %10.2f ms  %12zu bytes\n", what, dt, bytes);
+}
+
 /* ------------------------------------------------------------------ lazily materialised results (opt-in: RFB200_LAZY=1)
  *
  * Inside a query scope most operator results are consumed by the next GPU operator (mask -> where -> gather/fold), yet
@@ -307,11 +326,14 @@ static void lazy_invalidate_image(void *dev) {
 }
 
 static void lazy_fill(lazy_t *z, int in_handler) { /* pages -> read/write, bytes <- device */
+    const double t0 = ops_trace_limit() >= 0.0 ? ops_now_ms() : 0.0;
     mprotect(z->lo, (size_t)(z->hi - z->lo), PROT_READ | PROT_WRITE);
     rfb_sync(G.ctx);
     /* inside the signal handler: plain synchronous copy, free of our own threads and locks; otherwise the fast ring */
     if (in_handler) rfb_d2h_plain(G.ctx, z->lo, (const char *)z->dev + (z->lo - z->payload), (size_t)(z->hi - z->lo));
     else { rfb_d2h(G.ctx, z->lo, (const char *)z->dev + (z->lo - z->payload), (size_t)(z->hi - z->lo)); rfb_sync(G.ctx); }
+    if (!in_handler) ops_trace("lazy fill (scope end)", t0, (size_t)(z->hi - z->lo));
+    else if (ops_trace_limit() >= 0.0) { char b[96]; const int k = snprintf(b, sizeof b, "[rfb200 ops] lazy fault-in %.2f ms %zu bytes\n", ops_now_ms() - t0, (size_t)(z->hi - z->lo)); if (k > 0) (void)!write(2, b, (size_t)k); }
 }
 
 static void lazy_segv(int sig, siginfo_t *si, void *uc) {
@@ -487,6 +509,7 @@ static void *dev_buffer(size_t bytes, size_t *got) {
         return d;
     }
     void *d = NULL;
+    const double t0 = ops_trace_limit() >= 0.0 ? ops_now_ms() : 0.0;
     if (rfb_dev_alloc(G.ctx, bytes, &d) != RFB_OK) {
         /* out of device memory: drop the pool and retry once */
         for (int i = 0; i < G.npool; i++) rfb_dev_free(G.ctx, G.pool[i].dev);
@@ -494,6 +517,7 @@ static void *dev_buffer(size_t bytes, size_t *got) {
         if (rfb_dev_alloc(G.ctx, bytes, &d) != RFB_OK) { set_err("%s", rfb_last_error()); return NULL; }
     }
     *got = bytes;
+    ops_trace("device allocation", t0, bytes);
     return d;
 }
 
@@ -541,7 +565,9 @@ static void *dev_payload(const void *payload, int64_t len, int type, int keep) {
     size_t got = 0;
     void *d = dev_buffer((size_t)len * w, &got);
     if (!d) return NULL;
+    const double t0 = ops_trace_limit() >= 0.0 ? ops_now_ms() : 0.0;
     if (len > 0 && rfb_h2d(G.ctx, d, payload, (size_t)len * w) != RFB_OK) { set_err("%s", rfb_last_error()); rfb_dev_free(G.ctx, d); return NULL; }
+    ops_trace("column shipment", t0, (size_t)len * w);
     if (!track(d, got, payload, len, type, keep)) { rfb_sync(G.ctx); rfb_dev_free(G.ctx, d); return NULL; }
     G.stat_ships++;
     return d;
@@ -1147,8 +1173,11 @@ static obj_p aggr_op(int op, obj_p val, obj_p index) {
     void *dv = dev_column(val), *dg = dev_column(gids), *df = filtered ? dev_column(filter) : NULL;
     void *dout = dev_temp((size_t)(groups > 0 ? groups : 1) * 8);
     if (!dv || !dg || (filtered && !df) || !dout) { res = G.host->err_limit(); goto out; }
+    if (ops_trace_limit() >= 0.0) { const double tp = ops_now_ms(); rfb_sync(G.ctx); ops_trace("pending before aggr", tp, 0); }
+    const double t0 = ops_trace_limit() >= 0.0 ? ops_now_ms() : 0.0;
     int rc = rfb_aggr_dev(G.ctx, op, val->type, dv, (const int64_t *)df, (const int64_t *)dg, len, groups, dout);
     if (rc) { res = status_to_obj(rc); goto out; }
+    if (ops_trace_limit() >= 0.0) { rfb_sync(G.ctx); ops_trace("rfb_aggr_dev", t0, (size_t)len * 8); }
     res = to_host_vector(ot, groups, dout);
 out:
     leave(sc);
