@@ -406,17 +406,26 @@ static void lazy_on_free(const void *obj) {
     }
 }
 
-/* is [lo, hi) still one of OUR protected ranges?  (/proc/self/maps: a mapping with no permissions covering it) */
+/* is [lo, hi) still one of OUR protected ranges?  /proc/self/maps (sorted by address): every byte of the range must lie in a
+ * mapping without read and write permission.  The range may span SEVERAL such mappings — mprotect splits mappings, and two
+ * neighbours with different histories (an allocator arena that grew by a second mmap) do not merge back into one line — so the
+ * lines are walked in order; a hole or a readable / writable piece means the host has unmapped or reused the block. */
 static int lazy_still_ours(const char *lo, const char *hi) {
     FILE *f = fopen("/proc/self/maps", "r");
     if (!f) return 0;
     char line[512];
+    unsigned long cur = (unsigned long)lo;
+    const unsigned long end = (unsigned long)hi;
     int ours = 0;
     while (fgets(line, sizeof(line), f)) {
         unsigned long a, b;
         char perms[8];
         if (sscanf(line, "%lx-%lx %7s", &a, &b, perms) != 3) continue;
-        if ((unsigned long)lo >= a && (unsigned long)hi <= b) { ours = (perms[0] == '-' && perms[1] == '-'); break; }
+        if (b <= cur) continue;                       /* below the part still to be covered */
+        if (a > cur) break;                           /* a hole: unmapped */
+        if (perms[0] != '-' || perms[1] != '-') break;   /* somebody else's memory now */
+        cur = b;
+        if (cur >= end) { ours = 1; break; }
     }
     fclose(f);
     return ours;
