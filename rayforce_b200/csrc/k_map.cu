@@ -266,6 +266,49 @@ struct DivConstI64Narrow {
     }
 };
 
+// ... and when that I64 atom fits 32 bits (it nearly always does: `xbar time 60000`), every intermediate of the reference's 64-bit
+// arithmetic on a widened 32-bit operand stays below 2^32 in magnitude, so the division runs on a 32-bit magic number (one
+// 32-bit multiply-high) and the narrowing (i32) cast of the 64-bit result equals the wrapped 32-bit product
+struct DivMagic32 { u32 m; int more; };
+__device__ __forceinline__ u32 udiv_magic32(u32 n, const DivMagic32 &g) {
+    const u32 q = __umulhi(g.m, n);
+    return (((n - q) >> 1) + q) >> g.more;
+}
+static DivMagic32 div_magic32_of(u32 d) {        // 2 <= d < 2^31
+    DivMagic32 g;
+    const int fl = 31 - __builtin_clz(d);
+    if ((d & (d - 1)) == 0) { g.m = 0; g.more = fl - 1; return g; }
+    const u64 num = 1ULL << (32 + fl);
+    u32 pm = (u32)(num / d);
+    const u32 rem = (u32)(num % d);
+    pm += pm;
+    const u32 twice = rem + rem;
+    if (twice >= d || twice < rem) pm += 1;
+    g.m = pm + 1;
+    g.more = fl;
+    return g;
+}
+struct DivConstI64Narrow32 {                     // y: an I64 atom with 2 <= |y| < 2^31
+    int op;
+    i64 y;
+    u32 ay;
+    DivMagic32 g;
+    __device__ __forceinline__ i32 operator()(i32 x, i32) const {
+        if (x == NULL_I32) return NULL_I32;
+        if (op == RFB_XBAR) {
+            const i64 t = x < 0 ? (i64)x + 1 - y : (i64)x;                  // |t| < 2^32
+            const u32 at = (u32)(t < 0 ? -t : t);
+            const u32 q = udiv_magic32(at, g);
+            const u32 sq = ((t < 0) != (y < 0)) ? 0u - q : q;                // truncating quotient, mod 2^32
+            return (i32)(sq * (u32)y);
+        }
+        const u32 ax = (u32)(x < 0 ? -(i64)x : (i64)x);
+        const u32 q = udiv_magic32(ax, g), r = ax - q * ay;
+        const u32 fq = ((x < 0) != (y < 0)) ? 0u - q - (r != 0 ? 1u : 0u) : q;   // floor quotient, mod 2^32
+        return op == RFB_DIV ? (i32)fq : (i32)((u32)x - fq * (u32)y);
+    }
+};
+
 // result typing: the per-case macro arguments of core/math.c:251-1782 / infer_*_type core/math.c:92-223
 bool binop_types(int op, int xt, int yt, int *mt, int *ot) {
     const bool okx = (xt == RFB_I32 || xt == RFB_I64 || xt == RFB_F64), oky = (yt == RFB_I32 || yt == RFB_I64 || yt == RFB_F64);
@@ -397,6 +440,10 @@ extern "C" int rfb_binop_dev(rfb_ctx_t *ctx, int op, int xt, const void *x, int6
             const i64 d = ys->v.i64;
             if (d != 0 && d != NULL_I64 && d != 1 && d != -1) {
                 const u64 ad = d < 0 ? 0ULL - (u64)d : (u64)d;
+                if (ad < (1ULL << 31)) {
+                    DivConstI64Narrow32 f32{op, d, (u32)ad, div_magic32_of((u32)ad)};
+                    return launch_map2<i32, i32, i32, false, true>(ctx, x, i32(), nullptr, 0, out, xn, f32);
+                }
                 DivConstI64Narrow f{DivConstI64{op, d, ad, div_magic_of(ad)}};
                 return launch_map2<i32, i32, i32, false, true>(ctx, x, i32(), nullptr, 0, out, xn, f);
             }
