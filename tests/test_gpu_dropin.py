@@ -8,6 +8,7 @@ The binaries are built by oracle/Makefile in the authoring container (they need 
 snapshot (oracle/_ref is git-ignored, not gpurun-ignored); nothing here reads /root/reference."""
 import os
 import re
+import shutil
 import subprocess
 
 import pytest
@@ -86,10 +87,25 @@ def test_rayfall_script_output_is_identical_stock_vs_dropin(lazy):
         assert m and int(m.group(1)) > 20 and int(m.group(3)) > 0, err1[-2000:]
 
 
+def loadfn_misfired(out):
+    """The reference's own `loadfn` reports a spurious error on some address-space layouts: dynlib_loadfn tests
+    `IS_ERR((obj_p)dl)` on the dynlib_t it has just opened (reference core/dynlib.c:153-161), which reads byte 2 of the struct —
+    bits 16-23 of the heap address of the path string — and takes 0x7f (TYPE_ERR, core/rayforce.h:95) there for an error object.
+    The script then stops at the loadfn line ("Error: ok", errno 0) and the process faults later in
+    runtime_destroy -> dynlib_close -> drop_obj (core/runtime.c:225-229).  No code of the library has run at that point (the
+    address is chosen before dlopen); measured on the B200 box: 6 of 82 runs (tools/run_plugin_loop.sh, fault trace in
+    INTEGRATION.md §5).  Such a run says nothing about the plugin and is repeated."""
+    return "loadfn" in out and "Error" in out and not re.search(r"plugin\s+\(sum x\)", out)
+
+
 def test_stock_binary_loads_the_fused_entry_point_as_a_plugin():
     stock = need("rayforce_ref")
-    rc, out, err = run([stock, "-f", os.path.join("integration", "demo", "plugin.rfl")])
-    assert rc == 0, err[-2000:]
+    unbuffered = [shutil.which("stdbuf"), "-o0"] if shutil.which("stdbuf") else []   # the error report must survive the later fault
+    for attempt in range(8):
+        rc, out, err = run(unbuffered + [stock, "-f", os.path.join("integration", "demo", "plugin.rfl")])
+        if not loadfn_misfired(out):
+            break
+    assert rc == 0, out[-2000:] + err[-2000:]
     a = re.search(r"plugin\s+\(sum x\) where \(< x 500000\) : (\d+)", out)
     b = re.search(r"select\s+\(sum x\) where \(< x 500000\) : \[(\d+)\]", out)
     assert a and b and a.group(1) == b.group(1), out
