@@ -43,6 +43,8 @@ GOLDEN = 0x9E3779B97F4A7C15
 METRIC = "billion rows/sec on 1e9-row int64 filter+sum"
 UNIT = "Grows/s"
 CPU_SAMPLE_ROWS = 100_000_000
+COLLECT_EVERY = 10         # device-resident loop: the host waits for (and checks) the result of every 10th pass; the passes in
+                           # between are queued behind each other on the stream, each still delivering its merged result to host memory
 
 
 def shifted_seed(seed: int, first_row: int) -> int:
@@ -249,6 +251,8 @@ def workload_config(args, world, merge_mode="nccl"):
                         "k = 2^39 (50%% selectivity), %d rows per GPU sharded by row range" % args.rows,
             "rows_per_gpu": args.rows, "global_rows": args.rows * world, "selectivity": 0.5,
             "l2_policy": "inputs (8 GB per GPU) far exceed the 126 MB L2; no flush needed",
+            "host_collects": "every pass writes its (merged) result into mapped host memory from the GPU; the host waits for and "
+                             "checks every %dth pass and the last one, the passes in between are queued on the stream" % COLLECT_EVERY,
             "merge": "none (1 GPU)" if world == 1 else MERGE_TEXT.get(merge_mode, merge_mode)}
 
 
@@ -490,15 +494,20 @@ def run_gpu_arm(args):
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)            # all ranks or none
             merge_mode = "peer" if int(flag.item()) == 1 else "nccl"
 
-    def step_resident(ev_s=None, ev_e=None):
-        """one pass, column resident in HBM -> (rows, sum) on the host"""
+    def step_resident(ev_s=None, ev_e=None, collect=True):
+        """one pass, column resident in HBM -> (rows, sum) on the host.  Every pass ends with the GPU writing its (merged)
+        result into mapped host memory; collect=False only skips the HOST's wait for it, so that the next pass is already
+        queued behind this one (a stream of queries) — the host then reads the result of a later pass (COLLECT_EVERY)."""
         if world > 1 and merge_mode == "peer":
             if ev_s is not None:
                 ev_s.record(stream)
             ctx.filter_fold_async(capi.LT, capi.I64, x, K_CONST, capi.F_SUM | capi.F_CNT, capi.I64, x, n)
             if ev_e is not None:
                 ev_e.record(stream)
-            r = ctx.fold_allreduce_peers(capi.I64)
+            ctx.fold_allreduce_peers_async(capi.I64)
+            if not collect:
+                return None
+            r = ctx.fold_peers_result(capi.I64)
             return r.nonnull, r.sum
         if world == 1:
             if ev_s is not None:
@@ -506,6 +515,8 @@ def run_gpu_arm(args):
             ctx.filter_fold_async(capi.LT, capi.I64, x, K_CONST, capi.F_SUM | capi.F_CNT, capi.I64, x, n)
             if ev_e is not None:
                 ev_e.record(stream)
+            if not collect:
+                return None
             r = ctx.fold_result(capi.I64)
             return r.nonnull, r.sum
         ctx.set_result_ptr(res)
@@ -536,7 +547,10 @@ def run_gpu_arm(args):
         sampler.start()
     t_start.record(stream)
     for i in range(K):
-        got = step_resident(*evs[i])
+        r = step_resident(*evs[i], collect=(i % COLLECT_EVERY == COLLECT_EVERY - 1 or i == K - 1))
+        if r is not None:
+            assert r == first, "non-deterministic result %r vs %r at step %d" % (r, first, i)
+            got = r
     t_end.record(stream)
     torch.cuda.synchronize()
     if world > 1:

@@ -353,7 +353,10 @@ int rfb_fold_host(rfb_ctx_t *ctx, int folds, int type, const void *x, int64_t n,
  *                                                  rank's partial into every peer's mailbox (P2P stores over NVLink + a sequence
  *                                                  flag), waits for the peers' partials, folds them in rank order and reports
  *                                                  the merged rfb_fold_t where a single-GPU fold reports.  Every rank must call
- *                                                  it the same number of times.  Bit-identical on all ranks. */
+ *                                                  it the same number of times.  Bit-identical on all ranks.
+ *                                                  out == NULL: launch only — queries can be queued back to back (fold, exchange,
+ *                                                  fold, exchange ... on the context's stream) without a host synchronisation;
+ *     rfb_fold_peers_result(ctx, out)              drains the stream and reports the merged result of the last exchange. */
 int rfb_peer_mailbox_create(rfb_ctx_t *ctx, void *ipc_handle_64);
 /* The exchange step of a group-by sharded by row range (`select {(sum v) (count v)} by k`), over NVLink peer memory:
  *     rfb_peer_groups_create(ctx, capacity, h)     this rank's exchange buffer (two halves of capacity (key, sum, count) rows) and
@@ -373,6 +376,7 @@ int rfb_group_merge_peers(rfb_ctx_t *ctx, const int64_t *keys, const int64_t *su
                           int64_t *out_keys, int64_t *out_sums, int64_t *out_counts, int64_t max_groups, int64_t *groups);
 int rfb_peer_mailbox_bind(rfb_ctx_t *ctx, int rank, int world, const void *handles);
 int rfb_fold_allreduce_peers(rfb_ctx_t *ctx, int val_type, rfb_fold_t *out);
+int rfb_fold_peers_result(rfb_ctx_t *ctx, rfb_fold_t *out);
 
 /* The fused multi-column queries over HOST columns (configs 3-5 end to end): the columns are shipped whole, then
  * rfb_group_sum_count_dev / rfb_fma_fold_dev run; group lists come back into HOST arrays of max_groups entries. */

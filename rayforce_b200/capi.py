@@ -143,6 +143,7 @@ SIGNATURES = {
     "rfb_peer_mailbox_create": (_ci, [_vp, _vp]),
     "rfb_peer_mailbox_bind": (_ci, [_vp, _ci, _ci, _vp]),
     "rfb_fold_allreduce_peers": (_ci, [_vp, _ci, _P(Fold)]),
+    "rfb_fold_peers_result": (_ci, [_vp, _P(Fold)]),
     "rfb_peer_groups_create": (_ci, [_vp, _i64, _vp]),
     "rfb_peer_groups_bind": (_ci, [_vp, _ci, _ci, _vp]),
     "rfb_group_merge_peers": (_ci, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _P(_i64)]),

@@ -122,7 +122,7 @@ extern "C" int rfb_peer_mailbox_bind(rfb_ctx_t *ctx, int rank, int world, const 
 }
 
 extern "C" int rfb_fold_allreduce_peers(rfb_ctx_t *ctx, int val_type, rfb_fold_t *out) {
-    RFB_ARG(ctx && out && ctx->mbox_world >= 1, "rfb_fold_allreduce_peers: bind the mailboxes first");
+    RFB_ARG(ctx && ctx->mbox_world >= 1, "rfb_fold_allreduce_peers: bind the mailboxes first");
     if (ctx->result_override) { rfb_set_error("fold results are redirected (rfb_ctx_set_result_ptr)"); return RFB_ERR_ARG; }
     const int vk = rfb_kind_of(val_type);
     if (!vk) { rfb_set_error("peer all-reduce: unsupported value type %d", val_type); return RFB_ERR_TYPE; }
@@ -134,8 +134,19 @@ extern "C" int rfb_fold_allreduce_peers(rfb_ctx_t *ctx, int val_type, rfb_fold_t
     if (vk == K_F64) k_peer_allreduce<true><<<1, 32, 0, ctx->stream>>>(local, pe, ctx->mbox_rank, ctx->mbox_world, seq, vk, merged);
     else k_peer_allreduce<false><<<1, 32, 0, ctx->stream>>>(local, pe, ctx->mbox_rank, ctx->mbox_world, seq, vk, merged);
     RFB_CHECK_LAUNCH(ctx);
+    if (!out) return RFB_OK;    // asynchronous form: the merged result is collected with rfb_fold_peers_result()
     RFB_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(out, merged, sizeof(rfb_fold_t));
+    return RFB_OK;
+}
+
+// the merged result of the LAST rfb_fold_allreduce_peers(ctx, type, NULL) on this context (drains the stream first).  Fold and
+// exchange launches may be queued back to back without a host synchronisation in between: both are ordered by the stream, and
+// the two-buffer argument above only needs that order.
+extern "C" int rfb_fold_peers_result(rfb_ctx_t *ctx, rfb_fold_t *out) {
+    RFB_ARG(ctx && out && ctx->mbox_world >= 1, "rfb_fold_peers_result: bind the mailboxes first");
+    RFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, (rfb_fold_t *)ctx->h_result + (RFB_RESULT_SLOTS - 1), sizeof(rfb_fold_t));
     return RFB_OK;
 }
 

@@ -167,6 +167,15 @@ class Context:
         check(self.lib.rfb_fold_allreduce_peers(self.h, type_, C.byref(f)))
         return FoldResult(f, type_)
 
+    def fold_allreduce_peers_async(self, type_: int) -> None:
+        """enqueue the exchange only; collect the last one with fold_peers_result()"""
+        check(self.lib.rfb_fold_allreduce_peers(self.h, type_, None))
+
+    def fold_peers_result(self, type_: int) -> FoldResult:
+        f = Fold()
+        check(self.lib.rfb_fold_peers_result(self.h, C.byref(f)))
+        return FoldResult(f, type_)
+
     def peer_groups_setup(self, rank: int, world: int, capacity: int, group=None) -> None:
         """one process per GPU: this rank's group exchange buffer (capacity rows), IPC handles exchanged over torch.distributed"""
         import torch.distributed as dist

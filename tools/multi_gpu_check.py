@@ -60,6 +60,13 @@ def main():
                 ctx.filter_fold_async(capi.LT, capi.I64, x, K, capi.F_ALL, capi.I64, x, n)
                 pr = ctx.fold_allreduce_peers(capi.I64)
                 peer_ok &= (pr.rows, pr.nonnull, pr.sum, pr.min, pr.max) == tuple(merged)
+            # queued back to back without a host synchronisation (what bench.py's device-resident loop does): seven fold +
+            # exchange pairs, alternating predicates so that a stale mailbox buffer would show, one collection at the end
+            for i in range(7):
+                ctx.filter_fold_async(capi.LT if i % 2 == 0 else capi.GE, capi.I64, x, K, capi.F_ALL, capi.I64, x, n)
+                ctx.fold_allreduce_peers_async(capi.I64)
+            pr = ctx.fold_peers_result(capi.I64)
+            peer_ok &= (pr.rows, pr.nonnull, pr.sum, pr.min, pr.max) == tuple(merged)
         except Exception as e:                                   # CUDA IPC not available in this sandbox: reported, not fatal
             peer_ok = None
             peer_err = str(e)
