@@ -927,6 +927,38 @@ __device__ __forceinline__ void sacc_add_small(const SAcc &a, u32 s, i64 v) {
     atomicAdd(&a.cnt[s], 1u);
 }
 
+// 32-bit records (values below 2^VB <= 2^20): ONE shared atomic per record.  The slot's first word packs the record count (top 8
+// bits) over the value sum (low 24 bits): a record adds 2^24 + v.  With T the exact total of what was added, the word is
+// T mod 2^32.  The adder whose value overflowed the 24-bit sum field sees it in the returned old word (the low 24 bits evolve as
+// sum mod 2^24 whatever the upper bits do) and counts a CARRY in the second word; the adder that wrapped the whole word counts a
+// WRAP in the third.  Both events are exact functions of (old, increment), so at flush time
+//     T = wraps * 2^32 + word,   sum = carries * 2^24 + (word mod 2^24),   count = (T >> 24) - carries
+// hold exactly.  A carry needs ~2^24 / v records (>= 16), a wrap <= 256: 1.07 atomics per record instead of 2.
+__device__ __forceinline__ void sacc_add_packed(const SAcc &a, u32 s, u32 v) {
+    const u32 inc = (1u << 24) + v;
+    const u32 old = atomicAdd(&a.lo[s], inc);
+    if ((old & 0xFFFFFFu) + v >= (1u << 24)) atomicAdd(&a.hi[s], 1u);
+    if ((u32)(old + inc) < inc) atomicAdd(&a.cnt[s], 1u);
+}
+__device__ __forceinline__ void sacc_flush_packed(const SAcc &a, int slots, i64 slot0, const Accums &ga) {
+    for (int s = threadIdx.x; s < slots; s += blockDim.x) {
+        const u32 w = a.lo[s], carries = a.hi[s], wraps = a.cnt[s];
+        if (!(w | carries | wraps)) continue;
+        const i64 g = slot0 + s;
+        const u64 total = ((u64)wraps << 32) | w;
+        const u64 sum = ((u64)carries << 24) + (w & 0xFFFFFFu);
+        if (sum) atomicAdd((unsigned long long *)ga.sum + g, (unsigned long long)sum);
+        atomicAdd((unsigned long long *)ga.cnt + g, (unsigned long long)((total >> 24) - carries));
+        a.lo[s] = 0; a.hi[s] = 0; a.cnt[s] = 0;
+    }
+}
+template <typename REC> __device__ __forceinline__ void msa_add(const SAcc &a, u32 s, i64 v) {
+    if constexpr (sizeof(REC) == 4) sacc_add_packed(a, s, (u32)v); else sacc_add_small(a, s, v);
+}
+template <typename REC> __device__ __forceinline__ void msa_flush(const SAcc &a, int slots, i64 slot0, const Accums &ga) {
+    if constexpr (sizeof(REC) == 4) sacc_flush_packed(a, slots, slot0, ga); else sacc_flush(a, slots, slot0, ga);
+}
+
 // accumulate pass of the narrow path: one CTA per SM, the partition's records staged by the TMA unit (cp.async.bulk into an
 // mbarrier ring) next to the partition's 2^KPL accumulators.  Partition p = absolute bucket ((kbase >> KPL) + p) mod 32.
 constexpr int MS_UNIT = 4096;                   // records per work unit
@@ -1005,7 +1037,7 @@ k_ms_accum_tma(RecStore rs, int P, i64 kbase, i64 kmin, Accums ga) {
         __syncthreads();                                                       // unit u-1 fully consumed: its stage may be re-armed
         if (tid == 0 && u + (STAGES - 1) < u1) issue(u + (STAGES - 1));
         if (s_ubase[p + 1] <= u) {
-            if (dirty) sacc_flush(a, KPN, (i64)((u64)kbase + (u64)p * KPN - (u64)kmin), ga);
+            if (dirty) msa_flush<REC>(a, KPN, (i64)((u64)kbase + (u64)p * KPN - (u64)kmin), ga);
             __syncthreads();
             dirty = false;
             while (s_ubase[p + 1] <= u) p++;
@@ -1027,13 +1059,13 @@ k_ms_accum_tma(RecStore rs, int P, i64 kbase, i64 kmin, Accums ga) {
                 r[0] = w0.x; r[1] = w0.y; r[2] = w1.x; r[3] = w1.y;
             }
 #pragma unroll
-            for (int j = 0; j < PER; j++) sacc_add_small(a, F::slot(r[j]), F::val(r[j]));
+            for (int j = 0; j < PER; j++) msa_add<REC>(a, F::slot(r[j]), F::val(r[j]));
         } else {
-            for (u32 q = q0; q < rows && q < q0 + PER; q++) sacc_add_small(a, F::slot(st[q]), F::val(st[q]));
+            for (u32 q = q0; q < rows && q < q0 + PER; q++) msa_add<REC>(a, F::slot(st[q]), F::val(st[q]));
         }
     }
     __syncthreads();
-    if (dirty) sacc_flush(a, KPN, (i64)((u64)kbase + (u64)p * KPN - (u64)kmin), ga);
+    if (dirty) msa_flush<REC>(a, KPN, (i64)((u64)kbase + (u64)p * KPN - (u64)kmin), ga);
 }
 
 
